@@ -1,0 +1,154 @@
+/*
+ * vidsitu_b200 -- C ABI of the B200-native SlowFast / I3D event-clip forward.
+ *
+ * This is the drop-in boundary for the hot path of TheShadow29/VidSitu.  The
+ * reference has no FFI on this path: its "interface" is the set of torch.nn
+ * calls made by SFBase.forward_encoder / head / forward_decoder
+ * (vidsitu_code/mdl_sf_base.py:116-216) through the SlowFast submodule.  Each
+ * entry point below replaces one family of those calls and cites it.  The
+ * Python host (vidsitu_b200/sf_base.py) binds them with ctypes; INTEGRATION.md
+ * shows the stub a maintainer would add to the reference.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative vsb_status otherwise;
+ *     vsb_last_error() returns a thread-local human-readable message;
+ *   - all tensor pointers are DEVICE pointers owned by the caller (torch's
+ *     caching allocator in practice); nothing here allocates device memory;
+ *   - work is enqueued on the caller's stream (cudaStream_t passed as void*)
+ *     and never synchronises, so a whole forward can be captured in a CUDA graph;
+ *   - activations are channels-last NTHWC; `*_pitch` is the element distance
+ *     between consecutive pixels (>= channels), so an op can read or write a
+ *     channel slice of a wider buffer (the Fast->Slow concat,
+ *     SlowFast/slowfast/models/video_model_builder.py:124-131);
+ *   - dtype: VSB_BF16 runs the tcgen05/TMEM tensor-core kernels, VSB_F32 runs
+ *     the CUDA-core verification kernels (fp32 storage + FFMA accumulate).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with VSB_ERR_CUDA.
+ */
+#ifndef VIDSITU_B200_H_
+#define VIDSITU_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSB_ABI_VERSION 1
+
+typedef enum vsb_status {
+  VSB_OK = 0,
+  VSB_ERR_INVALID = -1, /* bad argument / unsupported shape            */
+  VSB_ERR_CUDA = -2,    /* CUDA runtime or driver error                */
+  VSB_ERR_ALIGN = -3    /* pointer / pitch violates a TMA requirement  */
+} vsb_status;
+
+typedef enum vsb_dtype { VSB_BF16 = 0, VSB_F32 = 1 } vsb_dtype;
+
+int vsb_abi_version(void);
+const char* vsb_last_error(void);
+/* number of kernels launched by this library since load (bench "gpu_launches") */
+uint64_t vsb_launch_count(void);
+
+/* ------------------------------------------------------------------ pack
+ * Replaces utils/video_utils.py:147-164 (tensor_normalize: x/255, -mean, /std)
+ * + dat_loader.py:483 (permute to CTHW) + utils/video_utils.py:41-74
+ * (pack_pathway_output: temporal index_select for the slow pathway).
+ * frames: uint8 [n, t_in, h, w, 3]; out: [n, t_out, h, w, c_pad] with
+ * out[.., t, .., c] = (frames[.., idx[t], .., c'] / 255 - mean[c]) / std[c],
+ * c' = 2-c if reverse_channels else c; channels 3..c_pad-1 are written as 0.
+ * idx is a HOST array of t_out frame indices (t_out <= 64).                 */
+int vsb_pack_frames(const uint8_t* frames, int n, int t_in, int h, int w, const int* idx, int t_out,
+                    const float* mean3, const float* std3, int reverse_channels, void* out, int c_pad, int dtype,
+                    void* stream);
+
+/* ------------------------------------------------------------------ conv
+ * Replaces nn.Conv3d(bias=False) + eval-mode nn.BatchNorm3d (+ nn.ReLU)
+ * (+ residual add) as used by stem_helper.py:157-178, resnet_helper.py:182-240,
+ * 326-358 and video_model_builder.py:109-131:
+ *   out[m, co] = act( scale[co] * sum_{tap,ci} in[pix(m,tap), ci] * wgt[co,tap,ci]
+ *                     + bias[co] + residual[m, co] )
+ * wgt is packed [cout][kt*kh*kw][cin] (K-major) in `dtype`; scale/bias are fp32
+ * (frozen BN folded: scale = gamma/sqrt(var+eps), bias = beta - mean*scale, or
+ * scale = 1, bias = conv bias for the Nonlocal 1x1x1 convs).                 */
+typedef struct vsb_conv_desc {
+  int dtype;                    /* vsb_dtype                                     */
+  const void* in;               /* [n, t, h, w, in_pitch], first cin channels    */
+  int n, t, h, w, cin, in_pitch;
+  const void* wgt;              /* [cout][kt*kh*kw][cin]                         */
+  int cout;
+  int kt, kh, kw;
+  int st, sh, sw;
+  int pt_lo, ph_lo, pw_lo;      /* leading (lower) zero padding                  */
+  int pt_hi, ph_hi, pw_hi;      /* trailing padding (== lower for every reference conv;
+                                   differs only for the re-viewed stem)          */
+  const float* scale;           /* [cout]                                        */
+  const float* bias;            /* [cout]                                        */
+  const void* residual;         /* nullable, [M, res_pitch]                      */
+  int res_pitch;
+  int relu;
+  void* out;                    /* [M, out_pitch], M = n*to*ho*wo                */
+  int out_pitch;
+  /* tuning, 0 = automatic */
+  int block_n;                  /* 16..256, multiple of 16, divides cout         */
+  int kchunk;                   /* 16 / 32 / 64 channels per TMA box             */
+  int stages;                   /* smem pipeline depth                           */
+} vsb_conv_desc;
+
+typedef struct vsb_conv_plan vsb_conv_plan;
+
+int vsb_conv3d_plan_create(const vsb_conv_desc* desc, vsb_conv_plan** plan);
+int vsb_conv3d_run(const vsb_conv_plan* plan, void* stream);
+void vsb_conv3d_plan_destroy(vsb_conv_plan* plan);
+/* output extent of a plan: M = n*to*ho*wo and (to, ho, wo) */
+int vsb_conv3d_plan_out_shape(const vsb_conv_plan* plan, int* to, int* ho, int* wo);
+/* 2*M*cout*taps*cin of the convolution as launched (padded channels included) */
+double vsb_conv3d_plan_flops(const vsb_conv_plan* plan);
+
+/* --------------------------------------------------------------- max-pool
+ * Replaces nn.MaxPool3d (stem_helper.py:169-171, video_model_builder.py:235-241,
+ * nonlocal_helper.py:98-103).  Implicit -inf padding as in PyTorch.  Channels
+ * [c, c_out) of the output are written as zero (channel padding).           */
+int vsb_maxpool3d(const void* in, int n, int t, int h, int w, int c, int in_pitch, void* out, int out_pitch,
+                  int c_out, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw, int dtype,
+                  void* stream);
+
+/* ------------------------------------------------- global average pool
+ * Replaces nn.AdaptiveAvgPool3d((1,1,1)) + torch.cat of ResNetBasicHead_Trimmed
+ * (vidsitu_code/mdl_sf_base.py:95-113): feats[i, feat_off + ch] = mean over the
+ * thw positions of clip i.  feats is fp32 [n, feat_pitch].                   */
+int vsb_global_avgpool(const void* in, int n, int thw, int c, int in_pitch, float* feats, int feat_pitch,
+                       int feat_off, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ linear
+ * Replaces nn.Linear (+ nn.ReLU) of proj_head (vidsitu_code/mdl_sf_base.py:161-167):
+ * y[i, o] = act(b[o] + sum_k x[i,k] * w[o,k]); all fp32, w row-major [dout, din]. */
+int vsb_linear(const float* x, int n, int din, const float* w, const float* b, float* y, int dout, int relu,
+               void* stream);
+
+/* --------------------------------------------------------- non-local attention
+ * Replaces the two einsums + softmax of Nonlocal.forward
+ * (SlowFast/slowfast/models/nonlocal_helper.py:123-141).  Per clip i:
+ *   A = theta_i [tq, c] . phi_i [tk, c]^T ; softmax: A = softmax(A * c^-0.5) over tk;
+ *   dot_product: A = A / tk ;  out_i [tq, c] = A . g_i [tk, c].
+ * theta/phi/g/out are channels-last with their own pitches.                  */
+int vsb_nonlocal_attention(const void* theta, int theta_pitch, const void* phi, int phi_pitch, const void* g,
+                           int g_pitch, void* out, int out_pitch, int n, int tq, int tk, int c, int softmax,
+                           int dtype, void* stream);
+
+/* ------------------------------------------------------------- layout helper
+ * NTHWC (pitch) -> NCTHW fp32 contiguous, for callers that want the reference's
+ * forward_features() tensors (mdl_sf_base.py:21-34) materialised.           */
+int vsb_nthwc_to_ncthw_f32(const void* in, int n, int thw, int c, int in_pitch, float* out, int dtype,
+                           void* stream);
+
+/* NCTHW fp32 (the reference's already-normalised clip tensors,
+ * vidsitu_code/mdl_sf_base.py:169-180) -> NTHWC with the c <= 3 planes packed into
+ * c_pad == 4 channels (channel 3 = 0), bf16 or fp32.                          */
+int vsb_ncthw_f32_to_nthwc(const float* in, int n, int c, long long thw, void* out, int c_pad, int dtype,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDSITU_B200_H_ */

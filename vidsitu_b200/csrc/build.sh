@@ -1,0 +1,19 @@
+#!/usr/bin/env bash
+# Builds vidsitu_b200/libvidsitu_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+out="${here}/../libvidsitu_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+mkdir -p "${here}/build"
+objs=()
+for src in api conv_igemm_sm100 conv_simt ops_mem nonlocal; do
+  obj="${here}/build/${src}.o"
+  if [[ ! -f "${obj}" || "${here}/${src}.cu" -nt "${obj}" || "${here}/ptx.cuh" -nt "${obj}" || "${here}/common.h" -nt "${obj}" || "${here}/../../include/vidsitu_b200.h" -nt "${obj}" ]]; then
+    "${NVCC}" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+      -Xcompiler -fPIC -Xptxas -v -c "${here}/${src}.cu" -o "${obj}" 2> "${here}/build/${src}.ptxas.log" \
+      || { cat "${here}/build/${src}.ptxas.log" >&2; exit 1; }
+  fi
+  objs+=("${obj}")
+done
+"${NVCC}" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o "${out}" "${objs[@]}"
+echo "built ${out}"

@@ -1,0 +1,448 @@
+// HBM-bound ops of the event-clip forward: frame pack, 3-D max-pool, global
+// average pool, the fp32 projection head and a layout helper.  All are
+// channels-last with 128-bit accesses; none of them is reshaped into a GEMM.
+#include <cuda_bf16.h>
+#include <float.h>
+
+#include "common.h"
+
+namespace vsb {
+
+// ---------------------------------------------------------------------- pack
+// uint8 [n, t_in, h, w, 3]  ->  [n, t_out, h, w, 4] (bf16 or fp32), channel 3 = 0.
+// Reference: utils/video_utils.py:147-164 (x/255, -mean, /std, in that order, fp32)
+// then utils/video_utils.py:41-74 (slow-pathway temporal index_select).  The three
+// fp32 operations are evaluated once per (channel, byte value) into a 768-entry
+// shared-memory table with IEEE division, so every output equals the reference's
+// fp32 value (then rounded once to bf16 in bf16 mode).
+struct PackIdx {
+  int v[64];
+};
+
+template <typename OutT>
+__device__ __forceinline__ void store_px4(OutT* dst, float r, float g, float b);
+template <>
+__device__ __forceinline__ void store_px4<float>(float* dst, float r, float g, float b) {
+  *reinterpret_cast<float4*>(dst) = make_float4(r, g, b, 0.f);
+}
+template <>
+__device__ __forceinline__ void store_px4<__nv_bfloat16>(__nv_bfloat16* dst, float r, float g, float b) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(r, g);
+  __nv_bfloat162 hi = __floats2bfloat162_rn(b, 0.f);
+  uint2 v;
+  v.x = *reinterpret_cast<uint32_t*>(&lo);
+  v.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = v;
+}
+
+// One thread = 16 consecutive pixels of one frame: 3 x 128-bit loads (48 B of
+// uint8), 16 x 4-channel stores.  frame_px (= h*w) must be a multiple of 16.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+pack_frames_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, int n, int t_in, int t_out,
+                   long long frame_px, PackIdx idx, float m0, float m1, float m2, float s0, float s1, float s2,
+                   int reverse) {
+  __shared__ float lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    const int c = i >> 8, x = i & 255;
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+    const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    float v = __fdiv_rn((float)x, 255.0f);
+    v = __fsub_rn(v, mean);
+    v = __fdiv_rn(v, sd);
+    lut[c][x] = v;
+  }
+  __syncthreads();
+  const long long units_per_frame = frame_px >> 4;
+  const long long total = (long long)n * t_out * units_per_frame;
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total;
+       u += (long long)gridDim.x * blockDim.x) {
+    const long long unit = u % units_per_frame;
+    const long long f = u / units_per_frame;
+    const int to = (int)(f % t_out);
+    const long long clip = f / t_out;
+    const uint8_t* src = frames + ((clip * t_in + idx.v[to]) * frame_px + unit * 16) * 3;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(src) + 2);
+    const uint32_t wds[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    OutT* dst = out + ((clip * t_out + to) * frame_px + unit * 16) * 4;
+#pragma unroll
+    for (int px = 0; px < 16; ++px) {
+      uint32_t ch[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int byte = px * 3 + k;
+        ch[k] = (wds[byte >> 2] >> ((byte & 3) * 8)) & 0xFF;
+      }
+      // REVERSE_INPUT_CHANNEL flips AFTER the per-channel normalisation (video_utils.py:54-55)
+      const float r = reverse ? lut[2][ch[2]] : lut[0][ch[0]];
+      const float g = lut[1][ch[1]];
+      const float bb = reverse ? lut[0][ch[0]] : lut[2][ch[2]];
+      store_px4<OutT>(dst + px * 4, r, g, bb);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ max-pool
+template <typename T>
+struct Vec16;  // 16-byte vector of T
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[8]) {
+    const float4 x = *reinterpret_cast<const float4*>(p);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  }
+  __device__ static void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 x = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+struct PoolParams {
+  int n, t, h, w, c, in_pitch;
+  int to, ho, wo, out_pitch, c_out;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+};
+
+// One thread = one 16-byte channel vector of one output pixel.
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ in, T* __restrict__ out, PoolParams p) {
+  constexpr int V = Vec16<T>::N;
+  const int cvecs = p.c_out / V;
+  const long long total = (long long)p.n * p.to * p.ho * p.wo * cvecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvecs);
+    long long r = i / cvecs;
+    const int wo = (int)(r % p.wo); r /= p.wo;
+    const int ho = (int)(r % p.ho); r /= p.ho;
+    const int to = (int)(r % p.to); r /= p.to;
+    const int nn = (int)r;
+    float best[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) best[k] = 0.f;
+    const int c0 = cv * V;
+    if (c0 < p.c) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) best[k] = -FLT_MAX;
+      for (int a = 0; a < p.kt; ++a) {
+        const int it = to * p.st - p.pt + a;
+        if (it < 0 || it >= p.t) continue;
+        for (int b = 0; b < p.kh; ++b) {
+          const int ih = ho * p.sh - p.ph + b;
+          if (ih < 0 || ih >= p.h) continue;
+          for (int d = 0; d < p.kw; ++d) {
+            const int iw = wo * p.sw - p.pw + d;
+            if (iw < 0 || iw >= p.w) continue;
+            float v[8];
+            Vec16<T>::load(in + ((((long long)nn * p.t + it) * p.h + ih) * p.w + iw) * p.in_pitch + c0, v);
+#pragma unroll
+            for (int k = 0; k < V; ++k) best[k] = fmaxf(best[k], v[k]);
+          }
+        }
+      }
+      // channels of this vector beyond c are padding -> 0
+#pragma unroll
+      for (int k = 0; k < V; ++k)
+        if (c0 + k >= p.c) best[k] = 0.f;
+    }
+    Vec16<T>::store(out + ((((long long)nn * p.to + to) * p.ho + ho) * p.wo + wo) * p.out_pitch + c0, best);
+  }
+}
+
+// ------------------------------------------------------- global average pool
+// grid (n, ceil(c / (32*V))): each warp strides over the thw positions, each lane
+// owns one 16-byte channel vector; partial sums meet in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256)
+global_avgpool_kernel(const T* __restrict__ in, float* __restrict__ feats, int thw, int c, int in_pitch,
+                      int feat_pitch, int feat_off) {
+  constexpr int V = Vec16<T>::N;
+  __shared__ float part[8][32 * 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int clip = blockIdx.x;
+  const int c0 = (blockIdx.y * 32 + lane) * V;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (c0 < c) {
+    const T* base = in + (long long)clip * thw * in_pitch + c0;
+    for (int pos = warp; pos < thw; pos += 8) {
+      float v[8];
+      Vec16<T>::load(base + (long long)pos * in_pitch, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) part[warp][lane * V + k] = acc[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * V; i += blockDim.x) {
+    const int ch = blockIdx.y * 32 * V + i;
+    if (ch < c) {
+      float s = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) s += part[wq][i];
+      feats[(long long)clip * feat_pitch + feat_off + ch] = s / (float)thw;
+    }
+  }
+}
+
+// -------------------------------------------------------------------- linear
+// One warp = one output neuron for a tile of up to 8 rows: lanes stride over K
+// with 128-bit loads, then a shuffle tree reduces the 32 partial dot products.
+constexpr int LIN_ROWS = 8;
+__global__ void __launch_bounds__(256)
+linear_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+              float* __restrict__ y, int n, int din, int dout, int relu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + warp;
+  const int r0 = blockIdx.y * LIN_ROWS;
+  if (o >= dout) return;
+  float acc[LIN_ROWS];
+#pragma unroll
+  for (int r = 0; r < LIN_ROWS; ++r) acc[r] = 0.f;
+  const float* wr = w + (long long)o * din;
+  const int nrows = min(LIN_ROWS, n - r0);
+  if ((din & 3) == 0) {
+    for (int k = lane * 4; k < din; k += 128) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+      for (int r = 0; r < LIN_ROWS; ++r) {
+        if (r < nrows) {
+          const float4 xv = *reinterpret_cast<const float4*>(x + (long long)(r0 + r) * din + k);
+          acc[r] = fmaf(wv.x, xv.x, acc[r]);
+          acc[r] = fmaf(wv.y, xv.y, acc[r]);
+          acc[r] = fmaf(wv.z, xv.z, acc[r]);
+          acc[r] = fmaf(wv.w, xv.w, acc[r]);
+        }
+      }
+    }
+  } else {
+    for (int k = lane; k < din; k += 32) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int r = 0; r < LIN_ROWS; ++r)
+        if (r < nrows) acc[r] = fmaf(wv, x[(long long)(r0 + r) * din + k], acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < LIN_ROWS; ++r) {
+    float v = acc[r];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0 && r < nrows) {
+      v += b ? b[o] : 0.f;
+      if (relu) v = fmaxf(v, 0.f);
+      y[(long long)(r0 + r) * dout + o] = v;
+    }
+  }
+}
+
+// ----------------------------------------------------- NTHWC -> NCTHW (fp32)
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+nthwc_to_ncthw_kernel(const T* __restrict__ in, float* __restrict__ out, int thw, int c, int in_pitch) {
+  __shared__ float tile[32][33];
+  const int clip = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int pos = p0 + j, ch = c0 + tx;
+    tile[j][tx] = (pos < thw && ch < c) ? to_f32<T>(in[((long long)clip * thw + pos) * in_pitch + ch]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int ch = c0 + j, pos = p0 + tx;
+    if (pos < thw && ch < c) out[((long long)clip * c + ch) * thw + pos] = tile[tx][j];
+  }
+}
+
+// ------------------------------------------------ NCTHW fp32 -> NTHWC (c_pad)
+// Entry for callers that hold the reference's already-normalised fp32 NCTHW clip
+// tensors (vidsitu_code/mdl_sf_base.py:169-180): one thread per pixel gathers the
+// c (<= 4) planes and writes one zero-padded 4-channel pixel.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+ncthw_to_nthwc4_kernel(const float* __restrict__ in, OutT* __restrict__ out, long long n, int c, long long thw) {
+  const long long total = n * thw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long clip = i / thw, pos = i - clip * thw;
+    const float* src = in + clip * c * thw + pos;
+    const float r = src[0];
+    const float g = c > 1 ? src[thw] : 0.f;
+    const float b = c > 2 ? src[2 * thw] : 0.f;
+    store_px4<OutT>(out + i * 4, r, g, b);
+  }
+}
+
+static inline unsigned grid_for(long long total, int block) {
+  long long g = ceil_div_ll(total, block);
+  const long long cap = 148ll * 32;  // grid-stride loops: a few waves of the 148 SMs
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace vsb
+
+using namespace vsb;
+
+extern "C" int vsb_pack_frames(const uint8_t* frames, int n, int t_in, int h, int w, const int* idx, int t_out,
+                               const float* mean3, const float* std3, int reverse_channels, void* out, int c_pad,
+                               int dtype, void* stream) {
+  VSB_CHECK_ARG(frames && idx && mean3 && std3 && out, "null argument");
+  VSB_CHECK_ARG(n > 0 && t_in > 0 && h > 0 && w > 0 && t_out > 0 && t_out <= 64, "bad extent (t_out <= 64)");
+  VSB_CHECK_ARG(c_pad == 4, "pack writes 4 channels per pixel (c_pad == 4)");
+  VSB_CHECK_ARG(dtype == VSB_BF16 || dtype == VSB_F32, "bad dtype");
+  const long long frame_px = (long long)h * w;
+  VSB_CHECK_ARG(frame_px % 16 == 0, "h*w must be a multiple of 16 for the 128-bit loads");
+  VSB_CHECK_ARG((reinterpret_cast<uintptr_t>(frames) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "frames/out must be 16-byte aligned");
+  PackIdx pi;
+  for (int i = 0; i < t_out; ++i) {
+    VSB_CHECK_ARG(idx[i] >= 0 && idx[i] < t_in, "frame index %d out of range", idx[i]);
+    pi.v[i] = idx[i];
+  }
+  for (int i = t_out; i < 64; ++i) pi.v[i] = 0;
+  const long long total = (long long)n * t_out * (frame_px / 16);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = grid_for(total, 256);
+  if (dtype == VSB_BF16) {
+    pack_frames_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(frames, static_cast<__nv_bfloat16*>(out), n, t_in, t_out,
+                                                          frame_px, pi, mean3[0], mean3[1], mean3[2], std3[0],
+                                                          std3[1], std3[2], reverse_channels);
+  } else {
+    pack_frames_kernel<float><<<grid, 256, 0, s>>>(frames, static_cast<float*>(out), n, t_in, t_out, frame_px, pi,
+                                                   mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2],
+                                                   reverse_channels);
+  }
+  VSB_CHECK_LAUNCH("pack_frames_kernel");
+  return VSB_OK;
+}
+
+extern "C" int vsb_maxpool3d(const void* in, int n, int t, int h, int w, int c, int in_pitch, void* out,
+                             int out_pitch, int c_out, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph,
+                             int pw, int dtype, void* stream) {
+  VSB_CHECK_ARG(in && out, "null argument");
+  VSB_CHECK_ARG(dtype == VSB_BF16 || dtype == VSB_F32, "bad dtype");
+  const int V = dtype == VSB_BF16 ? 8 : 4;
+  VSB_CHECK_ARG(n > 0 && t > 0 && h > 0 && w > 0 && c > 0 && c_out >= c, "bad extent");
+  VSB_CHECK_ARG(c_out % V == 0 && in_pitch % V == 0 && out_pitch % V == 0 && in_pitch >= c && out_pitch >= c_out,
+                "channel counts / pitches must be multiples of the 16-byte vector (%d)", V);
+  VSB_CHECK_ARG(((c + V - 1) / V) * V <= in_pitch, "input pitch too small for vector loads");
+  VSB_CHECK_ARG(2 * pt <= kt && 2 * ph <= kh && 2 * pw <= kw, "padding larger than half the window");
+  PoolParams p;
+  p.n = n; p.t = t; p.h = h; p.w = w; p.c = c; p.in_pitch = in_pitch;
+  p.to = (t + 2 * pt - kt) / st + 1;
+  p.ho = (h + 2 * ph - kh) / sh + 1;
+  p.wo = (w + 2 * pw - kw) / sw + 1;
+  VSB_CHECK_ARG(p.to > 0 && p.ho > 0 && p.wo > 0, "empty output");
+  p.out_pitch = out_pitch; p.c_out = c_out;
+  p.kt = kt; p.kh = kh; p.kw = kw; p.st = st; p.sh = sh; p.sw = sw; p.pt = pt; p.ph = ph; p.pw = pw;
+  const long long total = (long long)n * p.to * p.ho * p.wo * (c_out / V);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = grid_for(total, 256);
+  if (dtype == VSB_BF16)
+    maxpool3d_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in),
+                                                        static_cast<__nv_bfloat16*>(out), p);
+  else
+    maxpool3d_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(in), static_cast<float*>(out), p);
+  VSB_CHECK_LAUNCH("maxpool3d_kernel");
+  return VSB_OK;
+}
+
+extern "C" int vsb_global_avgpool(const void* in, int n, int thw, int c, int in_pitch, float* feats, int feat_pitch,
+                                  int feat_off, int dtype, void* stream) {
+  VSB_CHECK_ARG(in && feats, "null argument");
+  VSB_CHECK_ARG(dtype == VSB_BF16 || dtype == VSB_F32, "bad dtype");
+  const int V = dtype == VSB_BF16 ? 8 : 4;
+  VSB_CHECK_ARG(n > 0 && thw > 0 && c > 0 && c % V == 0 && in_pitch % V == 0 && in_pitch >= c, "bad extent");
+  VSB_CHECK_ARG(feat_off >= 0 && feat_off + c <= feat_pitch, "feature slice outside the row");
+  dim3 grid(n, ceil_div(c, 32 * V));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == VSB_BF16)
+    global_avgpool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in), feats, thw, c,
+                                                             in_pitch, feat_pitch, feat_off);
+  else
+    global_avgpool_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(in), feats, thw, c, in_pitch,
+                                                      feat_pitch, feat_off);
+  VSB_CHECK_LAUNCH("global_avgpool_kernel");
+  return VSB_OK;
+}
+
+extern "C" int vsb_linear(const float* x, int n, int din, const float* w, const float* b, float* y, int dout,
+                          int relu, void* stream) {
+  VSB_CHECK_ARG(x && w && y, "null argument");
+  VSB_CHECK_ARG(n > 0 && din > 0 && dout > 0, "bad extent");
+  VSB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0,
+                "x and w must be 16-byte aligned");
+  dim3 grid(ceil_div(dout, 8), ceil_div(n, LIN_ROWS));
+  linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, b, y, n, din, dout, relu);
+  VSB_CHECK_LAUNCH("linear_kernel");
+  return VSB_OK;
+}
+
+extern "C" int vsb_nthwc_to_ncthw_f32(const void* in, int n, int thw, int c, int in_pitch, float* out, int dtype,
+                                      void* stream) {
+  VSB_CHECK_ARG(in && out, "null argument");
+  VSB_CHECK_ARG(dtype == VSB_BF16 || dtype == VSB_F32, "bad dtype");
+  VSB_CHECK_ARG(n > 0 && thw > 0 && c > 0 && in_pitch >= c, "bad extent");
+  VSB_CHECK_ARG(n <= 65535, "batch above the grid.z limit");
+  dim3 grid(ceil_div(thw, 32), ceil_div(c, 32), n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == VSB_BF16)
+    nthwc_to_ncthw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in), out, thw, c,
+                                                             in_pitch);
+  else
+    nthwc_to_ncthw_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(in), out, thw, c, in_pitch);
+  VSB_CHECK_LAUNCH("nthwc_to_ncthw_kernel");
+  return VSB_OK;
+}
+
+extern "C" int vsb_ncthw_f32_to_nthwc(const float* in, int n, int c, long long thw, void* out, int c_pad, int dtype,
+                                      void* stream) {
+  VSB_CHECK_ARG(in && out, "null argument");
+  VSB_CHECK_ARG(dtype == VSB_BF16 || dtype == VSB_F32, "bad dtype");
+  VSB_CHECK_ARG(n > 0 && thw > 0 && c >= 1 && c <= 3 && c_pad == 4, "supports c <= 3 packed into c_pad == 4");
+  VSB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = grid_for((long long)n * thw, 256);
+  if (dtype == VSB_BF16)
+    ncthw_to_nthwc4_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(in, static_cast<__nv_bfloat16*>(out), n, c, thw);
+  else
+    ncthw_to_nthwc4_kernel<float><<<grid, 256, 0, s>>>(in, static_cast<float*>(out), n, c, thw);
+  VSB_CHECK_LAUNCH("ncthw_to_nthwc4_kernel");
+  return VSB_OK;
+}

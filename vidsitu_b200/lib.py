@@ -1,0 +1,101 @@
+"""ctypes binding of libvidsitu_b200.so (the C ABI declared in include/vidsitu_b200.h).
+
+The library is the product: if it is missing, or a call fails, this module raises --
+there is no PyTorch / CPU fallback behind any of these wrappers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+VSB_BF16 = 0
+VSB_F32 = 1
+
+_LIB_NAME = "libvidsitu_b200.so"
+_lib = None
+
+
+class VsbError(RuntimeError):
+    """A libvidsitu_b200 entry point returned a non-zero status."""
+
+
+class ConvDesc(C.Structure):
+    """Mirror of `vsb_conv_desc` (include/vidsitu_b200.h)."""
+
+    _fields_ = [
+        ("dtype", C.c_int),
+        ("inp", C.c_void_p),
+        ("n", C.c_int), ("t", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int), ("in_pitch", C.c_int),
+        ("wgt", C.c_void_p),
+        ("cout", C.c_int),
+        ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int),
+        ("st", C.c_int), ("sh", C.c_int), ("sw", C.c_int),
+        ("pt_lo", C.c_int), ("ph_lo", C.c_int), ("pw_lo", C.c_int),
+        ("pt_hi", C.c_int), ("ph_hi", C.c_int), ("pw_hi", C.c_int),
+        ("scale", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("res_pitch", C.c_int),
+        ("relu", C.c_int),
+        ("out", C.c_void_p),
+        ("out_pitch", C.c_int),
+        ("block_n", C.c_int), ("kchunk", C.c_int), ("stages", C.c_int),
+    ]
+
+
+def lib_path() -> Path:
+    env = os.environ.get("VIDSITU_B200_LIB")
+    return Path(env) if env else Path(__file__).resolve().parent / _LIB_NAME
+
+
+def load() -> C.CDLL:
+    """Load the shared library once; raise (never fall back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not path.exists():
+        raise VsbError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(vidsitu_b200/csrc/build.sh). There is no fallback implementation."
+        )
+    lib = C.CDLL(str(path))
+    i, vp, f32p, ll = C.c_int, C.c_void_p, C.c_void_p, C.c_longlong
+    lib.vsb_abi_version.restype = i
+    lib.vsb_last_error.restype = C.c_char_p
+    lib.vsb_launch_count.restype = C.c_uint64
+    lib.vsb_pack_frames.argtypes = [vp, i, i, i, i, C.POINTER(C.c_int), i, C.POINTER(C.c_float),
+                                    C.POINTER(C.c_float), i, vp, i, i, vp]
+    lib.vsb_conv3d_plan_create.argtypes = [C.POINTER(ConvDesc), C.POINTER(vp)]
+    lib.vsb_conv3d_run.argtypes = [vp, vp]
+    lib.vsb_conv3d_plan_destroy.argtypes = [vp]
+    lib.vsb_conv3d_plan_destroy.restype = None
+    lib.vsb_conv3d_plan_out_shape.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
+    lib.vsb_conv3d_plan_flops.argtypes = [vp]
+    lib.vsb_conv3d_plan_flops.restype = C.c_double
+    lib.vsb_maxpool3d.argtypes = [vp, i, i, i, i, i, i, vp, i, i, i, i, i, i, i, i, i, i, i, i, vp]
+    lib.vsb_global_avgpool.argtypes = [vp, i, i, i, i, f32p, i, i, i, vp]
+    lib.vsb_linear.argtypes = [f32p, i, i, f32p, f32p, f32p, i, i, vp]
+    lib.vsb_nonlocal_attention.argtypes = [vp, i, vp, i, vp, i, vp, i, i, i, i, i, i, i, vp]
+    lib.vsb_nthwc_to_ncthw_f32.argtypes = [vp, i, i, i, i, f32p, i, vp]
+    lib.vsb_ncthw_f32_to_nthwc.argtypes = [f32p, i, i, ll, vp, i, i, vp]
+    lib.vsb_debug_im2col_probe.argtypes = [vp] + [i] * 25 + [vp, vp]
+    for name in ("vsb_pack_frames", "vsb_conv3d_plan_create", "vsb_conv3d_run", "vsb_conv3d_plan_out_shape",
+                 "vsb_maxpool3d", "vsb_global_avgpool", "vsb_linear", "vsb_nonlocal_attention",
+                 "vsb_nthwc_to_ncthw_f32", "vsb_ncthw_f32_to_nthwc", "vsb_debug_im2col_probe"):
+        getattr(lib, name).restype = i
+    if lib.vsb_abi_version() != 1:
+        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().vsb_last_error().decode("utf-8", "replace")
+        raise VsbError(f"{what} failed (status {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().vsb_launch_count())

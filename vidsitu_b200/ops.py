@@ -1,0 +1,190 @@
+"""Operator-level host wrappers: torch tensors in (device memory + current stream are
+the only things torch provides), C-ABI calls out.  Each function mirrors one family
+of reference calls; see include/vidsitu_b200.h for the file:line citations.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import lib as _l
+from .lib import VSB_BF16, VSB_F32, ConvDesc, VsbError, check
+
+TORCH_DTYPE = {VSB_BF16: torch.bfloat16, VSB_F32: torch.float32}
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise VsbError("vidsitu_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+
+
+@dataclass
+class Act:
+    """A channels-last activation: `buf` holds [n, t, h, w, pitch] elements, the
+    logical tensor is its channel slice [c_off, c_off + c)."""
+
+    buf: torch.Tensor
+    n: int
+    t: int
+    h: int
+    w: int
+    c: int            # stored channels of this view (padded to the dtype's channel quantum)
+    pitch: int
+    c_off: int = 0
+    c_real: int = -1  # logical (reference) channel count
+
+    def __post_init__(self):
+        if self.c_real < 0:
+            self.c_real = self.c
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + self.c_off * self.buf.element_size()
+
+    @property
+    def pixels(self) -> int:
+        return self.n * self.t * self.h * self.w
+
+    def nthwc(self) -> torch.Tensor:
+        """[n, t, h, w, c_real] torch view of the logical tensor (no copy)."""
+        v = self.buf.view(-1)[: self.pixels * self.pitch].view(self.n, self.t, self.h, self.w, self.pitch)
+        return v[..., self.c_off: self.c_off + self.c_real]
+
+
+class ConvPlan:
+    """One planned conv launch (TMA descriptors are encoded once, at plan time)."""
+
+    def __init__(self, dtype: int, x: Act, wgt: torch.Tensor, cout: int, kernel: Sequence[int],
+                 stride: Sequence[int], pad_lo: Sequence[int], pad_hi: Optional[Sequence[int]],
+                 scale: torch.Tensor, bias: torch.Tensor, out: Act, residual: Optional[Act] = None,
+                 relu: bool = False, block_n: int = 0, kchunk: int = 0, stages: int = 0):
+        _require_cuda(x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None)
+        pad_hi = pad_lo if pad_hi is None else pad_hi
+        d = ConvDesc()
+        d.dtype = dtype
+        d.inp = x.ptr
+        d.n, d.t, d.h, d.w, d.cin, d.in_pitch = x.n, x.t, x.h, x.w, x.c, x.pitch
+        d.wgt = wgt.data_ptr()
+        d.cout = cout
+        d.kt, d.kh, d.kw = kernel
+        d.st, d.sh, d.sw = stride
+        d.pt_lo, d.ph_lo, d.pw_lo = pad_lo
+        d.pt_hi, d.ph_hi, d.pw_hi = pad_hi
+        d.scale = scale.data_ptr()
+        d.bias = bias.data_ptr()
+        d.residual = residual.ptr if residual is not None else None
+        d.res_pitch = residual.pitch if residual is not None else 0
+        d.relu = int(relu)
+        d.out = out.ptr
+        d.out_pitch = out.pitch
+        d.block_n, d.kchunk, d.stages = block_n, kchunk, stages
+        expect = torch.bfloat16 if dtype == VSB_BF16 else torch.float32
+        if x.buf.dtype != expect or wgt.dtype != expect or out.buf.dtype != expect:
+            raise VsbError(f"conv tensors must be {expect}")
+        if scale.dtype != torch.float32 or bias.dtype != torch.float32:
+            raise VsbError("scale/bias must be float32")
+        taps = d.kt * d.kh * d.kw
+        if wgt.numel() != cout * taps * x.c:
+            raise VsbError(f"packed weight has {wgt.numel()} elements, expected {cout}x{taps}x{x.c}")
+        self._keep = (x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None)
+        self._h = C.c_void_p()
+        self._lib = _l.load()
+        check(self._lib.vsb_conv3d_plan_create(C.byref(d), C.byref(self._h)), "vsb_conv3d_plan_create")
+        to, ho, wo = C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.vsb_conv3d_plan_out_shape(self._h, C.byref(to), C.byref(ho), C.byref(wo)), "out_shape")
+        self.out_shape = (to.value, ho.value, wo.value)
+        self.flops = float(self._lib.vsb_conv3d_plan_flops(self._h))
+        if x.n * to.value * ho.value * wo.value != out.pixels:
+            raise VsbError(f"conv output extent {x.n}x{self.out_shape} does not match the output buffer "
+                           f"({out.n},{out.t},{out.h},{out.w})")
+
+    def run(self) -> None:
+        check(self._lib.vsb_conv3d_run(self._h, _stream_ptr()), "vsb_conv3d_run")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.vsb_conv3d_plan_destroy(h)
+            h.value = None
+
+
+def pack_frames(frames: torch.Tensor, idx: Sequence[int], mean: Sequence[float], std: Sequence[float],
+                out: Act, dtype: int, reverse_channels: bool = False) -> None:
+    """frames uint8 [n, t_in, h, w, 3] -> out [n, len(idx), h, w, 4] (normalised, temporally subsampled)."""
+    _require_cuda(frames, out.buf)
+    if frames.dtype != torch.uint8 or frames.dim() != 5 or frames.shape[-1] != 3 or not frames.is_contiguous():
+        raise VsbError("frames must be a contiguous uint8 [n, t, h, w, 3] tensor")
+    n, t_in, h, w, _ = frames.shape
+    if (out.n, out.t, out.h, out.w, out.pitch, out.c_off) != (n, len(idx), h, w, 4, 0):
+        raise VsbError("pack output must be a dense [n, len(idx), h, w, 4] activation")
+    idx_arr = (C.c_int * len(idx))(*[int(i) for i in idx])
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    check(_l.load().vsb_pack_frames(frames.data_ptr(), n, t_in, h, w, idx_arr, len(idx), m, s,
+                                    int(reverse_channels), out.ptr, 4, dtype, _stream_ptr()), "vsb_pack_frames")
+
+
+def ncthw_to_act(x: torch.Tensor, out: Act, dtype: int) -> None:
+    """fp32 NCTHW clip tensor (reference layout) -> 4-channel NTHWC activation."""
+    _require_cuda(x, out.buf)
+    if x.dtype != torch.float32 or x.dim() != 5 or not x.is_contiguous():
+        raise VsbError("expected a contiguous float32 [n, c, t, h, w] tensor")
+    n, c, t, h, w = x.shape
+    if (out.n, out.t, out.h, out.w, out.pitch) != (n, t, h, w, 4):
+        raise VsbError("output activation must be dense [n, t, h, w, 4]")
+    check(_l.load().vsb_ncthw_f32_to_nthwc(x.data_ptr(), n, c, t * h * w, out.ptr, 4, dtype, _stream_ptr()),
+          "vsb_ncthw_f32_to_nthwc")
+
+
+def maxpool3d(x: Act, out: Act, kernel, stride, pad, dtype: int) -> None:
+    _require_cuda(x.buf, out.buf)
+    check(_l.load().vsb_maxpool3d(x.ptr, x.n, x.t, x.h, x.w, x.c_real, x.pitch, out.ptr, out.pitch, out.c,
+                                  kernel[0], kernel[1], kernel[2], stride[0], stride[1], stride[2],
+                                  pad[0], pad[1], pad[2], dtype, _stream_ptr()), "vsb_maxpool3d")
+
+
+def global_avgpool(x: Act, feats: torch.Tensor, feat_off: int, dtype: int) -> None:
+    _require_cuda(x.buf, feats)
+    if feats.dtype != torch.float32 or feats.dim() != 2 or feats.shape[0] != x.n:
+        raise VsbError("feats must be float32 [n, D]")
+    check(_l.load().vsb_global_avgpool(x.ptr, x.n, x.t * x.h * x.w, x.c_real, x.pitch, feats.data_ptr(),
+                                       feats.stride(0), feat_off, dtype, _stream_ptr()), "vsb_global_avgpool")
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], y: torch.Tensor, relu: bool) -> None:
+    _require_cuda(x, w, y)
+    for t in (x, w, y):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise VsbError("linear operands must be contiguous float32")
+    n, din = x.shape
+    dout = w.shape[0]
+    if w.shape[1] != din or tuple(y.shape) != (n, dout):
+        raise VsbError("linear shape mismatch")
+    check(_l.load().vsb_linear(x.data_ptr(), n, din, w.data_ptr(), b.data_ptr() if b is not None else None,
+                               y.data_ptr(), dout, int(relu), _stream_ptr()), "vsb_linear")
+
+
+def nonlocal_attention(theta: Act, phi: Act, g: Act, out: Act, softmax: bool, dtype: int) -> None:
+    _require_cuda(theta.buf, phi.buf, g.buf, out.buf)
+    tq = theta.t * theta.h * theta.w
+    tk = phi.t * phi.h * phi.w
+    check(_l.load().vsb_nonlocal_attention(theta.ptr, theta.pitch, phi.ptr, phi.pitch, g.ptr, g.pitch, out.ptr,
+                                           out.pitch, theta.n, tq, tk, theta.c_real, int(softmax), dtype,
+                                           _stream_ptr()), "vsb_nonlocal_attention")
+
+
+def act_to_ncthw(x: Act, dtype: int) -> torch.Tensor:
+    """Materialise an activation as the reference's float32 [n, c, t, h, w] tensor."""
+    _require_cuda(x.buf)
+    out = torch.empty((x.n, x.c_real, x.t, x.h, x.w), dtype=torch.float32, device=x.buf.device)
+    check(_l.load().vsb_nthwc_to_ncthw_f32(x.ptr, x.n, x.t * x.h * x.w, x.c_real, x.pitch, out.data_ptr(), dtype,
+                                           _stream_ptr()), "vsb_nthwc_to_ncthw_f32")
+    return out
