@@ -226,12 +226,13 @@ def run_mem_checks():
             out = torch.empty((n, len(idx), h, w, 4), dtype=tdt, device=dev)
             ops.pack_frames(frames, idx, mean, std, Act(out, n, len(idx), h, w, 4, 4), dtype, rev)
             torch.cuda.synchronize()
-            x = frames[:, idx].float() / 255.0
-            x = x - torch.tensor(mean, device=dev)
-            x = x / torch.tensor(std, device=dev)
+            # reference arithmetic on the CPU, like the reference's dataloader (true IEEE division)
+            xc = frames[:, idx].cpu().float() / 255.0
+            xc = xc - torch.tensor(mean)
+            xc = xc / torch.tensor(std)
             if rev:
-                x = x[..., [2, 1, 0]]
-            ref = torch.cat([x, torch.zeros_like(x[..., :1])], dim=-1)
+                xc = xc[..., [2, 1, 0]]
+            ref = torch.cat([xc, torch.zeros_like(xc[..., :1])], dim=-1).to(dev)
             if dtype == L.VSB_F32:
                 ok = bool(torch.equal(out, ref))
                 res[f"pack_f32_rev{int(rev)}"] = {"ok": ok, "max_abs_err": float((out - ref).abs().max())}
