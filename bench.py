@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Headline benchmark: event clips/sec of the SlowFast-R50 8x8 feature-extraction forward
+(BASELINE.json configs[1]: batch 64 synthetic event clips, bf16, per B200).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (tcgen05 kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference path on the host CPU cores
+
+A step = one pass of the hot path over one batch of 64 clips per GPU: frame pack (uint8 ->
+bf16 NTHWC, both pathways) + 110 conv launches + pools + GAP + projection head (+ for N>1 the
+all-gather of the [64, 2304] features).  `value` times it with the uint8 frames already in HBM;
+`e2e` times the same through vidsitu_b200.HostPipeline with the frames in pinned host memory
+(H2D of every batch and D2H of its features inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+MODEL = "slow_fast_nl_r50_8x8"
+WORKLOAD = "SlowFast-R50 8x8 feature extraction, batch 64 synthetic event clips (32x224x224 fast / 8 slow) per GPU"
+GFLOP_PER_CLIP = 100.615  # SURVEY.md section 8d / appendix A.1 (asserted in tests/test_host.py)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1383.6), d.get("bf16_tflops", 1636.3), d.get("hbm_gbs", 6529.7), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_clips_per_s(steps: int, warmup: int, clips: int = 5):
+    """The reference algorithm on the host cores: the oracle port (oracle/sf_oracle.py, validated
+    against the real reference in tests/test_oracle.py), fp32, eval, all threads; one step = one
+    video = 5 event clips (BASELINE.json configs[0])."""
+    import torch
+    from common import build_model, synthetic_frames
+    from oracle import sf_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, cfg, _ = build_model(MODEL, seed=0, crop=224)
+    sd = model.state_dict()
+    frames = synthetic_frames(clips, 32, 224, seed=1234)
+    xs = O.clips_from_frames(frames, cfg.sf_mdl)
+    for _ in range(warmup):
+        O.sfbase_forward(sd, cfg.sf_mdl, xs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.sfbase_forward(sd, cfg.sf_mdl, xs)
+    dt = time.perf_counter() - t0
+    return clips * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 40))
+    val, ms, cores = cpu_reference_clips_per_s(steps, max(1, min(args.warmup, 3)))
+    sample = f"{steps} steps x 5 clips (1 synthetic video) of the same SlowFast-R50 8x8 224x224 forward, fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": "event clips/sec SlowFast-R50 8x8", "value": round(val, 4), "unit": "clips/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": round(ms, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference path = CPU fp32 forward (the reference's own test-free "
+                   "PyTorch modules restated in oracle/sf_oracle.py and pinned to the real reference's outputs)"},
+        "cpu_baseline": {"value": round(val, 4), "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 4), "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--per-op", default="", help="write per-launch timings (json) to this path")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from common import build_model, synthetic_frames
+    from vidsitu_b200 import lib
+    from vidsitu_b200.dist import gather_rows
+    from vidsitu_b200.pipeline import HostPipeline
+
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    model, cfg, _ = build_model(MODEL, seed=0, crop=224, micro_batch=B)
+    model = model.to(dev)
+    # two distinct synthetic batches per rank; 2 x 308 MB of uint8 frames (> the 126 MB L2) alternate between steps
+    host_frames = [synthetic_frames(B, 32, 224, seed=1234 + 17 * rank + i).pin_memory() for i in range(2)]
+    dev_frames = [f.to(dev) for f in host_frames]
+    eng = model._engine(B, dev)
+    eng.capture()
+    launches_per_step = eng.num_launches + (2 if model.spec.num_pathways == 2 else 1)
+
+    def step(i):
+        eng.load_frames(dev_frames[i % 2])
+        eng.replay()
+        if world > 1:
+            gather_rows(eng.feats, world * B, rows_per_item=B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public host API (pinned host frames -> pinned host features)
+    e2e = None
+    if not args.no_e2e:
+        pipe = HostPipeline(model, B, dev)
+        for i in range(args.warmup):
+            pipe.submit(host_frames[i % 2])
+        pipe.flush()
+        barrier()
+        t0 = time.perf_counter()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(pipe.copy_stream)
+        checksum = 0.0
+        pending = []
+        for i in range(args.steps):
+            pending.append(pipe.submit(host_frames[i % 2]))
+            if len(pending) > 1:
+                checksum += float(pipe.result(pending.pop(0))[0, 0])   # the host really reads each result
+        while pending:
+            checksum += float(pipe.result(pending.pop(0))[0, 0])
+        s1.record(pipe.compute_stream)
+        pipe.flush()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        dev_ms = s0.elapsed_time(s1)
+        t = torch.tensor([max(dev_ms, wall_ms)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        e2e = {"value": round(world * B * args.steps / (e2e_ms / 1e3), 2), "unit": "clips/s",
+               "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+               "ms_per_step": round(e2e_ms / args.steps, 3), "checksum": round(checksum, 4)}
+
+    # ---- roofline of the dominant kernel (conv_igemm_kernel): CUDA events around every launch, eager
+    peak_sus, peak_burst, hbm, peak_src = measured_peaks()
+    per_op = eng.time_ops(iters=3) if rank == 0 else []
+    roofline = None
+    if rank == 0:
+        conv = [(n, ms_, f) for n, ms_, f in per_op if f > 0 and not n.startswith("proj_head")]
+        conv_ms = sum(ms_ for _, ms_, _ in conv)
+        all_ms = sum(ms_ for _, ms_, _ in per_op)
+        flops = GFLOP_PER_CLIP * 1e9 * B
+        achieved = flops / (conv_ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel", "achieved": round(achieved, 2),
+                    "peak": peak_sus, "unit": "TFLOP/s", "frac": round(achieved / peak_sus, 4), "traffic": None,
+                    "peak_source": f"{peak_src} bf16_tflops_sustained (burst {peak_burst})",
+                    "launches_per_step": len(conv), "conv_ms_per_step": round(conv_ms, 3),
+                    "conv_share_of_step": round(conv_ms / all_ms, 4),
+                    "step_tflops": round(flops / (ms / args.steps / 1e3) / 1e12, 2),
+                    "step_frac": round(flops / (ms / args.steps / 1e3) / 1e12 / peak_sus, 4)}
+        if args.per_op:
+            json.dump([{"op": n, "ms": round(m, 4), "gflop": round(f / 1e9, 3)} for n, m, f in per_op],
+                      open(args.per_op, "w"), indent=0)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, cms, cores = cpu_reference_clips_per_s(steps=3, warmup=1)
+        cpu_baseline = {"value": round(val, 4), "unit": "clips/s", "cores": cores, "kind": "port",
+                        "sample": "3 steps x 5 clips (1 synthetic video, BASELINE.json configs[0]) of the same forward, "
+                                  "fp32 oracle port on the host cores"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "event clips/sec SlowFast-R50 8x8", "value": round(value, 2), "unit": "clips/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "model": MODEL,
+                       "weights": "random-init (seed 0) + seeded BatchNorm statistics",
+                       "l2": "inputs larger than L2: 2 alternating 308 MB uint8 frame batches per GPU, "
+                             "activations >> 126 MB", "cuda_graph": True,
+                       "parallelism": f"clip-sharded x{world}, features all-gathered each step" if world > 1 else "single GPU"},
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,200 @@
+"""GPU parity tests (-m gpu): every call goes through the C ABI of libvidsitu_b200.so.
+
+Checkers: plain torch fp32 on the same GPU for single ops (TF32 off), the committed
+reference outputs (tests/golden) and the CPU oracle for whole networks.
+
+Tolerances (BASELINE.json north_star): bf16 features within max relative error 1e-2
+(relative to max(|ref|, floor), floor = 10 % of the mean |ref| -- pooled post-ReLU means
+can be arbitrarily close to 0) and cosine >= 0.9999 against the reference's fp32;
+fp32 mode: identical top-5 verb index SET per clip and 1e-3 relative on features.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from common import ROOT, build_model, synthetic_frames
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+META = json.load(open(os.path.join(GOLD, "golden_meta.json")))
+
+
+def rel_err(got: np.ndarray, ref: np.ndarray, floor_frac: float = 0.1):
+    floor = floor_frac * float(np.abs(ref).mean())
+    return float((np.abs(got - ref) / np.maximum(np.abs(ref), floor)).max())
+
+
+def cosine(got: np.ndarray, ref: np.ndarray):
+    num = (got * ref).sum(-1)
+    den = np.linalg.norm(got, axis=-1) * np.linalg.norm(ref, axis=-1)
+    return float((num / den).min())
+
+
+# ------------------------------------------------------------------ single ops
+def _cases():
+    import gpu_check_ops as G
+    return G.CONV_CASES
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
+def test_conv_bf16_tensor_core(case):
+    import gpu_check_ops as G
+    info = G.run_conv_case(case, 0)
+    assert info["ok"], info
+
+
+@pytest.mark.parametrize("case", [c for c in _cases() if c[5] * c[6] <= 300000], ids=lambda c: c[0])
+def test_conv_fp32_cuda_core(case):
+    import gpu_check_ops as G
+    info = G.run_conv_case(case, 1)
+    assert info["ok"], info
+
+
+@pytest.mark.parametrize("kt,cout", [(1, 64), (5, 8), (5, 64)])
+def test_stem_quad_view(kt, cout):
+    import gpu_check_ops as G
+    info = G.run_stem_case(kt, cout)
+    assert info["ok"], info
+
+
+def test_memory_bound_ops():
+    import gpu_check_ops as G
+    res = G.run_mem_checks()
+    bad = {k: v for k, v in res.items() if not v["ok"]}
+    assert not bad, bad
+
+
+def test_conv_rejects_bad_arguments():
+    from vidsitu_b200 import ops
+    from vidsitu_b200.lib import VSB_BF16, VsbError
+    x = torch.zeros((1, 1, 8, 8, 24), dtype=torch.bfloat16, device="cuda")     # cin not a multiple of 16
+    w = torch.zeros((16, 1, 24), dtype=torch.bfloat16, device="cuda")
+    s = torch.ones(16, device="cuda")
+    o = torch.zeros((1, 1, 8, 8, 16), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(VsbError):
+        ops.ConvPlan(VSB_BF16, ops.Act(x, 1, 1, 8, 8, 24, 24), w, 16, (1, 1, 1), (1, 1, 1), (0, 0, 0), None, s, s,
+                     ops.Act(o, 1, 1, 8, 8, 16, 16))
+    with pytest.raises(VsbError):   # CPU tensors are refused: there is no CPU path
+        ops.linear(torch.zeros(2, 4), torch.zeros(3, 4), None, torch.zeros(2, 3), False)
+
+
+# ------------------------------------------------------------------ whole networks vs the reference's outputs
+def _run_model(case, precision):
+    m = META[case]
+    model, cfg, _ = build_model(m["sf_mdl_name"], seed=m["seed"], randomize_bn=not m["raw_init"], crop=m["crop"],
+                                precision=precision)
+    model = model.cuda()
+    frames = synthetic_frames(m["clips"], cfg.sf_mdl.DATA.NUM_FRAMES, m["crop"], seed=1234 + m["seed"]).cuda()
+    feats, logits = model.extract_features(frames, want_logits=True)
+    torch.cuda.synchronize()
+    return model, cfg, frames, feats.cpu().numpy(), logits.cpu().numpy()
+
+
+BF16_CASES = ["sf50_n2_64", "sf50_rawinit_n2_64", "i3d_nln_n2_64", "slow_n2_64", "c2d_n2_64", "sf101_n2_64",
+              "sf50_n5_224", "i3d_n2_224", "i3d_nln_n2_224", "sf101_n1_224"]
+
+
+@pytest.mark.parametrize("case", BF16_CASES)
+def test_bf16_features_match_reference(case):
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    _, _, _, feats, logits = _run_model(case, "bf16")
+    assert np.isfinite(feats).all() and np.isfinite(logits).all()
+    re, cs = rel_err(feats, g["pooled"]), cosine(feats, g["pooled"])
+    print(f"{case}: bf16 pooled max-rel-err {re:.4g} cosine {cs:.6f}; logits rel {rel_err(logits, g['logits']):.4g}")
+    assert cs >= 0.9999, (re, cs)
+    assert re <= 1e-2, (re, cs)
+    assert cosine(logits, g["logits"]) >= 0.9999
+
+
+@pytest.mark.parametrize("case", ["sf50_n2_64", "i3d_nln_n2_64", "sf101_n2_64", "sf50_n5_224", "i3d_nln_n2_224"])
+def test_fp32_top5_and_features_match_reference(case):
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    _, _, _, feats, logits = _run_model(case, "fp32")
+    re = rel_err(feats, g["pooled"])
+    print(f"{case}: fp32 pooled max-rel-err {re:.3g}")
+    assert re <= 1e-3
+    top5 = np.argsort(-logits, axis=-1, kind="stable")[:, :5]
+    # bit-exact top-5 index SET per clip (evl_vsitu.py:41-67 keeps the 5 best verbs)
+    assert np.array_equal(np.sort(top5, -1), np.sort(g["top5"], -1))
+
+
+def test_dropin_surface_matches_reference_contract():
+    """forward_encoder / head / forward with the reference's input dict (mdl_sf_base.py:169-216)."""
+    from oracle import sf_oracle as O
+    case = "sf50_n5_224"
+    m = META[case]
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    model, cfg, _ = build_model(m["sf_mdl_name"], seed=m["seed"], crop=m["crop"])
+    model = model.cuda()
+    frames = synthetic_frames(5, 32, 224, seed=1234 + m["seed"])
+    slow, fast = O.clips_from_frames(frames, cfg.sf_mdl)
+    inp = {"frms_ev_slow_tensor": slow.unsqueeze(0).cuda(), "frms_ev_fast_tensor": fast.unsqueeze(0).cuda(),
+           "vseg_idx": torch.zeros(1, dtype=torch.long).cuda()}
+    enc = model.forward_encoder(inp)
+    assert [tuple(e.shape) for e in enc] == [(5, 2048, 8, 7, 7), (5, 256, 32, 7, 7)]
+    assert all(e.dtype == torch.float32 for e in enc)
+    pooled = model.head(enc)
+    assert tuple(pooled.shape) == (5, 2304, 1, 1, 1)
+    out = model(inp)["mdl_out"]
+    assert tuple(out.shape) == (1, 5, 1560)
+    p = pooled.flatten(1).cpu().numpy()
+    assert cosine(p, g["pooled"]) >= 0.9999 and rel_err(p, g["pooled"]) <= 1e-2
+    assert cosine(out.view(5, -1).cpu().numpy(), g["logits"]) >= 0.9999
+    # fused path == drop-in path (same kernels, same per-clip arithmetic)
+    f2, l2 = model.forward_pooled(inp)
+    assert torch.equal(f2.view(5, -1), pooled.flatten(1))
+    # feature map samples against the reference's
+    for pth, e in enumerate(enc):
+        flat = e.flatten().cpu()
+        samp = flat[:: max(1, flat.numel() // 8192)][:8192].numpy()
+        ref = g[f"fmap{pth}_sample"]
+        assert float(np.abs(samp - ref).max()) <= 0.05 * float(np.abs(ref).max())
+
+
+def test_state_dict_roundtrip_and_reload_changes_output():
+    model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=10, crop=64)
+    model = model.cuda()
+    frames = synthetic_frames(2, 32, 64, seed=7).cuda()
+    f1 = model.extract_features(frames).clone()
+    other, _, _ = build_model("slow_fast_nl_r50_8x8", seed=99, crop=64)
+    model.load_state_dict(other.state_dict())
+    f2 = model.extract_features(frames).clone()
+    assert not torch.equal(f1, f2)
+    again, _, _ = build_model("slow_fast_nl_r50_8x8", seed=10, crop=64)
+    model.load_state_dict(again.state_dict())
+    assert torch.equal(model.extract_features(frames), f1)
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+def test_full_size_batch64_properties():
+    """BASELINE.json config 2 (SF50, 64 clips, 224x224): deterministic, batch-invariant per clip,
+    graph replay == eager launches, and consistent with the reference on the 5 golden clips."""
+    case = "sf50_n5_224"
+    m = META[case]
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    model, cfg, _ = build_model(m["sf_mdl_name"], seed=m["seed"], crop=224, micro_batch=64)
+    model = model.cuda()
+    gold_frames = synthetic_frames(5, 32, 224, seed=1234 + m["seed"])
+    extra = synthetic_frames(59, 32, 224, seed=4321)
+    frames = torch.cat([gold_frames, extra]).cuda()
+    f_a = model.extract_features(frames).clone()
+    f_b = model.extract_features(frames).clone()
+    assert torch.equal(f_a, f_b)                                   # deterministic
+    f_eager = model.extract_features(frames, use_graph=False).clone()
+    assert torch.equal(f_a, f_eager)                               # graph replay == eager
+    model.micro_batch = 5
+    f_small = model.extract_features(frames[:5]).clone()
+    assert torch.equal(f_small, f_a[:5])                           # a clip's result does not depend on its batch
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(0)).cuda()
+    model.micro_batch = 64
+    f_perm = model.extract_features(frames[perm].contiguous())
+    assert torch.equal(f_perm, f_a[perm])                          # permutation equivariance
+    got = f_a[:5].cpu().numpy()
+    assert cosine(got, g["pooled"]) >= 0.9999 and rel_err(got, g["pooled"]) <= 1e-2

@@ -1,0 +1,183 @@
+"""CPU-side tests: config / spec / state_dict contract, weight preparation, the C-ABI
+library's exports, sharding logic (gloo, world_size 2).  No compute call needs a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import ROOT, build_model
+from vidsitu_b200 import lib as L
+from vidsitu_b200.arch import build_spec
+from vidsitu_b200.config import SF_MDL_PRESETS, make_cfg, make_comm
+from vidsitu_b200.weights import fold_bn, pack_conv_weight, stem_quad_weight
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = L.load()
+    assert lib.vsb_abi_version() == 1
+    declared = set()
+    for hdr in ("vidsitu_b200.h", "vidsitu_b200_debug.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared |= set(re.findall(r"\b(vsb_[a-z0-9_]+)\s*\(", src))
+    assert len(declared) >= 15
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("only meaningful on a machine without a CUDA device")
+    from vidsitu_b200 import ops
+    from vidsitu_b200.lib import VsbError
+    model, cfg, _ = build_model("slow_fast_nl_r50_8x8", crop=64)
+    with pytest.raises(VsbError):
+        model.extract_features(torch.zeros((1, 32, 64, 64, 3), dtype=torch.uint8))
+    with pytest.raises(VsbError):
+        ops.linear(torch.zeros(2, 4), torch.zeros(3, 4), None, torch.zeros(2, 3), False)
+    # a device-less plan_create must be an error status with a message, not a crash
+    d = L.ConvDesc()
+    h = ctypes.c_void_p()
+    assert L.load().vsb_conv3d_plan_create(ctypes.byref(d), ctypes.byref(h)) != 0
+    assert L.load().vsb_last_error()
+
+
+@pytest.mark.parametrize("name,nconv,dims", [
+    ("slow_fast_nl_r50_8x8", 110, [2048, 256]), ("i3d_r50_8x8", 53, [2048]), ("i3d_r50_nl_8x8", 73, [2048]),
+    ("slow_fast_r101_16x8", 212, [2048, 256]), ("slow_nl_r50_8x8", 53, [2048]), ("c2d_r50_8x8", 53, [2048])])
+def test_spec_matches_survey_tables(name, nconv, dims):
+    spec = build_spec(make_cfg(name).sf_mdl)
+    assert len(spec.all_convs()) == nconv
+    assert spec.feat_dims == dims
+
+
+def test_sf50_conv_flops_match_survey():
+    """100.615 conv GFLOP per SlowFast-R50 8x8 clip at 224x224."""
+    spec = build_spec(make_cfg("slow_fast_nl_r50_8x8").sf_mdl)
+    from oracle.flops import conv_gflop_per_clip
+    assert abs(conv_gflop_per_clip(spec) - 100.615) < 0.01
+    assert abs(conv_gflop_per_clip(build_spec(make_cfg("i3d_r50_8x8").sf_mdl)) - 56.814) < 0.01
+    assert abs(conv_gflop_per_clip(build_spec(make_cfg("slow_fast_r101_16x8").sf_mdl)) - 326.187) < 0.01
+
+
+def test_state_dict_key_contract():
+    model, _, _ = build_model("slow_fast_nl_r50_8x8", crop=64)
+    sd = model.state_dict()
+    assert len(sd) == 666        # 662 sf_mdl.* + 4 proj_head.* 
+    for k, shape in {
+        "sf_mdl.s1.pathway0_stem.conv.weight": (64, 3, 1, 7, 7),
+        "sf_mdl.s1.pathway1_stem.conv.weight": (8, 3, 5, 7, 7),
+        "sf_mdl.s1_fuse.conv_f2s.weight": (16, 8, 7, 1, 1),
+        "sf_mdl.s2.pathway0_res0.branch1.weight": (256, 80, 1, 1, 1),
+        "sf_mdl.s4.pathway0_res0.branch2.a.weight": (256, 640, 3, 1, 1),
+        "sf_mdl.s5.pathway1_res2.branch2.c_bn.running_var": (256,),
+        "sf_mdl.head.projection.weight": (400, 2304),
+        "proj_head.0.weight": (1152, 2304),
+        "proj_head.2.bias": (1560,),
+    }.items():
+        assert tuple(sd[k].shape) == shape, k
+    nl, _, _ = build_model("i3d_r50_nl_8x8", crop=64)
+    keys = nl.state_dict().keys()
+    assert "sf_mdl.s3.pathway0_nonlocal1.conv_theta.bias" in keys
+    assert "sf_mdl.s4.pathway0_nonlocal5.bn.running_mean" in keys
+    assert "sf_mdl.s3.pathway0_nonlocal0.conv_theta.weight" not in keys
+
+
+def test_module_prefix_checkpoints_load():
+    """feat_extractor.py:147-153 strips a DDP 'module.' prefix before load_state_dict."""
+    model, _, _ = build_model("i3d_r50_8x8", crop=64)
+    ddp = {"module." + k: v for k, v in model.state_dict().items()}
+    stripped = {k[len("module."):]: v for k, v in ddp.items()}
+    missing, unexpected = model.load_state_dict(stripped, strict=True)
+    assert not missing and not unexpected
+
+
+def test_training_mode_is_refused():
+    model, _, _ = build_model("i3d_r50_8x8", crop=64)
+    with pytest.raises(NotImplementedError):
+        model.train()
+
+
+def test_unknown_config_values_are_rejected():
+    cfg = make_cfg("slow_fast_nl_r50_8x8")
+    cfg.sf_mdl.BN.NORM_TYPE = "sync_batchnorm"
+    with pytest.raises(NotImplementedError):
+        build_spec(cfg.sf_mdl)
+    cfg = make_cfg("i3d_r50_8x8")
+    cfg.sf_mdl.MODEL.ARCH = "x3d"
+    with pytest.raises(NotImplementedError):
+        build_spec(cfg.sf_mdl)
+    with pytest.raises(KeyError):
+        make_cfg("nope")
+    assert set(SF_MDL_PRESETS) >= {"slow_fast_nl_r50_8x8", "slow_nl_r50_8x8", "c2d_r50_8x8", "i3d_r50_8x8",
+                                   "i3d_r50_nl_8x8"}
+    assert make_comm(make_cfg("i3d_r50_8x8").sf_mdl).path_type == "single"
+
+
+def test_weight_packing_and_bn_fold():
+    torch.manual_seed(0)
+    w = torch.randn(24, 10, 3, 1, 1)
+    p = pack_conv_weight(w, 16, 32, torch.float32)
+    assert p.shape == (32, 3, 16) and float(p[24:].abs().max()) == 0 and float(p[:, :, 10:].abs().max()) == 0
+    assert torch.equal(p[:24, :, :10].permute(0, 2, 1).reshape(24, 10, 3, 1, 1), w)
+    g, b, m, v = torch.rand(8) + 0.5, torch.randn(8), torch.randn(8), torch.rand(8) + 0.5
+    s, o = fold_bn(g, b, m, v, 1e-5, 16)
+    x = torch.randn(4, 8, 2, 3, 3)
+    ref = F.batch_norm(x, m, v, g, b, training=False, eps=1e-5)
+    got = x * s[:8].view(1, -1, 1, 1, 1) + o[:8].view(1, -1, 1, 1, 1)
+    assert torch.allclose(got, ref, atol=1e-5) and float(s[8:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("kt,cout", [(1, 64), (5, 8)])
+def test_stem_quad_view_is_the_same_convolution(kt, cout):
+    torch.manual_seed(1)
+    n, t, h, w = 1, 3, 16, 16
+    x = torch.randn(n, t, h, w, 3)
+    wt = torch.randn(cout, 3, kt, 7, 7)
+    ref = F.conv3d(x.permute(0, 4, 1, 2, 3), wt, stride=(1, 2, 2), padding=(kt // 2, 3, 3)).permute(0, 2, 3, 4, 1)
+    x4 = torch.zeros(n, t, h, w, 4)
+    x4[..., :3] = x
+    wq = stem_quad_weight(wt, torch.float32).view(2 * cout, kt, 7, 3, 16).permute(0, 4, 1, 2, 3)
+    y = F.conv3d(x4.view(n, t, h, w // 4, 16).permute(0, 4, 1, 2, 3), wq, stride=(1, 2, 1), padding=(kt // 2, 3, 1))
+    y = y.permute(0, 2, 3, 4, 1).reshape(n, t, h // 2, w // 2, cout)
+    assert torch.allclose(y, ref, atol=1e-4)
+
+
+def test_shard_ranges_partition_the_videos():
+    from vidsitu_b200.dist import shard_counts, shard_range
+    for n in (0, 1, 7, 8, 1326):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(shard_counts(n, world)) - min(shard_counts(n, world)) <= 1
+
+
+def test_gather_rows_world2_gloo(tmp_path):
+    """N>1 host path: contiguous video shards + one all-gather, run as 2 gloo ranks on CPU."""
+    script = tmp_path / "w.py"
+    script.write_text(f"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {ROOT!r})
+from vidsitu_b200.dist import shard_range, gather_rows
+dist.init_process_group('gloo')
+r, w = dist.get_rank(), dist.get_world_size()
+n_vid = 7
+full = torch.arange(n_vid * 5 * 3, dtype=torch.float32).view(n_vid * 5, 3)
+s, e = shard_range(n_vid, r, w)
+out = gather_rows(full[s * 5:e * 5].clone(), n_vid * 5)
+assert torch.equal(out, full), (r, out)
+dist.destroy_process_group()
+print('ok', r)
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                         capture_output=True, text=True, timeout=240, env=env)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 2

@@ -1,0 +1,380 @@
+"""Kernel plan of one event-clip forward (the body of the hot path).
+
+`ClipEngine` turns a `NetSpec` + a reference-layout state_dict into a static program
+of C-ABI calls over a fixed set of device buffers for a fixed clip count `n`:
+
+  inputs   [n, T_p, 224, 224, 4]   filled by the pack kernel (uint8 frames) or by the
+                                   NCTHW->NTHWC converter (reference fp32 tensors)
+  trunk    stems -> (lateral) -> res2..res5 (+ non-local), every conv one launch with
+           BN/ReLU/residual folded into its epilogue; the Fast->Slow lateral conv
+           writes straight into the channel slice of the slow tensor it is
+           concatenated to (video_model_builder.py:124-131), so no torch.cat pass
+  head     global average pool -> feats [n, D] fp32 -> Linear/ReLU/Linear -> logits
+
+It mirrors the stage order of SlowFast_FeatModel / ResNet_FeatModel.forward_features
+(vidsitu_code/mdl_sf_base.py:21-34, 46-55).  The whole program is stream-ordered and
+allocation-free, so it is captured once into a CUDA graph and replayed.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .arch import BlockSpec, ConvSpec, NetSpec, NonlocalSpec
+from .lib import VSB_BF16, VSB_F32, VsbError
+from .ops import Act, ConvPlan
+from .weights import fold_bn, identity_affine, pack_conv_weight, round_up, stem_quad_weight
+
+
+class _Pool:
+    """Stream-ordered buffer reuse: activations die as soon as their last reader has been
+    enqueued, and every op of a pool runs on one stream, so a freed buffer can be
+    handed to the next producer without a fence."""
+
+    def __init__(self, device, elem_dtype: torch.dtype):
+        self.device = device
+        self.dtype = elem_dtype
+        self.free: List[torch.Tensor] = []
+        self.total_bytes = 0
+
+    def take(self, numel: int) -> torch.Tensor:
+        best = None
+        for i, b in enumerate(self.free):
+            if b.numel() >= numel and (best is None or b.numel() < self.free[best].numel()):
+                best = i
+        if best is not None and self.free[best].numel() <= 2 * numel:
+            return self.free.pop(best)
+        buf = torch.empty(numel, dtype=self.dtype, device=self.device)
+        self.total_bytes += buf.numel() * buf.element_size()
+        return buf
+
+    def give(self, buf: torch.Tensor) -> None:
+        self.free.append(buf)
+
+
+class ClipEngine:
+    def __init__(self, spec: NetSpec, tensors: Dict[str, torch.Tensor], n: int, dtype: int = VSB_BF16,
+                 device: Optional[torch.device] = None, proj_head: Optional[Sequence[torch.Tensor]] = None,
+                 tune: Optional[dict] = None, bn_eps: float = 1e-5):
+        if not torch.cuda.is_available():
+            raise VsbError("ClipEngine needs a CUDA device: the forward is made of sm_100a kernels only")
+        self.spec = spec
+        self.n = int(n)
+        self.dtype = dtype
+        self.tdt = ops.TORCH_DTYPE[dtype]
+        self.device = torch.device(device if device is not None else "cuda")
+        self.tune = dict(tune or {})
+        self.bn_eps = bn_eps
+        self._t = tensors
+        self._keep: List[torch.Tensor] = []
+        self.trunk_ops: List[Tuple[str, Callable[[], None], float]] = []   # (name, launch, flops)
+        self.head_ops: List[Tuple[str, Callable[[], None], float]] = []
+        self._pool = _Pool(self.device, self.tdt)
+        self._graph = None
+        self.crop = spec.crop
+        if self.crop % 4 or (self.crop * self.crop) % 16:
+            raise VsbError("crop size must be a multiple of 4")
+        frames = spec.pathway_frames()
+        # ---- inputs
+        self.inputs: List[Act] = []
+        for t in frames:
+            buf = torch.zeros(self.n * t * self.crop * self.crop * 4, dtype=self.tdt, device=self.device)
+            self.inputs.append(Act(buf, self.n, t, self.crop, self.crop, 4, 4, c_real=3))
+        # slow-pathway temporal indices, exactly as utils/video_utils.py:62-69
+        t_fast = spec.num_frames
+        self.fast_idx = list(range(t_fast))
+        if spec.num_pathways == 2:
+            self.slow_idx = torch.linspace(0, t_fast - 1, t_fast // spec.alpha).long().tolist()
+        # ---- trunk
+        self.trunk_out = self._build_trunk()
+        # ---- head
+        d = sum(spec.feat_dims)
+        self.feats = torch.zeros((self.n, d), dtype=torch.float32, device=self.device)
+        off = 0
+        for p, x in enumerate(self.trunk_out):
+            self.head_ops.append((f"head.pathway{p}_avgpool",
+                                  (lambda x=x, off=off: ops.global_avgpool(x, self.feats, off, self.dtype)), 0.0))
+            off += x.c_real
+        self.logits = None
+        if proj_head is not None:
+            w0, b0, w1, b1 = [t.detach().to(self.device, torch.float32).contiguous() for t in proj_head]
+            self._keep += [w0, b0, w1, b1]
+            self.hidden = torch.zeros((self.n, w0.shape[0]), dtype=torch.float32, device=self.device)
+            self.logits = torch.zeros((self.n, w1.shape[0]), dtype=torch.float32, device=self.device)
+            self.head_ops.append(("proj_head.0", lambda: ops.linear(self.feats, w0, b0, self.hidden, True),
+                                  2.0 * self.n * w0.numel()))
+            self.head_ops.append(("proj_head.2", lambda: ops.linear(self.hidden, w1, b1, self.logits, False),
+                                  2.0 * self.n * w1.numel()))
+        self._t = None  # drop the reference-layout tensors
+
+    # ------------------------------------------------------------------ building blocks
+    def _store(self, c: int) -> int:
+        return round_up(c)
+
+    def _alloc(self, n, t, h, w, c_real, pitch: Optional[int] = None) -> Act:
+        c = self._store(c_real)
+        pitch = pitch or c
+        buf = self._pool.take(n * t * h * w * pitch)
+        return Act(buf, n, t, h, w, c, pitch, 0, c_real)
+
+    def _free(self, a: Act) -> None:
+        if a.buf is not None and not any(a.buf is i.buf for i in self.inputs):
+            self._pool.give(a.buf)
+
+    def _tensor(self, key: str) -> torch.Tensor:
+        if key not in self._t:
+            raise KeyError(f"state_dict has no {key!r}")
+        return self._t[key].detach().to(self.device, torch.float32)
+
+    def _affine(self, cs: ConvSpec, cout_store: int):
+        bias = self._tensor(cs.key + ".bias") if cs.has_bias else None
+        if cs.bn is not None:
+            return fold_bn(self._tensor(cs.bn + ".weight"), self._tensor(cs.bn + ".bias"),
+                           self._tensor(cs.bn + ".running_mean"), self._tensor(cs.bn + ".running_var"),
+                           self.bn_eps, cout_store, bias)
+        return identity_affine(cs.cout, cout_store, bias, self.device)
+
+    def _out_dims(self, x: Act, cs: ConvSpec):
+        to = (x.t + 2 * cs.pad[0] - cs.kernel[0]) // cs.stride[0] + 1
+        ho = (x.h + 2 * cs.pad[1] - cs.kernel[1]) // cs.stride[1] + 1
+        wo = (x.w + 2 * cs.pad[2] - cs.kernel[2]) // cs.stride[2] + 1
+        return to, ho, wo
+
+    def _conv(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act] = None, relu: Optional[bool] = None):
+        if x.c_real != cs.cin:
+            raise VsbError(f"{cs.key}: input has {x.c_real} channels, conv expects {cs.cin}")
+        w = pack_conv_weight(self._tensor(cs.key + ".weight"), x.c, out.c, self.tdt)
+        scale, bias = self._affine(cs, out.c)
+        tune = dict(self.tune.get("*", {}))
+        tune.update(self.tune.get(cs.key, {}))
+        plan = ConvPlan(self.dtype, x, w, out.c, cs.kernel, cs.stride, cs.pad, None, scale, bias, out, residual,
+                        cs.relu if relu is None else relu, **tune)
+        self._keep.append(plan)
+        m = out.pixels
+        self.trunk_ops.append((cs.key, plan.run, float(m) * cs.flops_per_out_pixel))
+
+    def _stem(self, p: int, x: Act) -> Act:
+        st = self.spec.stems[p]
+        cs = st.conv
+        n, t = x.n, x.t
+        to, ho, wo = self._out_dims(Act(None, n, t, x.h, x.w, 4, 4), cs)
+        y = self._alloc(n, to, ho, wo, cs.cout, pitch=cs.cout)   # dense [.., cout] (no channel padding yet)
+        y.c = cs.cout
+        scale, bias = self._affine(cs, cs.cout)
+        wt = self._tensor(cs.key + ".weight")
+        if self.dtype == VSB_BF16:
+            # quad view (weights.stem_quad_weight): cin'=16, cout'=2*cout, kernel (kt,7,3), stride (1,2,1)
+            if cs.kernel[1:] != (7, 7) or cs.stride != (1, 2, 2) or cs.pad[1:] != (3, 3) or (2 * cs.cout) % 16:
+                raise VsbError("stem geometry outside the quad-view restatement")
+            wq = stem_quad_weight(wt, self.tdt)
+            xin = Act(x.buf, n, t, x.h, x.w // 4, 16, 16)
+            yout = Act(y.buf, n, to, ho, wo // 2, 2 * cs.cout, 2 * cs.cout)
+            tune = dict(self.tune.get("*", {}))
+            tune.update(self.tune.get(cs.key, {}))
+            plan = ConvPlan(self.dtype, xin, wq, 2 * cs.cout, (cs.kernel[0], 7, 3), (1, 2, 1), (cs.pad[0], 3, 1),
+                            None, torch.cat([scale, scale]), torch.cat([bias, bias]), yout, None, True, **tune)
+        else:
+            wp = pack_conv_weight(wt, 4, cs.cout, self.tdt)
+            plan = ConvPlan(self.dtype, x, wp, cs.cout, cs.kernel, cs.stride, cs.pad, None, scale, bias, y, None,
+                            True)
+        self._keep.append(plan)
+        self.trunk_ops.append((cs.key, plan.run, float(y.pixels) * cs.flops_per_out_pixel))
+        return y
+
+    def _maxpool(self, name: str, x: Act, kernel, stride, pad, pitch: Optional[int] = None) -> Act:
+        to = (x.t + 2 * pad[0] - kernel[0]) // stride[0] + 1
+        ho = (x.h + 2 * pad[1] - kernel[1]) // stride[1] + 1
+        wo = (x.w + 2 * pad[2] - kernel[2]) // stride[2] + 1
+        y = self._alloc(x.n, to, ho, wo, x.c_real, pitch=pitch)
+        self.trunk_ops.append((name, lambda: ops.maxpool3d(x, y, kernel, stride, pad, self.dtype), 0.0))
+        return y
+
+    def _block(self, x: Act, blk: BlockSpec, out_pitch: Optional[int]) -> Act:
+        n = x.n
+        ta, ha, wa = self._out_dims(x, blk.a)
+        a = self._alloc(n, ta, ha, wa, blk.a.cout)
+        self._conv(blk.a, x, a)
+        tb, hb, wb = self._out_dims(a, blk.b)
+        b = self._alloc(n, tb, hb, wb, blk.b.cout)
+        self._conv(blk.b, a, b)
+        self._free(a)
+        if blk.branch1 is not None:
+            sc = self._alloc(n, tb, hb, wb, blk.branch1.cout)
+            self._conv(blk.branch1, x, sc)
+            res = sc
+        else:
+            sc = None
+            res = x
+        y = self._alloc(n, tb, hb, wb, blk.c.cout, pitch=out_pitch)
+        # relu(shortcut + BN(c(.)))   resnet_helper.py:352-358
+        self._conv(blk.c, b, y, residual=res, relu=True)
+        self._free(b)
+        if sc is not None:
+            self._free(sc)
+        self._free(x)
+        return y
+
+    def _nonlocal(self, x: Act, nl: NonlocalSpec, out_pitch: Optional[int]) -> Act:
+        n = x.n
+        theta = self._alloc(n, x.t, x.h, x.w, nl.dim_inner)
+        self._conv(nl.theta, x, theta)
+        if nl.pool is not None:
+            xp = self._maxpool(nl.prefix + ".pool", x, nl.pool, nl.pool, (0, 0, 0))
+        else:
+            xp = x
+        phi = self._alloc(n, xp.t, xp.h, xp.w, nl.dim_inner)
+        g = self._alloc(n, xp.t, xp.h, xp.w, nl.dim_inner)
+        self._conv(nl.phi, xp, phi)
+        self._conv(nl.g, xp, g)
+        if xp is not x:
+            self._free(xp)
+        att = self._alloc(n, x.t, x.h, x.w, nl.dim_inner)
+        tq, tk = x.t * x.h * x.w, xp.t * xp.h * xp.w
+        self.trunk_ops.append((nl.prefix + ".attention",
+                               lambda: ops.nonlocal_attention(theta, phi, g, att, nl.softmax, self.dtype),
+                               4.0 * n * tq * tk * nl.dim_inner))
+        y = self._alloc(n, x.t, x.h, x.w, nl.dim, pitch=out_pitch)
+        # x + BN(conv_out(.)), no ReLU   nonlocal_helper.py:145-148
+        self._conv(nl.out, att, y, residual=x, relu=False)
+        for a in (theta, phi, g, att, x):
+            self._free(a)
+        return y
+
+    def _stage(self, x: Act, blocks: List[BlockSpec], out_pitch: Optional[int]) -> Act:
+        for i, blk in enumerate(blocks):
+            last = i == len(blocks) - 1
+            x = self._block(x, blk, out_pitch if (last and blk.nonlocal_ is None) else None)
+            if blk.nonlocal_ is not None:
+                x = self._nonlocal(x, blk.nonlocal_, out_pitch if last else None)
+        return x
+
+    def _build_trunk(self) -> List[Act]:
+        spec = self.spec
+        npw = spec.num_pathways
+        xs: List[Act] = []
+        # s1: stem conv + BN + ReLU + max-pool per pathway (stem_helper.py:173-178)
+        for p in range(npw):
+            y = self._stem(p, self.inputs[p])
+            st = spec.stems[p]
+            fuse = spec.fuses[0] if p == 0 else None
+            pitch = self._store(y.c_real) + fuse.cout if fuse is not None else None
+            xs.append(self._maxpool(f"s1.pathway{p}_stem.pool_layer", y, st.pool_kernel, st.pool_stride, st.pool_pad,
+                                    pitch))
+            self._free(y)
+        for si in range(4):
+            fuse = spec.fuses[si]
+            if fuse is not None:
+                xs[0] = self._lateral(fuse, xs[0], xs[1])
+            stage = spec.stages[si]
+            nxt_fuse = spec.fuses[si + 1] if si + 1 < 4 else None
+            for p in range(npw):
+                out_c = stage[p][-1].c.cout
+                pitch = self._store(out_c) + nxt_fuse.cout if (nxt_fuse is not None and p == 0) else None
+                xs[p] = self._stage(xs[p], stage[p], pitch)
+            if si == 0:
+                # pathway{p}_pool after res2 (mdl_sf_base.py:26-28): identity [1,1,1] pools are skipped
+                for p in range(npw):
+                    k = spec.pool1[p]
+                    if any(v != 1 for v in k):
+                        if nxt_fuse is not None and p == 0:
+                            raise VsbError("pool1 on a pathway that carries a lateral concat is not planned")
+                        y = self._maxpool(f"pathway{p}_pool", xs[p], k, k, (0, 0, 0))
+                        self._free(xs[p])
+                        xs[p] = y
+        return xs
+
+    def _lateral(self, fuse: ConvSpec, x_s: Act, x_f: Act) -> Act:
+        """FuseFastToSlow: conv(7x1x1, stride alpha)+BN+ReLU written into channels [C_s, C_s+C_fuse)
+        of the slow tensor; returns the widened slow activation (the torch.cat result)."""
+        c_s = x_s.c
+        if x_s.pitch != c_s + fuse.cout or c_s != x_s.c_real:
+            raise VsbError("slow activation was not allocated with room for the lateral channels")
+        dst = Act(x_s.buf, x_s.n, x_s.t, x_s.h, x_s.w, fuse.cout, x_s.pitch, c_off=c_s, c_real=fuse.cout)
+        to, ho, wo = self._out_dims(x_f, fuse)
+        if (to, ho, wo) != (x_s.t, x_s.h, x_s.w):
+            raise VsbError("lateral conv output does not match the slow pathway extent")
+        self._conv(fuse, x_f, dst)
+        return Act(x_s.buf, x_s.n, x_s.t, x_s.h, x_s.w, x_s.pitch, x_s.pitch, 0, x_s.pitch)
+
+    # --------------------------------------------------------------------------- running
+    def load_frames(self, frames: torch.Tensor) -> None:
+        """uint8 [n, T, H, W, 3] frames of the fast/single pathway window (dat_loader.py:474-476)."""
+        spec = self.spec
+        if frames.shape[0] != self.n or frames.shape[1] != spec.num_frames:
+            raise VsbError(f"expected frames [{self.n}, {spec.num_frames}, {self.crop}, {self.crop}, 3]")
+        if spec.num_pathways == 2:
+            ops.pack_frames(frames, self.slow_idx, spec.mean, spec.std, self.inputs[0], self.dtype,
+                            spec.reverse_input_channel)
+            ops.pack_frames(frames, self.fast_idx, spec.mean, spec.std, self.inputs[1], self.dtype,
+                            spec.reverse_input_channel)
+        else:
+            ops.pack_frames(frames, self.fast_idx, spec.mean, spec.std, self.inputs[0], self.dtype,
+                            spec.reverse_input_channel)
+
+    def load_ncthw(self, xs: Sequence[torch.Tensor]) -> None:
+        """The reference's already-normalised fp32 [n, 3, T_p, H, W] pathway tensors."""
+        if len(xs) != len(self.inputs):
+            raise VsbError(f"expected {len(self.inputs)} pathway tensors")
+        for x, a in zip(xs, self.inputs):
+            if tuple(x.shape) != (self.n, 3, a.t, a.h, a.w):
+                raise VsbError(f"pathway tensor {tuple(x.shape)} != {(self.n, 3, a.t, a.h, a.w)}")
+            ops.ncthw_to_act(x.contiguous(), a, self.dtype)
+
+    def run_trunk(self) -> None:
+        for _, fn, _ in self.trunk_ops:
+            fn()
+
+    def run_head(self) -> None:
+        for _, fn, _ in self.head_ops:
+            fn()
+
+    def run(self) -> None:
+        self.run_trunk()
+        self.run_head()
+
+    def capture(self) -> None:
+        """Capture trunk + head once into a CUDA graph (inputs/outputs are static buffers)."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.run()          # warm-up outside capture (lazy module loading, func attributes)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self._graph = g
+
+    def replay(self) -> None:
+        if self._graph is None:
+            self.capture()
+        self._graph.replay()
+
+    @property
+    def num_launches(self) -> int:
+        return len(self.trunk_ops) + len(self.head_ops)
+
+    @property
+    def conv_flops(self) -> float:
+        """Algorithmic conv FLOPs (2*MAC on the reference's un-padded shapes) of one run."""
+        return sum(f for name, _, f in self.trunk_ops if not name.endswith(".attention"))
+
+    def features_ncthw(self) -> List[torch.Tensor]:
+        return [ops.act_to_ncthw(x, self.dtype) for x in self.trunk_out]
+
+    def time_ops(self, iters: int = 3) -> List[Tuple[str, float, float]]:
+        """Per-launch device time (ms, best of `iters`) -- tuning / profiling aid."""
+        out = []
+        for name, fn, flops in self.trunk_ops + self.head_ops:
+            best = float("inf")
+            for _ in range(iters):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out.append((name, best, flops))
+        return out
