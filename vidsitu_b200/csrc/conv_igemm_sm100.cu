@@ -34,22 +34,29 @@ struct IgemmParams {
   int lt, lh, lw;  // lower corner = -leading pad
   int kh, kw;
   int cin, cin_chunks, total_chunks, cps, kchunk;
-  int block_n, n_tiles, stages;
+  int block_n, n_tiles, total_tiles, stages;
+  int epi_n, epi_chunks;  // epilogue column chunk (<= 64) and chunks per tile
   uint32_t idesc, tmem_cols;
   const float* scale;
   const float* bias;
-  const __nv_bfloat16* residual;
-  long long res_pitch;
-  __nv_bfloat16* out;
-  long long out_pitch;
+  int has_residual;
   int relu;
 };
 
 constexpr int kBlockM = 128;
 constexpr int kThreads = 192;
 
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Persistent CTA: loops over output tiles (tile = blockIdx.x + i * gridDim.x, the n-tile index
+// fastest so co-running CTAs share the activation tile in L2).  Three pipelines:
+//   smem  full/empty[stages]   TMA producer  <-> MMA issuer
+//   TMEM  full/empty[2]        MMA issuer    <-> epilogue (two accumulators: the epilogue of tile i
+//                                                overlaps the main loop of tile i+1)
+//   epi   ready[2]             staging buffers of the epilogue (residual TMA load in, TMA store out)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                   const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -57,26 +64,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t row_bytes = p.kchunk * 2;
   const uint32_t a_chunk_bytes = kBlockM * row_bytes;
   const uint32_t b_chunk_bytes = p.block_n * row_bytes;
-  const uint32_t stage_bytes = p.cps * (a_chunk_bytes + b_chunk_bytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  const uint32_t stage_bytes = (p.cps * (a_chunk_bytes + b_chunk_bytes) + 1023u) & ~1023u;
+  const uint32_t epi_row_bytes = p.epi_n * 2;
+  const uint32_t epi_buf_bytes = kBlockM * epi_row_bytes;
+  uint8_t* epi_buf = smem + (size_t)p.stages * stage_bytes;  // 2 buffers, each a multiple of 1024 bytes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_buf + 2 * epi_buf_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* accum_bar = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tmem_full = empty_bar + p.stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* epi_ready = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_ready + 2);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x % p.n_tiles;
-  const int m_tile = blockIdx.x / p.n_tiles;
-  const int m0 = m_tile * kBlockM;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_out);
+    if (p.has_residual) tma_prefetch_desc(&map_res);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&epi_ready[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 5) {
@@ -93,108 +108,175 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 4) {
     if (lane == 0) {
       // ------------------------------------------------------ TMA producer
-      const int wo = m0 % p.wo;
-      const int r1 = m0 / p.wo;
-      const int ho = r1 % p.ho;
-      const int r2 = r1 / p.ho;
-      const int to_ = r2 % p.to;
-      const int n0 = r2 / p.to;
-      const int w0 = wo * p.sw + p.lw;
-      const int h0 = ho * p.sh + p.lh;
-      const int d0 = to_ * p.st + p.lt;
-      for (int ks = 0; ks < num_kstages; ++ks) {
-        const int slot = ks % p.stages;
-        const uint32_t parity = ((ks / p.stages) & 1) ^ 1;
-        mbar_wait(&empty_bar[slot], parity);
-        const int g0 = ks * p.cps;
-        const int nch = min(p.cps, p.total_chunks - g0);
-        mbar_expect_tx(&full_bar[slot], nch * (a_chunk_bytes + b_chunk_bytes));
-        uint8_t* a_dst = smem + (size_t)slot * stage_bytes;
-        uint8_t* b_dst = a_dst + p.cps * a_chunk_bytes;
-        for (int c = 0; c < nch; ++c) {
-          const int g = g0 + c;
-          const int tap = g / p.cin_chunks;
-          const int cc = g - tap * p.cin_chunks;
-          const int kw_ = tap % p.kw;
-          const int r = tap / p.kw;
-          const int kh_ = r % p.kh;
-          const int kt_ = r / p.kh;
-          tma_load_im2col_5d(a_dst + c * a_chunk_bytes, &map_a, &full_bar[slot], cc * p.kchunk, w0, h0, d0, n0,
-                             (uint16_t)kw_, (uint16_t)kh_, (uint16_t)kt_);
-          tma_load_2d(b_dst + c * b_chunk_bytes, &map_b, &full_bar[slot], tap * p.cin + cc * p.kchunk,
-                      n_tile * p.block_n);
+      int kit = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m0 = (tile / p.n_tiles) * kBlockM;
+        const int wo = m0 % p.wo;
+        const int r1 = m0 / p.wo;
+        const int ho = r1 % p.ho;
+        const int r2 = r1 / p.ho;
+        const int to_ = r2 % p.to;
+        const int n0 = r2 / p.to;
+        const int w0 = wo * p.sw + p.lw;
+        const int h0 = ho * p.sh + p.lh;
+        const int d0 = to_ * p.st + p.lt;
+        for (int ks = 0; ks < num_kstages; ++ks, ++kit) {
+          const int slot = kit % p.stages;
+          const uint32_t parity = ((kit / p.stages) & 1) ^ 1;
+          mbar_wait(&empty_bar[slot], parity);
+          const int g0 = ks * p.cps;
+          const int nch = min(p.cps, p.total_chunks - g0);
+          mbar_expect_tx(&full_bar[slot], nch * (a_chunk_bytes + b_chunk_bytes));
+          uint8_t* a_dst = smem + (size_t)slot * stage_bytes;
+          uint8_t* b_dst = a_dst + p.cps * a_chunk_bytes;
+          for (int c = 0; c < nch; ++c) {
+            const int g = g0 + c;
+            const int tap = g / p.cin_chunks;
+            const int cc = g - tap * p.cin_chunks;
+            const int kw_ = tap % p.kw;
+            const int r = tap / p.kw;
+            const int kh_ = r % p.kh;
+            const int kt_ = r / p.kh;
+            tma_load_im2col_5d(a_dst + c * a_chunk_bytes, &map_a, &full_bar[slot], cc * p.kchunk, w0, h0, d0, n0,
+                               (uint16_t)kw_, (uint16_t)kh_, (uint16_t)kt_);
+            tma_load_2d(b_dst + c * b_chunk_bytes, &map_b, &full_bar[slot], tap * p.cin + cc * p.kchunk,
+                        n_tile * p.block_n);
+          }
         }
       }
     }
   } else if (warp == 5) {
     if (lane == 0) {
       // -------------------------------------------------------- MMA issuer
-      uint32_t accumulate = 0;
       const int kk = p.kchunk >> 4;
-      for (int ks = 0; ks < num_kstages; ++ks) {
-        const int slot = ks % p.stages;
-        const uint32_t parity = (ks / p.stages) & 1;
-        mbar_wait(&full_bar[slot], parity);
+      int kit = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const int acc = tcount & 1;
+        mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
-        const int nch = min(p.cps, p.total_chunks - ks * p.cps);
-        const uint32_t a0 = smem_u32(smem + (size_t)slot * stage_bytes);
-        const uint32_t b0 = a0 + p.cps * a_chunk_bytes;
-        for (int c = 0; c < nch; ++c) {
-          for (int k = 0; k < kk; ++k) {
-            const uint64_t adesc = umma_smem_desc(a0 + c * a_chunk_bytes + k * 32, row_bytes);
-            const uint64_t bdesc = umma_smem_desc(b0 + c * b_chunk_bytes + k * 32, row_bytes);
-            umma_bf16(tmem_base, adesc, bdesc, p.idesc, accumulate);
-            accumulate = 1;
+        const uint32_t tmem_d = tmem_base + acc * p.block_n;
+        uint32_t accumulate = 0;
+        for (int ks = 0; ks < num_kstages; ++ks, ++kit) {
+          const int slot = kit % p.stages;
+          mbar_wait(&full_bar[slot], (kit / p.stages) & 1);
+          tc_fence_after();
+          const int nch = min(p.cps, p.total_chunks - ks * p.cps);
+          const uint32_t a0 = smem_u32(smem + (size_t)slot * stage_bytes);
+          const uint32_t b0 = a0 + p.cps * a_chunk_bytes;
+          for (int c = 0; c < nch; ++c) {
+            for (int k = 0; k < kk; ++k) {
+              const uint64_t adesc = umma_smem_desc(a0 + c * a_chunk_bytes + k * 32, row_bytes);
+              const uint64_t bdesc = umma_smem_desc(b0 + c * b_chunk_bytes + k * 32, row_bytes);
+              umma_bf16(tmem_d, adesc, bdesc, p.idesc, accumulate);
+              accumulate = 1;
+            }
           }
+          umma_commit(&empty_bar[slot]);  // frees the smem slot once these MMAs retire
         }
-        umma_commit(&empty_bar[slot]);  // frees the smem slot once these MMAs retire
+        umma_commit(&tmem_full[acc]);  // accumulator complete
       }
-      umma_commit(accum_bar);  // accumulator complete
     }
   } else {
-    // ---------------------------------------------------------- epilogue
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const long long row = (long long)m0 + warp * 32 + lane;
-    const bool valid = row < p.m_total;
-    const int nbase = n_tile * p.block_n;
-    __nv_bfloat16* orow = p.out + row * p.out_pitch + nbase;
-    const __nv_bfloat16* rrow = p.residual ? p.residual + row * p.res_pitch + nbase : nullptr;
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int j0 = 0; j0 < p.block_n; j0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + j0, v);
-      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-      if (rrow && valid) {
-        r0 = *reinterpret_cast<const uint4*>(rrow + j0);
-        r1 = *reinterpret_cast<const uint4*>(rrow + j0 + 8);
-      }
-      float sc[16], bi[16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + nbase + j0) + q);
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + j0) + q);
-        sc[4 * q + 0] = s4.x; sc[4 * q + 1] = s4.y; sc[4 * q + 2] = s4.z; sc[4 * q + 3] = s4.w;
-        bi[4 * q + 0] = b4.x; bi[4 * q + 1] = b4.y; bi[4 * q + 2] = b4.z; bi[4 * q + 3] = b4.w;
-      }
-      tmem_ld_wait();
-      const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-      uint32_t o[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float x0 = fmaf(__uint_as_float(v[2 * q]), sc[2 * q], bi[2 * q]) + bf16_lo(rr[q]);
-        float x1 = fmaf(__uint_as_float(v[2 * q + 1]), sc[2 * q + 1], bi[2 * q + 1]) + bf16_hi(rr[q]);
-        if (p.relu) {
-          x0 = fmaxf(x0, 0.f);
-          x1 = fmaxf(x1, 0.f);
-        }
-        o[q] = pack_bf16x2(x0, x1);
-      }
-      if (valid) {
-        *reinterpret_cast<uint4*>(orow + j0) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(orow + j0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+    // ---------------------------------------------------------- epilogue (warps 0-3)
+    const bool leader = threadIdx.x == 0;
+    const int row = warp * 32 + lane;  // row of the tile == TMEM lane
+    const uint32_t swz_mask = epi_row_bytes == 128 ? 7u : (epi_row_bytes == 64 ? 3u : 1u);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    int q = 0;  // running chunk counter: staging buffer = q & 1
+    if (leader) {
+      // make staging buffer 0 ready for the first chunk of the first tile
+      if (p.has_residual) {
+        mbar_expect_tx(&epi_ready[0], epi_buf_bytes);
+        tma_load_2d(epi_buf, &map_res, &epi_ready[0], (blockIdx.x % p.n_tiles) * p.block_n,
+                    (blockIdx.x / p.n_tiles) * kBlockM);
+      } else {
+        mbar_arrive(&epi_ready[0]);
       }
     }
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const int n_tile = tile % p.n_tiles;
+      const int m0 = (tile / p.n_tiles) * kBlockM;
+      const int nbase = n_tile * p.block_n;
+      const int acc = tcount & 1;
+      mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      for (int c = 0; c < p.epi_chunks; ++c, ++q) {
+        const int b = q & 1;
+        uint8_t* buf = epi_buf + b * epi_buf_bytes;
+        mbar_wait(&epi_ready[b], (q >> 1) & 1);  // buffer free (+ residual landed)
+        const int col0 = nbase + c * p.epi_n;
+        for (int j0 = 0; j0 < p.epi_n; j0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(lane_taddr + acc * p.block_n + c * p.epi_n + j0, v);
+          // this thread's 32 bytes of the staging row, as two swizzled 16-byte chunks
+          const uint32_t off0 = row * epi_row_bytes + j0 * 2;
+          uint4* s0 = reinterpret_cast<uint4*>(buf + (off0 ^ (((off0 >> 7) & swz_mask) << 4)));
+          const uint32_t off1 = off0 + 16;
+          uint4* s1 = reinterpret_cast<uint4*>(buf + (off1 ^ (((off1 >> 7) & swz_mask) << 4)));
+          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+          if (p.has_residual) {
+            r0 = *s0;
+            r1 = *s1;
+          }
+          float sc[16], bi[16];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + j0) + qq);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j0) + qq);
+            sc[4 * qq + 0] = s4.x; sc[4 * qq + 1] = s4.y; sc[4 * qq + 2] = s4.z; sc[4 * qq + 3] = s4.w;
+            bi[4 * qq + 0] = b4.x; bi[4 * qq + 1] = b4.y; bi[4 * qq + 2] = b4.z; bi[4 * qq + 3] = b4.w;
+          }
+          tmem_ld_wait();
+          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          uint32_t o[8];
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) {
+            float x0 = fmaf(__uint_as_float(v[2 * qq]), sc[2 * qq], bi[2 * qq]) + bf16_lo(rr[qq]);
+            float x1 = fmaf(__uint_as_float(v[2 * qq + 1]), sc[2 * qq + 1], bi[2 * qq + 1]) + bf16_hi(rr[qq]);
+            if (p.relu) {
+              x0 = fmaxf(x0, 0.f);
+              x1 = fmaxf(x1, 0.f);
+            }
+            o[qq] = pack_bf16x2(x0, x1);
+          }
+          *s0 = make_uint4(o[0], o[1], o[2], o[3]);
+          *s1 = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        if (c == p.epi_chunks - 1) {
+          // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
+        epi_bar_sync();
+        if (leader) {
+          tma_store_2d(&map_out, buf, col0, m0);  // rows >= m_total are clipped by the TMA unit
+          tma_store_commit();
+          // prepare the other staging buffer for the next chunk (same tile, or first chunk of the next tile)
+          int nc = c + 1, ntile = tile;
+          if (nc == p.epi_chunks) {
+            nc = 0;
+            ntile = tile + gridDim.x;
+          }
+          if (ntile < p.total_tiles) {
+            tma_store_wait_read1();  // the store issued from that buffer one chunk ago has read it
+            const int nb = b ^ 1;
+            if (p.has_residual) {
+              mbar_expect_tx(&epi_ready[nb], epi_buf_bytes);
+              tma_load_2d(epi_buf + nb * epi_buf_bytes, &map_res, &epi_ready[nb],
+                          (ntile % p.n_tiles) * p.block_n + nc * p.epi_n, (ntile / p.n_tiles) * kBlockM);
+            } else {
+              mbar_arrive(&epi_ready[nb]);
+            }
+          }
+        }
+        __syncwarp();  // warp 0 reconverges before the next warp-aligned tcgen05.ld
+      }
+    }
+    if (leader) tma_store_wait_all();  // all output bytes are in global memory before the CTA exits
   }
 
   tc_fence_before();
@@ -329,7 +411,7 @@ struct vsb_conv_plan {
   int to, ho, wo;
   long long m_total;
   // bf16 tensor-core path
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_out, map_res;
   vsb::IgemmParams params;
   size_t smem_bytes;
   unsigned grid;
@@ -403,18 +485,26 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   const int total_chunks = taps * cin_chunks;
   int cps = 64 / kchunk;
   if (cps > total_chunks) cps = total_chunks;
-  const int stage_bytes = cps * (kBlockM + block_n) * kchunk * 2;
+  const int stage_bytes = (cps * (kBlockM + block_n) * kchunk * 2 + 1023) & ~1023;
+  const int epi_n = block_n >= 64 ? 64 : block_n;
+  if (block_n % epi_n) FAIL(VSB_ERR_INVALID, "block_n %d is not a multiple of the epilogue chunk %d", block_n, epi_n);
+  const int epi_bytes = 2 * kBlockM * epi_n * 2;
+  const int num_kstages = ceil_div(total_chunks, cps);
+  uint32_t tmem_cols = 32;  // two accumulators; TMEM allocations are powers of two >= 32 columns
+  while (tmem_cols < (uint32_t)(2 * block_n)) tmem_cols <<= 1;
+  const int fixed_bytes = epi_bytes + (2 * 16 + 8) * 8 + 1024;
   int stages = d->stages;
   if (!stages) {
-    const int small_budget = 110 * 1024;  // 2 CTAs / SM
-    if (4 * stage_bytes <= small_budget) stages = 4;
-    else if (3 * stage_bytes <= small_budget) stages = 3;
-    else stages = 4;
+    // 512 TMEM columns => one CTA per SM anyway: use the whole shared memory; otherwise leave room for two
+    const int budget = (tmem_cols == 512 ? 227 : 113) * 1024 - fixed_bytes;
+    stages = budget / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = (227 * 1024 - fixed_bytes) / stage_bytes;
   }
-  const int num_kstages = ceil_div(total_chunks, cps);
-  if (stages > num_kstages) stages = num_kstages;
-  if (stages < 1) stages = 1;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  if (stages > 16) stages = 16;
+  if (stages > num_kstages * 2) stages = num_kstages * 2 > 0 ? num_kstages * 2 : 1;
+  if (stages < 1) FAIL(VSB_ERR_INVALID, "one pipeline stage (%d bytes) does not fit in shared memory", stage_bytes);
+  const size_t smem_bytes = (size_t)stages * stage_bytes + fixed_bytes;
   if (smem_bytes > 227 * 1024) FAIL(VSB_ERR_INVALID, "pipeline needs %zu bytes of shared memory", smem_bytes);
 
   int rc = load_driver_entry_points();
@@ -436,6 +526,23 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
     delete plan;
     return rc;
   }
+  // output / residual tiles move through TMA too: [m_total rows, cout cols], row pitch in bytes
+  const CUtensorMapSwizzle epi_swz = swizzle_for(epi_n * 2);
+  rc = encode_tiled_2d(&plan->map_out, d->out, d->cout, m_total, (long long)d->out_pitch * 2, epi_n, kBlockM, epi_swz);
+  if (rc != VSB_OK) {
+    delete plan;
+    return rc;
+  }
+  if (d->residual) {
+    rc = encode_tiled_2d(&plan->map_res, d->residual, d->cout, m_total, (long long)d->res_pitch * 2, epi_n, kBlockM,
+                         epi_swz);
+    if (rc != VSB_OK) {
+      delete plan;
+      return rc;
+    }
+  } else {
+    plan->map_res = plan->map_out;
+  }
 #undef FAIL
 
   IgemmParams& p = plan->params;
@@ -446,17 +553,28 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   p.kh = d->kh; p.kw = d->kw;
   p.cin = d->cin; p.cin_chunks = cin_chunks; p.total_chunks = total_chunks; p.cps = cps; p.kchunk = kchunk;
   p.block_n = block_n; p.n_tiles = d->cout / block_n; p.stages = stages;
+  p.total_tiles = (int)(ceil_div_ll(m_total, kBlockM) * p.n_tiles);
+  p.epi_n = epi_n; p.epi_chunks = block_n / epi_n;
   p.idesc = umma_idesc_bf16(kBlockM, block_n);
-  p.tmem_cols = 32;  // TMEM allocations are powers of two >= 32 columns
-  while (p.tmem_cols < (uint32_t)block_n) p.tmem_cols <<= 1;
+  p.tmem_cols = tmem_cols;
   p.scale = d->scale; p.bias = d->bias;
-  p.residual = static_cast<const __nv_bfloat16*>(d->residual);
-  p.res_pitch = d->res_pitch;
-  p.out = static_cast<__nv_bfloat16*>(d->out);
-  p.out_pitch = d->out_pitch;
+  p.has_residual = d->residual != nullptr;
   p.relu = d->relu;
   plan->smem_bytes = smem_bytes;
-  plan->grid = (unsigned)(ceil_div_ll(m_total, kBlockM) * p.n_tiles);
+  int ctas_per_sm = (int)(512 / tmem_cols);
+  const int by_smem = (int)((227 * 1024) / smem_bytes);
+  if (ctas_per_sm > by_smem) ctas_per_sm = by_smem;
+  if (ctas_per_sm > 2) ctas_per_sm = 2;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    (void)cudaGetLastError();
+  }
+  long long grid = (long long)sms * ctas_per_sm;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  plan->grid = (unsigned)grid;
   plan->desc.block_n = block_n;
   plan->desc.kchunk = kchunk;
   plan->desc.stages = stages;
@@ -479,7 +597,8 @@ extern "C" int vsb_conv3d_run(const vsb_conv_plan* plan, void* stream) {
   VSB_CHECK_ARG(plan, "null plan");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (plan->desc.dtype == VSB_F32) return launch_conv_simt(plan->desc, plan->to, plan->ho, plan->wo, s);
-  conv_igemm_kernel<<<plan->grid, kThreads, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->params);
+  conv_igemm_kernel<<<plan->grid, kThreads, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_out,
+                                                                    plan->map_res, plan->params);
   VSB_CHECK_LAUNCH("conv_igemm_kernel");
   return VSB_OK;
 }
