@@ -54,13 +54,15 @@ uint64_t vsb_launch_count(void);
  * Replaces utils/video_utils.py:147-164 (tensor_normalize: x/255, -mean, /std)
  * + dat_loader.py:483 (permute to CTHW) + utils/video_utils.py:41-74
  * (pack_pathway_output: temporal index_select for the slow pathway).
- * frames: uint8 [n, t_in, h, w, 3]; out: [n, t_out, h, w, c_pad] with
- * out[.., t, .., c] = (frames[.., idx[t], .., c'] / 255 - mean[c]) / std[c],
+ * frames: uint8 [n, t_in, h, w, 3]; out: [n, t_out, h, out_w, c_pad] with
+ * out[.., t, y, x_off + x, c] = (frames[.., idx[t], y, x, c'] / 255 - mean[c]) / std[c],
  * c' = 2-c if reverse_channels else c; channels 3..c_pad-1 are written as 0.
+ * out_w >= x_off + w lets the caller keep zero columns around each row (the stem's
+ * halo, so the stem conv needs no W padding); those columns are never written.
  * idx is a HOST array of t_out frame indices (t_out <= 64).                 */
 int vsb_pack_frames(const uint8_t* frames, int n, int t_in, int h, int w, const int* idx, int t_out,
-                    const float* mean3, const float* std3, int reverse_channels, void* out, int c_pad, int dtype,
-                    void* stream);
+                    const float* mean3, const float* std3, int reverse_channels, void* out, int c_pad, int out_w,
+                    int x_off, int dtype, void* stream);
 
 /* ------------------------------------------------------------------ conv
  * Replaces nn.Conv3d(bias=False) + eval-mode nn.BatchNorm3d (+ nn.ReLU)
@@ -144,9 +146,10 @@ int vsb_nthwc_to_ncthw_f32(const void* in, int n, int thw, int c, int in_pitch, 
 
 /* NCTHW fp32 (the reference's already-normalised clip tensors,
  * vidsitu_code/mdl_sf_base.py:169-180) -> NTHWC with the c <= 3 planes packed into
- * c_pad == 4 channels (channel 3 = 0), bf16 or fp32.                          */
-int vsb_ncthw_f32_to_nthwc(const float* in, int n, int c, long long thw, void* out, int c_pad, int dtype,
-                           void* stream);
+ * c_pad == 4 channels (channel 3 = 0), bf16 or fp32; rows of w pixels are written at
+ * pixel offset x_off of output rows of out_w pixels (see vsb_pack_frames).    */
+int vsb_ncthw_f32_to_nthwc(const float* in, int n, int c, long long thw, int w, void* out, int c_pad, int out_w,
+                           int x_off, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

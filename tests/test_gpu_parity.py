@@ -86,6 +86,18 @@ def test_stem_quad_view(kt, cout):
     assert info["ok"], info
 
 
+def _group_cases():
+    import gpu_check_ops as G
+    return G.GROUP_CASES
+
+
+@pytest.mark.parametrize("case", _group_cases(), ids=lambda c: c[0])
+def test_pixel_group_restatement(case):
+    import gpu_check_ops as G
+    info = G.run_group_case(*case)
+    assert info["ok"], info
+
+
 def test_memory_bound_ops():
     import gpu_check_ops as G
     res = G.run_mem_checks()

@@ -27,7 +27,7 @@ import torch.nn.functional as F
 from vidsitu_b200 import lib as L
 from vidsitu_b200 import ops
 from vidsitu_b200.ops import Act, ConvPlan
-from vidsitu_b200.weights import pack_conv_weight, stem_quad_weight
+from vidsitu_b200.weights import group_conv_weight, pack_conv_weight, stem_quad_weight
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -177,6 +177,60 @@ def run_stem_case(kt, cout, dtype=L.VSB_BF16):
     return info
 
 
+def run_group_case(name, cin, cout, k, s, p, J, W, cin_store, cout_store, shift=0, wbuf=None, use_res=False):
+    """Pixel-group restatement (weights.group_conv_weight) through the tensor-core kernel vs the plain conv."""
+    dev = "cuda"
+    n, t, h = 2, 4, 12
+    g = torch.Generator(device="cpu").manual_seed(zlib.crc32(name.encode()) % (2 ** 31))
+    wb = wbuf or W
+    x = torch.randn((n, t, h, W, cin), generator=g).to(torch.bfloat16)
+    xs = torch.zeros((n, t, h, wb, cin_store), dtype=torch.bfloat16)
+    xs[:, :, :, shift:shift + W, :cin] = x
+    xs = xs.to(dev)
+    fan_in = cin * k[0] * k[1] * k[2]
+    wt = (torch.randn((cout, cin) + tuple(k), generator=g) / fan_in ** 0.5).to(torch.bfloat16).to(dev)
+    scale = torch.zeros(cout_store, device=dev)
+    bias = torch.zeros(cout_store, device=dev)
+    scale[:cout] = (torch.rand(cout, generator=g) + 0.5).to(dev)
+    bias[:cout] = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    to = (t + 2 * p[0] - k[0]) // s[0] + 1
+    ho = (h + 2 * p[1] - k[1]) // s[1] + 1
+    wo = (W + 2 * p[2] - k[2]) // s[2] + 1
+    res = None
+    if use_res:
+        res = torch.zeros((n, to, ho, wo, cout_store), dtype=torch.bfloat16)
+        res[..., :cout] = torch.randn((n, to, ho, wo, cout), generator=g).to(torch.bfloat16)
+        res = res.to(dev)
+    outbuf = torch.full((n, to, ho, wo, cout_store), 7.0, dtype=torch.bfloat16, device=dev)
+    G = J * s[2]
+    wq, ngt, plo = group_conv_weight(wt.float(), cin_store, cout_store, J, s[2], p[2] - shift, torch.bfloat16)
+    xin = Act(xs, n, t, h, wb // G, G * cin_store, G * cin_store)
+    yout = Act(outbuf, n, to, ho, wo // J, J * cout_store, J * cout_store)
+    ra = Act(res, n, to, ho, wo // J, J * cout_store, J * cout_store) if use_res else None
+    phi = yout.w - 1 + ngt - xin.w - plo
+    plan = ConvPlan(L.VSB_BF16, xin, wq, J * cout_store, (k[0], k[1], ngt), (s[0], s[1], 1), (p[0], p[1], plo),
+                    (p[0], p[1], phi), scale.repeat(J), bias.repeat(J), yout, ra, True)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = _ref_conv(x.to(dev), wt, s, p, scale[:cout], bias[:cout], res[..., :cout] if use_res else None, True)
+    info = _compare(outbuf[..., :cout], ref, atol=2e-2, rtol=1.6e-2)
+    info["pad_zero"] = bool((outbuf[..., cout:] == 0).all())
+    info["ok"] = info["n_bad"] == 0 and info["finite"] and info["pad_zero"]
+    return info
+
+
+GROUP_CASES = [
+    ("g_sp3_8_8_J4", 8, 8, (1, 3, 3), (1, 1, 1), (0, 1, 1), 4, 56, 16, 16, 0, None, False),
+    ("g_sp3_s2_16_J4", 16, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1), 4, 56, 16, 16, 0, None, False),
+    ("g_pw_8_32_J4_res", 8, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0), 4, 28, 16, 32, 0, None, True),
+    ("g_tm3_32_8_J2", 32, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0), 2, 28, 32, 16, 0, None, False),
+    ("g_pw_s2_32_64_J2", 32, 64, (1, 1, 1), (1, 2, 2), (0, 0, 0), 2, 56, 32, 64, 0, None, False),
+    ("g_stem_fast_J8", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 8, 64, 4, 8, 3, 80, False),
+    ("g_stem_slow_J4", 3, 64, (1, 7, 7), (1, 2, 2), (0, 3, 3), 4, 64, 4, 64, 3, 80, False),
+    ("g_stem_fast_J8_224", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 8, 224, 4, 8, 3, 240, False),
+]
+
+
 def run_probe():
     """Dump raw im2col loads of an index-valued tensor so the traversal can be read offline."""
     import ctypes as C
@@ -239,6 +293,14 @@ def run_mem_checks():
             else:
                 ok = bool(torch.equal(out, ref.to(torch.bfloat16)))
                 res[f"pack_bf16_rev{int(rev)}"] = {"ok": ok, "max_abs_err": float((out.float() - ref).abs().max())}
+    # ---- pack into zero-bordered rows (x_off = 3, row of w + 16 pixels)
+    out = torch.zeros((n, len(idx), h, w + 16, 4), dtype=torch.bfloat16, device=dev)
+    ops.pack_frames(frames, idx, mean, std, Act(out, n, len(idx), h, w + 16, 4, 4), L.VSB_BF16, False, 3)
+    torch.cuda.synchronize()
+    xc = (frames[:, idx].cpu().float() / 255.0 - torch.tensor(mean)) / torch.tensor(std)
+    ref = torch.zeros((n, len(idx), h, w + 16, 4))
+    ref[:, :, :, 3:3 + w, :3] = xc
+    res["pack_bf16_bordered"] = {"ok": bool(torch.equal(out.cpu(), ref.to(torch.bfloat16)))}
     # ---- ncthw -> nthwc4
     xin = torch.randn((2, 3, 4, 8, 8), generator=g).to(dev)
     out = torch.empty((2, 4, 8, 8, 4), dtype=torch.float32, device=dev)
@@ -345,6 +407,14 @@ def child(args):
                 save()
                 report["conv_bf16"][case[0]] = run_conv_case(case, L.VSB_BF16)
                 save()
+            report.setdefault("group", {})
+            for gc in GROUP_CASES:
+                if gc[0] in report["group"]:
+                    continue
+                report["group"][gc[0]] = {"ok": False, "crashed": True}
+                save()
+                report["group"][gc[0]] = run_group_case(*gc)
+                save()
             for kt, cout in ((1, 64), (5, 8), (5, 64)):
                 key = f"stem_kt{kt}_c{cout}"
                 if key in report["stem"]:
@@ -387,7 +457,7 @@ def main():
         time.sleep(1)
     report = json.load(open(args.out)) if os.path.exists(args.out) else {}
     n_ok = n_bad = 0
-    for sec in ("mem", "conv_f32", "conv_bf16", "stem"):
+    for sec in ("mem", "conv_f32", "conv_bf16", "stem", "group"):
         for k, v in report.get(sec, {}).items():
             ok = bool(v.get("ok"))
             n_ok += ok

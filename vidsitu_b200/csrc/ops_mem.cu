@@ -40,8 +40,8 @@ __device__ __forceinline__ void store_px4<__nv_bfloat16>(__nv_bfloat16* dst, flo
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 pack_frames_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, int n, int t_in, int t_out,
-                   long long frame_px, PackIdx idx, float m0, float m1, float m2, float s0, float s1, float s2,
-                   int reverse) {
+                   long long frame_px, int w, int out_w, int x_off, PackIdx idx, float m0, float m1, float m2,
+                   float s0, float s1, float s2, int reverse) {
   __shared__ float lut[3][256];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) {
     const int c = i >> 8, x = i & 255;
@@ -66,7 +66,12 @@ pack_frames_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, i
     const uint4 b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
     const uint4 c = __ldg(reinterpret_cast<const uint4*>(src) + 2);
     const uint32_t wds[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-    OutT* dst = out + ((clip * t_out + to) * frame_px + unit * 16) * 4;
+    // output rows may be wider than the frame (zero columns the conv halo reads): w % 16 == 0, so the
+    // 16 pixels of a unit stay inside one row
+    const long long px0 = unit * 16;
+    const long long y = px0 / w, x = px0 - y * w;
+    const long long h = frame_px / w;
+    OutT* dst = out + (((clip * t_out + to) * h + y) * out_w + x_off + x) * 4;
 #pragma unroll
     for (int px = 0; px < 16; ++px) {
       uint32_t ch[3];
@@ -294,7 +299,8 @@ nthwc_to_ncthw_kernel(const T* __restrict__ in, float* __restrict__ out, int thw
 // c (<= 4) planes and writes one zero-padded 4-channel pixel.
 template <typename OutT>
 __global__ void __launch_bounds__(256)
-ncthw_to_nthwc4_kernel(const float* __restrict__ in, OutT* __restrict__ out, long long n, int c, long long thw) {
+ncthw_to_nthwc4_kernel(const float* __restrict__ in, OutT* __restrict__ out, long long n, int c, long long thw,
+                       int w, int out_w, int x_off) {
   const long long total = n * thw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -303,7 +309,8 @@ ncthw_to_nthwc4_kernel(const float* __restrict__ in, OutT* __restrict__ out, lon
     const float r = src[0];
     const float g = c > 1 ? src[thw] : 0.f;
     const float b = c > 2 ? src[2 * thw] : 0.f;
-    store_px4<OutT>(out + i * 4, r, g, b);
+    const long long row = i / w, x = i - row * w;
+    store_px4<OutT>(out + (row * out_w + x_off + x) * 4, r, g, b);
   }
 }
 
@@ -321,13 +328,14 @@ using namespace vsb;
 
 extern "C" int vsb_pack_frames(const uint8_t* frames, int n, int t_in, int h, int w, const int* idx, int t_out,
                                const float* mean3, const float* std3, int reverse_channels, void* out, int c_pad,
-                               int dtype, void* stream) {
+                               int out_w, int x_off, int dtype, void* stream) {
   VSB_CHECK_ARG(frames && idx && mean3 && std3 && out, "null argument");
   VSB_CHECK_ARG(n > 0 && t_in > 0 && h > 0 && w > 0 && t_out > 0 && t_out <= 64, "bad extent (t_out <= 64)");
   VSB_CHECK_ARG(c_pad == 4, "pack writes 4 channels per pixel (c_pad == 4)");
   VSB_CHECK_ARG(dtype == VSB_BF16 || dtype == VSB_F32, "bad dtype");
   const long long frame_px = (long long)h * w;
-  VSB_CHECK_ARG(frame_px % 16 == 0, "h*w must be a multiple of 16 for the 128-bit loads");
+  VSB_CHECK_ARG(w % 16 == 0, "w must be a multiple of 16 for the 128-bit loads");
+  VSB_CHECK_ARG(x_off >= 0 && out_w >= w + x_off, "output row (%d pixels) cannot hold %d + %d", out_w, x_off, w);
   VSB_CHECK_ARG((reinterpret_cast<uintptr_t>(frames) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "frames/out must be 16-byte aligned");
   PackIdx pi;
@@ -341,11 +349,11 @@ extern "C" int vsb_pack_frames(const uint8_t* frames, int n, int t_in, int h, in
   const unsigned grid = grid_for(total, 256);
   if (dtype == VSB_BF16) {
     pack_frames_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(frames, static_cast<__nv_bfloat16*>(out), n, t_in, t_out,
-                                                          frame_px, pi, mean3[0], mean3[1], mean3[2], std3[0],
-                                                          std3[1], std3[2], reverse_channels);
+                                                          frame_px, w, out_w, x_off, pi, mean3[0], mean3[1], mean3[2],
+                                                          std3[0], std3[1], std3[2], reverse_channels);
   } else {
-    pack_frames_kernel<float><<<grid, 256, 0, s>>>(frames, static_cast<float*>(out), n, t_in, t_out, frame_px, pi,
-                                                   mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2],
+    pack_frames_kernel<float><<<grid, 256, 0, s>>>(frames, static_cast<float*>(out), n, t_in, t_out, frame_px, w, out_w,
+                                                   x_off, pi, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2],
                                                    reverse_channels);
   }
   VSB_CHECK_LAUNCH("pack_frames_kernel");
@@ -431,18 +439,20 @@ extern "C" int vsb_nthwc_to_ncthw_f32(const void* in, int n, int thw, int c, int
   return VSB_OK;
 }
 
-extern "C" int vsb_ncthw_f32_to_nthwc(const float* in, int n, int c, long long thw, void* out, int c_pad, int dtype,
-                                      void* stream) {
+extern "C" int vsb_ncthw_f32_to_nthwc(const float* in, int n, int c, long long thw, int w, void* out, int c_pad,
+                                      int out_w, int x_off, int dtype, void* stream) {
   VSB_CHECK_ARG(in && out, "null argument");
   VSB_CHECK_ARG(dtype == VSB_BF16 || dtype == VSB_F32, "bad dtype");
   VSB_CHECK_ARG(n > 0 && thw > 0 && c >= 1 && c <= 3 && c_pad == 4, "supports c <= 3 packed into c_pad == 4");
+  VSB_CHECK_ARG(w > 0 && thw % w == 0 && x_off >= 0 && out_w >= w + x_off, "bad row geometry");
   VSB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = grid_for((long long)n * thw, 256);
   if (dtype == VSB_BF16)
-    ncthw_to_nthwc4_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(in, static_cast<__nv_bfloat16*>(out), n, c, thw);
+    ncthw_to_nthwc4_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(in, static_cast<__nv_bfloat16*>(out), n, c, thw, w,
+                                                              out_w, x_off);
   else
-    ncthw_to_nthwc4_kernel<float><<<grid, 256, 0, s>>>(in, static_cast<float*>(out), n, c, thw);
+    ncthw_to_nthwc4_kernel<float><<<grid, 256, 0, s>>>(in, static_cast<float*>(out), n, c, thw, w, out_w, x_off);
   VSB_CHECK_LAUNCH("ncthw_to_nthwc4_kernel");
   return VSB_OK;
 }

@@ -25,7 +25,7 @@ from . import ops
 from .arch import BlockSpec, ConvSpec, NetSpec, NonlocalSpec
 from .lib import VSB_BF16, VSB_F32, VsbError
 from .ops import Act, ConvPlan
-from .weights import fold_bn, identity_affine, pack_conv_weight, round_up, stem_quad_weight
+from .weights import fold_bn, group_conv_weight, identity_affine, pack_conv_weight, round_up
 
 
 class _Pool:
@@ -74,14 +74,19 @@ class ClipEngine:
         self._pool = _Pool(self.device, self.tdt)
         self._graph = None
         self.crop = spec.crop
-        if self.crop % 4 or (self.crop * self.crop) % 16:
-            raise VsbError("crop size must be a multiple of 4")
+        if self.crop % 16:
+            raise VsbError("crop size must be a multiple of 16")
         frames = spec.pathway_frames()
-        # ---- inputs
+        # ---- inputs: 4 channels per pixel.  On the tensor-core path every row carries its own zero
+        # border (3 pixels left = the stem's W padding, 13 right), so the stem conv runs on 16-pixel
+        # groups without any W padding (weights.group_conv_weight); the border is zeroed once here and
+        # never written again.
+        self.x_off = 3 if dtype == VSB_BF16 else 0
+        self.w_buf = self.crop + 16 if dtype == VSB_BF16 else self.crop
         self.inputs: List[Act] = []
         for t in frames:
-            buf = torch.zeros(self.n * t * self.crop * self.crop * 4, dtype=self.tdt, device=self.device)
-            self.inputs.append(Act(buf, self.n, t, self.crop, self.crop, 4, 4, c_real=3))
+            buf = torch.zeros(self.n * t * self.crop * self.w_buf * 4, dtype=self.tdt, device=self.device)
+            self.inputs.append(Act(buf, self.n, t, self.crop, self.w_buf, 4, 4, c_real=3))
         # slow-pathway temporal indices, exactly as utils/video_utils.py:62-69
         t_fast = spec.num_frames
         self.fast_idx = list(range(t_fast))
@@ -142,15 +147,49 @@ class ClipEngine:
         wo = (x.w + 2 * cs.pad[2] - cs.kernel[2]) // cs.stride[2] + 1
         return to, ho, wo
 
+    def _tune(self, key: str) -> dict:
+        tune = dict(self.tune.get("*", {}))
+        tune.update(self.tune.get(key, {}))
+        return tune
+
+    def _group_factor(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act]) -> int:
+        """Pixels per GEMM row (weights.group_conv_weight): thin-channel layers are re-viewed so that
+        one im2col row is >= 128 bytes."""
+        if self.dtype != VSB_BF16 or x.c >= 64:
+            return 1
+        dense = lambda a: a is None or (a.pitch == a.c and a.c_off == 0)
+        if not (dense(x) and dense(out) and dense(residual)):
+            return 1
+        j = self._tune(cs.key).get("group", 64 // x.c)
+        sw = cs.stride[2]
+        while j > 1 and (out.w % j or x.w % (j * sw) or out.w // j != x.w // (j * sw)):
+            j //= 2
+        return max(j, 1)
+
     def _conv(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act] = None, relu: Optional[bool] = None):
         if x.c_real != cs.cin:
             raise VsbError(f"{cs.key}: input has {x.c_real} channels, conv expects {cs.cin}")
-        w = pack_conv_weight(self._tensor(cs.key + ".weight"), x.c, out.c, self.tdt)
         scale, bias = self._affine(cs, out.c)
-        tune = dict(self.tune.get("*", {}))
-        tune.update(self.tune.get(cs.key, {}))
-        plan = ConvPlan(self.dtype, x, w, out.c, cs.kernel, cs.stride, cs.pad, None, scale, bias, out, residual,
-                        cs.relu if relu is None else relu, **tune)
+        tune = {k: v for k, v in self._tune(cs.key).items() if k in ("block_n", "kchunk", "stages")}
+        relu = cs.relu if relu is None else relu
+        wt = self._tensor(cs.key + ".weight")
+        j = self._group_factor(cs, x, out, residual)
+        if j > 1:
+            sw = cs.stride[2]
+            g = j * sw
+            w, ngt, plo = group_conv_weight(wt, x.c, out.c, j, sw, cs.pad[2], self.tdt)
+            xin = Act(x.buf, x.n, x.t, x.h, x.w // g, g * x.c, g * x.c)
+            yout = Act(out.buf, out.n, out.t, out.h, out.w // j, j * out.c, j * out.c)
+            res = None if residual is None else Act(residual.buf, out.n, out.t, out.h, out.w // j, j * out.c,
+                                                    j * out.c)
+            phi = yout.w - 1 + ngt - xin.w - plo
+            plan = ConvPlan(self.dtype, xin, w, j * out.c, (cs.kernel[0], cs.kernel[1], ngt),
+                            (cs.stride[0], cs.stride[1], 1), (cs.pad[0], cs.pad[1], plo), (cs.pad[0], cs.pad[1], phi),
+                            scale.repeat(j), bias.repeat(j), yout, res, relu, **tune)
+        else:
+            w = pack_conv_weight(wt, x.c, out.c, self.tdt)
+            plan = ConvPlan(self.dtype, x, w, out.c, cs.kernel, cs.stride, cs.pad, None, scale, bias, out, residual,
+                            relu, **tune)
         self._keep.append(plan)
         m = out.pixels
         self.trunk_ops.append((cs.key, plan.run, float(m) * cs.flops_per_out_pixel))
@@ -159,22 +198,31 @@ class ClipEngine:
         st = self.spec.stems[p]
         cs = st.conv
         n, t = x.n, x.t
-        to, ho, wo = self._out_dims(Act(None, n, t, x.h, x.w, 4, 4), cs)
+        to, ho, wo = self._out_dims(Act(None, n, t, self.crop, self.crop, 4, 4), cs)
         y = self._alloc(n, to, ho, wo, cs.cout, pitch=cs.cout)   # dense [.., cout] (no channel padding yet)
         y.c = cs.cout
         scale, bias = self._affine(cs, cs.cout)
         wt = self._tensor(cs.key + ".weight")
+        tune = {k: v for k, v in self._tune(cs.key).items() if k in ("block_n", "kchunk", "stages")}
         if self.dtype == VSB_BF16:
-            # quad view (weights.stem_quad_weight): cin'=16, cout'=2*cout, kernel (kt,7,3), stride (1,2,1)
-            if cs.kernel[1:] != (7, 7) or cs.stride != (1, 2, 2) or cs.pad[1:] != (3, 3) or (2 * cs.cout) % 16:
-                raise VsbError("stem geometry outside the quad-view restatement")
-            wq = stem_quad_weight(wt, self.tdt)
-            xin = Act(x.buf, n, t, x.h, x.w // 4, 16, 16)
-            yout = Act(y.buf, n, to, ho, wo // 2, 2 * cs.cout, 2 * cs.cout)
-            tune = dict(self.tune.get("*", {}))
-            tune.update(self.tune.get(cs.key, {}))
-            plan = ConvPlan(self.dtype, xin, wq, 2 * cs.cout, (cs.kernel[0], 7, 3), (1, 2, 1), (cs.pad[0], 3, 1),
-                            None, torch.cat([scale, scale]), torch.cat([bias, bias]), yout, None, True, **tune)
+            # J output pixels per GEMM row on the zero-bordered input rows (x' = x + x_off, so the
+            # conv needs no W padding): cin' = 2J*4, cout' = J*cout, kernel (kt,7,ngt), stride (1,2,1)
+            sw = cs.stride[2]
+            j = self._tune(cs.key).get("group", 8 if cs.cout * 8 <= 64 else 4)
+            while j > 1 and (wo % j or self.w_buf % (j * sw) or (j * cs.cout) % 16):
+                j //= 2
+            g = j * sw
+            if (j * cs.cout) % 16 or self.w_buf % g or g * 4 < 16:
+                raise VsbError("stem geometry outside the pixel-group restatement")
+            wq, ngt, plo = group_conv_weight(wt, 4, cs.cout, j, sw, cs.pad[2] - self.x_off, self.tdt)
+            xin = Act(x.buf, n, t, x.h, self.w_buf // g, g * 4, g * 4)
+            yout = Act(y.buf, n, to, ho, wo // j, j * cs.cout, j * cs.cout)
+            phi = yout.w - 1 + ngt - xin.w - plo
+            if plo < 0 or xin.w + plo + phi - ngt + 1 != yout.w:
+                raise VsbError("stem pixel-group geometry does not close")
+            plan = ConvPlan(self.dtype, xin, wq, j * cs.cout, (cs.kernel[0], cs.kernel[1], ngt),
+                            (cs.stride[0], cs.stride[1], 1), (cs.pad[0], cs.pad[1], plo),
+                            (cs.pad[0], cs.pad[1], phi), scale.repeat(j), bias.repeat(j), yout, None, True, **tune)
         else:
             wp = pack_conv_weight(wt, 4, cs.cout, self.tdt)
             plan = ConvPlan(self.dtype, x, wp, cs.cout, cs.kernel, cs.stride, cs.pad, None, scale, bias, y, None,
@@ -306,21 +354,21 @@ class ClipEngine:
             raise VsbError(f"expected frames [{self.n}, {spec.num_frames}, {self.crop}, {self.crop}, 3]")
         if spec.num_pathways == 2:
             ops.pack_frames(frames, self.slow_idx, spec.mean, spec.std, self.inputs[0], self.dtype,
-                            spec.reverse_input_channel)
+                            spec.reverse_input_channel, self.x_off)
             ops.pack_frames(frames, self.fast_idx, spec.mean, spec.std, self.inputs[1], self.dtype,
-                            spec.reverse_input_channel)
+                            spec.reverse_input_channel, self.x_off)
         else:
             ops.pack_frames(frames, self.fast_idx, spec.mean, spec.std, self.inputs[0], self.dtype,
-                            spec.reverse_input_channel)
+                            spec.reverse_input_channel, self.x_off)
 
     def load_ncthw(self, xs: Sequence[torch.Tensor]) -> None:
         """The reference's already-normalised fp32 [n, 3, T_p, H, W] pathway tensors."""
         if len(xs) != len(self.inputs):
             raise VsbError(f"expected {len(self.inputs)} pathway tensors")
         for x, a in zip(xs, self.inputs):
-            if tuple(x.shape) != (self.n, 3, a.t, a.h, a.w):
-                raise VsbError(f"pathway tensor {tuple(x.shape)} != {(self.n, 3, a.t, a.h, a.w)}")
-            ops.ncthw_to_act(x.contiguous(), a, self.dtype)
+            if tuple(x.shape) != (self.n, 3, a.t, a.h, self.crop):
+                raise VsbError(f"pathway tensor {tuple(x.shape)} != {(self.n, 3, a.t, a.h, self.crop)}")
+            ops.ncthw_to_act(x.contiguous(), a, self.dtype, self.x_off)
 
     def run_trunk(self) -> None:
         for _, fn, _ in self.trunk_ops:

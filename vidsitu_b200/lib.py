@@ -66,7 +66,7 @@ def load() -> C.CDLL:
     lib.vsb_last_error.restype = C.c_char_p
     lib.vsb_launch_count.restype = C.c_uint64
     lib.vsb_pack_frames.argtypes = [vp, i, i, i, i, C.POINTER(C.c_int), i, C.POINTER(C.c_float),
-                                    C.POINTER(C.c_float), i, vp, i, i, vp]
+                                    C.POINTER(C.c_float), i, vp, i, i, i, i, vp]
     lib.vsb_conv3d_plan_create.argtypes = [C.POINTER(ConvDesc), C.POINTER(vp)]
     lib.vsb_conv3d_run.argtypes = [vp, vp]
     lib.vsb_conv3d_plan_destroy.argtypes = [vp]
@@ -79,7 +79,7 @@ def load() -> C.CDLL:
     lib.vsb_linear.argtypes = [f32p, i, i, f32p, f32p, f32p, i, i, vp]
     lib.vsb_nonlocal_attention.argtypes = [vp, i, vp, i, vp, i, vp, i, i, i, i, i, i, i, vp]
     lib.vsb_nthwc_to_ncthw_f32.argtypes = [vp, i, i, i, i, f32p, i, vp]
-    lib.vsb_ncthw_f32_to_nthwc.argtypes = [f32p, i, i, ll, vp, i, i, vp]
+    lib.vsb_ncthw_f32_to_nthwc.argtypes = [f32p, i, i, ll, i, vp, i, i, i, i, vp]
     lib.vsb_debug_im2col_probe.argtypes = [vp] + [i] * 25 + [vp, vp]
     for name in ("vsb_pack_frames", "vsb_conv3d_plan_create", "vsb_conv3d_run", "vsb_conv3d_plan_out_shape",
                  "vsb_maxpool3d", "vsb_global_avgpool", "vsb_linear", "vsb_nonlocal_attention",

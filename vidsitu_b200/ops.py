@@ -117,31 +117,33 @@ class ConvPlan:
 
 
 def pack_frames(frames: torch.Tensor, idx: Sequence[int], mean: Sequence[float], std: Sequence[float],
-                out: Act, dtype: int, reverse_channels: bool = False) -> None:
-    """frames uint8 [n, t_in, h, w, 3] -> out [n, len(idx), h, w, 4] (normalised, temporally subsampled)."""
+                out: Act, dtype: int, reverse_channels: bool = False, x_off: int = 0) -> None:
+    """frames uint8 [n, t_in, h, w, 3] -> out [n, len(idx), h, out.w, 4] (normalised, temporally subsampled),
+    frame columns written at pixel offset x_off of each (possibly wider, zero-bordered) output row."""
     _require_cuda(frames, out.buf)
     if frames.dtype != torch.uint8 or frames.dim() != 5 or frames.shape[-1] != 3 or not frames.is_contiguous():
         raise VsbError("frames must be a contiguous uint8 [n, t, h, w, 3] tensor")
     n, t_in, h, w, _ = frames.shape
-    if (out.n, out.t, out.h, out.w, out.pitch, out.c_off) != (n, len(idx), h, w, 4, 0):
-        raise VsbError("pack output must be a dense [n, len(idx), h, w, 4] activation")
+    if (out.n, out.t, out.h, out.pitch, out.c_off) != (n, len(idx), h, 4, 0) or out.w < w + x_off:
+        raise VsbError("pack output must be a dense [n, len(idx), h, >= w + x_off, 4] activation")
     idx_arr = (C.c_int * len(idx))(*[int(i) for i in idx])
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
     check(_l.load().vsb_pack_frames(frames.data_ptr(), n, t_in, h, w, idx_arr, len(idx), m, s,
-                                    int(reverse_channels), out.ptr, 4, dtype, _stream_ptr()), "vsb_pack_frames")
+                                    int(reverse_channels), out.ptr, 4, out.w, x_off, dtype, _stream_ptr()),
+          "vsb_pack_frames")
 
 
-def ncthw_to_act(x: torch.Tensor, out: Act, dtype: int) -> None:
+def ncthw_to_act(x: torch.Tensor, out: Act, dtype: int, x_off: int = 0) -> None:
     """fp32 NCTHW clip tensor (reference layout) -> 4-channel NTHWC activation."""
     _require_cuda(x, out.buf)
     if x.dtype != torch.float32 or x.dim() != 5 or not x.is_contiguous():
         raise VsbError("expected a contiguous float32 [n, c, t, h, w] tensor")
     n, c, t, h, w = x.shape
-    if (out.n, out.t, out.h, out.w, out.pitch) != (n, t, h, w, 4):
-        raise VsbError("output activation must be dense [n, t, h, w, 4]")
-    check(_l.load().vsb_ncthw_f32_to_nthwc(x.data_ptr(), n, c, t * h * w, out.ptr, 4, dtype, _stream_ptr()),
-          "vsb_ncthw_f32_to_nthwc")
+    if (out.n, out.t, out.h, out.pitch) != (n, t, h, 4) or out.w < w + x_off:
+        raise VsbError("output activation must be dense [n, t, h, >= w + x_off, 4]")
+    check(_l.load().vsb_ncthw_f32_to_nthwc(x.data_ptr(), n, c, t * h * w, w, out.ptr, 4, out.w, x_off, dtype,
+                                           _stream_ptr()), "vsb_ncthw_f32_to_nthwc")
 
 
 def maxpool3d(x: Act, out: Act, kernel, stride, pad, dtype: int) -> None:

@@ -70,3 +70,34 @@ def stem_quad_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
             qt, r = pos // 4, pos % 4
             out[p, :, :, :, qt, r, :cin] = w[:, :, :, :, k].permute(0, 2, 3, 1)
     return out.reshape(2 * cout, kt * kh * 3, 16).to(dtype).contiguous()
+
+
+def group_conv_weight(w: torch.Tensor, cin_store: int, cout_store: int, J: int, stride_w: int, pad_w: int,
+                      dtype: torch.dtype):
+    """Restate a conv along W on "pixel groups": J neighbouring output pixels become one GEMM row
+    with J*cout_store channels, G = J*stride_w neighbouring input pixels one row of G*cin_store
+    channels.  Memory is untouched -- [.., W, C] *is* [.., W/G, G*C] -- only the weights are
+    expanded (block-Toeplitz along W):
+
+        output pixel  J*j + p   reads input pixel  G*j + off,   off = p*stride_w - pad_w + kw
+        W'[p*cout_store + co, (kt, kh, gt - gmin), r*cin_store + ci] = W[co, ci, kt, kh, kw]
+        with gt = floor(off / G), r = off mod G.
+
+    Why: the im2col TMA unit issues one request per pixel row; rows of 16-32 channels (32-64 B) are
+    request-rate bound, 128 B rows are not.  The extra zero MACs are free on layers that are
+    nowhere near the tensor-pipe roofline (stems, the 8..64-channel Fast pathway).
+
+    Returns (packed [J*cout_store, kt*kh*ngt, G*cin_store], ngt, pad_lo) where the grouped conv has
+    kernel width ngt, stride 1 and leading pad pad_lo along W'."""
+    cout, cin, kt, kh, kw = w.shape
+    G = J * stride_w
+    offs = [p * stride_w - pad_w + k for p in range(J) for k in range(kw)]
+    gmin, gmax = min(offs) // G, max(offs) // G
+    ngt = gmax - gmin + 1
+    out = torch.zeros((J, cout_store, kt, kh, ngt, G, cin_store), dtype=torch.float32, device=w.device)
+    wp = w.permute(0, 2, 3, 1, 4)  # cout, kt, kh, cin, kw
+    for p in range(J):
+        for k in range(kw):
+            off = p * stride_w - pad_w + k
+            out[p, :cout, :, :, off // G - gmin, off % G, :cin] = wp[..., k]
+    return out.reshape(J * cout_store, kt * kh * ngt, G * cin_store).to(dtype).contiguous(), ngt, -gmin
