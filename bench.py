@@ -252,7 +252,8 @@ def main():
                     "step_tflops": round(flops / (ms / args.steps / 1e3) / 1e12, 2),
                     "step_frac": round(flops / (ms / args.steps / 1e3) / 1e12 / peak_sus, 4)}
         if args.per_op:
-            json.dump([{"op": n, "ms": round(m, 4), "gflop": round(f / 1e9, 3)} for n, m, f in per_op],
+            json.dump([{"op": n, "ms": round(m, 4), "gflop": round(f / 1e9, 3),
+                        "mbytes": round(eng.op_bytes.get(n, 0) / 1e6, 2)} for n, m, f in per_op],
                       open(args.per_op, "w"), indent=0)
 
     cpu_baseline = None

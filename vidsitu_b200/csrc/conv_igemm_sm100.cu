@@ -20,6 +20,8 @@
 // another's main loop.
 #include <cuda.h>  // CUtensorMap types only; entry points are fetched at run time
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <new>
 
@@ -36,6 +38,9 @@ struct IgemmParams {
   int cin, cin_chunks, total_chunks, cps, kchunk;
   int block_n, n_tiles, total_tiles, stages;
   int epi_n, epi_chunks;  // epilogue column chunk (<= 64) and chunks per tile
+  int epi_bufs;           // staging buffers of the epilogue (residual prefetch distance = epi_bufs - 1)
+  int b_resident;         // all weight chunks stay in shared memory for the CTA's lifetime (n_tiles == 1)
+  uint32_t stage_bytes, off_bres, off_epi, off_bar;  // shared-memory layout (bytes from the 1 KiB-aligned base)
   uint32_t idesc, tmem_cols;
   const float* scale;
   const float* bias;
@@ -45,6 +50,7 @@ struct IgemmParams {
 
 constexpr int kBlockM = 128;
 constexpr int kThreads = 192;
+constexpr int kMaxEpiBufs = 8;
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -64,16 +70,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t row_bytes = p.kchunk * 2;
   const uint32_t a_chunk_bytes = kBlockM * row_bytes;
   const uint32_t b_chunk_bytes = p.block_n * row_bytes;
-  const uint32_t stage_bytes = (p.cps * (a_chunk_bytes + b_chunk_bytes) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = p.stage_bytes;
   const uint32_t epi_row_bytes = p.epi_n * 2;
   const uint32_t epi_buf_bytes = kBlockM * epi_row_bytes;
-  uint8_t* epi_buf = smem + (size_t)p.stages * stage_bytes;  // 2 buffers, each a multiple of 1024 bytes
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_buf + 2 * epi_buf_bytes);
+  uint8_t* bres = smem + p.off_bres;   // resident weights (b_resident)
+  uint8_t* epi_buf = smem + p.off_epi;  // epi_bufs buffers, each a multiple of 1024 bytes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* epi_ready = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_ready + 2);
+  uint64_t* bres_bar = epi_ready + kMaxEpiBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
@@ -90,8 +98,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
-      mbar_init(&epi_ready[i], 1);
     }
+    for (int i = 0; i < p.epi_bufs; ++i) mbar_init(&epi_ready[i], 1);
+    mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 5) {
@@ -107,8 +116,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   if (warp == 4) {
     if (lane == 0) {
-      // ------------------------------------------------------ TMA producer
-      int kit = 0;
+      // ------------------------------------------------------ TMA producer (one thread)
+      // The loop body is kept free of divisions: filter-tap / channel-chunk indices advance as
+      // counters, the weight K coordinate is simply chunk * kchunk.
+      if (p.b_resident) {
+        // weight-stationary: every chunk of the [block_n x K] weight matrix is loaded exactly once
+        mbar_expect_tx(bres_bar, p.total_chunks * b_chunk_bytes);
+        for (int g = 0; g < p.total_chunks; ++g)
+          tma_load_2d(bres + g * b_chunk_bytes, &map_b, bres_bar, g * p.kchunk, 0);
+      }
+      const uint32_t stage_tx = p.b_resident ? a_chunk_bytes : a_chunk_bytes + b_chunk_bytes;
+      const uint32_t b_off = p.cps * a_chunk_bytes;
+      int slot = 0;
+      uint32_t parity = 1;  // first pass over the ring: slots are free
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         const int m0 = (tile / p.n_tiles) * kBlockM;
@@ -121,60 +141,92 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int w0 = wo * p.sw + p.lw;
         const int h0 = ho * p.sh + p.lh;
         const int d0 = to_ * p.st + p.lt;
-        for (int ks = 0; ks < num_kstages; ++ks, ++kit) {
-          const int slot = kit % p.stages;
-          const uint32_t parity = ((kit / p.stages) & 1) ^ 1;
+        const int ncol = n_tile * p.block_n;
+        int cc = 0, kw_ = 0, kh_ = 0, kt_ = 0, kcoord = 0;
+        int left = p.total_chunks;
+        while (left > 0) {
+          const int nch = left < p.cps ? left : p.cps;
+          left -= nch;
           mbar_wait(&empty_bar[slot], parity);
-          const int g0 = ks * p.cps;
-          const int nch = min(p.cps, p.total_chunks - g0);
-          mbar_expect_tx(&full_bar[slot], nch * (a_chunk_bytes + b_chunk_bytes));
-          uint8_t* a_dst = smem + (size_t)slot * stage_bytes;
-          uint8_t* b_dst = a_dst + p.cps * a_chunk_bytes;
+          mbar_expect_tx(&full_bar[slot], nch * stage_tx);
+          uint8_t* a_dst = smem + (uint32_t)slot * stage_bytes;
+          uint8_t* b_dst = a_dst + b_off;
           for (int c = 0; c < nch; ++c) {
-            const int g = g0 + c;
-            const int tap = g / p.cin_chunks;
-            const int cc = g - tap * p.cin_chunks;
-            const int kw_ = tap % p.kw;
-            const int r = tap / p.kw;
-            const int kh_ = r % p.kh;
-            const int kt_ = r / p.kh;
-            tma_load_im2col_5d(a_dst + c * a_chunk_bytes, &map_a, &full_bar[slot], cc * p.kchunk, w0, h0, d0, n0,
-                               (uint16_t)kw_, (uint16_t)kh_, (uint16_t)kt_);
-            tma_load_2d(b_dst + c * b_chunk_bytes, &map_b, &full_bar[slot], tap * p.cin + cc * p.kchunk,
-                        n_tile * p.block_n);
+            tma_load_im2col_5d(a_dst, &map_a, &full_bar[slot], cc, w0, h0, d0, n0, (uint16_t)kw_, (uint16_t)kh_,
+                               (uint16_t)kt_);
+            if (!p.b_resident) tma_load_2d(b_dst, &map_b, &full_bar[slot], kcoord, ncol);
+            a_dst += a_chunk_bytes;
+            b_dst += b_chunk_bytes;
+            kcoord += p.kchunk;
+            cc += p.kchunk;
+            if (cc == p.cin) {
+              cc = 0;
+              if (++kw_ == p.kw) {
+                kw_ = 0;
+                if (++kh_ == p.kh) {
+                  kh_ = 0;
+                  ++kt_;
+                }
+              }
+            }
+          }
+          if (++slot == p.stages) {
+            slot = 0;
+            parity ^= 1;
           }
         }
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      // -------------------------------------------------------- MMA issuer
-      const int kk = p.kchunk >> 4;
-      int kit = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-        const int acc = tcount & 1;
-        mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+    // -------------------------------------------------------- MMA issuer
+    // The whole warp walks the loop (uniform control flow keeps descriptors in uniform registers);
+    // one elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors differ only in their low
+    // 32 bits (start address >> 4), so the inner loop is a handful of 32-bit adds per MMA.
+    const uint64_t desc_hi = umma_smem_desc(0, row_bytes) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo_flags = (uint32_t)(umma_smem_desc(0, row_bytes) & 0xFFFFC000ull);
+    const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+    const uint32_t bres_lo = (smem_u32(bres) & 0x3FFFFu) >> 4;
+    const uint32_t stage_lo = stage_bytes >> 4, a_chunk_lo = a_chunk_bytes >> 4, b_chunk_lo = b_chunk_bytes >> 4;
+    const uint32_t b_off_lo = (p.cps * a_chunk_bytes) >> 4;
+    const int kk = p.kchunk >> 4;
+    int slot = 0, tcount = 0;
+    uint32_t parity = 0;
+    if (p.b_resident) mbar_wait(bres_bar, 0);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * p.block_n;
+      uint32_t accumulate = 0;
+      uint32_t bres_cur = bres_lo;
+      int left = p.total_chunks;
+      while (left > 0) {
+        const int nch = left < p.cps ? left : p.cps;
+        left -= nch;
+        mbar_wait(&full_bar[slot], parity);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * p.block_n;
-        uint32_t accumulate = 0;
-        for (int ks = 0; ks < num_kstages; ++ks, ++kit) {
-          const int slot = kit % p.stages;
-          mbar_wait(&full_bar[slot], (kit / p.stages) & 1);
-          tc_fence_after();
-          const int nch = min(p.cps, p.total_chunks - ks * p.cps);
-          const uint32_t a0 = smem_u32(smem + (size_t)slot * stage_bytes);
-          const uint32_t b0 = a0 + p.cps * a_chunk_bytes;
+        if (elect_one()) {
+          uint32_t a_lo = smem_lo + slot * stage_lo;
+          uint32_t b_lo = p.b_resident ? bres_cur : a_lo + b_off_lo;
           for (int c = 0; c < nch; ++c) {
             for (int k = 0; k < kk; ++k) {
-              const uint64_t adesc = umma_smem_desc(a0 + c * a_chunk_bytes + k * 32, row_bytes);
-              const uint64_t bdesc = umma_smem_desc(b0 + c * b_chunk_bytes + k * 32, row_bytes);
+              const uint64_t adesc = desc_hi | (uint64_t)(desc_lo_flags | (a_lo + 2 * k));
+              const uint64_t bdesc = desc_hi | (uint64_t)(desc_lo_flags | (b_lo + 2 * k));
               umma_bf16(tmem_d, adesc, bdesc, p.idesc, accumulate);
               accumulate = 1;
             }
+            a_lo += a_chunk_lo;
+            b_lo += b_chunk_lo;
           }
           umma_commit(&empty_bar[slot]);  // frees the smem slot once these MMAs retire
+          if (left == 0) umma_commit(&tmem_full[acc]);  // accumulator complete
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        __syncwarp();
+        bres_cur += nch * b_chunk_lo;
+        if (++slot == p.stages) {
+          slot = 0;
+          parity ^= 1;
+        }
       }
     }
   } else {
@@ -183,16 +235,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int row = warp * 32 + lane;  // row of the tile == TMEM lane
     const uint32_t swz_mask = epi_row_bytes == 128 ? 7u : (epi_row_bytes == 64 ? 3u : 1u);
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    int q = 0;  // running chunk counter: staging buffer = q & 1
-    if (leader) {
-      // make staging buffer 0 ready for the first chunk of the first tile
+    const int nb = p.epi_bufs;
+    int q = 0;        // running chunk counter: staging buffer = q % nb
+    // prefetch cursor of the leader: the next (tile, chunk) whose staging buffer has not been armed yet
+    int pf_tile = blockIdx.x, pf_chunk = 0, pf_q = 0;
+    auto arm_next = [&]() {
+      // hand staging buffer pf_q % nb to chunk pf_q: start its residual load, or just mark it free
+      const int bsel = pf_q % nb;
       if (p.has_residual) {
-        mbar_expect_tx(&epi_ready[0], epi_buf_bytes);
-        tma_load_2d(epi_buf, &map_res, &epi_ready[0], (blockIdx.x % p.n_tiles) * p.block_n,
-                    (blockIdx.x / p.n_tiles) * kBlockM);
+        mbar_expect_tx(&epi_ready[bsel], epi_buf_bytes);
+        tma_load_2d(epi_buf + bsel * epi_buf_bytes, &map_res, &epi_ready[bsel],
+                    (pf_tile % p.n_tiles) * p.block_n + pf_chunk * p.epi_n, (pf_tile / p.n_tiles) * kBlockM);
       } else {
-        mbar_arrive(&epi_ready[0]);
+        mbar_arrive(&epi_ready[bsel]);
       }
+      ++pf_q;
+      if (++pf_chunk == p.epi_chunks) {
+        pf_chunk = 0;
+        pf_tile += gridDim.x;
+      }
+    };
+    if (leader) {
+      for (int i = 0; i < nb - 1 && pf_tile < p.total_tiles; ++i) arm_next();
     }
     int tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
@@ -203,9 +267,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
       tc_fence_after();
       for (int c = 0; c < p.epi_chunks; ++c, ++q) {
-        const int b = q & 1;
+        const int b = q % nb;
         uint8_t* buf = epi_buf + b * epi_buf_bytes;
-        mbar_wait(&epi_ready[b], (q >> 1) & 1);  // buffer free (+ residual landed)
+        mbar_wait(&epi_ready[b], (q / nb) & 1);  // buffer free (+ residual landed)
         const int col0 = nbase + c * p.epi_n;
         for (int j0 = 0; j0 < p.epi_n; j0 += 16) {
           uint32_t v[16];
@@ -255,22 +319,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (leader) {
           tma_store_2d(&map_out, buf, col0, m0);  // rows >= m_total are clipped by the TMA unit
           tma_store_commit();
-          // prepare the other staging buffer for the next chunk (same tile, or first chunk of the next tile)
-          int nc = c + 1, ntile = tile;
-          if (nc == p.epi_chunks) {
-            nc = 0;
-            ntile = tile + gridDim.x;
-          }
-          if (ntile < p.total_tiles) {
-            tma_store_wait_read1();  // the store issued from that buffer one chunk ago has read it
-            const int nb = b ^ 1;
-            if (p.has_residual) {
-              mbar_expect_tx(&epi_ready[nb], epi_buf_bytes);
-              tma_load_2d(epi_buf + nb * epi_buf_bytes, &map_res, &epi_ready[nb],
-                          (ntile % p.n_tiles) * p.block_n + nc * p.epi_n, (ntile / p.n_tiles) * kBlockM);
-            } else {
-              mbar_arrive(&epi_ready[nb]);
-            }
+          // arm the buffer of chunk q + nb - 1 (the one chunk q - 1 used): its store must have read it
+          if (pf_tile < p.total_tiles) {
+            tma_store_wait_read1();
+            arm_next();
           }
         }
         __syncwarp();  // warp 0 reconverges before the next warp-aligned tcgen05.ld
@@ -485,27 +537,49 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   const int total_chunks = taps * cin_chunks;
   int cps = 64 / kchunk;
   if (cps > total_chunks) cps = total_chunks;
-  const int stage_bytes = (cps * (kBlockM + block_n) * kchunk * 2 + 1023) & ~1023;
+  const int n_tiles = d->cout / block_n;
   const int epi_n = block_n >= 64 ? 64 : block_n;
   if (block_n % epi_n) FAIL(VSB_ERR_INVALID, "block_n %d is not a multiple of the epilogue chunk %d", block_n, epi_n);
-  const int epi_bytes = 2 * kBlockM * epi_n * 2;
   const int num_kstages = ceil_div(total_chunks, cps);
   uint32_t tmem_cols = 32;  // two accumulators; TMEM allocations are powers of two >= 32 columns
   while (tmem_cols < (uint32_t)(2 * block_n)) tmem_cols <<= 1;
-  const int fixed_bytes = epi_bytes + (2 * 16 + 8) * 8 + 1024;
+  // ---- shared-memory plan.  Weight-stationary when one n-tile covers cout and the whole [cout x K]
+  // matrix fits: B is fetched once per CTA instead of once per tile.  With a residual the epilogue
+  // keeps 4 staging buffers so 3 residual chunks are in flight (HBM latency), otherwise 2.
+  const int a_stage = cps * kBlockM * kchunk * 2, b_stage = cps * block_n * kchunk * 2;
+  const long long bres_bytes = (long long)total_chunks * block_n * kchunk * 2;
+  static const bool no_bres = getenv("VSB_NO_BRES") != nullptr;
+  const bool b_resident = !no_bres && n_tiles == 1 && bres_bytes <= 96 * 1024;
+  const int stage_bytes = ((b_resident ? a_stage : a_stage + b_stage) + 1023) & ~1023;
+  const int epi_buf_bytes = kBlockM * epi_n * 2;
+  int epi_bufs = d->residual ? 4 : 2;
+  const int bar_bytes = 1024;
   int stages = d->stages;
-  if (!stages) {
-    // 512 TMEM columns => one CTA per SM anyway: use the whole shared memory; otherwise leave room for two
-    const int budget = (tmem_cols == 512 ? 227 : 113) * 1024 - fixed_bytes;
-    stages = budget / stage_bytes;
-    if (stages > 8) stages = 8;
-    if (stages < 2) stages = (227 * 1024 - fixed_bytes) / stage_bytes;
+  size_t smem_bytes = 0;
+  for (;;) {
+    const int fixed = (b_resident ? (int)((bres_bytes + 1023) & ~1023ll) : 0) + epi_bufs * epi_buf_bytes + bar_bytes + 1024;
+    if (!d->stages) {
+      // 512 TMEM columns => one CTA per SM anyway: use the whole shared memory; otherwise try to leave
+      // room for two CTAs per SM and fall back to one big CTA when that starves the pipeline
+      int budget = (tmem_cols == 512 ? 227 : 113) * 1024 - fixed;
+      stages = budget > 0 ? budget / stage_bytes : 0;
+      if (stages < 3 && stages < 2 * num_kstages) stages = (227 * 1024 - fixed) / stage_bytes;
+      if (stages > 8) stages = 8;
+    }
+    if (stages > 16) stages = 16;
+    if (stages > num_kstages * 2) stages = num_kstages * 2;
+    smem_bytes = (size_t)(stages > 0 ? stages : 0) * stage_bytes + fixed;
+    if (stages >= 2 && smem_bytes <= 227 * 1024) break;
+    if (stages >= 1 && smem_bytes <= 227 * 1024 && epi_bufs == 2) break;
+    if (epi_bufs > 2) {
+      epi_bufs = 2;  // give the shared memory back to the main-loop pipeline
+      continue;
+    }
+    FAIL(VSB_ERR_INVALID, "pipeline (%d stages x %d bytes) does not fit in shared memory", stages, stage_bytes);
   }
-  if (stages > 16) stages = 16;
-  if (stages > num_kstages * 2) stages = num_kstages * 2 > 0 ? num_kstages * 2 : 1;
-  if (stages < 1) FAIL(VSB_ERR_INVALID, "one pipeline stage (%d bytes) does not fit in shared memory", stage_bytes);
-  const size_t smem_bytes = (size_t)stages * stage_bytes + fixed_bytes;
-  if (smem_bytes > 227 * 1024) FAIL(VSB_ERR_INVALID, "pipeline needs %zu bytes of shared memory", smem_bytes);
+  const uint32_t off_bres = (uint32_t)stages * stage_bytes;
+  const uint32_t off_epi = off_bres + (b_resident ? (uint32_t)((bres_bytes + 1023) & ~1023ll) : 0u);
+  const uint32_t off_bar = off_epi + epi_bufs * epi_buf_bytes;
 
   int rc = load_driver_entry_points();
   if (rc != VSB_OK) {
@@ -552,7 +626,9 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   p.lt = lower[2]; p.lh = lower[1]; p.lw = lower[0];
   p.kh = d->kh; p.kw = d->kw;
   p.cin = d->cin; p.cin_chunks = cin_chunks; p.total_chunks = total_chunks; p.cps = cps; p.kchunk = kchunk;
-  p.block_n = block_n; p.n_tiles = d->cout / block_n; p.stages = stages;
+  p.block_n = block_n; p.n_tiles = n_tiles; p.stages = stages;
+  p.epi_bufs = epi_bufs; p.b_resident = b_resident ? 1 : 0;
+  p.stage_bytes = stage_bytes; p.off_bres = off_bres; p.off_epi = off_epi; p.off_bar = off_bar;
   p.total_tiles = (int)(ceil_div_ll(m_total, kBlockM) * p.n_tiles);
   p.epi_n = epi_n; p.epi_chunks = block_n / epi_n;
   p.idesc = umma_idesc_bf16(kBlockM, block_n);

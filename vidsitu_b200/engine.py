@@ -73,6 +73,7 @@ class ClipEngine:
         self.head_ops: List[Tuple[str, Callable[[], None], float]] = []
         self._pool = _Pool(self.device, self.tdt)
         self._graph = None
+        self.op_bytes: Dict[str, float] = {}
         self.crop = spec.crop
         if self.crop % 16:
             raise VsbError("crop size must be a multiple of 16")
@@ -192,6 +193,8 @@ class ClipEngine:
                             relu, **tune)
         self._keep.append(plan)
         m = out.pixels
+        es = 2 if self.dtype == VSB_BF16 else 4
+        self.op_bytes[cs.key] = es * (x.pixels * x.c + m * out.c * (2 if residual is not None else 1))
         self.trunk_ops.append((cs.key, plan.run, float(m) * cs.flops_per_out_pixel))
 
     def _stem(self, p: int, x: Act) -> Act:
@@ -228,6 +231,8 @@ class ClipEngine:
             plan = ConvPlan(self.dtype, x, wp, cs.cout, cs.kernel, cs.stride, cs.pad, None, scale, bias, y, None,
                             True)
         self._keep.append(plan)
+        es = 2 if self.dtype == VSB_BF16 else 4
+        self.op_bytes[cs.key] = es * (x.pixels * 4 + y.pixels * cs.cout)
         self.trunk_ops.append((cs.key, plan.run, float(y.pixels) * cs.flops_per_out_pixel))
         return y
 
@@ -236,6 +241,8 @@ class ClipEngine:
         ho = (x.h + 2 * pad[1] - kernel[1]) // stride[1] + 1
         wo = (x.w + 2 * pad[2] - kernel[2]) // stride[2] + 1
         y = self._alloc(x.n, to, ho, wo, x.c_real, pitch=pitch)
+        es = 2 if self.dtype == VSB_BF16 else 4
+        self.op_bytes[name] = es * (x.pixels * x.c_real + y.pixels * y.c)
         self.trunk_ops.append((name, lambda: ops.maxpool3d(x, y, kernel, stride, pad, self.dtype), 0.0))
         return y
 
