@@ -49,10 +49,12 @@ struct IgemmParams {
 };
 
 constexpr int kBlockM = 128;
-constexpr int kThreads = 192;
-constexpr int kMaxEpiBufs = 8;
+constexpr int kEpiWarps = 8;
+constexpr int kProducerWarp = kEpiWarps;
+constexpr int kMmaWarp = kEpiWarps + 1;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kMaxEpiBufs = 4;  // per epilogue warp
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // Persistent CTA: loops over output tiles (tile = blockIdx.x + i * gridDim.x, the n-tile index
 // fastest so co-running CTAs share the activation tile in L2).  Three pipelines:
@@ -60,7 +62,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 //   TMEM  full/empty[2]        MMA issuer    <-> epilogue (two accumulators: the epilogue of tile i
 //                                                overlaps the main loop of tile i+1)
 //   epi   ready[2]             staging buffers of the epilogue (residual TMA load in, TMA store out)
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)  // 2 CTAs / SM must fit: <= 102 registers per thread
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                   const IgemmParams p) {
@@ -72,7 +74,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t b_chunk_bytes = p.block_n * row_bytes;
   const uint32_t stage_bytes = p.stage_bytes;
   const uint32_t epi_row_bytes = p.epi_n * 2;
-  const uint32_t epi_buf_bytes = kBlockM * epi_row_bytes;
   uint8_t* bres = smem + p.off_bres;   // resident weights (b_resident)
   uint8_t* epi_buf = smem + p.off_epi;  // epi_bufs buffers, each a multiple of 1024 bytes
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
@@ -80,13 +81,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* tmem_full = empty_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* epi_ready = tmem_empty + 2;
-  uint64_t* bres_bar = epi_ready + kMaxEpiBufs;
+  uint64_t* bres_bar = epi_ready + kEpiWarps * kMaxEpiBufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     tma_prefetch_desc(&map_out);
@@ -97,13 +98,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], kEpiWarps);  // one arrival per epilogue warp
     }
-    for (int i = 0; i < p.epi_bufs; ++i) mbar_init(&epi_ready[i], 1);
+    for (int i = 0; i < kEpiWarps * kMaxEpiBufs; ++i) mbar_init(&epi_ready[i], 1);
     mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
@@ -114,7 +115,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int num_kstages = (p.total_chunks + p.cps - 1) / p.cps;
 
-  if (warp == 4) {
+  if (warp == kProducerWarp) {
     if (lane == 0) {
       // ------------------------------------------------------ TMA producer (one thread)
       // The loop body is kept free of divisions: filter-tap / channel-chunk indices advance as
@@ -177,7 +178,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // -------------------------------------------------------- MMA issuer
     // The whole warp walks the loop (uniform control flow keeps descriptors in uniform registers);
     // one elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors differ only in their low
@@ -230,34 +231,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else {
-    // ---------------------------------------------------------- epilogue (warps 0-3)
-    const bool leader = threadIdx.x == 0;
-    const int row = warp * 32 + lane;  // row of the tile == TMEM lane
+    // ---------------------------------------------------------- epilogue (warps 0-7)
+    // Eight independent per-warp pipelines: warp w owns TMEM lanes / tile rows [32*(w&3), +32) and
+    // every second column chunk (global chunk parity == w>>2).  Each warp has its own staging
+    // slabs (32 rows x epi_n), its own residual TMA loads and its own TMA stores -- no block-level
+    // barrier anywhere in the epilogue.
+    const int quarter = warp & 3, grp = warp >> 2;
     const uint32_t swz_mask = epi_row_bytes == 128 ? 7u : (epi_row_bytes == 64 ? 3u : 1u);
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t slab_bytes = 32 * epi_row_bytes;
     const int nb = p.epi_bufs;
-    int q = 0;        // running chunk counter: staging buffer = q % nb
-    // prefetch cursor of the leader: the next (tile, chunk) whose staging buffer has not been armed yet
-    int pf_tile = blockIdx.x, pf_chunk = 0, pf_q = 0;
-    auto arm_next = [&]() {
-      // hand staging buffer pf_q % nb to chunk pf_q: start its residual load, or just mark it free
+    uint8_t* my_bufs = epi_buf + (size_t)warp * nb * slab_bytes;
+    uint64_t* my_ready = epi_ready + warp * kMaxEpiBufs;
+    const int row_in_tile = quarter * 32;
+    // prefetch cursor (lane 0): next chunk of THIS warp whose staging slab has not been armed yet
+    int pf_tile = blockIdx.x, pf_chunk = 0, pf_gq = 0, pf_q = 0;
+    auto pf_skip = [&]() {  // advance the cursor to the next chunk owned by this warp's group
+      while (pf_tile < p.total_tiles && (pf_gq & 1) != grp) {
+        ++pf_gq;
+        if (++pf_chunk == p.epi_chunks) {
+          pf_chunk = 0;
+          pf_tile += gridDim.x;
+        }
+      }
+    };
+    auto arm_next = [&]() {  // hand slab pf_q % nb to that chunk: start its residual load, or mark it free
       const int bsel = pf_q % nb;
       if (p.has_residual) {
-        mbar_expect_tx(&epi_ready[bsel], epi_buf_bytes);
-        tma_load_2d(epi_buf + bsel * epi_buf_bytes, &map_res, &epi_ready[bsel],
-                    (pf_tile % p.n_tiles) * p.block_n + pf_chunk * p.epi_n, (pf_tile / p.n_tiles) * kBlockM);
+        mbar_expect_tx(&my_ready[bsel], slab_bytes);
+        tma_load_2d(my_bufs + bsel * slab_bytes, &map_res, &my_ready[bsel],
+                    (pf_tile % p.n_tiles) * p.block_n + pf_chunk * p.epi_n,
+                    (pf_tile / p.n_tiles) * kBlockM + row_in_tile);
       } else {
-        mbar_arrive(&epi_ready[bsel]);
+        mbar_arrive(&my_ready[bsel]);
       }
       ++pf_q;
+      ++pf_gq;
       if (++pf_chunk == p.epi_chunks) {
         pf_chunk = 0;
         pf_tile += gridDim.x;
       }
+      pf_skip();
     };
-    if (leader) {
+    if (lane == 0) {
+      pf_skip();
       for (int i = 0; i < nb - 1 && pf_tile < p.total_tiles; ++i) arm_next();
     }
+    __syncwarp();
+    int q = 0;   // chunks processed by this warp: staging slab = q % nb
+    int gq = 0;  // global chunk counter of the CTA (all tiles, all chunks)
     int tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       const int n_tile = tile % p.n_tiles;
@@ -266,16 +288,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int acc = tcount & 1;
       mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
       tc_fence_after();
-      for (int c = 0; c < p.epi_chunks; ++c, ++q) {
+      for (int c = 0; c < p.epi_chunks; ++c, ++gq) {
+        if ((gq & 1) != grp) continue;
         const int b = q % nb;
-        uint8_t* buf = epi_buf + b * epi_buf_bytes;
-        mbar_wait(&epi_ready[b], (q / nb) & 1);  // buffer free (+ residual landed)
+        uint8_t* buf = my_bufs + b * slab_bytes;
+        mbar_wait(&my_ready[b], (q / nb) & 1);  // slab free (+ residual landed)
         const int col0 = nbase + c * p.epi_n;
         for (int j0 = 0; j0 < p.epi_n; j0 += 16) {
           uint32_t v[16];
           tmem_ld16(lane_taddr + acc * p.block_n + c * p.epi_n + j0, v);
-          // this thread's 32 bytes of the staging row, as two swizzled 16-byte chunks
-          const uint32_t off0 = row * epi_row_bytes + j0 * 2;
+          // this thread's 32 bytes of its staging row, as two swizzled 16-byte chunks
+          const uint32_t off0 = lane * epi_row_bytes + j0 * 2;
           uint4* s0 = reinterpret_cast<uint4*>(buf + (off0 ^ (((off0 >> 7) & swz_mask) << 4)));
           const uint32_t off1 = off0 + 16;
           uint4* s1 = reinterpret_cast<uint4*>(buf + (off1 ^ (((off1 >> 7) & swz_mask) << 4)));
@@ -284,21 +307,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             r0 = *s0;
             r1 = *s1;
           }
-          float sc[16], bi[16];
+          float bi[16];
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + j0) + qq);
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j0) + qq);
-            sc[4 * qq + 0] = s4.x; sc[4 * qq + 1] = s4.y; sc[4 * qq + 2] = s4.z; sc[4 * qq + 3] = s4.w;
             bi[4 * qq + 0] = b4.x; bi[4 * qq + 1] = b4.y; bi[4 * qq + 2] = b4.z; bi[4 * qq + 3] = b4.w;
           }
-          tmem_ld_wait();
+          float x[16];
+          if (p.scale) {
+            float sc[16];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + j0) + qq);
+              sc[4 * qq + 0] = s4.x; sc[4 * qq + 1] = s4.y; sc[4 * qq + 2] = s4.z; sc[4 * qq + 3] = s4.w;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) x[e] = fmaf(__uint_as_float(v[e]), sc[e], bi[e]);
+          } else {  // BatchNorm scale already folded into the weights
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) x[e] = __uint_as_float(v[e]) + bi[e];
+          }
           const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
           uint32_t o[8];
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) {
-            float x0 = fmaf(__uint_as_float(v[2 * qq]), sc[2 * qq], bi[2 * qq]) + bf16_lo(rr[qq]);
-            float x1 = fmaf(__uint_as_float(v[2 * qq + 1]), sc[2 * qq + 1], bi[2 * qq + 1]) + bf16_hi(rr[qq]);
+            float x0 = x[2 * qq] + bf16_lo(rr[qq]);
+            float x1 = x[2 * qq + 1] + bf16_hi(rr[qq]);
             if (p.relu) {
               x0 = fmaxf(x0, 0.f);
               x1 = fmaxf(x1, 0.f);
@@ -308,32 +344,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           *s0 = make_uint4(o[0], o[1], o[2], o[3]);
           *s1 = make_uint4(o[4], o[5], o[6], o[7]);
         }
-        if (c == p.epi_chunks - 1) {
-          // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
-        epi_bar_sync();
-        if (leader) {
-          tma_store_2d(&map_out, buf, col0, m0);  // rows >= m_total are clipped by the TMA unit
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_out, buf, col0, m0 + row_in_tile);  // rows >= m_total are clipped by the TMA unit
           tma_store_commit();
-          // arm the buffer of chunk q + nb - 1 (the one chunk q - 1 used): its store must have read it
+          // arm the slab of this warp's chunk q + nb - 1 (the one chunk q - 1 used): its store must have read it
           if (pf_tile < p.total_tiles) {
             tma_store_wait_read1();
             arm_next();
           }
         }
-        __syncwarp();  // warp 0 reconverges before the next warp-aligned tcgen05.ld
+        __syncwarp();  // reconverge before the next warp-aligned tcgen05.ld
+        ++q;
       }
+      // every tcgen05.ld this warp issues for the accumulator has completed: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    if (leader) tma_store_wait_all();  // all output bytes are in global memory before the CTA exits
+    if (lane == 0) tma_store_wait_all();  // this warp's output bytes are in global memory before the CTA exits
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -475,7 +510,8 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   VSB_CHECK_ARG(d && out_plan, "null argument");
   *out_plan = nullptr;
   VSB_CHECK_ARG(d->dtype == VSB_BF16 || d->dtype == VSB_F32, "dtype must be VSB_BF16 or VSB_F32");
-  VSB_CHECK_ARG(d->in && d->wgt && d->out && d->scale && d->bias, "null tensor pointer");
+  VSB_CHECK_ARG(d->in && d->wgt && d->out && d->bias, "null tensor pointer");
+  VSB_CHECK_ARG(d->scale || d->dtype == VSB_BF16, "scale may be null (= 1) only on the bf16 path");
   VSB_CHECK_ARG(d->n > 0 && d->t > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "non-positive extent");
   VSB_CHECK_ARG(d->kt > 0 && d->kh > 0 && d->kw > 0 && d->st > 0 && d->sh > 0 && d->sw > 0, "bad kernel/stride");
   VSB_CHECK_ARG(d->in_pitch >= d->cin && d->out_pitch >= d->cout, "pitch smaller than channel count");
@@ -538,9 +574,12 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   int cps = 64 / kchunk;
   if (cps > total_chunks) cps = total_chunks;
   const int n_tiles = d->cout / block_n;
-  const int epi_n = block_n >= 64 ? 64 : block_n;
-  if (block_n % epi_n) FAIL(VSB_ERR_INVALID, "block_n %d is not a multiple of the epilogue chunk %d", block_n, epi_n);
   const int num_kstages = ceil_div(total_chunks, cps);
+  // epilogue column chunk: 64 columns (128-byte staging rows); compute-bound layers (long K loop, no
+  // residual) take 32-column chunks so the staging slabs leave room for one more main-loop stage
+  int epi_n = block_n >= 64 ? 64 : block_n;
+  if (block_n >= 64 && !d->residual && num_kstages >= 8) epi_n = 32;
+  if (block_n % epi_n) FAIL(VSB_ERR_INVALID, "block_n %d is not a multiple of the epilogue chunk %d", block_n, epi_n);
   uint32_t tmem_cols = 32;  // two accumulators; TMEM allocations are powers of two >= 32 columns
   while (tmem_cols < (uint32_t)(2 * block_n)) tmem_cols <<= 1;
   // ---- shared-memory plan.  Weight-stationary when one n-tile covers cout and the whole [cout x K]
@@ -551,8 +590,8 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   static const bool no_bres = getenv("VSB_NO_BRES") != nullptr;
   const bool b_resident = !no_bres && n_tiles == 1 && bres_bytes <= 96 * 1024;
   const int stage_bytes = ((b_resident ? a_stage : a_stage + b_stage) + 1023) & ~1023;
-  const int epi_buf_bytes = kBlockM * epi_n * 2;
-  int epi_bufs = d->residual ? 4 : 2;
+  const int epi_buf_bytes = kEpiWarps * 32 * epi_n * 2;  // one 32-row slab per epilogue warp
+  int epi_bufs = d->residual ? 3 : 2;  // slabs per epilogue warp (residual prefetch distance = epi_bufs - 1)
   const int bar_bytes = 1024;
   int stages = d->stages;
   size_t smem_bytes = 0;
@@ -569,8 +608,8 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
     if (stages > 16) stages = 16;
     if (stages > num_kstages * 2) stages = num_kstages * 2;
     smem_bytes = (size_t)(stages > 0 ? stages : 0) * stage_bytes + fixed;
-    if (stages >= 2 && smem_bytes <= 227 * 1024) break;
-    if (stages >= 1 && smem_bytes <= 227 * 1024 && epi_bufs == 2) break;
+    if (stages >= 3 && smem_bytes <= 227 * 1024) break;
+    if (stages >= 1 && smem_bytes <= 227 * 1024 && (epi_bufs == 2 || stages >= 2 * num_kstages)) break;
     if (epi_bufs > 2) {
       epi_bufs = 2;  // give the shared memory back to the main-loop pipeline
       continue;
@@ -602,13 +641,13 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   }
   // output / residual tiles move through TMA too: [m_total rows, cout cols], row pitch in bytes
   const CUtensorMapSwizzle epi_swz = swizzle_for(epi_n * 2);
-  rc = encode_tiled_2d(&plan->map_out, d->out, d->cout, m_total, (long long)d->out_pitch * 2, epi_n, kBlockM, epi_swz);
+  rc = encode_tiled_2d(&plan->map_out, d->out, d->cout, m_total, (long long)d->out_pitch * 2, epi_n, 32, epi_swz);
   if (rc != VSB_OK) {
     delete plan;
     return rc;
   }
   if (d->residual) {
-    rc = encode_tiled_2d(&plan->map_res, d->residual, d->cout, m_total, (long long)d->res_pitch * 2, epi_n, kBlockM,
+    rc = encode_tiled_2d(&plan->map_res, d->residual, d->cout, m_total, (long long)d->res_pitch * 2, epi_n, 32,
                          epi_swz);
     if (rc != VSB_OK) {
       delete plan;
