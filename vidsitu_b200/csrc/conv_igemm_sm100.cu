@@ -62,6 +62,7 @@ constexpr int kMaxEpiBufs = 4;  // per epilogue warp
 //   TMEM  full/empty[2]        MMA issuer    <-> epilogue (two accumulators: the epilogue of tile i
 //                                                overlaps the main loop of tile i+1)
 //   epi   ready[2]             staging buffers of the epilogue (residual TMA load in, TMA store out)
+template <int KK>  // KK = kchunk / 16 MMAs per channel chunk; CPS = 4 / KK chunks per pipeline stage
 __global__ void __launch_bounds__(kThreads, 2)  // 2 CTAs / SM must fit: <= 102 registers per thread
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
@@ -126,27 +127,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int g = 0; g < p.total_chunks; ++g)
           tma_load_2d(bres + g * b_chunk_bytes, &map_b, bres_bar, g * p.kchunk, 0);
       }
-      const uint32_t stage_tx = p.b_resident ? a_chunk_bytes : a_chunk_bytes + b_chunk_bytes;
-      const uint32_t b_off = p.cps * a_chunk_bytes;
+      const bool b_resident = p.b_resident != 0;
+      const uint32_t stage_tx = b_resident ? a_chunk_bytes : a_chunk_bytes + b_chunk_bytes;
+      const int cps = 4 / KK, kchunk = 16 * KK;
+      const uint32_t b_off = cps * a_chunk_bytes;
+      const int total_chunks = p.total_chunks, stages = p.stages, total_tiles = p.total_tiles, n_tiles = p.n_tiles;
+      const int cin = p.cin, fkw = p.kw, fkh = p.kh, block_n = p.block_n;
+      const int owo = p.wo, oho = p.ho, oto = p.to, sw = p.sw, sh = p.sh, st = p.st, lw = p.lw, lh = p.lh, lt = p.lt;
+      const int tile_step = gridDim.x;
       int slot = 0;
       uint32_t parity = 1;  // first pass over the ring: slots are free
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m0 = (tile / p.n_tiles) * kBlockM;
-        const int wo = m0 % p.wo;
-        const int r1 = m0 / p.wo;
-        const int ho = r1 % p.ho;
-        const int r2 = r1 / p.ho;
-        const int to_ = r2 % p.to;
-        const int n0 = r2 / p.to;
-        const int w0 = wo * p.sw + p.lw;
-        const int h0 = ho * p.sh + p.lh;
-        const int d0 = to_ * p.st + p.lt;
-        const int ncol = n_tile * p.block_n;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step) {
+        const int n_tile = tile % n_tiles;
+        const int m0 = (tile / n_tiles) * kBlockM;
+        const int wo = m0 % owo;
+        const int r1 = m0 / owo;
+        const int ho = r1 % oho;
+        const int r2 = r1 / oho;
+        const int to_ = r2 % oto;
+        const int n0 = r2 / oto;
+        const int w0 = wo * sw + lw;
+        const int h0 = ho * sh + lh;
+        const int d0 = to_ * st + lt;
+        const int ncol = n_tile * block_n;
         int cc = 0, kw_ = 0, kh_ = 0, kt_ = 0, kcoord = 0;
-        int left = p.total_chunks;
+        int left = total_chunks;
         while (left > 0) {
-          const int nch = left < p.cps ? left : p.cps;
+          const int nch = left < cps ? left : cps;
           left -= nch;
           mbar_wait(&empty_bar[slot], parity);
           mbar_expect_tx(&full_bar[slot], nch * stage_tx);
@@ -155,23 +162,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           for (int c = 0; c < nch; ++c) {
             tma_load_im2col_5d(a_dst, &map_a, &full_bar[slot], cc, w0, h0, d0, n0, (uint16_t)kw_, (uint16_t)kh_,
                                (uint16_t)kt_);
-            if (!p.b_resident) tma_load_2d(b_dst, &map_b, &full_bar[slot], kcoord, ncol);
+            if (!b_resident) tma_load_2d(b_dst, &map_b, &full_bar[slot], kcoord, ncol);
             a_dst += a_chunk_bytes;
             b_dst += b_chunk_bytes;
-            kcoord += p.kchunk;
-            cc += p.kchunk;
-            if (cc == p.cin) {
+            kcoord += kchunk;
+            cc += kchunk;
+            if (cc == cin) {
               cc = 0;
-              if (++kw_ == p.kw) {
+              if (++kw_ == fkw) {
                 kw_ = 0;
-                if (++kh_ == p.kh) {
+                if (++kh_ == fkh) {
                   kh_ = 0;
                   ++kt_;
                 }
               }
             }
           }
-          if (++slot == p.stages) {
+          if (++slot == stages) {
             slot = 0;
             parity ^= 1;
           }
@@ -182,51 +189,81 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // -------------------------------------------------------- MMA issuer
     // The whole warp walks the loop (uniform control flow keeps descriptors in uniform registers);
     // one elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors differ only in their low
-    // 32 bits (start address >> 4), so the inner loop is a handful of 32-bit adds per MMA.
+    // 32 bits (start address >> 4); a full stage is CPS*KK = 4 fully unrolled MMAs.  Every kernel
+    // parameter used in the loop is copied to a local first (one constant-bank load, not one per use).
+    constexpr int CPS = 4 / KK;
     const uint64_t desc_hi = umma_smem_desc(0, row_bytes) & 0xFFFFFFFF00000000ull;
     const uint32_t desc_lo_flags = (uint32_t)(umma_smem_desc(0, row_bytes) & 0xFFFFC000ull);
     const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
     const uint32_t bres_lo = (smem_u32(bres) & 0x3FFFFu) >> 4;
     const uint32_t stage_lo = stage_bytes >> 4, a_chunk_lo = a_chunk_bytes >> 4, b_chunk_lo = b_chunk_bytes >> 4;
-    const uint32_t b_off_lo = (p.cps * a_chunk_bytes) >> 4;
-    const int kk = p.kchunk >> 4;
+    const uint32_t b_off_lo = (CPS * a_chunk_bytes) >> 4;
+    const uint32_t idesc = p.idesc;
+    const int total_chunks = p.total_chunks, stages = p.stages, total_tiles = p.total_tiles, block_n = p.block_n;
+    const int full_stages = total_chunks / CPS, tail_chunks = total_chunks - full_stages * CPS;
+    const bool b_resident = p.b_resident != 0;
+    const int tile_step = gridDim.x;
     int slot = 0, tcount = 0;
-    uint32_t parity = 0;
-    if (p.b_resident) mbar_wait(bres_bar, 0);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+    uint32_t parity = 0, a_slot_lo = smem_lo;
+    if (b_resident) mbar_wait(bres_bar, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step, ++tcount) {
       const int acc = tcount & 1;
       mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * p.block_n;
-      uint32_t accumulate = 0;
+      const uint32_t tmem_d = tmem_base + acc * block_n;
       uint32_t bres_cur = bres_lo;
-      int left = p.total_chunks;
-      while (left > 0) {
-        const int nch = left < p.cps ? left : p.cps;
-        left -= nch;
+      for (int ks = 0; ks < full_stages; ++ks) {
         mbar_wait(&full_bar[slot], parity);
         tc_fence_after();
         if (elect_one()) {
-          uint32_t a_lo = smem_lo + slot * stage_lo;
-          uint32_t b_lo = p.b_resident ? bres_cur : a_lo + b_off_lo;
-          for (int c = 0; c < nch; ++c) {
-            for (int k = 0; k < kk; ++k) {
+          const uint32_t a_lo = a_slot_lo;
+          const uint32_t b_lo = b_resident ? bres_cur : a_slot_lo + b_off_lo;
+#pragma unroll
+          for (int c = 0; c < CPS; ++c) {
+#pragma unroll
+            for (int k = 0; k < KK; ++k) {
+              const uint64_t adesc = desc_hi | (uint64_t)(desc_lo_flags | (a_lo + c * a_chunk_lo + 2 * k));
+              const uint64_t bdesc = desc_hi | (uint64_t)(desc_lo_flags | (b_lo + c * b_chunk_lo + 2 * k));
+              umma_bf16(tmem_d, adesc, bdesc, idesc, (ks | c | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[slot]);  // frees the smem slot once these MMAs retire
+          if (tail_chunks == 0 && ks == full_stages - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        bres_cur += CPS * b_chunk_lo;
+        a_slot_lo += stage_lo;
+        if (++slot == stages) {
+          slot = 0;
+          parity ^= 1;
+          a_slot_lo = smem_lo;
+        }
+      }
+      if (tail_chunks) {  // last, partially filled stage
+        mbar_wait(&full_bar[slot], parity);
+        tc_fence_after();
+        if (elect_one()) {
+          uint32_t a_lo = a_slot_lo;
+          uint32_t b_lo = b_resident ? bres_cur : a_slot_lo + b_off_lo;
+          for (int c = 0; c < tail_chunks; ++c) {
+#pragma unroll
+            for (int k = 0; k < KK; ++k) {
               const uint64_t adesc = desc_hi | (uint64_t)(desc_lo_flags | (a_lo + 2 * k));
               const uint64_t bdesc = desc_hi | (uint64_t)(desc_lo_flags | (b_lo + 2 * k));
-              umma_bf16(tmem_d, adesc, bdesc, p.idesc, accumulate);
-              accumulate = 1;
+              umma_bf16(tmem_d, adesc, bdesc, idesc, (full_stages | c | k) != 0 ? 1u : 0u);
             }
             a_lo += a_chunk_lo;
             b_lo += b_chunk_lo;
           }
-          umma_commit(&empty_bar[slot]);  // frees the smem slot once these MMAs retire
-          if (left == 0) umma_commit(&tmem_full[acc]);  // accumulator complete
+          umma_commit(&empty_bar[slot]);
+          umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
-        bres_cur += nch * b_chunk_lo;
-        if (++slot == p.stages) {
+        a_slot_lo += stage_lo;
+        if (++slot == stages) {
           slot = 0;
           parity ^= 1;
+          a_slot_lo = smem_lo;
         }
       }
     }
@@ -571,8 +608,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   const int taps = d->kt * d->kh * d->kw;
   const int cin_chunks = d->cin / kchunk;
   const int total_chunks = taps * cin_chunks;
-  int cps = 64 / kchunk;
-  if (cps > total_chunks) cps = total_chunks;
+  const int cps = 64 / kchunk;  // a pipeline stage always has room for 64 K-elements
   const int n_tiles = d->cout / block_n;
   const int num_kstages = ceil_div(total_chunks, cps);
   // epilogue column chunk: 64 columns (128-byte staging rows); compute-bound layers (long K loop, no
@@ -697,7 +733,11 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_igemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) {
     set_error("cudaFuncSetAttribute(conv_igemm_kernel) failed: %s", cudaGetErrorString(attr_err));
@@ -712,8 +752,20 @@ extern "C" int vsb_conv3d_run(const vsb_conv_plan* plan, void* stream) {
   VSB_CHECK_ARG(plan, "null plan");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (plan->desc.dtype == VSB_F32) return launch_conv_simt(plan->desc, plan->to, plan->ho, plan->wo, s);
-  conv_igemm_kernel<<<plan->grid, kThreads, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_out,
-                                                                    plan->map_res, plan->params);
+  switch (plan->params.kchunk) {
+    case 16:
+      conv_igemm_kernel<1><<<plan->grid, kThreads, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_out,
+                                                                         plan->map_res, plan->params);
+      break;
+    case 32:
+      conv_igemm_kernel<2><<<plan->grid, kThreads, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_out,
+                                                                         plan->map_res, plan->params);
+      break;
+    default:
+      conv_igemm_kernel<4><<<plan->grid, kThreads, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_out,
+                                                                         plan->map_res, plan->params);
+      break;
+  }
   VSB_CHECK_LAUNCH("conv_igemm_kernel");
   return VSB_OK;
 }
