@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VSB_ABI_VERSION 1
+#define VSB_ABI_VERSION 2
 
 typedef enum vsb_status {
   VSB_OK = 0,
@@ -95,6 +95,17 @@ typedef struct vsb_conv_desc {
   int block_n;                  /* 16..256, multiple of 16, divides cout         */
   int kchunk;                   /* 16 / 32 / 64 channels per TMA box             */
   int stages;                   /* smem pipeline depth                           */
+  /* algorithm of the bf16 path: 0 = automatic, 1 = im2col-mode implicit GEMM (any conv),
+   * 2 = shared-memory window (input rows loaded once, every filter tap is a shifted
+   * tcgen05 descriptor over them; needs st == sw == 1, sh in {1,2}, cin*2 in {32,64,128} bytes,
+   * cout <= 256 and the whole weight matrix resident in shared memory).                */
+  int algo;
+  /* window algorithm only: input-channel range [lo, hi) (multiples of 16) that tap kw actually
+   * reads -- pixel-group restated convs (block-Toeplitz weights) touch only a few pixels of
+   * their outer groups.  hi == 0 means the full range.  When any range is partial, wgt holds
+   * only those channels: [cout][kt][kh][sum_kw (hi - lo)].                             */
+  int kw_c_lo[8];
+  int kw_c_hi[8];
 } vsb_conv_desc;
 
 typedef struct vsb_conv_plan vsb_conv_plan;

@@ -16,6 +16,23 @@ int vsb_debug_im2col_probe(const void* in, int n, int t, int h, int w, int c, in
                            int uw, int uh, int ut, int sw, int sh, int st, int chan_box, int pixel_box, int cc,
                            int cw, int ch, int cd, int cn, int ow, int oh, int od, void* out, void* stream);
 
+/* One tcgen05.mma chain (M=128, N=n, K=16*ksteps) on a bf16 [a_rows, row_bytes/2] A tile and a
+ * [n, row_bytes/2] B tile loaded with the matching TMA swizzle; the A/B descriptor start addresses
+ * are advanced by shift_bytes / b_shift_bytes (rows * row_bytes + K-slice bytes).  base_mode 1 also
+ * sets the descriptor's base_offset field to (addr >> 7) & 7.  out: fp32 [128, n]. */
+int vsb_debug_umma_semantics(const void* a, int a_rows, const void* b, int n, int row_bytes, int ksteps,
+                             int shift_bytes, int b_shift_bytes, int base_mode, float* out, void* stream);
+
+/* Issue-rate probe: each of `grid` CTAs issues iters*4 MMAs (M=128, N=n, K=16) cycling over
+ * a_tiles 16 KiB A tiles; clk[cta] = cycles from first issue to completion. */
+int vsb_debug_umma_rate(int n, int iters, int a_tiles, int a_from_same, int grid, int smem_pad_kb, long long* clk,
+                        void* stream);
+
+/* Role timeline counters of a window-algorithm conv plan created with VSB_WIN_DEBUG=1 in the
+ * environment (see conv_win_sm100.cu); synchronises the device, copies 16 counters and clears them. */
+struct vsb_conv_plan;
+int vsb_debug_conv_stats(const struct vsb_conv_plan* plan, long long* out16);
+
 #ifdef __cplusplus
 }
 #endif

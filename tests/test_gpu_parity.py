@@ -98,6 +98,19 @@ def test_pixel_group_restatement(case):
     assert info["ok"], info
 
 
+def _window_cases():
+    import gpu_check_ops as G
+    return G.WINDOW_CASES
+
+
+@pytest.mark.parametrize("case", _window_cases(), ids=lambda c: c[0])
+def test_window_conv(case):
+    """conv_win_sm100.cu (algo=2): smem-resident input window + shifted-descriptor taps vs torch conv3d."""
+    import gpu_check_ops as G
+    info = G.run_window_case(*case)
+    assert info["ok"], info
+
+
 def test_memory_bound_ops():
     import gpu_check_ops as G
     res = G.run_mem_checks()

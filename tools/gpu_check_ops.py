@@ -27,7 +27,8 @@ import torch.nn.functional as F
 from vidsitu_b200 import lib as L
 from vidsitu_b200 import ops
 from vidsitu_b200.ops import Act, ConvPlan
-from vidsitu_b200.weights import group_conv_weight, pack_conv_weight, stem_quad_weight
+from vidsitu_b200.weights import (group_conv_weight, group_tap_ranges, pack_conv_weight, slice_tap_channels,
+                                  stem_quad_weight)
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -219,6 +220,73 @@ def run_group_case(name, cin, cout, k, s, p, J, W, cin_store, cout_store, shift=
     return info
 
 
+def run_window_case(name, cin, cout, k, s, p, J, W, H, cin_store, cout_store, shift=0, wbuf=None, use_res=False,
+                    n=2, t=4, relu=True):
+    """Shared-memory window algorithm (conv_win_sm100.cu, algo=2) on a pixel-group restated conv with
+    sliced tap channel ranges vs the plain conv."""
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(zlib.crc32(name.encode()) % (2 ** 31))
+    wb = wbuf or W
+    x = torch.randn((n, t, H, W, cin), generator=g).to(torch.bfloat16)
+    xs = torch.zeros((n, t, H, wb, cin_store), dtype=torch.bfloat16)
+    xs[:, :, :, shift:shift + W, :cin] = x
+    xs = xs.to(dev)
+    fan_in = cin * k[0] * k[1] * k[2]
+    wt = (torch.randn((cout, cin) + tuple(k), generator=g) / fan_in ** 0.5).to(torch.bfloat16).to(dev)
+    scale = torch.zeros(cout_store, device=dev)
+    bias = torch.zeros(cout_store, device=dev)
+    scale[:cout] = (torch.rand(cout, generator=g) + 0.5).to(dev)
+    bias[:cout] = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    to = (t + 2 * p[0] - k[0]) // s[0] + 1
+    ho = (H + 2 * p[1] - k[1]) // s[1] + 1
+    wo = (W + 2 * p[2] - k[2]) // s[2] + 1
+    res = None
+    if use_res:
+        res = torch.zeros((n, to, ho, wo, cout_store), dtype=torch.bfloat16)
+        res[..., :cout] = torch.randn((n, to, ho, wo, cout), generator=g).to(torch.bfloat16)
+        res = res.to(dev)
+    outbuf = torch.full((n, to, ho, wo, cout_store), 7.0, dtype=torch.bfloat16, device=dev)
+    G = J * s[2]
+    wq, ngt, plo = group_conv_weight(wt.float(), cin_store, cout_store, J, s[2], p[2] - shift, torch.bfloat16)
+    ranges = group_tap_ranges(k[2], cin_store, J, s[2], p[2] - shift)
+    wq = slice_tap_channels(wq, k[0] * k[1], ngt, ranges)
+    xin = Act(xs, n, t, H, wb // G, G * cin_store, G * cin_store)
+    yout = Act(outbuf, n, to, ho, wo // J, J * cout_store, J * cout_store)
+    ra = Act(res, n, to, ho, wo // J, J * cout_store, J * cout_store) if use_res else None
+    phi = yout.w - 1 + ngt - xin.w - plo
+    plan = ConvPlan(L.VSB_BF16, xin, wq, J * cout_store, (k[0], k[1], ngt), (s[0], s[1], 1), (p[0], p[1], plo),
+                    (p[0], p[1], phi), scale.repeat(J), bias.repeat(J), yout, ra, relu, algo=2, kw_ranges=ranges)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = _ref_conv(x.to(dev), wt, s, p, scale[:cout], bias[:cout], res[..., :cout] if use_res else None, relu)
+    info = _compare(outbuf[..., :cout], ref, atol=2e-2, rtol=1.6e-2)
+    info["pad_zero"] = bool((outbuf[..., cout:] == 0).all())
+    info["ok"] = info["n_bad"] == 0 and info["finite"] and info["pad_zero"]
+    return info
+
+
+# (name, cin, cout, kernel, stride, pad, J, W, H, cin_store, cout_store, shift, wbuf, residual[, n, t, relu])
+WINDOW_CASES = [
+    ("w_sp3_64_64_56", 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, 56, 56, 64, 64, 0, None, False, 2, 2),
+    ("w_sp3_64_64_28_res", 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, 28, 28, 64, 64, 0, None, True, 2, 2),
+    ("w_sp3_64_32_14", 64, 32, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, 14, 14, 64, 32, 0, None, False, 3, 2),
+    ("w_sp3_64_64_7_wrap", 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, 7, 7, 64, 64, 0, None, False, 3, 2),
+    ("w_sp3_32_128_oddH", 32, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, 28, 13, 32, 128, 0, None, False, 2, 3),
+    ("w_sp3_16_256_norelu", 16, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, 12, 20, 16, 256, 0, None, False, 1, 2, False),
+    ("w_g_sp3_8_8_J8", 8, 8, (1, 3, 3), (1, 1, 1), (0, 1, 1), 8, 56, 56, 8, 8, 0, None, False, 2, 3),
+    ("w_g_sp3_16_16_J4", 16, 16, (1, 3, 3), (1, 1, 1), (0, 1, 1), 4, 28, 28, 16, 16, 0, None, False, 2, 3),
+    ("w_g_sp3_32_32_J2", 32, 32, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 14, 14, 32, 32, 0, None, False, 2, 3),
+    ("w_g_sp3_s2_16_J2", 16, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1), 2, 56, 56, 16, 16, 0, None, False, 2, 3),
+    ("w_g_sp3_s2_8_J4_oddH", 8, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1), 4, 32, 27, 8, 16, 0, None, False, 2, 2),
+    ("w_sp33_kt3_16", 16, 32, (3, 3, 3), (1, 1, 1), (1, 1, 1), 1, 14, 14, 16, 32, 0, None, False, 2, 6),
+    ("w_stem_slow_J2", 3, 64, (1, 7, 7), (1, 2, 2), (0, 3, 3), 2, 64, 64, 4, 64, 3, 80, False, 2, 3),
+    ("w_stem_fast_J2", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 2, 64, 64, 4, 8, 3, 80, False, 2, 7),
+    ("w_stem_fast_J2_T1", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 2, 64, 64, 4, 8, 3, 80, False, 1, 1),
+    ("w_stem_fast_J2_224", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 2, 224, 224, 4, 8, 3, 240, False, 3, 8),
+    ("w_stem_slow_J2_224", 3, 64, (1, 7, 7), (1, 2, 2), (0, 3, 3), 2, 224, 224, 4, 64, 3, 240, False, 2, 3),
+]
+
+
 GROUP_CASES = [
     ("g_sp3_8_8_J4", 8, 8, (1, 3, 3), (1, 1, 1), (0, 1, 1), 4, 56, 16, 16, 0, None, False),
     ("g_sp3_s2_16_J4", 16, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1), 4, 56, 16, 16, 0, None, False),
@@ -379,7 +447,7 @@ def child(args):
         json.dump(report, open(args.out, "w"), indent=1)
 
     report["device"] = torch.cuda.get_device_name(0)
-    sections = [args.only] if args.only else ["mem", "simt", "probe", "conv"]
+    sections = [args.only] if args.only else ["mem", "simt", "probe", "conv", "window"]
     try:
         if "mem" in sections and "mem" not in report:
             report["mem"] = run_mem_checks()
@@ -399,6 +467,15 @@ def child(args):
             save()
             report["probe"] = run_probe()
             save()
+        if "window" in sections:
+            report.setdefault("window", {})
+            for wc in WINDOW_CASES:
+                if wc[0] in report["window"]:
+                    continue
+                report["window"][wc[0]] = {"ok": False, "crashed": True}
+                save()
+                report["window"][wc[0]] = run_window_case(*wc)
+                save()
         if "conv" in sections:
             for case in CONV_CASES:
                 if case[0] in report["conv_bf16"]:
@@ -457,7 +534,7 @@ def main():
         time.sleep(1)
     report = json.load(open(args.out)) if os.path.exists(args.out) else {}
     n_ok = n_bad = 0
-    for sec in ("mem", "conv_f32", "conv_bf16", "stem", "group"):
+    for sec in ("mem", "conv_f32", "conv_bf16", "stem", "group", "window"):
         for k, v in report.get(sec, {}).items():
             ok = bool(v.get("ok"))
             n_ok += ok

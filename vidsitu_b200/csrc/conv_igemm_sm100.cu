@@ -26,27 +26,10 @@
 #include <new>
 
 #include "common.h"
+#include "conv_plan.h"
 #include "ptx.cuh"
 
 namespace vsb {
-
-struct IgemmParams {
-  int m_total, to, ho, wo;
-  int st, sh, sw;
-  int lt, lh, lw;  // lower corner = -leading pad
-  int kh, kw;
-  int cin, cin_chunks, total_chunks, cps, kchunk;
-  int block_n, n_tiles, total_tiles, stages;
-  int epi_n, epi_chunks;  // epilogue column chunk (<= 64) and chunks per tile
-  int epi_bufs;           // staging buffers of the epilogue (residual prefetch distance = epi_bufs - 1)
-  int b_resident;         // all weight chunks stay in shared memory for the CTA's lifetime (n_tiles == 1)
-  uint32_t stage_bytes, off_bres, off_epi, off_bar;  // shared-memory layout (bytes from the 1 KiB-aligned base)
-  uint32_t idesc, tmem_cols;
-  const float* scale;
-  const float* bias;
-  int has_residual;
-  int relu;
-};
 
 constexpr int kBlockM = 128;
 constexpr int kEpiWarps = 8;
@@ -434,19 +417,11 @@ __global__ void im2col_probe_kernel(const __grid_constant__ CUtensorMap map, int
 
 // ------------------------------------------------------------------ host side
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
-                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn g_encode_tiled = nullptr;
+EncodeTiledFn g_encode_tiled = nullptr;
 static EncodeIm2colFn g_encode_im2col = nullptr;
 static int g_driver_version = 0;
 
-static int load_driver_entry_points() {
+int load_driver_entry_points() {
   static std::once_flag once;
   static int status = VSB_OK;
   std::call_once(once, [] {
@@ -474,7 +449,7 @@ static int load_driver_entry_points() {
   return status;
 }
 
-static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+CUtensorMapSwizzle swizzle_for(int row_bytes) {
   return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                              : (row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
@@ -530,17 +505,6 @@ int launch_conv_simt(const vsb_conv_desc& d, int to, int ho, int wo, cudaStream_
 
 }  // namespace vsb
 
-struct vsb_conv_plan {
-  vsb_conv_desc desc;
-  int to, ho, wo;
-  long long m_total;
-  // bf16 tensor-core path
-  CUtensorMap map_a, map_b, map_out, map_res;
-  vsb::IgemmParams params;
-  size_t smem_bytes;
-  unsigned grid;
-};
-
 using namespace vsb;
 
 extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** out_plan) {
@@ -568,9 +532,29 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   plan->wo = wo;
   plan->m_total = m_total;
 
+  plan->algo = 1;
   if (d->dtype == VSB_F32) {
     *out_plan = plan;
     return VSB_OK;
+  }
+  VSB_CHECK_ARG(d->algo >= 0 && d->algo <= 2, "algo must be 0 (auto), 1 (im2col) or 2 (window)");
+  if (d->algo == 2) {
+    const int wrc = win_plan_build(plan, d, to, ho, wo);
+    if (wrc == VSB_OK) {
+      plan->algo = 2;
+      *out_plan = plan;
+      return VSB_OK;
+    }
+    if (wrc > 0) set_error("conv is outside the domain of the shared-memory window algorithm (algo = 2)");
+    delete plan;
+    return wrc > 0 ? VSB_ERR_INVALID : wrc;
+  }
+  for (int k = 0; k < 8; ++k) {
+    if (d->kw_c_hi[k] != 0 && (d->kw_c_lo[k] != 0 || d->kw_c_hi[k] != d->cin)) {
+      set_error("partial per-tap channel ranges need the window algorithm (algo = 2)");
+      delete plan;
+      return VSB_ERR_INVALID;
+    }
   }
 
 #define FAIL(code, ...)     \
@@ -752,6 +736,7 @@ extern "C" int vsb_conv3d_run(const vsb_conv_plan* plan, void* stream) {
   VSB_CHECK_ARG(plan, "null plan");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (plan->desc.dtype == VSB_F32) return launch_conv_simt(plan->desc, plan->to, plan->ho, plan->wo, s);
+  if (plan->algo == 2) return win_plan_launch(plan, s);
   switch (plan->params.kchunk) {
     case 16:
       conv_igemm_kernel<1><<<plan->grid, kThreads, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_out,
@@ -804,5 +789,15 @@ extern "C" int vsb_debug_im2col_probe(const void* in, int n, int t, int h, int w
   im2col_probe_kernel<<<1, 128, bytes + 1024, static_cast<cudaStream_t>(stream)>>>(
       map, cc, cw, ch, cd, cn, ow, oh, od, bytes, static_cast<uint8_t*>(out));
   VSB_CHECK_LAUNCH("im2col_probe_kernel");
+  return VSB_OK;
+}
+
+// ---- debug: role timeline counters of a window-algorithm plan (VSB_WIN_DEBUG=1 at plan creation)
+extern "C" int vsb_debug_conv_stats(const vsb_conv_plan* plan, long long* out16) {
+  VSB_CHECK_ARG(plan && out16, "null argument");
+  VSB_CHECK_ARG(plan->algo == 2 && plan->win.dbg, "plan has no debug counters (window algorithm + VSB_WIN_DEBUG only)");
+  VSB_CHECK_CUDA(cudaDeviceSynchronize());
+  VSB_CHECK_CUDA(cudaMemcpy(out16, plan->win.dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  VSB_CHECK_CUDA(cudaMemset(plan->win.dbg, 0, 16 * sizeof(long long)));
   return VSB_OK;
 }

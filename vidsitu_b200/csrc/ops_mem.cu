@@ -35,14 +35,17 @@ __device__ __forceinline__ void store_px4<__nv_bfloat16>(__nv_bfloat16* dst, flo
   *reinterpret_cast<uint2*>(dst) = v;
 }
 
-// One thread = 16 consecutive pixels of one frame: 3 x 128-bit loads (48 B of
-// uint8), 16 x 4-channel stores.  frame_px (= h*w) must be a multiple of 16.
+// One block iteration = up to 1024 consecutive pixels of one frame: 192 threads stage the 3 KiB of
+// uint8 with 128-bit loads, then thread i converts pixels i, i+256, ... so that every store
+// instruction of a warp writes 32 consecutive pixels (fully coalesced 8/16-byte stores).
+// frame_px (= h*w) must be a multiple of 16.
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 pack_frames_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, int n, int t_in, int t_out,
-                   long long frame_px, int w, int out_w, int x_off, PackIdx idx, float m0, float m1, float m2,
+                   int frame_px, int w, int out_w, int x_off, PackIdx idx, float m0, float m1, float m2,
                    float s0, float s1, float s2, int reverse) {
   __shared__ float lut[3][256];
+  __shared__ __align__(16) uint8_t raw[2][3072];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) {
     const int c = i >> 8, x = i & 255;
     const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
@@ -52,39 +55,36 @@ pack_frames_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, i
     v = __fdiv_rn(v, sd);
     lut[c][x] = v;
   }
-  __syncthreads();
-  const long long units_per_frame = frame_px >> 4;
-  const long long total = (long long)n * t_out * units_per_frame;
-  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total;
-       u += (long long)gridDim.x * blockDim.x) {
-    const long long unit = u % units_per_frame;
-    const long long f = u / units_per_frame;
+  const int chunks_per_frame = (frame_px + 1023) >> 10;
+  const long long total = (long long)n * t_out * chunks_per_frame;
+  const int h = frame_px / w;
+  int buf = 0;
+  for (long long u = blockIdx.x; u < total; u += gridDim.x, buf ^= 1) {
+    const int chunk = (int)(u % chunks_per_frame);
+    const long long f = u / chunks_per_frame;
     const int to = (int)(f % t_out);
     const long long clip = f / t_out;
-    const uint8_t* src = frames + ((clip * t_in + idx.v[to]) * frame_px + unit * 16) * 3;
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
-    const uint4 c = __ldg(reinterpret_cast<const uint4*>(src) + 2);
-    const uint32_t wds[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-    // output rows may be wider than the frame (zero columns the conv halo reads): w % 16 == 0, so the
-    // 16 pixels of a unit stay inside one row
-    const long long px0 = unit * 16;
-    const long long y = px0 / w, x = px0 - y * w;
-    const long long h = frame_px / w;
-    OutT* dst = out + (((clip * t_out + to) * h + y) * out_w + x_off + x) * 4;
+    const int px0 = chunk << 10;
+    const int npx = min(1024, frame_px - px0);  // multiple of 16
+    const uint8_t* src = frames + ((clip * t_in + idx.v[to]) * (long long)frame_px + px0) * 3;
+    if ((int)threadIdx.x * 16 < npx * 3)
+      *reinterpret_cast<uint4*>(raw[buf] + threadIdx.x * 16) = __ldg(reinterpret_cast<const uint4*>(src) + threadIdx.x);
+    __syncthreads();  // also orders the LUT fill; the other buffer is free: its readers passed the previous barrier
+    OutT* dst_frame = out + ((clip * t_out + to) * (long long)h) * out_w * 4;
 #pragma unroll
-    for (int px = 0; px < 16; ++px) {
-      uint32_t ch[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int byte = px * 3 + k;
-        ch[k] = (wds[byte >> 2] >> ((byte & 3) * 8)) & 0xFF;
+    for (int k = 0; k < 4; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < npx) {
+        const int px = px0 + i;
+        const int y = px / w, x = px - y * w;
+        const uint8_t* b = raw[buf] + i * 3;
+        const uint32_t c0 = b[0], c1 = b[1], c2 = b[2];
+        // REVERSE_INPUT_CHANNEL flips AFTER the per-channel normalisation (video_utils.py:54-55)
+        const float r = reverse ? lut[2][c2] : lut[0][c0];
+        const float g = lut[1][c1];
+        const float bb = reverse ? lut[0][c0] : lut[2][c2];
+        store_px4<OutT>(dst_frame + ((long long)y * out_w + x_off + x) * 4, r, g, bb);
       }
-      // REVERSE_INPUT_CHANNEL flips AFTER the per-channel normalisation (video_utils.py:54-55)
-      const float r = reverse ? lut[2][ch[2]] : lut[0][ch[0]];
-      const float g = lut[1][ch[1]];
-      const float bb = reverse ? lut[0][ch[0]] : lut[2][ch[2]];
-      store_px4<OutT>(dst + px * 4, r, g, bb);
     }
   }
 }
@@ -95,10 +95,10 @@ struct Vec16;  // 16-byte vector of T
 template <>
 struct Vec16<float> {
   static constexpr int N = 4;
-  __device__ static void load(const float* p, float (&v)[8]) {
-    const float4 x = *reinterpret_cast<const float4*>(p);
-    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  __device__ static void unpack(const uint4& x, float (&v)[8]) {
+    v[0] = __uint_as_float(x.x); v[1] = __uint_as_float(x.y); v[2] = __uint_as_float(x.z); v[3] = __uint_as_float(x.w);
   }
+  __device__ static void load(const float* p, float (&v)[8]) { unpack(*reinterpret_cast<const uint4*>(p), v); }
   __device__ static void store(float* p, const float (&v)[8]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -106,8 +106,7 @@ struct Vec16<float> {
 template <>
 struct Vec16<__nv_bfloat16> {
   static constexpr int N = 8;
-  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 x = *reinterpret_cast<const uint4*>(p);
+  __device__ static void unpack(const uint4& x, float (&v)[8]) {
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -115,6 +114,7 @@ struct Vec16<__nv_bfloat16> {
       v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
     }
   }
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) { unpack(*reinterpret_cast<const uint4*>(p), v); }
   __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
     uint32_t w[4];
 #pragma unroll
@@ -132,12 +132,15 @@ struct PoolParams {
   int kt, kh, kw, st, sh, sw, pt, ph, pw;
 };
 
-// One thread = one 16-byte channel vector of one output pixel.
-template <typename T>
+// One thread = one 16-byte channel vector of one output pixel.  KT/KH/KW > 0 fix the window at
+// compile time: the (at most 9) loads are issued back to back before the first max, which is what
+// keeps enough bytes in flight to approach the HBM rate; 0 = run-time window (generic fallback).
+template <typename T, int KT, int KH, int KW>
 __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ in, T* __restrict__ out, PoolParams p) {
   constexpr int V = Vec16<T>::N;
   const int cvecs = p.c_out / V;
   const long long total = (long long)p.n * p.to * p.ho * p.wo * cvecs;
+  const int kt = KT ? KT : p.kt, kh = KH ? KH : p.kh, kw = KW ? KW : p.kw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvecs);
@@ -153,19 +156,48 @@ __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ in
     if (c0 < p.c) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) best[k] = -FLT_MAX;
-      for (int a = 0; a < p.kt; ++a) {
-        const int it = to * p.st - p.pt + a;
-        if (it < 0 || it >= p.t) continue;
-        for (int b = 0; b < p.kh; ++b) {
-          const int ih = ho * p.sh - p.ph + b;
-          if (ih < 0 || ih >= p.h) continue;
-          for (int d = 0; d < p.kw; ++d) {
-            const int iw = wo * p.sw - p.pw + d;
-            if (iw < 0 || iw >= p.w) continue;
+      if (KT * KH * KW > 0) {
+        constexpr int TAPS = KT * KH * KW > 0 ? KT * KH * KW : 1;
+        uint4 raw[TAPS];
+        bool ok[TAPS];
+#pragma unroll
+        for (int a = 0; a < (KT ? KT : 1); ++a)
+#pragma unroll
+          for (int b = 0; b < (KH ? KH : 1); ++b)
+#pragma unroll
+            for (int d = 0; d < (KW ? KW : 1); ++d) {
+              const int it = to * p.st - p.pt + a, ih = ho * p.sh - p.ph + b, iw = wo * p.sw - p.pw + d;
+              const int tap = (a * (KH ? KH : 1) + b) * (KW ? KW : 1) + d;
+              ok[tap] = it >= 0 && it < p.t && ih >= 0 && ih < p.h && iw >= 0 && iw < p.w;
+              raw[tap] = make_uint4(0, 0, 0, 0);
+              if (ok[tap])
+                raw[tap] = *reinterpret_cast<const uint4*>(
+                    in + ((((long long)nn * p.t + it) * p.h + ih) * p.w + iw) * p.in_pitch + c0);
+            }
+#pragma unroll
+        for (int tap = 0; tap < TAPS; ++tap) {
+          if (ok[tap]) {
             float v[8];
-            Vec16<T>::load(in + ((((long long)nn * p.t + it) * p.h + ih) * p.w + iw) * p.in_pitch + c0, v);
+            Vec16<T>::unpack(raw[tap], v);
 #pragma unroll
             for (int k = 0; k < V; ++k) best[k] = fmaxf(best[k], v[k]);
+          }
+        }
+      } else {
+        for (int a = 0; a < kt; ++a) {
+          const int it = to * p.st - p.pt + a;
+          if (it < 0 || it >= p.t) continue;
+          for (int b = 0; b < kh; ++b) {
+            const int ih = ho * p.sh - p.ph + b;
+            if (ih < 0 || ih >= p.h) continue;
+            for (int d = 0; d < kw; ++d) {
+              const int iw = wo * p.sw - p.pw + d;
+              if (iw < 0 || iw >= p.w) continue;
+              float v[8];
+              Vec16<T>::load(in + ((((long long)nn * p.t + it) * p.h + ih) * p.w + iw) * p.in_pitch + c0, v);
+#pragma unroll
+              for (int k = 0; k < V; ++k) best[k] = fmaxf(best[k], v[k]);
+            }
           }
         }
       }
@@ -344,17 +376,18 @@ extern "C" int vsb_pack_frames(const uint8_t* frames, int n, int t_in, int h, in
     pi.v[i] = idx[i];
   }
   for (int i = t_out; i < 64; ++i) pi.v[i] = 0;
-  const long long total = (long long)n * t_out * (frame_px / 16);
+  VSB_CHECK_ARG(frame_px < (1ll << 30), "frame too large");
+  const long long total = (long long)n * t_out * ((frame_px + 1023) / 1024);  // 1024-pixel chunks
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const unsigned grid = grid_for(total, 256);
+  const unsigned grid = (unsigned)(total < 148ll * 16 ? total : 148ll * 16);
   if (dtype == VSB_BF16) {
     pack_frames_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(frames, static_cast<__nv_bfloat16*>(out), n, t_in, t_out,
-                                                          frame_px, w, out_w, x_off, pi, mean3[0], mean3[1], mean3[2],
-                                                          std3[0], std3[1], std3[2], reverse_channels);
+                                                          (int)frame_px, w, out_w, x_off, pi, mean3[0], mean3[1],
+                                                          mean3[2], std3[0], std3[1], std3[2], reverse_channels);
   } else {
-    pack_frames_kernel<float><<<grid, 256, 0, s>>>(frames, static_cast<float*>(out), n, t_in, t_out, frame_px, w, out_w,
-                                                   x_off, pi, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2],
-                                                   reverse_channels);
+    pack_frames_kernel<float><<<grid, 256, 0, s>>>(frames, static_cast<float*>(out), n, t_in, t_out, (int)frame_px, w,
+                                                   out_w, x_off, pi, mean3[0], mean3[1], mean3[2], std3[0], std3[1],
+                                                   std3[2], reverse_channels);
   }
   VSB_CHECK_LAUNCH("pack_frames_kernel");
   return VSB_OK;
@@ -382,11 +415,18 @@ extern "C" int vsb_maxpool3d(const void* in, int n, int t, int h, int w, int c, 
   const long long total = (long long)n * p.to * p.ho * p.wo * (c_out / V);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = grid_for(total, 256);
-  if (dtype == VSB_BF16)
-    maxpool3d_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in),
-                                                        static_cast<__nv_bfloat16*>(out), p);
-  else
-    maxpool3d_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(in), static_cast<float*>(out), p);
+#define VSB_POOL_LAUNCH(T, KT, KH, KW) \
+  maxpool3d_kernel<T, KT, KH, KW><<<grid, 256, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), p)
+  if (dtype == VSB_BF16) {
+    if (kt == 1 && kh == 3 && kw == 3) VSB_POOL_LAUNCH(__nv_bfloat16, 1, 3, 3);       // stem pool
+    else if (kt == 2 && kh == 1 && kw == 1) VSB_POOL_LAUNCH(__nv_bfloat16, 2, 1, 1);  // i3d / c2d pathway pool
+    else if (kt == 1 && kh == 2 && kw == 2) VSB_POOL_LAUNCH(__nv_bfloat16, 1, 2, 2);  // non-local pool
+    else VSB_POOL_LAUNCH(__nv_bfloat16, 0, 0, 0);
+  } else {
+    if (kt == 1 && kh == 3 && kw == 3) VSB_POOL_LAUNCH(float, 1, 3, 3);
+    else VSB_POOL_LAUNCH(float, 0, 0, 0);
+  }
+#undef VSB_POOL_LAUNCH
   VSB_CHECK_LAUNCH("maxpool3d_kernel");
   return VSB_OK;
 }

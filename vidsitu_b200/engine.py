@@ -25,7 +25,8 @@ from . import ops
 from .arch import BlockSpec, ConvSpec, NetSpec, NonlocalSpec
 from .lib import VSB_BF16, VSB_F32, VsbError
 from .ops import Act, ConvPlan
-from .weights import fold_bn, group_conv_weight, identity_affine, pack_conv_weight, round_up
+from .weights import (fold_bn, group_conv_weight, group_tap_ranges, identity_affine, pack_conv_weight, round_up,
+                      slice_tap_channels)
 
 
 class _Pool:
@@ -167,6 +168,53 @@ class ClipEngine:
             j //= 2
         return max(j, 1)
 
+    def _window_plan(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act], relu: bool, scale, bias, wt,
+                     pad_w: Optional[int] = None, j: Optional[int] = None) -> Optional[ConvPlan]:
+        """Shared-memory window algorithm (conv_win_sm100.cu) for convs with spatial taps and <= 64
+        (grouped) input channels: returns the plan, or None when the layer is outside its domain."""
+        if self.dtype != VSB_BF16 or self._tune(cs.key).get("algo", "auto") == "im2col":
+            return None
+        if cs.kernel[1] * cs.kernel[2] == 1 or cs.stride[0] != 1 or x.h < 14:
+            return None
+        dense = lambda a: a is None or (a.pitch == a.c and a.c_off == 0)
+        sw = cs.stride[2]
+        if j is None:
+            j = self._tune(cs.key).get("win_group", max(1, (64 // x.c) // sw) if x.c <= 64 else 0)
+        if j < 1:
+            return None
+        # stems pass pad_w: their input rows carry a zero border, so grouped widths need not match
+        while j > 1 and (out.w % j or x.w % (j * sw) or (pad_w is None and out.w // j != x.w // (j * sw))):
+            j //= 2
+        g = j * sw
+        if g * x.c > 64 or (g * x.c) % 16 or (j * out.c) % 16 or j * out.c > 256:
+            return None
+        if g > 1 and not (dense(x) and dense(out) and dense(residual)):
+            return None
+        if x.w % g or out.w % j:
+            return None
+        pad_w = cs.pad[2] if pad_w is None else pad_w
+        w, ngt, plo = group_conv_weight(wt, x.c, out.c, j, sw, pad_w, self.tdt)
+        if ngt > 8 or plo < 0:
+            return None
+        ranges = group_tap_ranges(cs.kernel[2], x.c, j, sw, pad_w)
+        w = slice_tap_channels(w, cs.kernel[0] * cs.kernel[1], ngt, ranges)
+        xin = Act(x.buf, x.n, x.t, x.h, x.w // g, g * x.c, g * x.pitch if g == 1 else g * x.c, x.c_off if g == 1 else 0)
+        yout = Act(out.buf, out.n, out.t, out.h, out.w // j, j * out.c, out.pitch if j == 1 else j * out.c,
+                   out.c_off if j == 1 else 0)
+        res = None
+        if residual is not None:
+            res = Act(residual.buf, out.n, out.t, out.h, out.w // j, j * out.c,
+                      residual.pitch if j == 1 else j * out.c, residual.c_off if j == 1 else 0)
+        phi = yout.w - 1 + ngt - xin.w - plo
+        try:
+            return ConvPlan(self.dtype, xin, w, j * out.c, (cs.kernel[0], cs.kernel[1], ngt),
+                            (cs.stride[0], cs.stride[1], 1), (cs.pad[0], cs.pad[1], plo), (cs.pad[0], cs.pad[1], phi),
+                            scale.repeat(j), bias.repeat(j), yout, res, relu, algo=2, kw_ranges=ranges)
+        except VsbError:
+            if self._tune(cs.key).get("algo") == "window":
+                raise
+            return None
+
     def _conv(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act] = None, relu: Optional[bool] = None):
         if x.c_real != cs.cin:
             raise VsbError(f"{cs.key}: input has {x.c_real} channels, conv expects {cs.cin}")
@@ -174,8 +222,11 @@ class ClipEngine:
         tune = {k: v for k, v in self._tune(cs.key).items() if k in ("block_n", "kchunk", "stages")}
         relu = cs.relu if relu is None else relu
         wt = self._tensor(cs.key + ".weight")
-        j = self._group_factor(cs, x, out, residual)
-        if j > 1:
+        plan = self._window_plan(cs, x, out, residual, relu, scale, bias, wt)
+        j = self._group_factor(cs, x, out, residual) if plan is None else 0
+        if plan is not None:
+            pass
+        elif j > 1:
             sw = cs.stride[2]
             g = j * sw
             w, ngt, plo = group_conv_weight(wt, x.c, out.c, j, sw, cs.pad[2], self.tdt)
@@ -207,7 +258,18 @@ class ClipEngine:
         scale, bias = self._affine(cs, cs.cout)
         wt = self._tensor(cs.key + ".weight")
         tune = {k: v for k, v in self._tune(cs.key).items() if k in ("block_n", "kchunk", "stages")}
-        if self.dtype == VSB_BF16:
+        plan = None
+        if (self.dtype == VSB_BF16 and self.w_buf % 4 == 0 and wo % 2 == 0
+                and self._tune(cs.key).get("algo") == "window"):
+            # (off by default: 32-byte slots make the TMA box loads request-rate bound; measured slower)
+            # window algorithm on 2-pixel groups: 4 input pixels x 4 channels = one 32-byte slot
+            xw = Act(x.buf, n, t, x.h, self.w_buf, 4, 4)
+            yw = Act(y.buf, n, to, ho, wo, cs.cout, cs.cout)
+            plan = self._window_plan(cs, xw, yw, None, True, scale, bias, wt, pad_w=cs.pad[2] - self.x_off,
+                                     j=self._tune(cs.key).get("win_group", 2))
+        if plan is not None:
+            pass
+        elif self.dtype == VSB_BF16:
             # J output pixels per GEMM row on the zero-bordered input rows (x' = x + x_off, so the
             # conv needs no W padding): cin' = 2J*4, cout' = J*cout, kernel (kt,7,ngt), stride (1,2,1)
             sw = cs.stride[2]

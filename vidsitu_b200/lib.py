@@ -41,6 +41,9 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p),
         ("out_pitch", C.c_int),
         ("block_n", C.c_int), ("kchunk", C.c_int), ("stages", C.c_int),
+        ("algo", C.c_int),
+        ("kw_c_lo", C.c_int * 8),
+        ("kw_c_hi", C.c_int * 8),
     ]
 
 
@@ -81,12 +84,16 @@ def load() -> C.CDLL:
     lib.vsb_nthwc_to_ncthw_f32.argtypes = [vp, i, i, i, i, f32p, i, vp]
     lib.vsb_ncthw_f32_to_nthwc.argtypes = [f32p, i, i, ll, i, vp, i, i, i, i, vp]
     lib.vsb_debug_im2col_probe.argtypes = [vp] + [i] * 25 + [vp, vp]
+    lib.vsb_debug_umma_semantics.argtypes = [vp, i, vp, i, i, i, i, i, i, vp, vp]
+    lib.vsb_debug_umma_rate.argtypes = [i, i, i, i, i, i, vp, vp]
+    lib.vsb_debug_conv_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
     for name in ("vsb_pack_frames", "vsb_conv3d_plan_create", "vsb_conv3d_run", "vsb_conv3d_plan_out_shape",
                  "vsb_maxpool3d", "vsb_global_avgpool", "vsb_linear", "vsb_nonlocal_attention",
-                 "vsb_nthwc_to_ncthw_f32", "vsb_ncthw_f32_to_nthwc", "vsb_debug_im2col_probe"):
+                 "vsb_nthwc_to_ncthw_f32", "vsb_ncthw_f32_to_nthwc", "vsb_debug_im2col_probe",
+                 "vsb_debug_umma_semantics", "vsb_debug_umma_rate", "vsb_debug_conv_stats"):
         getattr(lib, name).restype = i
-    if lib.vsb_abi_version() != 1:
-        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 1")
+    if lib.vsb_abi_version() != 2:
+        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 2")
     _lib = lib
     return lib
 

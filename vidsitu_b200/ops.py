@@ -65,7 +65,8 @@ class ConvPlan:
     def __init__(self, dtype: int, x: Act, wgt: torch.Tensor, cout: int, kernel: Sequence[int],
                  stride: Sequence[int], pad_lo: Sequence[int], pad_hi: Optional[Sequence[int]],
                  scale: torch.Tensor, bias: torch.Tensor, out: Act, residual: Optional[Act] = None,
-                 relu: bool = False, block_n: int = 0, kchunk: int = 0, stages: int = 0):
+                 relu: bool = False, block_n: int = 0, kchunk: int = 0, stages: int = 0, algo: int = 0,
+                 kw_ranges: Optional[Sequence[Sequence[int]]] = None):
         _require_cuda(x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None)
         pad_hi = pad_lo if pad_hi is None else pad_hi
         d = ConvDesc()
@@ -86,14 +87,21 @@ class ConvPlan:
         d.out = out.ptr
         d.out_pitch = out.pitch
         d.block_n, d.kchunk, d.stages = block_n, kchunk, stages
+        d.algo = algo
+        k_per_tap_row = x.c * d.kw
+        if kw_ranges is not None:
+            if len(kw_ranges) != d.kw or d.kw > 8:
+                raise VsbError("kw_ranges needs one (lo, hi) pair per kw tap (kw <= 8)")
+            for k, (lo, hi) in enumerate(kw_ranges):
+                d.kw_c_lo[k], d.kw_c_hi[k] = int(lo), int(hi)
+            k_per_tap_row = sum(int(hi) - int(lo) for lo, hi in kw_ranges)
         expect = torch.bfloat16 if dtype == VSB_BF16 else torch.float32
         if x.buf.dtype != expect or wgt.dtype != expect or out.buf.dtype != expect:
             raise VsbError(f"conv tensors must be {expect}")
         if scale.dtype != torch.float32 or bias.dtype != torch.float32:
             raise VsbError("scale/bias must be float32")
-        taps = d.kt * d.kh * d.kw
-        if wgt.numel() != cout * taps * x.c:
-            raise VsbError(f"packed weight has {wgt.numel()} elements, expected {cout}x{taps}x{x.c}")
+        if wgt.numel() != cout * d.kt * d.kh * k_per_tap_row:
+            raise VsbError(f"packed weight has {wgt.numel()} elements, expected {cout}x{d.kt * d.kh}x{k_per_tap_row}")
         self._keep = (x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None)
         self._h = C.c_void_p()
         self._lib = _l.load()

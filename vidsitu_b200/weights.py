@@ -101,3 +101,29 @@ def group_conv_weight(w: torch.Tensor, cin_store: int, cout_store: int, J: int, 
             off = p * stride_w - pad_w + k
             out[p, :cout, :, :, off // G - gmin, off % G, :cin] = wp[..., k]
     return out.reshape(J * cout_store, kt * kh * ngt, G * cin_store).to(dtype).contiguous(), ngt, -gmin
+
+
+def group_tap_ranges(kw: int, cin_store: int, J: int, stride_w: int, pad_w: int):
+    """Per grouped tap gt of `group_conv_weight`: the 16-aligned channel range [lo, hi) of the
+    G*cin_store-channel input group that carries non-zero weights (the outer groups of a
+    block-Toeplitz tap row only contribute their first / last few pixels)."""
+    G = J * stride_w
+    offs = [p * stride_w - pad_w + k for p in range(J) for k in range(kw)]
+    gmin, gmax = min(offs) // G, max(offs) // G
+    ranges = []
+    for gt in range(gmin, gmax + 1):
+        rs = [o % G for o in offs if o // G == gt]
+        lo = (min(rs) * cin_store) // 16 * 16
+        hi = -(-((max(rs) + 1) * cin_store) // 16) * 16
+        ranges.append((lo, min(hi, G * cin_store)))
+    return ranges
+
+
+def slice_tap_channels(w: torch.Tensor, taps_outer: int, kw: int, ranges) -> torch.Tensor:
+    """[cout, taps_outer*kw, cin] -> [cout, taps_outer * sum(hi-lo)] keeping, for every kw tap, only
+    its channel range (the layout the window conv kernel expects when ranges are partial)."""
+    cout, taps, cin = w.shape
+    assert taps == taps_outer * kw and len(ranges) == kw
+    v = w.view(cout, taps_outer, kw, cin)
+    parts = [v[:, :, k, lo:hi] for k, (lo, hi) in enumerate(ranges)]
+    return torch.cat(parts, dim=2).reshape(cout, -1).contiguous()
