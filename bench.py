@@ -250,8 +250,16 @@ def main():
         all_ms = sum(ms_ for _, ms_, _ in per_op)
         flops = GFLOP_PER_CLIP * 1e9 * B
         achieved = flops / (conv_ms / 1e3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel", "achieved": round(achieved, 2),
-                    "peak": peak_sus, "unit": "TFLOP/s", "frac": round(achieved / peak_sus, 4), "traffic": None,
+        traffic = None   # DRAM bytes of the conv launches of one step, from the committed ncu capture
+        tp = os.path.join(ROOT, "profiles", "r01_step_dram_traffic.json")
+        if os.path.exists(tp) and B == 64:
+            ks = json.load(open(tp))["kernels"]
+            traffic = int(sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks if k["kernel"].startswith("conv_")))
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_win_kernel (all conv launches of a step)",
+                    "achieved": round(achieved, 2),
+                    "peak": peak_sus, "unit": "TFLOP/s", "frac": round(achieved / peak_sus, 4), "traffic": traffic,
+                    "traffic_note": "dram__bytes_read+write summed over the conv launches of one step (ncu, "
+                                    "profiles/r01_step_dram_traffic.json); algorithmic activation bytes 46 GB",
                     "peak_source": f"{peak_src} bf16_tflops_sustained (burst {peak_burst})",
                     "launches_per_step": len(conv), "conv_ms_per_step": round(conv_ms, 3),
                     "conv_share_of_step": round(conv_ms / all_ms, 4),

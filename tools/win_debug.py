@@ -1,5 +1,5 @@
-"""Role timeline of the window conv kernel on the SF50 layers that use it (VSB_WIN_DEBUG counters).
-    VSB_WIN_DEBUG=1 python tools/win_debug.py [op-substring ...]"""
+"""Role timeline of the tensor-core conv kernels on SF50 layers (VSB_WIN_DEBUG counters).
+    python tools/win_debug.py [op-substring ...]"""
 import ctypes as C, os, sys
 os.environ["VSB_WIN_DEBUG"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,28 +15,25 @@ eng = model._engine(n, torch.device("cuda"))
 frames = synthetic_frames(n, 32, 224, seed=1).cuda()
 eng.load_frames(frames); eng.run(); torch.cuda.synchronize()
 want = sys.argv[1:] or ["s2.pathway0_res1.branch2.b", "s2.pathway1_res1.branch2.b", "s3.pathway1_res1.branch2.b"]
-names = ["prod_wait_empty", "mma_wait_acc", "mma_wait_window", "mma_issue", "epi_wait_acc", "epi_wait_slab",
-         "epi_math", "epi_wait_store_read", "cta_total", "tiles", "epi_fence_syncwarp", "epi_tmem_ld", "x"]
+names = ["prod_wait_empty", "mma_wait_acc", "mma_wait_data", "mma_issue", "epi_wait_acc", "epi_wait_slab",
+         "epi_math", "epi_wait_store_read", "cta_total", "tiles", "epi_fence"]
 lib = L.load()
-plans = {}
-for pl in eng._keep:
-    if hasattr(pl, "_h"):
-        plans[id(pl)] = pl
 for name, fn, _ in eng.trunk_ops:
     if not any(w in name for w in want):
         continue
     plan = getattr(fn, "__self__", None)
-    if plan is None:
+    if plan is None or not hasattr(plan, "_h"):
         continue
     out = (C.c_longlong * 16)()
     if lib.vsb_debug_conv_stats(plan._h, out) != 0:
-        print(name, "-> not a window plan"); continue
+        print(name, "-> no counters"); continue
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     L.check(lib.vsb_debug_conv_stats(plan._h, out), "stats")
-    v = list(out)[:13]
-    tiles = max(v[9], 1)
-    ctas = 148
-    print(f"{name}: {e0.elapsed_time(e1)*1e3:.1f} us, tiles(epi warp0)={tiles}, cta_total/CTA={v[8]/ctas:.0f} clk")
-    for k in (0, 1, 2, 3, 4, 5, 6, 10, 7):
-        print(f"   {names[k]:22s} {v[k]/tiles:9.0f} clk/tile")
+    v = list(out)
+    grid, stages, smem = v[13], v[14], v[15]
+    tiles = max(v[9], 1)          # tiles seen by epilogue warp 0 of every CTA = all tiles
+    per_cta = tiles / grid
+    print(f"{name}: {e0.elapsed_time(e1)*1e3:.1f} us  grid={grid} stages={stages} smem={smem//1024}K tiles={tiles} "
+          f"({per_cta:.1f}/CTA)  cta_total={v[8]/grid:.0f} clk = {v[8]/grid/per_cta:.0f} clk/tile")
+    print("   " + "  ".join(f"{names[k]}={v[k]/tiles:.0f}" for k in (0, 1, 2, 3, 4, 5, 6, 7)))

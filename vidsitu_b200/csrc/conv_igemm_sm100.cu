@@ -27,15 +27,13 @@
 
 #include "common.h"
 #include "conv_plan.h"
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace vsb {
 
 constexpr int kBlockM = 128;
-constexpr int kEpiWarps = 8;
-constexpr int kProducerWarp = kEpiWarps;
-constexpr int kMmaWarp = kEpiWarps + 1;
-constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kMaxEpiWarps = 16;
 constexpr int kMaxEpiBufs = 4;  // per epilogue warp
 
 
@@ -45,13 +43,30 @@ constexpr int kMaxEpiBufs = 4;  // per epilogue warp
 //   TMEM  full/empty[2]        MMA issuer    <-> epilogue (two accumulators: the epilogue of tile i
 //                                                overlaps the main loop of tile i+1)
 //   epi   ready[2]             staging buffers of the epilogue (residual TMA load in, TMA store out)
-template <int KK>  // KK = kchunk / 16 MMAs per channel chunk; CPS = 4 / KK chunks per pipeline stage
-__global__ void __launch_bounds__(kThreads, 2)  // 2 CTAs / SM must fit: <= 102 registers per thread
+// Optional role timeline (kDbg, VSB_WIN_DEBUG=1 at plan time): cycles each role spends waiting, summed over CTAs
+// (same slots as conv_win_sm100.cu).
+#define IG_T(idx, stmt)                                   \
+  do {                                                    \
+    if (kDbg) {                                           \
+      const long long _t0 = clock64();                    \
+      stmt;                                               \
+      dbg_acc[idx] += (uint32_t)(clock64() - _t0);        \
+    } else {                                              \
+      stmt;                                               \
+    }                                                     \
+  } while (0)
+
+// KK = kchunk / 16 MMAs per channel chunk (CPS = 4 / KK chunks per pipeline stage); EW = epilogue warps:
+// 8 (two CTAs per SM: <= 102 registers per thread) or 16 (one CTA per SM; four warps per TMEM lane quarter
+// hide the latency chain TMEM -> registers -> shared memory of layers whose epilogue is the bottleneck).
+template <int KK, bool kDbg, int EW>
+__global__ void __launch_bounds__((EW + 2) * 32, EW == 8 ? 2 : 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                   const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kEpiWarps = EW, kProducerWarp = EW, kMmaWarp = EW + 1;
 
   const uint32_t row_bytes = p.kchunk * 2;
   const uint32_t a_chunk_bytes = kBlockM * row_bytes;
@@ -65,11 +80,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* tmem_full = empty_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* epi_ready = tmem_empty + 2;
-  uint64_t* bres_bar = epi_ready + kEpiWarps * kMaxEpiBufs;
+  uint64_t* bres_bar = epi_ready + kMaxEpiWarps * kMaxEpiBufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
+  uint32_t dbg_acc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long dbg_start = kDbg ? clock64() : 0;
 
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -138,7 +155,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         while (left > 0) {
           const int nch = left < cps ? left : cps;
           left -= nch;
-          mbar_wait(&empty_bar[slot], parity);
+          IG_T(0, mbar_wait(&empty_bar[slot], parity));
           mbar_expect_tx(&full_bar[slot], nch * stage_tx);
           uint8_t* a_dst = smem + (uint32_t)slot * stage_bytes;
           uint8_t* b_dst = a_dst + b_off;
@@ -191,13 +208,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (b_resident) mbar_wait(bres_bar, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step, ++tcount) {
       const int acc = tcount & 1;
-      mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+      IG_T(1, mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1));  // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * block_n;
       uint32_t bres_cur = bres_lo;
       for (int ks = 0; ks < full_stages; ++ks) {
-        mbar_wait(&full_bar[slot], parity);
+        IG_T(2, mbar_wait(&full_bar[slot], parity));
         tc_fence_after();
+        const long long issue_t0 = kDbg ? clock64() : 0;
         if (elect_one()) {
           const uint32_t a_lo = a_slot_lo;
           const uint32_t b_lo = b_resident ? bres_cur : a_slot_lo + b_off_lo;
@@ -214,6 +232,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (tail_chunks == 0 && ks == full_stages - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
         }
         __syncwarp();
+        if (kDbg) dbg_acc[3] += (uint32_t)(clock64() - issue_t0);
         bres_cur += CPS * b_chunk_lo;
         a_slot_lo += stage_lo;
         if (++slot == stages) {
@@ -223,7 +242,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
       }
       if (tail_chunks) {  // last, partially filled stage
-        mbar_wait(&full_bar[slot], parity);
+        IG_T(2, mbar_wait(&full_bar[slot], parity));
         tc_fence_after();
         if (elect_one()) {
           uint32_t a_lo = a_slot_lo;
@@ -251,9 +270,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else {
-    // ---------------------------------------------------------- epilogue (warps 0-7)
-    // Eight independent per-warp pipelines: warp w owns TMEM lanes / tile rows [32*(w&3), +32) and
-    // every second column chunk (global chunk parity == w>>2).  Each warp has its own staging
+    // ---------------------------------------------------------- epilogue (warps 0 .. EW-1)
+    // Independent per-warp pipelines: warp w owns TMEM lanes / tile rows [32*(w&3), +32) and every
+    // (EW/4)-th column chunk (global chunk counter mod EW/4 == w>>2).  Each warp has its own staging
     // slabs (32 rows x epi_n), its own residual TMA loads and its own TMA stores -- no block-level
     // barrier anywhere in the epilogue.
     const int quarter = warp & 3, grp = warp >> 2;
@@ -264,10 +283,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint8_t* my_bufs = epi_buf + (size_t)warp * nb * slab_bytes;
     uint64_t* my_ready = epi_ready + warp * kMaxEpiBufs;
     const int row_in_tile = quarter * 32;
+    const float relu_floor = p.relu ? 0.f : -__int_as_float(0x7f800000);
     // prefetch cursor (lane 0): next chunk of THIS warp whose staging slab has not been armed yet
     int pf_tile = blockIdx.x, pf_chunk = 0, pf_gq = 0, pf_q = 0;
     auto pf_skip = [&]() {  // advance the cursor to the next chunk owned by this warp's group
-      while (pf_tile < p.total_tiles && (pf_gq & 1) != grp) {
+      while (pf_tile < p.total_tiles && (pf_gq & (EW / 4 - 1)) != grp) {
         ++pf_gq;
         if (++pf_chunk == p.epi_chunks) {
           pf_chunk = 0;
@@ -306,72 +326,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int m0 = (tile / p.n_tiles) * kBlockM;
       const int nbase = n_tile * p.block_n;
       const int acc = tcount & 1;
-      mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+      IG_T(4, mbar_wait(&tmem_full[acc], (tcount >> 1) & 1));
+      if (kDbg) dbg_acc[9] += 1;
       tc_fence_after();
       for (int c = 0; c < p.epi_chunks; ++c, ++gq) {
-        if ((gq & 1) != grp) continue;
+        if ((gq & (EW / 4 - 1)) != grp) continue;
         const int b = q % nb;
         uint8_t* buf = my_bufs + b * slab_bytes;
-        mbar_wait(&my_ready[b], (q / nb) & 1);  // slab free (+ residual landed)
+        IG_T(5, mbar_wait(&my_ready[b], (q / nb) & 1));  // slab free (+ residual landed)
+        const long long math_t0 = kDbg ? clock64() : 0;
         const int col0 = nbase + c * p.epi_n;
-        for (int j0 = 0; j0 < p.epi_n; j0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(lane_taddr + acc * p.block_n + c * p.epi_n + j0, v);
-          // this thread's 32 bytes of its staging row, as two swizzled 16-byte chunks
-          const uint32_t off0 = lane * epi_row_bytes + j0 * 2;
-          uint4* s0 = reinterpret_cast<uint4*>(buf + (off0 ^ (((off0 >> 7) & swz_mask) << 4)));
-          const uint32_t off1 = off0 + 16;
-          uint4* s1 = reinterpret_cast<uint4*>(buf + (off1 ^ (((off1 >> 7) & swz_mask) << 4)));
-          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-          if (p.has_residual) {
-            r0 = *s0;
-            r1 = *s1;
-          }
-          float bi[16];
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j0) + qq);
-            bi[4 * qq + 0] = b4.x; bi[4 * qq + 1] = b4.y; bi[4 * qq + 2] = b4.z; bi[4 * qq + 3] = b4.w;
-          }
-          float x[16];
-          if (p.scale) {
-            float sc[16];
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + j0) + qq);
-              sc[4 * qq + 0] = s4.x; sc[4 * qq + 1] = s4.y; sc[4 * qq + 2] = s4.z; sc[4 * qq + 3] = s4.w;
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) x[e] = fmaf(__uint_as_float(v[e]), sc[e], bi[e]);
-          } else {  // BatchNorm scale already folded into the weights
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) x[e] = __uint_as_float(v[e]) + bi[e];
-          }
-          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-          uint32_t o[8];
-#pragma unroll
-          for (int qq = 0; qq < 8; ++qq) {
-            float x0 = x[2 * qq] + bf16_lo(rr[qq]);
-            float x1 = x[2 * qq + 1] + bf16_hi(rr[qq]);
-            if (p.relu) {
-              x0 = fmaxf(x0, 0.f);
-              x1 = fmaxf(x1, 0.f);
-            }
-            o[qq] = pack_bf16x2(x0, x1);
-          }
-          *s0 = make_uint4(o[0], o[1], o[2], o[3]);
-          *s1 = make_uint4(o[4], o[5], o[6], o[7]);
+        {
+          const uint32_t taddr = lane_taddr + acc * p.block_n + c * p.epi_n;
+          const float* sc = p.scale ? p.scale + col0 : nullptr;
+          if (p.has_residual)
+            epi_convert_chunk_g<true>(taddr, p.epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane, sc, p.bias + col0,
+                                      relu_floor);
+          else
+            epi_convert_chunk_g<false>(taddr, p.epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane, sc,
+                                       p.bias + col0, relu_floor);
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
         __syncwarp();
+        if (kDbg) dbg_acc[6] += (uint32_t)(clock64() - math_t0);
         if (lane == 0) {
           tma_store_2d(&map_out, buf, col0, m0 + row_in_tile);  // rows >= m_total are clipped by the TMA unit
           tma_store_commit();
           // arm the slab of this warp's chunk q + nb - 1 (the one chunk q - 1 used): its store must have read it
           if (pf_tile < p.total_tiles) {
-            tma_store_wait_read1();
+            IG_T(7, tma_store_wait_read1());
             arm_next();
           }
         }
@@ -386,6 +369,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) tma_store_wait_all();  // this warp's output bytes are in global memory before the CTA exits
   }
 
+  if (kDbg && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == 0)) {
+    if (warp == 0) dbg_acc[8] = (uint32_t)(clock64() - dbg_start);
+    for (int i = 0; i < 11; ++i)
+      if (dbg_acc[i]) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg) + i, (unsigned long long)dbg_acc[i]);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -595,46 +583,63 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   const int cps = 64 / kchunk;  // a pipeline stage always has room for 64 K-elements
   const int n_tiles = d->cout / block_n;
   const int num_kstages = ceil_div(total_chunks, cps);
-  // epilogue column chunk: 64 columns (128-byte staging rows); compute-bound layers (long K loop, no
-  // residual) take 32-column chunks so the staging slabs leave room for one more main-loop stage
-  int epi_n = block_n >= 64 ? 64 : block_n;
-  if (block_n >= 64 && !d->residual && num_kstages >= 8) epi_n = 32;
-  if (block_n % epi_n) FAIL(VSB_ERR_INVALID, "block_n %d is not a multiple of the epilogue chunk %d", block_n, epi_n);
   uint32_t tmem_cols = 32;  // two accumulators; TMEM allocations are powers of two >= 32 columns
   while (tmem_cols < (uint32_t)(2 * block_n)) tmem_cols <<= 1;
   // ---- shared-memory plan.  Weight-stationary when one n-tile covers cout and the whole [cout x K]
   // matrix fits: B is fetched once per CTA instead of once per tile.  With a residual the epilogue
-  // keeps 4 staging buffers so 3 residual chunks are in flight (HBM latency), otherwise 2.
+  // keeps 3 staging buffers per warp so 2 residual chunks are in flight (HBM latency), otherwise 2.
   const int a_stage = cps * kBlockM * kchunk * 2, b_stage = cps * block_n * kchunk * 2;
   const long long bres_bytes = (long long)total_chunks * block_n * kchunk * 2;
   static const bool no_bres = getenv("VSB_NO_BRES") != nullptr;
   const bool b_resident = !no_bres && n_tiles == 1 && bres_bytes <= 96 * 1024;
   const int stage_bytes = ((b_resident ? a_stage : a_stage + b_stage) + 1023) & ~1023;
-  const int epi_buf_bytes = kEpiWarps * 32 * epi_n * 2;  // one 32-row slab per epilogue warp
-  int epi_bufs = d->residual ? 3 : 2;  // slabs per epilogue warp (residual prefetch distance = epi_bufs - 1)
   const int bar_bytes = 1024;
-  int stages = d->stages;
+  int epi_warps = 8, epi_n = 0, epi_bufs = 0, stages = 0, epi_buf_bytes = 0;
   size_t smem_bytes = 0;
-  for (;;) {
-    const int fixed = (b_resident ? (int)((bres_bytes + 1023) & ~1023ll) : 0) + epi_bufs * epi_buf_bytes + bar_bytes + 1024;
-    if (!d->stages) {
-      // 512 TMEM columns => one CTA per SM anyway: use the whole shared memory; otherwise try to leave
-      // room for two CTAs per SM and fall back to one big CTA when that starves the pipeline
-      int budget = (tmem_cols == 512 ? 227 : 113) * 1024 - fixed;
-      stages = budget > 0 ? budget / stage_bytes : 0;
-      if (stages < 3 && stages < 2 * num_kstages) stages = (227 * 1024 - fixed) / stage_bytes;
-      if (stages > 8) stages = 8;
+  // Two shapes of CTA.  (A) 8 epilogue warps, sized so that two CTAs share an SM when they fit: two MMA
+  // chains and two epilogues per SM.  (B) when only one CTA fits anyway: 16 epilogue warps with
+  // 32-column chunks -- four warps per TMEM lane quarter keep the accumulator drain (the bottleneck of
+  // the wide 1x1x1 layers: short K, 256 output columns, residual) off the critical path.
+  static const char* ew_env = getenv("VSB_EPI_WARPS");
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    // (measured on B200: the 16-warp shape does not beat 8 warps -- these layers are HBM-bound, the accumulator
+    // wait is back-pressure -- so it is opt-in: VSB_EPI_WARPS=16)
+    epi_warps = (ew_env && atoi(ew_env) == 16) ? 16 : 8;
+    // epilogue column chunk: 64 columns (128-byte staging rows); compute-bound layers (long K loop, no
+    // residual) and the 16-warp shape take 32-column chunks so the staging slabs leave room for the ring
+    epi_n = block_n >= 64 ? 64 : block_n;
+    if (block_n >= 64 && ((!d->residual && num_kstages >= 8) || epi_warps == 16)) epi_n = 32;
+    if (block_n % epi_n) FAIL(VSB_ERR_INVALID, "block_n %d is not a multiple of the epilogue chunk %d", block_n, epi_n);
+    epi_buf_bytes = epi_warps * 32 * epi_n * 2;  // one 32-row slab per epilogue warp
+    epi_bufs = d->residual ? 3 : 2;  // slabs per epilogue warp (residual prefetch distance = epi_bufs - 1)
+    stages = d->stages;
+    bool fits = false;
+    for (;;) {
+      const int fixed = (b_resident ? (int)((bres_bytes + 1023) & ~1023ll) : 0) + epi_bufs * epi_buf_bytes + bar_bytes + 1024;
+      if (!d->stages) {
+        // 512 TMEM columns or 16 epilogue warps => one CTA per SM anyway: use the whole shared memory;
+        // otherwise try to leave room for two CTAs per SM and fall back to one big CTA when that starves
+        // the pipeline
+        int budget = ((tmem_cols == 512 || epi_warps == 16) ? 227 : 113) * 1024 - fixed;
+        stages = budget > 0 ? budget / stage_bytes : 0;
+        if (stages < 3 && stages < 2 * num_kstages) stages = (227 * 1024 - fixed) / stage_bytes;
+        if (stages > 8) stages = 8;
+      }
+      if (stages > 16) stages = 16;
+      if (stages > num_kstages * 2) stages = num_kstages * 2;
+      smem_bytes = (size_t)(stages > 0 ? stages : 0) * stage_bytes + fixed;
+      if (stages >= 3 && smem_bytes <= 227 * 1024) { fits = true; break; }
+      if (stages >= 1 && smem_bytes <= 227 * 1024 && (epi_bufs == 2 || stages >= 2 * num_kstages)) { fits = true; break; }
+      if (epi_bufs > 2) {
+        epi_bufs = 2;  // give the shared memory back to the main-loop pipeline
+        continue;
+      }
+      break;
     }
-    if (stages > 16) stages = 16;
-    if (stages > num_kstages * 2) stages = num_kstages * 2;
-    smem_bytes = (size_t)(stages > 0 ? stages : 0) * stage_bytes + fixed;
-    if (stages >= 3 && smem_bytes <= 227 * 1024) break;
-    if (stages >= 1 && smem_bytes <= 227 * 1024 && (epi_bufs == 2 || stages >= 2 * num_kstages)) break;
-    if (epi_bufs > 2) {
-      epi_bufs = 2;  // give the shared memory back to the main-loop pipeline
-      continue;
-    }
-    FAIL(VSB_ERR_INVALID, "pipeline (%d stages x %d bytes) does not fit in shared memory", stages, stage_bytes);
+    if (!fits) FAIL(VSB_ERR_INVALID, "pipeline (%d stages x %d bytes) does not fit in shared memory", stages, stage_bytes);
+    const bool two_ctas = epi_warps == 8 && tmem_cols <= 256 && smem_bytes <= 113 * 1024;
+    (void)two_ctas;
+    break;
   }
   const uint32_t off_bres = (uint32_t)stages * stage_bytes;
   const uint32_t off_epi = off_bres + (b_resident ? (uint32_t)((bres_bytes + 1023) & ~1023ll) : 0u);
@@ -687,6 +692,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   p.cin = d->cin; p.cin_chunks = cin_chunks; p.total_chunks = total_chunks; p.cps = cps; p.kchunk = kchunk;
   p.block_n = block_n; p.n_tiles = n_tiles; p.stages = stages;
   p.epi_bufs = epi_bufs; p.b_resident = b_resident ? 1 : 0;
+  p.epi_warps = epi_warps;
   p.stage_bytes = stage_bytes; p.off_bres = off_bres; p.off_epi = off_epi; p.off_bar = off_bar;
   p.total_tiles = (int)(ceil_div_ll(m_total, kBlockM) * p.n_tiles);
   p.epi_n = epi_n; p.epi_chunks = block_n / epi_n;
@@ -695,12 +701,17 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   p.scale = d->scale; p.bias = d->bias;
   p.has_residual = d->residual != nullptr;
   p.relu = d->relu;
+  p.dbg = nullptr;
+  if (getenv("VSB_WIN_DEBUG")) {  // debug only: the one place the library allocates device memory
+    if (cudaMalloc(&p.dbg, 16 * sizeof(long long)) == cudaSuccess) (void)cudaMemset(p.dbg, 0, 16 * sizeof(long long));
+    else p.dbg = nullptr;
+  }
   plan->smem_bytes = smem_bytes;
   int ctas_per_sm = (int)(512 / tmem_cols);
   const int by_smem = (int)((227 * 1024) / smem_bytes);
   if (ctas_per_sm > by_smem) ctas_per_sm = by_smem;
   if (ctas_per_sm > 2) ctas_per_sm = 2;
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm < 1 || epi_warps == 16) ctas_per_sm = 1;
   int sms = 148;
   {
     int dev = 0;
@@ -717,11 +728,16 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_igemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#define VSB_IG_ATTR(KK, DBG)                                                                                     \
+  if (attr_err == cudaSuccess)                                                                                   \
+    attr_err = cudaFuncSetAttribute(conv_igemm_kernel<KK, DBG, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                    227 * 1024);                                                                 \
+  if (attr_err == cudaSuccess)                                                                                   \
+    attr_err = cudaFuncSetAttribute(conv_igemm_kernel<KK, DBG, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                    227 * 1024)
+    VSB_IG_ATTR(1, false); VSB_IG_ATTR(2, false); VSB_IG_ATTR(4, false);
+    VSB_IG_ATTR(1, true); VSB_IG_ATTR(2, true); VSB_IG_ATTR(4, true);
+#undef VSB_IG_ATTR
   });
   if (attr_err != cudaSuccess) {
     set_error("cudaFuncSetAttribute(conv_igemm_kernel) failed: %s", cudaGetErrorString(attr_err));
@@ -737,20 +753,28 @@ extern "C" int vsb_conv3d_run(const vsb_conv_plan* plan, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (plan->desc.dtype == VSB_F32) return launch_conv_simt(plan->desc, plan->to, plan->ho, plan->wo, s);
   if (plan->algo == 2) return win_plan_launch(plan, s);
+#define VSB_IG_LAUNCH(KK, DBG)                                                                              \
+  do {                                                                                                      \
+    if (plan->params.epi_warps == 16)                                                                       \
+      conv_igemm_kernel<KK, DBG, 16><<<plan->grid, 18 * 32, plan->smem_bytes, s>>>(                         \
+          plan->map_a, plan->map_b, plan->map_out, plan->map_res, plan->params);                            \
+    else                                                                                                    \
+      conv_igemm_kernel<KK, DBG, 8><<<plan->grid, 10 * 32, plan->smem_bytes, s>>>(                          \
+          plan->map_a, plan->map_b, plan->map_out, plan->map_res, plan->params);                            \
+  } while (0)
+  const bool dbg = plan->params.dbg != nullptr;
   switch (plan->params.kchunk) {
     case 16:
-      conv_igemm_kernel<1><<<plan->grid, kThreads, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_out,
-                                                                         plan->map_res, plan->params);
+      if (dbg) VSB_IG_LAUNCH(1, true); else VSB_IG_LAUNCH(1, false);
       break;
     case 32:
-      conv_igemm_kernel<2><<<plan->grid, kThreads, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_out,
-                                                                         plan->map_res, plan->params);
+      if (dbg) VSB_IG_LAUNCH(2, true); else VSB_IG_LAUNCH(2, false);
       break;
     default:
-      conv_igemm_kernel<4><<<plan->grid, kThreads, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_out,
-                                                                         plan->map_res, plan->params);
+      if (dbg) VSB_IG_LAUNCH(4, true); else VSB_IG_LAUNCH(4, false);
       break;
   }
+#undef VSB_IG_LAUNCH
   VSB_CHECK_LAUNCH("conv_igemm_kernel");
   return VSB_OK;
 }
@@ -795,9 +819,13 @@ extern "C" int vsb_debug_im2col_probe(const void* in, int n, int t, int h, int w
 // ---- debug: role timeline counters of a window-algorithm plan (VSB_WIN_DEBUG=1 at plan creation)
 extern "C" int vsb_debug_conv_stats(const vsb_conv_plan* plan, long long* out16) {
   VSB_CHECK_ARG(plan && out16, "null argument");
-  VSB_CHECK_ARG(plan->algo == 2 && plan->win.dbg, "plan has no debug counters (window algorithm + VSB_WIN_DEBUG only)");
+  long long* dbg = plan->algo == 2 ? plan->win.dbg : plan->params.dbg;
+  VSB_CHECK_ARG(plan->desc.dtype == VSB_BF16 && dbg, "plan has no debug counters (bf16 plans created under VSB_WIN_DEBUG)");
   VSB_CHECK_CUDA(cudaDeviceSynchronize());
-  VSB_CHECK_CUDA(cudaMemcpy(out16, plan->win.dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-  VSB_CHECK_CUDA(cudaMemset(plan->win.dbg, 0, 16 * sizeof(long long)));
+  VSB_CHECK_CUDA(cudaMemcpy(out16, dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  VSB_CHECK_CUDA(cudaMemset(dbg, 0, 16 * sizeof(long long)));
+  out16[13] = plan->grid;
+  out16[14] = plan->algo == 2 ? plan->win.stages : plan->params.stages;
+  out16[15] = (long long)plan->smem_bytes;
   return VSB_OK;
 }

@@ -16,6 +16,7 @@ struct IgemmParams {
   int block_n, n_tiles, total_tiles, stages;
   int epi_n, epi_chunks;  // epilogue column chunk (<= 64) and chunks per tile
   int epi_bufs;           // staging buffers of the epilogue (residual prefetch distance = epi_bufs - 1)
+  int epi_warps;          // 8 (two CTAs per SM) or 16 (one CTA per SM)
   int b_resident;         // all weight chunks stay in shared memory for the CTA's lifetime (n_tiles == 1)
   uint32_t stage_bytes, off_bres, off_epi, off_bar;  // shared-memory layout (bytes from the 1 KiB-aligned base)
   uint32_t idesc, tmem_cols;
@@ -23,8 +24,8 @@ struct IgemmParams {
   const float* bias;
   int has_residual;
   int relu;
+  long long* dbg;  // role timeline counters (VSB_WIN_DEBUG), else null
 };
-
 
 // ---- shared-memory window algorithm (conv_win_sm100.cu)
 constexpr int kWinMaxTaps = 64;

@@ -91,6 +91,73 @@ __device__ __forceinline__ void epi_convert_chunk(uint32_t taddr, int ncols, uin
   }
 }
 
+// Same conversion with the per-channel (scale, bias) read from global memory (read-only path, L1
+// resident): scale == nullptr means the BatchNorm scale is already folded into the weights.
+template <bool kRes>
+__device__ __forceinline__ void epi_convert16_g(const uint32_t* v, const float* scale, const float* bias,
+                                                uint32_t buf_s, uint32_t off0, uint32_t swz_mask, float relu_floor) {
+  const uint32_t a0 = buf_s + (off0 ^ (((off0 >> 7) & swz_mask) << 4));
+  const uint32_t off1 = off0 + 16;
+  const uint32_t a1 = buf_s + (off1 ^ (((off1 >> 7) & swz_mask) << 4));
+  uint32_t rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (kRes) {
+    const uint4 r0 = lds128(a0), r1 = lds128(a1);
+    rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w;
+    rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+  }
+  float x[16];
+#pragma unroll
+  for (int qq = 0; qq < 4; ++qq) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + qq);
+    if (scale) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale) + qq);
+      x[4 * qq + 0] = fmaf(__uint_as_float(v[4 * qq + 0]), s4.x, b4.x);
+      x[4 * qq + 1] = fmaf(__uint_as_float(v[4 * qq + 1]), s4.y, b4.y);
+      x[4 * qq + 2] = fmaf(__uint_as_float(v[4 * qq + 2]), s4.z, b4.z);
+      x[4 * qq + 3] = fmaf(__uint_as_float(v[4 * qq + 3]), s4.w, b4.w);
+    } else {
+      x[4 * qq + 0] = __uint_as_float(v[4 * qq + 0]) + b4.x;
+      x[4 * qq + 1] = __uint_as_float(v[4 * qq + 1]) + b4.y;
+      x[4 * qq + 2] = __uint_as_float(v[4 * qq + 2]) + b4.z;
+      x[4 * qq + 3] = __uint_as_float(v[4 * qq + 3]) + b4.w;
+    }
+  }
+  uint32_t o[8];
+#pragma unroll
+  for (int qq = 0; qq < 8; ++qq) {
+    float x0 = x[2 * qq], x1 = x[2 * qq + 1];
+    if (kRes) {
+      x0 += bf16_lo(rr[qq]);
+      x1 += bf16_hi(rr[qq]);
+    }
+    o[qq] = pack_bf16x2(fmaxf(x0, relu_floor), fmaxf(x1, relu_floor));
+  }
+  sts128(a0, o[0], o[1], o[2], o[3]);
+  sts128(a1, o[4], o[5], o[6], o[7]);
+}
+
+template <bool kRes>
+__device__ __forceinline__ void epi_convert_chunk_g(uint32_t taddr, int ncols, uint32_t buf_s, uint32_t row_bytes,
+                                                    uint32_t swz_mask, int lane, const float* scale,
+                                                    const float* bias, float relu_floor) {
+  if (ncols >= 32) {
+    for (int j0 = 0; j0 < ncols; j0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + j0, v);
+      tmem_ld_wait();
+      const uint32_t off0 = lane * row_bytes + j0 * 2;
+      epi_convert16_g<kRes>(v, scale ? scale + j0 : nullptr, bias + j0, buf_s, off0, swz_mask, relu_floor);
+      epi_convert16_g<kRes>(v + 16, scale ? scale + j0 + 16 : nullptr, bias + j0 + 16, buf_s, off0 + 32, swz_mask,
+                            relu_floor);
+    }
+  } else {
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+    tmem_ld_wait();
+    epi_convert16_g<kRes>(v, scale, bias, buf_s, lane * row_bytes, swz_mask, relu_floor);
+  }
+}
+
 // Division-free walk over run = run0, run0 + step, ... decomposed as run = (n * tdim + t) * yb_count + yb.
 struct TileCursor {
   int run, yb, t, n;

@@ -72,8 +72,15 @@ class ClipEngine:
         self._keep: List[torch.Tensor] = []
         self.trunk_ops: List[Tuple[str, Callable[[], None], float]] = []   # (name, launch, flops)
         self.head_ops: List[Tuple[str, Callable[[], None], float]] = []
-        self._pool = _Pool(self.device, self.tdt)
+        # one buffer pool per pathway: the two pathways may run on two streams, and a pool hands buffers
+        # back out in stream order only
+        self._pools = [_Pool(self.device, self.tdt) for _ in range(max(1, spec.num_pathways))]
+        self._pool = self._pools[0]
         self._graph = None
+        import os
+        self.two_streams = (spec.num_pathways == 2 and dtype == VSB_BF16
+                            and str(self.tune.get("*", {}).get("streams", os.environ.get("VSB_STREAMS", "2"))) == "2")
+        self._side_stream = None
         self.op_bytes: Dict[str, float] = {}
         self.crop = spec.crop
         if self.crop % 16:
@@ -373,6 +380,7 @@ class ClipEngine:
         xs: List[Act] = []
         # s1: stem conv + BN + ReLU + max-pool per pathway (stem_helper.py:173-178)
         for p in range(npw):
+            self._pool = self._pools[p]
             y = self._stem(p, self.inputs[p])
             st = spec.stems[p]
             fuse = spec.fuses[0] if p == 0 else None
@@ -387,12 +395,14 @@ class ClipEngine:
             stage = spec.stages[si]
             nxt_fuse = spec.fuses[si + 1] if si + 1 < 4 else None
             for p in range(npw):
+                self._pool = self._pools[p]
                 out_c = stage[p][-1].c.cout
                 pitch = self._store(out_c) + nxt_fuse.cout if (nxt_fuse is not None and p == 0) else None
                 xs[p] = self._stage(xs[p], stage[p], pitch)
             if si == 0:
                 # pathway{p}_pool after res2 (mdl_sf_base.py:26-28): identity [1,1,1] pools are skipped
                 for p in range(npw):
+                    self._pool = self._pools[p]
                     k = spec.pool1[p]
                     if any(v != 1 for v in k):
                         if nxt_fuse is not None and p == 0:
@@ -447,9 +457,60 @@ class ClipEngine:
         for _, fn, _ in self.head_ops:
             fn()
 
+    @staticmethod
+    def _op_stream(name: str) -> int:
+        """0 = slow-pathway stream, 1 = fast-pathway stream (which also runs the lateral convs)."""
+        return 1 if ("pathway1" in name or "_fuse" in name) else 0
+
     def run(self) -> None:
-        self.run_trunk()
-        self.run_head()
+        """One forward.  SlowFast nets run their two pathways on two streams (fork after the inputs are
+        packed, join before the projection head): the pathways only meet at the lateral convs
+        (video_model_builder.py:124-131), which wait for the slow stage they write into and are waited
+        for by the next slow stage.  Stream order inside a pathway is the program order."""
+        if not self.two_streams:
+            self.run_trunk()
+            self.run_head()
+            return
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(self.device)
+        side = self._side_stream
+        streams = (main, side)
+
+        def sync(src: int, dst: int) -> None:
+            ev = torch.cuda.Event()
+            ev.record(streams[src])
+            streams[dst].wait_event(ev)
+
+        sync(0, 1)
+        prev_fuse = False
+        for name, fn, _ in self.trunk_ops:
+            sid = self._op_stream(name)
+            is_fuse = "_fuse" in name
+            if is_fuse:
+                sync(0, 1)          # the slow tensor the lateral conv writes into is complete (and live)
+            elif sid == 0 and prev_fuse:
+                sync(1, 0)          # the next slow stage reads the concatenated channels
+            if sid == 0:
+                fn()
+                if prev_fuse:
+                    prev_fuse = False
+            else:
+                with torch.cuda.stream(side):
+                    fn()
+                if is_fuse:
+                    prev_fuse = True
+        for name, fn, _ in self.head_ops:
+            if name.startswith("proj_head") and side is not None:
+                sync(1, 0)
+                side = None
+            if self._op_stream(name) == 1 and side is not None:
+                with torch.cuda.stream(side):
+                    fn()
+            else:
+                fn()
+        if side is not None:
+            sync(1, 0)
 
     def capture(self) -> None:
         """Capture trunk + head once into a CUDA graph (inputs/outputs are static buffers)."""
