@@ -210,6 +210,71 @@ __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ in
   }
 }
 
+// Stem pool fast path (bf16, window 1x3x3, stride (1,2,2), pad (0,1,1)): one block produces R output
+// rows of one frame.  Its 2R+1 input rows are staged in shared memory with fully coalesced 16-byte
+// loads (every input byte is fetched once per block instead of up to 2.25 times by scattered window
+// loads), then each thread reduces 3x3 windows with packed bf16 max (exact).
+__device__ __forceinline__ uint4 bf16x8_max(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_133_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, PoolParams p, int R) {
+  extern __shared__ uint4 pool_smem[];
+  const int cv_in = p.in_pitch / 8;             // 16-byte vectors per input pixel (row pitch in smem)
+  const int cv_real = (p.c + 7) / 8, cv_out = p.c_out / 8;
+  const int row_vecs = p.w * cv_in;
+  const int blocks_per_frame = (p.ho + R - 1) / R;
+  const int frame = blockIdx.x / blocks_per_frame;   // n * t + frame index (to == t)
+  const int yo0 = (blockIdx.x - frame * blocks_per_frame) * R;
+  const int rows_out = min(R, p.ho - yo0);
+  const int iy0 = 2 * yo0 - 1, rows_in = 2 * rows_out + 1;
+  const uint4* src = reinterpret_cast<const uint4*>(in) + (size_t)frame * p.h * row_vecs;
+  for (int i = threadIdx.x; i < rows_in * row_vecs; i += blockDim.x) {
+    const int r = i / row_vecs, v = i - r * row_vecs;
+    const int iy = iy0 + r;
+    if (iy >= 0 && iy < p.h) pool_smem[i] = src[(size_t)iy * row_vecs + v];
+  }
+  __syncthreads();
+  const uint4 ninf = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // bf16 -inf x 8
+  const int outs = rows_out * p.wo * cv_out;
+  uint4* dst = reinterpret_cast<uint4*>(out);
+  for (int o = threadIdx.x; o < outs; o += blockDim.x) {
+    const int cv = o % cv_out;
+    const int r2 = o / cv_out;
+    const int xo = r2 % p.wo, ro = r2 / p.wo;
+    uint4 best = make_uint4(0, 0, 0, 0);
+    if (cv < cv_real) {
+      best = ninf;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int iy = iy0 + 2 * ro + b;
+        if (iy < 0 || iy >= p.h) continue;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int ix = 2 * xo - 1 + d;
+          if (ix < 0 || ix >= p.w) continue;
+          best = bf16x8_max(best, pool_smem[((2 * ro + b) * p.w + ix) * cv_in + cv]);
+        }
+      }
+      const int c0 = cv * 8;
+      if (c0 + 8 > p.c) {  // channels of this vector beyond c are padding -> 0
+        uint16_t* h = reinterpret_cast<uint16_t*>(&best);
+        for (int k = 0; k < 8; ++k)
+          if (c0 + k >= p.c) h[k] = 0;
+      }
+    }
+    const size_t opix = ((size_t)frame * p.ho + yo0 + ro) * p.wo + xo;
+    dst[opix * (p.out_pitch / 8) + cv] = best;
+  }
+}
+
 // ------------------------------------------------------- global average pool
 // grid (n, ceil(c / (32*V))): each warp strides over the thw positions, each lane
 // owns one 16-byte channel vector; partial sums meet in shared memory.
@@ -415,6 +480,27 @@ extern "C" int vsb_maxpool3d(const void* in, int n, int t, int h, int w, int c, 
   const long long total = (long long)n * p.to * p.ho * p.wo * (c_out / V);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = grid_for(total, 256);
+  if (dtype == VSB_BF16 && kt == 1 && kh == 3 && kw == 3 && st == 1 && sh == 2 && sw == 2 && pt == 0 && ph == 1 &&
+      pw == 1 && in_pitch % 8 == 0 && out_pitch % 8 == 0 && c_out % 8 == 0) {
+    // rows per block: as many as fit ~60 KB of staged input rows
+    const long long row_bytes = (long long)w * in_pitch * 2;
+    int R = (int)((60 * 1024 / row_bytes - 1) / 2);
+    if (R > 8) R = 8;
+    if (R >= 1) {
+      const size_t smem = (size_t)(2 * R + 1) * row_bytes;
+      static bool attr_done = false;
+      if (!attr_done) {
+        VSB_CHECK_CUDA(cudaFuncSetAttribute(maxpool_133_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_done = true;
+      }
+      const long long blocks = (long long)n * p.to * ((p.ho + R - 1) / R);
+      VSB_CHECK_ARG(blocks < (1ll << 31), "too many pool blocks");
+      maxpool_133_rows_kernel<<<(unsigned)blocks, 256, smem, s>>>(static_cast<const __nv_bfloat16*>(in),
+                                                                 static_cast<__nv_bfloat16*>(out), p, R);
+      VSB_CHECK_LAUNCH("maxpool_133_rows_kernel");
+      return VSB_OK;
+    }
+  }
 #define VSB_POOL_LAUNCH(T, KT, KH, KW) \
   maxpool3d_kernel<T, KT, KH, KW><<<grid, 256, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), p)
   if (dtype == VSB_BF16) {

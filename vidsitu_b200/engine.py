@@ -125,10 +125,15 @@ class ClipEngine:
 
     # ------------------------------------------------------------------ building blocks
     def _store(self, c: int) -> int:
+        """Stored channel count.  8-channel tensors (the Fast pathway's res2 bottleneck) stay 8 wide on the
+        tensor-core path: they are only ever touched through pixel-group views (8 pixels x 8 channels = one
+        128-byte GEMM row), so padding them to the 16-channel MMA quantum would just double their traffic."""
+        if self.dtype == VSB_BF16 and c <= 8 and self.tune.get("*", {}).get("pad8", False) is False:
+            return round_up(c, 8)
         return round_up(c)
 
-    def _alloc(self, n, t, h, w, c_real, pitch: Optional[int] = None) -> Act:
-        c = self._store(c_real)
+    def _alloc(self, n, t, h, w, c_real, pitch: Optional[int] = None, min_c: int = 0) -> Act:
+        c = max(self._store(c_real), min_c)
         pitch = pitch or c
         buf = self._pool.take(n * t * h * w * pitch)
         return Act(buf, n, t, h, w, c, pitch, 0, c_real)
@@ -305,11 +310,11 @@ class ClipEngine:
         self.trunk_ops.append((cs.key, plan.run, float(y.pixels) * cs.flops_per_out_pixel))
         return y
 
-    def _maxpool(self, name: str, x: Act, kernel, stride, pad, pitch: Optional[int] = None) -> Act:
+    def _maxpool(self, name: str, x: Act, kernel, stride, pad, pitch: Optional[int] = None, min_c: int = 0) -> Act:
         to = (x.t + 2 * pad[0] - kernel[0]) // stride[0] + 1
         ho = (x.h + 2 * pad[1] - kernel[1]) // stride[1] + 1
         wo = (x.w + 2 * pad[2] - kernel[2]) // stride[2] + 1
-        y = self._alloc(x.n, to, ho, wo, x.c_real, pitch=pitch)
+        y = self._alloc(x.n, to, ho, wo, x.c_real, pitch=pitch, min_c=min_c)
         es = 2 if self.dtype == VSB_BF16 else 4
         self.op_bytes[name] = es * (x.pixels * x.c_real + y.pixels * y.c)
         self.trunk_ops.append((name, lambda: ops.maxpool3d(x, y, kernel, stride, pad, self.dtype), 0.0))
@@ -385,8 +390,9 @@ class ClipEngine:
             st = spec.stems[p]
             fuse = spec.fuses[0] if p == 0 else None
             pitch = self._store(y.c_real) + fuse.cout if fuse is not None else None
+            # (16 channels at least: the lateral conv reads this tensor un-grouped, 16 = one MMA K step)
             xs.append(self._maxpool(f"s1.pathway{p}_stem.pool_layer", y, st.pool_kernel, st.pool_stride, st.pool_pad,
-                                    pitch))
+                                    pitch, min_c=16))
             self._free(y)
         for si in range(4):
             fuse = spec.fuses[si]
