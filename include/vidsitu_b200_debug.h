@@ -33,6 +33,10 @@ int vsb_debug_umma_rate(int n, int iters, int a_tiles, int a_from_same, int grid
 struct vsb_conv_plan;
 int vsb_debug_conv_stats(const struct vsb_conv_plan* plan, long long* out16);
 
+/* How a conv plan will run: out8 = {algo (1 im2col, 2 window), temporal-scatter mode (0/1), pipeline
+ * stages, TMEM accumulators, grid, dynamic shared memory bytes, block_n, CTAs per SM the grid assumes}. */
+int vsb_debug_conv_plan_info(const struct vsb_conv_plan* plan, long long* out8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -261,7 +261,10 @@ def run_window_case(name, cin, cout, k, s, p, J, W, H, cin_store, cout_store, sh
     ref = _ref_conv(x.to(dev), wt, s, p, scale[:cout], bias[:cout], res[..., :cout] if use_res else None, relu)
     info = _compare(outbuf[..., :cout], ref, atol=2e-2, rtol=1.6e-2)
     info["pad_zero"] = bool((outbuf[..., cout:] == 0).all())
-    info["ok"] = info["n_bad"] == 0 and info["finite"] and info["pad_zero"]
+    info["plan"] = plan.info()
+    want_tsc = name.endswith("_tsc") or "_tsc_" in name
+    info["ok"] = (info["n_bad"] == 0 and info["finite"] and info["pad_zero"] and info["plan"]["algo"] == 2
+                  and (not want_tsc or info["plan"]["tsc"] == 1))
     return info
 
 
@@ -284,6 +287,14 @@ WINDOW_CASES = [
     ("w_stem_fast_J2_T1", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 2, 64, 64, 4, 8, 3, 80, False, 1, 1),
     ("w_stem_fast_J2_224", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 2, 224, 224, 4, 8, 3, 240, False, 3, 8),
     ("w_stem_slow_J2_224", 3, 64, (1, 7, 7), (1, 2, 2), (0, 3, 3), 2, 224, 224, 4, 64, 3, 240, False, 2, 3),
+    # temporal-scatter mode (kt > 1, kt * J * cout <= 256): accumulator ring of 16 / 8 slots, wrap-around, T edges
+    ("w_stem_fast_J4_tsc", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 4, 64, 64, 4, 8, 3, 80, False, 2, 7),
+    ("w_stem_fast_J4_tsc_T1", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 4, 64, 64, 4, 8, 3, 80, False, 1, 1),
+    ("w_stem_fast_J4_tsc_T2", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 4, 64, 64, 4, 8, 3, 80, False, 1, 2),
+    ("w_stem_fast_J4_tsc_T32", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 4, 64, 64, 4, 8, 3, 80, False, 3, 32),
+    ("w_stem_fast_J4_tsc_224", 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 4, 224, 224, 4, 8, 3, 240, False, 2, 19),
+    ("w_sp33_kt3_64_tsc", 16, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), 1, 14, 14, 16, 64, 0, None, False, 2, 13),
+    ("w_sp33_kt3_16_res_tsc", 16, 16, (3, 3, 3), (1, 1, 1), (1, 1, 1), 1, 28, 28, 16, 16, 0, None, True, 2, 21),
 ]
 
 

@@ -829,3 +829,17 @@ extern "C" int vsb_debug_conv_stats(const vsb_conv_plan* plan, long long* out16)
   out16[15] = (long long)plan->smem_bytes;
   return VSB_OK;
 }
+
+extern "C" int vsb_debug_conv_plan_info(const vsb_conv_plan* plan, long long* out8) {
+  VSB_CHECK_ARG(plan && out8, "null argument");
+  const bool win = plan->algo == 2;
+  out8[0] = plan->algo;
+  out8[1] = win ? plan->win.tsc : 0;
+  out8[2] = win ? plan->win.stages : plan->params.stages;
+  out8[3] = win ? plan->win.nacc : 2;
+  out8[4] = plan->grid;
+  out8[5] = (long long)plan->smem_bytes;
+  out8[6] = win ? plan->win.block_n : plan->params.block_n;
+  out8[7] = plan->smem_bytes <= 113 * 1024 ? 2 : 1;
+  return VSB_OK;
+}

@@ -53,7 +53,9 @@ struct WinParams {
   int k_per_frame;         // K elements of one frame (kh x sum of tap channel ranges)
   uint32_t b_block_bytes;
   int block_n, epi_n, epi_chunks, epi_bufs, epi_warps;
-  int nacc, nacc_shift;    // TMEM accumulators (2 or 4)
+  int nacc, nacc_shift;    // TMEM accumulators (2, 4, or the temporal-scatter ring: up to 16)
+  int tsc;                 // temporal-scatter mode: one N = kt * block_n MMA per K step, ring of nacc accumulators
+  int t_in;                // input frames
   int pair;                // MMA issuer interleaves two tiles (independent accumulation chains, shared B reads)
   int box_w, box_h;        // per-warp output box: 32 GEMM rows = box_h image rows x box_w slots
   uint32_t row_bytes;      // A row (slot) bytes: 32 / 64 / 128

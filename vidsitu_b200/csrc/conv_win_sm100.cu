@@ -58,6 +58,7 @@ constexpr int kProducerWarp = kEpiWarps;
 constexpr int kMmaWarp = kEpiWarps + 1;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kMaxEpiBufs = 4;
+constexpr int kMaxAcc = 16;  // TMEM accumulator ring slots (temporal-scatter mode uses all of them)
 }  // namespace
 
 template <bool kDbg>
@@ -74,8 +75,8 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;
-  uint64_t* tmem_empty = tmem_full + 4;
-  uint64_t* epi_ready = tmem_empty + 4;
+  uint64_t* tmem_empty = tmem_full + kMaxAcc;
+  uint64_t* epi_ready = tmem_empty + kMaxAcc;
   uint64_t* bres_bar = epi_ready + kEpiWarps * kMaxEpiBufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
@@ -94,7 +95,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], p.epi_warps);
     }
@@ -139,12 +140,22 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
       // frame kt's K range [kt*k_per_frame, +k_per_frame) starts on a block boundary in shared memory (a
       // block that runs past it just carries K columns no step refers to)
       mbar_expect_tx(bres_bar, p.b_blocks * p.b_block_bytes);
+      if (p.tsc) {
+        // temporal-scatter: K block j holds the weights of ALL temporal taps, kt descending = output frame
+        // ascending, as kt x [block_n rows x 128 B] (one N = kt * block_n operand)
+        const uint32_t tap_bytes = (uint32_t)p.block_n * 128u;
+        for (int kt = 0; kt < KT; ++kt)
+          for (int j = 0; j < p.b_blocks_per_frame; ++j)
+            tma_load_2d(bres + j * p.b_block_bytes + (uint32_t)(KT - 1 - kt) * tap_bytes, &map_b, bres_bar,
+                        kt * p.k_per_frame + j * 64, 0);
+      } else
       for (int kt = 0, g = 0; kt < KT; ++kt)
         for (int j = 0; j < p.b_blocks_per_frame; ++j, ++g)
           tma_load_2d(bres + g * p.b_block_bytes, &map_b, bres_bar, kt * p.k_per_frame + j * 64, 0);
       const CUtensorMap* m0 = p.sub_map[0] ? &map_in1 : &map_in0;
       const CUtensorMap* m1 = p.sub_map[1] ? &map_in1 : &map_in0;
-      const int nframes = L + KT - 1;
+      const int nframes = p.tsc ? p.t_in : L + KT - 1;  // temporal-scatter walks the real input frames only
+      const int f_base = p.tsc ? 0 : -p.pt_lo;
       int slot = 0;
       uint32_t parity = 1;  // first pass over the ring: slots are free
       TileCursor cur;
@@ -153,7 +164,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
         const int t0 = L == 1 ? cur.t : 0, n = cur.n;
         const int y0 = cur.yb * p.R;
         for (int fi = 0; fi < nframes; ++fi) {
-          const int f = t0 + fi - p.pt_lo;  // input frame; outside [0, T) -> zero-filled window
+          const int f = t0 + fi + f_base;  // input frame; outside [0, T) -> zero-filled window
           WIN_T(0, mbar_wait(&empty_bar[slot], parity));
           mbar_expect_tx(&full_bar[slot], p.stage_tx);
           uint8_t* dst = smem + (uint32_t)slot * p.stage_bytes;
@@ -185,7 +196,94 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
     int tcount = 0;
     const int amask = p.nacc - 1, ashift = p.nacc_shift;
     mbar_wait(bres_bar, 0);
-    if (p.pair) {
+    if (p.tsc) {
+      // Temporal-scatter (kt > 1): input-stationary along t.  The window of input frame f is read ONCE
+      // and multiplied by the weights of all temporal taps in a single N = nb * block_n MMA whose
+      // column blocks are the accumulators of output frames t = f + pt_lo - kt (kt descending = t
+      // ascending = consecutive slots of a ring of TMEM accumulators).  Versus the output-stationary
+      // loop this divides the shared-memory A reads (the bound of N <= 96 MMAs: ~60 clk per fresh
+      // 128 x 16 A slab whatever N) by kt, and the window ring only has to hide the load latency.
+      const int SL = p.nacc, slmask = SL - 1;
+      const int T_in = p.t_in, TO = p.to, ptl = p.pt_lo;
+      const uint32_t tap_lo = ((uint32_t)block_n * 128u) >> 4;      // B row block of one temporal tap
+      const uint32_t idesc0 = umma_idesc_bf16(128, 0), idesc_blk = ((uint32_t)block_n >> 3) << 17;
+      int slot = 0;
+      uint32_t par = 0;
+      int g0 = 0;  // global tile index of output frame 0 of the run (accumulator ring position)
+      for (int run = blockIdx.x; run < p.total_runs; run += gridDim.x, g0 += TO) {
+        for (int f = 0; f < T_in; ++f) {
+          const int t_top = f + ptl;
+          const int t_lo = t_top - (KT - 1) > 0 ? t_top - (KT - 1) : 0;
+          const int t_hi = t_top < TO - 1 ? t_top : TO - 1;
+          const bool top_fresh = f > 0 && t_top <= TO - 1;  // block t_top is written for the first time
+          // accumulators written for the first time must have been drained by the epilogue
+          if (f == 0) {
+            for (int t = t_lo; t <= t_hi; ++t)
+              WIN_T(1, mbar_wait(&tmem_empty[(g0 + t) & slmask], (((g0 + t) >> ashift) & 1) ^ 1));
+          } else if (top_fresh) {
+            WIN_T(1, mbar_wait(&tmem_empty[(g0 + t_top) & slmask], (((g0 + t_top) >> ashift) & 1) ^ 1));
+          }
+          WIN_T(2, mbar_wait(&full_bar[slot], par));
+          tc_fence_after();
+          const long long issue_t0 = kDbg ? clock64() : 0;
+          if (elect_one() && t_lo <= t_hi) {
+            const uint32_t a_slot = smem_lo + (uint32_t)slot * stage_lo;
+            const int nblk = t_hi - t_lo + 1;
+            const int s0 = (g0 + t_lo) & slmask;
+            const int n1 = nblk < SL - s0 ? nblk : SL - s0;  // blocks before the ring wraps
+            const int n2 = nblk - n1;                        // blocks from slot 0 on
+            const int rb0 = (KT - 1) - t_top + t_lo;         // B row block of output frame t_lo
+            const uint32_t d1 = tmem_base + (uint32_t)s0 * block_n, d2 = tmem_base;
+            const uint32_t acc_all = f == 0 ? 0u : 1u;
+            // step 0: the fresh top block (if any) must overwrite, the others accumulate
+            {
+              const uint2 e = step_tab[0];
+              const uint64_t ad = a_hi | (uint64_t)(e.x + a_slot);
+              const uint32_t b0 = e.y + bres_lo + (uint32_t)rb0 * tap_lo;
+              int m1 = n1, m2 = n2;
+              if (top_fresh) (n2 ? m2 : m1) -= 1;
+              if (m1) umma_bf16(d1, ad, b_hi | (uint64_t)b0, idesc0 + m1 * idesc_blk, acc_all);
+              if (m2) umma_bf16(d2, ad, b_hi | (uint64_t)(b0 + n1 * tap_lo), idesc0 + m2 * idesc_blk, acc_all);
+              if (top_fresh)
+                umma_bf16(tmem_base + (uint32_t)((g0 + t_top) & slmask) * block_n, ad,
+                          b_hi | (uint64_t)(b0 + (nblk - 1) * tap_lo), idesc0 + idesc_blk, 0u);
+            }
+            const uint32_t i1 = idesc0 + n1 * idesc_blk, i2 = idesc0 + n2 * idesc_blk;
+            if (n2 == 0) {
+#pragma unroll 4
+              for (int i = 1; i < spf; ++i) {
+                const uint2 e = step_tab[i];
+                umma_bf16(d1, a_hi | (uint64_t)(e.x + a_slot),
+                          b_hi | (uint64_t)(e.y + bres_lo + (uint32_t)rb0 * tap_lo), i1, 1u);
+              }
+            } else {
+#pragma unroll 2
+              for (int i = 1; i < spf; ++i) {
+                const uint2 e = step_tab[i];
+                const uint64_t ad = a_hi | (uint64_t)(e.x + a_slot);
+                const uint32_t b0 = e.y + bres_lo + (uint32_t)rb0 * tap_lo;
+                umma_bf16(d1, ad, b_hi | (uint64_t)b0, i1, 1u);
+                umma_bf16(d2, ad, b_hi | (uint64_t)(b0 + n1 * tap_lo), i2, 1u);
+              }
+            }
+            umma_commit(&empty_bar[slot]);
+            // output frames whose last contributing input frame this was
+            const int t_done = t_top - (KT - 1);
+            if (f == T_in - 1) {
+              for (int t = t_done > 0 ? t_done : 0; t < TO; ++t) umma_commit(&tmem_full[(g0 + t) & slmask]);
+            } else if (t_done >= 0 && t_done < TO) {
+              umma_commit(&tmem_full[(g0 + t_done) & slmask]);
+            }
+          }
+          __syncwarp();
+          if (kDbg) dbg_acc[3] += (uint32_t)(clock64() - issue_t0);
+          if (++slot == S) {
+            slot = 0;
+            par ^= 1;
+          }
+        }
+      }
+    } else if (p.pair) {
       // Two tiles at a time (KT == 1, one frame window each): their MMAs alternate, so two independent
       // accumulation chains are in flight and every weight K slice is used twice back to back.
       int slot = 0;
@@ -467,8 +565,14 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
   const int k_per_frame = d->kh * ksum;
   const int b_blocks_per_frame = (k_per_frame + 63) / 64;
   const int b_blocks = d->kt * b_blocks_per_frame;
-  const uint32_t b_block_bytes = (uint32_t)block_n * 128;
-  const long long b_bytes = (long long)b_blocks * b_block_bytes;
+  const long long b_bytes = (long long)b_blocks * block_n * 128;
+  // temporal-scatter mode (see the MMA issuer): all temporal taps in one N = kt * block_n MMA, output
+  // frames in a power-of-two ring of TMEM accumulators
+  static const bool no_tsc = getenv("VSB_WIN_NO_TSC") != nullptr;
+  int acc_slots = 512 / block_n > kMaxAcc ? kMaxAcc : 512 / block_n;
+  const bool tsc = !no_tsc && d->kt > 1 && d->kt * block_n <= 256 && (block_n & (block_n - 1)) == 0 &&
+                   acc_slots >= d->kt + 2 && d->pt_lo < d->kt && d->pt_hi < d->kt;
+  const uint32_t b_block_bytes = (uint32_t)block_n * 128 * (tsc ? d->kt : 1);
   int epi_n = block_n >= 64 ? 32 : block_n;  // >= 2 chunks per tile keep both epilogue warp groups busy
   if (block_n % epi_n) epi_n = 16;
   const int epi_chunks = block_n / epi_n;
@@ -485,14 +589,14 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
   for (;;) {
     const long long fixed = ((b_bytes + 1023) & ~1023ll) + (long long)epi_warps * epi_bufs * 32 * epi_n * 2 +
                             bar_bytes + 1024;
-    const int want = d->kt > 1 ? d->kt + 3 : 6;
+    const int want = tsc ? 3 : (d->kt > 1 ? d->kt + 3 : 6);
     // two co-resident CTAs per SM (two independent MMA chains) when a >= 4-stage ring fits in half the SM
     long long room = 113 * 1024 - fixed;
     if (d->kt > 1 || room < 4ll * stage_bytes) room = 227 * 1024 - fixed;
     stages = room > 0 ? (int)(room / stage_bytes) : 0;
     if (stages > want) stages = want;
     if (d->stages && stages > d->stages) stages = d->stages;
-    const int need = d->kt > 1 ? d->kt + 1 : 2;
+    const int need = tsc ? 2 : (d->kt > 1 ? d->kt + 1 : 2);
     if (stages >= need) {
       smem_bytes = (size_t)stages * stage_bytes + (size_t)fixed;
       break;
@@ -586,7 +690,9 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
   }
   p.steps_per_frame = spf;
   if (spf * 8 > 2048) return 1;
-  p.b_blocks = b_blocks; p.b_block_bytes = b_block_bytes;
+  p.b_blocks = tsc ? b_blocks_per_frame : b_blocks; p.b_block_bytes = b_block_bytes;
+  p.tsc = tsc ? 1 : 0;
+  p.t_in = d->t;
   p.b_blocks_per_frame = b_blocks_per_frame; p.k_per_frame = k_per_frame;
   p.block_n = block_n; p.epi_n = epi_n; p.epi_chunks = epi_chunks; p.epi_bufs = epi_bufs; p.epi_warps = epi_warps;
   p.box_w = box_w; p.box_h = box_h;
@@ -598,8 +704,9 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
   p.idesc = umma_idesc_bf16(128, block_n);
   static const bool no_pair = getenv("VSB_WIN_NO_PAIR") != nullptr;
   p.pair = (!no_pair && d->kt == 1 && block_n <= 128 && stages >= 4) ? 1 : 0;
-  p.nacc = p.pair ? 4 : 2;
-  p.nacc_shift = p.pair ? 2 : 1;
+  p.nacc = tsc ? acc_slots : (p.pair ? 4 : 2);
+  p.nacc_shift = 0;
+  while ((1 << p.nacc_shift) < p.nacc) ++p.nacc_shift;
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(p.nacc * block_n)) tmem_cols <<= 1;
   p.tmem_cols = tmem_cols;

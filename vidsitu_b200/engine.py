@@ -271,14 +271,16 @@ class ClipEngine:
         wt = self._tensor(cs.key + ".weight")
         tune = {k: v for k, v in self._tune(cs.key).items() if k in ("block_n", "kchunk", "stages")}
         plan = None
-        if (self.dtype == VSB_BF16 and self.w_buf % 4 == 0 and wo % 2 == 0
-                and self._tune(cs.key).get("algo") == "window"):
-            # (off by default: 32-byte slots make the TMA box loads request-rate bound; measured slower)
-            # window algorithm on 2-pixel groups: 4 input pixels x 4 channels = one 32-byte slot
+        algo = self._tune(cs.key).get("algo", "auto")
+        if self.dtype == VSB_BF16 and (algo == "window" or (algo == "auto" and cs.kernel[0] > 1)):
+            # window algorithm on J-pixel groups (2J input pixels x 4 channels = one slot).  Stems with
+            # temporal taps (the Fast pathway's 5x7x7) run in its temporal-scatter mode: J = 4 -> 64-byte
+            # slots, N = kt * 4 * cout per MMA, every frame window read from shared memory once.
+            # (kt == 1 stems: off by default -- 32-byte slots make the TMA box loads request-rate bound.)
             xw = Act(x.buf, n, t, x.h, self.w_buf, 4, 4)
             yw = Act(y.buf, n, to, ho, wo, cs.cout, cs.cout)
             plan = self._window_plan(cs, xw, yw, None, True, scale, bias, wt, pad_w=cs.pad[2] - self.x_off,
-                                     j=self._tune(cs.key).get("win_group", 2))
+                                     j=self._tune(cs.key).get("win_group", 4 if cs.kernel[0] > 1 else 2))
         if plan is not None:
             pass
         elif self.dtype == VSB_BF16:

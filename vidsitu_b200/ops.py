@@ -117,6 +117,13 @@ class ConvPlan:
     def run(self) -> None:
         check(self._lib.vsb_conv3d_run(self._h, _stream_ptr()), "vsb_conv3d_run")
 
+    def info(self) -> dict:
+        """How the plan runs (debug / tests): algorithm, mode, pipeline depth, grid, shared memory."""
+        out = (C.c_longlong * 8)()
+        check(self._lib.vsb_debug_conv_plan_info(self._h, out), "vsb_debug_conv_plan_info")
+        keys = ("algo", "tsc", "stages", "nacc", "grid", "smem_bytes", "block_n", "ctas_per_sm")
+        return dict(zip(keys, [int(v) for v in out]))
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:
