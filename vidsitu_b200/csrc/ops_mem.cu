@@ -3,6 +3,7 @@
 // channels-last with 128-bit accesses; none of them is reshaped into a GEMM.
 #include <cuda_bf16.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -275,6 +276,62 @@ maxpool_133_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __r
   }
 }
 
+// Stem pool, streaming form (bf16, window 1x3x3, stride (1,2,2), pad (0,1,1)): one thread owns one
+// 16-byte channel vector of one output column and walks RY output rows down the frame.  Per output
+// row it loads two new input rows x three columns (the third window row is the previous iteration's
+// last row, carried in registers), all with clamped coordinates -- a clamped duplicate never changes
+// a max, so there is no branch and no -inf.  Every input byte leaves HBM once; the 1.5x horizontal
+// overlap between neighbouring threads is served by L1.  No shared memory, no barrier: the SM keeps
+// thousands of independent 16-byte loads in flight.
+template <int RY>
+__global__ void __launch_bounds__(256)
+maxpool_133_stream_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolParams p, int strips,
+                          long long total) {
+  const int cv_in = p.in_pitch / 8, cv_out = p.c_out / 8, cv_real = (p.c + 7) / 8, op = p.out_pitch / 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cv_out);
+    long long r = idx / cv_out;
+    const int xo = (int)(r % p.wo); r /= p.wo;
+    const int strip = (int)(r % strips);
+    const long long frame = r / strips;
+    const int y0 = strip * RY, y1 = min(y0 + RY, p.ho);
+    uint4* dst = out + ((frame * p.ho + y0) * p.wo + xo) * op + cv;
+    const size_t dstep = (size_t)p.wo * op;
+    if (cv >= cv_real) {  // channel padding
+      for (int y = y0; y < y1; ++y, dst += dstep) *dst = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const int xc = 2 * xo, xl = xc > 0 ? xc - 1 : xc, xr = xc + 1 < p.w ? xc + 1 : xc;
+    const uint4* src = in + frame * p.h * p.w * cv_in + cv;
+    const size_t rstep = (size_t)p.w * cv_in;
+    const int ol = xl * cv_in, oc = xc * cv_in, orr = xr * cv_in;
+    uint4 carry;
+    {
+      const uint4* row = src + (size_t)(y0 > 0 ? 2 * y0 - 1 : 0) * rstep;
+      carry = bf16x8_max(bf16x8_max(row[ol], row[oc]), row[orr]);
+    }
+    // channels of this vector beyond c are padding -> 0
+    uint4 keep = make_uint4(~0u, ~0u, ~0u, ~0u);
+    if (cv * 8 + 8 > p.c) {
+      uint16_t* hk = reinterpret_cast<uint16_t*>(&keep);
+      for (int k = 0; k < 8; ++k)
+        if (cv * 8 + k >= p.c) hk[k] = 0;
+    }
+#pragma unroll 2
+    for (int y = y0; y < y1; ++y, dst += dstep) {
+      const uint4* ra = src + (size_t)(2 * y) * rstep;
+      const uint4* rb = src + (size_t)(2 * y + 1 < p.h ? 2 * y + 1 : 2 * y) * rstep;
+      const uint4 a0 = ra[ol], a1 = ra[oc], a2 = ra[orr], b0 = rb[ol], b1 = rb[oc], b2 = rb[orr];
+      const uint4 hb = bf16x8_max(bf16x8_max(b0, b1), b2);
+      uint4 best = bf16x8_max(bf16x8_max(bf16x8_max(a0, a1), a2), bf16x8_max(carry, hb));
+      carry = hb;
+      best.x &= keep.x; best.y &= keep.y; best.z &= keep.z; best.w &= keep.w;
+      *dst = best;
+    }
+  }
+}
+
 // ------------------------------------------------------- global average pool
 // grid (n, ceil(c / (32*V))): each warp strides over the thw positions, each lane
 // owns one 16-byte channel vector; partial sums meet in shared memory.
@@ -482,6 +539,18 @@ extern "C" int vsb_maxpool3d(const void* in, int n, int t, int h, int w, int c, 
   const unsigned grid = grid_for(total, 256);
   if (dtype == VSB_BF16 && kt == 1 && kh == 3 && kw == 3 && st == 1 && sh == 2 && sw == 2 && pt == 0 && ph == 1 &&
       pw == 1 && in_pitch % 8 == 0 && out_pitch % 8 == 0 && c_out % 8 == 0) {
+    static const bool staged = getenv("VSB_POOL_STAGED") != nullptr;  // previous shared-memory staged variant
+    if (!staged) {
+      constexpr int RY = 8;
+      const int strips = (p.ho + RY - 1) / RY;
+      const long long threads = (long long)n * p.to * strips * p.wo * (c_out / 8);
+      const long long blocks = (threads + 255) / 256;
+      VSB_CHECK_ARG(blocks < (1ll << 31), "too many pool blocks");
+      maxpool_133_stream_kernel<RY><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const uint4*>(in),
+                                                                    static_cast<uint4*>(out), p, strips, threads);
+      VSB_CHECK_LAUNCH("maxpool_133_stream_kernel");
+      return VSB_OK;
+    }
     // rows per block: as many as fit ~60 KB of staged input rows
     const long long row_bytes = (long long)w * in_pitch * 2;
     int R = (int)((60 * 1024 / row_bytes - 1) / 2);
@@ -536,12 +605,86 @@ extern "C" int vsb_global_avgpool(const void* in, int n, int thw, int c, int in_
   return VSB_OK;
 }
 
+// Tiled form for din % 4 == 0: a block owns LT_ROWS rows x 32 neurons.  The x chunk is staged once per
+// block in shared memory (the warp-per-neuron kernel above re-reads x through L2 once per warp:
+// 765 MB for proj_head.0 at 64 clips); a warp owns 4 neurons, lanes stride over K with 128-bit loads
+// and keep 4 x LT_ROWS accumulators; a shuffle tree reduces them.  Summation order is fixed
+// (deterministic, batch-invariant: a row's result does not depend on the other rows).
+constexpr int LT_ROWS = 16, LT_KC = 256;
+__global__ void __launch_bounds__(256)
+linear_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                    float* __restrict__ y, int n, int din, int dout, int relu) {
+  __shared__ float4 xs[LT_ROWS][LT_KC / 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o0 = blockIdx.x * 32 + warp * 4;
+  const int r0 = blockIdx.y * LT_ROWS;
+  float acc[4][LT_ROWS];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int r = 0; r < LT_ROWS; ++r) acc[j][r] = 0.f;
+  for (int kc = 0; kc < din; kc += LT_KC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < LT_ROWS * (LT_KC / 4); i += 256) {
+      const int r = i / (LT_KC / 4), k4 = i - r * (LT_KC / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < n && kc + k4 * 4 < din) v = *reinterpret_cast<const float4*>(x + (long long)(r0 + r) * din + kc + k4 * 4);
+      xs[r][k4] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < LT_KC / 128; ++h) {
+      const int k4 = h * 32 + lane;
+      const int k = kc + k4 * 4;
+      float4 wv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        wv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o0 + j < dout && k < din) wv[j] = __ldg(reinterpret_cast<const float4*>(w + (long long)(o0 + j) * din + k));
+      }
+#pragma unroll
+      for (int r = 0; r < LT_ROWS; ++r) {
+        const float4 xv = xs[r][k4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[j][r] = fmaf(wv[j].x, xv.x, acc[j][r]);
+          acc[j][r] = fmaf(wv[j].y, xv.y, acc[j][r]);
+          acc[j][r] = fmaf(wv[j].z, xv.z, acc[j][r]);
+          acc[j][r] = fmaf(wv[j].w, xv.w, acc[j][r]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int o = o0 + j;
+    const float bias = (b && o < dout) ? b[o] : 0.f;
+#pragma unroll
+    for (int r = 0; r < LT_ROWS; ++r) {
+      float v = acc[j][r];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0 && o < dout && r0 + r < n) {
+        v += bias;
+        if (relu) v = fmaxf(v, 0.f);
+        y[(long long)(r0 + r) * dout + o] = v;
+      }
+    }
+  }
+}
+
 extern "C" int vsb_linear(const float* x, int n, int din, const float* w, const float* b, float* y, int dout,
                           int relu, void* stream) {
   VSB_CHECK_ARG(x && w && y, "null argument");
   VSB_CHECK_ARG(n > 0 && din > 0 && dout > 0, "bad extent");
   VSB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0,
                 "x and w must be 16-byte aligned");
+  if ((din & 3) == 0) {
+    dim3 grid(ceil_div(dout, 32), ceil_div(n, LT_ROWS));
+    linear_tiled_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, b, y, n, din, dout, relu);
+    VSB_CHECK_LAUNCH("linear_tiled_kernel");
+    return VSB_OK;
+  }
   dim3 grid(ceil_div(dout, 8), ceil_div(n, LIN_ROWS));
   linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, b, y, n, din, dout, relu);
   VSB_CHECK_LAUNCH("linear_kernel");
