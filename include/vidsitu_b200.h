@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VSB_ABI_VERSION 2
+#define VSB_ABI_VERSION 3
 
 typedef enum vsb_status {
   VSB_OK = 0,
@@ -106,6 +106,18 @@ typedef struct vsb_conv_desc {
    * only those channels: [cout][kt][kh][sum_kw (hi - lo)].                             */
   int kw_c_lo[8];
   int kw_c_hi[8];
+  /* Optional second source (bf16 im2col algorithm only): a strided 1x1x1 conv over `in2` accumulated
+   * into the SAME output, i.e. the projection shortcut of a ResBlock (resnet_helper.py:326-358:
+   * relu(branch1_bn(branch1(x)) + branch2(x))) computed inside the block's last conv instead of as a
+   * separate launch whose result is written to and re-read from HBM as `residual`:
+   *   out[m, co] = act(scale[co] * (sum_k in[..] * wgt[co, k] + sum_ci in2[pix2(m), ci] * wgt[co, K + ci]) + bias[co])
+   * pix2(m) = (n, to*st2, ho*sh2, wo*sw2).  Both BatchNorms share the epilogue scale: the caller folds
+   * the ratio of the two BN scales into one of the weight blocks (fp32 master weights, one bf16
+   * rounding) and sums the biases.  wgt rows are [K = kt*kh*kw*cin | cin2 rounded up to kchunk].
+   * in2 == NULL: no second source.                                                        */
+  const void* in2;
+  int t2, h2, w2, cin2, in2_pitch;
+  int st2, sh2, sw2;
 } vsb_conv_desc;
 
 typedef struct vsb_conv_plan vsb_conv_plan;

@@ -111,6 +111,19 @@ def test_window_conv(case):
     assert info["ok"], info
 
 
+def _dual_cases():
+    import gpu_check_ops as G
+    return G.DUAL_CASES
+
+
+@pytest.mark.parametrize("case", _dual_cases(), ids=lambda c: c[0])
+def test_conv_with_fused_shortcut(case):
+    """vsb_conv_desc.in2: the ResBlock projection shortcut as a second K segment of the block's last conv."""
+    import gpu_check_ops as G
+    info = G.run_dual_case(*case)
+    assert info["ok"], info
+
+
 def test_memory_bound_ops():
     import gpu_check_ops as G
     res = G.run_mem_checks()

@@ -268,6 +268,49 @@ def run_window_case(name, cin, cout, k, s, p, J, W, H, cin_store, cout_store, sh
     return info
 
 
+def run_dual_case(name, cb, cx, cout, s, n, t, H, W, x_pitch=None):
+    """1x1x1 conv over `b` + strided 1x1x1 projection over `x` accumulated into one output
+    (vsb_conv_desc.in2: the ResBlock shortcut fused into the block's last conv)."""
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(zlib.crc32(name.encode()) % (2 ** 31))
+    ho, wo = (H - 1) // s + 1, (W - 1) // s + 1
+    xp = x_pitch or cx
+    b = torch.randn((n, t, ho, wo, cb), generator=g).to(torch.bfloat16).to(dev)
+    xfull = torch.randn((n, t, H, W, xp), generator=g).to(torch.bfloat16).to(dev)
+    wc = (torch.randn((cout, cb), generator=g) / cb ** 0.5).to(torch.bfloat16)
+    w1 = (torch.randn((cout, cx), generator=g) / cx ** 0.5).to(torch.bfloat16)
+    k2 = -(-cx // 64) * 64
+    wcat = torch.zeros((cout, cb + k2), dtype=torch.bfloat16)
+    wcat[:, :cb] = wc
+    wcat[:, cb:cb + cx] = w1
+    wcat = wcat.to(dev)
+    scale = (torch.rand(cout, generator=g) + 0.5).to(dev)
+    bias = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    outbuf = torch.full((n, t, ho, wo, cout), 7.0, dtype=torch.bfloat16, device=dev)
+    plan = ConvPlan(L.VSB_BF16, Act(b, n, t, ho, wo, cb, cb), wcat, cout, (1, 1, 1), (1, 1, 1), (0, 0, 0), None,
+                    scale, bias, Act(outbuf, n, t, ho, wo, cout, cout), None, True, kchunk=64,
+                    x2=Act(xfull, n, t, H, W, cx, xp), stride2=(1, s, s))
+    plan.run()
+    torch.cuda.synchronize()
+    xs = xfull[:, :, ::s, ::s, :cx].float()
+    acc = b.float() @ wc.float().to(dev).t() + xs @ w1.float().to(dev).t()
+    ref = torch.relu(acc * scale + bias)
+    info = _compare(outbuf, ref, atol=2e-2, rtol=1.6e-2)
+    info["plan"] = plan.info()
+    info["ok"] = info["n_bad"] == 0 and info["finite"]
+    return info
+
+
+# (name, c_b, c_x, cout, stride, n, t, H, W[, x_pitch])
+DUAL_CASES = [
+    ("dual_64_80_256_s1", 64, 80, 256, 1, 2, 2, 28, 28),          # slow res2: x = 64 + 16 lateral channels (OOB K fill)
+    ("dual_128_320_512_s2", 128, 320, 512, 2, 2, 2, 28, 28),      # slow res3
+    ("dual_256_640_1024_s2", 256, 640, 1024, 2, 1, 3, 14, 14),    # slow res4
+    ("dual_64_128_256_s2_odd", 64, 128, 256, 2, 3, 2, 7, 7),      # fast res5: odd extent, M tail
+    ("dual_64_64_128_pitch", 64, 64, 128, 1, 2, 2, 14, 14, 96),   # x is a channel slice of a wider buffer
+]
+
+
 # (name, cin, cout, kernel, stride, pad, J, W, H, cin_store, cout_store, shift, wbuf, residual[, n, t, relu])
 WINDOW_CASES = [
     ("w_sp3_64_64_56", 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 1, 56, 56, 64, 64, 0, None, False, 2, 2),
@@ -487,6 +530,15 @@ def child(args):
                 save()
                 report["window"][wc[0]] = run_window_case(*wc)
                 save()
+        if "dual" in sections or "conv" in sections:
+            report.setdefault("dual", {})
+            for dc in DUAL_CASES:
+                if dc[0] in report["dual"]:
+                    continue
+                report["dual"][dc[0]] = {"ok": False, "crashed": True}
+                save()
+                report["dual"][dc[0]] = run_dual_case(*dc)
+                save()
         if "conv" in sections:
             for case in CONV_CASES:
                 if case[0] in report["conv_bf16"]:
@@ -545,7 +597,7 @@ def main():
         time.sleep(1)
     report = json.load(open(args.out)) if os.path.exists(args.out) else {}
     n_ok = n_bad = 0
-    for sec in ("mem", "conv_f32", "conv_bf16", "stem", "group", "window"):
+    for sec in ("mem", "conv_f32", "conv_bf16", "stem", "group", "window", "dual"):
         for k, v in report.get(sec, {}).items():
             ok = bool(v.get("ok"))
             n_ok += ok

@@ -63,7 +63,7 @@ template <int KK, bool kDbg, int EW>
 __global__ void __launch_bounds__((EW + 2) * 32, EW == 8 ? 2 : 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
-                  const IgemmParams p) {
+                  const __grid_constant__ CUtensorMap map_a2, const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kEpiWarps = EW, kProducerWarp = EW, kMmaWarp = EW + 1;
@@ -90,6 +90,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&map_a);
+    if (p.chunks1 < p.total_chunks) tma_prefetch_desc(&map_a2);
     tma_prefetch_desc(&map_b);
     tma_prefetch_desc(&map_out);
     if (p.has_residual) tma_prefetch_desc(&map_res);
@@ -135,6 +136,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int cin = p.cin, fkw = p.kw, fkh = p.kh, block_n = p.block_n;
       const int owo = p.wo, oho = p.ho, oto = p.to, sw = p.sw, sh = p.sh, st = p.st, lw = p.lw, lh = p.lh, lt = p.lt;
       const int tile_step = gridDim.x;
+      const int chunks1 = p.chunks1, sw2 = p.sw2, sh2 = p.sh2, st2 = p.st2;
       int slot = 0;
       uint32_t parity = 1;  // first pass over the ring: slots are free
       for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step) {
@@ -152,6 +154,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int ncol = n_tile * block_n;
         int cc = 0, kw_ = 0, kh_ = 0, kt_ = 0, kcoord = 0;
         int left = total_chunks;
+        int left1 = chunks1;  // chunks still to come from the primary source
+        const int w2 = wo * sw2, h2 = ho * sh2, d2 = to_ * st2;
         while (left > 0) {
           const int nch = left < cps ? left : cps;
           left -= nch;
@@ -160,14 +164,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           uint8_t* a_dst = smem + (uint32_t)slot * stage_bytes;
           uint8_t* b_dst = a_dst + b_off;
           for (int c = 0; c < nch; ++c) {
-            tma_load_im2col_5d(a_dst, &map_a, &full_bar[slot], cc, w0, h0, d0, n0, (uint16_t)kw_, (uint16_t)kh_,
-                               (uint16_t)kt_);
+            if (left1 > 0) {
+              tma_load_im2col_5d(a_dst, &map_a, &full_bar[slot], cc, w0, h0, d0, n0, (uint16_t)kw_, (uint16_t)kh_,
+                                 (uint16_t)kt_);
+              if (--left1 == 0) cc = -kchunk;  // the second source starts at its channel 0
+            } else {
+              // fused shortcut projection: same 128 output pixels, strided 1x1x1 gather from the block input
+              // (channels past cin2 are zero-filled by the TMA unit, their weights are zero)
+              tma_load_im2col_5d(a_dst, &map_a2, &full_bar[slot], cc, w2, h2, d2, n0, 0, 0, 0);
+            }
             if (!b_resident) tma_load_2d(b_dst, &map_b, &full_bar[slot], kcoord, ncol);
             a_dst += a_chunk_bytes;
             b_dst += b_chunk_bytes;
             kcoord += kchunk;
             cc += kchunk;
-            if (cc == cin) {
+            if (cc == cin && left1 > 0) {
               cc = 0;
               if (++kw_ == fkw) {
                 kw_ = 0;
@@ -521,6 +532,11 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   plan->m_total = m_total;
 
   plan->algo = 1;
+  if (d->in2 && (d->dtype == VSB_F32 || d->algo == 2)) {
+    set_error("a second source needs the bf16 im2col algorithm");
+    delete plan;
+    return VSB_ERR_INVALID;
+  }
   if (d->dtype == VSB_F32) {
     *out_plan = plan;
     return VSB_OK;
@@ -579,7 +595,22 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   if (block_n < 16 || block_n > 256 || block_n % 16 || d->cout % block_n) FAIL(VSB_ERR_INVALID, "bad block_n %d for cout %d", block_n, d->cout);
   const int taps = d->kt * d->kh * d->kw;
   const int cin_chunks = d->cin / kchunk;
-  const int total_chunks = taps * cin_chunks;
+  // optional second source: strided 1x1x1 shortcut projection accumulated into the same tile
+  int cin2_chunks = 0;
+  if (d->in2) {
+    if (d->residual) FAIL(VSB_ERR_INVALID, "a conv takes either a residual or a second source, not both");
+    if (d->cin2 <= 0 || d->in2_pitch < d->cin2 || d->in2_pitch % 8 || d->cin2 % 8)
+      FAIL(VSB_ERR_INVALID, "second source: bad channel count / pitch (cin2 %d, pitch %d)", d->cin2, d->in2_pitch);
+    if (d->st2 < 1 || d->sh2 < 1 || d->sw2 < 1 || d->st2 > 8 || d->sh2 > 8 || d->sw2 > 8)
+      FAIL(VSB_ERR_INVALID, "second source: bad strides");
+    if ((d->t2 - 1) / d->st2 + 1 != to || (d->h2 - 1) / d->sh2 + 1 != ho || (d->w2 - 1) / d->sw2 + 1 != wo)
+      FAIL(VSB_ERR_INVALID, "second source [%d,%d,%d] / strides (%d,%d,%d) does not produce the conv's output [%d,%d,%d]",
+           d->t2, d->h2, d->w2, d->st2, d->sh2, d->sw2, to, ho, wo);
+    if (reinterpret_cast<uintptr_t>(d->in2) & 15) FAIL(VSB_ERR_ALIGN, "second source must be 16-byte aligned");
+    cin2_chunks = ceil_div(d->cin2, kchunk);
+  }
+  const int chunks1 = taps * cin_chunks;
+  const int total_chunks = chunks1 + cin2_chunks;
   const int cps = 64 / kchunk;  // a pipeline stage always has room for 64 K-elements
   const int n_tiles = d->cout / block_n;
   const int num_kstages = ceil_div(total_chunks, cps);
@@ -658,7 +689,17 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
     delete plan;
     return rc;
   }
-  const long long k_total = (long long)taps * d->cin;
+  plan->map_a2 = plan->map_a;
+  if (d->in2) {
+    const int zero3[3] = {0, 0, 0}, stride2[3] = {d->sw2, d->sh2, d->st2};
+    rc = encode_im2col_map(&plan->map_a2, d->in2, d->n, d->t2, d->h2, d->w2, d->cin2, d->in2_pitch, zero3, zero3,
+                           stride2, kchunk, kBlockM, swz);
+    if (rc != VSB_OK) {
+      delete plan;
+      return rc;
+    }
+  }
+  const long long k_total = (long long)taps * d->cin + (long long)cin2_chunks * kchunk;
   rc = encode_tiled_2d(&plan->map_b, d->wgt, k_total, d->cout, k_total * 2, kchunk, block_n, swz);
   if (rc != VSB_OK) {
     delete plan;
@@ -690,6 +731,8 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   p.lt = lower[2]; p.lh = lower[1]; p.lw = lower[0];
   p.kh = d->kh; p.kw = d->kw;
   p.cin = d->cin; p.cin_chunks = cin_chunks; p.total_chunks = total_chunks; p.cps = cps; p.kchunk = kchunk;
+  p.chunks1 = chunks1;
+  p.st2 = d->in2 ? d->st2 : 1; p.sh2 = d->in2 ? d->sh2 : 1; p.sw2 = d->in2 ? d->sw2 : 1;
   p.block_n = block_n; p.n_tiles = n_tiles; p.stages = stages;
   p.epi_bufs = epi_bufs; p.b_resident = b_resident ? 1 : 0;
   p.epi_warps = epi_warps;
@@ -757,10 +800,10 @@ extern "C" int vsb_conv3d_run(const vsb_conv_plan* plan, void* stream) {
   do {                                                                                                      \
     if (plan->params.epi_warps == 16)                                                                       \
       conv_igemm_kernel<KK, DBG, 16><<<plan->grid, 18 * 32, plan->smem_bytes, s>>>(                         \
-          plan->map_a, plan->map_b, plan->map_out, plan->map_res, plan->params);                            \
+          plan->map_a, plan->map_b, plan->map_out, plan->map_res, plan->map_a2, plan->params);              \
     else                                                                                                    \
       conv_igemm_kernel<KK, DBG, 8><<<plan->grid, 10 * 32, plan->smem_bytes, s>>>(                          \
-          plan->map_a, plan->map_b, plan->map_out, plan->map_res, plan->params);                            \
+          plan->map_a, plan->map_b, plan->map_out, plan->map_res, plan->map_a2, plan->params);              \
   } while (0)
   const bool dbg = plan->params.dbg != nullptr;
   switch (plan->params.kchunk) {
@@ -792,7 +835,7 @@ extern "C" int vsb_conv3d_plan_out_shape(const vsb_conv_plan* plan, int* to, int
 extern "C" double vsb_conv3d_plan_flops(const vsb_conv_plan* plan) {
   if (!plan) return 0.0;
   const vsb_conv_desc& d = plan->desc;
-  return 2.0 * (double)plan->m_total * d.cout * d.kt * d.kh * d.kw * d.cin;
+  return 2.0 * (double)plan->m_total * d.cout * ((double)d.kt * d.kh * d.kw * d.cin + (d.in2 ? d.cin2 : 0));
 }
 
 // ---- debug: im2col probe (declared in include/vidsitu_b200_debug.h)

@@ -13,6 +13,8 @@ struct IgemmParams {
   int lt, lh, lw;  // lower corner = -leading pad
   int kh, kw;
   int cin, cin_chunks, total_chunks, cps, kchunk;
+  int chunks1;            // K chunks of the primary source; chunks [chunks1, total_chunks) come from the second source
+  int st2, sh2, sw2;      // pixel strides of the second source (strided 1x1x1 shortcut projection)
   int block_n, n_tiles, total_tiles, stages;
   int epi_n, epi_chunks;  // epilogue column chunk (<= 64) and chunks per tile
   int epi_bufs;           // staging buffers of the epilogue (residual prefetch distance = epi_bufs - 1)
@@ -94,6 +96,7 @@ struct vsb_conv_plan {
   int algo;  // 1 = im2col implicit GEMM, 2 = shared-memory window
   // bf16 tensor-core path
   CUtensorMap map_a, map_b, map_out, map_res;
+  CUtensorMap map_a2;  // im2col algorithm: second source (fused shortcut projection)
   CUtensorMap map_a1;  // window algorithm, stride 2: odd-row view of the input
   vsb::IgemmParams params;
   vsb::WinParams win;

@@ -82,6 +82,7 @@ class ClipEngine:
                             and str(self.tune.get("*", {}).get("streams", os.environ.get("VSB_STREAMS", "2"))) == "2")
         self._side_stream = None
         self.op_bytes: Dict[str, float] = {}
+        self.fused_shortcuts: List[str] = []   # branch1 convs computed inside their block's last conv
         self.crop = spec.crop
         if self.crop % 16:
             raise VsbError("crop size must be a multiple of 16")
@@ -260,6 +261,46 @@ class ClipEngine:
         self.op_bytes[cs.key] = es * (x.pixels * x.c + m * out.c * (2 if residual is not None else 1))
         self.trunk_ops.append((cs.key, plan.run, float(m) * cs.flops_per_out_pixel))
 
+    def _conv_with_shortcut(self, c: ConvSpec, b: Act, br: ConvSpec, x: Act, out: Act) -> bool:
+        """relu(BN1(branch1(x)) + BN_c(c(b)))  (resnet_helper.py:352-358) as ONE launch: the strided 1x1x1
+        projection shortcut is a second K segment of the block's last conv (vsb_conv_desc.in2), so its
+        [M, 4*dim_inner] result is never written to HBM and never re-read as a residual.  Both frozen
+        BatchNorms must share the epilogue's per-channel scale: per channel the larger of the two scales
+        stays in the fp32 epilogue and the ratio (|.| <= 1) is folded into the other weight block before
+        its single bf16 rounding.  Returns False when the layer is outside the fused kernel's domain."""
+        if self.dtype != VSB_BF16 or self._tune(c.key).get("fuse_shortcut", True) is False:
+            return False
+        if tuple(c.kernel) != (1, 1, 1) or tuple(br.kernel) != (1, 1, 1) or tuple(c.stride) != (1, 1, 1) or br.stride[0] != 1:
+            return False
+        if b.c % 64 or b.pitch != b.c or b.c_off or x.c_off or x.c_real != br.cin or x.c < 64 or out.c % 16:
+            return False
+        s_c, b_c = self._affine(c, out.c)
+        s_1, b_1 = self._affine(br, out.c)
+        use_c = s_c.abs() >= s_1.abs()
+        s = torch.where(use_c, s_c, s_1)
+        safe = torch.where(s == 0, torch.ones_like(s), s)
+        r_c = torch.where(s == 0, torch.zeros_like(s), s_c / safe)
+        r_1 = torch.where(s == 0, torch.zeros_like(s), s_1 / safe)
+        kchunk = 64
+        k2 = round_up(x.c, kchunk)
+        w_c = pack_conv_weight(self._tensor(c.key + ".weight"), b.c, out.c, torch.float32).reshape(out.c, b.c)
+        w_1 = pack_conv_weight(self._tensor(br.key + ".weight"), k2, out.c, torch.float32).reshape(out.c, k2)
+        w = torch.cat([w_c * r_c[:, None], w_1 * r_1[:, None]], dim=1).to(self.tdt).contiguous()
+        tune = {k: v for k, v in self._tune(c.key).items() if k in ("block_n", "stages")}
+        try:
+            plan = ConvPlan(self.dtype, b, w, out.c, c.kernel, c.stride, c.pad, None, s, b_c + b_1, out, None, True,
+                            kchunk=kchunk, x2=x, stride2=br.stride, **tune)
+        except VsbError:
+            if self._tune(c.key).get("fuse_shortcut") is True:
+                raise
+            return False
+        self._keep.append(plan)
+        m = out.pixels
+        self.op_bytes[c.key] = 2 * (b.pixels * b.c + m * x.c + m * out.c)
+        self.trunk_ops.append((c.key, plan.run, float(m) * (c.flops_per_out_pixel + br.flops_per_out_pixel)))
+        self.fused_shortcuts.append(br.key)
+        return True
+
     def _stem(self, p: int, x: Act) -> Act:
         st = self.spec.stems[p]
         cs = st.conv
@@ -331,16 +372,25 @@ class ClipEngine:
         b = self._alloc(n, tb, hb, wb, blk.b.cout)
         self._conv(blk.b, a, b)
         self._free(a)
+        sc = None
+        y = None
         if blk.branch1 is not None:
-            sc = self._alloc(n, tb, hb, wb, blk.branch1.cout)
-            self._conv(blk.branch1, x, sc)
-            res = sc
+            y = self._alloc(n, tb, hb, wb, blk.c.cout, pitch=out_pitch)
+            if self._conv_with_shortcut(blk.c, b, blk.branch1, x, y):
+                res = None
+            else:
+                self._free(y)
+                y = None
+                sc = self._alloc(n, tb, hb, wb, blk.branch1.cout)
+                self._conv(blk.branch1, x, sc)
+                res = sc
         else:
-            sc = None
             res = x
-        y = self._alloc(n, tb, hb, wb, blk.c.cout, pitch=out_pitch)
+        if y is None:
+            y = self._alloc(n, tb, hb, wb, blk.c.cout, pitch=out_pitch)
         # relu(shortcut + BN(c(.)))   resnet_helper.py:352-358
-        self._conv(blk.c, b, y, residual=res, relu=True)
+        if res is not None:
+            self._conv(blk.c, b, y, residual=res, relu=True)
         self._free(b)
         if sc is not None:
             self._free(sc)

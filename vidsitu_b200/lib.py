@@ -44,6 +44,9 @@ class ConvDesc(C.Structure):
         ("algo", C.c_int),
         ("kw_c_lo", C.c_int * 8),
         ("kw_c_hi", C.c_int * 8),
+        ("in2", C.c_void_p),
+        ("t2", C.c_int), ("h2", C.c_int), ("w2", C.c_int), ("cin2", C.c_int), ("in2_pitch", C.c_int),
+        ("st2", C.c_int), ("sh2", C.c_int), ("sw2", C.c_int),
     ]
 
 
@@ -93,8 +96,8 @@ def load() -> C.CDLL:
                  "vsb_nthwc_to_ncthw_f32", "vsb_ncthw_f32_to_nthwc", "vsb_debug_im2col_probe",
                  "vsb_debug_umma_semantics", "vsb_debug_umma_rate", "vsb_debug_conv_stats", "vsb_debug_conv_plan_info"):
         getattr(lib, name).restype = i
-    if lib.vsb_abi_version() != 2:
-        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 2")
+    if lib.vsb_abi_version() != 3:
+        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 3")
     _lib = lib
     return lib
 

@@ -66,8 +66,10 @@ class ConvPlan:
                  stride: Sequence[int], pad_lo: Sequence[int], pad_hi: Optional[Sequence[int]],
                  scale: torch.Tensor, bias: torch.Tensor, out: Act, residual: Optional[Act] = None,
                  relu: bool = False, block_n: int = 0, kchunk: int = 0, stages: int = 0, algo: int = 0,
-                 kw_ranges: Optional[Sequence[Sequence[int]]] = None):
-        _require_cuda(x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None)
+                 kw_ranges: Optional[Sequence[Sequence[int]]] = None, x2: Optional[Act] = None,
+                 stride2: Sequence[int] = (1, 1, 1)):
+        _require_cuda(x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None,
+                      x2.buf if x2 is not None else None)
         pad_hi = pad_lo if pad_hi is None else pad_hi
         d = ConvDesc()
         d.dtype = dtype
@@ -95,14 +97,26 @@ class ConvPlan:
             for k, (lo, hi) in enumerate(kw_ranges):
                 d.kw_c_lo[k], d.kw_c_hi[k] = int(lo), int(hi)
             k_per_tap_row = sum(int(hi) - int(lo) for lo, hi in kw_ranges)
+        k2 = 0
+        if x2 is not None:
+            # second source (fused shortcut projection): strided 1x1x1 over x2, weights appended along K
+            if not kchunk:
+                raise VsbError("a second source needs an explicit kchunk (its weights are padded to it)")
+            d.in2 = x2.ptr
+            d.t2, d.h2, d.w2, d.cin2, d.in2_pitch = x2.t, x2.h, x2.w, x2.c, x2.pitch
+            d.st2, d.sh2, d.sw2 = stride2
+            k2 = -(-x2.c // kchunk) * kchunk
+            if x2.n != x.n or x2.buf.dtype != x.buf.dtype:
+                raise VsbError("second source must have the batch size and dtype of the first")
         expect = torch.bfloat16 if dtype == VSB_BF16 else torch.float32
         if x.buf.dtype != expect or wgt.dtype != expect or out.buf.dtype != expect:
             raise VsbError(f"conv tensors must be {expect}")
         if scale.dtype != torch.float32 or bias.dtype != torch.float32:
             raise VsbError("scale/bias must be float32")
-        if wgt.numel() != cout * d.kt * d.kh * k_per_tap_row:
-            raise VsbError(f"packed weight has {wgt.numel()} elements, expected {cout}x{d.kt * d.kh}x{k_per_tap_row}")
-        self._keep = (x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None)
+        if wgt.numel() != cout * (d.kt * d.kh * k_per_tap_row + k2):
+            raise VsbError(f"packed weight has {wgt.numel()} elements, expected {cout}x({d.kt * d.kh}x{k_per_tap_row}+{k2})")
+        self._keep = (x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None,
+                      x2.buf if x2 is not None else None)
         self._h = C.c_void_p()
         self._lib = _l.load()
         check(self._lib.vsb_conv3d_plan_create(C.byref(d), C.byref(self._h)), "vsb_conv3d_plan_create")
