@@ -82,6 +82,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* epi_ready = tmem_empty + 2;
   uint64_t* bres_bar = epi_ready + kMaxEpiWarps * kMaxEpiBufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  // The grid is a multiple of n_tiles, so tile % n_tiles == blockIdx.x % n_tiles for every tile of this
+  // CTA: one fixed column block -> its (scale, bias) pairs live in shared memory, and its weights can too.
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_tile0 = blockIdx.x / p.n_tiles, m_tile_step = gridDim.x / p.n_tiles;
+  float2* sb_tab = reinterpret_cast<float2*>(smem + p.off_bar + 1024);
+  for (int c = threadIdx.x; c < p.block_n; c += blockDim.x)
+    sb_tab[c] = make_float2(p.scale ? p.scale[n_tile * p.block_n + c] : 1.f, p.bias[n_tile * p.block_n + c]);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
@@ -126,22 +133,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // weight-stationary: every chunk of the [block_n x K] weight matrix is loaded exactly once
         mbar_expect_tx(bres_bar, p.total_chunks * b_chunk_bytes);
         for (int g = 0; g < p.total_chunks; ++g)
-          tma_load_2d(bres + g * b_chunk_bytes, &map_b, bres_bar, g * p.kchunk, 0);
+          tma_load_2d(bres + g * b_chunk_bytes, &map_b, bres_bar, g * p.kchunk, n_tile * p.block_n);
       }
       const bool b_resident = p.b_resident != 0;
       const uint32_t stage_tx = b_resident ? a_chunk_bytes : a_chunk_bytes + b_chunk_bytes;
       const int cps = 4 / KK, kchunk = 16 * KK;
       const uint32_t b_off = cps * a_chunk_bytes;
-      const int total_chunks = p.total_chunks, stages = p.stages, total_tiles = p.total_tiles, n_tiles = p.n_tiles;
+      const int total_chunks = p.total_chunks, stages = p.stages, m_tiles = p.total_tiles / p.n_tiles;
       const int cin = p.cin, fkw = p.kw, fkh = p.kh, block_n = p.block_n;
       const int owo = p.wo, oho = p.ho, oto = p.to, sw = p.sw, sh = p.sh, st = p.st, lw = p.lw, lh = p.lh, lt = p.lt;
-      const int tile_step = gridDim.x;
       const int chunks1 = p.chunks1, sw2 = p.sw2, sh2 = p.sh2, st2 = p.st2;
       int slot = 0;
       uint32_t parity = 1;  // first pass over the ring: slots are free
-      for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step) {
-        const int n_tile = tile % n_tiles;
-        const int m0 = (tile / n_tiles) * kBlockM;
+      for (int mt = m_tile0; mt < m_tiles; mt += m_tile_step) {
+        const int m0 = mt * kBlockM;
         const int wo = m0 % owo;
         const int r1 = m0 / owo;
         const int ho = r1 % oho;
@@ -210,14 +215,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t stage_lo = stage_bytes >> 4, a_chunk_lo = a_chunk_bytes >> 4, b_chunk_lo = b_chunk_bytes >> 4;
     const uint32_t b_off_lo = (CPS * a_chunk_bytes) >> 4;
     const uint32_t idesc = p.idesc;
-    const int total_chunks = p.total_chunks, stages = p.stages, total_tiles = p.total_tiles, block_n = p.block_n;
+    const int total_chunks = p.total_chunks, stages = p.stages, m_tiles = p.total_tiles / p.n_tiles, block_n = p.block_n;
     const int full_stages = total_chunks / CPS, tail_chunks = total_chunks - full_stages * CPS;
     const bool b_resident = p.b_resident != 0;
-    const int tile_step = gridDim.x;
     int slot = 0, tcount = 0;
     uint32_t parity = 0, a_slot_lo = smem_lo;
     if (b_resident) mbar_wait(bres_bar, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += tile_step, ++tcount) {
+    for (int mt = m_tile0; mt < m_tiles; mt += m_tile_step, ++tcount) {
       const int acc = tcount & 1;
       IG_T(1, mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1));  // epilogue drained this accumulator
       tc_fence_after();
@@ -295,82 +299,85 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t* my_ready = epi_ready + warp * kMaxEpiBufs;
     const int row_in_tile = quarter * 32;
     const float relu_floor = p.relu ? 0.f : -__int_as_float(0x7f800000);
+    const int m_tiles = p.total_tiles / p.n_tiles;
+    const int nbase = n_tile * p.block_n;
+    const uint32_t sb_s = smem_u32(sb_tab);
+    const int epi_n = p.epi_n, epi_chunks = p.epi_chunks;
+    const bool has_res = p.has_residual != 0;
     // prefetch cursor (lane 0): next chunk of THIS warp whose staging slab has not been armed yet
-    int pf_tile = blockIdx.x, pf_chunk = 0, pf_gq = 0, pf_q = 0;
+    int pf_mt = m_tile0, pf_chunk = 0, pf_gq = 0, pf_b = 0;
     auto pf_skip = [&]() {  // advance the cursor to the next chunk owned by this warp's group
-      while (pf_tile < p.total_tiles && (pf_gq & (EW / 4 - 1)) != grp) {
+      while (pf_mt < m_tiles && (pf_gq & (EW / 4 - 1)) != grp) {
         ++pf_gq;
-        if (++pf_chunk == p.epi_chunks) {
+        if (++pf_chunk == epi_chunks) {
           pf_chunk = 0;
-          pf_tile += gridDim.x;
+          pf_mt += m_tile_step;
         }
       }
     };
-    auto arm_next = [&]() {  // hand slab pf_q % nb to that chunk: start its residual load, or mark it free
-      const int bsel = pf_q % nb;
-      if (p.has_residual) {
-        mbar_expect_tx(&my_ready[bsel], slab_bytes);
-        tma_load_2d(my_bufs + bsel * slab_bytes, &map_res, &my_ready[bsel],
-                    (pf_tile % p.n_tiles) * p.block_n + pf_chunk * p.epi_n,
-                    (pf_tile / p.n_tiles) * kBlockM + row_in_tile);
+    auto arm_next = [&]() {  // hand the next slab of the ring to that chunk: start its residual load, or mark it free
+      if (has_res) {
+        mbar_expect_tx(&my_ready[pf_b], slab_bytes);
+        tma_load_2d(my_bufs + pf_b * slab_bytes, &map_res, &my_ready[pf_b], nbase + pf_chunk * epi_n,
+                    pf_mt * kBlockM + row_in_tile);
       } else {
-        mbar_arrive(&my_ready[bsel]);
+        mbar_arrive(&my_ready[pf_b]);
       }
-      ++pf_q;
+      if (++pf_b == nb) pf_b = 0;
       ++pf_gq;
-      if (++pf_chunk == p.epi_chunks) {
+      if (++pf_chunk == epi_chunks) {
         pf_chunk = 0;
-        pf_tile += gridDim.x;
+        pf_mt += m_tile_step;
       }
       pf_skip();
     };
     if (lane == 0) {
       pf_skip();
-      for (int i = 0; i < nb - 1 && pf_tile < p.total_tiles; ++i) arm_next();
+      for (int i = 0; i < nb - 1 && pf_mt < m_tiles; ++i) arm_next();
     }
     __syncwarp();
-    int q = 0;   // chunks processed by this warp: staging slab = q % nb
-    int gq = 0;  // global chunk counter of the CTA (all tiles, all chunks)
+    int b = 0;            // staging slab of this warp's current chunk (ring of nb)
+    uint32_t bpar = 0;    // parity of that slab's ready barrier
+    int gq = 0;           // global chunk counter of the CTA (all tiles, all chunks)
     int tcount = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      const int n_tile = tile % p.n_tiles;
-      const int m0 = (tile / p.n_tiles) * kBlockM;
-      const int nbase = n_tile * p.block_n;
+    for (int mt = m_tile0; mt < m_tiles; mt += m_tile_step, ++tcount) {
+      const int m0 = mt * kBlockM;
       const int acc = tcount & 1;
       IG_T(4, mbar_wait(&tmem_full[acc], (tcount >> 1) & 1));
       if (kDbg) dbg_acc[9] += 1;
       tc_fence_after();
-      for (int c = 0; c < p.epi_chunks; ++c, ++gq) {
+      for (int c = 0; c < epi_chunks; ++c, ++gq) {
         if ((gq & (EW / 4 - 1)) != grp) continue;
-        const int b = q % nb;
         uint8_t* buf = my_bufs + b * slab_bytes;
-        IG_T(5, mbar_wait(&my_ready[b], (q / nb) & 1));  // slab free (+ residual landed)
+        IG_T(5, mbar_wait(&my_ready[b], bpar));  // slab free (+ residual landed)
         const long long math_t0 = kDbg ? clock64() : 0;
-        const int col0 = nbase + c * p.epi_n;
+        const int col0 = c * epi_n;
         {
-          const uint32_t taddr = lane_taddr + acc * p.block_n + c * p.epi_n;
-          const float* sc = p.scale ? p.scale + col0 : nullptr;
-          if (p.has_residual)
-            epi_convert_chunk_g<true>(taddr, p.epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane, sc, p.bias + col0,
-                                      relu_floor);
+          const uint32_t taddr = lane_taddr + acc * p.block_n + col0;
+          if (has_res)
+            epi_convert_chunk<true>(taddr, epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane, sb_s + col0 * 8,
+                                    relu_floor);
           else
-            epi_convert_chunk_g<false>(taddr, p.epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane, sc,
-                                       p.bias + col0, relu_floor);
+            epi_convert_chunk<false>(taddr, epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane, sb_s + col0 * 8,
+                                     relu_floor);
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
         __syncwarp();
         if (kDbg) dbg_acc[6] += (uint32_t)(clock64() - math_t0);
         if (lane == 0) {
-          tma_store_2d(&map_out, buf, col0, m0 + row_in_tile);  // rows >= m_total are clipped by the TMA unit
+          tma_store_2d(&map_out, buf, nbase + col0, m0 + row_in_tile);  // rows >= m_total are clipped by the TMA unit
           tma_store_commit();
           // arm the slab of this warp's chunk q + nb - 1 (the one chunk q - 1 used): its store must have read it
-          if (pf_tile < p.total_tiles) {
+          if (pf_mt < m_tiles) {
             IG_T(7, tma_store_wait_read1());
             arm_next();
           }
         }
         __syncwarp();  // reconverge before the next warp-aligned tcgen05.ld
-        ++q;
+        if (++b == nb) {
+          b = 0;
+          bpar ^= 1;
+        }
       }
       // every tcgen05.ld this warp issues for the accumulator has completed: hand it back to the MMA warp
       tc_fence_before();
@@ -612,66 +619,91 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   const int chunks1 = taps * cin_chunks;
   const int total_chunks = chunks1 + cin2_chunks;
   const int cps = 64 / kchunk;  // a pipeline stage always has room for 64 K-elements
-  const int n_tiles = d->cout / block_n;
   const int num_kstages = ceil_div(total_chunks, cps);
-  uint32_t tmem_cols = 32;  // two accumulators; TMEM allocations are powers of two >= 32 columns
-  while (tmem_cols < (uint32_t)(2 * block_n)) tmem_cols <<= 1;
-  // ---- shared-memory plan.  Weight-stationary when one n-tile covers cout and the whole [cout x K]
-  // matrix fits: B is fetched once per CTA instead of once per tile.  With a residual the epilogue
-  // keeps 3 staging buffers per warp so 2 residual chunks are in flight (HBM latency), otherwise 2.
-  const int a_stage = cps * kBlockM * kchunk * 2, b_stage = cps * block_n * kchunk * 2;
-  const long long bres_bytes = (long long)total_chunks * block_n * kchunk * 2;
+  const int bar_bytes = 1024 + 2048;  // barriers + the CTA's (scale, bias) table (block_n <= 256 float2)
   static const bool no_bres = getenv("VSB_NO_BRES") != nullptr;
-  const bool b_resident = !no_bres && n_tiles == 1 && bres_bytes <= 96 * 1024;
-  const int stage_bytes = ((b_resident ? a_stage : a_stage + b_stage) + 1023) & ~1023;
-  const int bar_bytes = 1024;
-  int epi_warps = 8, epi_n = 0, epi_bufs = 0, stages = 0, epi_buf_bytes = 0;
-  size_t smem_bytes = 0;
-  // Two shapes of CTA.  (A) 8 epilogue warps, sized so that two CTAs share an SM when they fit: two MMA
-  // chains and two epilogues per SM.  (B) when only one CTA fits anyway: 16 epilogue warps with
-  // 32-column chunks -- four warps per TMEM lane quarter keep the accumulator drain (the bottleneck of
-  // the wide 1x1x1 layers: short K, 256 output columns, residual) off the critical path.
   static const char* ew_env = getenv("VSB_EPI_WARPS");
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    // (measured on B200: the 16-warp shape does not beat 8 warps -- these layers are HBM-bound, the accumulator
-    // wait is back-pressure -- so it is opt-in: VSB_EPI_WARPS=16)
-    epi_warps = (ew_env && atoi(ew_env) == 16) ? 16 : 8;
+  // (measured on B200: the 16-warp epilogue shape does not beat 8 warps -- these layers are HBM-bound, the
+  // accumulator wait is back-pressure -- so it is opt-in: VSB_EPI_WARPS=16)
+  const int epi_warps = (ew_env && atoi(ew_env) == 16) ? 16 : 8;
+
+  // ---- shared-memory plan for one (block_n, weight residency) choice.
+  // Weight-stationary: the CTA's [block_n x K] weight block is fetched once (every CTA owns ONE column block:
+  // the grid is a multiple of n_tiles) instead of once per tile.  With a residual the epilogue keeps 3
+  // staging slabs per warp so 2 residual chunks are in flight (HBM latency), otherwise 2.
+  struct SmemPlan { int stages, epi_n, epi_bufs, stage_bytes; size_t smem_bytes; long long bres_bytes; uint32_t tmem_cols; bool fits; };
+  auto plan_smem = [&](int bn, bool resident) {
+    SmemPlan sp{};
+    sp.tmem_cols = 32;  // two accumulators; TMEM allocations are powers of two >= 32 columns
+    while (sp.tmem_cols < (uint32_t)(2 * bn)) sp.tmem_cols <<= 1;
+    const int a_stage = cps * kBlockM * kchunk * 2, b_stage = cps * bn * kchunk * 2;
+    sp.bres_bytes = (long long)total_chunks * bn * kchunk * 2;
+    sp.stage_bytes = ((resident ? a_stage : a_stage + b_stage) + 1023) & ~1023;
     // epilogue column chunk: 64 columns (128-byte staging rows); compute-bound layers (long K loop, no
     // residual) and the 16-warp shape take 32-column chunks so the staging slabs leave room for the ring
-    epi_n = block_n >= 64 ? 64 : block_n;
-    if (block_n >= 64 && ((!d->residual && num_kstages >= 8) || epi_warps == 16)) epi_n = 32;
-    if (block_n % epi_n) FAIL(VSB_ERR_INVALID, "block_n %d is not a multiple of the epilogue chunk %d", block_n, epi_n);
-    epi_buf_bytes = epi_warps * 32 * epi_n * 2;  // one 32-row slab per epilogue warp
-    epi_bufs = d->residual ? 3 : 2;  // slabs per epilogue warp (residual prefetch distance = epi_bufs - 1)
-    stages = d->stages;
-    bool fits = false;
+    sp.epi_n = bn >= 64 ? 64 : bn;
+    if (bn >= 64 && ((!d->residual && num_kstages >= 8) || epi_warps == 16)) sp.epi_n = 32;
+    if (bn % sp.epi_n) return sp;
+    const int epi_buf_bytes = epi_warps * 32 * sp.epi_n * 2;  // one 32-row slab per epilogue warp
+    sp.epi_bufs = d->residual ? 3 : 2;  // slabs per epilogue warp (residual prefetch distance = epi_bufs - 1)
     for (;;) {
-      const int fixed = (b_resident ? (int)((bres_bytes + 1023) & ~1023ll) : 0) + epi_bufs * epi_buf_bytes + bar_bytes + 1024;
-      if (!d->stages) {
+      const long long fixed = (resident ? ((sp.bres_bytes + 1023) & ~1023ll) : 0) + sp.epi_bufs * epi_buf_bytes + bar_bytes + 1024;
+      int stages = d->stages;
+      if (!stages) {
         // 512 TMEM columns or 16 epilogue warps => one CTA per SM anyway: use the whole shared memory;
         // otherwise try to leave room for two CTAs per SM and fall back to one big CTA when that starves
         // the pipeline
-        int budget = ((tmem_cols == 512 || epi_warps == 16) ? 227 : 113) * 1024 - fixed;
-        stages = budget > 0 ? budget / stage_bytes : 0;
-        if (stages < 3 && stages < 2 * num_kstages) stages = (227 * 1024 - fixed) / stage_bytes;
+        long long budget = ((sp.tmem_cols == 512 || epi_warps == 16) ? 227 : 113) * 1024 - fixed;
+        stages = budget > 0 ? (int)(budget / sp.stage_bytes) : 0;
+        if (stages < 3 && stages < 2 * num_kstages) stages = (int)((227 * 1024 - fixed) / sp.stage_bytes);
         if (stages > 8) stages = 8;
       }
       if (stages > 16) stages = 16;
       if (stages > num_kstages * 2) stages = num_kstages * 2;
-      smem_bytes = (size_t)(stages > 0 ? stages : 0) * stage_bytes + fixed;
-      if (stages >= 3 && smem_bytes <= 227 * 1024) { fits = true; break; }
-      if (stages >= 1 && smem_bytes <= 227 * 1024 && (epi_bufs == 2 || stages >= 2 * num_kstages)) { fits = true; break; }
-      if (epi_bufs > 2) {
-        epi_bufs = 2;  // give the shared memory back to the main-loop pipeline
+      sp.stages = stages;
+      sp.smem_bytes = (size_t)((stages > 0 ? stages : 0) * (long long)sp.stage_bytes + fixed);
+      if (stages >= 3 && sp.smem_bytes <= 227 * 1024) { sp.fits = true; break; }
+      if (stages >= 1 && sp.smem_bytes <= 227 * 1024 && (sp.epi_bufs == 2 || stages >= 2 * num_kstages)) { sp.fits = true; break; }
+      if (sp.epi_bufs > 2) {
+        sp.epi_bufs = 2;  // give the shared memory back to the main-loop pipeline
         continue;
       }
       break;
     }
-    if (!fits) FAIL(VSB_ERR_INVALID, "pipeline (%d stages x %d bytes) does not fit in shared memory", stages, stage_bytes);
-    const bool two_ctas = epi_warps == 8 && tmem_cols <= 256 && smem_bytes <= 113 * 1024;
-    (void)two_ctas;
-    break;
+    return sp;
+  };
+  // Choice: (1) one column block covering cout with resident weights (<= 96 KB); (2) several column blocks
+  // with resident weights when block_n (or, unless the caller fixed it, block_n / 2) leaves room for a
+  // >= 3-stage ring and the epilogue slabs -- memory-bound 1x1x1 layers with cout > 256 otherwise spend more
+  // L2 -> SM bandwidth re-fetching weights per tile than on activations; (3) weights streamed with A.
+  SmemPlan sp{};
+  bool b_resident = false;
+  if (!no_bres) {
+    int cand[2] = {block_n, (!d->block_n && block_n == 256) ? 128 : 0};
+    for (int ci = 0; ci < 2 && !b_resident; ++ci) {
+      const int bn = cand[ci];
+      if (!bn) continue;
+      const int nt = d->cout / bn;
+      SmemPlan t = plan_smem(bn, true);
+      const long long limit = nt == 1 ? 96 * 1024 : 128 * 1024;
+      if (t.fits && t.bres_bytes <= limit && (nt == 1 || (t.stages >= 3 && t.epi_bufs == (d->residual ? 3 : 2)))) {
+        // compute-bound long-K layers keep the wide block (fewer A re-reads); resident mode is for short K
+        if (nt > 1 && num_kstages > 8) continue;
+        sp = t;
+        block_n = bn;
+        b_resident = true;
+      }
+    }
   }
+  if (!b_resident) sp = plan_smem(block_n, false);
+  if (block_n % (sp.epi_n ? sp.epi_n : 1) || !sp.epi_n) FAIL(VSB_ERR_INVALID, "block_n %d is not a multiple of the epilogue chunk", block_n);
+  if (!sp.fits) FAIL(VSB_ERR_INVALID, "pipeline (%d stages x %d bytes) does not fit in shared memory", sp.stages, sp.stage_bytes);
+  const int n_tiles = d->cout / block_n;
+  const uint32_t tmem_cols = sp.tmem_cols;
+  const long long bres_bytes = sp.bres_bytes;
+  const int stage_bytes = sp.stage_bytes, stages = sp.stages, epi_n = sp.epi_n, epi_bufs = sp.epi_bufs;
+  const int epi_buf_bytes = epi_warps * 32 * epi_n * 2;
+  const size_t smem_bytes = sp.smem_bytes;
   const uint32_t off_bres = (uint32_t)stages * stage_bytes;
   const uint32_t off_epi = off_bres + (b_resident ? (uint32_t)((bres_bytes + 1023) & ~1023ll) : 0u);
   const uint32_t off_bar = off_epi + epi_bufs * epi_buf_bytes;
@@ -763,6 +795,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   }
   long long grid = (long long)sms * ctas_per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
+  grid -= grid % p.n_tiles;  // every CTA owns one column block (total_tiles is a multiple of n_tiles too)
   plan->grid = (unsigned)grid;
   plan->desc.block_n = block_n;
   plan->desc.kchunk = kchunk;
