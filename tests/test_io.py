@@ -1,0 +1,124 @@
+"""CPU-side tests of the callers either side of the forward: checkpoint
+ingestion, the on-disk feature contract and the verb-prediction dict of EvalB."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from common import ROOT, build_model
+from vidsitu_b200 import checkpoint as CK
+from vidsitu_b200 import feat_io as FIO
+
+PAIRS = json.load(open(os.path.join(ROOT, "tests", "golden", "c2_name_pairs.json")))
+
+
+@pytest.mark.parametrize("name", sorted(PAIRS))
+def test_caffe2_names_match_the_reference_converter(name):
+    """Fixture = output of the reference's own regex table (tests/golden/make_c2_names.py)."""
+    model, _, _ = build_model(name, seed=0, crop=64)
+    keys = set(model.sf_mdl.state_dict().keys())
+    for c2, want in PAIRS[name]["pairs"]:
+        assert CK.convert_caffe2_name(c2) == want, c2
+    covered = {w for _, w in PAIRS[name]["pairs"]}
+    assert covered == {k for k in keys if not k.endswith("num_batches_tracked")}
+    for c2, ref_out in PAIRS[name]["solver_blobs"]:
+        # the reference maps these to strings that are not model keys and skips them (checkpoint.py:246-254)
+        assert ref_out not in keys
+        got = CK.convert_caffe2_name(c2)
+        assert got is None or got not in keys
+
+
+def _fake_caffe2_ckpt(model, path, seed=3):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    g = np.random.default_rng(seed)
+    sd = model.sf_mdl.state_dict()
+    inv = {want: c2 for c2, want in PAIRS["slow_fast_nl_r50_8x8"]["pairs"]}
+    blobs, truth = {}, {}
+    for k, v in sd.items():
+        if k.endswith("num_batches_tracked"):
+            continue
+        a = g.standard_normal(tuple(v.shape)).astype(np.float32)
+        if k.endswith("running_var"):
+            a = np.abs(a) + 0.5
+        blobs[inv[k]] = a
+        truth[k] = a
+    blobs["lr"] = np.float32(0.1)
+    blobs["model_iter"] = np.int64(100)
+    blobs["conv1_w_momentum"] = np.zeros((64, 3, 1, 7, 7), np.float32)
+    blobs["pred_w"] = np.zeros((7, 2304), np.float32)       # wrong class count -> shape mismatch, not loaded
+    truth.pop("head.projection.weight")
+    with open(path, "wb") as f:
+        pickle.dump({"blobs": blobs}, f, protocol=2)
+    return truth
+
+
+def test_caffe2_checkpoint_loads_into_sf_mdl(tmp_path):
+    model, _, _ = build_model("slow_fast_nl_r50_8x8", seed=0, crop=64)
+    before = model.sf_mdl.state_dict()["head.projection.weight"].clone()
+    truth = _fake_caffe2_ckpt(model, tmp_path / "c2.pkl")
+    rep = CK.load_caffe2_checkpoint(tmp_path / "c2.pkl", model.sf_mdl)
+    sd = model.sf_mdl.state_dict()
+    for k, a in truth.items():
+        assert np.array_equal(sd[k].numpy(), a), k
+    assert rep["mismatched"] == ["pred_w"]
+    assert set(rep["skipped"]) == {"lr", "model_iter", "conv1_w_momentum"}
+    assert torch.equal(sd["head.projection.weight"], before)
+    assert all(k.endswith("num_batches_tracked") or k == "head.projection.weight" for k in rep["missing"])
+
+
+def test_vidsitu_pth_with_module_prefix(tmp_path):
+    src, _, _ = build_model("i3d_r50_8x8", seed=5, crop=64)
+    dst, _, _ = build_model("i3d_r50_8x8", seed=6, crop=64)
+    torch.save({"model_state_dict": {"module." + k: v for k, v in src.state_dict().items()}}, tmp_path / "m.pth")
+    CK.load_vidsitu_checkpoint(tmp_path / "m.pth", dst)
+    for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert torch.equal(a, b), k
+    with pytest.raises(IndexError):
+        CK.strip_module_prefix("sf_mdl.s1.pathway0_stem.conv.weight")   # rem_mdl raises on un-prefixed keys too
+
+
+def test_feature_files_are_what_the_reference_writes_and_reads(tmp_path):
+    """feat_extractor.py:98-111 writes np.save(out_tdir/{vseg}_feats.npy, out_np[vix]) with out = [B,5,D] fp32;
+    dat_loader.py:503-511 reads it back and asserts 5 events."""
+    g = torch.Generator().manual_seed(0)
+    feats = torch.randn((3 * 5, 2304), generator=g)
+    names = ["v_aaa_seg_0_10", "v_bbb_seg_10_20", "v_ccc_seg_20_30"]
+    with FIO.FeatureWriter(tmp_path, "slow_fast_nl_r50_8x8_feats") as w:
+        w.put(feats, names)
+        w.put(feats.view(3, 5, -1) * 2, [n + "_x" for n in names])
+    out_dir = tmp_path / "slow_fast_nl_r50_8x8_feats"
+    assert w.files_written == 6
+    ref_np = feats.view(3, 5, -1).numpy()
+    for v, n in enumerate(names):
+        p = out_dir / f"{n}_feats.npy"
+        # byte-identical to the reference's own np.save call
+        import io
+        bio = io.BytesIO()
+        np.save(bio, ref_np[v])
+        assert p.read_bytes() == bio.getvalue()
+        t = FIO.read_frm_feats(out_dir, n)
+        assert t.dtype == torch.float32 and tuple(t.shape) == (5, 2304)
+        assert torch.equal(t, feats.view(3, 5, -1)[v])
+        assert torch.equal(FIO.read_frm_feats(out_dir, n + "_x"), 2 * t)
+    assert FIO.get_head_dim(str(out_dir)) == 2304
+    assert FIO.get_head_dim("/data/vsitu_vid_feats/i3d_r50_8x8") == 2048
+    assert FIO.get_head_dim("/x/sfast_feats") == 2304
+    with pytest.raises(NotImplementedError):
+        FIO.get_head_dim("/x/c2d")
+    with pytest.raises(AssertionError):
+        FIO.read_frm_feats(out_dir, "missing")
+    with pytest.raises(ValueError):
+        FIO.write_video_feats(out_dir, "bad", np.zeros((4, 2304), np.float32))
+
+
+def test_feature_writer_rejects_wrong_shapes(tmp_path):
+    w = FIO.FeatureWriter(tmp_path)
+    with pytest.raises(ValueError):
+        w.put(torch.zeros((7, 16)), ["a"])
+    with pytest.raises(ValueError):
+        w.put(torch.zeros((5, 16), dtype=torch.float64), ["a"])
+    w.close()
