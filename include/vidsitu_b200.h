@@ -161,6 +161,14 @@ int vsb_nonlocal_attention(const void* theta, int theta_pitch, const void* phi, 
                            int g_pitch, void* out, int out_pitch, int n, int tq, int tk, int c, int softmax,
                            int dtype, void* stream);
 
+/* ------------------------------------------------------- verb softmax + top-k
+ * Replaces F.softmax(mdl_out, -1) + sort(descending=True)[:topk_save] of
+ * EvalB.forward_one_batch (vidsitu_code/evl_vsitu.py:39-47): per row of the
+ * fp32 [n, pitch] logits (first v entries), idx[row, r] = index of the r-th largest
+ * probability (ties: lower index first, as a stable descending sort) and
+ * prob[row, r] = exp(x - max) / sum(exp(x - max)) of that entry, r < k <= 16.   */
+int vsb_softmax_topk(const float* logits, int n, int v, int pitch, int k, int* idx, float* prob, void* stream);
+
 /* ------------------------------------------------------------- layout helper
  * NTHWC (pitch) -> NCTHW fp32 contiguous, for callers that want the reference's
  * forward_features() tensors (mdl_sf_base.py:21-34) materialised.           */

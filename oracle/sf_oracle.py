@@ -195,3 +195,10 @@ def top5(logits: torch.Tensor) -> torch.Tensor:
     """EvalB.forward_one_batch: softmax, full descending sort, first five ids."""
     probs = F.softmax(logits, dim=-1)
     return probs.sort(dim=-1, descending=True)[1][..., :5]
+
+
+def topk_probs(logits: torch.Tensor, k: int = 5):
+    """EvalB.forward_one_batch (evl_vsitu.py:41-47, 57-60): (ids, scores) of the k most probable verbs."""
+    probs = F.softmax(logits, dim=-1)
+    s, i = probs.sort(dim=-1, descending=True, stable=True)
+    return i[..., :k], s[..., :k]

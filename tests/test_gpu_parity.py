@@ -257,3 +257,57 @@ def test_full_size_batch64_properties():
     assert torch.equal(f_perm, f_a[perm])                          # permutation equivariance
     got = f_a[:5].cpu().numpy()
     assert_bf16_close(got, g["pooled"], "batch-64 pooled[:5]")
+
+
+# ------------------------------------------------------------------ callers either side of the forward
+def test_softmax_topk_matches_evalb_sort():
+    """vsb_softmax_topk vs the oracle's softmax + stable descending sort (evl_vsitu.py:41-47): index lists
+    bit-exact (ties included: lower index first), scores to 1e-6 relative."""
+    from oracle import sf_oracle as O
+    from vidsitu_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for n, v, k in ((1, 5, 5), (7, 1560, 5), (320, 1560, 5), (3, 33, 16), (4, 4097, 1)):
+        x = torch.randn((n, v), generator=g) * 3
+        if v > 40:
+            x[:, 11] = x[:, 3]                     # exact ties
+            x[0, :] = 0.25                         # a constant row: indices 0..k-1
+        want_i, want_p = O.topk_probs(x, k)
+        idx, prob = ops.softmax_topk(x.cuda(), k)
+        assert torch.equal(idx.cpu().long(), want_i), (n, v, k)
+        assert torch.allclose(prob.cpu(), want_p, rtol=2e-6, atol=1e-9), (n, v, k)
+    x3 = torch.randn((2, 5, 1560), generator=g)
+    idx, prob = ops.softmax_topk(x3.cuda(), 5)
+    assert tuple(idx.shape) == (2, 5, 5) and torch.equal(idx.cpu().long(), O.topk_probs(x3, 5)[0])
+    from vidsitu_b200.lib import VsbError
+    with pytest.raises(VsbError):
+        ops.softmax_topk(torch.zeros((2, 4), device="cuda"), 5)      # k > v
+
+
+def test_predict_verbs_and_feature_files(tmp_path):
+    """EvalB prediction dicts (fp32 mode: the top-5 index SET equals the reference's) and the .npy files a
+    downstream get_frm_feats_all reads (feat_extractor.py:98-111)."""
+    from oracle import sf_oracle as O
+    from vidsitu_b200.feat_io import FeatureWriter, read_frm_feats
+    model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=10, crop=64, precision="fp32")
+    model = model.cuda()
+    frames = synthetic_frames(10, 32, 64, seed=77)
+    slow, fast = O.clips_from_frames(frames, cfg.sf_mdl)
+    _, pooled, logits = O.sfbase_forward(model.state_dict(), cfg.sf_mdl, [slow.clone(), fast.clone()])
+    inp = {"frms_ev_slow_tensor": slow.view(2, 5, *slow.shape[1:]).cuda(),
+           "frms_ev_fast_tensor": fast.view(2, 5, *fast.shape[1:]).cuda(),
+           "vseg_idx": torch.tensor([4, 9]).cuda()}
+    preds = model.predict_verbs(inp)
+    assert [p["ann_idx"] for p in preds] == [4, 9]
+    want_i, want_p = O.topk_probs(logits.view(2, 5, -1), 5)
+    for b, p in enumerate(preds):
+        assert len(p["pred_vbs_ev"]) == 5 and len(p["pred_scores_ev"]) == 5
+        for ev in range(5):
+            assert set(p["pred_vbs_ev"][ev]) == set(want_i[b, ev].tolist())
+            assert np.allclose(sorted(p["pred_scores_ev"][ev]), sorted(want_p[b, ev].tolist()), rtol=1e-3)
+    feats = model.extract_features(frames.cuda())
+    with FeatureWriter(tmp_path, "slow_fast_nl_r50_8x8") as w:
+        w.put(feats, ["vid_a", "vid_b"])
+    for v, name in enumerate(("vid_a", "vid_b")):
+        t = read_frm_feats(tmp_path / "slow_fast_nl_r50_8x8", name)
+        assert torch.equal(t, feats[5 * v: 5 * v + 5].cpu())
+        assert rel_err(t.numpy(), pooled[5 * v: 5 * v + 5].numpy()) <= 1e-3

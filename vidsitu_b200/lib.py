@@ -83,6 +83,7 @@ def load() -> C.CDLL:
     lib.vsb_maxpool3d.argtypes = [vp, i, i, i, i, i, i, vp, i, i, i, i, i, i, i, i, i, i, i, i, vp]
     lib.vsb_global_avgpool.argtypes = [vp, i, i, i, i, f32p, i, i, i, vp]
     lib.vsb_linear.argtypes = [f32p, i, i, f32p, f32p, f32p, i, i, vp]
+    lib.vsb_softmax_topk.argtypes = [f32p, i, i, i, i, vp, f32p, vp]
     lib.vsb_nonlocal_attention.argtypes = [vp, i, vp, i, vp, i, vp, i, i, i, i, i, i, i, vp]
     lib.vsb_nthwc_to_ncthw_f32.argtypes = [vp, i, i, i, i, f32p, i, vp]
     lib.vsb_ncthw_f32_to_nthwc.argtypes = [f32p, i, i, ll, i, vp, i, i, i, i, vp]
@@ -92,7 +93,7 @@ def load() -> C.CDLL:
     lib.vsb_debug_conv_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.vsb_debug_conv_plan_info.argtypes = [vp, C.POINTER(C.c_longlong)]
     for name in ("vsb_pack_frames", "vsb_conv3d_plan_create", "vsb_conv3d_run", "vsb_conv3d_plan_out_shape",
-                 "vsb_maxpool3d", "vsb_global_avgpool", "vsb_linear", "vsb_nonlocal_attention",
+                 "vsb_maxpool3d", "vsb_global_avgpool", "vsb_linear", "vsb_softmax_topk", "vsb_nonlocal_attention",
                  "vsb_nthwc_to_ncthw_f32", "vsb_ncthw_f32_to_nthwc", "vsb_debug_im2col_probe",
                  "vsb_debug_umma_semantics", "vsb_debug_umma_rate", "vsb_debug_conv_stats", "vsb_debug_conv_plan_info"):
         getattr(lib, name).restype = i

@@ -203,6 +203,24 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], y: torch
                                y.data_ptr(), dout, int(relu), _stream_ptr()), "vsb_linear")
 
 
+def softmax_topk(logits: torch.Tensor, k: int = 5):
+    """softmax + descending sort + [:k] of EvalB.forward_one_batch (evl_vsitu.py:39-47) on the last dim of
+    fp32 logits [..., V]: returns (idx int32 [..., k], prob fp32 [..., k])."""
+    _require_cuda(logits)
+    if logits.dtype != torch.float32:
+        raise VsbError("softmax_topk takes float32 logits")
+    lead = tuple(logits.shape[:-1])
+    x = logits.reshape(-1, logits.shape[-1])
+    if x.stride(-1) != 1 or x.stride(0) < x.shape[1]:
+        x = x.contiguous()
+    n, v = x.shape
+    idx = torch.empty((n, k), dtype=torch.int32, device=x.device)
+    prob = torch.empty((n, k), dtype=torch.float32, device=x.device)
+    check(_l.load().vsb_softmax_topk(x.data_ptr(), n, v, x.stride(0), k, idx.data_ptr(), prob.data_ptr(),
+                                     _stream_ptr()), "vsb_softmax_topk")
+    return idx.view(*lead, k), prob.view(*lead, k)
+
+
 def nonlocal_attention(theta: Act, phi: Act, g: Act, out: Act, softmax: bool, dtype: int) -> None:
     _require_cuda(theta.buf, phi.buf, g.buf, out.buf)
     tq = theta.t * theta.h * theta.w

@@ -247,6 +247,24 @@ class SFBase(nn.Module):
         mdl_out = self.forward_decoder(feat_out, inp)
         return {"mdl_out": mdl_out}
 
+    @torch.no_grad()
+    def predict_verbs(self, inp: Dict, topk_save: int = 5) -> List[dict]:
+        """`EvalB.forward_one_batch` (vidsitu_code/evl_vsitu.py:39-75): forward, softmax, descending sort,
+        top-5 verbs and scores per event, as the list of {"pred_vbs_ev", "pred_scores_ev", "ann_idx"}
+        dicts the evaluator pickles.  The softmax / ranking run on the GPU (vsb_softmax_topk); only
+        5 ids + 5 scores per event cross PCIe instead of the [B, 5, V] logits."""
+        mdl_out = self.forward(inp)["mdl_out"]
+        idx, prob = ops.softmax_topk(mdl_out.float(), topk_save)
+        idx_l, prob_l = idx.tolist(), prob.tolist()
+        ann_lst = inp["vseg_idx"].tolist()
+        symbols = getattr(self.comm.vb_id_vocab, "symbols", self.comm.vb_id_vocab)   # fairseq Dictionary.symbols
+        out = []
+        for pred_vbs, pred_scores, ann_idx in zip(idx_l, prob_l, ann_lst):
+            assert len(pred_vbs) == 5 and len(pred_scores) == 5
+            out.append({"pred_vbs_ev": [[symbols[pv] for pv in pvb] for pvb in pred_vbs],
+                        "pred_scores_ev": [list(pvs) for pvs in pred_scores], "ann_idx": ann_idx})
+        return out
+
     # ------------------------------------------------------------------ fused fast paths
     @torch.no_grad()
     def extract_features(self, frames: torch.Tensor, want_logits: bool = False, use_graph: bool = True):
