@@ -289,10 +289,10 @@ def test_predict_verbs_and_feature_files(tmp_path):
     from oracle import sf_oracle as O
     from vidsitu_b200.feat_io import FeatureWriter, read_frm_feats
     model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=10, crop=64, precision="fp32")
-    model = model.cuda()
     frames = synthetic_frames(10, 32, 64, seed=77)
     slow, fast = O.clips_from_frames(frames, cfg.sf_mdl)
-    _, pooled, logits = O.sfbase_forward(model.state_dict(), cfg.sf_mdl, [slow.clone(), fast.clone()])
+    _, pooled, logits = O.sfbase_forward(model.state_dict(), cfg.sf_mdl, [slow.clone(), fast.clone()])   # CPU oracle
+    model = model.cuda()
     inp = {"frms_ev_slow_tensor": slow.view(2, 5, *slow.shape[1:]).cuda(),
            "frms_ev_fast_tensor": fast.view(2, 5, *fast.shape[1:]).cuda(),
            "vseg_idx": torch.tensor([4, 9]).cuda()}
