@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VSB_ABI_VERSION 3
+#define VSB_ABI_VERSION 4
 
 typedef enum vsb_status {
   VSB_OK = 0,
@@ -118,7 +118,19 @@ typedef struct vsb_conv_desc {
   const void* in2;
   int t2, h2, w2, cin2, in2_pitch;
   int st2, sh2, sw2;
+  /* more tuning of the bf16 epilogue, 0 = automatic: column chunk of the per-warp staging slabs
+   * (32 or 64 channels) and slabs per epilogue warp (2..4; residual prefetch distance = epi_bufs - 1).
+   * They only move shared memory between the main-loop ring and the epilogue; results are unchanged. */
+  int epi_n;
+  int epi_bufs;
+  /* plan variants, OR of VSB_PLAN_* (0 = automatic); like the tuning above they never change results */
+  int flags;
 } vsb_conv_desc;
+
+#define VSB_PLAN_STREAM_WEIGHTS 1 /* im2col: never keep the weight block resident in shared memory      */
+#define VSB_PLAN_ONE_CTA 2        /* one CTA per SM even when two would fit                              */
+#define VSB_PLAN_NO_PAIR 4        /* window: the MMA issuer does not interleave two tiles                */
+#define VSB_PLAN_NO_TSCATTER 8    /* window: output-stationary temporal taps instead of temporal scatter */
 
 typedef struct vsb_conv_plan vsb_conv_plan;
 

@@ -35,4 +35,5 @@ step = e0.elapsed_time(e1) / 10
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump({"name": name, "tune": tune, "step_ms": step, "ops": [[o, round(ms, 4)] for o, ms, _ in ops]},
           open(f"gpurun_out/sweep_{name}.json", "w"))
-print(name, "step_ms", round(step, 3), "sum_ops", round(sum(ms for _, ms, _ in ops), 3), flush=True)
+chk = float(eng.feats.double().abs().sum())   # bit-exact across scheduling variants
+print(name, "step_ms", round(step, 3), "sum_ops", round(sum(ms for _, ms, _ in ops), 3), "feats_abs_sum", repr(chk), flush=True)

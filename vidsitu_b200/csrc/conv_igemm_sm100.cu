@@ -621,11 +621,15 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   const int cps = 64 / kchunk;  // a pipeline stage always has room for 64 K-elements
   const int num_kstages = ceil_div(total_chunks, cps);
   const int bar_bytes = 1024 + 2048;  // barriers + the CTA's (scale, bias) table (block_n <= 256 float2)
-  static const bool no_bres = getenv("VSB_NO_BRES") != nullptr;
+  static const bool no_bres_env = getenv("VSB_NO_BRES") != nullptr;
+  const bool no_bres = no_bres_env || (d->flags & VSB_PLAN_STREAM_WEIGHTS);
   static const char* ew_env = getenv("VSB_EPI_WARPS");
   // (measured on B200: the 16-warp epilogue shape does not beat 8 warps -- these layers are HBM-bound, the
   // accumulator wait is back-pressure -- so it is opt-in: VSB_EPI_WARPS=16)
   const int epi_warps = (ew_env && atoi(ew_env) == 16) ? 16 : 8;
+  if (d->epi_n != 0 && d->epi_n != 32 && d->epi_n != 64) FAIL(VSB_ERR_INVALID, "epi_n must be 0, 32 or 64");
+  if (d->epi_bufs != 0 && (d->epi_bufs < 2 || d->epi_bufs > kMaxEpiBufs)) FAIL(VSB_ERR_INVALID, "epi_bufs must be 0 or 2..4");
+  const int epi_n_env = d->epi_n, epi_bufs_env = d->epi_bufs;  // caller's tuning (0 = automatic)
 
   // ---- shared-memory plan for one (block_n, weight residency) choice.
   // Weight-stationary: the CTA's [block_n x K] weight block is fetched once (every CTA owns ONE column block:
@@ -643,9 +647,11 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
     // residual) and the 16-warp shape take 32-column chunks so the staging slabs leave room for the ring
     sp.epi_n = bn >= 64 ? 64 : bn;
     if (bn >= 64 && ((!d->residual && num_kstages >= 8) || epi_warps == 16)) sp.epi_n = 32;
+    if (bn >= 64 && epi_n_env) sp.epi_n = epi_n_env;
     if (bn % sp.epi_n) return sp;
     const int epi_buf_bytes = epi_warps * 32 * sp.epi_n * 2;  // one 32-row slab per epilogue warp
     sp.epi_bufs = d->residual ? 3 : 2;  // slabs per epilogue warp (residual prefetch distance = epi_bufs - 1)
+    if (epi_bufs_env) sp.epi_bufs = epi_bufs_env;
     for (;;) {
       const long long fixed = (resident ? ((sp.bres_bytes + 1023) & ~1023ll) : 0) + sp.epi_bufs * epi_buf_bytes + bar_bytes + 1024;
       int stages = d->stages;
@@ -659,6 +665,8 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
         if (stages > 8) stages = 8;
       }
       if (stages > 16) stages = 16;
+      // a caller-given depth that does not fit is shortened rather than rejected
+      while (d->stages && stages > 2 && (long long)stages * sp.stage_bytes + fixed > 227 * 1024) --stages;
       if (stages > num_kstages * 2) stages = num_kstages * 2;
       sp.stages = stages;
       sp.smem_bytes = (size_t)((stages > 0 ? stages : 0) * (long long)sp.stage_bytes + fixed);
@@ -686,7 +694,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
       const int nt = d->cout / bn;
       SmemPlan t = plan_smem(bn, true);
       const long long limit = nt == 1 ? 96 * 1024 : 128 * 1024;
-      if (t.fits && t.bres_bytes <= limit && (nt == 1 || (t.stages >= 3 && t.epi_bufs == (d->residual ? 3 : 2)))) {
+      if (t.fits && t.bres_bytes <= limit && (nt == 1 || (t.stages >= 3 && t.epi_bufs == (epi_bufs_env ? epi_bufs_env : (d->residual ? 3 : 2))))) {
         // compute-bound long-K layers keep the wide block (fewer A re-reads); resident mode is for short K
         if (nt > 1 && num_kstages > 8) continue;
         sp = t;
@@ -786,7 +794,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   const int by_smem = (int)((227 * 1024) / smem_bytes);
   if (ctas_per_sm > by_smem) ctas_per_sm = by_smem;
   if (ctas_per_sm > 2) ctas_per_sm = 2;
-  if (ctas_per_sm < 1 || epi_warps == 16) ctas_per_sm = 1;
+  if (ctas_per_sm < 1 || epi_warps == 16 || (d->flags & VSB_PLAN_ONE_CTA)) ctas_per_sm = 1;
   int sms = 148;
   {
     int dev = 0;

@@ -568,17 +568,20 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
   const long long b_bytes = (long long)b_blocks * block_n * 128;
   // temporal-scatter mode (see the MMA issuer): all temporal taps in one N = kt * block_n MMA, output
   // frames in a power-of-two ring of TMEM accumulators
-  static const bool no_tsc = getenv("VSB_WIN_NO_TSC") != nullptr;
+  static const bool no_tsc_env = getenv("VSB_WIN_NO_TSC") != nullptr;
+  const bool no_tsc = no_tsc_env || (d->flags & VSB_PLAN_NO_TSCATTER);
   int acc_slots = 512 / block_n > kMaxAcc ? kMaxAcc : 512 / block_n;
   const bool tsc = !no_tsc && d->kt > 1 && d->kt * block_n <= 256 && (block_n & (block_n - 1)) == 0 &&
                    acc_slots >= d->kt + 2 && d->pt_lo < d->kt && d->pt_hi < d->kt;
   const uint32_t b_block_bytes = (uint32_t)block_n * 128 * (tsc ? d->kt : 1);
   int epi_n = block_n >= 64 ? 32 : block_n;  // >= 2 chunks per tile keep both epilogue warp groups busy
+  if (d->epi_n && block_n >= 2 * d->epi_n && block_n % d->epi_n == 0) epi_n = d->epi_n;  // caller's tuning
   if (block_n % epi_n) epi_n = 16;
   const int epi_chunks = block_n / epi_n;
   const int epi_warps = epi_chunks >= 2 ? 8 : 4;
   if (epi_warps == 8 && (epi_chunks & 1)) return 1;  // chunk parity split needs an even chunk count
   int epi_bufs = d->residual ? 3 : 2;
+  if (d->epi_bufs >= 2 && d->epi_bufs <= kMaxEpiBufs) epi_bufs = d->epi_bufs;
   const int bar_bytes = 1024 + 2048 + 2048;  // barriers + per-step descriptor table + (scale, bias) pairs
   // the tensor-core operand read of the last stage runs up to 128 rows past the largest tap offset
   const uint32_t max_tap_rows = (uint32_t)((d->sh == 1 ? (d->kh - 1) : (d->kh - 1) / 2) * RP + d->kw - 1);
@@ -589,7 +592,8 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
   for (;;) {
     const long long fixed = ((b_bytes + 1023) & ~1023ll) + (long long)epi_warps * epi_bufs * 32 * epi_n * 2 +
                             bar_bytes + 1024;
-    const int want = tsc ? 3 : (d->kt > 1 ? d->kt + 3 : 6);
+    int want = tsc ? 3 : (d->kt > 1 ? d->kt + 3 : 6);
+    if (d->stages > want) want = d->stages;  // caller's tuning may deepen the ring (room permitting)
     // two co-resident CTAs per SM (two independent MMA chains) when a >= 4-stage ring fits in half the SM
     long long room = 113 * 1024 - fixed;
     if (d->kt > 1 || room < 4ll * stage_bytes) room = 227 * 1024 - fixed;
@@ -702,7 +706,8 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
   p.off_bar = p.off_epi + (uint32_t)(epi_warps * epi_bufs * 32 * epi_n * 2);
   p.off_tab = p.off_bar + 1024;
   p.idesc = umma_idesc_bf16(128, block_n);
-  static const bool no_pair = getenv("VSB_WIN_NO_PAIR") != nullptr;
+  static const bool no_pair_env = getenv("VSB_WIN_NO_PAIR") != nullptr;
+  const bool no_pair = no_pair_env || (d->flags & VSB_PLAN_NO_PAIR);
   p.pair = (!no_pair && d->kt == 1 && block_n <= 128 && stages >= 4) ? 1 : 0;
   p.nacc = tsc ? acc_slots : (p.pair ? 4 : 2);
   p.nacc_shift = 0;
@@ -725,7 +730,8 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
     if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     (void)cudaGetLastError();
   }
-  static const bool one_cta = getenv("VSB_WIN_ONE_CTA") != nullptr;
+  static const bool one_cta_env = getenv("VSB_WIN_ONE_CTA") != nullptr;
+  const bool one_cta = one_cta_env || (d->flags & VSB_PLAN_ONE_CTA);
   const int ctas_per_sm = (!one_cta && smem_bytes <= 113 * 1024 && tmem_cols <= 256) ? 2 : 1;
   plan->grid = (unsigned)(p.total_runs < sms * ctas_per_sm ? p.total_runs : sms * ctas_per_sm);
   plan->desc.block_n = block_n;

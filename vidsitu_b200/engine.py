@@ -17,6 +17,7 @@ allocation-free, so it is captured once into a CUDA graph and replayed.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -27,6 +28,20 @@ from .lib import VSB_BF16, VSB_F32, VsbError
 from .ops import Act, ConvPlan
 from .weights import (fold_bn, group_conv_weight, group_tap_ranges, identity_affine, pack_conv_weight, round_up,
                       slice_tap_channels)
+
+
+_PLAN_KNOBS = ("block_n", "kchunk", "stages", "epi_n", "epi_bufs", "flags")
+_TUNE_TABLE: Optional[dict] = None
+
+
+def _tune_table() -> dict:
+    """Per-shape plan tuning measured on B200 (tools/autotune.py); missing file = all automatic."""
+    global _TUNE_TABLE
+    if _TUNE_TABLE is None:
+        import json
+        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tune_table.json")
+        _TUNE_TABLE = json.load(open(p)).get("entries", {}) if os.path.exists(p) else {}
+    return _TUNE_TABLE
 
 
 class _Pool:
@@ -77,11 +92,18 @@ class ClipEngine:
         self._pools = [_Pool(self.device, self.tdt) for _ in range(max(1, spec.num_pathways))]
         self._pool = self._pools[0]
         self._graph = None
-        import os
+        self._main_stream = None
         self.two_streams = (spec.num_pathways == 2 and dtype == VSB_BF16
                             and str(self.tune.get("*", {}).get("streams", os.environ.get("VSB_STREAMS", "2"))) == "2")
         self._side_stream = None
+        # Lateral convs write a channel slice that no slow-pathway kernel touches, so with dedicated concat
+        # buffers the Fast stream never waits for the Slow one (only the next slow stage waits for the lateral).
+        self.early_lateral = self.two_streams and str(self.tune.get("*", {}).get(
+            "early_lateral", os.environ.get("VSB_EARLY_LATERAL", "1"))) == "1"
+        self._dedicated: List[torch.Tensor] = []
+        self.dedicated_bytes = 0
         self.op_bytes: Dict[str, float] = {}
+        self.op_sig: Dict[str, str] = {}
         self.fused_shortcuts: List[str] = []   # branch1 convs computed inside their block's last conv
         self.crop = spec.crop
         if self.crop % 16:
@@ -136,12 +158,20 @@ class ClipEngine:
     def _alloc(self, n, t, h, w, c_real, pitch: Optional[int] = None, min_c: int = 0) -> Act:
         c = max(self._store(c_real), min_c)
         pitch = pitch or c
-        buf = self._pool.take(n * t * h * w * pitch)
+        if pitch > c and self.early_lateral:
+            # a slow tensor with room for the lateral channels: the Fast pathway's stream writes its slice
+            # without waiting for the slow stage, so the buffer is never shared with another tensor
+            buf = torch.empty(n * t * h * w * pitch, dtype=self.tdt, device=self.device)
+            self._dedicated.append(buf)
+            self.dedicated_bytes += buf.numel() * buf.element_size()
+        else:
+            buf = self._pool.take(n * t * h * w * pitch)
         return Act(buf, n, t, h, w, c, pitch, 0, c_real)
 
     def _free(self, a: Act) -> None:
-        if a.buf is not None and not any(a.buf is i.buf for i in self.inputs):
-            self._pool.give(a.buf)
+        if a.buf is None or any(a.buf is i.buf for i in self.inputs) or any(a.buf is d for d in self._dedicated):
+            return
+        self._pool.give(a.buf)
 
     def _tensor(self, key: str) -> torch.Tensor:
         if key not in self._t:
@@ -162,10 +192,21 @@ class ClipEngine:
         wo = (x.w + 2 * cs.pad[2] - cs.kernel[2]) // cs.stride[2] + 1
         return to, ho, wo
 
-    def _tune(self, key: str) -> dict:
-        tune = dict(self.tune.get("*", {}))
+    def _tune(self, key: str, sig: Optional[str] = None) -> dict:
+        """Tuning of one conv, lowest to highest priority: the shipped per-shape table
+        (vidsitu_b200/tune_table.json, measured on B200 by tools/autotune.py), the caller's "*"
+        entry, the caller's per-layer entry."""
+        tune = dict(_tune_table().get(sig, {})) if (sig and self.tune.get("*", {}).get("table", True)) else {}
+        tune.update(self.tune.get("*", {}))
         tune.update(self.tune.get(key, {}))
         return tune
+
+    @staticmethod
+    def _sig(cs: ConvSpec, x: Act, out: Act, residual: Optional[Act], x2: Optional[Act] = None) -> str:
+        """Shape signature of a conv launch (the key of the tuning table)."""
+        k, st = cs.kernel, cs.stride
+        return (f"{x.c}>{out.c}|k{k[0]}{k[1]}{k[2]}|s{st[0]}{st[1]}{st[2]}|o{out.t}x{out.h}x{out.w}"
+                f"|p{x.pitch}>{out.pitch}|r{int(residual is not None)}|x{x2.c if x2 is not None else 0}")
 
     def _group_factor(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act]) -> int:
         """Pixels per GEMM row (weights.group_conv_weight): thin-channel layers are re-viewed so that
@@ -185,14 +226,15 @@ class ClipEngine:
                      pad_w: Optional[int] = None, j: Optional[int] = None) -> Optional[ConvPlan]:
         """Shared-memory window algorithm (conv_win_sm100.cu) for convs with spatial taps and <= 64
         (grouped) input channels: returns the plan, or None when the layer is outside its domain."""
-        if self.dtype != VSB_BF16 or self._tune(cs.key).get("algo", "auto") == "im2col":
+        tn = self._tune(cs.key, self._sig(cs, x, out, residual))
+        if self.dtype != VSB_BF16 or tn.get("algo", "auto") == "im2col":
             return None
         if cs.kernel[1] * cs.kernel[2] == 1 or cs.stride[0] != 1 or x.h < 14:
             return None
         dense = lambda a: a is None or (a.pitch == a.c and a.c_off == 0)
         sw = cs.stride[2]
         if j is None:
-            j = self._tune(cs.key).get("win_group", max(1, (64 // x.c) // sw) if x.c <= 64 else 0)
+            j = tn.get("win_group", max(1, (64 // x.c) // sw) if x.c <= 64 else 0)
         if j < 1:
             return None
         # stems pass pad_w: their input rows carry a zero border, so grouped widths need not match
@@ -222,9 +264,10 @@ class ClipEngine:
         try:
             return ConvPlan(self.dtype, xin, w, j * out.c, (cs.kernel[0], cs.kernel[1], ngt),
                             (cs.stride[0], cs.stride[1], 1), (cs.pad[0], cs.pad[1], plo), (cs.pad[0], cs.pad[1], phi),
-                            scale.repeat(j), bias.repeat(j), yout, res, relu, algo=2, kw_ranges=ranges)
+                            scale.repeat(j), bias.repeat(j), yout, res, relu, algo=2, kw_ranges=ranges,
+                            **{k: v for k, v in tn.items() if k in ("stages", "epi_n", "epi_bufs", "flags")})
         except VsbError:
-            if self._tune(cs.key).get("algo") == "window":
+            if tn.get("algo") == "window":
                 raise
             return None
 
@@ -232,11 +275,16 @@ class ClipEngine:
         if x.c_real != cs.cin:
             raise VsbError(f"{cs.key}: input has {x.c_real} channels, conv expects {cs.cin}")
         scale, bias = self._affine(cs, out.c)
-        tune = {k: v for k, v in self._tune(cs.key).items() if k in ("block_n", "kchunk", "stages")}
+        sig = self._sig(cs, x, out, residual)
+        self.op_sig[cs.key] = sig
+        tune = {k: v for k, v in self._tune(cs.key, sig).items() if k in _PLAN_KNOBS}
         relu = cs.relu if relu is None else relu
         wt = self._tensor(cs.key + ".weight")
         plan = self._window_plan(cs, x, out, residual, relu, scale, bias, wt)
         j = self._group_factor(cs, x, out, residual) if plan is None else 0
+        bn = tune.get("block_n", 0)
+        if bn and ((max(j, 1) * out.c) % bn or bn > max(j, 1) * out.c):
+            tune.pop("block_n")     # a table / "*" entry that does not fit this layer: automatic
         if plan is not None:
             pass
         elif j > 1:
@@ -286,7 +334,11 @@ class ClipEngine:
         w_c = pack_conv_weight(self._tensor(c.key + ".weight"), b.c, out.c, torch.float32).reshape(out.c, b.c)
         w_1 = pack_conv_weight(self._tensor(br.key + ".weight"), k2, out.c, torch.float32).reshape(out.c, k2)
         w = torch.cat([w_c * r_c[:, None], w_1 * r_1[:, None]], dim=1).to(self.tdt).contiguous()
-        tune = {k: v for k, v in self._tune(c.key).items() if k in ("block_n", "stages")}
+        sig = self._sig(c, b, out, None, x)
+        self.op_sig[c.key] = sig
+        tune = {k: v for k, v in self._tune(c.key, sig).items() if k in _PLAN_KNOBS and k != "kchunk"}
+        if tune.get("block_n", 0) and (out.c % tune["block_n"] or tune["block_n"] > out.c):
+            tune.pop("block_n")
         try:
             plan = ConvPlan(self.dtype, b, w, out.c, c.kernel, c.stride, c.pad, None, s, b_c + b_1, out, None, True,
                             kchunk=kchunk, x2=x, stride2=br.stride, **tune)
@@ -529,10 +581,17 @@ class ClipEngine:
             self.run_trunk()
             self.run_head()
             return
-        main = torch.cuda.current_stream()
+        origin = torch.cuda.current_stream()
+        prio = int(self.tune.get("*", {}).get("prio", os.environ.get("VSB_STREAM_PRIO", "0")))
         if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream(self.device)
+            # prio 1: the Slow pathway (the critical path) runs on a high-priority stream, the Fast pathway
+            # fills in; prio 2: the other way round; 0: Slow on the caller's stream, both default priority
+            self._side_stream = torch.cuda.Stream(self.device, priority=-1 if prio == 2 else 0)
+            self._main_stream = torch.cuda.Stream(self.device, priority=-1) if prio == 1 else None
         side = self._side_stream
+        main = self._main_stream if self._main_stream is not None else origin
+        if main is not origin:
+            main.wait_stream(origin)
         streams = (main, side)
 
         def sync(src: int, dst: int) -> None:
@@ -545,12 +604,13 @@ class ClipEngine:
         for name, fn, _ in self.trunk_ops:
             sid = self._op_stream(name)
             is_fuse = "_fuse" in name
-            if is_fuse:
-                sync(0, 1)          # the slow tensor the lateral conv writes into is complete (and live)
+            if is_fuse and not self.early_lateral:
+                sync(0, 1)          # pooled concat buffer: wait until the slow stage has made it live
             elif sid == 0 and prev_fuse:
                 sync(1, 0)          # the next slow stage reads the concatenated channels
             if sid == 0:
-                fn()
+                with torch.cuda.stream(main):
+                    fn()
                 if prev_fuse:
                     prev_fuse = False
             else:
@@ -566,9 +626,12 @@ class ClipEngine:
                 with torch.cuda.stream(side):
                     fn()
             else:
-                fn()
+                with torch.cuda.stream(main):
+                    fn()
         if side is not None:
             sync(1, 0)
+        if main is not origin:
+            origin.wait_stream(main)
 
     def capture(self) -> None:
         """Capture trunk + head once into a CUDA graph (inputs/outputs are static buffers)."""

@@ -47,6 +47,7 @@ class ConvDesc(C.Structure):
         ("in2", C.c_void_p),
         ("t2", C.c_int), ("h2", C.c_int), ("w2", C.c_int), ("cin2", C.c_int), ("in2_pitch", C.c_int),
         ("st2", C.c_int), ("sh2", C.c_int), ("sw2", C.c_int),
+        ("epi_n", C.c_int), ("epi_bufs", C.c_int), ("flags", C.c_int),
     ]
 
 
@@ -97,8 +98,8 @@ def load() -> C.CDLL:
                  "vsb_nthwc_to_ncthw_f32", "vsb_ncthw_f32_to_nthwc", "vsb_debug_im2col_probe",
                  "vsb_debug_umma_semantics", "vsb_debug_umma_rate", "vsb_debug_conv_stats", "vsb_debug_conv_plan_info"):
         getattr(lib, name).restype = i
-    if lib.vsb_abi_version() != 3:
-        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 3")
+    if lib.vsb_abi_version() != 4:
+        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 4")
     _lib = lib
     return lib
 

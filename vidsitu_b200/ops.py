@@ -67,7 +67,7 @@ class ConvPlan:
                  scale: torch.Tensor, bias: torch.Tensor, out: Act, residual: Optional[Act] = None,
                  relu: bool = False, block_n: int = 0, kchunk: int = 0, stages: int = 0, algo: int = 0,
                  kw_ranges: Optional[Sequence[Sequence[int]]] = None, x2: Optional[Act] = None,
-                 stride2: Sequence[int] = (1, 1, 1)):
+                 stride2: Sequence[int] = (1, 1, 1), epi_n: int = 0, epi_bufs: int = 0, flags: int = 0):
         _require_cuda(x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None,
                       x2.buf if x2 is not None else None)
         pad_hi = pad_lo if pad_hi is None else pad_hi
@@ -90,6 +90,7 @@ class ConvPlan:
         d.out_pitch = out.pitch
         d.block_n, d.kchunk, d.stages = block_n, kchunk, stages
         d.algo = algo
+        d.epi_n, d.epi_bufs, d.flags = epi_n, epi_bufs, flags
         k_per_tap_row = x.c * d.kw
         if kw_ranges is not None:
             if len(kw_ranges) != d.kw or d.kw > 8:
