@@ -22,7 +22,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import ROOT, build_model, synthetic_frames
+from common import NUM_VERBS, ROOT, build_model, synthetic_frames
 
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
@@ -311,3 +311,24 @@ def test_predict_verbs_and_feature_files(tmp_path):
         t = read_frm_feats(tmp_path / "slow_fast_nl_r50_8x8", name)
         assert torch.equal(t, feats[5 * v: 5 * v + 5].cpu())
         assert rel_err(t.numpy(), pooled[5 * v: 5 * v + 5].numpy()) <= 1e-3
+
+
+def test_whole_video_event_windowing():
+    """device-resident [B, 300, H, W, 3] videos, the five event windows cut by the pack kernel
+    (dat_loader.py:454-472).  Bit-equal to running the explicitly gathered clips, and within the bf16
+    tolerance of the oracle fed with the reference's own index tables."""
+    from oracle import sf_oracle as O
+    model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=10, crop=64)
+    g = torch.Generator().manual_seed(99)
+    videos = torch.randint(0, 256, (2, 300, 64, 64, 3), dtype=torch.uint8, generator=g)
+    windows = O.event_frame_indices(cfg.sf_mdl.DATA.NUM_FRAMES, cfg.sf_mdl.DATA.SAMPLING_RATE)
+    clips = torch.stack([videos[v][windows[ev]] for v in range(2) for ev in range(5)])      # [10, 32, 64, 64, 3]
+    _, pooled, logits = O.sfbase_forward(model.state_dict(), cfg.sf_mdl, O.clips_from_frames(clips, cfg.sf_mdl))
+    model = model.cuda()
+    feats, lg = model.extract_video_features(videos.cuda(), want_logits=True)
+    assert tuple(feats.shape) == (2, 5, 2304) and tuple(lg.shape) == (2, 5, NUM_VERBS)
+    assert_bf16_close(feats.view(10, -1).cpu().numpy(), pooled.numpy(), "whole-video pooled features")
+    by_clip = model.extract_features(clips.cuda())
+    assert torch.equal(by_clip.view(2, 5, -1), feats)
+    model.micro_batch = 5                       # one video per engine run
+    assert torch.equal(model.extract_video_features(videos.cuda()), feats)

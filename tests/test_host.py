@@ -181,3 +181,18 @@ print('ok', r)
                          capture_output=True, text=True, timeout=240, env=env)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 2
+
+
+def test_event_windows_match_the_oracle_and_the_reference_facts():
+    """vidsitu_b200.events (product) vs oracle.event_frame_indices (the reference restatement,
+    dat_loader.py:69-79,454-472 + utils/video_utils.py:18-38), plus the SURVEY 8(a1) facts."""
+    from oracle import sf_oracle as O
+    from vidsitu_b200 import events as E
+    assert E.event_centers(30) == [30, 90, 150, 210, 270]
+    for nf, rate in ((32, 2), (8, 8), (64, 2), (16, 4)):
+        for fps, total in ((30, 300), (30, 120), (25, 300), (30, 1)):
+            assert E.event_frame_indices(nf, rate, fps, total) == O.event_frame_indices(nf, rate, fps, total)
+    ev = E.event_frame_indices(32, 2)
+    assert ev[0][:3] == [0, 0, 2] and ev[0][-1] == 60 and ev[4][-2:] == [298, 299] and all(len(e) == 32 for e in ev)
+    assert E.event_frame_indices(8, 8)[0] == [0, 6, 14, 22, 30, 38, 46, 54]
+    assert E.event_frame_indices(64, 2)[0][:18] == [0] * 18

@@ -107,6 +107,8 @@ class NetSpec:
     mean: Tuple[float, ...] = (0.45, 0.45, 0.45)
     std: Tuple[float, ...] = (0.225, 0.225, 0.225)
     reverse_input_channel: bool = False
+    sampling_rate: int = 2      # DATA.SAMPLING_RATE: frame step inside an event window
+    target_fps: int = 30        # DATA.TARGET_FPS of the extracted frames
 
     def pathway_frames(self) -> List[int]:
         if self.num_pathways == 2:
@@ -266,4 +268,5 @@ def build_spec(cfg) -> NetSpec:
         fc_init_std=cfg.MODEL.FC_INIT_STD, crop=int(getattr(cfg.DATA, "CROP_SIZE", 224)),
         mean=tuple(cfg.DATA.MEAN), std=tuple(cfg.DATA.STD),
         reverse_input_channel=bool(cfg.DATA.REVERSE_INPUT_CHANNEL),
+        sampling_rate=int(cfg.DATA.SAMPLING_RATE), target_fps=int(getattr(cfg.DATA, "TARGET_FPS", 30)),
     )

@@ -550,6 +550,27 @@ class ClipEngine:
             ops.pack_frames(frames, self.fast_idx, spec.mean, spec.std, self.inputs[0], self.dtype,
                             spec.reverse_input_channel, self.x_off)
 
+    def load_videos(self, videos: torch.Tensor) -> None:
+        """uint8 [n/5, F, H, W, 3] whole videos (F = 300 extracted frames, dat_loader.py:454-458) resident
+        on the GPU: the five event windows of every video (events.event_frame_indices) are gathered by
+        the pack kernel straight from the video tensor.  Clips are laid out EVENT-major in the batch
+        (clip = event * n_videos + video): one pack launch per event and pathway."""
+        from .events import EVENTS_PER_VIDEO, event_frame_indices
+        spec = self.spec
+        if videos.dim() != 5 or videos.shape[0] * EVENTS_PER_VIDEO != self.n:
+            raise VsbError(f"expected videos [{self.n // EVENTS_PER_VIDEO}, F, {self.crop}, {self.crop}, 3] for "
+                           f"an engine of {self.n} clips")
+        n_vid, f = int(videos.shape[0]), int(videos.shape[1])
+        windows = event_frame_indices(spec.num_frames, spec.sampling_rate, spec.target_fps, f)
+        for ev, win in enumerate(windows):
+            for p, a in enumerate(self.inputs):
+                idx = [win[i] for i in self.slow_idx] if (spec.num_pathways == 2 and p == 0) else win
+                per_clip = a.t * a.h * a.w * a.pitch
+                sub = Act(a.buf[ev * n_vid * per_clip: (ev + 1) * n_vid * per_clip], n_vid, a.t, a.h, a.w, 4, 4,
+                          c_real=3)
+                ops.pack_frames(videos, idx, spec.mean, spec.std, sub, self.dtype, spec.reverse_input_channel,
+                                self.x_off)
+
     def load_ncthw(self, xs: Sequence[torch.Tensor]) -> None:
         """The reference's already-normalised fp32 [n, 3, T_p, H, W] pathway tensors."""
         if len(xs) != len(self.inputs):

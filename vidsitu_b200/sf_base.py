@@ -291,6 +291,37 @@ class SFBase(nn.Module):
         return f
 
     @torch.no_grad()
+    def extract_video_features(self, videos: torch.Tensor, want_logits: bool = False, use_graph: bool = True):
+        """videos: uint8 [B, F, H, W, 3] on the GPU, F = the 300 frames `get_frms_all` lists per video
+        (dat_loader.py:454-458).  The five event windows (dat_loader.py:69-79, 459-472) are cut on the
+        device by the pack kernel; returns feats [B, 5, D] fp32 - the array `FeatExtract.forward_all`
+        saves per video (feat_extractor.py:98-111) - and, on request, logits [B, 5, V]."""
+        if not videos.is_cuda:
+            raise VsbError("videos must be a CUDA tensor (pinned-host staging is the caller's H2D copy)")
+        b = videos.shape[0]
+        per = max(1, self.micro_batch // 5)
+        feats, logits = [], []
+        for s in range(0, b, per):
+            e = min(b, s + per)
+            eng = self._engine(5 * (e - s), videos.device)
+            eng.load_videos(videos[s:e])
+            if use_graph:
+                eng.replay()
+            else:
+                eng.run()
+            # engine rows are event-major (event * n_videos + video) -> [videos, 5, D]
+            # (copied out: the engine's output buffers are reused by the next chunk)
+            feats.append(torch.empty((e - s, 5, eng.feats.shape[1]), dtype=torch.float32, device=videos.device)
+                         .copy_(eng.feats.view(5, e - s, -1).transpose(0, 1)))
+            if want_logits:
+                logits.append(torch.empty((e - s, 5, eng.logits.shape[1]), dtype=torch.float32, device=videos.device)
+                              .copy_(eng.logits.view(5, e - s, -1).transpose(0, 1)))
+        f = torch.cat(feats, 0) if len(feats) > 1 else feats[0]
+        if want_logits:
+            return f, (torch.cat(logits, 0) if len(logits) > 1 else logits[0])
+        return f
+
+    @torch.no_grad()
     def forward_pooled(self, inp: Dict, want_logits: bool = True):
         """Same inputs as forward() (reference fp32 NCTHW tensors) but never materialises the
         [N,2048,T,7,7] maps: returns (feats [B,5,D], logits [B,5,V])."""
