@@ -111,6 +111,20 @@ def test_window_conv(case):
     assert info["ok"], info
 
 
+def _two_sm_cases():
+    import gpu_check_ops as G
+    return G.TWO_SM_CASES
+
+
+@pytest.mark.parametrize("case", _two_sm_cases(), ids=lambda c: c[0])
+def test_conv_two_sm_pairs(case):
+    """conv_igemm2_sm100.cu (VSB_PLAN_TWO_SM): CTA pairs, tcgen05 cta_group::2, 256-pixel tiles vs torch conv3d."""
+    import gpu_check_ops as G
+    info = G.run_conv_case(case, 0)
+    assert info["algo"] == 3, info          # the pair kernel really ran
+    assert info["ok"], info
+
+
 def _dual_cases():
     import gpu_check_ops as G
     return G.DUAL_CASES

@@ -136,6 +136,7 @@ def run_conv_case(case, dtype):
     plan = ConvPlan(dtype, xa, wp, cout, k, s, p, None, scale, bias, oa, ra, relu, **tune)
     plan.run()
     torch.cuda.synchronize()
+    plan_algo = plan.info()["algo"] if dtype == L.VSB_BF16 else 0
     ref = _ref_conv(x, wt, s, p, scale, bias, res, relu)
     got = outbuf[..., out_off:out_off + cout]
     if dtype == L.VSB_BF16:
@@ -149,6 +150,7 @@ def run_conv_case(case, dtype):
         if not info["slice_clean"]:
             info["n_bad"] += 1
     info["ok"] = info["n_bad"] == 0 and info["finite"]
+    info["algo"] = plan_algo
     return info
 
 
@@ -302,6 +304,18 @@ def run_dual_case(name, cb, cx, cout, s, n, t, H, W, x_pitch=None):
 
 
 # (name, c_b, c_x, cout, stride, n, t, H, W[, x_pitch])
+# two-SM variant (conv_igemm2_sm100.cu, VSB_PLAN_TWO_SM = 16): kchunk-64 layers with streamed weights
+TWO_SM_CASES = [
+    ("sm2_pw_256_256_res", 2, 2, 14, 14, 256, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), True, True, dict(flags=16)),     # 7 m-tiles (odd)
+    ("sm2_sp3_256", 2, 2, 14, 14, 256, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, dict(flags=16)),
+    ("sm2_tm3_1024_256", 1, 8, 14, 14, 1024, 256, (3, 1, 1), (1, 1, 1), (1, 0, 0), False, True, dict(flags=16)),
+    ("sm2_sp3_512_7x7", 3, 2, 7, 7, 512, 512, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, dict(flags=16)),         # 2 column blocks
+    ("sm2_pw_s2_320_512", 2, 2, 28, 28, 320, 512, (1, 1, 1), (1, 2, 2), (0, 0, 0), False, False, dict(flags=16)),
+    ("sm2_sp3_s2_128", 2, 2, 28, 28, 128, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), False, True, dict(flags=16)),
+    ("sm2_sp3_256_many_tiles", 8, 8, 14, 14, 256, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, dict(flags=16)),  # 98 m-tiles
+    ("sm2_sp3_256_bn128", 4, 4, 14, 14, 256, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, dict(flags=16, block_n=128)),
+]
+
 DUAL_CASES = [
     ("dual_64_80_256_s1", 64, 80, 256, 1, 2, 2, 28, 28),          # slow res2: x = 64 + 16 lateral channels (OOB K fill)
     ("dual_128_320_512_s2", 128, 320, 512, 2, 2, 2, 28, 28),      # slow res3

@@ -622,7 +622,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   const int num_kstages = ceil_div(total_chunks, cps);
   const int bar_bytes = 1024 + 2048;  // barriers + the CTA's (scale, bias) table (block_n <= 256 float2)
   static const bool no_bres_env = getenv("VSB_NO_BRES") != nullptr;
-  const bool no_bres = no_bres_env || (d->flags & VSB_PLAN_STREAM_WEIGHTS);
+  const bool no_bres = no_bres_env || (d->flags & (VSB_PLAN_STREAM_WEIGHTS | VSB_PLAN_TWO_SM));
   static const char* ew_env = getenv("VSB_EPI_WARPS");
   // (measured on B200: the 16-warp epilogue shape does not beat 8 warps -- these layers are HBM-bound, the
   // accumulator wait is back-pressure -- so it is opt-in: VSB_EPI_WARPS=16)
@@ -809,6 +809,46 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   plan->desc.kchunk = kchunk;
   plan->desc.stages = stages;
 
+  // ---- two-SM variant (conv_igemm2_sm100.cu): a CTA pair per 256-pixel tile, each CTA loads half of the
+  // weight rows.  Re-plans the ring for the smaller stage; everything else (maps, epilogue) is shared.
+  // Automatic for the layers it was built for (measured on B200, SF50 batch 64: every res4/res5 conv with
+  // streamed weights gains 12 - 20 %, s5 `b` reaches 1.39 PFLOP/s): 256-wide column blocks and K >= 512.
+  static const bool no_two_sm_env = getenv("VSB_NO_TWO_SM") != nullptr;
+  const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && block_n == 256 && total_chunks >= 8 &&
+                           p.total_tiles / p.n_tiles >= 16;
+  if (((d->flags & VSB_PLAN_TWO_SM) || two_sm_auto) && kchunk == 64 && !b_resident && block_n % 16 == 0 &&
+      block_n >= 32 && epi_warps == 8 && p.total_tiles / p.n_tiles >= 2) {
+    const uint32_t stage2 = (uint32_t)(kBlockM * 128 + (block_n / 2) * 128);
+    const long long fixed2 = (long long)epi_bufs * epi_buf_bytes + bar_bytes + 1024;
+    int stages2 = (int)((227 * 1024 - fixed2) / stage2);
+    if (d->stages && stages2 > d->stages) stages2 = d->stages;
+    if (stages2 > 12) stages2 = 12;
+    if (stages2 > total_chunks * 2) stages2 = total_chunks * 2;
+    if (stages2 >= 2) {
+      rc = encode_tiled_2d(&plan->map_b, d->wgt, k_total, d->cout, k_total * 2, kchunk, block_n / 2, swz);
+      if (rc != VSB_OK) {
+        delete plan;
+        return rc;
+      }
+      p.stages = stages2;
+      p.stage_bytes = stage2;
+      p.off_bres = (uint32_t)stages2 * stage2;
+      p.off_epi = p.off_bres;
+      p.off_bar = p.off_epi + epi_bufs * epi_buf_bytes;
+      p.idesc = umma_idesc_bf16(256, block_n);
+      plan->smem_bytes = (size_t)stages2 * stage2 + (size_t)fixed2;
+      plan->desc.stages = stages2;
+      const int pm_tiles = (p.total_tiles / p.n_tiles + 1) / 2;
+      long long pairs = sms / 2;
+      if (pairs > (long long)pm_tiles * p.n_tiles) pairs = (long long)pm_tiles * p.n_tiles;
+      pairs -= pairs % p.n_tiles;
+      if (pairs >= p.n_tiles && pairs >= 1) {
+        plan->grid = (unsigned)(2 * pairs);
+        plan->algo = 3;
+      }
+    }
+  }
+
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
@@ -837,6 +877,7 @@ extern "C" int vsb_conv3d_run(const vsb_conv_plan* plan, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (plan->desc.dtype == VSB_F32) return launch_conv_simt(plan->desc, plan->to, plan->ho, plan->wo, s);
   if (plan->algo == 2) return win_plan_launch(plan, s);
+  if (plan->algo == 3) return igemm2_launch(plan, s);
 #define VSB_IG_LAUNCH(KK, DBG)                                                                              \
   do {                                                                                                      \
     if (plan->params.epi_warps == 16)                                                                       \

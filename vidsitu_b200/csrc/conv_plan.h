@@ -86,6 +86,8 @@ CUtensorMapSwizzle swizzle_for(int row_bytes);
 // algorithm's domain (caller falls back to im2col), a negative vsb_status on error
 int win_plan_build(struct ::vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, int wo);
 int win_plan_launch(const struct ::vsb_conv_plan* plan, cudaStream_t stream);
+// two-SM (cta_group::2) variant of the im2col kernel (conv_igemm2_sm100.cu); plan->algo == 3
+int igemm2_launch(const struct ::vsb_conv_plan* plan, cudaStream_t stream);
 
 }  // namespace vsb
 
@@ -93,7 +95,7 @@ struct vsb_conv_plan {
   vsb_conv_desc desc;
   int to, ho, wo;
   long long m_total;
-  int algo;  // 1 = im2col implicit GEMM, 2 = shared-memory window
+  int algo;  // 1 = im2col implicit GEMM, 2 = shared-memory window, 3 = im2col on CTA pairs (cta_group::2)
   // bf16 tensor-core path
   CUtensorMap map_a, map_b, map_out, map_res;
   CUtensorMap map_a2;  // im2col algorithm: second source (fused shortcut projection)
