@@ -313,6 +313,8 @@ TWO_SM_CASES = [
     ("sm2_pw_s2_320_512", 2, 2, 28, 28, 320, 512, (1, 1, 1), (1, 2, 2), (0, 0, 0), False, False, dict(flags=16)),
     ("sm2_sp3_s2_128", 2, 2, 28, 28, 128, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), False, True, dict(flags=16)),
     ("sm2_sp3_256_many_tiles", 8, 8, 14, 14, 256, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, dict(flags=16)),  # 98 m-tiles
+    ("sm2_sp3_32_256_k32", 2, 4, 28, 28, 32, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, dict(flags=16)),      # 64-byte rows
+    ("sm2_pw_96_128_k32", 2, 4, 14, 14, 96, 128, (1, 1, 1), (1, 1, 1), (0, 0, 0), True, True, dict(flags=16)),
     ("sm2_sp3_256_bn128", 4, 4, 14, 14, 256, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, dict(flags=16, block_n=128)),
 ]
 

@@ -100,7 +100,8 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
 }
 }  // namespace
 
-// kchunk = 64 only (128-byte swizzled rows, 4 MMAs of K = 16 per chunk, one chunk per ring stage).
+// KK = kchunk / 16: 64- or 128-byte swizzled rows, KK MMAs of K = 16 per chunk, one chunk per ring stage.
+template <int KK>
 __global__ void __launch_bounds__((kEW + 2) * 32, 1)
 conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
@@ -108,7 +109,8 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kProducerWarp = kEW, kMmaWarp = kEW + 1;
-  constexpr uint32_t row_bytes = 128;
+  constexpr uint32_t row_bytes = KK * 32;
+  constexpr int kchunk = KK * 16;
   constexpr uint32_t a_chunk_bytes = kBlockM * row_bytes;
   const uint32_t half_n = p.block_n >> 1;
   const uint32_t b_chunk_bytes = half_n * row_bytes;  // this CTA's half of the weight rows
@@ -198,13 +200,13 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (left1 > 0) {
             tma2_load_im2col_5d(a_dst, &map_a, full_leader, cc, w0, h0, d0, n0, (uint16_t)kw_, (uint16_t)kh_,
                                 (uint16_t)kt_);
-            if (--left1 == 0) cc = -64;
+            if (--left1 == 0) cc = -kchunk;
           } else {
             tma2_load_im2col_5d(a_dst, &map_a2, full_leader, cc, w2, h2, d2, n0, 0, 0, 0);
           }
           tma2_load_2d(b_dst, &map_b, full_leader, kcoord, ncol);
-          kcoord += 64;
-          cc += 64;
+          kcoord += kchunk;
+          cc += kchunk;
           if (cc == cin && left1 > 0) {
             cc = 0;
             if (++kw_ == fkw) {
@@ -243,7 +245,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < KK; ++k) {
               const uint64_t adesc = desc_hi | (uint64_t)(desc_lo_flags | (a_slot_lo + 2 * k));
               const uint64_t bdesc = desc_hi | (uint64_t)(desc_lo_flags | (a_slot_lo + b_off_lo + 2 * k));
               umma2_bf16(tmem_d, adesc, bdesc, idesc, (g | k) != 0 ? 1u : 0u);
@@ -372,7 +374,9 @@ int igemm2_launch(const vsb_conv_plan* plan, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_igemm2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_igemm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) {
     set_error("cudaFuncSetAttribute(conv_igemm2_kernel) failed: %s", cudaGetErrorString(attr_err));
@@ -390,8 +394,11 @@ int igemm2_launch(const vsb_conv_plan* plan, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm2_kernel, plan->map_a, plan->map_b, plan->map_out, plan->map_res,
-                                     plan->map_a2, plan->params);
+  cudaError_t e = plan->params.kchunk == 64
+                      ? cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<4>, plan->map_a, plan->map_b, plan->map_out,
+                                           plan->map_res, plan->map_a2, plan->params)
+                      : cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<2>, plan->map_a, plan->map_b, plan->map_out,
+                                           plan->map_res, plan->map_a2, plan->params);
   if (e != cudaSuccess) {
     set_error("launch of conv_igemm2_kernel failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

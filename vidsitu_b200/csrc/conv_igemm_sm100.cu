@@ -814,11 +814,12 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   // Automatic for the layers it was built for (measured on B200, SF50 batch 64: every res4/res5 conv with
   // streamed weights gains 12 - 20 %, s5 `b` reaches 1.39 PFLOP/s): 256-wide column blocks and K >= 512.
   static const bool no_two_sm_env = getenv("VSB_NO_TWO_SM") != nullptr;
-  const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && block_n == 256 && total_chunks >= 8 &&
-                           p.total_tiles / p.n_tiles >= 16;
-  if (((d->flags & VSB_PLAN_TWO_SM) || two_sm_auto) && kchunk == 64 && !b_resident && block_n % 16 == 0 &&
-      block_n >= 32 && epi_warps == 8 && p.total_tiles / p.n_tiles >= 2) {
-    const uint32_t stage2 = (uint32_t)(kBlockM * 128 + (block_n / 2) * 128);
+  // (64-byte rows, i.e. the pixel-grouped slow stem: measured slower in pairs, 0.46 vs 0.42 ms - opt-in only)
+  const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && block_n == 256 && kchunk == 64 &&
+                           total_chunks >= 8 && p.total_tiles / p.n_tiles >= 16;
+  if (((d->flags & VSB_PLAN_TWO_SM) || two_sm_auto) && (kchunk == 64 || kchunk == 32) && !b_resident &&
+      block_n % 16 == 0 && block_n >= 32 && epi_warps == 8 && p.total_tiles / p.n_tiles >= 2) {
+    const uint32_t stage2 = (uint32_t)((kBlockM + block_n / 2) * kchunk * 2);
     const long long fixed2 = (long long)epi_bufs * epi_buf_bytes + bar_bytes + 1024;
     int stages2 = (int)((227 * 1024 - fixed2) / stage2);
     if (d->stages && stages2 > d->stages) stages2 = d->stages;

@@ -362,7 +362,7 @@ class ClipEngine:
         y.c = cs.cout
         scale, bias = self._affine(cs, cs.cout)
         wt = self._tensor(cs.key + ".weight")
-        tune = {k: v for k, v in self._tune(cs.key).items() if k in ("block_n", "kchunk", "stages")}
+        tune = {k: v for k, v in self._tune(cs.key).items() if k in _PLAN_KNOBS}
         plan = None
         algo = self._tune(cs.key).get("algo", "auto")
         if self.dtype == VSB_BF16 and (algo == "window" or (algo == "auto" and cs.kernel[0] > 1)):
