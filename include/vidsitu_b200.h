@@ -125,6 +125,9 @@ typedef struct vsb_conv_desc {
   int epi_bufs;
   /* plan variants, OR of VSB_PLAN_* (0 = automatic); like the tuning above they never change results */
   int flags;
+  /* bf16 path, im2col algorithm, no residual: write the 16-bit outputs as IEEE half instead of bf16
+   * (attention scores of the non-local block: 3 more mantissa bits in front of the softmax).        */
+  int out_f16;
 } vsb_conv_desc;
 
 #define VSB_PLAN_STREAM_WEIGHTS 1 /* im2col: never keep the weight block resident in shared memory      */
@@ -176,6 +179,17 @@ int vsb_linear(const float* x, int n, int din, const float* w, const float* b, f
 int vsb_nonlocal_attention(const void* theta, int theta_pitch, const void* phi, int phi_pitch, const void* g,
                            int g_pitch, void* out, int out_pitch, int n, int tq, int tk, int c, int softmax,
                            int dtype, void* stream);
+
+/* Tensor-core route of the same block (bf16): the caller runs the two einsums as per-clip 1x1x1 convs
+ * (vsb_conv3d_*: scores_i = theta_i . phi_i^T with phi_i as the [tk, c] weight matrix and the softmax
+ * scale in `scale`; out_i = P_i . g_i with g_i^T as the [c, tk] weight matrix) and these two kernels in
+ * between.  vsb_score_rows: in place on bf16 scores [rows, pitch]: columns [0, valid) <- softmax over them
+ * (softmax != 0; nonlocal_helper.py:128-131) or unchanged (dot_product, already divided by tk), columns
+ * [valid, width) <- 0 (the zero K padding of the second product).  vsb_transpose_pad: bf16
+ * out[i][ch][k] = in[i][k][ch] for k < rows, 0 for rows <= k < out_pitch.                              */
+int vsb_score_rows(void* scores, long long rows, int valid, int width, int pitch, int softmax, void* stream);
+int vsb_transpose_pad(const void* in, int in_pitch, void* out, int n, int rows, int cols, int out_pitch,
+                      void* stream);
 
 /* ------------------------------------------------------- verb softmax + top-k
  * Replaces F.softmax(mdl_out, -1) + sort(descending=True)[:topk_save] of

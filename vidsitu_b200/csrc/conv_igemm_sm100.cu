@@ -357,6 +357,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (has_res)
             epi_convert_chunk<true>(taddr, epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane, sb_s + col0 * 8,
                                     relu_floor);
+          else if (p.out_f16)
+            epi_convert_chunk<false, true>(taddr, epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane,
+                                           sb_s + col0 * 8, relu_floor);
           else
             epi_convert_chunk<false>(taddr, epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane, sb_s + col0 * 8,
                                      relu_floor);
@@ -549,6 +552,11 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
     return VSB_OK;
   }
   VSB_CHECK_ARG(d->algo >= 0 && d->algo <= 2, "algo must be 0 (auto), 1 (im2col) or 2 (window)");
+  if (d->out_f16 && (d->algo == 2 || d->residual || d->in2)) {
+    set_error("out_f16 needs the im2col algorithm without residual / second source");
+    delete plan;
+    return VSB_ERR_INVALID;
+  }
   if (d->algo == 2) {
     const int wrc = win_plan_build(plan, d, to, ho, wo);
     if (wrc == VSB_OK) {
@@ -598,6 +606,15 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   if (!block_n) {
     block_n = 256;
     while (block_n > 16 && d->cout % block_n) block_n >>= 1;
+    if (block_n < 64 && d->cout > 64) {
+      // no power-of-two column block (e.g. the 784 keys of a res3 non-local block as output channels):
+      // the widest multiple of 16 that divides cout (784 -> 112, 208 -> 208)
+      for (int bn = 256; bn > block_n; bn -= 16)
+        if (d->cout % bn == 0) {
+          block_n = bn;
+          break;
+        }
+    }
   }
   if (block_n < 16 || block_n > 256 || block_n % 16 || d->cout % block_n) FAIL(VSB_ERR_INVALID, "bad block_n %d for cout %d", block_n, d->cout);
   const int taps = d->kt * d->kh * d->kw;
@@ -648,6 +665,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
     sp.epi_n = bn >= 64 ? 64 : bn;
     if (bn >= 64 && ((!d->residual && num_kstages >= 8) || epi_warps == 16)) sp.epi_n = 32;
     if (bn >= 64 && epi_n_env) sp.epi_n = epi_n_env;
+    while (sp.epi_n > 16 && bn % sp.epi_n) sp.epi_n >>= 1;  // column blocks like 112 or 208: 16-column chunks
     if (bn % sp.epi_n) return sp;
     const int epi_buf_bytes = epi_warps * 32 * sp.epi_n * 2;  // one 32-row slab per epilogue warp
     sp.epi_bufs = d->residual ? 3 : 2;  // slabs per epilogue warp (residual prefetch distance = epi_bufs - 1)
@@ -784,6 +802,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   p.scale = d->scale; p.bias = d->bias;
   p.has_residual = d->residual != nullptr;
   p.relu = d->relu;
+  p.out_f16 = d->out_f16 ? 1 : 0;
   p.dbg = nullptr;
   if (getenv("VSB_WIN_DEBUG")) {  // debug only: the one place the library allocates device memory
     if (cudaMalloc(&p.dbg, 16 * sizeof(long long)) == cudaSuccess) (void)cudaMemset(p.dbg, 0, 16 * sizeof(long long));
@@ -815,9 +834,9 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   // streamed weights gains 12 - 20 %, s5 `b` reaches 1.39 PFLOP/s): 256-wide column blocks and K >= 512.
   static const bool no_two_sm_env = getenv("VSB_NO_TWO_SM") != nullptr;
   // (64-byte rows, i.e. the pixel-grouped slow stem: measured slower in pairs, 0.46 vs 0.42 ms - opt-in only)
-  const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && block_n == 256 && kchunk == 64 &&
+  const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && !d->out_f16 && block_n == 256 && kchunk == 64 &&
                            total_chunks >= 8 && p.total_tiles / p.n_tiles >= 16;
-  if (((d->flags & VSB_PLAN_TWO_SM) || two_sm_auto) && (kchunk == 64 || kchunk == 32) && !b_resident &&
+  if (((d->flags & VSB_PLAN_TWO_SM) || two_sm_auto) && !d->out_f16 && (kchunk == 64 || kchunk == 32) && !b_resident &&
       block_n % 16 == 0 && block_n >= 32 && epi_warps == 8 && p.total_tiles / p.n_tiles >= 2) {
     const uint32_t stage2 = (uint32_t)((kBlockM + block_n / 2) * kchunk * 2);
     const long long fixed2 = (long long)epi_bufs * epi_buf_bytes + bar_bytes + 1024;

@@ -26,6 +26,7 @@ struct IgemmParams {
   const float* bias;
   int has_residual;
   int relu;
+  int out_f16;     // 16-bit outputs are IEEE half instead of bf16 (vsb_conv_desc.out_f16)
   long long* dbg;  // role timeline counters (VSB_WIN_DEBUG), else null
 };
 

@@ -2,6 +2,8 @@
 // frozen-BatchNorm scale/bias (+ residual) (+ ReLU) in fp32 -> one bf16 rounding -> swizzled
 // shared-memory slab that a TMA store ships out.  Also a division-free tile cursor.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "ptx.cuh"
 
 namespace vsb {
@@ -38,7 +40,13 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 // One thread's 16 accumulator columns -> its 32 bytes of the staging row (two swizzled 16-byte
 // chunks).  buf_s / sb_s are SHARED-space addresses: the slab, and the (scale, bias) float2 pairs of
 // these 16 columns (constant for the kernel: plain asm so the loads can be hoisted); relu_floor = 0 or -inf.
-template <bool kRes>
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// kF16: the 16-bit output is IEEE half instead of bf16 (attention scores: 3 more mantissa bits before the softmax)
+template <bool kRes, bool kF16 = false>
 __device__ __forceinline__ void epi_convert16(const uint32_t* v, uint32_t sb_s, uint32_t buf_s, uint32_t off0,
                                               uint32_t swz_mask, float relu_floor) {
   const uint32_t a0 = buf_s + (off0 ^ (((off0 >> 7) & swz_mask) << 4));
@@ -62,7 +70,7 @@ __device__ __forceinline__ void epi_convert16(const uint32_t* v, uint32_t sb_s, 
     }
     x0 = fmaxf(x0, relu_floor);
     x1 = fmaxf(x1, relu_floor);
-    o[qq] = pack_bf16x2(x0, x1);
+    o[qq] = kF16 ? pack_f16x2(x0, x1) : pack_bf16x2(x0, x1);
   }
   sts128(a0, o[0], o[1], o[2], o[3]);
   sts128(a1, o[4], o[5], o[6], o[7]);
@@ -71,7 +79,7 @@ __device__ __forceinline__ void epi_convert16(const uint32_t* v, uint32_t sb_s, 
 // One warp converts its 32 rows x ncols (16 / 32 / 64) accumulator block into the slab at shared
 // address buf_s (rows of row_bytes = ncols * 2).  taddr = TMEM address of (lane quarter, first column);
 // sb_s = shared address of the (scale, bias) pair of the chunk's first column.
-template <bool kRes>
+template <bool kRes, bool kF16 = false>
 __device__ __forceinline__ void epi_convert_chunk(uint32_t taddr, int ncols, uint32_t buf_s, uint32_t row_bytes,
                                                   uint32_t swz_mask, int lane, uint32_t sb_s, float relu_floor) {
   if (ncols >= 32) {
@@ -80,14 +88,14 @@ __device__ __forceinline__ void epi_convert_chunk(uint32_t taddr, int ncols, uin
       tmem_ld32(taddr + j0, v);
       tmem_ld_wait();
       const uint32_t off0 = lane * row_bytes + j0 * 2;
-      epi_convert16<kRes>(v, sb_s + j0 * 8, buf_s, off0, swz_mask, relu_floor);
-      epi_convert16<kRes>(v + 16, sb_s + (j0 + 16) * 8, buf_s, off0 + 32, swz_mask, relu_floor);
+      epi_convert16<kRes, kF16>(v, sb_s + j0 * 8, buf_s, off0, swz_mask, relu_floor);
+      epi_convert16<kRes, kF16>(v + 16, sb_s + (j0 + 16) * 8, buf_s, off0 + 32, swz_mask, relu_floor);
     }
   } else {
     uint32_t v[16];
     tmem_ld16(taddr, v);
     tmem_ld_wait();
-    epi_convert16<kRes>(v, sb_s, buf_s, lane * row_bytes, swz_mask, relu_floor);
+    epi_convert16<kRes, kF16>(v, sb_s, buf_s, lane * row_bytes, swz_mask, relu_floor);
   }
 }
 

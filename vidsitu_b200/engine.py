@@ -458,6 +458,11 @@ class ClipEngine:
         else:
             xp = x
         phi = self._alloc(n, xp.t, xp.h, xp.w, nl.dim_inner)
+        if self.dtype == VSB_BF16:
+            # the tensor-core route reads phi_i as a weight matrix of round_up(keys, 16) rows: slack after the last clip
+            self._free(phi)
+            phi = Act(self._pool.take(phi.pixels * phi.pitch + 16 * phi.pitch), n, xp.t, xp.h, xp.w, phi.c, phi.pitch, 0,
+                      phi.c_real)
         g = self._alloc(n, xp.t, xp.h, xp.w, nl.dim_inner)
         self._conv(nl.phi, xp, phi)
         self._conv(nl.g, xp, g)
@@ -465,15 +470,71 @@ class ClipEngine:
             self._free(xp)
         att = self._alloc(n, x.t, x.h, x.w, nl.dim_inner)
         tq, tk = x.t * x.h * x.w, xp.t * xp.h * xp.w
-        self.trunk_ops.append((nl.prefix + ".attention",
-                               lambda: ops.nonlocal_attention(theta, phi, g, att, nl.softmax, self.dtype),
-                               4.0 * n * tq * tk * nl.dim_inner))
+        if not self._nonlocal_gemms(nl, theta, phi, g, att, tq, tk):
+            self.trunk_ops.append((nl.prefix + ".attention",
+                                   lambda: ops.nonlocal_attention(theta, phi, g, att, nl.softmax, self.dtype),
+                                   4.0 * n * tq * tk * nl.dim_inner))
         y = self._alloc(n, x.t, x.h, x.w, nl.dim, pitch=out_pitch)
         # x + BN(conv_out(.)), no ReLU   nonlocal_helper.py:145-148
         self._conv(nl.out, att, y, residual=x, relu=False)
         for a in (theta, phi, g, att, x):
             self._free(a)
         return y
+
+    def _nonlocal_gemms(self, nl: NonlocalSpec, theta: Act, phi: Act, g: Act, att: Act, tq: int, tk: int) -> bool:
+        """The two einsums of Nonlocal.forward (nonlocal_helper.py:123-141) on the tensor cores: per clip,
+        scores_i = theta_i . phi_i^T is a 1x1x1 conv of theta_i whose WEIGHTS are phi_i ([keys, c], the softmax
+        scale c^-1/2 - or 1/keys - in the epilogue), vsb_score_rows normalises the rows and zeroes the K padding,
+        and out_i = P_i . g_i is a 1x1x1 conv of P_i whose weights are g_i^T ([c, keys], vsb_transpose_pad).
+        Returns False when the block is outside this route (fp32 mode, odd shapes): the CUDA-core kernel runs."""
+        if self.dtype != VSB_BF16 or self._tune(nl.prefix).get("nl_gemm", True) is False:
+            return False
+        c = theta.c
+        dense = all(a.pitch == a.c and a.c_off == 0 for a in (theta, phi, g, att))
+        if not dense or c % 64 or phi.c != c or g.c != c or att.c != c or tk % 2:
+            return False
+        n = theta.n
+        kc, kp = round_up(tk, 16), round_up(tk, 64)
+        scores = self._pool.take(n * tq * kp)
+        g_t = self._pool.take(n * c * kp)
+        dev = self.device
+        s_scale = torch.full((kc,), float(c) ** -0.5 if nl.softmax else 1.0 / tk, dtype=torch.float32, device=dev)
+        s_bias = torch.zeros(kc, dtype=torch.float32, device=dev)
+        y_scale = torch.ones(c, dtype=torch.float32, device=dev)
+        y_bias = torch.zeros(c, dtype=torch.float32, device=dev)
+        t, h, w = theta.t, theta.h, theta.w
+        plans_s, plans_y = [], []
+        for i in range(n):
+            th_i = Act(theta.buf[i * tq * c:(i + 1) * tq * c], 1, t, h, w, c, c)
+            sc_out = Act(scores[i * tq * kp:(i + 1) * tq * kp], 1, t, h, w, kc, kp)
+            w_phi = phi.buf[i * tk * c:i * tk * c + kc * c]
+            plans_s.append(ConvPlan(self.dtype, th_i, w_phi, kc, (1, 1, 1), (1, 1, 1), (0, 0, 0), None, s_scale, s_bias,
+                                    sc_out, None, False, out_f16=True))   # half scores: 11 mantissa bits into exp()
+            sc_in = Act(scores[i * tq * kp:(i + 1) * tq * kp], 1, t, h, w, kp, kp)
+            out_i = Act(att.buf[i * tq * c:(i + 1) * tq * c], 1, t, h, w, c, c)
+            plans_y.append(ConvPlan(self.dtype, sc_in, g_t[i * c * kp:(i + 1) * c * kp], c, (1, 1, 1), (1, 1, 1),
+                                    (0, 0, 0), None, y_scale, y_bias, out_i, None, False))
+        self._keep += plans_s + plans_y + [s_scale, s_bias, y_scale, y_bias, scores, g_t]
+
+        def run_scores():
+            for p in plans_s:
+                p.run()
+
+        def run_out():
+            for p in plans_y:
+                p.run()
+
+        fl = 2.0 * n * tq * tk * c
+        self.trunk_ops.append((nl.prefix + ".g_transpose", lambda: ops.transpose_pad(g, g_t, kp), 0.0))
+        self.trunk_ops.append((nl.prefix + ".scores", run_scores, fl))
+        self.trunk_ops.append((nl.prefix + ".softmax",
+                               lambda: ops.score_rows(scores, n * tq, tk, kp, kp, nl.softmax), 0.0))
+        self.trunk_ops.append((nl.prefix + ".attention_out", run_out, fl))
+        self._pool.give(scores)
+        self._pool.give(g_t)
+        self.op_bytes[nl.prefix + ".scores"] = 2.0 * n * (tq * c + tk * c + tq * kc)
+        self.op_bytes[nl.prefix + ".attention_out"] = 2.0 * n * (tq * kp + tk * c + tq * c)
+        return True
 
     def _stage(self, x: Act, blocks: List[BlockSpec], out_pitch: Optional[int]) -> Act:
         for i, blk in enumerate(blocks):
@@ -679,7 +740,8 @@ class ClipEngine:
     @property
     def conv_flops(self) -> float:
         """Algorithmic conv FLOPs (2*MAC on the reference's un-padded shapes) of one run."""
-        return sum(f for name, _, f in self.trunk_ops if not name.endswith(".attention"))
+        return sum(f for name, _, f in self.trunk_ops
+                   if not name.endswith((".attention", ".scores", ".attention_out")))
 
     def features_ncthw(self) -> List[torch.Tensor]:
         return [ops.act_to_ncthw(x, self.dtype) for x in self.trunk_out]

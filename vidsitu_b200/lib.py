@@ -47,7 +47,7 @@ class ConvDesc(C.Structure):
         ("in2", C.c_void_p),
         ("t2", C.c_int), ("h2", C.c_int), ("w2", C.c_int), ("cin2", C.c_int), ("in2_pitch", C.c_int),
         ("st2", C.c_int), ("sh2", C.c_int), ("sw2", C.c_int),
-        ("epi_n", C.c_int), ("epi_bufs", C.c_int), ("flags", C.c_int),
+        ("epi_n", C.c_int), ("epi_bufs", C.c_int), ("flags", C.c_int), ("out_f16", C.c_int),
     ]
 
 
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
     lib.vsb_linear.argtypes = [f32p, i, i, f32p, f32p, f32p, i, i, vp]
     lib.vsb_softmax_topk.argtypes = [f32p, i, i, i, i, vp, f32p, vp]
     lib.vsb_nonlocal_attention.argtypes = [vp, i, vp, i, vp, i, vp, i, i, i, i, i, i, i, vp]
+    lib.vsb_score_rows.argtypes = [vp, ll, i, i, i, i, vp]
+    lib.vsb_transpose_pad.argtypes = [vp, i, vp, i, i, i, i, vp]
     lib.vsb_nthwc_to_ncthw_f32.argtypes = [vp, i, i, i, i, f32p, i, vp]
     lib.vsb_ncthw_f32_to_nthwc.argtypes = [f32p, i, i, ll, i, vp, i, i, i, i, vp]
     lib.vsb_debug_im2col_probe.argtypes = [vp] + [i] * 25 + [vp, vp]
@@ -95,6 +97,7 @@ def load() -> C.CDLL:
     lib.vsb_debug_conv_plan_info.argtypes = [vp, C.POINTER(C.c_longlong)]
     for name in ("vsb_pack_frames", "vsb_conv3d_plan_create", "vsb_conv3d_run", "vsb_conv3d_plan_out_shape",
                  "vsb_maxpool3d", "vsb_global_avgpool", "vsb_linear", "vsb_softmax_topk", "vsb_nonlocal_attention",
+                 "vsb_score_rows", "vsb_transpose_pad",
                  "vsb_nthwc_to_ncthw_f32", "vsb_ncthw_f32_to_nthwc", "vsb_debug_im2col_probe",
                  "vsb_debug_umma_semantics", "vsb_debug_umma_rate", "vsb_debug_conv_stats", "vsb_debug_conv_plan_info"):
         getattr(lib, name).restype = i

@@ -67,7 +67,7 @@ class ConvPlan:
                  scale: torch.Tensor, bias: torch.Tensor, out: Act, residual: Optional[Act] = None,
                  relu: bool = False, block_n: int = 0, kchunk: int = 0, stages: int = 0, algo: int = 0,
                  kw_ranges: Optional[Sequence[Sequence[int]]] = None, x2: Optional[Act] = None,
-                 stride2: Sequence[int] = (1, 1, 1), epi_n: int = 0, epi_bufs: int = 0, flags: int = 0):
+                 stride2: Sequence[int] = (1, 1, 1), epi_n: int = 0, epi_bufs: int = 0, flags: int = 0, out_f16: bool = False):
         _require_cuda(x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None,
                       x2.buf if x2 is not None else None)
         pad_hi = pad_lo if pad_hi is None else pad_hi
@@ -91,6 +91,7 @@ class ConvPlan:
         d.block_n, d.kchunk, d.stages = block_n, kchunk, stages
         d.algo = algo
         d.epi_n, d.epi_bufs, d.flags = epi_n, epi_bufs, flags
+        d.out_f16 = int(out_f16)
         k_per_tap_row = x.c * d.kw
         if kw_ranges is not None:
             if len(kw_ranges) != d.kw or d.kw > 8:
@@ -238,3 +239,18 @@ def act_to_ncthw(x: Act, dtype: int) -> torch.Tensor:
     check(_l.load().vsb_nthwc_to_ncthw_f32(x.ptr, x.n, x.t * x.h * x.w, x.c_real, x.pitch, out.data_ptr(), dtype,
                                            _stream_ptr()), "vsb_nthwc_to_ncthw_f32")
     return out
+
+
+def score_rows(scores: torch.Tensor, rows: int, valid: int, width: int, pitch: int, softmax: bool) -> None:
+    """In place on bf16 scores [rows, pitch]: softmax over columns [0, valid) (or unchanged), zeros in [valid, width)."""
+    _require_cuda(scores)
+    check(_l.load().vsb_score_rows(scores.data_ptr(), rows, valid, width, pitch, int(softmax), _stream_ptr()),
+          "vsb_score_rows")
+
+
+def transpose_pad(src: Act, out: torch.Tensor, out_pitch: int) -> None:
+    """bf16 [n, keys, c] (pitch) -> out [n, c, out_pitch], zero-padded along keys."""
+    _require_cuda(src.buf, out)
+    keys = src.t * src.h * src.w
+    check(_l.load().vsb_transpose_pad(src.ptr, src.pitch, out.data_ptr(), src.n, keys, src.c, out_pitch,
+                                      _stream_ptr()), "vsb_transpose_pad")
