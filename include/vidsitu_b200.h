@@ -128,6 +128,11 @@ typedef struct vsb_conv_desc {
   /* bf16 path, im2col algorithm, no residual: write the 16-bit outputs as IEEE half instead of bf16
    * (attention scores of the non-local block: 3 more mantissa bits in front of the softmax).        */
   int out_f16;
+  /* Per-clip weights (bf16, im2col algorithm, 1x1x1 stride-1 convs without residual): > 0 makes clip i use
+   * the [cout][cin] weight matrix that starts wgt_clip_rows rows after clip i-1's, i.e. a batched product
+   * out_i = in_i . W_i^T - the two einsums of the non-local block with phi_i / g_i^T as W_i
+   * (nonlocal_helper.py:123-141).  `wgt` must hold (n-1) * wgt_clip_rows + cout rows.  0 = one matrix.   */
+  int wgt_clip_rows;
 } vsb_conv_desc;
 
 #define VSB_PLAN_STREAM_WEIGHTS 1 /* im2col: never keep the weight block resident in shared memory      */

@@ -125,6 +125,30 @@ def test_conv_two_sm_pairs(case):
     assert info["ok"], info
 
 
+@pytest.mark.parametrize("n,t,h,w,cin,rows,cout,f16", [(3, 2, 10, 10, 128, 200, 208, True), (2, 4, 14, 14, 256, 112, 112, False),
+                                                     (5, 1, 7, 7, 64, 64, 64, False)])
+def test_conv_per_clip_weights(n, t, h, w, cin, rows, cout, f16):
+    """vsb_conv_desc.wgt_clip_rows (+ out_f16): out_i = in_i . W_i^T with clip i's matrix `rows` rows after clip
+    i-1's (cout > rows: the extra rows are the next clip's, as in the non-local score product)."""
+    from vidsitu_b200.lib import VSB_BF16
+    from vidsitu_b200.ops import Act, ConvPlan
+    g = torch.Generator().manual_seed(n * 1000 + cout)
+    x = torch.randn((n, t, h, w, cin), generator=g).bfloat16().cuda()
+    wall = (torch.randn(((n - 1) * rows + cout, cin), generator=g) / cin ** 0.5).bfloat16().cuda()
+    out = torch.zeros((n, t, h, w, cout), dtype=torch.bfloat16, device="cuda")
+    scale = torch.full((cout,), 0.5, device="cuda")
+    bias = torch.zeros(cout, device="cuda")
+    plan = ConvPlan(VSB_BF16, Act(x, n, t, h, w, cin, cin), wall, cout, (1, 1, 1), (1, 1, 1), (0, 0, 0), None, scale, bias,
+                    Act(out, n, t, h, w, cout, cout), None, False, out_f16=f16, wgt_clip_rows=rows)
+    plan.run()
+    torch.cuda.synchronize()
+    got = (out.view(torch.float16) if f16 else out).float()
+    for i in range(n):
+        ref = 0.5 * x[i].float().reshape(-1, cin) @ wall[i * rows:i * rows + cout].float().t()
+        err = (got[i].reshape(-1, cout) - ref).abs().max().item()
+        assert err <= (4e-3 if f16 else 2e-2) * max(1.0, ref.abs().max().item()), (i, err)
+
+
 def _dual_cases():
     import gpu_check_ops as G
     return G.DUAL_CASES

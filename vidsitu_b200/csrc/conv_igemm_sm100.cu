@@ -145,8 +145,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int chunks1 = p.chunks1, sw2 = p.sw2, sh2 = p.sh2, st2 = p.st2;
       int slot = 0;
       uint32_t parity = 1;  // first pass over the ring: slots are free
+      const int clip_tiles = p.clip_tiles, clip_rows = p.clip_rows, wgt_clip_rows = p.wgt_clip_rows;
       for (int mt = m_tile0; mt < m_tiles; mt += m_tile_step) {
-        const int m0 = mt * kBlockM;
+        int m0 = mt * kBlockM, wrow0 = 0;
+        if (clip_rows) {  // per-clip weights: tile lt of clip cb (its last tile runs into the next clip: never stored)
+          const int cb = mt / clip_tiles;
+          m0 = cb * clip_rows + (mt - cb * clip_tiles) * kBlockM;
+          wrow0 = cb * wgt_clip_rows;
+        }
         const int wo = m0 % owo;
         const int r1 = m0 / owo;
         const int ho = r1 % oho;
@@ -156,7 +162,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int w0 = wo * sw + lw;
         const int h0 = ho * sh + lh;
         const int d0 = to_ * st + lt;
-        const int ncol = n_tile * block_n;
+        const int ncol = n_tile * block_n + wrow0;
         int cc = 0, kw_ = 0, kh_ = 0, kt_ = 0, kcoord = 0;
         int left = total_chunks;
         int left1 = chunks1;  // chunks still to come from the primary source
@@ -368,7 +374,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         __syncwarp();
         if (kDbg) dbg_acc[6] += (uint32_t)(clock64() - math_t0);
         if (lane == 0) {
-          tma_store_2d(&map_out, buf, nbase + col0, m0 + row_in_tile);  // rows >= m_total are clipped by the TMA unit
+          if (p.clip_rows) {  // 3-D map [cout, rows of a clip, clips]: rows past the clip's end are clipped
+            const int cb = mt / p.clip_tiles;
+            tma_store_3d(&map_out, buf, nbase + col0, (mt - cb * p.clip_tiles) * kBlockM + row_in_tile, cb);
+          } else {
+            tma_store_2d(&map_out, buf, nbase + col0, m0 + row_in_tile);  // rows >= m_total are clipped by the TMA unit
+          }
           tma_store_commit();
           // arm the slab of this warp's chunk q + nb - 1 (the one chunk q - 1 used): its store must have read it
           if (pf_mt < m_tiles) {
@@ -552,6 +563,12 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
     return VSB_OK;
   }
   VSB_CHECK_ARG(d->algo >= 0 && d->algo <= 2, "algo must be 0 (auto), 1 (im2col) or 2 (window)");
+  if (d->wgt_clip_rows < 0 || (d->wgt_clip_rows > 0 && (d->algo == 2 || d->residual || d->in2 || d->kt * d->kh * d->kw != 1 ||
+                                                        d->st * d->sh * d->sw != 1))) {
+    set_error("per-clip weights need a 1x1x1 stride-1 conv on the im2col algorithm without residual / second source");
+    delete plan;
+    return VSB_ERR_INVALID;
+  }
   if (d->out_f16 && (d->algo == 2 || d->residual || d->in2)) {
     set_error("out_f16 needs the im2col algorithm without residual / second source");
     delete plan;
@@ -639,7 +656,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   const int num_kstages = ceil_div(total_chunks, cps);
   const int bar_bytes = 1024 + 2048;  // barriers + the CTA's (scale, bias) table (block_n <= 256 float2)
   static const bool no_bres_env = getenv("VSB_NO_BRES") != nullptr;
-  const bool no_bres = no_bres_env || (d->flags & (VSB_PLAN_STREAM_WEIGHTS | VSB_PLAN_TWO_SM));
+  const bool no_bres = no_bres_env || (d->flags & (VSB_PLAN_STREAM_WEIGHTS | VSB_PLAN_TWO_SM)) || d->wgt_clip_rows > 0;
   static const char* ew_env = getenv("VSB_EPI_WARPS");
   // (measured on B200: the 16-warp epilogue shape does not beat 8 warps -- these layers are HBM-bound, the
   // accumulator wait is back-pressure -- so it is opt-in: VSB_EPI_WARPS=16)
@@ -758,13 +775,30 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
     }
   }
   const long long k_total = (long long)taps * d->cin + (long long)cin2_chunks * kchunk;
-  rc = encode_tiled_2d(&plan->map_b, d->wgt, k_total, d->cout, k_total * 2, kchunk, block_n, swz);
+  const int clip_rows = d->wgt_clip_rows > 0 ? to * ho * wo : 0;
+  // per-clip weights: clip i's [cout, K] matrix starts wgt_clip_rows rows after clip i-1's (they may overlap
+  // when cout was rounded up: the extra rows are the next clip's, their products are discarded by the caller)
+  const long long wgt_rows = clip_rows ? (long long)(d->n - 1) * d->wgt_clip_rows + d->cout : d->cout;
+  rc = encode_tiled_2d(&plan->map_b, d->wgt, k_total, wgt_rows, k_total * 2, kchunk, block_n, swz);
   if (rc != VSB_OK) {
     delete plan;
     return rc;
   }
   // output / residual tiles move through TMA too: [m_total rows, cout cols], row pitch in bytes
   const CUtensorMapSwizzle epi_swz = swizzle_for(epi_n * 2);
+  if (clip_rows) {
+    cuuint64_t dims[3] = {(cuuint64_t)d->cout, (cuuint64_t)clip_rows, (cuuint64_t)d->n};
+    cuuint64_t strides[2] = {(cuuint64_t)d->out_pitch * 2, (cuuint64_t)clip_rows * d->out_pitch * 2};
+    cuuint32_t box[3] = {(cuuint32_t)epi_n, 32, 1}, estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(&plan->map_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, d->out, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, epi_swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    rc = VSB_OK;
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(per-clip output) failed (CUresult %d)", (int)r);
+      rc = VSB_ERR_CUDA;
+    }
+  } else
   rc = encode_tiled_2d(&plan->map_out, d->out, d->cout, m_total, (long long)d->out_pitch * 2, epi_n, 32, epi_swz);
   if (rc != VSB_OK) {
     delete plan;
@@ -795,7 +829,10 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   p.epi_bufs = epi_bufs; p.b_resident = b_resident ? 1 : 0;
   p.epi_warps = epi_warps;
   p.stage_bytes = stage_bytes; p.off_bres = off_bres; p.off_epi = off_epi; p.off_bar = off_bar;
-  p.total_tiles = (int)(ceil_div_ll(m_total, kBlockM) * p.n_tiles);
+  p.clip_rows = clip_rows;
+  p.clip_tiles = clip_rows ? ceil_div(clip_rows, kBlockM) : 0;
+  p.wgt_clip_rows = d->wgt_clip_rows;
+  p.total_tiles = clip_rows ? d->n * p.clip_tiles * p.n_tiles : (int)(ceil_div_ll(m_total, kBlockM) * p.n_tiles);
   p.epi_n = epi_n; p.epi_chunks = block_n / epi_n;
   p.idesc = umma_idesc_bf16(kBlockM, block_n);
   p.tmem_cols = tmem_cols;
@@ -834,9 +871,9 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   // streamed weights gains 12 - 20 %, s5 `b` reaches 1.39 PFLOP/s): 256-wide column blocks and K >= 512.
   static const bool no_two_sm_env = getenv("VSB_NO_TWO_SM") != nullptr;
   // (64-byte rows, i.e. the pixel-grouped slow stem: measured slower in pairs, 0.46 vs 0.42 ms - opt-in only)
-  const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && !d->out_f16 && block_n == 256 && kchunk == 64 &&
+  const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && !d->out_f16 && !d->wgt_clip_rows && block_n == 256 && kchunk == 64 &&
                            total_chunks >= 8 && p.total_tiles / p.n_tiles >= 16;
-  if (((d->flags & VSB_PLAN_TWO_SM) || two_sm_auto) && !d->out_f16 && (kchunk == 64 || kchunk == 32) && !b_resident &&
+  if (((d->flags & VSB_PLAN_TWO_SM) || two_sm_auto) && !d->out_f16 && !d->wgt_clip_rows && (kchunk == 64 || kchunk == 32) && !b_resident &&
       block_n % 16 == 0 && block_n >= 32 && epi_warps == 8 && p.total_tiles / p.n_tiles >= 2) {
     const uint32_t stage2 = (uint32_t)((kBlockM + block_n / 2) * kchunk * 2);
     const long long fixed2 = (long long)epi_bufs * epi_buf_bytes + bar_bytes + 1024;

@@ -27,6 +27,10 @@ struct IgemmParams {
   int has_residual;
   int relu;
   int out_f16;     // 16-bit outputs are IEEE half instead of bf16 (vsb_conv_desc.out_f16)
+  // per-clip weights (vsb_conv_desc.wgt_clip_rows > 0): tiles never straddle clips
+  int clip_rows;       // output pixels per clip (0 = one weight matrix for all clips)
+  int clip_tiles;      // m-tiles per clip = ceil(clip_rows / 128)
+  int wgt_clip_rows;   // weight rows between consecutive clips' matrices
   long long* dbg;  // role timeline counters (VSB_WIN_DEBUG), else null
 };
 

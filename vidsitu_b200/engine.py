@@ -503,26 +503,14 @@ class ClipEngine:
         y_scale = torch.ones(c, dtype=torch.float32, device=dev)
         y_bias = torch.zeros(c, dtype=torch.float32, device=dev)
         t, h, w = theta.t, theta.h, theta.w
-        plans_s, plans_y = [], []
-        for i in range(n):
-            th_i = Act(theta.buf[i * tq * c:(i + 1) * tq * c], 1, t, h, w, c, c)
-            sc_out = Act(scores[i * tq * kp:(i + 1) * tq * kp], 1, t, h, w, kc, kp)
-            w_phi = phi.buf[i * tk * c:i * tk * c + kc * c]
-            plans_s.append(ConvPlan(self.dtype, th_i, w_phi, kc, (1, 1, 1), (1, 1, 1), (0, 0, 0), None, s_scale, s_bias,
-                                    sc_out, None, False, out_f16=True))   # half scores: 11 mantissa bits into exp()
-            sc_in = Act(scores[i * tq * kp:(i + 1) * tq * kp], 1, t, h, w, kp, kp)
-            out_i = Act(att.buf[i * tq * c:(i + 1) * tq * c], 1, t, h, w, c, c)
-            plans_y.append(ConvPlan(self.dtype, sc_in, g_t[i * c * kp:(i + 1) * c * kp], c, (1, 1, 1), (1, 1, 1),
-                                    (0, 0, 0), None, y_scale, y_bias, out_i, None, False))
-        self._keep += plans_s + plans_y + [s_scale, s_bias, y_scale, y_bias, scores, g_t]
-
-        def run_scores():
-            for p in plans_s:
-                p.run()
-
-        def run_out():
-            for p in plans_y:
-                p.run()
+        # one launch per product: clip i's weight matrix starts tk (resp. c) rows after clip i-1's
+        plan_s = ConvPlan(self.dtype, theta, phi.buf, kc, (1, 1, 1), (1, 1, 1), (0, 0, 0), None, s_scale, s_bias,
+                          Act(scores, n, t, h, w, kc, kp), None, False, out_f16=True,   # half scores: 11 mantissa bits into exp()
+                          wgt_clip_rows=tk)
+        plan_y = ConvPlan(self.dtype, Act(scores, n, t, h, w, kp, kp), g_t, c, (1, 1, 1), (1, 1, 1), (0, 0, 0), None,
+                          y_scale, y_bias, att, None, False, wgt_clip_rows=c)
+        self._keep += [plan_s, plan_y, s_scale, s_bias, y_scale, y_bias, scores, g_t]
+        run_scores, run_out = plan_s.run, plan_y.run
 
         fl = 2.0 * n * tq * tk * c
         self.trunk_ops.append((nl.prefix + ".g_transpose", lambda: ops.transpose_pad(g, g_t, kp), 0.0))

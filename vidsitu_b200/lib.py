@@ -47,7 +47,7 @@ class ConvDesc(C.Structure):
         ("in2", C.c_void_p),
         ("t2", C.c_int), ("h2", C.c_int), ("w2", C.c_int), ("cin2", C.c_int), ("in2_pitch", C.c_int),
         ("st2", C.c_int), ("sh2", C.c_int), ("sw2", C.c_int),
-        ("epi_n", C.c_int), ("epi_bufs", C.c_int), ("flags", C.c_int), ("out_f16", C.c_int),
+        ("epi_n", C.c_int), ("epi_bufs", C.c_int), ("flags", C.c_int), ("out_f16", C.c_int), ("wgt_clip_rows", C.c_int),
     ]
 
 

@@ -67,7 +67,8 @@ class ConvPlan:
                  scale: torch.Tensor, bias: torch.Tensor, out: Act, residual: Optional[Act] = None,
                  relu: bool = False, block_n: int = 0, kchunk: int = 0, stages: int = 0, algo: int = 0,
                  kw_ranges: Optional[Sequence[Sequence[int]]] = None, x2: Optional[Act] = None,
-                 stride2: Sequence[int] = (1, 1, 1), epi_n: int = 0, epi_bufs: int = 0, flags: int = 0, out_f16: bool = False):
+                 stride2: Sequence[int] = (1, 1, 1), epi_n: int = 0, epi_bufs: int = 0, flags: int = 0, out_f16: bool = False,
+                 wgt_clip_rows: int = 0):
         _require_cuda(x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None,
                       x2.buf if x2 is not None else None)
         pad_hi = pad_lo if pad_hi is None else pad_hi
@@ -92,6 +93,7 @@ class ConvPlan:
         d.algo = algo
         d.epi_n, d.epi_bufs, d.flags = epi_n, epi_bufs, flags
         d.out_f16 = int(out_f16)
+        d.wgt_clip_rows = int(wgt_clip_rows)
         k_per_tap_row = x.c * d.kw
         if kw_ranges is not None:
             if len(kw_ranges) != d.kw or d.kw > 8:
@@ -115,7 +117,10 @@ class ConvPlan:
             raise VsbError(f"conv tensors must be {expect}")
         if scale.dtype != torch.float32 or bias.dtype != torch.float32:
             raise VsbError("scale/bias must be float32")
-        if wgt.numel() != cout * (d.kt * d.kh * k_per_tap_row + k2):
+        if wgt_clip_rows:
+            if wgt.numel() < ((x.n - 1) * wgt_clip_rows + cout) * x.c:
+                raise VsbError("per-clip weights: wgt holds fewer than (n-1)*wgt_clip_rows + cout rows")
+        elif wgt.numel() != cout * (d.kt * d.kh * k_per_tap_row + k2):
             raise VsbError(f"packed weight has {wgt.numel()} elements, expected {cout}x({d.kt * d.kh}x{k_per_tap_row}+{k2})")
         self._keep = (x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None,
                       x2.buf if x2 is not None else None)
