@@ -137,6 +137,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--model", default=MODEL, help="sf_mdl_name of another backbone (BASELINE.json configs 3/4); "
+                    "the default is the headline SlowFast-R50 8x8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--per-op", default="", help="write per-launch timings (json) to this path")
@@ -164,10 +166,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    model, cfg, _ = build_model(MODEL, seed=0, crop=224, micro_batch=B)
+    model, cfg, _ = build_model(args.model, seed=0, crop=224, micro_batch=B)
     model = model.to(dev)
+    t_frames = cfg.sf_mdl.DATA.NUM_FRAMES
     # two distinct synthetic batches per rank; 2 x 308 MB of uint8 frames (> the 126 MB L2) alternate between steps
-    host_frames = [synthetic_frames(B, 32, 224, seed=1234 + 17 * rank + i).pin_memory() for i in range(2)]
+    host_frames = [synthetic_frames(B, t_frames, 224, seed=1234 + 17 * rank + i).pin_memory() for i in range(2)]
     dev_frames = [f.to(dev) for f in host_frames]
     eng = model._engine(B, dev)
     eng.capture()
@@ -248,11 +251,11 @@ def main():
         conv = [(n, ms_, f) for n, ms_, f in per_op if f > 0 and not n.startswith("proj_head")]
         conv_ms = sum(ms_ for _, ms_, _ in conv)
         all_ms = sum(ms_ for _, ms_, _ in per_op)
-        flops = GFLOP_PER_CLIP * 1e9 * B
+        flops = (GFLOP_PER_CLIP * 1e9 if args.model == MODEL else eng.conv_flops / B) * B
         achieved = flops / (conv_ms / 1e3) / 1e12
         traffic = None   # DRAM bytes of the conv launches of one step, from the committed ncu capture
         tp = os.path.join(ROOT, "profiles", "r01_step_dram_traffic.json")
-        if os.path.exists(tp) and B == 64:
+        if os.path.exists(tp) and B == 64 and args.model == MODEL:
             ks = json.load(open(tp))["kernels"]
             traffic = int(sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks if k["kernel"].startswith("conv_")))
         roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_win_kernel (all conv launches of a step)",
@@ -279,10 +282,11 @@ def main():
 
     if rank == 0:
         print(json.dumps({
-            "metric": "event clips/sec SlowFast-R50 8x8", "value": round(value, 2), "unit": "clips/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+            "metric": "event clips/sec SlowFast-R50 8x8" if args.model == MODEL else f"event clips/sec {args.model}",
+            "value": round(value, 2), "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": B, "model": MODEL,
+            "config": {"workload": WORKLOAD if args.model == MODEL else f"{args.model} feature extraction, batch {B} "
+                       f"synthetic event clips ({t_frames}x224x224) per GPU", "clips_per_gpu_per_step": B, "model": args.model,
                        "weights": "random-init (seed 0) + seeded BatchNorm statistics",
                        "l2": "inputs larger than L2: 2 alternating 308 MB uint8 frame batches per GPU, "
                              "activations >> 126 MB", "cuda_graph": True,
