@@ -61,7 +61,7 @@ for row_bytes in ((128, 64, 32) if which in ("all", "sem") else ()):
 clk = torch.zeros(148 * 2, dtype=torch.int64, device=dev)
 for grid, pad in (((148, 118), (296, 0)) if which in ("all", "rate") else ()):
     for same in (0, 1):
-        for n in (16, 32, 64, 96, 128, 192, 256):
+        for n in (16, 32, 64, 80, 96, 128, 160, 192, 208, 256):
             iters = 2000
             rc = lib.vsb_debug_umma_rate(n, iters, 4, same, grid, pad, clk.data_ptr(), None)
             L.check(rc, "vsb_debug_umma_rate")
