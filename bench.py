@@ -258,7 +258,7 @@ def main():
         if os.path.exists(tp) and B == 64 and args.model == MODEL:
             ks = json.load(open(tp))["kernels"]
             traffic = int(sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks if k["kernel"].startswith("conv_")))
-        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_win_kernel (all conv launches of a step)",
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_igemm2_kernel + conv_win_kernel (all conv launches of a step)",
                     "achieved": round(achieved, 2),
                     "peak": peak_sus, "unit": "TFLOP/s", "frac": round(achieved / peak_sus, 4), "traffic": traffic,
                     "traffic_note": "dram__bytes_read+write summed over the conv launches of one step (ncu, "

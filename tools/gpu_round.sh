@@ -16,7 +16,7 @@ timeout 600 python bench.py --per-op gpurun_out/per_op.json > gpurun_out/bench.j
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
   --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --profile-range > gpurun_out/ncu_bench.log 2>&1; echo "ncu launches rc=$?"
-OPS="${VSB_FULL_OPS:-s1.pathway1_stem.conv s1.pathway0_stem.conv s1.pathway0_stem.pool_layer s2.pathway0_res1.branch2.a s2.pathway0_res1.branch2.b s2.pathway0_res1.branch2.c s2.pathway1_res1.branch2.a s2.pathway1_res1.branch2.b s2.pathway1_res1.branch2.c s3.pathway0_res1.branch2.b s4.pathway0_res1.branch2.b s5.pathway0_res1.branch2.b}"
+OPS="${VSB_FULL_OPS:-s1.pathway1_stem.conv s1.pathway0_stem.conv s2.pathway0_res1.branch2.b s2.pathway0_res1.branch2.c s2.pathway1_res1.branch2.b s3.pathway0_res1.branch2.b s4.pathway0_res1.branch2.a s4.pathway0_res1.branch2.c s5.pathway0_res1.branch2.b}"
 timeout 420 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/ops_full \
   python tools/profile_ops.py $OPS > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 grep profiling gpurun_out/ncu_full.log | awk '{print $2}' > gpurun_out/ops_full.labels

@@ -37,6 +37,9 @@ def launches(path, skip=0):
     rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
     hdr, rows = rows[0], rows[1:]
     k, v = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    if "Metric Name" in hdr:   # several metrics per launch: keep the duration rows only
+        mn = hdr.index("Metric Name")
+        rows = [r for r in rows if r[mn] == "gpu__time_duration.sum"]
     rows = rows[skip:]
     agg = collections.OrderedDict()
     for r in rows:
