@@ -661,7 +661,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   // (measured on B200: the 16-warp epilogue shape does not beat 8 warps -- these layers are HBM-bound, the
   // accumulator wait is back-pressure -- so it is opt-in: VSB_EPI_WARPS=16)
   const int epi_warps = (ew_env && atoi(ew_env) == 16) ? 16 : 8;
-  if (d->epi_n != 0 && d->epi_n != 32 && d->epi_n != 64) FAIL(VSB_ERR_INVALID, "epi_n must be 0, 32 or 64");
+  if (d->epi_n != 0 && d->epi_n != 16 && d->epi_n != 32 && d->epi_n != 64) FAIL(VSB_ERR_INVALID, "epi_n must be 0, 16, 32 or 64");
   if (d->epi_bufs != 0 && (d->epi_bufs < 2 || d->epi_bufs > kMaxEpiBufs)) FAIL(VSB_ERR_INVALID, "epi_bufs must be 0 or 2..4");
   const int epi_n_env = d->epi_n, epi_bufs_env = d->epi_bufs;  // caller's tuning (0 = automatic)
 
