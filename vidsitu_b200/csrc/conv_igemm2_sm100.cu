@@ -100,7 +100,7 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
 }
 }  // namespace
 
-// KK = kchunk / 16: 64- or 128-byte swizzled rows, KK MMAs of K = 16 per chunk, one chunk per ring stage.
+// KK = kchunk / 16: 64- or 128-byte swizzled rows, KK MMAs of K = 16 per chunk, 4 / KK chunks per ring stage.
 template <int KK>
 __global__ void __launch_bounds__((kEW + 2) * 32, 1)
 conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -169,7 +169,9 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == kProducerWarp) {
     if (lane == 0) {
       // ------------------------------------------------------ TMA producer (one thread per CTA)
-      const uint32_t stage_tx = 2u * (a_chunk_bytes + b_chunk_bytes);  // bytes of BOTH CTAs per chunk
+      constexpr int CPS = 4 / KK;  // chunks per ring stage: a stage always carries 64 K-elements (4 MMAs)
+      const uint32_t chunk_tx = 2u * (a_chunk_bytes + b_chunk_bytes);  // bytes of BOTH CTAs per chunk
+      const uint32_t b_off = CPS * a_chunk_bytes;
       const int total_chunks = p.total_chunks, stages = p.stages;
       const int cin = p.cin, fkw = p.kw, fkh = p.kh, block_n = p.block_n;
       const int owo = p.wo, oho = p.ho, oto = p.to, sw = p.sw, sh = p.sh, st = p.st, lw = p.lw, lh = p.lh, lt = p.lt;
@@ -191,29 +193,36 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int ncol = n_tile * block_n + (int)rank * (int)half_n;
         int cc = 0, kw_ = 0, kh_ = 0, kt_ = 0, kcoord = 0;
         int left1 = chunks1;
-        for (int g = 0; g < total_chunks; ++g) {
+        int left = total_chunks;
+        while (left > 0) {
+          const int nch = left < CPS ? left : CPS;
+          left -= nch;
           mbar_wait(&empty_bar[slot], parity);
-          if (leader) mbar_expect_tx(&full_bar[slot], stage_tx);
+          if (leader) mbar_expect_tx(&full_bar[slot], nch * chunk_tx);
           const uint32_t full_leader = mapa_u32(&full_bar[slot], 0);
           uint8_t* a_dst = smem + (uint32_t)slot * stage_bytes;
-          uint8_t* b_dst = a_dst + a_chunk_bytes;
-          if (left1 > 0) {
-            tma2_load_im2col_5d(a_dst, &map_a, full_leader, cc, w0, h0, d0, n0, (uint16_t)kw_, (uint16_t)kh_,
-                                (uint16_t)kt_);
-            if (--left1 == 0) cc = -kchunk;
-          } else {
-            tma2_load_im2col_5d(a_dst, &map_a2, full_leader, cc, w2, h2, d2, n0, 0, 0, 0);
-          }
-          tma2_load_2d(b_dst, &map_b, full_leader, kcoord, ncol);
-          kcoord += kchunk;
-          cc += kchunk;
-          if (cc == cin && left1 > 0) {
-            cc = 0;
-            if (++kw_ == fkw) {
-              kw_ = 0;
-              if (++kh_ == fkh) {
-                kh_ = 0;
-                ++kt_;
+          uint8_t* b_dst = a_dst + b_off;
+          for (int c = 0; c < nch; ++c) {
+            if (left1 > 0) {
+              tma2_load_im2col_5d(a_dst, &map_a, full_leader, cc, w0, h0, d0, n0, (uint16_t)kw_, (uint16_t)kh_,
+                                  (uint16_t)kt_);
+              if (--left1 == 0) cc = -kchunk;
+            } else {
+              tma2_load_im2col_5d(a_dst, &map_a2, full_leader, cc, w2, h2, d2, n0, 0, 0, 0);
+            }
+            tma2_load_2d(b_dst, &map_b, full_leader, kcoord, ncol);
+            a_dst += a_chunk_bytes;
+            b_dst += b_chunk_bytes;
+            kcoord += kchunk;
+            cc += kchunk;
+            if (cc == cin && left1 > 0) {
+              cc = 0;
+              if (++kw_ == fkw) {
+                kw_ = 0;
+                if (++kh_ == fkh) {
+                  kh_ = 0;
+                  ++kt_;
+                }
               }
             }
           }
@@ -230,7 +239,9 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const uint64_t desc_hi = umma_smem_desc(0, row_bytes) & 0xFFFFFFFF00000000ull;
       const uint32_t desc_lo_flags = (uint32_t)(umma_smem_desc(0, row_bytes) & 0xFFFFC000ull);
       const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
-      const uint32_t stage_lo = stage_bytes >> 4, b_off_lo = a_chunk_bytes >> 4;
+      constexpr int CPS = 4 / KK;
+      const uint32_t stage_lo = stage_bytes >> 4, a_chunk_lo = a_chunk_bytes >> 4, b_chunk_lo = b_chunk_bytes >> 4;
+      const uint32_t b_off_lo = (CPS * a_chunk_bytes) >> 4;
       const uint32_t idesc = p.idesc;
       const int total_chunks = p.total_chunks, stages = p.stages, block_n = p.block_n;
       int slot = 0, tcount = 0;
@@ -240,18 +251,25 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);  // both CTAs drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * block_n;
-        for (int g = 0; g < total_chunks; ++g) {
+        for (int g = 0; g < total_chunks; g += CPS) {
+          const int nch = total_chunks - g < CPS ? total_chunks - g : CPS;
           mbar_wait(&full_bar[slot], parity);
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < KK; ++k) {
-              const uint64_t adesc = desc_hi | (uint64_t)(desc_lo_flags | (a_slot_lo + 2 * k));
-              const uint64_t bdesc = desc_hi | (uint64_t)(desc_lo_flags | (a_slot_lo + b_off_lo + 2 * k));
-              umma2_bf16(tmem_d, adesc, bdesc, idesc, (g | k) != 0 ? 1u : 0u);
+            for (int c = 0; c < CPS; ++c) {
+              if (c < nch) {
+#pragma unroll
+                for (int k = 0; k < KK; ++k) {
+                  const uint64_t adesc = desc_hi | (uint64_t)(desc_lo_flags | (a_slot_lo + c * a_chunk_lo + 2 * k));
+                  const uint64_t bdesc =
+                      desc_hi | (uint64_t)(desc_lo_flags | (a_slot_lo + b_off_lo + c * b_chunk_lo + 2 * k));
+                  umma2_bf16(tmem_d, adesc, bdesc, idesc, (g | c | k) != 0 ? 1u : 0u);
+                }
+              }
             }
             umma2_commit_both(&empty_bar[slot]);
-            if (g == total_chunks - 1) umma2_commit_both(&tmem_full[acc]);
+            if (g + CPS >= total_chunks) umma2_commit_both(&tmem_full[acc]);
           }
           __syncwarp();
           a_slot_lo += stage_lo;

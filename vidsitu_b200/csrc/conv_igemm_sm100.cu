@@ -870,17 +870,18 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   // Automatic for the layers it was built for (measured on B200, SF50 batch 64: every res4/res5 conv with
   // streamed weights gains 12 - 20 %, s5 `b` reaches 1.39 PFLOP/s): 256-wide column blocks and K >= 512.
   static const bool no_two_sm_env = getenv("VSB_NO_TWO_SM") != nullptr;
-  // (64-byte rows, i.e. the pixel-grouped slow stem: measured slower in pairs, 0.46 vs 0.42 ms - opt-in only)
-  const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && !d->out_f16 && !d->wgt_clip_rows && block_n == 256 && kchunk == 64 &&
+  // (64-byte rows, i.e. the pixel-grouped stems: 2 - 4 % faster in pairs once a ring stage carries two chunks;
+  // with one chunk = two MMAs per stage the issuer was the bottleneck: 0.46 vs 0.42 ms)
+  const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && !d->out_f16 && !d->wgt_clip_rows && block_n == 256 && (kchunk == 64 || kchunk == 32) &&
                            total_chunks >= 8 && p.total_tiles / p.n_tiles >= 16;
   if (((d->flags & VSB_PLAN_TWO_SM) || two_sm_auto) && !d->out_f16 && !d->wgt_clip_rows && (kchunk == 64 || kchunk == 32) && !b_resident &&
       block_n % 16 == 0 && block_n >= 32 && epi_warps == 8 && p.total_tiles / p.n_tiles >= 2) {
-    const uint32_t stage2 = (uint32_t)((kBlockM + block_n / 2) * kchunk * 2);
+    const uint32_t stage2 = (uint32_t)((kBlockM + block_n / 2) * 128);  // 64 K-elements per stage: 64 / kchunk chunks
     const long long fixed2 = (long long)epi_bufs * epi_buf_bytes + bar_bytes + 1024;
     int stages2 = (int)((227 * 1024 - fixed2) / stage2);
     if (d->stages && stages2 > d->stages) stages2 = d->stages;
     if (stages2 > 12) stages2 = 12;
-    if (stages2 > total_chunks * 2) stages2 = total_chunks * 2;
+    if (stages2 > num_kstages * 2) stages2 = num_kstages * 2;
     if (stages2 >= 2) {
       rc = encode_tiled_2d(&plan->map_b, d->wgt, k_total, d->cout, k_total * 2, kchunk, block_n / 2, swz);
       if (rc != VSB_OK) {
