@@ -142,6 +142,7 @@ typedef struct vsb_conv_desc {
 #define VSB_PLAN_TWO_SM 16        /* im2col: CTA pairs (tcgen05 cta_group::2), 256-pixel tiles, each CTA
                                      streams half of the weight rows; kchunk 64 layers with streamed weights
                                      (automatic for 256-wide column blocks with K >= 512)                 */
+#define VSB_PLAN_NO_TILE_SPLIT 64 /* window: epilogue warp groups always split column chunks, never tiles    */
 #define VSB_PLAN_ONE_SM 32        /* im2col: never use CTA pairs                                          */
 
 typedef struct vsb_conv_plan vsb_conv_plan;

@@ -30,6 +30,7 @@ CANDIDATES = {
     "bn256en32eb4": {"block_n": 256, "epi_n": 32, "epi_bufs": 4}, "bn256en32": {"block_n": 256, "epi_n": 32},
     "st2sw": {"stages": 2, "flags": 1}, "en32eb4sw": {"epi_n": 32, "epi_bufs": 4, "flags": 1},
     "sm1": {"flags": 32}, "sm2": {"flags": 16}, "sm2en32": {"flags": 16, "epi_n": 32}, "sm2en32eb4": {"flags": 16, "epi_n": 32, "epi_bufs": 4},
+    "nots": {"flags": 64}, "ts_en64": {"epi_n": 64},
     "sm2en16": {"flags": 16, "epi_n": 16}, "en16": {"epi_n": 16},
     "sm2bn128": {"flags": 16, "block_n": 128}, "sm2st6": {"flags": 16, "stages": 6}, "sm2st4": {"flags": 16, "stages": 4},
 }

@@ -61,6 +61,7 @@ struct WinParams {
   uint32_t b_block_bytes;
   int block_n, epi_n, epi_chunks, epi_bufs, epi_warps;
   int nacc, nacc_shift;    // TMEM accumulators (2, 4, or the temporal-scatter ring: up to 16)
+  int tsplit;              // epilogue warp groups take alternate tiles (narrow tiles) instead of alternate column chunks
   int tsc;                 // temporal-scatter mode: one N = kt * block_n MMA per K step, ring of nacc accumulators
   int t_in;                // input frames
   int pair;                // MMA issuer interleaves two tiles (independent accumulation chains, shared B reads)

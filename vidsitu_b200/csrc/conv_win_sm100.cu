@@ -97,7 +97,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
     }
     for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], p.epi_warps);
+      mbar_init(&tmem_empty[i], p.tsplit ? p.epi_warps >> 1 : p.epi_warps);
     }
     for (int i = 0; i < kEpiWarps * kMaxEpiBufs; ++i) mbar_init(&epi_ready[i], 1);
     mbar_init(bres_bar, 1);
@@ -399,10 +399,22 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
     const float relu_floor = p.relu ? 0.f : -__int_as_float(0x7f800000);
     const uint32_t sb_s = smem_u32(sb_tab);
     // prefetch cursor (lane 0): next chunk of THIS warp whose staging slab has not been armed yet
+    // Work split between the two groups of four epilogue warps: column chunks of every tile (chunk parity ==
+    // group), or - tile split, for narrow tiles (<= 2 chunks) whose epilogue is one latency chain per warp -
+    // whole tiles (tile parity == group), so that two tiles drain concurrently.
+    const bool tsplit = p.tsplit != 0;
     TileCursor pf;
     pf.init(blockIdx.x, gridDim.x, p.yb_count, tdim);
-    int pf_tl = 0, pf_chunk = ngrp == 2 ? grp : 0, pf_q = 0;
-    const int chunk_step = ngrp;  // this warp's chunks: grp, grp + ngrp, ...
+    int pf_tl = 0, pf_chunk = (ngrp == 2 && !tsplit) ? grp : 0, pf_q = 0;
+    const int chunk_step = tsplit ? 1 : ngrp;  // this warp's chunks: grp, grp + ngrp, ... (all of them when tile-split)
+    const int chunk0 = (ngrp == 2 && !tsplit) ? grp : 0;
+    auto pf_next_tile = [&]() {
+      if (++pf_tl == L) {
+        pf_tl = 0;
+        pf.next();
+      }
+    };
+    if (tsplit && grp == 1) pf_next_tile();  // group 1 starts at the second tile
     auto arm_next = [&]() {
       const int bsel = pf_q % nb;
       if (p.has_residual) {
@@ -416,11 +428,9 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
       ++pf_q;
       pf_chunk += chunk_step;
       if (pf_chunk >= chunks) {
-        pf_chunk = ngrp == 2 ? grp : 0;
-        if (++pf_tl == L) {
-          pf_tl = 0;
-          pf.next();
-        }
+        pf_chunk = chunk0;
+        pf_next_tile();
+        if (tsplit) pf_next_tile();  // skip the other group's tile
       }
     };
     if (lane == 0) {
@@ -434,11 +444,12 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
       for (int tl = 0; tl < L; ++tl, ++tcount) {
         const int y0 = cur.yb * p.R;
         const int tn = cur.n * p.to + (L == 1 ? cur.t : tl);
+        if (tsplit && (tcount & 1) != grp) continue;  // the other group's tile
         const int acc = tcount & (p.nacc - 1);
         WIN_T(4, mbar_wait(&tmem_full[acc], (tcount >> p.nacc_shift) & 1));
         if (kDbg) dbg_acc[9] += 1;
         tc_fence_after();
-        for (int c = ngrp == 2 ? grp : 0; c < chunks; c += chunk_step) {
+        for (int c = chunk0; c < chunks; c += chunk_step) {
           const int b = q % nb;
           uint8_t* buf = my_bufs + b * slab_bytes;
           WIN_T(5, mbar_wait(&my_ready[b], (q / nb) & 1));  // slab free (+ residual landed)
@@ -574,12 +585,21 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
   const bool tsc = !no_tsc && d->kt > 1 && d->kt * block_n <= 256 && (block_n & (block_n - 1)) == 0 &&
                    acc_slots >= d->kt + 2 && d->pt_lo < d->kt && d->pt_hi < d->kt;
   const uint32_t b_block_bytes = (uint32_t)block_n * 128 * (tsc ? d->kt : 1);
-  int epi_n = block_n >= 64 ? 32 : block_n;  // >= 2 chunks per tile keep both epilogue warp groups busy
+  // Epilogue work split between the two groups of four warps.  Tiles of <= 64 columns: the groups take alternate
+  // TILES, each tile one 64-column chunk (measured on B200: fast-pathway `b` convs 0.079 -> 0.063 ms, the chain
+  // TMEM -> registers -> smem -> TMA store of a narrow tile is one latency-bound sequence per warp, so two tiles
+  // in flight beat two half-tiles).  Wider tiles: alternate 32-column chunks of every tile.
+  // (not in temporal-scatter mode: the fast stem is MMA-bound and has no shared memory left for 8 warps' slabs)
+  static const bool no_tsplit_env = getenv("VSB_WIN_NO_TSPLIT") != nullptr;
+  const bool want_tsplit = !no_tsplit_env && !(d->flags & VSB_PLAN_NO_TILE_SPLIT) && !tsc;
+  int epi_n = block_n >= 64 ? 32 : block_n;
+  if (want_tsplit && block_n == 64 && d->epi_n != 32) epi_n = 64;
   if (d->epi_n && block_n >= 2 * d->epi_n && block_n % d->epi_n == 0) epi_n = d->epi_n;  // caller's tuning
   if (block_n % epi_n) epi_n = 16;
   const int epi_chunks = block_n / epi_n;
-  const int epi_warps = epi_chunks >= 2 ? 8 : 4;
-  if (epi_warps == 8 && (epi_chunks & 1)) return 1;  // chunk parity split needs an even chunk count
+  const bool tsplit = want_tsplit && epi_chunks == 1;
+  const int epi_warps = (epi_chunks >= 2 || tsplit) ? 8 : 4;
+  if (epi_warps == 8 && !tsplit && (epi_chunks & 1)) return 1;  // chunk parity split needs an even chunk count
   int epi_bufs = d->residual ? 3 : 2;
   if (d->epi_bufs >= 2 && d->epi_bufs <= kMaxEpiBufs) epi_bufs = d->epi_bufs;
   const int bar_bytes = 1024 + 2048 + 2048;  // barriers + per-step descriptor table + (scale, bias) pairs
@@ -696,6 +716,7 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
   if (spf * 8 > 2048) return 1;
   p.b_blocks = tsc ? b_blocks_per_frame : b_blocks; p.b_block_bytes = b_block_bytes;
   p.tsc = tsc ? 1 : 0;
+  p.tsplit = tsplit ? 1 : 0;
   p.t_in = d->t;
   p.b_blocks_per_frame = b_blocks_per_frame; p.k_per_frame = k_per_frame;
   p.block_n = block_n; p.epi_n = epi_n; p.epi_chunks = epi_chunks; p.epi_bufs = epi_bufs; p.epi_warps = epi_warps;
