@@ -196,3 +196,18 @@ def test_event_windows_match_the_oracle_and_the_reference_facts():
     assert ev[0][:3] == [0, 0, 2] and ev[0][-1] == 60 and ev[4][-2:] == [298, 299] and all(len(e) == 32 for e in ev)
     assert E.event_frame_indices(8, 8)[0] == [0, 6, 14, 22, 30, 38, 46, 54]
     assert E.event_frame_indices(64, 2)[0][:18] == [0] * 18
+
+
+def test_tuning_table_is_well_formed():
+    """vidsitu_b200/tune_table.json (tools/autotune.py): shape signatures -> plan knobs that never change results."""
+    import json
+    import re
+    from vidsitu_b200.engine import _PLAN_KNOBS
+    p = os.path.join(ROOT, "vidsitu_b200", "tune_table.json")
+    tab = json.load(open(p))
+    assert tab["entries"] and all(m["gpu"] == "NVIDIA B200" for m in tab["meta"])
+    sig = re.compile(r"^\d+>\d+\|k\d{3}\|s\d{3}\|o\d+x\d+x\d+\|p\d+>\d+\|r[01]\|x\d+$")
+    for k, knobs in tab["entries"].items():
+        assert sig.match(k), k
+        assert knobs and set(knobs) <= set(_PLAN_KNOBS) | {"algo", "win_group"}, (k, knobs)
+        assert knobs.get("epi_n", 32) in (16, 32, 64) and knobs.get("epi_bufs", 2) in (2, 3, 4)
