@@ -143,6 +143,9 @@ typedef struct vsb_conv_desc {
                                      streams half of the weight rows; kchunk 64 layers with streamed weights
                                      (automatic for 256-wide column blocks with K >= 512)                 */
 #define VSB_PLAN_NO_TILE_SPLIT 64 /* window: epilogue warp groups always split column chunks, never tiles    */
+#define VSB_PLAN_REVERSE 128      /* walk the output in DESCENDING order (tiles / clips).  A kernel that starts where
+                                     its producer finished finds the most recently written ~100 MB of its input still
+                                     in the 126 MB L2; the engine alternates the direction along each pathway.       */
 #define VSB_PLAN_ONE_SM 32        /* im2col: never use CTA pairs                                          */
 
 typedef struct vsb_conv_plan vsb_conv_plan;

@@ -181,6 +181,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int pm = pm0; pm < pm_tiles; pm += pm_step) {
         int mt = 2 * pm + (int)rank;
         if (mt >= m_tiles) mt = m_tiles - 1;  // odd tile count: the peer recomputes the last tile (not stored)
+        if (p.reverse) mt = m_tiles - 1 - mt;
         const int m0 = mt * kBlockM;
         const int wo = m0 % owo;
         const int r1 = m0 / owo;
@@ -313,7 +314,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       if (has_res && mt < m_tiles) {
         mbar_expect_tx(&my_ready[pf_b], slab_bytes);
         tma_load_2d(my_bufs + pf_b * slab_bytes, &map_res, &my_ready[pf_b], nbase + pf_chunk * epi_n,
-                    mt * kBlockM + row_in_tile);
+                    (p.reverse ? m_tiles - 1 - mt : mt) * kBlockM + row_in_tile);
       } else {
         mbar_arrive(&my_ready[pf_b]);
       }
@@ -336,7 +337,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     for (int pm = pm0; pm < pm_tiles; pm += pm_step, ++tcount) {
       const int mt = 2 * pm + (int)rank;
       const bool valid = mt < m_tiles;
-      const int m0 = mt * kBlockM;
+      const int m0 = (p.reverse ? m_tiles - 1 - mt : mt) * kBlockM;
       const int acc = tcount & 1;
       mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
       tc_fence_after();

@@ -146,7 +146,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int slot = 0;
       uint32_t parity = 1;  // first pass over the ring: slots are free
       const int clip_tiles = p.clip_tiles, clip_rows = p.clip_rows, wgt_clip_rows = p.wgt_clip_rows;
-      for (int mt = m_tile0; mt < m_tiles; mt += m_tile_step) {
+      const bool rev = p.reverse != 0;
+      for (int mt_ = m_tile0; mt_ < m_tiles; mt_ += m_tile_step) {
+        const int mt = rev ? m_tiles - 1 - mt_ : mt_;
         int m0 = mt * kBlockM, wrow0 = 0;
         if (clip_rows) {  // per-clip weights: tile lt of clip cb (its last tile runs into the next clip: never stored)
           const int cb = mt / clip_tiles;
@@ -325,7 +327,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (has_res) {
         mbar_expect_tx(&my_ready[pf_b], slab_bytes);
         tma_load_2d(my_bufs + pf_b * slab_bytes, &map_res, &my_ready[pf_b], nbase + pf_chunk * epi_n,
-                    pf_mt * kBlockM + row_in_tile);
+                    (p.reverse ? m_tiles - 1 - pf_mt : pf_mt) * kBlockM + row_in_tile);
       } else {
         mbar_arrive(&my_ready[pf_b]);
       }
@@ -346,7 +348,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t bpar = 0;    // parity of that slab's ready barrier
     int gq = 0;           // global chunk counter of the CTA (all tiles, all chunks)
     int tcount = 0;
-    for (int mt = m_tile0; mt < m_tiles; mt += m_tile_step, ++tcount) {
+    for (int mt_ = m_tile0; mt_ < m_tiles; mt_ += m_tile_step, ++tcount) {
+      const int mt = p.reverse ? m_tiles - 1 - mt_ : mt_;
       const int m0 = mt * kBlockM;
       const int acc = tcount & 1;
       IG_T(4, mbar_wait(&tmem_full[acc], (tcount >> 1) & 1));
@@ -840,6 +843,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   p.has_residual = d->residual != nullptr;
   p.relu = d->relu;
   p.out_f16 = d->out_f16 ? 1 : 0;
+  p.reverse = (d->flags & VSB_PLAN_REVERSE) ? 1 : 0;
   p.dbg = nullptr;
   if (getenv("VSB_WIN_DEBUG")) {  // debug only: the one place the library allocates device memory
     if (cudaMalloc(&p.dbg, 16 * sizeof(long long)) == cudaSuccess) (void)cudaMemset(p.dbg, 0, 16 * sizeof(long long));

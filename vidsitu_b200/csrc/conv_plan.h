@@ -26,6 +26,7 @@ struct IgemmParams {
   const float* bias;
   int has_residual;
   int relu;
+  int reverse;     // walk the output tiles in descending order (VSB_PLAN_REVERSE)
   int out_f16;     // 16-bit outputs are IEEE half instead of bf16 (vsb_conv_desc.out_f16)
   // per-clip weights (vsb_conv_desc.wgt_clip_rows > 0): tiles never straddle clips
   int clip_rows;       // output pixels per clip (0 = one weight matrix for all clips)
@@ -61,6 +62,7 @@ struct WinParams {
   uint32_t b_block_bytes;
   int block_n, epi_n, epi_chunks, epi_bufs, epi_warps;
   int nacc, nacc_shift;    // TMEM accumulators (2, 4, or the temporal-scatter ring: up to 16)
+  int reverse, n_clips;    // walk the clips in descending order (VSB_PLAN_REVERSE)
   int tsplit;              // epilogue warp groups take alternate tiles (narrow tiles) instead of alternate column chunks
   int tsc;                 // temporal-scatter mode: one N = kt * block_n MMA per K step, ring of nacc accumulators
   int t_in;                // input frames

@@ -161,7 +161,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
       TileCursor cur;
       cur.init(blockIdx.x, gridDim.x, p.yb_count, L == 1 ? p.to : 1);
       for (; cur.run < p.total_runs; cur.next()) {
-        const int t0 = L == 1 ? cur.t : 0, n = cur.n;
+        const int t0 = L == 1 ? cur.t : 0, n = p.reverse ? p.n_clips - 1 - cur.n : cur.n;
         const int y0 = cur.yb * p.R;
         for (int fi = 0; fi < nframes; ++fi) {
           const int f = t0 + fi + f_base;  // input frame; outside [0, T) -> zero-filled window
@@ -418,7 +418,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
     auto arm_next = [&]() {
       const int bsel = pf_q % nb;
       if (p.has_residual) {
-        const int tn = pf.n * p.to + (L == 1 ? pf.t : pf_tl);
+        const int tn = (p.reverse ? p.n_clips - 1 - pf.n : pf.n) * p.to + (L == 1 ? pf.t : pf_tl);
         mbar_expect_tx(&my_ready[bsel], slab_bytes);
         tma_load_4d(my_bufs + bsel * slab_bytes, &map_res, &my_ready[bsel], pf_chunk * p.epi_n, bx0,
                     pf.yb * p.R + by0, tn);
@@ -443,7 +443,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
     for (; cur.run < p.total_runs; cur.next()) {
       for (int tl = 0; tl < L; ++tl, ++tcount) {
         const int y0 = cur.yb * p.R;
-        const int tn = cur.n * p.to + (L == 1 ? cur.t : tl);
+        const int tn = (p.reverse ? p.n_clips - 1 - cur.n : cur.n) * p.to + (L == 1 ? cur.t : tl);
         if (tsplit && (tcount & 1) != grp) continue;  // the other group's tile
         const int acc = tcount & (p.nacc - 1);
         WIN_T(4, mbar_wait(&tmem_full[acc], (tcount >> p.nacc_shift) & 1));
@@ -717,6 +717,8 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
   p.b_blocks = tsc ? b_blocks_per_frame : b_blocks; p.b_block_bytes = b_block_bytes;
   p.tsc = tsc ? 1 : 0;
   p.tsplit = tsplit ? 1 : 0;
+  p.reverse = (d->flags & VSB_PLAN_REVERSE) ? 1 : 0;
+  p.n_clips = d->n;
   p.t_in = d->t;
   p.b_blocks_per_frame = b_blocks_per_frame; p.k_per_frame = k_per_frame;
   p.block_n = block_n; p.epi_n = epi_n; p.epi_chunks = epi_chunks; p.epi_bufs = epi_bufs; p.epi_warps = epi_warps;

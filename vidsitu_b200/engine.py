@@ -100,6 +100,11 @@ class ClipEngine:
         # buffers the Fast stream never waits for the Slow one (only the next slow stage waits for the lateral).
         self.early_lateral = self.two_streams and str(self.tune.get("*", {}).get(
             "early_lateral", os.environ.get("VSB_EARLY_LATERAL", "1"))) == "1"
+        # Direction of the tile walk, alternating along each pathway's chain a -> b -> c -> a' ...: a kernel that
+        # starts where its producer finished finds the most recently written part of its input still in L2.
+        self.alternate = str(self.tune.get("*", {}).get("alternate", os.environ.get("VSB_ALTERNATE", "1"))) == "1"
+        self._rev = [True] * max(1, spec.num_pathways)   # the stem pools write ascending: the first conv walks down
+        self._pw = 0
         self._dedicated: List[torch.Tensor] = []
         self.dedicated_bytes = 0
         self.op_bytes: Dict[str, float] = {}
@@ -223,7 +228,7 @@ class ClipEngine:
         return max(j, 1)
 
     def _window_plan(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act], relu: bool, scale, bias, wt,
-                     pad_w: Optional[int] = None, j: Optional[int] = None) -> Optional[ConvPlan]:
+                     pad_w: Optional[int] = None, j: Optional[int] = None, rev_flag: int = 0) -> Optional[ConvPlan]:
         """Shared-memory window algorithm (conv_win_sm100.cu) for convs with spatial taps and <= 64
         (grouped) input channels: returns the plan, or None when the layer is outside its domain."""
         tn = self._tune(cs.key, self._sig(cs, x, out, residual))
@@ -265,22 +270,26 @@ class ClipEngine:
             return ConvPlan(self.dtype, xin, w, j * out.c, (cs.kernel[0], cs.kernel[1], ngt),
                             (cs.stride[0], cs.stride[1], 1), (cs.pad[0], cs.pad[1], plo), (cs.pad[0], cs.pad[1], phi),
                             scale.repeat(j), bias.repeat(j), yout, res, relu, algo=2, kw_ranges=ranges,
-                            **{k: v for k, v in tn.items() if k in ("stages", "epi_n", "epi_bufs", "flags")})
+                            **dict({k: v for k, v in tn.items() if k in ("stages", "epi_n", "epi_bufs")},
+                                   flags=int(tn.get("flags", 0)) | rev_flag))
         except VsbError:
             if tn.get("algo") == "window":
                 raise
             return None
 
-    def _conv(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act] = None, relu: Optional[bool] = None):
+    def _conv(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act] = None, relu: Optional[bool] = None,
+              reverse: bool = False):
         if x.c_real != cs.cin:
             raise VsbError(f"{cs.key}: input has {x.c_real} channels, conv expects {cs.cin}")
         scale, bias = self._affine(cs, out.c)
         sig = self._sig(cs, x, out, residual)
         self.op_sig[cs.key] = sig
         tune = {k: v for k, v in self._tune(cs.key, sig).items() if k in _PLAN_KNOBS}
+        rev_flag = 128 if (reverse and self.alternate and self.dtype == VSB_BF16) else 0   # VSB_PLAN_REVERSE
+        tune["flags"] = int(tune.get("flags", 0)) | rev_flag
         relu = cs.relu if relu is None else relu
         wt = self._tensor(cs.key + ".weight")
-        plan = self._window_plan(cs, x, out, residual, relu, scale, bias, wt)
+        plan = self._window_plan(cs, x, out, residual, relu, scale, bias, wt, rev_flag=rev_flag)
         j = self._group_factor(cs, x, out, residual) if plan is None else 0
         bn = tune.get("block_n", 0)
         if bn and ((max(j, 1) * out.c) % bn or bn > max(j, 1) * out.c):
@@ -309,7 +318,7 @@ class ClipEngine:
         self.op_bytes[cs.key] = es * (x.pixels * x.c + m * out.c * (2 if residual is not None else 1))
         self.trunk_ops.append((cs.key, plan.run, float(m) * cs.flops_per_out_pixel))
 
-    def _conv_with_shortcut(self, c: ConvSpec, b: Act, br: ConvSpec, x: Act, out: Act) -> bool:
+    def _conv_with_shortcut(self, c: ConvSpec, b: Act, br: ConvSpec, x: Act, out: Act, reverse: bool = False) -> bool:
         """relu(BN1(branch1(x)) + BN_c(c(b)))  (resnet_helper.py:352-358) as ONE launch: the strided 1x1x1
         projection shortcut is a second K segment of the block's last conv (vsb_conv_desc.in2), so its
         [M, 4*dim_inner] result is never written to HBM and never re-read as a residual.  Both frozen
@@ -339,6 +348,7 @@ class ClipEngine:
         tune = {k: v for k, v in self._tune(c.key, sig).items() if k in _PLAN_KNOBS and k != "kchunk"}
         if tune.get("block_n", 0) and (out.c % tune["block_n"] or tune["block_n"] > out.c):
             tune.pop("block_n")
+        tune["flags"] = int(tune.get("flags", 0)) | (128 if (reverse and self.alternate) else 0)
         try:
             plan = ConvPlan(self.dtype, b, w, out.c, c.kernel, c.stride, c.pad, None, s, b_c + b_1, out, None, True,
                             kchunk=kchunk, x2=x, stride2=br.stride, **tune)
@@ -417,24 +427,27 @@ class ClipEngine:
 
     def _block(self, x: Act, blk: BlockSpec, out_pitch: Optional[int]) -> Act:
         n = x.n
+        pw = self._pools.index(self._pool)
+        d = self._rev[pw]              # a and c walk in direction d, b against it; the next block flips
+        self._rev[pw] = not d
         ta, ha, wa = self._out_dims(x, blk.a)
         a = self._alloc(n, ta, ha, wa, blk.a.cout)
-        self._conv(blk.a, x, a)
+        self._conv(blk.a, x, a, reverse=d)
         tb, hb, wb = self._out_dims(a, blk.b)
         b = self._alloc(n, tb, hb, wb, blk.b.cout)
-        self._conv(blk.b, a, b)
+        self._conv(blk.b, a, b, reverse=not d)
         self._free(a)
         sc = None
         y = None
         if blk.branch1 is not None:
             y = self._alloc(n, tb, hb, wb, blk.c.cout, pitch=out_pitch)
-            if self._conv_with_shortcut(blk.c, b, blk.branch1, x, y):
+            if self._conv_with_shortcut(blk.c, b, blk.branch1, x, y, reverse=d):
                 res = None
             else:
                 self._free(y)
                 y = None
                 sc = self._alloc(n, tb, hb, wb, blk.branch1.cout)
-                self._conv(blk.branch1, x, sc)
+                self._conv(blk.branch1, x, sc, reverse=d)
                 res = sc
         else:
             res = x
@@ -442,7 +455,7 @@ class ClipEngine:
             y = self._alloc(n, tb, hb, wb, blk.c.cout, pitch=out_pitch)
         # relu(shortcut + BN(c(.)))   resnet_helper.py:352-358
         if res is not None:
-            self._conv(blk.c, b, y, residual=res, relu=True)
+            self._conv(blk.c, b, y, residual=res, relu=True, reverse=d)
         self._free(b)
         if sc is not None:
             self._free(sc)
