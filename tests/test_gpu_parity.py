@@ -370,3 +370,36 @@ def test_whole_video_event_windowing():
     assert torch.equal(by_clip.view(2, 5, -1), feats)
     model.micro_batch = 5                       # one video per engine run
     assert torch.equal(model.extract_video_features(videos.cuda()), feats)
+
+
+def test_input_slots_overlap_pack_and_trunk():
+    """Two input slots (pack of batch k+1 on its own stream while the trunk reads batch k): same bits as the
+    one-slot engine, through the raw engine and through HostPipeline."""
+    from vidsitu_b200.pipeline import HostPipeline
+    model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=10, crop=64)
+    model = model.cuda()
+    batches = [synthetic_frames(5, 32, 64, seed=300 + i) for i in range(4)]
+    want = [model.extract_features(b.cuda()).clone() for b in batches]
+    model2, _, _ = build_model("slow_fast_nl_r50_8x8", seed=10, crop=64)
+    model2.input_slots = 2
+    model2 = model2.cuda()
+    eng = model2._engine(5, torch.device("cuda"))
+    assert len(eng.input_sets) == 2
+    eng.capture()
+    eng.load_frames(batches[0].cuda(), 0)
+    eng.load_frames(batches[1].cuda(), 1)
+    eng.replay(1)
+    assert torch.equal(eng.feats, want[1])
+    eng.replay(0)
+    assert torch.equal(eng.feats, want[0])
+    pipe = HostPipeline(model2, 5, torch.device("cuda"))
+    slots = []
+    got = []
+    for i, b in enumerate(batches):
+        slots.append(pipe.submit(b.pin_memory()))
+        if len(slots) > 1:
+            got.append(pipe.result(slots.pop(0)).clone())
+    got.append(pipe.result(slots.pop(0)).clone())
+    pipe.flush()
+    for g, w in zip(got, want):
+        assert torch.equal(g.cuda(), w)

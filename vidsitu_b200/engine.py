@@ -73,7 +73,7 @@ class _Pool:
 class ClipEngine:
     def __init__(self, spec: NetSpec, tensors: Dict[str, torch.Tensor], n: int, dtype: int = VSB_BF16,
                  device: Optional[torch.device] = None, proj_head: Optional[Sequence[torch.Tensor]] = None,
-                 tune: Optional[dict] = None, bn_eps: float = 1e-5):
+                 tune: Optional[dict] = None, bn_eps: float = 1e-5, input_slots: int = 1):
         if not torch.cuda.is_available():
             raise VsbError("ClipEngine needs a CUDA device: the forward is made of sm_100a kernels only")
         self.spec = spec
@@ -120,10 +120,16 @@ class ClipEngine:
         # never written again.
         self.x_off = 3 if dtype == VSB_BF16 else 0
         self.w_buf = self.crop + 16 if dtype == VSB_BF16 else self.crop
-        self.inputs: List[Act] = []
-        for t in frames:
-            buf = torch.zeros(self.n * t * self.crop * self.w_buf * 4, dtype=self.tdt, device=self.device)
-            self.inputs.append(Act(buf, self.n, t, self.crop, self.w_buf, 4, 4, c_real=3))
+        # `input_slots` > 1: several input buffer sets, so that the frames of batch k+1 can be packed (on another
+        # stream) while the trunk still reads batch k; everything behind the stems is shared
+        self.input_sets: List[List[Act]] = []
+        self._slot = 0
+        for _ in range(max(1, int(input_slots))):
+            acts = []
+            for t in frames:
+                buf = torch.zeros(self.n * t * self.crop * self.w_buf * 4, dtype=self.tdt, device=self.device)
+                acts.append(Act(buf, self.n, t, self.crop, self.w_buf, 4, 4, c_real=3))
+            self.input_sets.append(acts)
         # slow-pathway temporal indices, exactly as utils/video_utils.py:62-69
         t_fast = spec.num_frames
         self.fast_idx = list(range(t_fast))
@@ -174,7 +180,8 @@ class ClipEngine:
         return Act(buf, n, t, h, w, c, pitch, 0, c_real)
 
     def _free(self, a: Act) -> None:
-        if a.buf is None or any(a.buf is i.buf for i in self.inputs) or any(a.buf is d for d in self._dedicated):
+        if a.buf is None or any(a.buf is i.buf for acts in self.input_sets for i in acts) or \
+                any(a.buf is d for d in self._dedicated):
             return
         self._pool.give(a.buf)
 
@@ -364,12 +371,22 @@ class ClipEngine:
         return True
 
     def _stem(self, p: int, x: Act) -> Act:
-        st = self.spec.stems[p]
-        cs = st.conv
+        """Stem conv of pathway p.  One plan per input slot (the slots differ only in the input buffer): the op
+        runs the plan of the slot selected at launch / capture time."""
+        cs = self.spec.stems[p].conv
         n, t = x.n, x.t
         to, ho, wo = self._out_dims(Act(None, n, t, self.crop, self.crop, 4, 4), cs)
         y = self._alloc(n, to, ho, wo, cs.cout, pitch=cs.cout)   # dense [.., cout] (no channel padding yet)
         y.c = cs.cout
+        plans = [self._stem_plan(cs, inputs[p], y, to, ho, wo) for inputs in self.input_sets]
+        self._keep += plans
+        es = 2 if self.dtype == VSB_BF16 else 4
+        self.op_bytes[cs.key] = es * (x.pixels * 4 + y.pixels * cs.cout)
+        self.trunk_ops.append((cs.key, lambda: plans[self._slot].run(), float(y.pixels) * cs.flops_per_out_pixel))
+        return y
+
+    def _stem_plan(self, cs: ConvSpec, x: Act, y: Act, to: int, ho: int, wo: int) -> ConvPlan:
+        n, t = x.n, x.t
         scale, bias = self._affine(cs, cs.cout)
         wt = self._tensor(cs.key + ".weight")
         tune = {k: v for k, v in self._tune(cs.key).items() if k in _PLAN_KNOBS}
@@ -409,11 +426,7 @@ class ClipEngine:
             wp = pack_conv_weight(wt, 4, cs.cout, self.tdt)
             plan = ConvPlan(self.dtype, x, wp, cs.cout, cs.kernel, cs.stride, cs.pad, None, scale, bias, y, None,
                             True)
-        self._keep.append(plan)
-        es = 2 if self.dtype == VSB_BF16 else 4
-        self.op_bytes[cs.key] = es * (x.pixels * 4 + y.pixels * cs.cout)
-        self.trunk_ops.append((cs.key, plan.run, float(y.pixels) * cs.flops_per_out_pixel))
-        return y
+        return plan
 
     def _maxpool(self, name: str, x: Act, kernel, stride, pad, pitch: Optional[int] = None, min_c: int = 0) -> Act:
         to = (x.t + 2 * pad[0] - kernel[0]) // stride[0] + 1
@@ -598,8 +611,21 @@ class ClipEngine:
         return Act(x_s.buf, x_s.n, x_s.t, x_s.h, x_s.w, x_s.pitch, x_s.pitch, 0, x_s.pitch)
 
     # --------------------------------------------------------------------------- running
-    def load_frames(self, frames: torch.Tensor) -> None:
-        """uint8 [n, T, H, W, 3] frames of the fast/single pathway window (dat_loader.py:474-476)."""
+    @property
+    def inputs(self) -> List[Act]:
+        """Input activations of the current slot."""
+        return self.input_sets[self._slot]
+
+    def select_slot(self, slot: int) -> None:
+        if not 0 <= slot < len(self.input_sets):
+            raise VsbError(f"input slot {slot} outside [0, {len(self.input_sets)})")
+        self._slot = slot
+
+    def load_frames(self, frames: torch.Tensor, slot: Optional[int] = None) -> None:
+        """uint8 [n, T, H, W, 3] frames of the fast/single pathway window (dat_loader.py:474-476), packed into
+        input slot `slot` (default: the current one)."""
+        if slot is not None:
+            self.select_slot(slot)
         spec = self.spec
         if frames.shape[0] != self.n or frames.shape[1] != spec.num_frames:
             raise VsbError(f"expected frames [{self.n}, {spec.num_frames}, {self.crop}, {self.crop}, 3]")
@@ -724,15 +750,22 @@ class ClipEngine:
             self.run()          # warm-up outside capture (lazy module loading, func attributes)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.run()
-        self._graph = g
+        keep = self._slot
+        self._graph = []
+        for slot in range(len(self.input_sets)):   # one graph per input slot (only the stem launches differ)
+            self._slot = slot
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run()
+            self._graph.append(g)
+        self._slot = keep
 
-    def replay(self) -> None:
+    def replay(self, slot: Optional[int] = None) -> None:
         if self._graph is None:
             self.capture()
-        self._graph.replay()
+        if slot is not None:
+            self.select_slot(slot)
+        self._graph[self._slot].replay()
 
     @property
     def num_launches(self) -> int:

@@ -35,11 +35,13 @@ class HostPipeline:
         self.slot_free = [torch.cuda.Event() for _ in range(slots)]
         self.done = [torch.cuda.Event() for _ in range(slots)]
         self._k = 0
+        self.eng_slots = len(self.eng.input_sets)
+        self.in_free = [torch.cuda.Event() for _ in range(self.eng_slots)]
         self.h2d_bytes = self.stage[0].numel()
         self.d2h_bytes = self.out_feats[0].numel() * 4 + (self.out_logits[0].numel() * 4 if want_logits else 0)
         with torch.cuda.stream(self.compute_stream):
             self.eng.capture()
-        for e in self.slot_free:
+        for e in self.slot_free + self.in_free:
             e.record(self.compute_stream)
 
     def submit(self, frames_host: torch.Tensor) -> int:
@@ -48,15 +50,24 @@ class HostPipeline:
             raise VsbError("frames must live in pinned host memory")
         s = self._k % len(self.stage)
         self._k += 1
+        es = s % self.eng_slots                                   # input slot of the engine
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.slot_free[s])      # the pack kernels of the previous user are done
             self.stage[s].copy_(frames_host, non_blocking=True)
+            if self.eng_slots > 1:
+                # pack on the copy stream into the engine's other input slot: it overlaps the previous batch's
+                # trunk, which still reads its own slot (freed when that trunk's stems are done = in_free)
+                self.copy_stream.wait_event(self.in_free[es])
+                self.eng.load_frames(self.stage[s], es)
+                self.slot_free[s].record(self.copy_stream)
             self.h2d_done[s].record(self.copy_stream)
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(self.h2d_done[s])
-            self.eng.load_frames(self.stage[s])
-            self.slot_free[s].record(self.compute_stream)
-            self.eng.replay()
+            if self.eng_slots == 1:
+                self.eng.load_frames(self.stage[s])
+                self.slot_free[s].record(self.compute_stream)
+            self.eng.replay(es)
+            self.in_free[es].record(self.compute_stream)
             self.out_feats[s].copy_(self.eng.feats, non_blocking=True)
             if self.want_logits:
                 self.out_logits[s].copy_(self.eng.logits, non_blocking=True)

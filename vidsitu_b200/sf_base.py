@@ -194,7 +194,8 @@ class SFBase(nn.Module):
         if eng is None:
             tensors = {k: v for k, v in self.sf_mdl.state_dict().items()}
             ph = (self.proj_head[0].weight, self.proj_head[0].bias, self.proj_head[2].weight, self.proj_head[2].bias)
-            eng = ClipEngine(self.spec, tensors, n, _PRECISIONS[self.precision], device, proj_head=ph, tune=self.tune)
+            eng = ClipEngine(self.spec, tensors, n, _PRECISIONS[self.precision], device, proj_head=ph, tune=self.tune,
+                             input_slots=getattr(self, "input_slots", 1))
             self._engines[key] = eng
         return eng
 
