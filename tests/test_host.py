@@ -211,3 +211,22 @@ def test_tuning_table_is_well_formed():
         assert sig.match(k), k
         assert knobs and set(knobs) <= set(_PLAN_KNOBS) | {"algo", "win_group"}, (k, knobs)
         assert knobs.get("epi_n", 32) in (16, 32, 64) and knobs.get("epi_bufs", 2) in (2, 3, 4)
+
+
+def test_ctypes_conv_desc_matches_the_c_header(tmp_path):
+    """The ctypes mirror of vsb_conv_desc (vidsitu_b200/lib.py) against the C header, compiled with gcc: total
+    size and the offsets of fields spread over the struct (a silent mismatch would corrupt every plan)."""
+    import ctypes as C
+    import subprocess
+    fields = ["dtype", "wgt", "cout", "scale", "out_pitch", "block_n", "algo", "kw_c_hi", "in2", "sw2", "epi_n",
+              "epi_bufs", "flags", "out_f16", "wgt_clip_rows"]
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vidsitu_b200.h"\nint main(void){'
+                   'printf("%zu", sizeof(vsb_conv_desc));'
+                   + "".join(f'printf(" %zu", offsetof(vsb_conv_desc, {f}));' for f in fields) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got[0] == C.sizeof(L.ConvDesc)
+    for f, off in zip(fields, got[1:]):
+        assert getattr(L.ConvDesc, f).offset == off, f
