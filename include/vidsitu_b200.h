@@ -146,6 +146,7 @@ typedef struct vsb_conv_desc {
 #define VSB_PLAN_REVERSE 128      /* walk the output in DESCENDING order (tiles / clips).  A kernel that starts where
                                      its producer finished finds the most recently written ~100 MB of its input still
                                      in the 126 MB L2; the engine alternates the direction along each pathway.       */
+#define VSB_PLAN_TWO_SM_RESIDENT 256 /* CTA pairs with the weight block resident, half in each CTA (K*block_n <= 224 KB) */
 #define VSB_PLAN_ONE_SM 32        /* im2col: never use CTA pairs                                          */
 
 typedef struct vsb_conv_plan vsb_conv_plan;

@@ -29,6 +29,7 @@ CANDIDATES = {
     "st2bn128": {"stages": 2, "block_n": 128}, "st3bn128": {"stages": 3, "block_n": 128},
     "bn256en32eb4": {"block_n": 256, "epi_n": 32, "epi_bufs": 4}, "bn256en32": {"block_n": 256, "epi_n": 32},
     "st2sw": {"stages": 2, "flags": 1}, "en32eb4sw": {"epi_n": 32, "epi_bufs": 4, "flags": 1},
+    "sm2r": {"flags": 256}, "sm2r_en32eb4": {"flags": 256, "epi_n": 32, "epi_bufs": 4}, "sm2r_en32": {"flags": 256, "epi_n": 32},
     "sm1": {"flags": 32}, "sm2": {"flags": 16}, "sm2en32": {"flags": 16, "epi_n": 32}, "sm2en32eb4": {"flags": 16, "epi_n": 32, "epi_bufs": 4},
     "nots": {"flags": 64}, "ts_en64": {"epi_n": 64},
     "sm2en16": {"flags": 16, "epi_n": 16}, "en16": {"epi_n": 16},

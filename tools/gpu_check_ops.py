@@ -315,6 +315,8 @@ TWO_SM_CASES = [
     ("sm2_sp3_256_many_tiles", 8, 8, 14, 14, 256, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, dict(flags=16)),  # 98 m-tiles
     ("sm2_sp3_32_256_k32", 2, 4, 28, 28, 32, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, dict(flags=16)),      # 64-byte rows
     ("sm2_pw_96_128_k32", 2, 4, 14, 14, 96, 128, (1, 1, 1), (1, 1, 1), (0, 0, 0), True, True, dict(flags=16)),
+    ("sm2r_pw_256_1024_res", 2, 4, 14, 14, 256, 1024, (1, 1, 1), (1, 1, 1), (0, 0, 0), True, True, dict(flags=256)),   # resident halves
+    ("sm2r_pw_128_512", 3, 2, 28, 28, 128, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0), False, True, dict(flags=256)),
     ("sm2_sp3_256_bn128", 4, 4, 14, 14, 256, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, dict(flags=16, block_n=128)),
 ]
 

@@ -122,7 +122,9 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* tmem_full = empty_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* epi_ready = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_ready + kEW * kMaxEpiBufs2);
+  uint64_t* bres_bar = epi_ready + kEW * kMaxEpiBufs2;  // resident weight halves of the pair have landed (leader's copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint8_t* bres = smem + p.off_bres;                    // this CTA's half of the resident weight block
 
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -154,6 +156,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&tmem_empty[i], 2 * kEW);  // (leader's copy is the one in use) every epilogue warp of the pair
     }
     for (int i = 0; i < kEW * kMaxEpiBufs2; ++i) mbar_init(&epi_ready[i], 1);
+    mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -172,6 +175,17 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       constexpr int CPS = 4 / KK;  // chunks per ring stage: a stage always carries 64 K-elements (4 MMAs)
       const uint32_t chunk_tx = 2u * (a_chunk_bytes + b_chunk_bytes);  // bytes of BOTH CTAs per chunk
       const uint32_t b_off = CPS * a_chunk_bytes;
+      const bool b_resident = p.b_resident != 0;
+      if (b_resident) {
+        // weight-stationary pair: each CTA fetches its half of the [block_n x K] block once; both halves' bytes
+        // are counted on the leader's barrier (the leader issues the MMAs)
+        const uint32_t bres_leader = mapa_u32(bres_bar, 0);
+        if (leader) mbar_expect_tx(bres_bar, 2u * (uint32_t)p.total_chunks * b_chunk_bytes);
+        for (int g = 0; g < p.total_chunks; ++g)
+          tma2_load_2d(bres + g * b_chunk_bytes, &map_b, bres_leader, g * kchunk,
+                       n_tile * p.block_n + (int)rank * (int)half_n);
+      }
+      const uint32_t chunk_tx_eff = b_resident ? 2u * a_chunk_bytes : chunk_tx;
       const int total_chunks = p.total_chunks, stages = p.stages;
       const int cin = p.cin, fkw = p.kw, fkh = p.kh, block_n = p.block_n;
       const int owo = p.wo, oho = p.ho, oto = p.to, sw = p.sw, sh = p.sh, st = p.st, lw = p.lw, lh = p.lh, lt = p.lt;
@@ -199,7 +213,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const int nch = left < CPS ? left : CPS;
           left -= nch;
           mbar_wait(&empty_bar[slot], parity);
-          if (leader) mbar_expect_tx(&full_bar[slot], nch * chunk_tx);
+          if (leader) mbar_expect_tx(&full_bar[slot], nch * chunk_tx_eff);
           const uint32_t full_leader = mapa_u32(&full_bar[slot], 0);
           uint8_t* a_dst = smem + (uint32_t)slot * stage_bytes;
           uint8_t* b_dst = a_dst + b_off;
@@ -211,7 +225,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             } else {
               tma2_load_im2col_5d(a_dst, &map_a2, full_leader, cc, w2, h2, d2, n0, 0, 0, 0);
             }
-            tma2_load_2d(b_dst, &map_b, full_leader, kcoord, ncol);
+            if (!b_resident) tma2_load_2d(b_dst, &map_b, full_leader, kcoord, ncol);
             a_dst += a_chunk_bytes;
             b_dst += b_chunk_bytes;
             kcoord += kchunk;
@@ -247,6 +261,9 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int total_chunks = p.total_chunks, stages = p.stages, block_n = p.block_n;
       int slot = 0, tcount = 0;
       uint32_t parity = 0, a_slot_lo = smem_lo;
+      const bool b_resident = p.b_resident != 0;
+      const uint32_t bres_lo = (smem_u32(bres) & 0x3FFFFu) >> 4;
+      if (b_resident) mbar_wait(bres_bar, 0);
       for (int pm = pm0; pm < pm_tiles; pm += pm_step, ++tcount) {
         const int acc = tcount & 1;
         mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);  // both CTAs drained this accumulator
@@ -263,8 +280,9 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
                 for (int k = 0; k < KK; ++k) {
                   const uint64_t adesc = desc_hi | (uint64_t)(desc_lo_flags | (a_slot_lo + c * a_chunk_lo + 2 * k));
-                  const uint64_t bdesc =
-                      desc_hi | (uint64_t)(desc_lo_flags | (a_slot_lo + b_off_lo + c * b_chunk_lo + 2 * k));
+                  const uint32_t b_lo = b_resident ? bres_lo + (uint32_t)(g + c) * b_chunk_lo
+                                                   : a_slot_lo + b_off_lo + c * b_chunk_lo;
+                  const uint64_t bdesc = desc_hi | (uint64_t)(desc_lo_flags | (b_lo + 2 * k));
                   umma2_bf16(tmem_d, adesc, bdesc, idesc, (g | c | k) != 0 ? 1u : 0u);
                 }
               }

@@ -659,7 +659,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   const int num_kstages = ceil_div(total_chunks, cps);
   const int bar_bytes = 1024 + 2048;  // barriers + the CTA's (scale, bias) table (block_n <= 256 float2)
   static const bool no_bres_env = getenv("VSB_NO_BRES") != nullptr;
-  const bool no_bres = no_bres_env || (d->flags & (VSB_PLAN_STREAM_WEIGHTS | VSB_PLAN_TWO_SM)) || d->wgt_clip_rows > 0;
+  const bool no_bres = no_bres_env || (d->flags & (VSB_PLAN_STREAM_WEIGHTS | VSB_PLAN_TWO_SM | VSB_PLAN_TWO_SM_RESIDENT)) || d->wgt_clip_rows > 0;
   static const char* ew_env = getenv("VSB_EPI_WARPS");
   // (measured on B200: the 16-warp epilogue shape does not beat 8 warps -- these layers are HBM-bound, the
   // accumulator wait is back-pressure -- so it is opt-in: VSB_EPI_WARPS=16)
@@ -878,10 +878,15 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   // with one chunk = two MMAs per stage the issuer was the bottleneck: 0.46 vs 0.42 ms)
   const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && !d->out_f16 && !d->wgt_clip_rows && block_n == 256 && (kchunk == 64 || kchunk == 32) &&
                            total_chunks >= 8 && p.total_tiles / p.n_tiles >= 16;
-  if (((d->flags & VSB_PLAN_TWO_SM) || two_sm_auto) && !d->out_f16 && !d->wgt_clip_rows && (kchunk == 64 || kchunk == 32) && !b_resident &&
+  if (((d->flags & (VSB_PLAN_TWO_SM | VSB_PLAN_TWO_SM_RESIDENT)) || two_sm_auto) && !d->out_f16 && !d->wgt_clip_rows && (kchunk == 64 || kchunk == 32) && !b_resident &&
       block_n % 16 == 0 && block_n >= 32 && epi_warps == 8 && p.total_tiles / p.n_tiles >= 2) {
-    const uint32_t stage2 = (uint32_t)((kBlockM + block_n / 2) * 128);  // 64 K-elements per stage: 64 / kchunk chunks
-    const long long fixed2 = (long long)epi_bufs * epi_buf_bytes + bar_bytes + 1024;
+    // weight-stationary pair (opt-in): each CTA keeps its half of the [block_n x K] block, the ring carries A only
+    const long long bres_half = (long long)total_chunks * (block_n / 2) * kchunk * 2;
+    const bool resident2 = (d->flags & VSB_PLAN_TWO_SM_RESIDENT) && bres_half <= 112 * 1024;
+    const uint32_t stage2 = resident2 ? (uint32_t)(kBlockM * 128)
+                                      : (uint32_t)((kBlockM + block_n / 2) * 128);  // 64 K-elements per stage
+    const long long bres2 = resident2 ? ((bres_half + 1023) & ~1023ll) : 0;
+    const long long fixed2 = bres2 + (long long)epi_bufs * epi_buf_bytes + bar_bytes + 1024;
     int stages2 = (int)((227 * 1024 - fixed2) / stage2);
     if (d->stages && stages2 > d->stages) stages2 = d->stages;
     if (stages2 > 12) stages2 = 12;
@@ -895,7 +900,8 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
       p.stages = stages2;
       p.stage_bytes = stage2;
       p.off_bres = (uint32_t)stages2 * stage2;
-      p.off_epi = p.off_bres;
+      p.off_epi = p.off_bres + (uint32_t)bres2;
+      p.b_resident = resident2 ? 1 : 0;
       p.off_bar = p.off_epi + epi_bufs * epi_buf_bytes;
       p.idesc = umma_idesc_bf16(256, block_n);
       plan->smem_bytes = (size_t)stages2 * stage2 + (size_t)fixed2;
