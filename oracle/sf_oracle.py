@@ -86,6 +86,12 @@ def clips_from_frames(frames_u8: torch.Tensor, cfg) -> List[torch.Tensor]:
 
 # --------------------------------------------------------------------------- model side
 def _bn(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor) -> torch.Tensor:
+    if prefix + ".bn.running_mean" in sd:
+        # SubBatchNorm3d in eval mode (batchnorm_helper.py:97-109): affine-less BN on the aggregated statistics,
+        # then the single weight / bias pair
+        x = F.batch_norm(x, sd[prefix + ".bn.running_mean"], sd[prefix + ".bn.running_var"], None, None,
+                         training=False, eps=BN_EPS)
+        return x * sd[prefix + ".weight"].view(-1, 1, 1, 1) + sd[prefix + ".bias"].view(-1, 1, 1, 1)
     return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
                         sd[prefix + ".bias"], training=False, eps=BN_EPS)
 

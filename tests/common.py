@@ -18,12 +18,12 @@ NUM_VERBS = 1560  # synthetic verb vocabulary size
 
 
 def build_model(sf_mdl_name: str, seed: int = 0, randomize_bn: bool = True, precision: str = "bf16", crop: int = 224,
-                **kw):
+                sf_overrides: dict = None, **kw):
     """vidsitu_b200.SFBase with seeded random-init weights (torch.manual_seed(seed)) and, by
     default, seeded non-trivial BatchNorm statistics (SURVEY.md section 7 hard part 1)."""
     from vidsitu_b200.sf_base import SFBase
 
-    cfg = make_cfg(sf_mdl_name)
+    cfg = make_cfg(sf_mdl_name, **(sf_overrides or {}))
     cfg.sf_mdl.DATA.CROP_SIZE = crop
     comm = make_comm(cfg.sf_mdl, NUM_VERBS)
     torch.manual_seed(seed)

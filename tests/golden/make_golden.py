@@ -37,6 +37,8 @@ CASES = {
     "c2d_n2_64": ("c2d_r50_8x8", 2, 64, 4),
     "sf101_n1_224": ("slow_fast_r101_16x8", 1, 224, 5),
     "sf101_n2_64": ("slow_fast_r101_16x8", 2, 64, 13),
+    # BN.NORM_TYPE = sub_batchnorm (SubBatchNorm3d: `<bn>.bn.*` aggregated + `<bn>.split_bn.*` per-split statistics)
+    "sf50_subbn_n2_64": ("slow_fast_nl_r50_8x8", 2, 64, 14, {"BN": {"NORM_TYPE": "sub_batchnorm", "NUM_SPLITS": 2}}),
 }
 
 
@@ -99,9 +101,10 @@ def load_reference():
 def run_case(name, M, VU):
     from common import build_model, synthetic_frames
 
-    sf_name, n, crop, seed = CASES[name]
+    sf_name, n, crop, seed = CASES[name][:4]
+    overrides = CASES[name][4] if len(CASES[name]) > 4 else None
     raw = "rawinit" in name
-    mine, cfg, comm = build_model(sf_name, seed=seed, randomize_bn=not raw, crop=crop)
+    mine, cfg, comm = build_model(sf_name, seed=seed, randomize_bn=not raw, crop=crop, sf_overrides=overrides)
     sd = mine.state_dict()
     ref = M.SFBase(cfg, comm).eval()
     missing, unexpected = ref.load_state_dict(sd, strict=True)
@@ -145,6 +148,7 @@ def run_case(name, M, VU):
         out[f"fmap{p}_sample"] = flat[:: max(1, flat.numel() // 8192)][:8192].numpy().astype(np.float32)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     meta = {"case": name, "sf_mdl_name": sf_name, "clips": n, "crop": crop, "seed": seed, "raw_init": raw,
+            "sf_overrides": overrides,
             "ref_cpu_seconds": round(dt, 3), "threads": torch.get_num_threads(), "num_state_dict_keys": len(sd),
             "pooled_absmax": float(pooled.abs().max()), "torch": torch.__version__}
     print(json.dumps(meta))

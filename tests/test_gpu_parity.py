@@ -187,7 +187,7 @@ def test_conv_rejects_bad_arguments():
 def _run_model(case, precision):
     m = META[case]
     model, cfg, _ = build_model(m["sf_mdl_name"], seed=m["seed"], randomize_bn=not m["raw_init"], crop=m["crop"],
-                                precision=precision)
+                                precision=precision, sf_overrides=m.get("sf_overrides"))
     model = model.cuda()
     frames = synthetic_frames(m["clips"], cfg.sf_mdl.DATA.NUM_FRAMES, m["crop"], seed=1234 + m["seed"]).cuda()
     feats, logits = model.extract_features(frames, want_logits=True)
@@ -195,7 +195,7 @@ def _run_model(case, precision):
     return model, cfg, frames, feats.cpu().numpy(), logits.cpu().numpy()
 
 
-BF16_CASES = ["sf50_n2_64", "sf50_rawinit_n2_64", "i3d_nln_n2_64", "slow_n2_64", "c2d_n2_64", "sf101_n2_64",
+BF16_CASES = ["sf50_n2_64", "sf50_rawinit_n2_64", "i3d_nln_n2_64", "slow_n2_64", "c2d_n2_64", "sf101_n2_64", "sf50_subbn_n2_64",
               "sf50_n5_224", "i3d_n2_224", "i3d_nln_n2_224", "sf101_n1_224"]
 
 
@@ -210,7 +210,8 @@ def test_bf16_features_match_reference(case):
     print(f"{case}: bf16 top-5 set equal to reference: {np.array_equal(np.sort(top5, -1), np.sort(g['top5'], -1))}")
 
 
-@pytest.mark.parametrize("case", ["sf50_n2_64", "i3d_nln_n2_64", "sf101_n2_64", "sf50_n5_224", "i3d_nln_n2_224"])
+@pytest.mark.parametrize("case", ["sf50_n2_64", "i3d_nln_n2_64", "sf101_n2_64", "sf50_subbn_n2_64", "sf50_n5_224",
+                                  "i3d_nln_n2_224"])
 def test_fp32_top5_and_features_match_reference(case):
     g = np.load(os.path.join(GOLD, case + ".npz"))
     _, _, _, feats, logits = _run_model(case, "fp32")

@@ -105,9 +105,11 @@ def test_training_mode_is_refused():
 
 def test_unknown_config_values_are_rejected():
     cfg = make_cfg("slow_fast_nl_r50_8x8")
-    cfg.sf_mdl.BN.NORM_TYPE = "sync_batchnorm"
+    cfg.sf_mdl.BN.NORM_TYPE = "layernorm"              # get_norm raises for anything but the three BN flavours
     with pytest.raises(NotImplementedError):
         build_spec(cfg.sf_mdl)
+    cfg.sf_mdl.BN.NORM_TYPE = "sync_batchnorm"         # NaiveSyncBatchNorm3d: a BatchNorm3d in eval mode
+    assert build_spec(cfg.sf_mdl).norm_type == "sync_batchnorm"
     cfg = make_cfg("i3d_r50_8x8")
     cfg.sf_mdl.MODEL.ARCH = "x3d"
     with pytest.raises(NotImplementedError):
@@ -230,3 +232,32 @@ def test_ctypes_conv_desc_matches_the_c_header(tmp_path):
     assert got[0] == C.sizeof(L.ConvDesc)
     for f, off in zip(fields, got[1:]):
         assert getattr(L.ConvDesc, f).offset == off, f
+
+
+def test_sub_batchnorm_layout_and_aggregation():
+    """BN.NORM_TYPE = sub_batchnorm (SubBatchNorm3d, batchnorm_helper.py:37-109): the state_dict key set the real
+    reference accepted with strict=True when the fixture was made (996 keys), the aggregation formula, and the
+    key lookup the engine folds from."""
+    import json
+    from vidsitu_b200.model import SubBNParams
+    from vidsitu_b200.weights import bn_tensor_keys
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_meta.json")))["sf50_subbn_n2_64"]
+    model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=meta["seed"], crop=64, sf_overrides=meta["sf_overrides"])
+    sd = model.state_dict()
+    assert len(sd) == meta["num_state_dict_keys"] == 996
+    assert "sf_mdl.s2.pathway0_res0.branch2.a_bn.bn.running_var" in sd
+    assert sd["sf_mdl.s2.pathway0_res0.branch2.a_bn.split_bn.running_mean"].numel() == 2 * 64
+    bn = SubBNParams(6, 3)
+    g = torch.Generator().manual_seed(0)
+    bn.split_bn.running_mean.copy_(torch.randn(18, generator=g))
+    bn.split_bn.running_var.copy_(torch.rand(18, generator=g) + 0.5)
+    bn.aggregate_stats()
+    m, v = bn.split_bn.running_mean.view(3, 6), bn.split_bn.running_var.view(3, 6)
+    assert torch.allclose(bn.bn.running_mean, m.mean(0))
+    assert torch.allclose(bn.bn.running_var, v.mean(0) + ((m - m.mean(0)) ** 2).mean(0))
+    t = {k[len("sf_mdl."):]: v for k, v in sd.items() if k.startswith("sf_mdl.")}
+    assert bn_tensor_keys(t, "s1.pathway0_stem.bn")[2:] == ("s1.pathway0_stem.bn.bn.running_mean",
+                                                          "s1.pathway0_stem.bn.bn.running_var")
+    plain, _, _ = build_model("slow_fast_nl_r50_8x8", seed=0, crop=64)
+    tp = {k[len("sf_mdl."):]: v for k, v in plain.state_dict().items() if k.startswith("sf_mdl.")}
+    assert bn_tensor_keys(tp, "s1.pathway0_stem.bn")[2] == "s1.pathway0_stem.bn.running_mean"

@@ -11,7 +11,8 @@ cases = sys.argv[1:] or list(META)
 for case in cases:
     m = META[case]; g = np.load(os.path.join(GOLD, case + ".npz"))
     for prec in ("bf16", "fp32"):
-        model, cfg, _ = build_model(m["sf_mdl_name"], seed=m["seed"], randomize_bn=not m["raw_init"], crop=m["crop"], precision=prec)
+        model, cfg, _ = build_model(m["sf_mdl_name"], seed=m["seed"], randomize_bn=not m["raw_init"], crop=m["crop"], precision=prec,
+                                    sf_overrides=m.get("sf_overrides"))
         model = model.cuda()
         frames = synthetic_frames(m["clips"], cfg.sf_mdl.DATA.NUM_FRAMES, m["crop"], seed=1234 + m["seed"]).cuda()
         feats, logits = model.extract_features(frames, want_logits=True)

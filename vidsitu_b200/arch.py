@@ -107,6 +107,8 @@ class NetSpec:
     mean: Tuple[float, ...] = (0.45, 0.45, 0.45)
     std: Tuple[float, ...] = (0.225, 0.225, 0.225)
     reverse_input_channel: bool = False
+    norm_type: str = "batchnorm"   # BN.NORM_TYPE
+    num_splits: int = 1            # BN.NUM_SPLITS (sub_batchnorm)
     sampling_rate: int = 2      # DATA.SAMPLING_RATE: frame step inside an event window
     target_fps: int = 30        # DATA.TARGET_FPS of the extracted frames
 
@@ -194,8 +196,10 @@ def _stage(name: str, dim_in, dim_out, dim_inner, temp_kernels, strides, num_blo
 
 def build_spec(cfg) -> NetSpec:
     """cfg = `cfg.sf_mdl` (yacs CfgNode or vidsitu_b200.config.AttrDict)."""
-    if cfg.BN.NORM_TYPE != "batchnorm":
-        raise NotImplementedError("only BN.NORM_TYPE='batchnorm' (frozen, eval mode) is supported")
+    # get_norm (batchnorm_helper.py:15-34): all three are frozen per-channel affines in eval mode; sub_batchnorm
+    # keeps its statistics under `<bn>.bn.*` / `<bn>.split_bn.*` (SubBatchNorm3d, batchnorm_helper.py:37-109)
+    if cfg.BN.NORM_TYPE not in ("batchnorm", "sub_batchnorm", "sync_batchnorm"):
+        raise NotImplementedError(f"Norm type {cfg.BN.NORM_TYPE} is not supported")
     if cfg.DETECTION.ENABLE:
         raise NotImplementedError("DETECTION.ENABLE is not on the VidSitu path")
     name = cfg.MODEL.MODEL_NAME
@@ -269,4 +273,5 @@ def build_spec(cfg) -> NetSpec:
         mean=tuple(cfg.DATA.MEAN), std=tuple(cfg.DATA.STD),
         reverse_input_channel=bool(cfg.DATA.REVERSE_INPUT_CHANNEL),
         sampling_rate=int(cfg.DATA.SAMPLING_RATE), target_fps=int(getattr(cfg.DATA, "TARGET_FPS", 30)),
+        norm_type=str(cfg.BN.NORM_TYPE), num_splits=int(getattr(cfg.BN, "NUM_SPLITS", 1)),
     )

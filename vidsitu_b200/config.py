@@ -42,7 +42,7 @@ class AttrDict(dict):
 
 # Defaults of the keys on the hot path (SlowFast/slowfast/config/defaults.py).
 _DEFAULTS = {
-    "BN": {"NORM_TYPE": "batchnorm"},                                   # defaults.py:36
+    "BN": {"NORM_TYPE": "batchnorm", "NUM_SPLITS": 1, "NUM_SYNC_DEVICES": 1},   # defaults.py:36-52
     "RESNET": {
         "TRANS_FUNC": "bottleneck_transform", "NUM_GROUPS": 1, "WIDTH_PER_GROUP": 64,
         "INPLACE_RELU": True, "STRIDE_1X1": False, "ZERO_INIT_FINAL_BN": False, "DEPTH": 50,

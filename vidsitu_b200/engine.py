@@ -26,7 +26,7 @@ from . import ops
 from .arch import BlockSpec, ConvSpec, NetSpec, NonlocalSpec
 from .lib import VSB_BF16, VSB_F32, VsbError
 from .ops import Act, ConvPlan
-from .weights import (fold_bn, group_conv_weight, group_tap_ranges, identity_affine, pack_conv_weight, round_up,
+from .weights import (bn_tensor_keys, fold_bn, group_conv_weight, group_tap_ranges, identity_affine, pack_conv_weight, round_up,
                       slice_tap_channels)
 
 
@@ -193,8 +193,8 @@ class ClipEngine:
     def _affine(self, cs: ConvSpec, cout_store: int):
         bias = self._tensor(cs.key + ".bias") if cs.has_bias else None
         if cs.bn is not None:
-            return fold_bn(self._tensor(cs.bn + ".weight"), self._tensor(cs.bn + ".bias"),
-                           self._tensor(cs.bn + ".running_mean"), self._tensor(cs.bn + ".running_var"),
+            kw, kb, km, kv = bn_tensor_keys(self._t, cs.bn)
+            return fold_bn(self._tensor(kw), self._tensor(kb), self._tensor(km), self._tensor(kv),
                            self.bn_eps, cout_store, bias)
         return identity_affine(cs.cout, cout_store, bias, self.device)
 

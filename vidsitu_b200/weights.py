@@ -27,6 +27,14 @@ def pack_conv_weight(w: torch.Tensor, cin_store: int, cout_store: int, dtype: to
     return out.to(dtype).contiguous()
 
 
+def bn_tensor_keys(tensors, bn_key: str):
+    """(weight, bias, running_mean, running_var) key names of the frozen norm layer `bn_key` in a reference-layout
+    state_dict: nn.BatchNorm3d / NaiveSyncBatchNorm3d keep all four side by side, SubBatchNorm3d keeps the
+    statistics its eval forward uses under `<bn_key>.bn.*` (batchnorm_helper.py:55-62, 97-109)."""
+    stats = bn_key + ".bn" if (bn_key + ".bn.running_mean") in tensors else bn_key
+    return bn_key + ".weight", bn_key + ".bias", stats + ".running_mean", stats + ".running_var"
+
+
 def fold_bn(gamma, beta, mean, var, eps: float, cout_store: int, conv_bias=None):
     """y = gamma * (x + conv_bias - mean) / sqrt(var + eps) + beta  ==  scale * x + bias."""
     scale = gamma.double() / torch.sqrt(var.double() + eps)
