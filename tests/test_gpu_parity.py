@@ -404,3 +404,42 @@ def test_input_slots_overlap_pack_and_trunk():
     pipe.flush()
     for g, w in zip(got, want):
         assert torch.equal(g.cuda(), w)
+
+
+def test_feature_dump_cli_from_jpeg_frames(tmp_path):
+    """tools/extract_features.py (the counterpart of feat_extractor.py:120-175) on two synthetic videos stored the
+    reference's way (300 JPEGs each): the .npy files equal the oracle run on the same decoded frames through the
+    reference's own window tables (bf16 tolerance), one [5, 2304] fp32 file per video."""
+    import extract_features as X
+    from PIL import Image
+    from oracle import sf_oracle as O
+    from vidsitu_b200 import frames_io as F
+    from vidsitu_b200.feat_io import read_frm_feats
+    rng = np.random.default_rng(5)
+    names = ["v_one_seg_0", "v_two_seg_3"]
+    for v in names:
+        d = tmp_path / "frames" / v
+        d.mkdir(parents=True)
+        for ix in range(1, 301):
+            Image.fromarray(rng.integers(0, 256, size=(40, 56, 3), dtype=np.uint8)).save(d / f"{v}_{ix:06d}.jpg")
+    (tmp_path / "split.json").write_text(json.dumps(names))
+    torch.manual_seed(21)
+    rc = X.main(["--frames-dir", str(tmp_path / "frames"), "--split-file", str(tmp_path / "split.json"),
+                 "--out-dir", str(tmp_path / "feats"), "--mdl-name-used", "slow_fast_test", "--crop", "64",
+                 "--videos-per-batch", "2", "--workers", "0"])
+    assert rc == 0
+    # the same random-init weights for the oracle: the CLI builds SFBase(cfg, comm) under the current torch seed
+    from vidsitu_b200.config import make_cfg, make_comm
+    from vidsitu_b200.sf_base import SFBase
+    cfg = make_cfg("slow_fast_nl_r50_8x8")
+    cfg.sf_mdl.DATA.CROP_SIZE = 64
+    torch.manual_seed(21)
+    ref_model = SFBase(cfg, make_comm(cfg.sf_mdl, 1560), micro_batch=10)
+    windows = O.event_frame_indices(32, 2)
+    for v in names:
+        paths = F.frame_paths(tmp_path / "frames", v)
+        clips = torch.from_numpy(np.stack([np.stack([F.read_img(paths[i], 64) for i in w]) for w in windows]))
+        _, pooled, _ = O.sfbase_forward(ref_model.state_dict(), cfg.sf_mdl, O.clips_from_frames(clips, cfg.sf_mdl))
+        got = read_frm_feats(tmp_path / "feats" / "slow_fast_test", v)
+        assert tuple(got.shape) == (5, 2304) and got.dtype == torch.float32
+        assert_bf16_close(got.numpy(), pooled.numpy(), f"{v} features from JPEG frames")

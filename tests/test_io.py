@@ -122,3 +122,44 @@ def test_feature_writer_rejects_wrong_shapes(tmp_path):
     with pytest.raises(ValueError):
         w.put(torch.zeros((5, 16), dtype=torch.float64), ["a"])
     w.close()
+
+
+def _write_video(tdir, vseg, total, rng):
+    from PIL import Image
+    d = tdir / vseg
+    d.mkdir(parents=True)
+    for ix in range(1, total + 1):
+        arr = rng.integers(0, 256, size=(48, 64, 3), dtype=np.uint8)
+        Image.fromarray(arr).save(d / f"{vseg}_{ix:06d}.jpg", quality=95)
+
+
+def test_frame_ingest_matches_the_reference_reader(tmp_path):
+    """frames_io: the `{vseg}_{i:06d}.jpg` naming (dat_loader.py:455-458), `read_img` (:183-191: open, RGB,
+    resize with PIL's default filter), and the whole-video tensor holding exactly the frames the event windows
+    select, at their own indices."""
+    from PIL import Image
+    from oracle import sf_oracle as O
+    from vidsitu_b200 import frames_io as F
+    rng = np.random.default_rng(0)
+    _write_video(tmp_path, "v_abc_seg_1", 300, rng)
+    paths = F.frame_paths(tmp_path, "v_abc_seg_1")
+    assert len(paths) == 300 and paths[0].name == "v_abc_seg_1_000001.jpg" and paths[299].name == "v_abc_seg_1_000300.jpg"
+    ref = np.array(Image.open(paths[7]).convert("RGB").resize((224, 224)))            # the reference's three calls
+    assert np.array_equal(F.read_img(paths[7]), ref) and ref.shape == (224, 224, 3)
+    need = F.needed_frames(32, 2)
+    windows = O.event_frame_indices(32, 2)
+    assert need == sorted({i for w in windows for i in w}) and len(need) <= 160
+    vid = F.load_video(tmp_path, "v_abc_seg_1", need, size=32)
+    assert vid.dtype == torch.uint8 and tuple(vid.shape) == (300, 32, 32, 3)
+    for ev, w in enumerate(windows):                                                 # every window frame is there
+        clip = np.stack([F.read_img(paths[i], 32) for i in w])
+        assert np.array_equal(vid[w].numpy(), clip), ev
+    unused = sorted(set(range(300)) - set(need))
+    assert unused and not vid[unused].any()
+    ds = F.VideoFrames(tmp_path, ["v_abc_seg_1"], 32, 2, size=32)
+    frames, idxs = F.collate_videos([ds[0]])
+    assert tuple(frames.shape) == (1, 300, 32, 32, 3) and idxs == [0]
+    (tmp_path / "split.json").write_text('["v_abc_seg_1"]')
+    assert F.read_vseg_list(tmp_path / "split.json") == ["v_abc_seg_1"]
+    with pytest.raises(AssertionError):
+        F.load_video(tmp_path, "missing", need, size=32)

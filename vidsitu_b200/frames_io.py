@@ -1,0 +1,95 @@
+"""Frame ingest of the offline feature dump (host side).
+
+The reference stores every 10-second video as 300 JPEGs `{video_frms_tdir}/{vseg}/{vseg}_{i:06d}.jpg`
+(i = 1..300, 30 fps; `VsituDS.get_frms_all` vidsitu_code/dat_loader.py:454-458) and, per event, opens
+the NUM_FRAMES frames of the window with PIL, converts to RGB and resizes to 224 x 224
+(`read_img` :183-191), then normalises and packs them on the CPU (:474-486) - 160 decodes and
+5 x 24 MB of fp32 per video.  Here a video is decoded ONCE into a uint8 `[300, H, W, 3]` tensor, only
+the frames some event window selects (`events.event_frame_indices`; at most 150 distinct ones for
+SlowFast 8x8), and everything after the decode - windowing, normalisation, pathway packing - runs in
+the pack kernel on the device-resident video (`SFBase.extract_video_features`).
+
+JPEG decoding itself stays on the host (PIL, exactly the reference's three calls, in DataLoader
+worker processes): it is outside the hot path's scope.
+"""
+from __future__ import annotations
+
+import json
+import pickle
+from pathlib import Path
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from .events import VIDEO_FRAMES, event_frame_indices
+
+
+def frame_paths(video_frms_tdir, vseg: str, num_frames: int = VIDEO_FRAMES) -> List[Path]:
+    """`{tdir}/{vseg}/{vseg}_{ix:06d}.jpg` for ix = 1..300 (dat_loader.py:455-458): list index = frame index."""
+    d = Path(video_frms_tdir) / vseg
+    return [d / f"{vseg}_{ix:06d}.jpg" for ix in range(1, num_frames + 1)]
+
+
+def read_img(img_fpath, size: int = 224) -> np.ndarray:
+    """H x W x 3 uint8, as `VsituDS.read_img` (dat_loader.py:183-191): open, RGB, `resize((224, 224))` with
+    PIL's default filter."""
+    from PIL import Image
+    img = Image.open(img_fpath).convert("RGB")
+    img = img.resize((size, size))
+    return np.array(img)
+
+
+def needed_frames(num_frames: int, sampling_rate: int, fps: int = 30, total: int = VIDEO_FRAMES) -> List[int]:
+    """Distinct frame indices any of the five event windows selects."""
+    return sorted({i for win in event_frame_indices(num_frames, sampling_rate, fps, total) for i in win})
+
+
+def load_video(video_frms_tdir, vseg: str, needed: Sequence[int], size: int = 224,
+               total: int = VIDEO_FRAMES) -> torch.Tensor:
+    """uint8 [total, size, size, 3]; frames outside `needed` stay zero (no window reads them)."""
+    paths = frame_paths(video_frms_tdir, vseg, total)
+    out = np.zeros((total, size, size, 3), dtype=np.uint8)
+    for i in needed:
+        if not paths[i].exists():
+            raise AssertionError(f"{paths[i]} doesn't exist")     # read_file_with_assertion semantics
+        out[i] = read_img(paths[i], size)
+    return torch.from_numpy(out)
+
+
+def read_vseg_list(path) -> List[str]:
+    """A split file of the reference (`cfg.ds.vsitu.split_files_lb[split]`: JSON list of vseg names; pickle and
+    one-name-per-line text are accepted too)."""
+    p = Path(path)
+    if not p.exists():
+        raise AssertionError(f"{p} doesn't exist")
+    if p.suffix == ".json":
+        return list(json.load(open(p)))
+    if p.suffix in (".pkl", ".pickle"):
+        return list(pickle.load(open(p, "rb")))
+    return [ln.strip() for ln in open(p) if ln.strip()]
+
+
+class VideoFrames(Dataset):
+    """One item = one video: (`frames` uint8 [300, size, size, 3], index).  The analogue of `VsituDS_All`
+    (vidsitu_code/feat_extractor.py:20-74) for the whole-video path: DataLoader workers do the JPEG decodes,
+    the main process only moves uint8 tensors."""
+
+    def __init__(self, video_frms_tdir, vseg_lst: Sequence[str], num_frames: int, sampling_rate: int,
+                 fps: int = 30, size: int = 224, total: int = VIDEO_FRAMES):
+        self.tdir = Path(video_frms_tdir)
+        self.vseg_lst = list(vseg_lst)
+        self.size, self.total = int(size), int(total)
+        self.needed = needed_frames(num_frames, sampling_rate, fps, total)
+
+    def __len__(self) -> int:
+        return len(self.vseg_lst)
+
+    def __getitem__(self, idx: int) -> Tuple[torch.Tensor, int]:
+        return load_video(self.tdir, self.vseg_lst[idx], self.needed, self.size, self.total), idx
+
+
+def collate_videos(batch):
+    frames = torch.stack([b[0] for b in batch])
+    return frames, [b[1] for b in batch]
