@@ -519,6 +519,10 @@ class ClipEngine:
         dense = all(a.pitch == a.c and a.c_off == 0 for a in (theta, phi, g, att))
         if not dense or c % 64 or phi.c != c or g.c != c or att.c != c or tk % 2:
             return False
+        if not nl.softmax:
+            # "dot_product" instantiation: no VidSitu config places such a block (Kinetics_c2_SLOW_8x8_R50.yaml has
+            # none), so the batched route was never measured with it - it stays on the CUDA-core kernel
+            return False
         if tk < 128:
             # few keys (small crops): bf16 probabilities do not average out (max error 0.0100 vs 0.0070 of the feature
             # scale on the crop-64 fixture) and the CUDA-core kernel costs nothing at this size
