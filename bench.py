@@ -6,7 +6,7 @@
     python bench.py --impl reference --gpus N --steps K ...   # the reference path on the host CPU cores
 
 A step = one pass of the hot path over one batch of 64 clips per GPU: frame pack (uint8 ->
-bf16 NTHWC, both pathways) + 110 conv launches + pools + GAP + projection head (+ for N>1 the
+bf16 NTHWC, both pathways) + 105 conv launches + pools + GAP + projection head (+ for N>1 the
 all-gather of the [64, 2304] features).  `value` times it with the uint8 frames already in HBM;
 `e2e` times the same through vidsitu_b200.HostPipeline with the frames in pinned host memory
 (H2D of every batch and D2H of its features inside the timed region).
