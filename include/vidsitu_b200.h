@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VSB_ABI_VERSION 4
+#define VSB_ABI_VERSION 5
 
 typedef enum vsb_status {
   VSB_OK = 0,
@@ -158,6 +158,44 @@ void vsb_conv3d_plan_destroy(vsb_conv_plan* plan);
 int vsb_conv3d_plan_out_shape(const vsb_conv_plan* plan, int* to, int* ho, int* wo);
 /* 2*M*cout*taps*cin of the convolution as launched (padded channels included) */
 double vsb_conv3d_plan_flops(const vsb_conv_plan* plan);
+
+/* ------------------------------------------------- fused identity bottleneck block
+ * Replaces, in ONE launch, the three convs of BottleneckTransform (SlowFast/slowfast/models/
+ * resnet_helper.py:225-240: a = Conv3d [kt,1,1] pad [kt/2,0,0] + BN + ReLU, b = Conv3d [1,3,3] pad [0,1,1]
+ * + BN + ReLU, c = Conv3d 1x1x1 + BN) and the identity ResBlock around them (resnet_helper.py:352-358:
+ * relu(x + branch2(x))), for blocks WITHOUT a projection shortcut and with unit strides / dilation:
+ *   out = relu(x + sc * (relu(sb * (relu(sa * (x (*) wa) + ba) (*) wb) + bb) . wc) + bc)
+ * a's and b's outputs are rounded to bf16 exactly where the three-launch path rounds them, but never leave the
+ * SM: x is read and out is written, 8 instead of 16 bottleneck-widths of HBM traffic per pixel.  bf16 only.
+ * x / out: [n, t, h, w, pitch] with c stored channels (multiple of 16, <= 256); d = stored bottleneck width
+ * (16, 32 or 64); wa [d][kt][c], wb [d][3*3][d] (tap = kh*3 + kw), wc [c][d], all bf16 K-major, zero-padded to
+ * the stored widths; s? / b? = folded frozen-BatchNorm scale / bias (fp32; [d], [d], [c]).
+ * A "pixel" may be a pixel GROUP: the caller can restate thin layers on groups of J pixels along W
+ * (block-Toeplitz weights, [.., W, C] viewed as [.., W/J, J*C]); the kernel only sees slots.          */
+typedef struct vsb_bottleneck_desc {
+  const void* x;
+  int n, t, h, w, c, x_pitch;
+  void* out;
+  int out_pitch;
+  int d;
+  int kt;                       /* temporal taps of conv a: 1 or 3                 */
+  const void* wa;
+  const void* wb;
+  const void* wc;
+  const float* sa; const float* ba;
+  const float* sb; const float* bb;
+  const float* sc; const float* bc;
+  /* tuning, 0 = automatic: x ring depth, tiles per walk, CTAs */
+  int stages, walk_len, grid;
+} vsb_bottleneck_desc;
+
+typedef struct vsb_bottleneck_plan vsb_bottleneck_plan;
+int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* desc, vsb_bottleneck_plan** plan);
+int vsb_bottleneck_run(const vsb_bottleneck_plan* plan, void* stream);
+void vsb_bottleneck_plan_destroy(vsb_bottleneck_plan* plan);
+/* out8 = {slots per flat row, flat rows per frame, x ring stages, tiles per walk, grid, dynamic shared memory
+ * bytes, tiles per clip, TMEM columns} */
+int vsb_bottleneck_plan_info(const vsb_bottleneck_plan* plan, long long* out8);
 
 /* --------------------------------------------------------------- max-pool
  * Replaces nn.MaxPool3d (stem_helper.py:169-171, video_model_builder.py:235-241,

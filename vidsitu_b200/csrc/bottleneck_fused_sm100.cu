@@ -1,0 +1,801 @@
+// Fused identity bottleneck block: out = relu(x + BN_c(c(relu(BN_b(b(relu(BN_a(a(x)))))))))  in ONE launch.
+//
+// Reference ops replaced: BottleneckTransform a -> b -> c (SlowFast/slowfast/models/resnet_helper.py:225-240:
+// a = Conv3d [kt,1,1] + BN + ReLU, b = Conv3d [1,3,3] pad 1 + BN + ReLU, c = Conv3d 1x1x1 + BN) and the identity
+// ResBlock around it (resnet_helper.py:352-358: relu(x + branch2(x))), for blocks without a projection shortcut
+// and with unit strides.  Layer by layer this is three launches and 16 d bytes of HBM traffic per pixel
+// (d = bottleneck width in bf16 bytes: x 4d in, a d out / d in, b d out / d in, residual 4d in, out 4d); here
+// x is read (once from HBM, the temporal taps and the residual from L2) and out is written: 8 d.
+//
+// Geometry: "flat raster walk".  A clip is laid out as one flat array of SLOTS (slot = one GEMM row = one pixel,
+// or one pixel group when the host restates the convs on groups): T frames x FP flat rows x RP slots, RP a power
+// of two > W, FP > H, so every image row is followed by >= 1 zero slot and every frame by >= 1 zero row -- those
+// zeros ARE the padding of the 3x3 conv.  M-tile m = flat slots [128 m, 128 m + 128).  For every tile of a walk
+//   a-phase : a[m]   = relu(BN(x[m] . Wa))            x chunks by TMA (kt frames x channel chunks), acc in TMEM,
+//                                                      epilogue -> bf16 -> shared-memory RING of a-tiles (zeros
+//                                                      written at the padding slots)
+//   b-phase : b[m]   = relu(BN(sum_taps a[m + dy RP + dx] . Wb[tap]))   every tap is a 128-row UMMA operand whose
+//                                                      descriptor start address is shifted by whole slots inside
+//                                                      the ring (hardware swizzle is a function of the absolute
+//                                                      address: conv_win_sm100.cu), acc in TMEM, epilogue -> bf16
+//                                                      -> shared-memory P tile
+//   c-phase : out[m] = relu(BN(b[m] . Wc) + x[m])     acc in TMEM, residual by TMA into the staging slab, TMA store
+// The ring holds 4 a-tiles plus a MIRROR of ring tile 0 behind tile 3, so that the 128-slot operand of any tap,
+// which starts in tile (m-1) or m and runs into the next one, is contiguous in shared memory.  All weights are
+// resident.  Warp roles (18 warps): 0-3 a-epilogue, 4-7 b-epilogue, 8-15 c-epilogue (two groups of four, alternate
+// tiles), 16 TMA producer, 17 MMA issuer.  The MMA issuer runs the three phases software-pipelined over the
+// CTA's whole tile sequence: step g issues a(g), b(centre g-2) and c(centre g-3); tcgen05.mma executes in issue
+// order and a commit covers everything issued before it, which is what makes the ring reuse safe without extra
+// barriers (a(g)'s epilogue overwrites the ring tile that b(centre g-5) was the last to read).
+#include <cuda.h>
+
+#include <stdlib.h>
+
+#include <mutex>
+#include <new>
+
+#include "common.h"
+#include "conv_plan.h"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace vsb {
+
+namespace {
+constexpr int kRing = 4;  // a-tiles in the ring (power of two) + 1 mirror tile
+constexpr int kMaxBoxes = 16;
+constexpr int kMaxStages = 24;
+constexpr int kBEpiWarp0 = 4, kCEpiWarp0 = 8, kProducerWarp = 16, kMmaWarp = 17;
+constexpr int kThreads = 18 * 32;
+constexpr int kCEpiWarps = 8;
+constexpr int kMaxEpiBufs = 3;
+}  // namespace
+
+struct FusedParams {
+  // flat slot space
+  int W, H, T, n_clips;
+  int RP, rp_shift, FP;
+  int rows_per_tile;            // 128 / RP
+  int box_rows, boxes_per_tile; // x TMA boxes: box_rows flat rows each
+  uint32_t box_bytes;
+  int tiles_per_clip;
+  int walk_len, walks_per_clip, total_walks;
+  int row_bias;                 // multiple of FP added before the (t, y) split so that the dividend is >= 0
+  // channels
+  int kt, kc, cchunks, chunks_per_tile;
+  int ksteps_x;                 // kc / 16
+  int d16, ksteps_d;            // bottleneck width (multiple of 16), d16 / 16
+  int cout;
+  uint32_t x_row_bytes, a_row_bytes, chunk_bytes;
+  int stages;
+  // shared-memory layout (bytes from the 1 KiB-aligned base)
+  uint32_t off_wa, off_wb, off_wc, off_ring, off_p, off_epi, off_bar, off_tab;
+  uint32_t wa_block_bytes, wb_block_bytes, wc_bytes, tile_bytes;
+  // TMEM columns
+  uint32_t tmem_cols, tm_a, tm_b, tm_c, tm_ab_stride, tm_c_stride;
+  uint32_t idesc_a, idesc_b, idesc_c;
+  // c epilogue
+  int epi_n, epi_chunks, epi_bufs, bw, bh;
+  const float *sa, *ba, *sb, *bb, *sc, *bc;
+};
+
+// Enumerates the a-tiles of one CTA: walks w = blockIdx.x, + gridDim.x, ...; tiles j = 0 .. L+1 of each walk are the
+// flat tiles m0-1 .. m0+L of clip n (the first and last one only feed the 3x3 halo of their neighbours).
+struct ATileIter {
+  int w, j, L, n, m0;
+  __device__ __forceinline__ void load_walk(const FusedParams& p) {
+    if (w < p.total_walks) {
+      n = w / p.walks_per_clip;
+      const int c = w - n * p.walks_per_clip;
+      m0 = c * p.walk_len;
+      const int m1 = m0 + p.walk_len < p.tiles_per_clip ? m0 + p.walk_len : p.tiles_per_clip;
+      L = m1 - m0;
+    }
+  }
+  __device__ __forceinline__ void init(const FusedParams& p) {
+    w = blockIdx.x;
+    j = 0;
+    load_walk(p);
+  }
+  __device__ __forceinline__ bool valid(const FusedParams& p) const { return w < p.total_walks; }
+  __device__ __forceinline__ void next(const FusedParams& p) {
+    if (++j == L + 2) {
+      j = 0;
+      w += gridDim.x;
+      load_walk(p);
+    }
+  }
+  __device__ __forceinline__ int m() const { return m0 - 1 + j; }
+};
+
+// 16 accumulator columns of one row -> bf16 -> 32 bytes of a swizzled K-major operand row, written to dst_s and
+// (when dst2_s != 0) to its mirror; `keep` = 0 writes zeros (padding slots).  ReLU always.
+__device__ __forceinline__ void fb_convert16(const uint32_t* v, uint32_t sb_s, uint32_t dst_s, uint32_t dst2_s,
+                                             uint32_t off0, uint32_t swz_mask, uint32_t keep) {
+  const uint32_t s0 = off0 ^ (((off0 >> 7) & swz_mask) << 4);
+  const uint32_t off1 = off0 + 16;
+  const uint32_t s1 = off1 ^ (((off1 >> 7) & swz_mask) << 4);
+  uint32_t o[8];
+#pragma unroll
+  for (int qq = 0; qq < 8; ++qq) {
+    const float4 p2 = lds128f(sb_s + 16 * qq);  // (scale, bias) of two columns
+    const float x0 = fmaxf(fmaf(__uint_as_float(v[2 * qq]), p2.x, p2.y), 0.f);
+    const float x1 = fmaxf(fmaf(__uint_as_float(v[2 * qq + 1]), p2.z, p2.w), 0.f);
+    o[qq] = pack_bf16x2(x0, x1) & keep;
+  }
+  sts128(dst_s + s0, o[0], o[1], o[2], o[3]);
+  sts128(dst_s + s1, o[4], o[5], o[6], o[7]);
+  if (dst2_s) {
+    sts128(dst2_s + s0, o[0], o[1], o[2], o[3]);
+    sts128(dst2_s + s1, o[4], o[5], o[6], o[7]);
+  }
+}
+
+// One warp converts its 32 rows x ncols accumulator block into rows [row0, row0 + 32) of an operand tile.
+__device__ __forceinline__ void fb_convert_rows(uint32_t taddr, int ncols, uint32_t dst_s, uint32_t dst2_s,
+                                                uint32_t row_bytes, uint32_t swz_mask, int row, uint32_t sb_s,
+                                                uint32_t keep) {
+  if (ncols >= 32) {
+    for (int j0 = 0; j0 < ncols; j0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + j0, v);
+      tmem_ld_wait();
+      const uint32_t off0 = (uint32_t)row * row_bytes + j0 * 2;
+      fb_convert16(v, sb_s + j0 * 8, dst_s, dst2_s, off0, swz_mask, keep);
+      fb_convert16(v + 16, sb_s + (j0 + 16) * 8, dst_s, dst2_s, off0 + 32, swz_mask, keep);
+    }
+  } else {
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+    tmem_ld_wait();
+    fb_convert16(v, sb_s, dst_s, dst2_s, (uint32_t)row * row_bytes, swz_mask, keep);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wa,
+                        const __grid_constant__ CUtensorMap map_wb, const __grid_constant__ CUtensorMap map_wc,
+                        const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out,
+                        const __grid_constant__ FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* x_empty = x_full + kMaxStages;
+  uint64_t* a_full = x_empty + kMaxStages;
+  uint64_t* a_done = a_full + 2;
+  uint64_t* b_full = a_done + 2;
+  uint64_t* b_done = b_full + 2;
+  uint64_t* c_full = b_done + 2;
+  uint64_t* c_empty = c_full + 2;
+  uint64_t* epi_ready = c_empty + 2;
+  uint64_t* w_bar = epi_ready + kCEpiWarps * kMaxEpiBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_wa);
+    tma_prefetch_desc(&map_wb);
+    tma_prefetch_desc(&map_wc);
+    tma_prefetch_desc(&map_res);
+    tma_prefetch_desc(&map_out);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_done[i], 4);
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_done[i], 4);
+      mbar_init(&c_full[i], 1);
+      mbar_init(&c_empty[i], 4);
+    }
+    for (int i = 0; i < kCEpiWarps * kMaxEpiBufs; ++i) mbar_init(&epi_ready[i], 1);
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  // (scale, bias) pairs of the three convs
+  float2* sb_a = reinterpret_cast<float2*>(smem + p.off_tab);
+  float2* sb_b = sb_a + p.d16;
+  float2* sb_c = sb_b + p.d16;
+  for (int c = threadIdx.x; c < p.d16; c += blockDim.x) {
+    sb_a[c] = make_float2(p.sa[c], p.ba[c]);
+    sb_b[c] = make_float2(p.sb[c], p.bb[c]);
+  }
+  for (int c = threadIdx.x; c < p.cout; c += blockDim.x) sb_c[c] = make_float2(p.sc[c], p.bc[c]);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (one thread)
+      // resident weights: Wa as chunks_per_tile blocks [d16 rows x kc], Wb as 9 tap blocks [d16 x d16], Wc [cout x d16]
+      mbar_expect_tx(w_bar, (uint32_t)p.chunks_per_tile * (uint32_t)p.d16 * p.x_row_bytes +
+                                9u * (uint32_t)p.d16 * p.a_row_bytes + (uint32_t)p.cout * p.a_row_bytes);
+      for (int q = 0; q < p.chunks_per_tile; ++q)
+        tma_load_2d(smem + p.off_wa + q * p.wa_block_bytes, &map_wa, w_bar, q * p.kc, 0);
+      for (int tap = 0; tap < 9; ++tap)
+        tma_load_2d(smem + p.off_wb + tap * p.wb_block_bytes, &map_wb, w_bar, tap * p.d16, 0);
+      tma_load_2d(smem + p.off_wc, &map_wc, w_bar, 0, 0);
+
+      int slot = 0;
+      uint32_t parity = 1;  // first pass over the ring: slots are free
+      const int S = p.stages, nbox = p.boxes_per_tile, kt = p.kt, cch = p.cchunks, kc = p.kc;
+      const int FP = p.FP, pt = p.kt >> 1;
+      ATileIter it;
+      for (it.init(p); it.valid(p); it.next(p)) {
+        const int r0 = it.m() * p.rows_per_tile + p.row_bias;  // >= 0
+        int bt[kMaxBoxes], by[kMaxBoxes];
+        for (int b = 0; b < nbox; ++b) {
+          const int r = r0 + b * p.box_rows;
+          const int tq = r / FP;
+          bt[b] = tq - p.row_bias / FP;  // frame (may be -1 or T: zero-filled by the TMA unit)
+          by[b] = r - tq * FP;           // row inside the frame (>= H: zero-filled)
+        }
+        for (int dt = 0; dt < kt; ++dt) {
+          for (int cc = 0; cc < cch; ++cc) {
+            mbar_wait(&x_empty[slot], parity);
+            mbar_expect_tx(&x_full[slot], p.chunk_bytes);
+            uint8_t* dst = smem + (uint32_t)slot * p.chunk_bytes;
+            for (int b = 0; b < nbox; ++b)
+              tma_load_5d(dst + b * p.box_bytes, &map_x, &x_full[slot], cc * kc, 0, by[b], bt[b] + dt - pt, it.n);
+            if (++slot == S) {
+              slot = 0;
+              parity ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint64_t x_hi = umma_smem_desc(0, p.x_row_bytes) & 0xFFFFFFFF00000000ull;
+    const uint32_t x_fl = (uint32_t)(umma_smem_desc(0, p.x_row_bytes) & 0xFFFFC000ull);
+    const uint64_t d_hi = umma_smem_desc(0, p.a_row_bytes) & 0xFFFFFFFF00000000ull;
+    const uint32_t d_fl = (uint32_t)(umma_smem_desc(0, p.a_row_bytes) & 0xFFFFC000ull);
+    const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+    const uint32_t wa_lo = smem_lo + (p.off_wa >> 4), wb_lo = smem_lo + (p.off_wb >> 4), wc_lo = smem_lo + (p.off_wc >> 4);
+    const uint32_t ring_lo = smem_lo + (p.off_ring >> 4), p_lo = smem_lo + (p.off_p >> 4);
+    const uint32_t chunk_lo = p.chunk_bytes >> 4, tile_lo = p.tile_bytes >> 4;
+    const uint32_t wa_blk_lo = p.wa_block_bytes >> 4, wb_blk_lo = p.wb_block_bytes >> 4;
+    const int S = p.stages, cpt = p.chunks_per_tile, ksx = p.ksteps_x, ksd = p.ksteps_d;
+    const uint32_t idesc_a = p.idesc_a, idesc_b = p.idesc_b, idesc_c = p.idesc_c;
+    // tap table: start slot of tap (dy, dx) relative to the centre tile, as (starts in the previous tile?, 16-byte units)
+    uint32_t tap_off[9];
+    uint32_t tap_prev = 0;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int o = (tap / 3 - 1) * p.RP + (tap % 3 - 1);
+      if (o < 0) tap_prev |= 1u << tap;
+      tap_off[tap] = ((uint32_t)(o < 0 ? 128 + o : o) * p.a_row_bytes) >> 4;
+    }
+    int slot = 0;
+    uint32_t xpar = 0;
+    int g = 0;          // step = global index of the a-tile issued in this step
+    int gb = 0, gc = 0; // b-tiles / c-tiles issued so far
+    int a_waited = 0;   // a-tiles whose epilogue this thread has observed (in order)
+    int b_waited = 0;
+    int j1 = -1, j2 = -1;  // walk-local index of a-tiles g-1 and g-2 (-1: none)
+    mbar_wait(w_bar, 0);
+    ATileIter it;
+    it.init(p);
+    for (;; ++g) {
+      const bool have_a = it.valid(p);
+      if (!have_a && j1 < 2 && j2 < 2) break;
+      if (have_a) {
+        // accumulator g & 1 was last used by a-tile g-2: its epilogue must have drained it
+        while (a_waited < g - 1) {
+          mbar_wait(&a_done[a_waited & 1], (a_waited >> 1) & 1);
+          ++a_waited;
+        }
+        tc_fence_after();
+        const uint32_t tm_d = tmem_base + p.tm_a + (uint32_t)(g & 1) * p.tm_ab_stride;
+        for (int q = 0; q < cpt; ++q) {
+          mbar_wait(&x_full[slot], xpar);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = smem_lo + (uint32_t)slot * chunk_lo;
+            const uint32_t b_lo = wa_lo + (uint32_t)q * wa_blk_lo;
+            for (int k = 0; k < ksx; ++k)
+              umma_bf16(tm_d, x_hi | (uint64_t)(x_fl | (a_lo + 2 * k)), x_hi | (uint64_t)(x_fl | (b_lo + 2 * k)),
+                        idesc_a, (q | k) != 0 ? 1u : 0u);
+            umma_commit(&x_empty[slot]);
+            if (q == cpt - 1) umma_commit(&a_full[g & 1]);
+          }
+          __syncwarp();
+          if (++slot == S) {
+            slot = 0;
+            xpar ^= 1;
+          }
+        }
+      }
+      if (j1 >= 2) {
+        // b-tile whose centre is a-tile g-2 (previous g-3, next g-1): all three must be in the ring
+        while (a_waited < g) {
+          mbar_wait(&a_done[a_waited & 1], (a_waited >> 1) & 1);
+          ++a_waited;
+        }
+        while (b_waited < gb - 1) {
+          mbar_wait(&b_done[b_waited & 1], (b_waited >> 1) & 1);
+          ++b_waited;
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t prev_lo = ring_lo + (uint32_t)((g - 3) & (kRing - 1)) * tile_lo;
+          const uint32_t cen_lo = ring_lo + (uint32_t)((g - 2) & (kRing - 1)) * tile_lo;
+          const uint32_t tm_d = tmem_base + p.tm_b + (uint32_t)(gb & 1) * p.tm_ab_stride;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t a_lo = ((tap_prev >> tap) & 1 ? prev_lo : cen_lo) + tap_off[tap];
+            const uint32_t b_lo = wb_lo + (uint32_t)tap * wb_blk_lo;
+            for (int k = 0; k < ksd; ++k)
+              umma_bf16(tm_d, d_hi | (uint64_t)(d_fl | (a_lo + 2 * k)), d_hi | (uint64_t)(d_fl | (b_lo + 2 * k)),
+                        idesc_b, (tap | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&b_full[gb & 1]);
+        }
+        __syncwarp();
+        ++gb;
+      }
+      if (j2 >= 2) {
+        // c-tile gc: needs the P tile of b-tile gc and a drained accumulator gc & 1
+        while (b_waited < gc + 1) {
+          mbar_wait(&b_done[b_waited & 1], (b_waited >> 1) & 1);
+          ++b_waited;
+        }
+        mbar_wait(&c_empty[gc & 1], ((gc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = p_lo + (uint32_t)(gc & 1) * tile_lo;
+          const uint32_t tm_d = tmem_base + p.tm_c + (uint32_t)(gc & 1) * p.tm_c_stride;
+          for (int k = 0; k < ksd; ++k)
+            umma_bf16(tm_d, d_hi | (uint64_t)(d_fl | (a_lo + 2 * k)), d_hi | (uint64_t)(d_fl | (wc_lo + 2 * k)), idesc_c,
+                      k != 0 ? 1u : 0u);
+          umma_commit(&c_full[gc & 1]);
+        }
+        __syncwarp();
+        ++gc;
+      }
+      j2 = j1;
+      j1 = have_a ? it.j : -1;
+      if (have_a) it.next(p);
+    }
+  } else if (warp < kBEpiWarp0) {
+    // ---------------------------------------------------------------- a-epilogue (warps 0-3)
+    const int quarter = warp & 3;
+    const uint32_t swz_mask = p.a_row_bytes == 128 ? 7u : (p.a_row_bytes == 64 ? 3u : 1u);
+    const uint32_t lane_taddr = tmem_base + p.tm_a + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t ring_s = smem_u32(smem + p.off_ring);
+    const uint32_t sb_s = smem_u32(sb_a);
+    const int row = quarter * 32 + lane;
+    int g = 0;
+    ATileIter it;
+    for (it.init(p); it.valid(p); it.next(p), ++g) {
+      // is my slot a real pixel (group) of the clip, or padding?
+      const int f = it.m() * 128 + row;
+      const int r = (f >> p.rp_shift) + p.row_bias;  // arithmetic shift: floor for the negative halo tile
+      const int xs = f & (p.RP - 1);
+      const int tq = r / p.FP;
+      const int t = tq - p.row_bias / p.FP, y = r - tq * p.FP;
+      const uint32_t keep = (xs < p.W && y < p.H && t >= 0 && t < p.T) ? 0xFFFFFFFFu : 0u;
+      const int pos = g & (kRing - 1);
+      const uint32_t dst = ring_s + (uint32_t)pos * p.tile_bytes;
+      const uint32_t dst2 = pos == 0 ? ring_s + (uint32_t)kRing * p.tile_bytes : 0u;
+      mbar_wait(&a_full[g & 1], (g >> 1) & 1);
+      tc_fence_after();
+      fb_convert_rows(lane_taddr + (uint32_t)(g & 1) * p.tm_ab_stride, p.d16, dst, dst2, p.a_row_bytes, swz_mask, row,
+                      sb_s, keep);
+      fence_proxy_async_smem();  // ring writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_done[g & 1]);
+    }
+  } else if (warp < kCEpiWarp0) {
+    // ---------------------------------------------------------------- b-epilogue (warps 4-7)
+    const int quarter = warp & 3;
+    const uint32_t swz_mask = p.a_row_bytes == 128 ? 7u : (p.a_row_bytes == 64 ? 3u : 1u);
+    const uint32_t lane_taddr = tmem_base + p.tm_b + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t p_s = smem_u32(smem + p.off_p);
+    const uint32_t sb_s = smem_u32(sb_b);
+    const int row = quarter * 32 + lane;
+    int gb = 0;
+    ATileIter it;
+    for (it.init(p); it.valid(p); it.next(p)) {
+      if (it.j < 2) continue;
+      mbar_wait(&b_full[gb & 1], (gb >> 1) & 1);
+      tc_fence_after();
+      fb_convert_rows(lane_taddr + (uint32_t)(gb & 1) * p.tm_ab_stride, p.d16, p_s + (uint32_t)(gb & 1) * p.tile_bytes, 0u,
+                      p.a_row_bytes, swz_mask, row, sb_s, 0xFFFFFFFFu);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_done[gb & 1]);
+      ++gb;
+    }
+  } else if (warp < kProducerWarp) {
+    // ---------------------------------------------------------------- c-epilogue (warps 8-15)
+    // group grp (four warps = the four TMEM lane quarters) takes the c-tiles of parity grp; every warp owns 32 GEMM
+    // rows = a [bw slots x bh rows] box of the output and walks the tile's column chunks through its private slabs.
+    const int cw = warp - kCEpiWarp0;
+    const int quarter = cw & 3, grp = cw >> 2;
+    const uint32_t epi_row_bytes = p.epi_n * 2;
+    const uint32_t swz_mask = epi_row_bytes == 128 ? 7u : (epi_row_bytes == 64 ? 3u : 1u);
+    const uint32_t lane_taddr = tmem_base + p.tm_c + (uint32_t)grp * p.tm_c_stride + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t slab_bytes = 32 * epi_row_bytes;
+    const int nb = p.epi_bufs, chunks = p.epi_chunks;
+    uint8_t* my_bufs = smem + p.off_epi + (size_t)cw * nb * slab_bytes;
+    uint64_t* my_ready = epi_ready + cw * kMaxEpiBufs;
+    const uint32_t sb_s = smem_u32(sb_c);
+    // output box of (tile m, this warp): returns false when the whole box is padding
+    auto box_of = [&](int n, int m, int& xs0, int& y, int& tn) {
+      const int f0 = m * 128 + quarter * 32;
+      const int r = f0 >> p.rp_shift;
+      xs0 = f0 & (p.RP - 1);
+      const int t = r / p.FP;
+      y = r - t * p.FP;
+      tn = n * p.T + t;
+      return y < p.H && xs0 < p.W;
+    };
+    // next b-tile of this group at or after the iterator's position; gbx counts all b-tiles passed
+    auto seek = [&](ATileIter& it, int& gbx) {
+      while (it.valid(p)) {
+        if (it.j >= 2) {
+          if ((gbx & 1) == grp) return true;
+          ++gbx;
+        }
+        it.next(p);
+      }
+      return false;
+    };
+    // prefetch cursor (lane 0): next chunk of this warp whose slab has not been armed yet
+    ATileIter pf;
+    int pf_gb = 0, pf_chunk = 0, pf_q = 0;
+    pf.init(p);
+    bool pf_ok = seek(pf, pf_gb);
+    auto arm_next = [&]() {
+      const int bsel = pf_q % nb;
+      int xs0, y, tn;
+      if (box_of(pf.n, pf.m0 + pf.j - 2, xs0, y, tn)) {
+        mbar_expect_tx(&my_ready[bsel], slab_bytes);
+        tma_load_4d(my_bufs + bsel * slab_bytes, &map_res, &my_ready[bsel], pf_chunk * p.epi_n, xs0, y, tn);
+      } else {
+        mbar_arrive(&my_ready[bsel]);
+      }
+      ++pf_q;
+      if (++pf_chunk == chunks) {
+        pf_chunk = 0;
+        ++pf_gb;
+        pf.next(p);
+        pf_ok = seek(pf, pf_gb);
+      }
+    };
+    if (lane == 0) {
+      for (int i = 0; i < nb - 1 && pf_ok; ++i) arm_next();
+    }
+    __syncwarp();
+    int q = 0, gbx = 0, tcount = 0;
+    ATileIter it;
+    it.init(p);
+    while (seek(it, gbx)) {
+      int xs0, y, tn;
+      const bool live = box_of(it.n, it.m0 + it.j - 2, xs0, y, tn);
+      mbar_wait(&c_full[grp], tcount & 1);
+      tc_fence_after();
+      for (int c = 0; c < chunks; ++c) {
+        const int b = q % nb;
+        uint8_t* buf = my_bufs + b * slab_bytes;
+        mbar_wait(&my_ready[b], (q / nb) & 1);  // slab free (+ residual landed)
+        const int col0 = c * p.epi_n;
+        if (live)
+          epi_convert_chunk<true>(lane_taddr + col0, p.epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane,
+                                  sb_s + col0 * 8, 0.f);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (live) tma_store_4d(&map_out, buf, col0, xs0, y, tn);  // slots >= W / rows >= H are clipped by the TMA unit
+          tma_store_commit();
+          if (pf_ok) {
+            tma_store_wait_read1();
+            arm_next();
+          }
+        }
+        __syncwarp();
+        ++q;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&c_empty[grp]);
+      ++tcount;
+      ++gbx;
+      it.next(p);
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+}  // namespace vsb
+
+// ------------------------------------------------------------------ host side
+using namespace vsb;
+
+struct vsb_bottleneck_plan {
+  vsb_bottleneck_desc desc;
+  CUtensorMap map_x, map_wa, map_wb, map_wc, map_res, map_out;
+  FusedParams params;
+  size_t smem_bytes;
+  unsigned grid;
+};
+
+static int fb_encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                              strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed (CUresult %d)", what, (int)r);
+    return VSB_ERR_CUDA;
+  }
+  return VSB_OK;
+}
+
+extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bottleneck_plan** out_plan) {
+  VSB_CHECK_ARG(d && out_plan, "null argument");
+  *out_plan = nullptr;
+  VSB_CHECK_ARG(d->x && d->out && d->wa && d->wb && d->wc, "null tensor pointer");
+  VSB_CHECK_ARG(d->sa && d->ba && d->sb && d->bb && d->sc && d->bc, "null scale / bias pointer");
+  VSB_CHECK_ARG(d->n > 0 && d->t > 0 && d->h > 0 && d->w > 0, "non-positive extent");
+  VSB_CHECK_ARG(d->kt == 1 || d->kt == 3, "kt must be 1 or 3");
+  VSB_CHECK_ARG(d->d == 16 || d->d == 32 || d->d == 64, "bottleneck width (stored) must be 16, 32 or 64");
+  VSB_CHECK_ARG(d->c % 16 == 0 && d->c >= 16 && d->c <= 256, "block width (stored) must be a multiple of 16 in [16, 256]");
+  VSB_CHECK_ARG(d->x_pitch >= d->c && d->out_pitch >= d->c && d->x_pitch % 8 == 0 && d->out_pitch % 8 == 0,
+                "pitches must be >= c and multiples of 8 elements");
+  VSB_CHECK_ARG(((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->out) |
+                  reinterpret_cast<uintptr_t>(d->wa) | reinterpret_cast<uintptr_t>(d->wb) |
+                  reinterpret_cast<uintptr_t>(d->wc)) & 15) == 0, "tensor pointers must be 16-byte aligned");
+  VSB_CHECK_ARG(d->w < 128, "row wider than 127 slots");
+
+  FusedParams p{};
+  p.W = d->w; p.H = d->h; p.T = d->t; p.n_clips = d->n;
+  int RP = 8;
+  while (RP < d->w + 1) RP <<= 1;
+  p.RP = RP;
+  p.rp_shift = 0;
+  while ((1 << p.rp_shift) < RP) ++p.rp_shift;
+  p.rows_per_tile = 128 / RP;
+  // c-epilogue box: 32 slots = bw slots x bh rows
+  p.bw = RP >= 32 ? 32 : RP;
+  p.bh = 32 / p.bw;
+  // x TMA boxes: whole tiles when a frame is a whole number of tiles (FP a multiple of the tile rows is cheap),
+  // else single flat rows; output boxes of bh rows must not straddle frames
+  // frame pitch FP (flat rows per frame, > H): a multiple of the output box rows, a clip a whole number of tiles; the
+  // x boxes take as many rows as divide both the tile and FP -- the largest box whose FP rounding costs <= 7 % rows
+  auto fp_for = [&](int q) {
+    int fp = ceil_div(d->h + 1, q) * q;
+    while (fp % p.bh || ((long long)d->t * fp * RP) % 128) fp += q;
+    return fp;
+  };
+  const int fp_min = fp_for(1);
+  int FP = fp_min, box_rows = 1;
+  for (int br = p.rows_per_tile; br > 1; br >>= 1) {
+    const int fp = fp_for(br);
+    if (fp * 100 <= fp_min * 107) {
+      FP = fp;
+      box_rows = br;
+      break;
+    }
+  }
+  VSB_CHECK_ARG(FP * RP <= (1 << 20), "frame too large");
+  p.FP = FP;
+  p.box_rows = box_rows;
+  p.boxes_per_tile = p.rows_per_tile / box_rows;
+  VSB_CHECK_ARG(p.boxes_per_tile >= 1 && p.boxes_per_tile <= kMaxBoxes, "too many TMA boxes per tile");
+  p.tiles_per_clip = (int)(((long long)d->t * FP * RP) / 128);
+  p.row_bias = ceil_div(p.rows_per_tile, FP) * FP;
+
+  // channels
+  p.kt = d->kt;
+  p.kc = d->c % 64 == 0 ? 64 : (d->c % 32 == 0 ? 32 : 16);
+  p.cchunks = d->c / p.kc;
+  p.chunks_per_tile = p.kt * p.cchunks;
+  p.ksteps_x = p.kc / 16;
+  p.d16 = d->d;
+  p.ksteps_d = d->d / 16;
+  p.cout = d->c;
+  p.x_row_bytes = (uint32_t)p.kc * 2;
+  p.a_row_bytes = (uint32_t)d->d * 2;
+  p.chunk_bytes = 128u * p.x_row_bytes;
+  p.box_bytes = (uint32_t)box_rows * RP * p.x_row_bytes;
+  VSB_CHECK_ARG(p.box_bytes % 256 == 0, "x box is not a whole number of swizzle atoms");
+
+  // c epilogue
+  p.epi_n = d->c % 64 == 0 ? 64 : (d->c % 32 == 0 ? 32 : 16);
+  p.epi_chunks = d->c / p.epi_n;
+  p.epi_bufs = 2;
+
+  // TMEM
+  p.tm_ab_stride = d->d < 32 ? 32 : (uint32_t)d->d;
+  p.tm_c_stride = d->c < 32 ? 32 : (uint32_t)d->c;
+  p.tm_a = 0;
+  p.tm_b = 2 * p.tm_ab_stride;
+  p.tm_c = 4 * p.tm_ab_stride;
+  const uint32_t need_cols = 4 * p.tm_ab_stride + 2 * p.tm_c_stride;
+  VSB_CHECK_ARG(need_cols <= 512, "accumulators need %u TMEM columns (> 512)", need_cols);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < need_cols) p.tmem_cols <<= 1;
+  p.idesc_a = umma_idesc_bf16(128, d->d);
+  p.idesc_b = umma_idesc_bf16(128, d->d);
+  p.idesc_c = umma_idesc_bf16(128, d->c);
+
+  // shared memory
+  auto up1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  p.wa_block_bytes = up1k((uint32_t)d->d * p.x_row_bytes);
+  p.wb_block_bytes = up1k((uint32_t)d->d * p.a_row_bytes);
+  p.wc_bytes = up1k((uint32_t)d->c * p.a_row_bytes);
+  p.tile_bytes = 128u * p.a_row_bytes;
+  const uint32_t w_bytes = p.chunks_per_tile * p.wa_block_bytes + 9 * p.wb_block_bytes + p.wc_bytes;
+  const uint32_t ring_bytes = (kRing + 1) * p.tile_bytes, p_bytes = 2 * p.tile_bytes;
+  const uint32_t epi_bytes = up1k((uint32_t)kCEpiWarps * p.epi_bufs * 32u * p.epi_n * 2u);
+  const uint32_t tab_bytes = up1k((uint32_t)(2 * d->d + d->c) * 8u);
+  const uint32_t fixed = w_bytes + ring_bytes + p_bytes + epi_bytes + 1024 + tab_bytes + 1024;
+  long long room = 227ll * 1024 - fixed;
+  int stages = room > 0 ? (int)(room / p.chunk_bytes) : 0;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (d->stages > 0 && stages > d->stages) stages = d->stages;
+  if (stages < p.chunks_per_tile + 1 && stages < 2) {
+    set_error("fused bottleneck does not fit in shared memory (weights %u B, fixed %u B)", w_bytes, fixed);
+    return VSB_ERR_INVALID;
+  }
+  VSB_CHECK_ARG(stages >= 2, "fused bottleneck: x ring of %d stages (weights %u B, fixed %u B) is too shallow", stages,
+                w_bytes, fixed);
+  p.stages = stages;
+  p.off_wa = (uint32_t)stages * p.chunk_bytes;
+  p.off_wb = p.off_wa + p.chunks_per_tile * p.wa_block_bytes;
+  p.off_wc = p.off_wb + 9 * p.wb_block_bytes;
+  p.off_ring = p.off_wc + p.wc_bytes;
+  p.off_p = p.off_ring + ring_bytes;
+  p.off_epi = p.off_p + p_bytes;
+  p.off_bar = p.off_epi + epi_bytes;
+  p.off_tab = p.off_bar + 1024;
+  const size_t smem_bytes = (size_t)p.off_tab + tab_bytes + 1024;
+
+  p.sa = d->sa; p.ba = d->ba; p.sb = d->sb; p.bb = d->bb; p.sc = d->sc; p.bc = d->bc;
+
+  // walks: contiguous tile ranges of one clip, dealt round-robin to the CTAs; pick the length that minimises the
+  // busiest CTA's a-tile count (every walk pays two halo tiles)
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    (void)cudaGetLastError();
+  }
+  if (d->grid > 0 && d->grid < sms) sms = d->grid;
+  {
+    long long best_cost = -1;
+    int best_wl = p.tiles_per_clip;
+    const int wl_min = p.tiles_per_clip < 6 ? p.tiles_per_clip : 6;
+    for (int wl = p.tiles_per_clip; wl >= wl_min; --wl) {
+      const int wpc = ceil_div(p.tiles_per_clip, wl);
+      const long long walks = (long long)wpc * d->n;
+      const long long rounds = ceil_div_ll(walks, sms);
+      const long long cost = rounds * (wl + 2 + 3);  // + pipeline fill per walk
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_wl = wl;
+      }
+    }
+    if (d->walk_len > 0 && d->walk_len <= p.tiles_per_clip) best_wl = d->walk_len;
+    p.walk_len = best_wl;
+    p.walks_per_clip = ceil_div(p.tiles_per_clip, best_wl);
+    p.total_walks = p.walks_per_clip * d->n;
+  }
+
+  int rc = load_driver_entry_points();
+  if (rc != VSB_OK) return rc;
+  vsb_bottleneck_plan* plan = new (std::nothrow) vsb_bottleneck_plan();
+  VSB_CHECK_ARG(plan, "out of host memory");
+  plan->desc = *d;
+#define FB_FAIL(rc_)   \
+  do {                 \
+    delete plan;       \
+    return rc_;        \
+  } while (0)
+  {
+    // x: (C, W, H, T, N), box [kc, RP, box_rows, 1, 1]; out-of-bounds slots / rows / frames are zero-filled
+    cuuint64_t dims[5] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->t, (cuuint64_t)d->n};
+    cuuint64_t str[4] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->w * d->x_pitch * 2,
+                         (cuuint64_t)d->h * d->w * d->x_pitch * 2, (cuuint64_t)d->t * d->h * d->w * d->x_pitch * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.kc, (cuuint32_t)RP, (cuuint32_t)box_rows, 1, 1};
+    rc = fb_encode(&plan->map_x, d->x, 5, dims, str, box, swizzle_for((int)p.x_row_bytes), "block input");
+    if (rc != VSB_OK) FB_FAIL(rc);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->kt * d->c, (cuuint64_t)d->d};
+    cuuint64_t str[1] = {(cuuint64_t)d->kt * d->c * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)d->d};
+    rc = fb_encode(&plan->map_wa, d->wa, 2, dims, str, box, swizzle_for((int)p.x_row_bytes), "a weights");
+    if (rc != VSB_OK) FB_FAIL(rc);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)9 * d->d, (cuuint64_t)d->d};
+    cuuint64_t str[1] = {(cuuint64_t)9 * d->d * 2};
+    cuuint32_t box[2] = {(cuuint32_t)d->d, (cuuint32_t)d->d};
+    rc = fb_encode(&plan->map_wb, d->wb, 2, dims, str, box, swizzle_for((int)p.a_row_bytes), "b weights");
+    if (rc != VSB_OK) FB_FAIL(rc);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->d, (cuuint64_t)d->c};
+    cuuint64_t str[1] = {(cuuint64_t)d->d * 2};
+    cuuint32_t box[2] = {(cuuint32_t)d->d, (cuuint32_t)d->c};
+    rc = fb_encode(&plan->map_wc, d->wc, 2, dims, str, box, swizzle_for((int)p.a_row_bytes), "c weights");
+    if (rc != VSB_OK) FB_FAIL(rc);
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->t * d->n};
+    cuuint32_t box[4] = {(cuuint32_t)p.epi_n, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+    cuuint64_t ostr[3] = {(cuuint64_t)d->out_pitch * 2, (cuuint64_t)d->w * d->out_pitch * 2,
+                          (cuuint64_t)d->h * d->w * d->out_pitch * 2};
+    rc = fb_encode(&plan->map_out, d->out, 4, dims, ostr, box, swizzle_for(p.epi_n * 2), "block output");
+    if (rc != VSB_OK) FB_FAIL(rc);
+    cuuint64_t rstr[3] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->w * d->x_pitch * 2,
+                          (cuuint64_t)d->h * d->w * d->x_pitch * 2};
+    rc = fb_encode(&plan->map_res, d->x, 4, dims, rstr, box, swizzle_for(p.epi_n * 2), "block residual");
+    if (rc != VSB_OK) FB_FAIL(rc);
+  }
+  plan->params = p;
+  plan->smem_bytes = smem_bytes;
+  plan->grid = (unsigned)(p.total_walks < sms ? p.total_walks : sms);
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(bottleneck_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(bottleneck_fused_kernel) failed: %s", cudaGetErrorString(attr_err));
+    FB_FAIL(VSB_ERR_CUDA);
+  }
+  *out_plan = plan;
+  return VSB_OK;
+}
+
+extern "C" int vsb_bottleneck_run(const vsb_bottleneck_plan* plan, void* stream) {
+  VSB_CHECK_ARG(plan, "null plan");
+  bottleneck_fused_kernel<<<plan->grid, kThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+      plan->map_x, plan->map_wa, plan->map_wb, plan->map_wc, plan->map_res, plan->map_out, plan->params);
+  VSB_CHECK_LAUNCH("bottleneck_fused_kernel");
+  return VSB_OK;
+}
+
+extern "C" void vsb_bottleneck_plan_destroy(vsb_bottleneck_plan* plan) { delete plan; }
+
+extern "C" int vsb_bottleneck_plan_info(const vsb_bottleneck_plan* plan, long long* out8) {
+  VSB_CHECK_ARG(plan && out8, "null argument");
+  const FusedParams& p = plan->params;
+  out8[0] = p.RP;
+  out8[1] = p.FP;
+  out8[2] = p.stages;
+  out8[3] = p.walk_len;
+  out8[4] = plan->grid;
+  out8[5] = (long long)plan->smem_bytes;
+  out8[6] = p.tiles_per_clip;
+  out8[7] = p.tmem_cols;
+  return VSB_OK;
+}

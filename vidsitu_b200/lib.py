@@ -51,6 +51,24 @@ class ConvDesc(C.Structure):
     ]
 
 
+class BottleneckDesc(C.Structure):
+    """Mirror of `vsb_bottleneck_desc` (include/vidsitu_b200.h)."""
+
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("n", C.c_int), ("t", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int), ("x_pitch", C.c_int),
+        ("out", C.c_void_p),
+        ("out_pitch", C.c_int),
+        ("d", C.c_int),
+        ("kt", C.c_int),
+        ("wa", C.c_void_p), ("wb", C.c_void_p), ("wc", C.c_void_p),
+        ("sa", C.c_void_p), ("ba", C.c_void_p),
+        ("sb", C.c_void_p), ("bb", C.c_void_p),
+        ("sc", C.c_void_p), ("bc", C.c_void_p),
+        ("stages", C.c_int), ("walk_len", C.c_int), ("grid", C.c_int),
+    ]
+
+
 def lib_path() -> Path:
     env = os.environ.get("VIDSITU_B200_LIB")
     return Path(env) if env else Path(__file__).resolve().parent / _LIB_NAME
@@ -81,6 +99,11 @@ def load() -> C.CDLL:
     lib.vsb_conv3d_plan_out_shape.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     lib.vsb_conv3d_plan_flops.argtypes = [vp]
     lib.vsb_conv3d_plan_flops.restype = C.c_double
+    lib.vsb_bottleneck_plan_create.argtypes = [C.POINTER(BottleneckDesc), C.POINTER(vp)]
+    lib.vsb_bottleneck_run.argtypes = [vp, vp]
+    lib.vsb_bottleneck_plan_destroy.argtypes = [vp]
+    lib.vsb_bottleneck_plan_destroy.restype = None
+    lib.vsb_bottleneck_plan_info.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.vsb_maxpool3d.argtypes = [vp, i, i, i, i, i, i, vp, i, i, i, i, i, i, i, i, i, i, i, i, vp]
     lib.vsb_global_avgpool.argtypes = [vp, i, i, i, i, f32p, i, i, i, vp]
     lib.vsb_linear.argtypes = [f32p, i, i, f32p, f32p, f32p, i, i, vp]
@@ -95,14 +118,15 @@ def load() -> C.CDLL:
     lib.vsb_debug_umma_rate.argtypes = [i, i, i, i, i, i, vp, vp]
     lib.vsb_debug_conv_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.vsb_debug_conv_plan_info.argtypes = [vp, C.POINTER(C.c_longlong)]
-    for name in ("vsb_pack_frames", "vsb_conv3d_plan_create", "vsb_conv3d_run", "vsb_conv3d_plan_out_shape",
+    for name in ("vsb_pack_frames", "vsb_bottleneck_plan_create", "vsb_bottleneck_run", "vsb_bottleneck_plan_info",
+                 "vsb_conv3d_plan_create", "vsb_conv3d_run", "vsb_conv3d_plan_out_shape",
                  "vsb_maxpool3d", "vsb_global_avgpool", "vsb_linear", "vsb_softmax_topk", "vsb_nonlocal_attention",
                  "vsb_score_rows", "vsb_transpose_pad",
                  "vsb_nthwc_to_ncthw_f32", "vsb_ncthw_f32_to_nthwc", "vsb_debug_im2col_probe",
                  "vsb_debug_umma_semantics", "vsb_debug_umma_rate", "vsb_debug_conv_stats", "vsb_debug_conv_plan_info"):
         getattr(lib, name).restype = i
-    if lib.vsb_abi_version() != 4:
-        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 4")
+    if lib.vsb_abi_version() != 5:
+        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 5")
     _lib = lib
     return lib
 

@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import lib as _l
-from .lib import VSB_BF16, VSB_F32, ConvDesc, VsbError, check
+from .lib import VSB_BF16, VSB_F32, BottleneckDesc, ConvDesc, VsbError, check
 
 TORCH_DTYPE = {VSB_BF16: torch.bfloat16, VSB_F32: torch.float32}
 
@@ -149,6 +149,56 @@ class ConvPlan:
         h = getattr(self, "_h", None)
         if h is not None and h.value:
             self._lib.vsb_conv3d_plan_destroy(h)
+            h.value = None
+
+
+class BottleneckPlan:
+    """One planned fused identity-bottleneck launch (vsb_bottleneck_*): out = relu(x + c(b(a(x)))) with the three
+    frozen BatchNorms folded, a's and b's outputs never leaving the SM.  All tensors bf16, weights K-major and
+    zero-padded to the stored widths: wa [d, kt, c], wb [d, 9, d], wc [c, d]."""
+
+    def __init__(self, x: Act, out: Act, d: int, kt: int, wa: torch.Tensor, wb: torch.Tensor, wc: torch.Tensor,
+                 sa: torch.Tensor, ba: torch.Tensor, sb: torch.Tensor, bb: torch.Tensor, sc: torch.Tensor,
+                 bc: torch.Tensor, stages: int = 0, walk_len: int = 0, grid: int = 0):
+        _require_cuda(x.buf, out.buf, wa, wb, wc, sa, ba, sb, bb, sc, bc)
+        c = x.c
+        if (out.n, out.t, out.h, out.w, out.c) != (x.n, x.t, x.h, x.w, c):
+            raise VsbError("fused bottleneck: output extent / width must equal the input's")
+        for t in (x.buf, out.buf, wa, wb, wc):
+            if t.dtype != torch.bfloat16:
+                raise VsbError("fused bottleneck tensors must be bfloat16")
+        if wa.numel() != d * kt * c or wb.numel() != d * 9 * d or wc.numel() != c * d:
+            raise VsbError(f"fused bottleneck weights must be [{d},{kt},{c}], [{d},9,{d}], [{c},{d}]")
+        for t, nn in ((sa, d), (ba, d), (sb, d), (bb, d), (sc, c), (bc, c)):
+            if t.dtype != torch.float32 or t.numel() != nn or not t.is_contiguous():
+                raise VsbError("fused bottleneck scale / bias must be contiguous float32 of the stored widths")
+        dsc = BottleneckDesc()
+        dsc.x = x.ptr
+        dsc.n, dsc.t, dsc.h, dsc.w, dsc.c, dsc.x_pitch = x.n, x.t, x.h, x.w, c, x.pitch
+        dsc.out = out.ptr
+        dsc.out_pitch = out.pitch
+        dsc.d, dsc.kt = d, kt
+        dsc.wa, dsc.wb, dsc.wc = wa.data_ptr(), wb.data_ptr(), wc.data_ptr()
+        dsc.sa, dsc.ba, dsc.sb, dsc.bb, dsc.sc, dsc.bc = (t.data_ptr() for t in (sa, ba, sb, bb, sc, bc))
+        dsc.stages, dsc.walk_len, dsc.grid = stages, walk_len, grid
+        self._keep = (x.buf, out.buf, wa, wb, wc, sa, ba, sb, bb, sc, bc)
+        self._h = C.c_void_p()
+        self._lib = _l.load()
+        check(self._lib.vsb_bottleneck_plan_create(C.byref(dsc), C.byref(self._h)), "vsb_bottleneck_plan_create")
+
+    def run(self) -> None:
+        check(self._lib.vsb_bottleneck_run(self._h, _stream_ptr()), "vsb_bottleneck_run")
+
+    def info(self) -> dict:
+        out = (C.c_longlong * 8)()
+        check(self._lib.vsb_bottleneck_plan_info(self._h, out), "vsb_bottleneck_plan_info")
+        keys = ("rp", "fp", "stages", "walk_len", "grid", "smem_bytes", "tiles_per_clip", "tmem_cols")
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.vsb_bottleneck_plan_destroy(h)
             h.value = None
 
 
