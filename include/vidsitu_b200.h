@@ -193,7 +193,7 @@ typedef struct vsb_bottleneck_plan vsb_bottleneck_plan;
 int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* desc, vsb_bottleneck_plan** plan);
 int vsb_bottleneck_run(const vsb_bottleneck_plan* plan, void* stream);
 void vsb_bottleneck_plan_destroy(vsb_bottleneck_plan* plan);
-/* out8 = {slots per flat row, flat rows per frame, x ring stages, tiles per walk, grid, dynamic shared memory
+/* out8 = {slots per flat row, flat rows per frame, x ring slots * 100 + chunks per slot, tiles per CTA, grid, dynamic shared memory
  * bytes, tiles per clip, TMEM columns} */
 int vsb_bottleneck_plan_info(const vsb_bottleneck_plan* plan, long long* out8);
 

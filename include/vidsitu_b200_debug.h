@@ -28,6 +28,13 @@ int vsb_debug_umma_semantics(const void* a, int a_rows, const void* b, int n, in
 int vsb_debug_umma_rate(int n, int iters, int a_tiles, int a_from_same, int grid, int smem_pad_kb, long long* clk,
                         void* stream);
 
+/* Issue-rate probe 2: groups x per_group MMAs (M=128, N=n, K=16) with a tcgen05.commit after every group (commit_each)
+ * or only at the end; A rows of row_bytes (32/64/128, matching swizzle), start shifted by shift_rows rows (+1 row per
+ * MMA of a group when walk != 0).  clk[2*cta] = cycles until the last instruction was issued, clk[2*cta+1] = until
+ * completion. */
+int vsb_debug_umma_rate2(int n, int groups, int per_group, int commit_each, int row_bytes, int shift_rows, int walk,
+                         int grid, long long* clk, void* stream);
+
 /* Role timeline counters of a window-algorithm conv plan created with VSB_WIN_DEBUG=1 in the
  * environment (see conv_win_sm100.cu); synchronises the device, copies 16 counters and clears them. */
 struct vsb_conv_plan;
@@ -36,6 +43,11 @@ int vsb_debug_conv_stats(const struct vsb_conv_plan* plan, long long* out16);
 /* How a conv plan will run: out8 = {algo (1 im2col, 2 window), temporal-scatter mode (0/1), pipeline
  * stages, TMEM accumulators, grid, dynamic shared memory bytes, block_n, CTAs per SM the grid assumes}. */
 int vsb_debug_conv_plan_info(const struct vsb_conv_plan* plan, long long* out8);
+
+/* Role timeline counters of a fused-bottleneck plan created with VSB_FUSED_DEBUG=1 in the environment
+ * (see bottleneck_fused_sm100.cu); synchronises the device, copies 32 counters and clears them. */
+struct vsb_bottleneck_plan;
+int vsb_debug_bottleneck_stats(const struct vsb_bottleneck_plan* plan, long long* out32);
 
 #ifdef __cplusplus
 }

@@ -45,10 +45,13 @@ namespace {
 constexpr int kRing = 4;  // a-tiles in the ring (power of two) + 1 mirror tile
 constexpr int kMaxBoxes = 16;
 constexpr int kMaxStages = 24;
-constexpr int kBEpiWarp0 = 4, kCEpiWarp0 = 8, kProducerWarp = 16, kMmaWarp = 17;
-constexpr int kThreads = 18 * 32;
+constexpr int kBEpiWarp0 = 4, kCEpiWarp0 = 8, kProducerWarp = 16, kMmaWarp = 17, kMmaAWarp = 18;
+constexpr int kThreads = 19 * 32;
 constexpr int kCEpiWarps = 8;
 constexpr int kMaxEpiBufs = 3;
+#ifndef FB_PRETEST
+#define FB_PRETEST 0
+#endif
 }  // namespace
 
 struct FusedParams {
@@ -59,7 +62,8 @@ struct FusedParams {
   int box_rows, boxes_per_tile; // x TMA boxes: box_rows flat rows each
   uint32_t box_bytes;
   int tiles_per_clip;
-  int walk_len, walks_per_clip, total_walks;
+  int walk_len;                 // longest contiguous tile run of one clip a CTA walks without re-priming the halo
+  int tiles_per_cta, total_tiles;
   int row_bias;                 // multiple of FP added before the (t, y) split so that the dividend is >= 0
   // channels
   int kt, kc, cchunks, chunks_per_tile;
@@ -67,7 +71,10 @@ struct FusedParams {
   int d16, ksteps_d;            // bottleneck width (multiple of 16), d16 / 16
   int cout;
   uint32_t x_row_bytes, a_row_bytes, chunk_bytes;
-  int stages;
+  int stages;                   // x ring: `stages` slots of `cps` chunks each (one full / empty barrier pair per slot)
+  int cps, slots_per_tile;
+  int pf_dist;                  // L2 prefetch distance of the x loads, in tiles (0 = off)
+  uint32_t stage_bytes;
   // shared-memory layout (bytes from the 1 KiB-aligned base)
   uint32_t off_wa, off_wb, off_wc, off_ring, off_p, off_epi, off_bar, off_tab;
   uint32_t wa_block_bytes, wb_block_bytes, wc_bytes, tile_bytes;
@@ -77,31 +84,35 @@ struct FusedParams {
   // c epilogue
   int epi_n, epi_chunks, epi_bufs, bw, bh;
   const float *sa, *ba, *sb, *bb, *sc, *bc;
+  long long* dbg;  // role timeline counters (VSB_FUSED_DEBUG), else null
 };
 
-// Enumerates the a-tiles of one CTA: walks w = blockIdx.x, + gridDim.x, ...; tiles j = 0 .. L+1 of each walk are the
-// flat tiles m0-1 .. m0+L of clip n (the first and last one only feed the 3x3 halo of their neighbours).
+// Enumerates the a-tiles of one CTA.  The CTA owns the contiguous range [cur0, end) of the launch's flat tile index
+// (clip-major); the range is cut at clip boundaries (and every walk_len tiles) into walks, and the a-tiles j = 0 .. L+1
+// of a walk are the flat tiles m0-1 .. m0+L of clip n (the first and last one only feed the 3x3 halo of their
+// neighbours).
 struct ATileIter {
-  int w, j, L, n, m0;
+  int cur, end, j, L, n, m0;
   __device__ __forceinline__ void load_walk(const FusedParams& p) {
-    if (w < p.total_walks) {
-      n = w / p.walks_per_clip;
-      const int c = w - n * p.walks_per_clip;
-      m0 = c * p.walk_len;
-      const int m1 = m0 + p.walk_len < p.tiles_per_clip ? m0 + p.walk_len : p.tiles_per_clip;
-      L = m1 - m0;
+    if (cur < end) {
+      n = cur / p.tiles_per_clip;
+      m0 = cur - n * p.tiles_per_clip;
+      L = end - cur;
+      if (L > p.tiles_per_clip - m0) L = p.tiles_per_clip - m0;
+      if (L > p.walk_len) L = p.walk_len;
     }
   }
   __device__ __forceinline__ void init(const FusedParams& p) {
-    w = blockIdx.x;
+    cur = blockIdx.x * p.tiles_per_cta;
+    end = cur + p.tiles_per_cta < p.total_tiles ? cur + p.tiles_per_cta : p.total_tiles;
     j = 0;
     load_walk(p);
   }
-  __device__ __forceinline__ bool valid(const FusedParams& p) const { return w < p.total_walks; }
+  __device__ __forceinline__ bool valid(const FusedParams&) const { return cur < end; }
   __device__ __forceinline__ void next(const FusedParams& p) {
     if (++j == L + 2) {
       j = 0;
-      w += gridDim.x;
+      cur += L;
       load_walk(p);
     }
   }
@@ -152,6 +163,40 @@ __device__ __forceinline__ void fb_convert_rows(uint32_t taddr, int ncols, uint3
   }
 }
 
+// MMA issue: tight table-driven loops (the issuing warp is instruction-fetch / issue bound, not tensor-pipe bound: a
+// fully unrolled issue sequence of a whole tile does not fit the instruction cache next to the four epilogue roles).
+// tab[i] = (A offset, B offset) of MMA i in 16-byte descriptor units, relative to the operand bases.
+__device__ __forceinline__ void fb_issue(uint32_t tm_d, uint64_t a_hi, uint64_t b_hi, uint32_t a_base, uint32_t b_base,
+                                         const uint2* tab, int n, uint32_t idesc, uint32_t acc_first) {
+  {
+    const uint2 e = tab[0];
+    umma_bf16(tm_d, a_hi | (uint64_t)(a_base + e.x), b_hi | (uint64_t)(b_base + e.y), idesc, acc_first);
+  }
+#pragma unroll 2
+  for (int i = 1; i < n; ++i) {
+    const uint2 e = tab[i];
+    umma_bf16(tm_d, a_hi | (uint64_t)(a_base + e.x), b_hi | (uint64_t)(b_base + e.y), idesc, 1u);
+  }
+}
+
+// Optional role timeline (VSB_FUSED_DEBUG=1 at plan time): cycles per role, summed over CTAs.
+//  0 producer: wait free x slot          1 MMA: wait a-acc drained     2 MMA: wait x chunk        3 MMA: wait a-tile in ring
+//  4 MMA: wait b-acc drained             5 MMA: wait P tile            6 MMA: wait c-acc drained  7 a-epi: wait a_full
+//  8 a-epi: work                         9 b-epi: wait b_full         10 b-epi: work             11 c-epi (warp 8): wait c_full
+// 12 c-epi: wait slab / residual        13 c-epi: work                14 c-epi: wait store read  15 CTA total (warp 0)
+// 16 a-tiles                            17 c-tiles of warp 8
+#define FB_T(idx, stmt)                              \
+  do {                                               \
+    if (kDbg) {                                      \
+      const long long _t0 = clock64();               \
+      stmt;                                          \
+      dbg_acc[idx] += (uint32_t)(clock64() - _t0);   \
+    } else {                                         \
+      stmt;                                          \
+    }                                                \
+  } while (0)
+
+template <bool kDbg>
 __global__ void __launch_bounds__(kThreads, 1)
 bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wa,
                         const __grid_constant__ CUtensorMap map_wb, const __grid_constant__ CUtensorMap map_wc,
@@ -163,8 +208,10 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* x_empty = x_full + kMaxStages;
   uint64_t* a_full = x_empty + kMaxStages;
-  uint64_t* a_done = a_full + 2;
-  uint64_t* b_full = a_done + 2;
+  uint64_t* a_done = a_full + 2;      // a-epilogue -> a-issuer: accumulator drained
+  uint64_t* a_ready = a_done + 2;     // a-epilogue -> b/c-issuer: ring tile written (one per ring slot)
+  uint64_t* ring_free = a_ready + kRing;  // b/c-issuer (commit) -> a-issuer: every MMA issued through step s has completed
+  uint64_t* b_full = ring_free + kRing;
   uint64_t* b_done = b_full + 2;
   uint64_t* c_full = b_done + 2;
   uint64_t* c_empty = c_full + 2;
@@ -174,6 +221,8 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  uint32_t dbg_acc[24] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long dbg_start = kDbg ? clock64() : 0;
 
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&map_x);
@@ -189,6 +238,10 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_done[i], 4);
+      mbar_init(&a_ready[i], 4);
+      mbar_init(&a_ready[i + 2], 4);
+      mbar_init(&ring_free[i], 1);
+      mbar_init(&ring_free[i + 2], 1);
       mbar_init(&b_full[i], 1);
       mbar_init(&b_done[i], 4);
       mbar_init(&c_full[i], 1);
@@ -211,6 +264,21 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     sb_b[c] = make_float2(p.sb[c], p.bb[c]);
   }
   for (int c = threadIdx.x; c < p.cout; c += blockDim.x) sb_c[c] = make_float2(p.sc[c], p.bc[c]);
+  // MMA offset tables (fb_issue): a-phase entries of one ring slot, the 9 taps of the b-phase, the c-phase
+  uint2* tab_a = reinterpret_cast<uint2*>(sb_c + p.cout);
+  uint2* tab_b = tab_a + p.cps * p.ksteps_x;
+  uint2* tab_c = tab_b + 9 * p.ksteps_d;
+  for (int i = threadIdx.x; i < p.cps * p.ksteps_x; i += blockDim.x) {
+    const uint32_t c = i / p.ksteps_x, k = i % p.ksteps_x;
+    tab_a[i] = make_uint2(c * (p.chunk_bytes >> 4) + 2 * k, c * (p.wa_block_bytes >> 4) + 2 * k);
+  }
+  for (int i = threadIdx.x; i < 9 * p.ksteps_d; i += blockDim.x) {
+    const int tap = i / p.ksteps_d, k = i % p.ksteps_d;
+    const int o = (tap / 3 - 1) * p.RP + (tap % 3 - 1);  // start slot relative to the centre tile (taps 0-3: < 0)
+    tab_b[i] = make_uint2((((uint32_t)(o < 0 ? 128 + o : o) * p.a_row_bytes) >> 4) + 2 * k,
+                          (uint32_t)tap * (p.wb_block_bytes >> 4) + 2 * k);
+  }
+  for (int i = threadIdx.x; i < p.ksteps_d; i += blockDim.x) tab_c[i] = make_uint2(2 * i, 2 * i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -220,6 +288,7 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer (one thread)
       // resident weights: Wa as chunks_per_tile blocks [d16 rows x kc], Wb as 9 tap blocks [d16 x d16], Wc [cout x d16]
+      // (Wb / Wc boxes are a_row_bytes wide: when that is more than d16 channels the extra K columns are never read)
       mbar_expect_tx(w_bar, (uint32_t)p.chunks_per_tile * (uint32_t)p.d16 * p.x_row_bytes +
                                 9u * (uint32_t)p.d16 * p.a_row_bytes + (uint32_t)p.cout * p.a_row_bytes);
       for (int q = 0; q < p.chunks_per_tile; ++q)
@@ -230,10 +299,35 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 
       int slot = 0;
       uint32_t parity = 1;  // first pass over the ring: slots are free
-      const int S = p.stages, nbox = p.boxes_per_tile, kt = p.kt, cch = p.cchunks, kc = p.kc;
-      const int FP = p.FP, pt = p.kt >> 1;
+      const int S = p.stages, nbox = p.boxes_per_tile, cch = p.cchunks, kc = p.kc, cps = p.cps;
+      const int FP = p.FP, pt = p.kt >> 1, cpt = p.chunks_per_tile, kt_ = p.kt;
+      // L2 prefetch cursor, pf_dist a-tiles ahead of the loads: the newest frame of a tile (dt = kt-1) is the one no
+      // earlier tile has touched (the others were loaded ~tiles_per_frame tiles ago and sit in the L2); fetching it
+      // early turns the ring's DRAM-latency loads into L2 hits (the ring only holds ~2 tiles of x)
+      ATileIter pf;
+      pf.init(p);
+      auto prefetch_tile = [&](const ATileIter& a) {
+        const int r0p = a.m() * p.rows_per_tile + p.row_bias;
+        const int dt0 = a.j == 0 ? 0 : kt_ - 1;  // the first tile of a walk has seen no frame yet
+        for (int b = 0; b < nbox; ++b) {
+          const int r = r0p + b * p.box_rows;
+          const int tq = r / FP;
+          const int t = tq - p.row_bias / FP, y = r - tq * FP;
+          if (y >= p.H) continue;
+          for (int dt = dt0; dt < kt_; ++dt) {
+            const int tt = t + dt - pt;
+            if (tt < 0 || tt >= p.T) continue;
+            for (int cc2 = 0; cc2 < cch; ++cc2) tma_prefetch_5d(&map_x, cc2 * kc, 0, y, tt, a.n);
+          }
+        }
+      };
+      for (int i = 0; i < p.pf_dist && pf.valid(p); ++i, pf.next(p)) prefetch_tile(pf);
       ATileIter it;
       for (it.init(p); it.valid(p); it.next(p)) {
+        if (p.pf_dist > 0 && pf.valid(p)) {
+          prefetch_tile(pf);
+          pf.next(p);
+        }
         const int r0 = it.m() * p.rows_per_tile + p.row_bias;  // >= 0
         int bt[kMaxBoxes], by[kMaxBoxes];
         for (int b = 0; b < nbox; ++b) {
@@ -242,133 +336,144 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           bt[b] = tq - p.row_bias / FP;  // frame (may be -1 or T: zero-filled by the TMA unit)
           by[b] = r - tq * FP;           // row inside the frame (>= H: zero-filled)
         }
-        for (int dt = 0; dt < kt; ++dt) {
-          for (int cc = 0; cc < cch; ++cc) {
-            mbar_wait(&x_empty[slot], parity);
-            mbar_expect_tx(&x_full[slot], p.chunk_bytes);
-            uint8_t* dst = smem + (uint32_t)slot * p.chunk_bytes;
+        int dt = 0, cc = 0;
+        for (int q = 0; q < cpt; q += cps) {
+          FB_T(0, mbar_wait(&x_empty[slot], parity));
+          mbar_expect_tx(&x_full[slot], p.stage_bytes);
+          uint8_t* dst = smem + (uint32_t)slot * p.stage_bytes;
+          for (int c = 0; c < cps; ++c) {
             for (int b = 0; b < nbox; ++b)
               tma_load_5d(dst + b * p.box_bytes, &map_x, &x_full[slot], cc * kc, 0, by[b], bt[b] + dt - pt, it.n);
-            if (++slot == S) {
-              slot = 0;
-              parity ^= 1;
+            dst += p.chunk_bytes;
+            if (++cc == cch) {
+              cc = 0;
+              ++dt;
             }
+          }
+          if (++slot == S) {
+            slot = 0;
+            parity ^= 1;
           }
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issuer
+    // descriptor low words carry the layout flags: (flags | address >> 4) + offsets never carries into bit 14
     const uint64_t x_hi = umma_smem_desc(0, p.x_row_bytes) & 0xFFFFFFFF00000000ull;
     const uint32_t x_fl = (uint32_t)(umma_smem_desc(0, p.x_row_bytes) & 0xFFFFC000ull);
     const uint64_t d_hi = umma_smem_desc(0, p.a_row_bytes) & 0xFFFFFFFF00000000ull;
     const uint32_t d_fl = (uint32_t)(umma_smem_desc(0, p.a_row_bytes) & 0xFFFFC000ull);
     const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
-    const uint32_t wa_lo = smem_lo + (p.off_wa >> 4), wb_lo = smem_lo + (p.off_wb >> 4), wc_lo = smem_lo + (p.off_wc >> 4);
-    const uint32_t ring_lo = smem_lo + (p.off_ring >> 4), p_lo = smem_lo + (p.off_p >> 4);
-    const uint32_t chunk_lo = p.chunk_bytes >> 4, tile_lo = p.tile_bytes >> 4;
+    const uint32_t xring_lo = x_fl | smem_lo, wa_lo = x_fl | (smem_lo + (p.off_wa >> 4));
+    const uint32_t wb_lo = d_fl | (smem_lo + (p.off_wb >> 4)), wc_lo = d_fl | (smem_lo + (p.off_wc >> 4));
+    const uint32_t ring_lo = d_fl | (smem_lo + (p.off_ring >> 4)), p_lo = d_fl | (smem_lo + (p.off_p >> 4));
+    const uint32_t chunk_lo = p.chunk_bytes >> 4, tile_lo = p.tile_bytes >> 4, stage_lo = p.stage_bytes >> 4;
     const uint32_t wa_blk_lo = p.wa_block_bytes >> 4, wb_blk_lo = p.wb_block_bytes >> 4;
-    const int S = p.stages, cpt = p.chunks_per_tile, ksx = p.ksteps_x, ksd = p.ksteps_d;
+    const int S = p.stages, spt = p.slots_per_tile, cps = p.cps, ksx = p.ksteps_x, ksd = p.ksteps_d;
     const uint32_t idesc_a = p.idesc_a, idesc_b = p.idesc_b, idesc_c = p.idesc_c;
-    // tap table: start slot of tap (dy, dx) relative to the centre tile, as (starts in the previous tile?, 16-byte units)
-    uint32_t tap_off[9];
-    uint32_t tap_prev = 0;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int o = (tap / 3 - 1) * p.RP + (tap % 3 - 1);
-      if (o < 0) tap_prev |= 1u << tap;
-      tap_off[tap] = ((uint32_t)(o < 0 ? 128 + o : o) * p.a_row_bytes) >> 4;
-    }
-    int slot = 0;
-    uint32_t xpar = 0;
-    int g = 0;          // step = global index of the a-tile issued in this step
-    int gb = 0, gc = 0; // b-tiles / c-tiles issued so far
-    int a_waited = 0;   // a-tiles whose epilogue this thread has observed (in order)
-    int b_waited = 0;
-    int j1 = -1, j2 = -1;  // walk-local index of a-tiles g-1 and g-2 (-1: none)
+    const int n_b_prev = 4 * ksd, n_b_cen = 5 * ksd;  // taps 0-3 start in the previous tile (RP >= 8)
+    (void)xring_lo; (void)wa_lo; (void)stage_lo; (void)wa_blk_lo; (void)chunk_lo; (void)cps; (void)ksx; (void)S; (void)spt;
+    (void)x_hi; (void)idesc_a;
+    // Steps s = 0 .. G+1 (G = a-tiles of this CTA): step s issues the b-tile whose centre is a-tile s-2 and the c-tile
+    // of the b-tile issued in step s-1, then commits ring_free[s & 3] (arrives once everything issued so far is done).
+    int s_ = 0;
+    int gb = 0, gc = 0;  // b-tiles / c-tiles issued so far
+    int b_waited = 0;    // b-tiles whose epilogue this warp has observed (in order)
+    int j1 = -1, j2 = -1;  // walk-local index of a-tiles s-1 and s-2 (-1: none)
     mbar_wait(w_bar, 0);
     ATileIter it;
     it.init(p);
-    for (;; ++g) {
+    for (;; ++s_) {
+      const int g = s_;
       const bool have_a = it.valid(p);
-      if (!have_a && j1 < 2 && j2 < 2) break;
-      if (have_a) {
-        // accumulator g & 1 was last used by a-tile g-2: its epilogue must have drained it
-        while (a_waited < g - 1) {
-          mbar_wait(&a_done[a_waited & 1], (a_waited >> 1) & 1);
-          ++a_waited;
-        }
-        tc_fence_after();
-        const uint32_t tm_d = tmem_base + p.tm_a + (uint32_t)(g & 1) * p.tm_ab_stride;
-        for (int q = 0; q < cpt; ++q) {
-          mbar_wait(&x_full[slot], xpar);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_lo = smem_lo + (uint32_t)slot * chunk_lo;
-            const uint32_t b_lo = wa_lo + (uint32_t)q * wa_blk_lo;
-            for (int k = 0; k < ksx; ++k)
-              umma_bf16(tm_d, x_hi | (uint64_t)(x_fl | (a_lo + 2 * k)), x_hi | (uint64_t)(x_fl | (b_lo + 2 * k)),
-                        idesc_a, (q | k) != 0 ? 1u : 0u);
-            umma_commit(&x_empty[slot]);
-            if (q == cpt - 1) umma_commit(&a_full[g & 1]);
-          }
-          __syncwarp();
-          if (++slot == S) {
-            slot = 0;
-            xpar ^= 1;
-          }
-        }
-      }
+      if (!have_a && j1 < 0 && j2 < 2) break;
+      // a-tile s-1 is in the ring (every tile is observed, in order, exactly once: its ring-slot barrier flips again
+      // only four tiles later, which the a-issuer cannot reach before this warp has passed this step)
+      if (j1 >= 0) FB_T(3, mbar_wait(&a_ready[(g - 1) & (kRing - 1)], ((g - 1) >> 2) & 1));
       if (j1 >= 2) {
-        // b-tile whose centre is a-tile g-2 (previous g-3, next g-1): all three must be in the ring
-        while (a_waited < g) {
-          mbar_wait(&a_done[a_waited & 1], (a_waited >> 1) & 1);
-          ++a_waited;
-        }
+        // b-tile whose centre is a-tile s-2 (previous s-3, next s-1)
         while (b_waited < gb - 1) {
-          mbar_wait(&b_done[b_waited & 1], (b_waited >> 1) & 1);
+          FB_T(4, mbar_wait(&b_done[b_waited & 1], (b_waited >> 1) & 1));
           ++b_waited;
         }
+        const long long i0 = kDbg ? clock64() : 0;
         tc_fence_after();
         if (elect_one()) {
           const uint32_t prev_lo = ring_lo + (uint32_t)((g - 3) & (kRing - 1)) * tile_lo;
           const uint32_t cen_lo = ring_lo + (uint32_t)((g - 2) & (kRing - 1)) * tile_lo;
           const uint32_t tm_d = tmem_base + p.tm_b + (uint32_t)(gb & 1) * p.tm_ab_stride;
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a_lo = ((tap_prev >> tap) & 1 ? prev_lo : cen_lo) + tap_off[tap];
-            const uint32_t b_lo = wb_lo + (uint32_t)tap * wb_blk_lo;
-            for (int k = 0; k < ksd; ++k)
-              umma_bf16(tm_d, d_hi | (uint64_t)(d_fl | (a_lo + 2 * k)), d_hi | (uint64_t)(d_fl | (b_lo + 2 * k)),
-                        idesc_b, (tap | k) != 0 ? 1u : 0u);
-          }
+          fb_issue(tm_d, d_hi, d_hi, prev_lo, wb_lo, tab_b, n_b_prev, idesc_b, 0u);
+          fb_issue(tm_d, d_hi, d_hi, cen_lo, wb_lo, tab_b + n_b_prev, n_b_cen, idesc_b, 1u);
           umma_commit(&b_full[gb & 1]);
         }
         __syncwarp();
+        if (kDbg) dbg_acc[19] += (uint32_t)(clock64() - i0);
         ++gb;
       }
       if (j2 >= 2) {
         // c-tile gc: needs the P tile of b-tile gc and a drained accumulator gc & 1
         while (b_waited < gc + 1) {
-          mbar_wait(&b_done[b_waited & 1], (b_waited >> 1) & 1);
+          FB_T(5, mbar_wait(&b_done[b_waited & 1], (b_waited >> 1) & 1));
           ++b_waited;
         }
-        mbar_wait(&c_empty[gc & 1], ((gc >> 1) & 1) ^ 1);
+        FB_T(6, mbar_wait(&c_empty[gc & 1], ((gc >> 1) & 1) ^ 1));
+        const long long i0 = kDbg ? clock64() : 0;
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_lo = p_lo + (uint32_t)(gc & 1) * tile_lo;
-          const uint32_t tm_d = tmem_base + p.tm_c + (uint32_t)(gc & 1) * p.tm_c_stride;
-          for (int k = 0; k < ksd; ++k)
-            umma_bf16(tm_d, d_hi | (uint64_t)(d_fl | (a_lo + 2 * k)), d_hi | (uint64_t)(d_fl | (wc_lo + 2 * k)), idesc_c,
-                      k != 0 ? 1u : 0u);
+          fb_issue(tmem_base + p.tm_c + (uint32_t)(gc & 1) * p.tm_c_stride, d_hi, d_hi, p_lo + (uint32_t)(gc & 1) * tile_lo,
+                   wc_lo, tab_c, ksd, idesc_c, 0u);
           umma_commit(&c_full[gc & 1]);
         }
         __syncwarp();
+        if (kDbg) dbg_acc[20] += (uint32_t)(clock64() - i0);
         ++gc;
       }
+      if (elect_one()) umma_commit(&ring_free[g & (kRing - 1)]);
+      __syncwarp();
       j2 = j1;
       j1 = have_a ? it.j : -1;
       if (have_a) it.next(p);
+    }
+  } else if (warp == kMmaAWarp) {
+    // ---------------------------------------------------------------- a-phase MMA issuer (second issuing warp)
+    // Two issuing warps: each one's barrier round trips and loop overhead overlap the other's tensor-pipe time (one
+    // warp issuing all three phases is issue-latency bound at ~1.7x the pipe time).  tcgen05.commit only tracks the
+    // issuing thread's own MMAs, so the ring-slot reuse (a-tile g overwrites a-tile g-4, last read by the b-tile of
+    // step g-1) is ordered through ring_free: a(g) is issued after step g-1 of the other warp has COMPLETED.
+    const uint64_t x_hi = umma_smem_desc(0, p.x_row_bytes) & 0xFFFFFFFF00000000ull;
+    const uint32_t x_fl = (uint32_t)(umma_smem_desc(0, p.x_row_bytes) & 0xFFFFC000ull);
+    const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+    const uint32_t xring_lo = x_fl | smem_lo, wa_lo = x_fl | (smem_lo + (p.off_wa >> 4));
+    const uint32_t stage_lo = p.stage_bytes >> 4, wa_blk_lo = p.wa_block_bytes >> 4;
+    const int S = p.stages, spt = p.slots_per_tile, cps = p.cps, n_a = p.cps * p.ksteps_x;
+    const uint32_t idesc_a = p.idesc_a;
+    int slot = 0;
+    uint32_t xpar = 0;
+    int g = 0;
+    mbar_wait(w_bar, 0);
+    ATileIter it;
+    for (it.init(p); it.valid(p); it.next(p), ++g) {
+      if (g >= 2) FB_T(1, mbar_wait(&a_done[g & 1], ((g - 2) >> 1) & 1));  // accumulator drained by a-tile g-2's epilogue
+      if (g >= 1) FB_T(21, mbar_wait(&ring_free[(g - 1) & (kRing - 1)], ((g - 1) >> 2) & 1));
+      const uint32_t tm_d = tmem_base + p.tm_a + (uint32_t)(g & 1) * p.tm_ab_stride;
+      for (int q = 0; q < spt; ++q) {
+        FB_T(2, mbar_wait(&x_full[slot], xpar));
+        const long long i0 = kDbg ? clock64() : 0;
+        tc_fence_after();
+        if (elect_one()) {
+          fb_issue(tm_d, x_hi, x_hi, xring_lo + (uint32_t)slot * stage_lo, wa_lo + (uint32_t)(q * cps) * wa_blk_lo, tab_a, n_a,
+                   idesc_a, q == 0 ? 0u : 1u);
+          umma_commit(&x_empty[slot]);
+          if (q == spt - 1) umma_commit(&a_full[g & 1]);
+        }
+        __syncwarp();
+        if (kDbg) dbg_acc[18] += (uint32_t)(clock64() - i0);
+        if (++slot == S) {
+          slot = 0;
+          xpar ^= 1;
+        }
+      }
     }
   } else if (warp < kBEpiWarp0) {
     // ---------------------------------------------------------------- a-epilogue (warps 0-3)
@@ -391,14 +496,22 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       const int pos = g & (kRing - 1);
       const uint32_t dst = ring_s + (uint32_t)pos * p.tile_bytes;
       const uint32_t dst2 = pos == 0 ? ring_s + (uint32_t)kRing * p.tile_bytes : 0u;
-      mbar_wait(&a_full[g & 1], (g >> 1) & 1);
+      FB_T(7, mbar_wait(&a_full[g & 1], (g >> 1) & 1));
+      const long long w0 = kDbg ? clock64() : 0;
       tc_fence_after();
       fb_convert_rows(lane_taddr + (uint32_t)(g & 1) * p.tm_ab_stride, p.d16, dst, dst2, p.a_row_bytes, swz_mask, row,
                       sb_s, keep);
       fence_proxy_async_smem();  // ring writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a_done[g & 1]);
+      if (lane == 0) {
+        mbar_arrive(&a_done[g & 1]);
+        mbar_arrive(&a_ready[g & (kRing - 1)]);
+      }
+      if (kDbg) {
+        dbg_acc[8] += (uint32_t)(clock64() - w0);
+        dbg_acc[16] += 1;
+      }
     }
   } else if (warp < kCEpiWarp0) {
     // ---------------------------------------------------------------- b-epilogue (warps 4-7)
@@ -412,7 +525,8 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     ATileIter it;
     for (it.init(p); it.valid(p); it.next(p)) {
       if (it.j < 2) continue;
-      mbar_wait(&b_full[gb & 1], (gb >> 1) & 1);
+      FB_T(9, mbar_wait(&b_full[gb & 1], (gb >> 1) & 1));
+      const long long w0 = kDbg ? clock64() : 0;
       tc_fence_after();
       fb_convert_rows(lane_taddr + (uint32_t)(gb & 1) * p.tm_ab_stride, p.d16, p_s + (uint32_t)(gb & 1) * p.tile_bytes, 0u,
                       p.a_row_bytes, swz_mask, row, sb_s, 0xFFFFFFFFu);
@@ -420,6 +534,7 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_done[gb & 1]);
+      if (kDbg) dbg_acc[10] += (uint32_t)(clock64() - w0);
       ++gb;
     }
   } else if (warp < kProducerWarp) {
@@ -489,12 +604,14 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     while (seek(it, gbx)) {
       int xs0, y, tn;
       const bool live = box_of(it.n, it.m0 + it.j - 2, xs0, y, tn);
-      mbar_wait(&c_full[grp], tcount & 1);
+      FB_T(11, mbar_wait(&c_full[grp], tcount & 1));
+      if (kDbg) dbg_acc[17] += 1;
       tc_fence_after();
       for (int c = 0; c < chunks; ++c) {
         const int b = q % nb;
         uint8_t* buf = my_bufs + b * slab_bytes;
-        mbar_wait(&my_ready[b], (q / nb) & 1);  // slab free (+ residual landed)
+        FB_T(12, mbar_wait(&my_ready[b], (q / nb) & 1));  // slab free (+ residual landed)
+        const long long w0 = kDbg ? clock64() : 0;
         const int col0 = c * p.epi_n;
         if (live)
           epi_convert_chunk<true>(lane_taddr + col0, p.epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane,
@@ -504,8 +621,9 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         if (lane == 0) {
           if (live) tma_store_4d(&map_out, buf, col0, xs0, y, tn);  // slots >= W / rows >= H are clipped by the TMA unit
           tma_store_commit();
+          if (kDbg) dbg_acc[13] += (uint32_t)(clock64() - w0);
           if (pf_ok) {
-            tma_store_wait_read1();
+            FB_T(14, tma_store_wait_read1());
             arm_next();
           }
         }
@@ -522,6 +640,11 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (lane == 0) tma_store_wait_all();
   }
 
+  if (kDbg && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == kMmaAWarp || warp == 0 || warp == kBEpiWarp0 || warp == kCEpiWarp0)) {
+    if (warp == 0) dbg_acc[15] = (uint32_t)(clock64() - dbg_start);
+    for (int i = 0; i < 24; ++i)
+      if (dbg_acc[i]) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg) + i, (unsigned long long)dbg_acc[i]);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -594,9 +717,10 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
   };
   const int fp_min = fp_for(1);
   int FP = fp_min, box_rows = 1;
+  const int waste_pct = getenv("VSB_FUSED_BOXWASTE") ? atoi(getenv("VSB_FUSED_BOXWASTE")) : 7;  // experiments
   for (int br = p.rows_per_tile; br > 1; br >>= 1) {
     const int fp = fp_for(br);
-    if (fp * 100 <= fp_min * 107) {
+    if (fp * 100 <= fp_min * (100 + waste_pct)) {
       FP = fp;
       box_rows = br;
       break;
@@ -620,13 +744,13 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
   p.ksteps_d = d->d / 16;
   p.cout = d->c;
   p.x_row_bytes = (uint32_t)p.kc * 2;
-  p.a_row_bytes = (uint32_t)d->d * 2;
+  p.a_row_bytes = d->d * 2 < 64 ? 64u : (uint32_t)d->d * 2;  // 32-byte operand rows run the tensor core ~3x slower (measured)
   p.chunk_bytes = 128u * p.x_row_bytes;
   p.box_bytes = (uint32_t)box_rows * RP * p.x_row_bytes;
   VSB_CHECK_ARG(p.box_bytes % 256 == 0, "x box is not a whole number of swizzle atoms");
 
   // c epilogue
-  p.epi_n = d->c % 64 == 0 ? 64 : (d->c % 32 == 0 ? 32 : 16);
+  p.epi_n = d->c % 32 == 0 ? 32 : 16;
   p.epi_chunks = d->c / p.epi_n;
   p.epi_bufs = 2;
 
@@ -653,20 +777,42 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
   const uint32_t w_bytes = p.chunks_per_tile * p.wa_block_bytes + 9 * p.wb_block_bytes + p.wc_bytes;
   const uint32_t ring_bytes = (kRing + 1) * p.tile_bytes, p_bytes = 2 * p.tile_bytes;
   const uint32_t epi_bytes = up1k((uint32_t)kCEpiWarps * p.epi_bufs * 32u * p.epi_n * 2u);
-  const uint32_t tab_bytes = up1k((uint32_t)(2 * d->d + d->c) * 8u);
+  const uint32_t tab_bytes = up1k((uint32_t)(2 * d->d + d->c) * 8u + (uint32_t)(p.kt * (d->c / 16) + 10 * (d->d / 16)) * 8u);
   const uint32_t fixed = w_bytes + ring_bytes + p_bytes + epi_bytes + 1024 + tab_bytes + 1024;
-  long long room = 227ll * 1024 - fixed;
-  int stages = room > 0 ? (int)(room / p.chunk_bytes) : 0;
+  // x ring: slots of cps chunks (one barrier pair per slot).  Prefer whole tiles per slot (fewest waits / commits in the
+  // single issuing thread) when >= 2 tiles fit, else halves ..., else single chunks.
+  const long long room = 227ll * 1024 - fixed;
+  int cps = 1, stages = 0;
+  const int cps_max = getenv("VSB_FUSED_CPS") ? atoi(getenv("VSB_FUSED_CPS")) : p.chunks_per_tile;  // experiments
+  for (int cand = cps_max < p.chunks_per_tile ? cps_max : p.chunks_per_tile; cand >= 1; --cand) {
+    if (p.chunks_per_tile % cand) continue;
+    const long long sb = (long long)cand * p.chunk_bytes;
+    const int st = room > 0 ? (int)(room / sb) : 0;
+    if (st * cand >= 2 * p.chunks_per_tile || (cand == 1 && st >= 2)) {
+      cps = cand;
+      stages = st;
+      break;
+    }
+  }
+  if (d->stages > 0 && d->stages < stages * cps) {  // caller's cap, in chunks
+    stages = d->stages / cps;
+    if (stages < 2) {
+      cps = 1;
+      stages = d->stages;
+    }
+  }
   if (stages > kMaxStages) stages = kMaxStages;
-  if (d->stages > 0 && stages > d->stages) stages = d->stages;
-  if (stages < p.chunks_per_tile + 1 && stages < 2) {
-    set_error("fused bottleneck does not fit in shared memory (weights %u B, fixed %u B)", w_bytes, fixed);
+  if (stages < 2) {
+    set_error("fused bottleneck does not fit in shared memory (weights %u B, fixed %u B, x chunk %u B)", w_bytes, fixed,
+              p.chunk_bytes);
     return VSB_ERR_INVALID;
   }
-  VSB_CHECK_ARG(stages >= 2, "fused bottleneck: x ring of %d stages (weights %u B, fixed %u B) is too shallow", stages,
-                w_bytes, fixed);
   p.stages = stages;
-  p.off_wa = (uint32_t)stages * p.chunk_bytes;
+  p.cps = cps;
+  p.slots_per_tile = p.chunks_per_tile / cps;
+  p.stage_bytes = (uint32_t)cps * p.chunk_bytes;
+  p.pf_dist = getenv("VSB_FUSED_PF") ? atoi(getenv("VSB_FUSED_PF")) : 0;  // measured: the TMA unit is the bound, prefetches only add to it
+  p.off_wa = (uint32_t)stages * p.stage_bytes;
   p.off_wb = p.off_wa + p.chunks_per_tile * p.wa_block_bytes;
   p.off_wc = p.off_wb + 9 * p.wb_block_bytes;
   p.off_ring = p.off_wc + p.wc_bytes;
@@ -677,9 +823,13 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
   const size_t smem_bytes = (size_t)p.off_tab + tab_bytes + 1024;
 
   p.sa = d->sa; p.ba = d->ba; p.sb = d->sb; p.bb = d->bb; p.sc = d->sc; p.bc = d->bc;
+  p.dbg = nullptr;
+  if (getenv("VSB_FUSED_DEBUG")) {  // debug only: the one place this file allocates device memory
+    if (cudaMalloc(&p.dbg, 32 * sizeof(long long)) == cudaSuccess) (void)cudaMemset(p.dbg, 0, 32 * sizeof(long long));
+    else p.dbg = nullptr;
+  }
 
-  // walks: contiguous tile ranges of one clip, dealt round-robin to the CTAs; pick the length that minimises the
-  // busiest CTA's a-tile count (every walk pays two halo tiles)
+  // every CTA owns one contiguous range of the clip-major tile index (cut into walks at clip boundaries)
   int sms = 148;
   {
     int dev = 0;
@@ -687,25 +837,10 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
     (void)cudaGetLastError();
   }
   if (d->grid > 0 && d->grid < sms) sms = d->grid;
-  {
-    long long best_cost = -1;
-    int best_wl = p.tiles_per_clip;
-    const int wl_min = p.tiles_per_clip < 6 ? p.tiles_per_clip : 6;
-    for (int wl = p.tiles_per_clip; wl >= wl_min; --wl) {
-      const int wpc = ceil_div(p.tiles_per_clip, wl);
-      const long long walks = (long long)wpc * d->n;
-      const long long rounds = ceil_div_ll(walks, sms);
-      const long long cost = rounds * (wl + 2 + 3);  // + pipeline fill per walk
-      if (best_cost < 0 || cost < best_cost) {
-        best_cost = cost;
-        best_wl = wl;
-      }
-    }
-    if (d->walk_len > 0 && d->walk_len <= p.tiles_per_clip) best_wl = d->walk_len;
-    p.walk_len = best_wl;
-    p.walks_per_clip = ceil_div(p.tiles_per_clip, best_wl);
-    p.total_walks = p.walks_per_clip * d->n;
-  }
+  p.total_tiles = p.tiles_per_clip * d->n;
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  p.tiles_per_cta = ceil_div(p.total_tiles, grid);
+  p.walk_len = (d->walk_len > 0 && d->walk_len < p.tiles_per_clip) ? d->walk_len : p.tiles_per_clip;
 
   int rc = load_driver_entry_points();
   if (rc != VSB_OK) return rc;
@@ -736,14 +871,14 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
   {
     cuuint64_t dims[2] = {(cuuint64_t)9 * d->d, (cuuint64_t)d->d};
     cuuint64_t str[1] = {(cuuint64_t)9 * d->d * 2};
-    cuuint32_t box[2] = {(cuuint32_t)d->d, (cuuint32_t)d->d};
+    cuuint32_t box[2] = {(cuuint32_t)(p.a_row_bytes / 2), (cuuint32_t)d->d};
     rc = fb_encode(&plan->map_wb, d->wb, 2, dims, str, box, swizzle_for((int)p.a_row_bytes), "b weights");
     if (rc != VSB_OK) FB_FAIL(rc);
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->d, (cuuint64_t)d->c};
     cuuint64_t str[1] = {(cuuint64_t)d->d * 2};
-    cuuint32_t box[2] = {(cuuint32_t)d->d, (cuuint32_t)d->c};
+    cuuint32_t box[2] = {(cuuint32_t)(p.a_row_bytes / 2), (cuuint32_t)d->c};
     rc = fb_encode(&plan->map_wc, d->wc, 2, dims, str, box, swizzle_for((int)p.a_row_bytes), "c weights");
     if (rc != VSB_OK) FB_FAIL(rc);
   }
@@ -761,12 +896,14 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
   }
   plan->params = p;
   plan->smem_bytes = smem_bytes;
-  plan->grid = (unsigned)(p.total_walks < sms ? p.total_walks : sms);
+  plan->grid = (unsigned)ceil_div(p.total_tiles, p.tiles_per_cta);
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(bottleneck_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(bottleneck_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(bottleneck_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) {
     set_error("cudaFuncSetAttribute(bottleneck_fused_kernel) failed: %s", cudaGetErrorString(attr_err));
@@ -778,21 +915,34 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
 
 extern "C" int vsb_bottleneck_run(const vsb_bottleneck_plan* plan, void* stream) {
   VSB_CHECK_ARG(plan, "null plan");
-  bottleneck_fused_kernel<<<plan->grid, kThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(
-      plan->map_x, plan->map_wa, plan->map_wb, plan->map_wc, plan->map_res, plan->map_out, plan->params);
+  if (plan->params.dbg)
+    bottleneck_fused_kernel<true><<<plan->grid, kThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+        plan->map_x, plan->map_wa, plan->map_wb, plan->map_wc, plan->map_res, plan->map_out, plan->params);
+  else
+    bottleneck_fused_kernel<false><<<plan->grid, kThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+        plan->map_x, plan->map_wa, plan->map_wb, plan->map_wc, plan->map_res, plan->map_out, plan->params);
   VSB_CHECK_LAUNCH("bottleneck_fused_kernel");
   return VSB_OK;
 }
 
 extern "C" void vsb_bottleneck_plan_destroy(vsb_bottleneck_plan* plan) { delete plan; }
 
+extern "C" int vsb_debug_bottleneck_stats(const vsb_bottleneck_plan* plan, long long* out32) {
+  VSB_CHECK_ARG(plan && out32, "null argument");
+  VSB_CHECK_ARG(plan->params.dbg, "plan was not created with VSB_FUSED_DEBUG=1");
+  VSB_CHECK_CUDA(cudaDeviceSynchronize());
+  VSB_CHECK_CUDA(cudaMemcpy(out32, plan->params.dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+  VSB_CHECK_CUDA(cudaMemset(plan->params.dbg, 0, 32 * sizeof(long long)));
+  return VSB_OK;
+}
+
 extern "C" int vsb_bottleneck_plan_info(const vsb_bottleneck_plan* plan, long long* out8) {
   VSB_CHECK_ARG(plan && out8, "null argument");
   const FusedParams& p = plan->params;
   out8[0] = p.RP;
   out8[1] = p.FP;
-  out8[2] = p.stages;
-  out8[3] = p.walk_len;
+  out8[2] = p.stages * 100 + p.cps;
+  out8[3] = p.tiles_per_cta;
   out8[4] = plan->grid;
   out8[5] = (long long)plan->smem_bytes;
   out8[6] = p.tiles_per_clip;

@@ -127,6 +127,63 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int n, int iters, int a_
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+
+// Issue-rate probe 2: `groups` groups of `per_group` MMAs (M=128, N=n, K=16), a tcgen05.commit after every group
+// (commit_each != 0) or only at the end; the A operand has `row_bytes` rows and its start address is shifted by
+// `shift_rows` rows (+1 row per MMA inside a group when walk != 0, like the taps of a 3x3 window).  Reports the
+// cycles of the issuing thread until its last instruction has been issued (clk[2*cta]) and until completion
+// (clk[2*cta+1]).
+__global__ void __launch_bounds__(128) umma_rate2_kernel(int n, int groups, int per_group, int commit_each, int row_bytes,
+                                                         int shift_rows, int walk, long long* clk) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t done, sink;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t total = 3u * 16384u + 256u * 128u;
+  for (uint32_t i = threadIdx.x * 16; i < total; i += blockDim.x * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(&done, 1);
+    mbar_init(&sink, 1u << 20);
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, n);
+    const uint32_t a0 = smem_u32(smem) + (uint32_t)shift_rows * row_bytes, b0 = smem_u32(smem) + 3u * 16384u;
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      for (int g = 0; g < groups; ++g) {
+        for (int k = 0; k < per_group; ++k)
+          umma_bf16(tmem + (g & 1) * n, umma_smem_desc(a0 + (walk ? (uint32_t)k * row_bytes : 0u), row_bytes),
+                    umma_smem_desc(b0, row_bytes), idesc, k != 0 ? 1u : 0u);
+        if (commit_each) umma_commit(&sink);
+      }
+      umma_commit(&done);
+      t1 = clock64();
+    }
+    __syncwarp();
+    mbar_wait(&done, 0);
+    const long long t2 = clock64();
+    if (t0) {
+      clk[2 * blockIdx.x] = t1 - t0;
+      clk[2 * blockIdx.x + 1] = t2 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -190,5 +247,19 @@ extern "C" int vsb_debug_umma_rate(int n, int iters, int a_tiles, int a_from_sam
   VSB_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   umma_rate_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(n, iters, a_tiles, a_from_same, clk);
   VSB_CHECK_LAUNCH("umma_rate_kernel");
+  return VSB_OK;
+}
+
+// clk: int64 [2 * grid]: (issue cycles, completion cycles) per CTA
+extern "C" int vsb_debug_umma_rate2(int n, int groups, int per_group, int commit_each, int row_bytes, int shift_rows,
+                                    int walk, int grid, long long* clk, void* stream) {
+  VSB_CHECK_ARG(clk && n >= 16 && n <= 128 && n % 16 == 0 && groups > 0 && per_group > 0 && per_group <= 64, "bad argument");
+  VSB_CHECK_ARG(row_bytes == 32 || row_bytes == 64 || row_bytes == 128, "row_bytes must be 32/64/128");
+  VSB_CHECK_ARG(shift_rows >= 0 && shift_rows <= 128, "bad shift");
+  const size_t smem = 3 * 16384 + 256 * 128 + 2048;
+  VSB_CHECK_CUDA(cudaFuncSetAttribute(umma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  umma_rate2_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(n, groups, per_group, commit_each, row_bytes,
+                                                                            shift_rows, walk, clk);
+  VSB_CHECK_LAUNCH("umma_rate2_kernel");
   return VSB_OK;
 }

@@ -25,7 +25,7 @@ import torch
 from . import ops
 from .arch import BlockSpec, ConvSpec, NetSpec, NonlocalSpec
 from .lib import VSB_BF16, VSB_F32, VsbError
-from .ops import Act, ConvPlan
+from .ops import Act, BottleneckPlan, ConvPlan
 from .weights import (bn_tensor_keys, fold_bn, group_conv_weight, group_tap_ranges, identity_affine, pack_conv_weight, round_up,
                       slice_tap_channels)
 
@@ -73,7 +73,8 @@ class _Pool:
 class ClipEngine:
     def __init__(self, spec: NetSpec, tensors: Dict[str, torch.Tensor], n: int, dtype: int = VSB_BF16,
                  device: Optional[torch.device] = None, proj_head: Optional[Sequence[torch.Tensor]] = None,
-                 tune: Optional[dict] = None, bn_eps: float = 1e-5, input_slots: int = 1):
+                 tune: Optional[dict] = None, bn_eps: float = 1e-5, input_slots: int = 1,
+                 prep_cache: Optional[dict] = None):
         if not torch.cuda.is_available():
             raise VsbError("ClipEngine needs a CUDA device: the forward is made of sm_100a kernels only")
         self.spec = spec
@@ -84,6 +85,9 @@ class ClipEngine:
         self.tune = dict(tune or {})
         self.bn_eps = bn_eps
         self._t = tensors
+        # prepared (folded / packed / uploaded) weights, keyed by layer and layout: shared by the engines of one model
+        # (one per batch size), so only the first engine pays for the preparation
+        self._cache = prep_cache if prep_cache is not None else {}
         self._keep: List[torch.Tensor] = []
         self.trunk_ops: List[Tuple[str, Callable[[], None], float]] = []   # (name, launch, flops)
         self.head_ops: List[Tuple[str, Callable[[], None], float]] = []
@@ -110,6 +114,7 @@ class ClipEngine:
         self.op_bytes: Dict[str, float] = {}
         self.op_sig: Dict[str, str] = {}
         self.fused_shortcuts: List[str] = []   # branch1 convs computed inside their block's last conv
+        self.fused_blocks: List[str] = []      # identity blocks that run as one fused a-b-c launch
         self.crop = spec.crop
         if self.crop % 16:
             raise VsbError("crop size must be a multiple of 16")
@@ -147,7 +152,8 @@ class ClipEngine:
             off += x.c_real
         self.logits = None
         if proj_head is not None:
-            w0, b0, w1, b1 = [t.detach().to(self.device, torch.float32).contiguous() for t in proj_head]
+            w0, b0, w1, b1 = self._memo(("proj_head",), lambda: tuple(
+                t.detach().to(self.device, torch.float32).contiguous() for t in proj_head))
             self._keep += [w0, b0, w1, b1]
             self.hidden = torch.zeros((self.n, w0.shape[0]), dtype=torch.float32, device=self.device)
             self.logits = torch.zeros((self.n, w1.shape[0]), dtype=torch.float32, device=self.device)
@@ -186,17 +192,36 @@ class ClipEngine:
         self._pool.give(a.buf)
 
     def _tensor(self, key: str) -> torch.Tensor:
+        """Reference-layout parameter as an fp32 HOST tensor: BatchNorm folding and weight packing are done on
+        the CPU (one upload per prepared tensor instead of a dozen tiny device kernels per layer)."""
         if key not in self._t:
             raise KeyError(f"state_dict has no {key!r}")
-        return self._t[key].detach().to(self.device, torch.float32)
+        return self._t[key].detach().float().cpu()
+
+    def _memo(self, key: tuple, make):
+        """Prepared tensors of one layer / layout, built once per model (`prep_cache`)."""
+        if key not in self._cache:
+            self._cache[key] = make()
+        return self._cache[key]
+
+    def _up(self, t: torch.Tensor) -> torch.Tensor:
+        return t.contiguous().to(self.device)
 
     def _affine(self, cs: ConvSpec, cout_store: int):
+        """Folded frozen BatchNorm (or conv bias) of a conv as HOST fp32 (scale, bias)."""
         bias = self._tensor(cs.key + ".bias") if cs.has_bias else None
         if cs.bn is not None:
             kw, kb, km, kv = bn_tensor_keys(self._t, cs.bn)
             return fold_bn(self._tensor(kw), self._tensor(kb), self._tensor(km), self._tensor(kv),
                            self.bn_eps, cout_store, bias)
-        return identity_affine(cs.cout, cout_store, bias, self.device)
+        return identity_affine(cs.cout, cout_store, bias, "cpu")
+
+    def _sb(self, cs: ConvSpec, cout_store: int, j: int = 1):
+        """Device (scale, bias) of a conv, repeated for j-pixel groups."""
+        def make():
+            s, b = self._affine(cs, cout_store)
+            return self._up(s.repeat(j)), self._up(b.repeat(j))
+        return self._memo((cs.key, "sb", cout_store, j), make)
 
     def _out_dims(self, x: Act, cs: ConvSpec):
         to = (x.t + 2 * cs.pad[0] - cs.kernel[0]) // cs.stride[0] + 1
@@ -234,7 +259,7 @@ class ClipEngine:
             j //= 2
         return max(j, 1)
 
-    def _window_plan(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act], relu: bool, scale, bias, wt,
+    def _window_plan(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act], relu: bool, wt,
                      pad_w: Optional[int] = None, j: Optional[int] = None, rev_flag: int = 0) -> Optional[ConvPlan]:
         """Shared-memory window algorithm (conv_win_sm100.cu) for convs with spatial taps and <= 64
         (grouped) input channels: returns the plan, or None when the layer is outside its domain."""
@@ -260,11 +285,17 @@ class ClipEngine:
         if x.w % g or out.w % j:
             return None
         pad_w = cs.pad[2] if pad_w is None else pad_w
-        w, ngt, plo = group_conv_weight(wt, x.c, out.c, j, sw, pad_w, self.tdt)
-        if ngt > 8 or plo < 0:
+
+        def make():
+            w, ngt, plo = group_conv_weight(wt, x.c, out.c, j, sw, pad_w, self.tdt)
+            if ngt > 8 or plo < 0:
+                return None, ngt, plo, None
+            ranges = group_tap_ranges(cs.kernel[2], x.c, j, sw, pad_w)
+            return self._up(slice_tap_channels(w, cs.kernel[0] * cs.kernel[1], ngt, ranges)), ngt, plo, ranges
+        w, ngt, plo, ranges = self._memo((cs.key, "win", x.c, out.c, j, sw, pad_w), make)
+        if w is None:
             return None
-        ranges = group_tap_ranges(cs.kernel[2], x.c, j, sw, pad_w)
-        w = slice_tap_channels(w, cs.kernel[0] * cs.kernel[1], ngt, ranges)
+        scale, bias = self._sb(cs, out.c, j)
         xin = Act(x.buf, x.n, x.t, x.h, x.w // g, g * x.c, g * x.pitch if g == 1 else g * x.c, x.c_off if g == 1 else 0)
         yout = Act(out.buf, out.n, out.t, out.h, out.w // j, j * out.c, out.pitch if j == 1 else j * out.c,
                    out.c_off if j == 1 else 0)
@@ -276,7 +307,7 @@ class ClipEngine:
         try:
             return ConvPlan(self.dtype, xin, w, j * out.c, (cs.kernel[0], cs.kernel[1], ngt),
                             (cs.stride[0], cs.stride[1], 1), (cs.pad[0], cs.pad[1], plo), (cs.pad[0], cs.pad[1], phi),
-                            scale.repeat(j), bias.repeat(j), yout, res, relu, algo=2, kw_ranges=ranges,
+                            scale, bias, yout, res, relu, algo=2, kw_ranges=ranges,
                             **dict({k: v for k, v in tn.items() if k in ("stages", "epi_n", "epi_bufs")},
                                    flags=int(tn.get("flags", 0)) | rev_flag))
         except VsbError:
@@ -288,7 +319,6 @@ class ClipEngine:
               reverse: bool = False):
         if x.c_real != cs.cin:
             raise VsbError(f"{cs.key}: input has {x.c_real} channels, conv expects {cs.cin}")
-        scale, bias = self._affine(cs, out.c)
         sig = self._sig(cs, x, out, residual)
         self.op_sig[cs.key] = sig
         tune = {k: v for k, v in self._tune(cs.key, sig).items() if k in _PLAN_KNOBS}
@@ -296,7 +326,7 @@ class ClipEngine:
         tune["flags"] = int(tune.get("flags", 0)) | rev_flag
         relu = cs.relu if relu is None else relu
         wt = self._tensor(cs.key + ".weight")
-        plan = self._window_plan(cs, x, out, residual, relu, scale, bias, wt, rev_flag=rev_flag)
+        plan = self._window_plan(cs, x, out, residual, relu, wt, rev_flag=rev_flag)
         j = self._group_factor(cs, x, out, residual) if plan is None else 0
         bn = tune.get("block_n", 0)
         if bn and ((max(j, 1) * out.c) % bn or bn > max(j, 1) * out.c):
@@ -306,7 +336,9 @@ class ClipEngine:
         elif j > 1:
             sw = cs.stride[2]
             g = j * sw
-            w, ngt, plo = group_conv_weight(wt, x.c, out.c, j, sw, cs.pad[2], self.tdt)
+            w, ngt, plo = self._memo((cs.key, "grp", x.c, out.c, j, sw, cs.pad[2]), lambda: (lambda r: (
+                self._up(r[0]), r[1], r[2]))(group_conv_weight(wt, x.c, out.c, j, sw, cs.pad[2], self.tdt)))
+            scale, bias = self._sb(cs, out.c, j)
             xin = Act(x.buf, x.n, x.t, x.h, x.w // g, g * x.c, g * x.c)
             yout = Act(out.buf, out.n, out.t, out.h, out.w // j, j * out.c, j * out.c)
             res = None if residual is None else Act(residual.buf, out.n, out.t, out.h, out.w // j, j * out.c,
@@ -314,9 +346,10 @@ class ClipEngine:
             phi = yout.w - 1 + ngt - xin.w - plo
             plan = ConvPlan(self.dtype, xin, w, j * out.c, (cs.kernel[0], cs.kernel[1], ngt),
                             (cs.stride[0], cs.stride[1], 1), (cs.pad[0], cs.pad[1], plo), (cs.pad[0], cs.pad[1], phi),
-                            scale.repeat(j), bias.repeat(j), yout, res, relu, **tune)
+                            scale, bias, yout, res, relu, **tune)
         else:
-            w = pack_conv_weight(wt, x.c, out.c, self.tdt)
+            w = self._memo((cs.key, "plain", x.c, out.c), lambda: self._up(pack_conv_weight(wt, x.c, out.c, self.tdt)))
+            scale, bias = self._sb(cs, out.c)
             plan = ConvPlan(self.dtype, x, w, out.c, cs.kernel, cs.stride, cs.pad, None, scale, bias, out, residual,
                             relu, **tune)
         self._keep.append(plan)
@@ -338,18 +371,22 @@ class ClipEngine:
             return False
         if b.c % 64 or b.pitch != b.c or b.c_off or x.c_off or x.c_real != br.cin or x.c < 64 or out.c % 16:
             return False
-        s_c, b_c = self._affine(c, out.c)
-        s_1, b_1 = self._affine(br, out.c)
-        use_c = s_c.abs() >= s_1.abs()
-        s = torch.where(use_c, s_c, s_1)
-        safe = torch.where(s == 0, torch.ones_like(s), s)
-        r_c = torch.where(s == 0, torch.zeros_like(s), s_c / safe)
-        r_1 = torch.where(s == 0, torch.zeros_like(s), s_1 / safe)
         kchunk = 64
         k2 = round_up(x.c, kchunk)
-        w_c = pack_conv_weight(self._tensor(c.key + ".weight"), b.c, out.c, torch.float32).reshape(out.c, b.c)
-        w_1 = pack_conv_weight(self._tensor(br.key + ".weight"), k2, out.c, torch.float32).reshape(out.c, k2)
-        w = torch.cat([w_c * r_c[:, None], w_1 * r_1[:, None]], dim=1).to(self.tdt).contiguous()
+
+        def make():
+            s_c, b_c = self._affine(c, out.c)
+            s_1, b_1 = self._affine(br, out.c)
+            use_c = s_c.abs() >= s_1.abs()
+            s = torch.where(use_c, s_c, s_1)
+            safe = torch.where(s == 0, torch.ones_like(s), s)
+            r_c = torch.where(s == 0, torch.zeros_like(s), s_c / safe)
+            r_1 = torch.where(s == 0, torch.zeros_like(s), s_1 / safe)
+            w_c = pack_conv_weight(self._tensor(c.key + ".weight"), b.c, out.c, torch.float32).reshape(out.c, b.c)
+            w_1 = pack_conv_weight(self._tensor(br.key + ".weight"), k2, out.c, torch.float32).reshape(out.c, k2)
+            w = torch.cat([w_c * r_c[:, None], w_1 * r_1[:, None]], dim=1).to(self.tdt)
+            return self._up(w), self._up(s), self._up(b_c + b_1)
+        w, s, b_sum = self._memo((c.key, "dual", b.c, k2, out.c), make)
         sig = self._sig(c, b, out, None, x)
         self.op_sig[c.key] = sig
         tune = {k: v for k, v in self._tune(c.key, sig).items() if k in _PLAN_KNOBS and k != "kchunk"}
@@ -357,7 +394,7 @@ class ClipEngine:
             tune.pop("block_n")
         tune["flags"] = int(tune.get("flags", 0)) | (128 if (reverse and self.alternate) else 0)
         try:
-            plan = ConvPlan(self.dtype, b, w, out.c, c.kernel, c.stride, c.pad, None, s, b_c + b_1, out, None, True,
+            plan = ConvPlan(self.dtype, b, w, out.c, c.kernel, c.stride, c.pad, None, s, b_sum, out, None, True,
                             kchunk=kchunk, x2=x, stride2=br.stride, **tune)
         except VsbError:
             if self._tune(c.key).get("fuse_shortcut") is True:
@@ -387,7 +424,6 @@ class ClipEngine:
 
     def _stem_plan(self, cs: ConvSpec, x: Act, y: Act, to: int, ho: int, wo: int) -> ConvPlan:
         n, t = x.n, x.t
-        scale, bias = self._affine(cs, cs.cout)
         wt = self._tensor(cs.key + ".weight")
         tune = {k: v for k, v in self._tune(cs.key).items() if k in _PLAN_KNOBS}
         plan = None
@@ -399,7 +435,7 @@ class ClipEngine:
             # (kt == 1 stems: off by default -- 32-byte slots make the TMA box loads request-rate bound.)
             xw = Act(x.buf, n, t, x.h, self.w_buf, 4, 4)
             yw = Act(y.buf, n, to, ho, wo, cs.cout, cs.cout)
-            plan = self._window_plan(cs, xw, yw, None, True, scale, bias, wt, pad_w=cs.pad[2] - self.x_off,
+            plan = self._window_plan(cs, xw, yw, None, True, wt, pad_w=cs.pad[2] - self.x_off,
                                      j=self._tune(cs.key).get("win_group", 4 if cs.kernel[0] > 1 else 2))
         if plan is not None:
             pass
@@ -413,7 +449,9 @@ class ClipEngine:
             g = j * sw
             if (j * cs.cout) % 16 or self.w_buf % g or g * 4 < 16:
                 raise VsbError("stem geometry outside the pixel-group restatement")
-            wq, ngt, plo = group_conv_weight(wt, 4, cs.cout, j, sw, cs.pad[2] - self.x_off, self.tdt)
+            wq, ngt, plo = self._memo((cs.key, "grp", 4, cs.cout, j, sw, cs.pad[2] - self.x_off), lambda: (lambda r: (
+                self._up(r[0]), r[1], r[2]))(group_conv_weight(wt, 4, cs.cout, j, sw, cs.pad[2] - self.x_off, self.tdt)))
+            scale, bias = self._sb(cs, cs.cout, j)
             xin = Act(x.buf, n, t, x.h, self.w_buf // g, g * 4, g * 4)
             yout = Act(y.buf, n, to, ho, wo // j, j * cs.cout, j * cs.cout)
             phi = yout.w - 1 + ngt - xin.w - plo
@@ -421,9 +459,10 @@ class ClipEngine:
                 raise VsbError("stem pixel-group geometry does not close")
             plan = ConvPlan(self.dtype, xin, wq, j * cs.cout, (cs.kernel[0], cs.kernel[1], ngt),
                             (cs.stride[0], cs.stride[1], 1), (cs.pad[0], cs.pad[1], plo),
-                            (cs.pad[0], cs.pad[1], phi), scale.repeat(j), bias.repeat(j), yout, None, True, **tune)
+                            (cs.pad[0], cs.pad[1], phi), scale, bias, yout, None, True, **tune)
         else:
-            wp = pack_conv_weight(wt, 4, cs.cout, self.tdt)
+            wp = self._memo((cs.key, "plain", 4, cs.cout), lambda: self._up(pack_conv_weight(wt, 4, cs.cout, self.tdt)))
+            scale, bias = self._sb(cs, cs.cout)
             plan = ConvPlan(self.dtype, x, wp, cs.cout, cs.kernel, cs.stride, cs.pad, None, scale, bias, y, None,
                             True)
         return plan
@@ -438,11 +477,72 @@ class ClipEngine:
         self.trunk_ops.append((name, lambda: ops.maxpool3d(x, y, kernel, stride, pad, self.dtype), 0.0))
         return y
 
+    def _fused_block(self, x: Act, blk: BlockSpec, out_pitch: Optional[int]) -> Optional[Act]:
+        """Identity ResBlock (no projection shortcut, unit strides) as ONE launch of the fused bottleneck kernel
+        (vsb_bottleneck_*, bottleneck_fused_sm100.cu): a's and b's outputs never reach HBM.  Thin layers are
+        restated on J-pixel groups (J * d = 16 channels at least) exactly like the single convs.  Returns None
+        when the block is outside the kernel's domain (then the three-launch path runs)."""
+        tn = self._tune(blk.prefix)
+        if self.dtype != VSB_BF16 or blk.branch1 is not None or blk.nonlocal_ is not None:
+            return None
+        if str(tn.get("fuse_block", os.environ.get("VSB_FUSE_BLOCK", "1"))) != "1":
+            return None
+        a, b, c = blk.a, blk.b, blk.c
+        if (tuple(a.kernel[1:]) != (1, 1) or a.kernel[0] not in (1, 3) or tuple(b.kernel) != (1, 3, 3)
+                or tuple(c.kernel) != (1, 1, 1) or any(s != 1 for cs in (a, b, c) for s in cs.stride)
+                or tuple(a.pad) != (a.kernel[0] // 2, 0, 0) or tuple(b.pad) != (0, 1, 1) or tuple(c.pad) != (0, 0, 0)
+                or c.cout != a.cin or x.c_real != a.cin or x.c_off or x.pitch != x.c):
+            return None
+        if out_pitch is not None and out_pitch != self._store(c.cout):
+            return None   # channel-slice outputs (the slow pathway's concat buffers) stay on the three-launch path
+        d_store = self._store(a.cout)
+        j = 1
+        while j * d_store < 16:
+            j *= 2
+        if x.w % j or (j * d_store) % 16 or j * d_store > 64 or (j * x.c) % 16 or j * x.c > 256:
+            return None
+        kt = a.kernel[0]
+
+        def make():
+            wa, _, _ = group_conv_weight(self._tensor(a.key + ".weight"), x.c, d_store, j, 1, 0, self.tdt)
+            wb, ngt, plo = group_conv_weight(self._tensor(b.key + ".weight"), d_store, d_store, j, 1, 1, self.tdt)
+            wc, _, _ = group_conv_weight(self._tensor(c.key + ".weight"), d_store, x.c, j, 1, 0, self.tdt)
+            if ngt != 3 or plo != 1:
+                return None
+            return self._up(wa), self._up(wb), self._up(wc)
+        w = self._memo((blk.prefix, "fused", x.c, d_store, j), make)
+        if w is None:
+            return None
+        sa, ba = self._sb(a, d_store, j)
+        sb_, bb = self._sb(b, d_store, j)
+        sc, bc = self._sb(c, x.c, j)
+        y = self._alloc(x.n, x.t, x.h, x.w, c.cout)
+        xg = Act(x.buf, x.n, x.t, x.h, x.w // j, j * x.c, j * x.c)
+        yg = Act(y.buf, y.n, y.t, y.h, y.w // j, j * y.c, j * y.c)
+        try:
+            plan = BottleneckPlan(xg, yg, j * d_store, kt, w[0], w[1], w[2], sa, ba, sb_, bb, sc, bc)
+        except VsbError:
+            if tn.get("fuse_block") is True:
+                raise
+            self._free(y)
+            return None
+        self._keep.append(plan)
+        name = blk.prefix + ".fused_abc"
+        self.op_bytes[name] = 2.0 * (x.pixels * x.c + y.pixels * y.c)
+        self.trunk_ops.append((name, plan.run, float(x.pixels) * (a.flops_per_out_pixel + b.flops_per_out_pixel
+                                                                  + c.flops_per_out_pixel)))
+        self.fused_blocks.append(blk.prefix)
+        self._free(x)
+        return y
+
     def _block(self, x: Act, blk: BlockSpec, out_pitch: Optional[int]) -> Act:
         n = x.n
         pw = self._pools.index(self._pool)
         d = self._rev[pw]              # a and c walk in direction d, b against it; the next block flips
         self._rev[pw] = not d
+        fused = self._fused_block(x, blk, out_pitch)
+        if fused is not None:
+            return fused
         ta, ha, wa = self._out_dims(x, blk.a)
         a = self._alloc(n, ta, ha, wa, blk.a.cout)
         self._conv(blk.a, x, a, reverse=d)

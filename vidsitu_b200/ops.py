@@ -192,8 +192,14 @@ class BottleneckPlan:
     def info(self) -> dict:
         out = (C.c_longlong * 8)()
         check(self._lib.vsb_bottleneck_plan_info(self._h, out), "vsb_bottleneck_plan_info")
-        keys = ("rp", "fp", "stages", "walk_len", "grid", "smem_bytes", "tiles_per_clip", "tmem_cols")
+        keys = ("rp", "fp", "stages_x100_cps", "tiles_per_cta", "grid", "smem_bytes", "tiles_per_clip", "tmem_cols")
         return dict(zip(keys, [int(v) for v in out]))
+
+    def stats(self) -> list:
+        """Role timeline counters (plan created under VSB_FUSED_DEBUG=1); clears them."""
+        out = (C.c_longlong * 32)()
+        check(self._lib.vsb_debug_bottleneck_stats(self._h, out), "vsb_debug_bottleneck_stats")
+        return [int(v) for v in out]
 
     def __del__(self):
         h = getattr(self, "_h", None)
