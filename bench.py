@@ -112,6 +112,53 @@ def cpu_reference_clips_per_s(steps: int, warmup: int, clips: int = 5):
     return clips * steps / dt, dt / steps * 1e3, cores
 
 
+def gpu_library_baseline(model, cfg, host_frames, dev, iters: int = 3):
+    """Informational: the reference's own torch modules (oracle restatement of the same forward: F.conv3d ->
+    cuDNN 9, F.batch_norm, ...) on THIS GPU at the bench batch, (a) fp32 with TF32 off = "reference PyTorch fp32 on
+    B200", (b) bf16 channels_last_3d = the cuDNN Blackwell bar (SURVEY.md 2.1 / BASELINE.md 3).  Inputs already on
+    the device and normalised (the frame pack is not part of this leg).  Returns clips/s of both."""
+    import torch
+    from oracle import sf_oracle as O
+
+    out = {}
+    n = host_frames.shape[0]
+    xs32 = [x.to(dev) for x in O.clips_from_frames(host_frames, cfg.sf_mdl)]
+    sd32 = {k: v.detach().to(dev, torch.float32) for k, v in model.state_dict().items()}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32, dt in (("torch_fp32_tf32off", False, torch.float32), ("torch_bf16_channels_last_3d", True, torch.bfloat16)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            if dt is torch.float32:
+                sd, xs = sd32, xs32
+            else:
+                sd = {k: (v.to(dt).contiguous(memory_format=torch.channels_last_3d) if v.dim() == 5 else v.to(dt))
+                      for k, v in sd32.items()}
+                xs = [x.to(dt).contiguous(memory_format=torch.channels_last_3d) for x in xs32]
+            try:
+                for _ in range(2):
+                    O.sfbase_forward(sd, cfg.sf_mdl, xs)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    O.sfbase_forward(sd, cfg.sf_mdl, xs)
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_time(e1) / iters
+                out[name] = {"clips_per_s": round(n / (ms / 1e3), 1), "ms_per_step": round(ms, 2)}
+            except Exception as e:  # noqa: BLE001 -- informational leg: never fails the bench
+                out[name] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+            del sd, xs
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    out["note"] = ("oracle restatement of the reference modules run through torch/cuDNN on this GPU, batch "
+                   f"{n}, device-resident normalised inputs, forward + head; informational, not a fallback")
+    return out
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
@@ -122,7 +169,10 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": "event clips/sec SlowFast-R50 8x8", "value": round(val, 4), "unit": "clips/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": round(ms, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference path = CPU fp32 forward (the reference's own test-free "
+        "config": {"workload": "SlowFast-R50 8x8 forward, 1 synthetic video x 5 event clips (32x224x224 fast / 8 slow) per "
+                               "step, fp32 on the host CPU cores (BASELINE.json configs[0]); clips/s is batch-size "
+                               "independent on this arm", "clips_per_step": 5, "headline_workload": WORKLOAD,
+                   "note": "reference path = CPU fp32 forward (the reference's own test-free "
                    "PyTorch modules restated in oracle/sf_oracle.py and pinned to the real reference's outputs)"},
         "cpu_baseline": {"value": round(val, 4), "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 4), "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -133,7 +183,7 @@ def run_reference(args, rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
@@ -141,6 +191,8 @@ def main():
                     "the default is the headline SlowFast-R50 8x8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true",
+                    help="skip the informational torch/cuDNN leg (reference modules on this GPU, fp32 and bf16)")
     ap.add_argument("--overlap-pack", action="store_true",
                     help="two input slots: the pack of batch k+1 runs on its own stream while the trunk reads batch k "
                          "(measured on B200: no gain, 5628 vs 5665 clips/s - the persistent conv CTAs leave it no room)")
@@ -267,35 +319,71 @@ def main():
                "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                "ms_per_step": round(e2e_ms / args.steps, 3), "checksum": round(checksum, 4)}
 
-    # ---- roofline of the dominant kernel (conv_igemm_kernel): CUDA events around every launch, eager
+    # ---- roofline of the conv launches.  The step is a CUDA graph, so the conv time INSIDE the timed region is the
+    # graph-replayed step time minus the (eagerly timed) frame pack, times the conv launches' share of the eagerly
+    # timed trunk + head (CUDA events around every launch; the ncu launch list under profiles/ gives the same share).
     peak_sus, peak_burst, hbm, peak_src = measured_peaks()
     per_op = eng.time_ops(iters=3) if rank == 0 else []
     roofline = None
     if rank == 0:
+        ms_step = ms / args.steps
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pack_ms = float("inf")
+        for i in range(3):
+            p0.record()
+            eng.load_frames(dev_frames[i % 2])
+            p1.record()
+            p1.synchronize()
+            pack_ms = min(pack_ms, p0.elapsed_time(p1))
         conv = [(n, ms_, f) for n, ms_, f in per_op if f > 0 and not n.startswith("proj_head")]
-        conv_ms = sum(ms_ for _, ms_, _ in conv)
-        all_ms = sum(ms_ for _, ms_, _ in per_op)
+        conv_eager = sum(ms_ for _, ms_, _ in conv)
+        all_eager = sum(ms_ for _, ms_, _ in per_op)
+        share = conv_eager / all_eager
+        conv_ms = max(ms_step - pack_ms, 0.0) * share          # conv time inside the graph-replayed step
+        assert conv_ms <= ms_step
         flops = (GFLOP_PER_CLIP * 1e9 if args.model == MODEL else eng.conv_flops / B) * B
         achieved = flops / (conv_ms / 1e3) / 1e12
-        traffic = None   # DRAM bytes of the conv launches of one step, from the committed ncu capture
-        tp = os.path.join(ROOT, "profiles", "r01_step_dram_traffic.json")
-        if os.path.exists(tp) and B == 64 and args.model == MODEL:
-            ks = json.load(open(tp))["kernels"]
-            traffic = int(sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks if k["kernel"].startswith("conv_")))
-        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_igemm2_kernel + conv_win_kernel (all conv launches of a step)",
-                    "achieved": round(achieved, 2),
-                    "peak": peak_sus, "unit": "TFLOP/s", "frac": round(achieved / peak_sus, 4), "traffic": traffic,
-                    "traffic_note": "dram__bytes_read+write summed over the conv launches of one step (ncu, "
-                                    "profiles/r01_step_dram_traffic.json); algorithmic activation bytes 46 GB",
-                    "peak_source": f"{peak_src} bf16_tflops_sustained (burst {peak_burst})",
-                    "launches_per_step": len(conv), "conv_ms_per_step": round(conv_ms, 3),
-                    "conv_share_of_step": round(conv_ms / all_ms, 4),
-                    "step_tflops": round(flops / (ms / args.steps / 1e3) / 1e12, 2),
-                    "step_frac": round(flops / (ms / args.steps / 1e3) / 1e12 / peak_sus, 4)}
+        step_tf = flops / (ms_step / 1e3) / 1e12
+        traffic = traffic_all = None   # DRAM bytes of one step, from the committed ncu capture of this round
+        tsrc = None
+        for cand in ("r02_step_dram_traffic.json", "r01_step_dram_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", cand)
+            if os.path.exists(tp) and B == 64 and args.model == MODEL:
+                ks = json.load(open(tp))["kernels"]
+                traffic = int(sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks if k["kernel"].startswith(("conv_", "bottleneck_"))))
+                traffic_all = int(sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks))
+                tsrc = cand
+                break
+        roofline = {"bound": "tensor", "kernel": "all conv launches of a step (conv_igemm_kernel, conv_igemm2_kernel, "
+                    "conv_win_kernel, bottleneck_fused_kernel)",
+                    "achieved": round(achieved, 2), "peak": peak_sus, "unit": "TFLOP/s",
+                    "frac": round(achieved / peak_sus, 4), "frac_sustained": round(achieved / peak_sus, 4),
+                    "frac_burst": round(achieved / peak_burst, 4), "peak_burst": peak_burst,
+                    "peak_source": f"{peak_src}: bf16_tflops_sustained (kernels timed inside a long step) and bf16_tflops (burst)",
+                    "traffic": traffic,
+                    "traffic_note": f"dram__bytes_read+write of the conv launches of one step (ncu, profiles/{tsrc}); not "
+                                    "re-measured by this run",
+                    "launches_per_step": len(conv), "conv_ms_per_step": round(conv_ms, 3), "pack_ms_per_step": round(pack_ms, 3),
+                    "conv_share_of_trunk_and_head": round(share, 4), "eager_conv_ms_sum": round(conv_eager, 3),
+                    "step_tflops": round(step_tf, 2), "step_frac": round(step_tf / peak_sus, 4),
+                    "step_frac_burst": round(step_tf / peak_burst, 4),
+                    "hbm": None if traffic_all is None else {
+                        "dram_bytes_per_step": traffic_all, "gbs": round(traffic_all / (ms_step / 1e3) / 1e9, 1),
+                        "peak_gbs": hbm, "frac": round(traffic_all / (ms_step / 1e3) / 1e9 / hbm, 4)}}
         if args.per_op:
             json.dump([{"op": n, "ms": round(m, 4), "gflop": round(f / 1e9, 3),
                         "mbytes": round(eng.op_bytes.get(n, 0) / 1e6, 2)} for n, m, f in per_op],
                       open(args.per_op, "w"), indent=0)
+
+    gpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        try:
+            gpu_baseline = gpu_library_baseline(model, cfg, host_frames[0], dev)
+            for k, v in gpu_baseline.items():
+                if isinstance(v, dict) and "clips_per_s" in v:
+                    v["ours_speedup"] = round(value / v["clips_per_s"], 2)
+        except Exception as e:  # noqa: BLE001
+            gpu_baseline = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -316,7 +404,9 @@ def main():
                              "activations >> 126 MB", "cuda_graph": True, "pack_overlap": nslots > 1,
                        "parallelism": f"clip-sharded x{world}, features all-gathered each step" if world > 1 else "single GPU"},
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "cpu_baseline_note": None if cpu_baseline is not None else "measured on rank 0 at N=1 only (see --impl reference)",
+            "gpu_baseline": gpu_baseline, "fused_blocks": len(getattr(eng, "fused_blocks", [])), "clocks": clocks,
         }))
     if world > 1:
         dist.destroy_process_group()

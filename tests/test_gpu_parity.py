@@ -162,6 +162,31 @@ def test_conv_with_fused_shortcut(case):
     assert info["ok"], info
 
 
+def _fused_cases():
+    import gpu_check_fused as GF
+    return [c for c in GF.CASES if c[0] not in ("kt1_c64_d64", "c256_d64_kt1_small")]
+
+
+@pytest.mark.parametrize("case", _fused_cases(), ids=lambda c: c[0])
+def test_fused_bottleneck_block(case):
+    """bottleneck_fused_sm100.cu (vsb_bottleneck_*): a -> b -> c + residual of an identity ResBlock in one launch vs
+    torch conv3d x3 with the two intermediates rounded to bf16 where the three-launch path rounds them."""
+    import gpu_check_fused as GF
+    info = GF.run_case(case)
+    assert info["ok"], info
+
+
+def test_fused_bottleneck_rejects_what_it_cannot_run():
+    """Outside its domain (shared memory / TMEM budget, widths) the plan fails with a message; nothing falls back
+    silently inside the library."""
+    import gpu_check_fused as GF
+    from vidsitu_b200.lib import VsbError
+    for name in ("kt1_c64_d64", "c256_d64_kt1_small"):
+        case = [c for c in GF.CASES if c[0] == name][0]
+        with pytest.raises(VsbError):
+            GF.run_case(case)
+
+
 def test_memory_bound_ops():
     import gpu_check_ops as G
     res = G.run_mem_checks()
@@ -211,7 +236,7 @@ def test_bf16_features_match_reference(case):
 
 
 @pytest.mark.parametrize("case", ["sf50_n2_64", "i3d_nln_n2_64", "sf101_n2_64", "sf50_subbn_n2_64", "sf50_n5_224",
-                                  "i3d_nln_n2_224"])
+                                  "i3d_n2_224", "i3d_nln_n2_224"])
 def test_fp32_top5_and_features_match_reference(case):
     g = np.load(os.path.join(GOLD, case + ".npz"))
     _, _, _, feats, logits = _run_model(case, "fp32")
@@ -256,6 +281,52 @@ def test_dropin_surface_matches_reference_contract():
         assert float(np.abs(samp - ref).max()) <= 0.05 * float(np.abs(ref).max())
 
 
+def test_fused_blocks_inside_the_network():
+    """Engine with the identity blocks of the Fast pathway (res2 on 2-pixel groups, res3, res4) as fused launches
+    (tune fuse_block): within the bf16 tolerance of the reference's outputs, and as close to the three-launch engine
+    as two bf16 roundings of the same sums can be."""
+    case = "sf50_n2_64"
+    m = META[case]
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    frames = synthetic_frames(m["clips"], 32, m["crop"], seed=1234 + m["seed"]).cuda()
+    outs = {}
+    for fuse in ("0", "1"):
+        model, cfg, _ = build_model(m["sf_mdl_name"], seed=m["seed"], crop=m["crop"], tune={"*": {"fuse_block": fuse}})
+        model = model.cuda()
+        outs[fuse] = model.extract_features(frames).cpu().numpy()
+        eng = model._engine(m["clips"], frames.device)
+        assert (len(eng.fused_blocks) > 0) == (fuse == "1"), eng.fused_blocks
+    assert_bf16_close(outs["1"], g["pooled"], "fused-block engine pooled")
+    assert cosine(outs["1"], outs["0"]) >= 0.99999
+
+
+def test_extract_features_returns_a_copy():
+    """The engine's output buffers are static (CUDA graph): a caller that keeps the returned tensor across calls must
+    not see it change."""
+    model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=10, crop=64)
+    model = model.cuda()
+    a = synthetic_frames(2, 32, 64, seed=1).cuda()
+    b = synthetic_frames(2, 32, 64, seed=2).cuda()
+    fa, la = model.extract_features(a, want_logits=True)
+    keep_f, keep_l = fa.clone(), la.clone()
+    fb, _ = model.extract_features(b, want_logits=True)
+    assert not torch.equal(fa, fb)
+    assert torch.equal(fa, keep_f) and torch.equal(la, keep_l)
+
+
+def test_tail_batch_engine_shares_prepared_weights():
+    """A second batch size re-uses the folded / packed weights of the first engine (prepared once per model)."""
+    model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=10, crop=64)
+    model = model.cuda()
+    f5 = model.extract_features(synthetic_frames(5, 32, 64, seed=3).cuda())
+    prep = model._prep[("bf16", "cuda:%d" % torch.cuda.current_device())]
+    n_prepared = len(prep)
+    ids = {k: id(v) for k, v in prep.items()}
+    f2 = model.extract_features(synthetic_frames(5, 32, 64, seed=3)[:2].contiguous().cuda())
+    assert len(prep) == n_prepared and all(id(prep[k]) == i for k, i in ids.items())
+    assert torch.equal(f2, f5[:2])
+
+
 def test_state_dict_roundtrip_and_reload_changes_output():
     model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=10, crop=64)
     model = model.cuda()
@@ -296,6 +367,93 @@ def test_full_size_batch64_properties():
     assert torch.equal(f_perm, f_a[perm])                          # permutation equivariance
     got = f_a[:5].cpu().numpy()
     assert_bf16_close(got, g["pooled"], "batch-64 pooled[:5]")
+
+
+@pytest.mark.parametrize("name", ["slow_fast_nl_r50_8x8", "i3d_r50_nl_8x8"])
+def test_batch64_every_clip_against_fp32_truth(name):
+    """BASELINE.json configs 2 / 3 at full size: ALL 64 clips of the bf16 run against on-box fp32 truth.  The truth
+    is this package's fp32 mode (CUDA-core kernels), which the golden tests pin to the CPU reference at 1e-6; the five
+    golden clips are checked against the committed reference outputs as well."""
+    gold = {"slow_fast_nl_r50_8x8": "sf50_n5_224", "i3d_r50_nl_8x8": "i3d_nln_n2_224"}[name]
+    m = META[gold]
+    g = np.load(os.path.join(GOLD, gold + ".npz"))
+    t = 32 if name.startswith("slow_fast") else 8
+    frames = torch.cat([synthetic_frames(m["clips"], t, 224, seed=1234 + m["seed"]),
+                        synthetic_frames(64 - m["clips"], t, 224, seed=999)]).cuda()
+    res = {}
+    for prec in ("fp32", "bf16"):
+        model, cfg, _ = build_model(name, seed=m["seed"], crop=224, precision=prec, micro_batch=64 if prec == "bf16" else 16)
+        model = model.cuda()
+        f, lg = model.extract_features(frames, want_logits=True)
+        res[prec] = (f.cpu().numpy(), lg.cpu().numpy())
+        del model
+        torch.cuda.empty_cache()
+    truth, truth_lg = res["fp32"]
+    assert rel_err(truth[:m["clips"]], g["pooled"], floor_frac=0.1) <= 1e-3       # truth == the reference on the golden clips
+    assert_bf16_close(res["bf16"][0], truth, f"{name} batch-64 pooled, all clips")
+    assert cosine(res["bf16"][1], truth_lg) >= 0.9999
+
+
+def test_sharded_run_is_bit_identical_to_the_whole_batch():
+    """BASELINE.json config 4 in one process: SlowFast-R101 16x8 clips split into two shards (two engines, as two
+    ranks would run them) give bit for bit the rows of the unsharded run (tools/gpu_shard_check.py does the same over
+    NCCL on 2/4/8 GPUs)."""
+    from vidsitu_b200.dist import shard_range
+    model, cfg, _ = build_model("slow_fast_r101_16x8", seed=3, crop=64, micro_batch=10)
+    model = model.cuda()
+    frames = synthetic_frames(10, 64, 64, seed=5).cuda()          # 2 videos x 5 events
+    whole = model.extract_features(frames)
+    parts = []
+    for r in range(2):
+        lo, hi = shard_range(2, 2, r)                              # videos of rank r
+        parts.append(model.extract_features(frames[5 * lo:5 * hi].contiguous()))
+    assert torch.equal(torch.cat(parts), whole)
+
+
+def test_checkpoints_through_the_feature_dump_cli(tmp_path):
+    """SURVEY 8(f1) end to end: a PySlowFast Caffe2 .pkl (--is-cu) and a VidSitu .pth with the DataParallel `module.`
+    prefix go through tools/extract_features.py --mdl-resume-path and come out as the features the oracle computes
+    from the same weights (feat_extractor.py:147-161)."""
+    import pickle
+    import extract_features as X
+    from PIL import Image
+    from oracle import sf_oracle as O
+    from vidsitu_b200 import frames_io as F
+    from vidsitu_b200.feat_io import read_frm_feats
+    rng = np.random.default_rng(11)
+    v = "v_ckpt_seg_1"
+    d = tmp_path / "frames" / v
+    d.mkdir(parents=True)
+    for ix in range(1, 301):
+        Image.fromarray(rng.integers(0, 256, size=(48, 64, 3), dtype=np.uint8)).save(d / f"{v}_{ix:06d}.jpg")
+    (tmp_path / "split.json").write_text(json.dumps([v]))
+    src, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=31, crop=64)          # the "trained" weights
+    windows = O.event_frame_indices(32, 2)
+    paths = F.frame_paths(tmp_path / "frames", v)
+    clips = torch.from_numpy(np.stack([np.stack([F.read_img(paths[i], 64) for i in w]) for w in windows]))
+
+    # (1) VidSitu .pth, module.-prefixed, strict
+    torch.save({"model_state_dict": {"module." + k: t for k, t in src.state_dict().items()}}, tmp_path / "m.pth")
+    rc = X.main(["--frames-dir", str(tmp_path / "frames"), "--split-file", str(tmp_path / "split.json"), "--out-dir",
+                 str(tmp_path / "feats"), "--mdl-name-used", "from_pth", "--crop", "64", "--videos-per-batch", "1",
+                 "--workers", "0", "--mdl-resume-path", str(tmp_path / "m.pth")])
+    assert rc == 0
+    _, pooled, _ = O.sfbase_forward(src.state_dict(), cfg.sf_mdl, O.clips_from_frames(clips, cfg.sf_mdl))
+    assert_bf16_close(read_frm_feats(tmp_path / "feats" / "from_pth", v).numpy(), pooled.numpy(), "features from a .pth")
+
+    # (2) Caffe2 .pkl of the backbone (blob names through the reference's own name table, inverted)
+    inv = {key: c2 for c2, key in json.load(open(os.path.join(GOLD, "c2_name_pairs.json")))["slow_fast_nl_r50_8x8"]["pairs"]
+           if key is not None}
+    blobs = {inv[k[len("sf_mdl."):]]: t.numpy() for k, t in src.state_dict().items()
+             if k.startswith("sf_mdl.") and k[len("sf_mdl."):] in inv}
+    with open(tmp_path / "c2.pkl", "wb") as f:
+        pickle.dump({"blobs": blobs}, f, protocol=2)
+    torch.manual_seed(77)       # the CLI's own random init: proj_head is not in a backbone checkpoint
+    rc = X.main(["--frames-dir", str(tmp_path / "frames"), "--split-file", str(tmp_path / "split.json"), "--out-dir",
+                 str(tmp_path / "feats"), "--mdl-name-used", "from_pkl", "--crop", "64", "--videos-per-batch", "1",
+                 "--workers", "0", "--mdl-resume-path", str(tmp_path / "c2.pkl"), "--is-cu"])
+    assert rc == 0
+    assert_bf16_close(read_frm_feats(tmp_path / "feats" / "from_pkl", v).numpy(), pooled.numpy(), "features from a .pkl")
 
 
 # ------------------------------------------------------------------ callers either side of the forward (SURVEY 8f)

@@ -261,3 +261,68 @@ def test_sub_batchnorm_layout_and_aggregation():
     plain, _, _ = build_model("slow_fast_nl_r50_8x8", seed=0, crop=64)
     tp = {k[len("sf_mdl."):]: v for k, v in plain.state_dict().items() if k.startswith("sf_mdl.")}
     assert bn_tensor_keys(tp, "s1.pathway0_stem.bn")[2] == "s1.pathway0_stem.bn.running_mean"
+
+
+def test_ctypes_bottleneck_desc_matches_the_c_header(tmp_path):
+    """ctypes mirror of vsb_bottleneck_desc against the C header (gcc): size and every field offset."""
+    import ctypes as C
+    fields = [f for f, _ in L.BottleneckDesc._fields_]
+    src = tmp_path / "szb.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vidsitu_b200.h"\nint main(void){'
+                   'printf("%zu", sizeof(vsb_bottleneck_desc));'
+                   + "".join(f'printf(" %zu", offsetof(vsb_bottleneck_desc, {f}));' for f in fields) + "return 0;}\n")
+    exe = tmp_path / "szb"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got[0] == C.sizeof(L.BottleneckDesc)
+    for f, off in zip(fields, got[1:]):
+        assert getattr(L.BottleneckDesc, f).offset == off, f
+    # a device-less plan_create is an error status with a message, never a crash
+    d, h = L.BottleneckDesc(), C.c_void_p()
+    assert L.load().vsb_bottleneck_plan_create(C.byref(d), C.byref(h)) != 0 and L.load().vsb_last_error()
+
+
+def test_presets_are_pinned_to_the_reference_yaml_files():
+    """config.SF_MDL_PRESETS restates the reference's backbone YAMLs in Python: every hot-path key the YAML sets must
+    come out of sf_mdl_cfg() with the YAML's value (tests/golden/yaml_presets.json is generated from the files by
+    tests/golden/make_yaml_presets.py)."""
+    import json
+    from vidsitu_b200.config import sf_mdl_cfg
+    pins = json.load(open(os.path.join(ROOT, "tests", "golden", "yaml_presets.json")))
+    assert set(pins) == set(SF_MDL_PRESETS)
+    unknown = []
+    for name, rec in pins.items():
+        cfg = sf_mdl_cfg(name)
+        for sec, kv in rec["keys"].items():
+            for k, v in kv.items():
+                if sec not in cfg or k not in cfg[sec]:
+                    unknown.append((name, sec, k))     # a key our config surface does not carry: must be irrelevant here
+                    continue
+                assert cfg[sec][k] == v, (name, rec["file"], sec, k, cfg[sec][k], v)
+    # keys the YAMLs set that the hot path never reads (SURVEY.md 8b lists what is read)
+    assert {(s, k) for _, s, k in unknown} <= {("MODEL", "LOSS_FUNC"), ("RESNET", "TRANS_FUNC"), ("DATA", "DECODING_BACKEND"),
+                                               ("DATA", "PATH_PREFIX"), ("DATA", "PATH_LABEL_SEPARATOR"),
+                                               ("DATA", "MULTI_LABEL"), ("DATA", "INV_UNIFORM_SAMPLE"),
+                                               ("DATA", "ENSEMBLE_METHOD"), ("MODEL", "HEAD_ACT")} | set(), unknown
+
+
+def test_spatial_dilation_is_refused_not_silently_wrong():
+    """RESNET.SPATIAL_DILATIONS > 1 dilates the 3x3 conv in the reference (resnet_helper.py:196-207); the kernels have
+    no dilation, so building such a spec must raise."""
+    with pytest.raises(NotImplementedError):
+        build_spec(make_cfg("i3d_r50_8x8", RESNET={"SPATIAL_DILATIONS": [[1], [1], [1], [2]]}).sf_mdl)
+    with pytest.raises(NotImplementedError):
+        build_spec(make_cfg("slow_fast_nl_r50_8x8", RESNET={"SPATIAL_DILATIONS": [[1, 1], [1, 1], [1, 2], [1, 1]]}).sf_mdl)
+
+
+def test_loading_weights_through_sf_mdl_invalidates_prepared_engines():
+    """The reference loads backbone checkpoints with load_checkpoint(model=mdl.sf_mdl, ...): every such path must drop
+    the kernels' prepared weight copies."""
+    model, _, _ = build_model("i3d_r50_8x8", seed=0, crop=64)
+    model._prep[("bf16", "cuda:0")] = {"stale": 1}
+    v0 = model._weights_version
+    model.sf_mdl.load_state_dict(model.sf_mdl.state_dict())
+    assert model._weights_version == v0 + 1 and not model._prep
+    model._prep[("bf16", "cuda:0")] = {"stale": 1}
+    model.sf_mdl.float()
+    assert not model._prep

@@ -163,3 +163,28 @@ def test_frame_ingest_matches_the_reference_reader(tmp_path):
     assert F.read_vseg_list(tmp_path / "split.json") == ["v_abc_seg_1"]
     with pytest.raises(AssertionError):
         F.load_video(tmp_path, "missing", need, size=32)
+
+
+def test_caffe2_checkpoint_loads_into_a_sub_batchnorm_model(tmp_path):
+    """BN.NORM_TYPE sub_batchnorm: Caffe2 running statistics go to `<bn>.split_bn.running_*`, tiled NUM_SPLITS times
+    (checkpoint.py:215-232, c2_normal_to_sub_bn :331-348), and the aggregated `<bn>.bn.*` the kernels fold follow."""
+    import json
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_meta.json")))["sf50_subbn_n2_64"]
+    plain, _, _ = build_model("slow_fast_nl_r50_8x8", seed=0, crop=64)
+    truth = _fake_caffe2_ckpt(plain, tmp_path / "c2.pkl")
+    sub, _, _ = build_model("slow_fast_nl_r50_8x8", seed=3, crop=64, sf_overrides=meta["sf_overrides"])
+    rep = CK.load_caffe2_checkpoint(tmp_path / "c2.pkl", sub.sf_mdl)
+    assert set(rep["skipped"]) == {"lr", "model_iter", "conv1_w_momentum"}
+    sd = sub.sf_mdl.state_dict()
+    n_split = meta["sf_overrides"]["BN"]["NUM_SPLITS"]
+    checked = 0
+    for k, a in truth.items():
+        if ".running_" in k:
+            pre, leaf = k.rsplit(".", 1)
+            assert np.array_equal(sd[f"{pre}.split_bn.{leaf}"].numpy(), np.concatenate([a] * n_split)), k
+            # identical splits: aggregated mean = the split mean, aggregated var = the split var
+            assert np.allclose(sd[f"{pre}.bn.{leaf}"].numpy(), a, rtol=1e-6, atol=1e-6), k
+            checked += 1
+        else:
+            assert np.array_equal(sd[k].numpy(), a), k
+    assert checked > 200

@@ -52,7 +52,10 @@ def main(argv=None) -> int:
     if args.mdl_resume_path:
         if args.is_cu:
             print("Using Caffe2 checkpoint")
-            checkpoint.load_caffe2_checkpoint(args.mdl_resume_path, mdl.sf_mdl)
+            rep = checkpoint.load_caffe2_checkpoint(args.mdl_resume_path, mdl.sf_mdl)
+            print(f"  loaded {len(rep['loaded'])} tensors; shape-mismatched blobs (not loaded): {rep['mismatched']}; "
+                  f"blobs without a model tensor: {len(rep['skipped'])}; model tensors not in the checkpoint: "
+                  f"{[k for k in rep['missing'] if not k.endswith('num_batches_tracked')]}")
         else:
             checkpoint.load_vidsitu_checkpoint(args.mdl_resume_path, mdl)
     mdl = mdl.to(torch.device("cuda")).eval()

@@ -6,6 +6,36 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from common import build_model, synthetic_frames
 GOLD = os.path.join(ROOT, "tests", "golden")
 META = json.load(open(os.path.join(GOLD, "golden_meta.json")))
+from oracle import sf_oracle as O   # checker (this is a test tool)
+
+
+def metrics(f, r, lg, g):
+    err = np.abs(f - r)
+    cos = float(((f * r).sum(-1) / (np.linalg.norm(f, axis=-1) * np.linalg.norm(r, axis=-1))).min())
+    mean = float(np.abs(r).mean())
+    top5 = np.sort(np.argsort(-lg, axis=-1, kind="stable")[:, :5], -1)
+    return {"cos": cos, "max_abs_over_max_ref": float(err.max() / np.abs(r).max()),
+            "rel_floor_0.1mean": float((err / np.maximum(np.abs(r), 0.1 * mean)).max()),
+            "rel_floor_mean": float((err / np.maximum(np.abs(r), mean)).max()),
+            "rel_l2": float(np.linalg.norm(f - r) / np.linalg.norm(r)),
+            "p99_rel_floor_0.1mean": float(np.percentile(err / np.maximum(np.abs(r), 0.1 * mean), 99)),
+            "logit_cos": float(((lg * g["logits"]).sum(-1) / (np.linalg.norm(lg, axis=-1) * np.linalg.norm(g["logits"], axis=-1))).min()),
+            "top5_set_equal": bool(np.array_equal(top5, np.sort(g["top5"], -1)))}
+
+
+def torch_bf16_comparator(model, cfg, frames_cpu):
+    """The EXTERNAL comparator of the bf16 tolerance: the reference's modules (oracle restatement: F.conv3d -> cuDNN,
+    F.batch_norm, ...) in bf16 channels_last_3d on this GPU, same weights and clips.  What a user gets from
+    `model.to(memory_format=torch.channels_last_3d).bfloat16()` on the reference."""
+    dev = torch.device("cuda")
+    sd = {k: (v.detach().to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last_3d) if v.dim() == 5
+              else v.detach().to(dev, torch.bfloat16)) for k, v in model.state_dict().items()}
+    xs = [x.to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+          for x in O.clips_from_frames(frames_cpu, cfg.sf_mdl)]
+    _, pooled, logits = O.sfbase_forward(sd, cfg.sf_mdl, xs)
+    return pooled.float().cpu().numpy(), logits.float().cpu().numpy()
+
+
 out = {}
 cases = sys.argv[1:] or list(META)
 for case in cases:
@@ -34,6 +64,15 @@ for case in cases:
                "logit_gap_5_6": float(np.min(-np.sort(-g["logits"], -1)[:, 4] + np.sort(-g["logits"], -1)[:, 5] * -1)) }
         out[f"{case}/{prec}"] = rec
         print(case, prec, json.dumps({k: (round(v, 6) if isinstance(v, float) else v) for k, v in rec.items()}), flush=True)
+        if prec == "bf16":
+            try:
+                cf, cl = torch_bf16_comparator(model, cfg, frames.cpu())
+                crec = metrics(cf, g["pooled"], cl, g)
+                out[f"{case}/torch_bf16_channels_last_3d"] = crec
+                print(case, "torch_bf16_cl3d", json.dumps({k: (round(v, 6) if isinstance(v, float) else v) for k, v in crec.items()}), flush=True)
+            except Exception as e:  # noqa: BLE001
+                out[f"{case}/torch_bf16_channels_last_3d"] = {"error": str(e)[:200]}
+                print(case, "torch_bf16_cl3d error", str(e)[:200], flush=True)
         del model
         torch.cuda.empty_cache()
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

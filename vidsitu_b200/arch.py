@@ -133,6 +133,10 @@ class NetSpec:
 def _bottleneck(prefix: str, dim_in: int, dim_out: int, dim_inner: int, temp_k: int, stride: int,
                 stride_1x1: bool, dilation: int) -> BlockSpec:
     """resnet_helper.py:243-358 (ResBlock) + :110-240 (BottleneckTransform)."""
+    if dilation != 1:
+        # resnet_helper.py:196-207 dilates the 3x3 (padding = dilation); ConvSpec / the kernels have no dilation, so a
+        # config with RESNET.SPATIAL_DILATIONS > 1 must fail loudly instead of computing a different conv
+        raise NotImplementedError(f"{prefix}: RESNET.SPATIAL_DILATIONS = {dilation} (only 1 is implemented)")
     str1, str3 = (stride, 1) if stride_1x1 else (1, stride)
     branch1 = None
     if dim_in != dim_out or stride != 1:

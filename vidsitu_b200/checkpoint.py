@@ -89,16 +89,25 @@ def convert_caffe2_name(name: str) -> Optional[str]:
 
 def convert_caffe2_blobs(blobs: Dict[str, np.ndarray], target: Dict[str, torch.Tensor]
                          ) -> Tuple["OrderedDict[str, torch.Tensor]", List[str], List[str]]:
-    """The conversion loop of checkpoint.py:210-257 for plain BatchNorm models: a blob is taken when its
-    converted name exists in `target` with the same shape.  Returns (state_dict, mismatched, skipped)."""
+    """The conversion loop of checkpoint.py:210-257: a blob is taken when its converted name exists in `target`
+    with the same shape.  Sub-BN models (BN.NORM_TYPE sub_batchnorm): running statistics go to
+    `<bn>.split_bn.running_*` (c2_normal_to_sub_bn, checkpoint.py:331-348) tiled NUM_SPLITS times
+    (checkpoint.py:215-232).  Returns (state_dict, mismatched, skipped)."""
     out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     mismatched, skipped = [], []
     for c2_name, blob in blobs.items():
         key = convert_caffe2_name(c2_name)
+        if key is not None and key not in target and "bn.running_" in key:
+            sub = key.replace("bn.running_", "bn.split_bn.running_")
+            if sub in target:
+                key = sub
         if key is None or key not in target:
             skipped.append(c2_name)
             continue
         arr = np.asarray(blob)
+        tshape = tuple(target[key].shape)
+        if len(tshape) == 1 and arr.ndim == 1 and tshape[0] > arr.shape[0] and tshape[0] % arr.shape[0] == 0:
+            arr = np.concatenate([arr] * (tshape[0] // arr.shape[0]))
         if tuple(arr.shape) == tuple(target[key].shape):
             out[key] = torch.tensor(arr).clone()
         else:
@@ -114,6 +123,14 @@ def load_caffe2_checkpoint(path, sf_mdl) -> Dict[str, List[str]]:
     target = sf_mdl.state_dict()
     sd, mismatched, skipped = convert_caffe2_blobs(ckpt["blobs"], target)
     res = sf_mdl.load_state_dict(sd, strict=False)
+    if any(".split_bn." in k for k in sd):
+        # eval-mode SubBatchNorm3d (and our BN folding) reads the aggregated `<bn>.bn.running_*`
+        # (batchnorm_helper.py:78-95): derive them from the split statistics just loaded
+        from .model import aggregate_sub_bn_stats
+        aggregate_sub_bn_stats(sf_mdl)
+    stat_blobs_skipped = [n for n in skipped if n.endswith(("_rm", "_riv"))]
+    if stat_blobs_skipped and any(".split_bn." in k for k in target):
+        raise ValueError(f"BatchNorm statistics blobs were not loaded into the sub-BN model: {stat_blobs_skipped[:4]} ...")
     owner = getattr(sf_mdl, "_owner", None)
     if owner is not None and owner() is not None:
         owner().invalidate_engines()   # kernels read prepared copies of the weights

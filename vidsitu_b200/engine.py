@@ -735,8 +735,12 @@ class ClipEngine:
         if slot is not None:
             self.select_slot(slot)
         spec = self.spec
-        if frames.shape[0] != self.n or frames.shape[1] != spec.num_frames:
-            raise VsbError(f"expected frames [{self.n}, {spec.num_frames}, {self.crop}, {self.crop}, 3]")
+        if frames.device != self.device:
+            raise VsbError(f"frames are on {frames.device}, the engine runs on {self.device}")
+        if (frames.shape[0] != self.n or frames.shape[1] != spec.num_frames
+                or tuple(frames.shape[2:4]) != (self.crop, self.crop)):
+            raise VsbError(f"expected frames [{self.n}, {spec.num_frames}, {self.crop}, {self.crop}, 3], got "
+                           f"{tuple(frames.shape)}")
         if spec.num_pathways == 2:
             ops.pack_frames(frames, self.slow_idx, spec.mean, spec.std, self.inputs[0], self.dtype,
                             spec.reverse_input_channel, self.x_off)
@@ -753,7 +757,8 @@ class ClipEngine:
         (clip = event * n_videos + video): one pack launch per event and pathway."""
         from .events import EVENTS_PER_VIDEO, event_frame_indices
         spec = self.spec
-        if videos.dim() != 5 or videos.shape[0] * EVENTS_PER_VIDEO != self.n:
+        if (videos.dim() != 5 or videos.shape[0] * EVENTS_PER_VIDEO != self.n
+                or tuple(videos.shape[2:4]) != (self.crop, self.crop)):
             raise VsbError(f"expected videos [{self.n // EVENTS_PER_VIDEO}, F, {self.crop}, {self.crop}, 3] for "
                            f"an engine of {self.n} clips")
         n_vid, f = int(videos.shape[0]), int(videos.shape[1])
@@ -789,7 +794,16 @@ class ClipEngine:
         """0 = slow-pathway stream, 1 = fast-pathway stream (which also runs the lateral convs)."""
         return 1 if ("pathway1" in name or "_fuse" in name) else 0
 
+    def _guard(self):
+        """Launches take torch's CURRENT stream and encode TMA maps in the CURRENT context: pin both to the engine's
+        device (a model on cuda:1 while cuda:0 is current would otherwise launch on the wrong device)."""
+        return torch.cuda.device(self.device)
+
     def run(self) -> None:
+        with self._guard():
+            self._run()
+
+    def _run(self) -> None:
         """One forward.  SlowFast nets run their two pathways on two streams (fork after the inputs are
         packed, join before the projection head): the pathways only meet at the lateral convs
         (video_model_builder.py:124-131), which wait for the slow stage they write into and are waited
@@ -851,11 +865,15 @@ class ClipEngine:
             origin.wait_stream(main)
 
     def capture(self) -> None:
+        with self._guard():
+            self._capture()
+
+    def _capture(self) -> None:
         """Capture trunk + head once into a CUDA graph (inputs/outputs are static buffers)."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self.run()          # warm-up outside capture (lazy module loading, func attributes)
+            self._run()          # warm-up outside capture (lazy module loading, func attributes)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         keep = self._slot
@@ -864,7 +882,7 @@ class ClipEngine:
             self._slot = slot
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.run()
+                self._run()
             self._graph.append(g)
         self._slot = keep
 
@@ -873,7 +891,8 @@ class ClipEngine:
             self.capture()
         if slot is not None:
             self.select_slot(slot)
-        self._graph[self._slot].replay()
+        with self._guard():
+            self._graph[self._slot].replay()
 
     @property
     def num_launches(self) -> int:

@@ -55,6 +55,22 @@ class BackboneModel(BackboneParams):
             raise VsbError("forward_features needs the owning SFBase (engine cache)")
         return self._owner()._forward_features(x)
 
+    # the kernels read prepared copies of the parameters: every way of changing them through `sf_mdl` alone
+    # (load_checkpoint(model=mdl.sf_mdl, ...), sf_mdl.load_state_dict, sf_mdl.to / .half / ...) drops those copies
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        owner = self._owner() if self._owner is not None else None
+        if owner is not None:
+            owner.invalidate_engines()
+        return out
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        owner = self._owner() if getattr(self, "_owner", None) is not None else None
+        if owner is not None and hasattr(owner, "_engines"):
+            owner.invalidate_engines()
+        return out
+
     def forward(self, x, bboxes=None):
         raise NotImplementedError("the reference never calls sf_mdl.forward on this path "
                                   "(mdl_sf_base.py:36-42 is broken upstream); use forward_features")
@@ -125,6 +141,8 @@ class SFBase(nn.Module):
         self.micro_batch = int(micro_batch)
         self.tune = tune
         self._engines: Dict[tuple, ClipEngine] = {}
+        self._prep: Dict[tuple, dict] = {}      # prepared weights per (precision, device), shared by all batch sizes
+        self._host_tensors: Optional[dict] = None
         self._weights_version = 0
         self.build_model()
 
@@ -173,12 +191,14 @@ class SFBase(nn.Module):
     def invalidate_engines(self) -> None:
         """Call after mutating parameters in place: kernels read prepared copies of the weights."""
         self._engines.clear()
+        self._prep.clear()
+        self._host_tensors = None
         self._weights_version += 1
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)
         if hasattr(self, "_engines"):
-            self._engines.clear()
+            self.invalidate_engines()
         return out
 
     def train(self, mode: bool = True):
@@ -189,13 +209,23 @@ class SFBase(nn.Module):
 
     # ------------------------------------------------------------------ engines
     def _engine(self, n: int, device) -> ClipEngine:
-        key = (n, self.precision, str(device))
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        slots = getattr(self, "input_slots", 1)
+        key = (n, self.precision, str(device), slots)
         eng = self._engines.get(key)
         if eng is None:
-            tensors = {k: v for k, v in self.sf_mdl.state_dict().items()}
+            if self._host_tensors is None:
+                # one device -> host copy of the reference-layout parameters; BatchNorm folding and weight packing
+                # run on the CPU and are cached per (precision, device): an engine for another batch size (a tail
+                # batch) re-uses the prepared tensors and only builds its plans and buffers
+                self._host_tensors = {k: v.detach().float().cpu() for k, v in self.sf_mdl.state_dict().items()}
             ph = (self.proj_head[0].weight, self.proj_head[0].bias, self.proj_head[2].weight, self.proj_head[2].bias)
-            eng = ClipEngine(self.spec, tensors, n, _PRECISIONS[self.precision], device, proj_head=ph, tune=self.tune,
-                             input_slots=getattr(self, "input_slots", 1))
+            with torch.cuda.device(device):
+                eng = ClipEngine(self.spec, self._host_tensors, n, _PRECISIONS[self.precision], device, proj_head=ph,
+                                 tune=self.tune, input_slots=slots,
+                                 prep_cache=self._prep.setdefault((self.precision, str(device)), {}))
             self._engines[key] = eng
         return eng
 
@@ -283,9 +313,11 @@ class SFBase(nn.Module):
                 eng.replay()
             else:
                 eng.run()
-            feats.append(eng.feats.clone() if e - s < n else eng.feats)
+            # always a copy: eng.feats / eng.logits are the engine's static CUDA-graph output buffers, the next
+            # call with the same batch size overwrites them
+            feats.append(eng.feats.clone())
             if want_logits:
-                logits.append(eng.logits.clone() if e - s < n else eng.logits)
+                logits.append(eng.logits.clone())
         f = torch.cat(feats, 0) if len(feats) > 1 else feats[0]
         if want_logits:
             return f, (torch.cat(logits, 0) if len(logits) > 1 else logits[0])
