@@ -215,6 +215,11 @@ def main():
     from vidsitu_b200.pipeline import HostPipeline
 
     args.warmup = max(args.warmup, 3)
+    # one process per GPU, pinned to the CPUs local to its GPU; the two pinned frame batches are first-touched on
+    # different NUMA nodes (when there are two) so that N ranks' H2D copies do not all read one memory controller
+    from vidsitu_b200 import numa
+    cpus = numa.bind_to_gpu(local_rank) if os.environ.get("VSB_NUMA_BIND", "1") == "1" else None
+    nodes = sorted(numa.numa_nodes()) if os.environ.get("VSB_NUMA_BIND", "1") == "1" else []
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -226,7 +231,11 @@ def main():
     model = model.to(dev)
     t_frames = cfg.sf_mdl.DATA.NUM_FRAMES
     # two distinct synthetic batches per rank; 2 x 308 MB of uint8 frames (> the 126 MB L2) alternate between steps
-    host_frames = [synthetic_frames(B, t_frames, 224, seed=1234 + 17 * rank + i).pin_memory() for i in range(2)]
+    host_frames = []
+    for i in range(2):
+        f = synthetic_frames(B, t_frames, 224, seed=1234 + 17 * rank + i)
+        with numa.on_node(nodes[(rank + i) % len(nodes)] if len(nodes) > 1 else None):
+            host_frames.append(f.pin_memory())
     dev_frames = [f.to(dev) for f in host_frames]
     eng = model._engine(B, dev)
     eng.capture()
@@ -402,7 +411,9 @@ def main():
                        "weights": "random-init (seed 0) + seeded BatchNorm statistics",
                        "l2": "inputs larger than L2: 2 alternating 308 MB uint8 frame batches per GPU, "
                              "activations >> 126 MB", "cuda_graph": True, "pack_overlap": nslots > 1,
-                       "parallelism": f"clip-sharded x{world}, features all-gathered each step" if world > 1 else "single GPU"},
+                       "parallelism": f"clip-sharded x{world}, features all-gathered each step" if world > 1 else "single GPU",
+                       "host_placement": {"rank0_cpus": (f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else None),
+                                          "numa_nodes": nodes}},
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "cpu_baseline_note": None if cpu_baseline is not None else "measured on rank 0 at N=1 only (see --impl reference)",

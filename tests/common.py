@@ -38,3 +38,18 @@ def synthetic_frames(n: int, t: int, crop: int = 224, seed: int = 1234) -> torch
     """uint8 [n, t, crop, crop, 3] uniform bytes (SURVEY.md section 8d generator)."""
     g = torch.Generator().manual_seed(seed)
     return torch.randint(0, 256, (n, t, crop, crop, 3), dtype=torch.uint8, generator=g)
+
+
+def torch_bf16_comparator(model, cfg, frames_cpu: torch.Tensor):
+    """EXTERNAL comparator of the bf16 tolerance (test infrastructure): the reference's own modules - the oracle
+    restatement, i.e. F.conv3d -> cuDNN, F.batch_norm, F.max_pool3d, einsum - run in bf16 channels_last_3d on the
+    GPU with the same weights and clips; what `model.to(memory_format=torch.channels_last_3d).bfloat16()` gives a user
+    of the reference.  Returns (pooled [N, D], logits [N, V]) as fp32 numpy arrays."""
+    from oracle import sf_oracle as O
+    dev = torch.device("cuda")
+    sd = {k: (v.detach().to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last_3d) if v.dim() == 5
+              else v.detach().to(dev, torch.bfloat16)) for k, v in model.state_dict().items()}
+    xs = [x.to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+          for x in O.clips_from_frames(frames_cpu, cfg.sf_mdl)]
+    _, pooled, logits = O.sfbase_forward(sd, cfg.sf_mdl, xs)
+    return pooled.float().cpu().numpy(), logits.float().cpu().numpy()

@@ -9,9 +9,14 @@ means can be arbitrarily close to 0, so "relative" needs a scale; the bf16 gate 
     max |got - ref| / max |ref|  <= 1e-2      (error relative to the feature scale)
     ||got - ref||_2 / ||ref||_2  <= 1e-2
     cosine per clip              >= 0.9999
-and, reported with a looser documented bound, the per-element form
-    max |got - ref| / max(|ref|, mean |ref|) <= 5e-2
-(measured on B200: 0.3 % / 0.3 % / 0.99999 / 1.3-3.4 %, profiles/r01_parity_report.json).
+and the per-element form  el = max |got - ref| / max(|ref|, mean |ref|), gated against an EXTERNAL comparator
+computed in the same test: the reference's own modules in bf16 channels_last_3d through torch / cuDNN on this GPU
+(common.torch_bf16_comparator), same weights, same clips, same fp32 reference:
+    el <= 2.5e-2,  or - where the library bf16 run is itself > 3.3e-2 off (an ill-conditioned case) -
+    el <= 0.75 * el(torch bf16);  never above 5e-2;
+and on every case our error may not exceed the comparator's by more than 25 % on any of the four metrics.
+Measured on B200 (profiles/r02_parity_report.json): ours 1.4 - 2.2 % per element on ten fixtures (torch bf16:
+2.0 - 4.3 %), 4.3 % on i3d_nln_n2_64 (torch bf16: 7.7 %: 16 pooled positions at crop 64 average little noise).
 fp32 mode: identical top-5 verb index SET per clip and 1e-3 per-element relative error.
 """
 import json
@@ -44,13 +49,23 @@ def scale_err(got: np.ndarray, ref: np.ndarray):
             float(np.linalg.norm(got - ref) / np.linalg.norm(ref)))
 
 
-def assert_bf16_close(got, ref, what=""):
+def assert_bf16_close(got, ref, what="", comparator=None):
+    """`comparator`: the torch bf16 channels_last_3d run of the reference modules on the same inputs (pooled features),
+    the external yardstick of the per-element gate (see the module docstring)."""
     mx, l2 = scale_err(got, ref)
     cs, el = cosine(got, ref), rel_err(got, ref)
     print(f"{what}: max|err|/max|ref| {mx:.4g}  rel-L2 {l2:.4g}  cosine {cs:.6f}  per-element(floor=mean) {el:.4g}")
     assert cs >= 0.9999, (mx, l2, cs, el)
     assert mx <= 1e-2 and l2 <= 1e-2, (mx, l2, cs, el)
     assert el <= 5e-2, (mx, l2, cs, el)
+    if comparator is not None:
+        mx_t, l2_t = scale_err(comparator, ref)
+        cs_t, el_t = cosine(comparator, ref), rel_err(comparator, ref)
+        print(f"{what}: torch bf16 channels_last_3d comparator: max|err|/max|ref| {mx_t:.4g}  rel-L2 {l2_t:.4g}  "
+              f"cosine {cs_t:.6f}  per-element {el_t:.4g}")
+        assert el <= 2.5e-2 or (el_t > 3.3e-2 and el <= 0.75 * el_t), (el, el_t)
+        assert mx <= 1.25 * mx_t and l2 <= 1.25 * l2_t and el <= 1.25 * el_t and (1 - cs) <= 1.25 * (1 - cs_t) + 1e-6, \
+            ((mx, mx_t), (l2, l2_t), (el, el_t), (cs, cs_t))
 
 
 def cosine(got: np.ndarray, ref: np.ndarray):
@@ -226,10 +241,12 @@ BF16_CASES = ["sf50_n2_64", "sf50_rawinit_n2_64", "i3d_nln_n2_64", "slow_n2_64",
 
 @pytest.mark.parametrize("case", BF16_CASES)
 def test_bf16_features_match_reference(case):
+    from common import torch_bf16_comparator
     g = np.load(os.path.join(GOLD, case + ".npz"))
-    _, _, _, feats, logits = _run_model(case, "bf16")
+    model, cfg, frames, feats, logits = _run_model(case, "bf16")
     assert np.isfinite(feats).all() and np.isfinite(logits).all()
-    assert_bf16_close(feats, g["pooled"], case + " pooled")
+    comp, _ = torch_bf16_comparator(model, cfg, frames.cpu())
+    assert_bf16_close(feats, g["pooled"], case + " pooled", comparator=comp)
     assert cosine(logits, g["logits"]) >= 0.9999
     top5 = np.argsort(-logits, axis=-1, kind="stable")[:, :5]
     print(f"{case}: bf16 top-5 set equal to reference: {np.array_equal(np.sort(top5, -1), np.sort(g['top5'], -1))}")
@@ -405,7 +422,7 @@ def test_sharded_run_is_bit_identical_to_the_whole_batch():
     whole = model.extract_features(frames)
     parts = []
     for r in range(2):
-        lo, hi = shard_range(2, 2, r)                              # videos of rank r
+        lo, hi = shard_range(2, r, 2)                              # videos of rank r
         parts.append(model.extract_features(frames[5 * lo:5 * hi].contiguous()))
     assert torch.equal(torch.cat(parts), whole)
 

@@ -23,17 +23,7 @@ def metrics(f, r, lg, g):
             "top5_set_equal": bool(np.array_equal(top5, np.sort(g["top5"], -1)))}
 
 
-def torch_bf16_comparator(model, cfg, frames_cpu):
-    """The EXTERNAL comparator of the bf16 tolerance: the reference's modules (oracle restatement: F.conv3d -> cuDNN,
-    F.batch_norm, ...) in bf16 channels_last_3d on this GPU, same weights and clips.  What a user gets from
-    `model.to(memory_format=torch.channels_last_3d).bfloat16()` on the reference."""
-    dev = torch.device("cuda")
-    sd = {k: (v.detach().to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last_3d) if v.dim() == 5
-              else v.detach().to(dev, torch.bfloat16)) for k, v in model.state_dict().items()}
-    xs = [x.to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
-          for x in O.clips_from_frames(frames_cpu, cfg.sf_mdl)]
-    _, pooled, logits = O.sfbase_forward(sd, cfg.sf_mdl, xs)
-    return pooled.float().cpu().numpy(), logits.float().cpu().numpy()
+from common import torch_bf16_comparator  # noqa: E402
 
 
 out = {}

@@ -166,6 +166,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer's barriers exist before anything is signalled across the pair
+  __syncthreads();     // (CTA barrier as well: compute-sanitizer racecheck does not model barrier.cluster)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 

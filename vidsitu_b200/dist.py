@@ -30,11 +30,26 @@ def shard_counts(n_items: int, world: int) -> List[int]:
     return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
 
 
+_GATHER_BUFS: dict = {}
+
+
+def _gather_bufs(local: torch.Tensor, longest: int, world: int):
+    """Padded send / receive buffers of gather_rows, allocated once per (shape, dtype, device, world)."""
+    key = (tuple(local.shape[1:]), local.dtype, str(local.device), longest, world)
+    bufs = _GATHER_BUFS.get(key)
+    if bufs is None:
+        padded = local.new_zeros((longest,) + tuple(local.shape[1:]))
+        out = local.new_empty((world * longest,) + tuple(local.shape[1:]))
+        bufs = _GATHER_BUFS[key] = (padded, out)
+    return bufs
+
+
 def gather_rows(local: torch.Tensor, n_total_rows: int, rows_per_item: int = 5) -> torch.Tensor:
     """All-gather row blocks of unequal length: every rank contributes the rows of its
     shard_range() of items (rows_per_item rows each); returns the [n_total_rows, D] tensor in
     item order on every rank.  Shards are padded to the longest one so a single
-    all_gather_into_tensor (NCCL) / all_gather (gloo) moves everything."""
+    all_gather_into_tensor (NCCL) / all_gather (gloo) moves everything.  On NCCL the buffers are allocated once and
+    re-used: the returned tensor is valid until the next call with the same shapes."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world = dist.get_world_size()
@@ -43,13 +58,18 @@ def gather_rows(local: torch.Tensor, n_total_rows: int, rows_per_item: int = 5) 
     if local.shape[0] != counts[dist.get_rank()]:
         raise ValueError(f"rank {dist.get_rank()} holds {local.shape[0]} rows, expected {counts[dist.get_rank()]}")
     longest = max(counts)
-    padded = local.new_zeros((longest,) + tuple(local.shape[1:]))
-    padded[: local.shape[0]] = local
+    equal = all(c == longest for c in counts)
     if dist.get_backend() == "nccl":
-        out = local.new_empty((world * longest,) + tuple(local.shape[1:]))
-        dist.all_gather_into_tensor(out, padded.contiguous())
+        padded, out = _gather_bufs(local, longest, world)
+        if equal and local.is_contiguous():
+            dist.all_gather_into_tensor(out, local)      # equal shards: no staging copy, the result is `out` itself
+            return out
+        padded[: local.shape[0]] = local
+        dist.all_gather_into_tensor(out, padded)
         parts = list(out.split(longest, dim=0))
     else:
+        padded = local.new_zeros((longest,) + tuple(local.shape[1:]))
+        padded[: local.shape[0]] = local
         parts = [torch.empty_like(padded) for _ in range(world)]
         dist.all_gather(parts, padded.contiguous())
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
