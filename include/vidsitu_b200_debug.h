@@ -44,6 +44,13 @@ int vsb_debug_conv_stats(const struct vsb_conv_plan* plan, long long* out16);
  * stages, TMEM accumulators, grid, dynamic shared memory bytes, block_n, CTAs per SM the grid assumes}. */
 int vsb_debug_conv_plan_info(const struct vsb_conv_plan* plan, long long* out8);
 
+/* TMA load-path probe: every CTA streams `tiles` 128-row tiles of a dense bf16 [n, t, h, w, c] tensor through a ring
+ * of `stages` slots that are freed as soon as they are full.  mode 0: tiled 5-D boxes [kc, RP, box_rows] (RP = power of
+ * two > w, out-of-bounds slots zero-filled; kt boxes per tile = frames t-1, t, t+1) as the fused bottleneck loads x;
+ * mode 1: 2-D boxes [kc, 128 pixels].  clk[cta] = cycles. */
+int vsb_debug_tma_rate(const void* x, int n, int t, int h, int w, int c, int mode, int kt, int box_rows, int stages,
+                       int tiles, int grid, long long* clk, void* stream);
+
 /* Role timeline counters of a fused-bottleneck plan created with VSB_FUSED_DEBUG=1 in the environment
  * (see bottleneck_fused_sm100.cu); synchronises the device, copies 32 counters and clears them. */
 struct vsb_bottleneck_plan;

@@ -74,12 +74,14 @@ struct FusedParams {
   int stages;                   // x ring: `stages` slots of `cps` chunks each (one full / empty barrier pair per slot)
   int cps, slots_per_tile;
   int pf_dist;                  // L2 prefetch distance of the x loads, in tiles (0 = off)
+  int x_im2col;                 // x chunks by ONE im2col-mode TMA load each (else tiled boxes of box_rows flat rows)
   uint32_t stage_bytes;
   // shared-memory layout (bytes from the 1 KiB-aligned base)
   uint32_t off_wa, off_wb, off_wc, off_ring, off_p, off_epi, off_bar, off_tab;
   uint32_t wa_block_bytes, wb_block_bytes, wc_bytes, tile_bytes;
   // TMEM columns
   uint32_t tmem_cols, tm_a, tm_b, tm_c, tm_ab_stride, tm_c_stride;
+  int c_bufs;                   // c accumulators per c-epilogue group (1 or 2): 2 * c_bufs in all
   uint32_t idesc_a, idesc_b, idesc_c;
   // c epilogue
   int epi_n, epi_chunks, epi_bufs, bw, bh;
@@ -213,9 +215,9 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   uint64_t* ring_free = a_ready + kRing;  // b/c-issuer (commit) -> a-issuer: every MMA issued through step s has completed
   uint64_t* b_full = ring_free + kRing;
   uint64_t* b_done = b_full + 2;
-  uint64_t* c_full = b_done + 2;
-  uint64_t* c_empty = c_full + 2;
-  uint64_t* epi_ready = c_empty + 2;
+  uint64_t* c_full = b_done + 2;      // [group * 2 + buffer]
+  uint64_t* c_empty = c_full + 4;
+  uint64_t* epi_ready = c_empty + 4;
   uint64_t* w_bar = epi_ready + kCEpiWarps * kMaxEpiBufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
@@ -245,7 +247,9 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       mbar_init(&b_full[i], 1);
       mbar_init(&b_done[i], 4);
       mbar_init(&c_full[i], 1);
+      mbar_init(&c_full[i + 2], 1);
       mbar_init(&c_empty[i], 4);
+      mbar_init(&c_empty[i + 2], 4);
     }
     for (int i = 0; i < kCEpiWarps * kMaxEpiBufs; ++i) mbar_init(&epi_ready[i], 1);
     mbar_init(w_bar, 1);
@@ -337,13 +341,31 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           by[b] = r - tq * FP;           // row inside the frame (>= H: zero-filled)
         }
         int dt = 0, cc = 0;
+        const int x0 = (it.m() * 128) & (p.RP - 1);   // first slot of the tile inside its flat row (im2col mode)
+        // halo tiles outside the clip (m = -1, m = tiles_per_clip): every slot is padding, the a-epilogue writes zeros
+        // whatever the accumulator holds -> nothing to load (im2col base coordinates must stay inside the bounding box)
+        const bool outside = p.x_im2col && (it.m() < 0 || it.m() >= p.tiles_per_clip);
         for (int q = 0; q < cpt; q += cps) {
           FB_T(0, mbar_wait(&x_empty[slot], parity));
+          if (outside) {
+            mbar_arrive(&x_full[slot]);
+            if (++slot == S) {
+              slot = 0;
+              parity ^= 1;
+            }
+            continue;
+          }
           mbar_expect_tx(&x_full[slot], p.stage_bytes);
           uint8_t* dst = smem + (uint32_t)slot * p.stage_bytes;
           for (int c = 0; c < cps; ++c) {
-            for (int b = 0; b < nbox; ++b)
-              tma_load_5d(dst + b * p.box_bytes, &map_x, &x_full[slot], cc * kc, 0, by[b], bt[b] + dt - pt, it.n);
+            if (p.x_im2col) {
+              // 128 consecutive flat slots from (slot 0 of flat row by[0], frame bt[0]): the traversal wraps W -> H -> T
+              // inside the padded bounding box [0, RP) x [0, FP) x [-pt, T - 1 + pt], out-of-tensor positions zero-filled
+              tma_load_im2col_5d(dst, &map_x, &x_full[slot], cc * kc, x0, by[0], bt[0] - pt, it.n, 0, 0, (uint16_t)dt);
+            } else {
+              for (int b = 0; b < nbox; ++b)
+                tma_load_5d(dst + b * p.box_bytes, &map_x, &x_full[slot], cc * kc, 0, by[b], bt[b] + dt - pt, it.n);
+            }
             dst += p.chunk_bytes;
             if (++cc == cch) {
               cc = 0;
@@ -417,13 +439,17 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           FB_T(5, mbar_wait(&b_done[b_waited & 1], (b_waited >> 1) & 1));
           ++b_waited;
         }
-        FB_T(6, mbar_wait(&c_empty[gc & 1], ((gc >> 1) & 1) ^ 1));
+        // c accumulator of tile gc: group gc & 1, buffer (gc >> 1) % c_bufs of that group, use number (gc >> 1) / c_bufs
+        const int cgrp = gc & 1, cuse = gc >> 1;
+        const int cbuf = p.c_bufs == 2 ? (cuse & 1) : 0, cphase = p.c_bufs == 2 ? (cuse >> 1) : cuse;
+        const int cidx = cgrp * 2 + cbuf;
+        FB_T(6, mbar_wait(&c_empty[cidx], (cphase & 1) ^ 1));
         const long long i0 = kDbg ? clock64() : 0;
         tc_fence_after();
         if (elect_one()) {
-          fb_issue(tmem_base + p.tm_c + (uint32_t)(gc & 1) * p.tm_c_stride, d_hi, d_hi, p_lo + (uint32_t)(gc & 1) * tile_lo,
-                   wc_lo, tab_c, ksd, idesc_c, 0u);
-          umma_commit(&c_full[gc & 1]);
+          fb_issue(tmem_base + p.tm_c + (uint32_t)(cgrp * p.c_bufs + cbuf) * p.tm_c_stride, d_hi, d_hi,
+                   p_lo + (uint32_t)(gc & 1) * tile_lo, wc_lo, tab_c, ksd, idesc_c, 0u);
+          umma_commit(&c_full[cidx]);
         }
         __syncwarp();
         if (kDbg) dbg_acc[20] += (uint32_t)(clock64() - i0);
@@ -440,7 +466,8 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     // Two issuing warps: each one's barrier round trips and loop overhead overlap the other's tensor-pipe time (one
     // warp issuing all three phases is issue-latency bound at ~1.7x the pipe time).  tcgen05.commit only tracks the
     // issuing thread's own MMAs, so the ring-slot reuse (a-tile g overwrites a-tile g-4, last read by the b-tile of
-    // step g-1) is ordered through ring_free: a(g) is issued after step g-1 of the other warp has COMPLETED.
+    // step g-1) is ordered through ring_free, which the a-EPILOGUE waits for before it writes the ring: this warp
+    // only needs a drained accumulator and its x chunks.
     const uint64_t x_hi = umma_smem_desc(0, p.x_row_bytes) & 0xFFFFFFFF00000000ull;
     const uint32_t x_fl = (uint32_t)(umma_smem_desc(0, p.x_row_bytes) & 0xFFFFC000ull);
     const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
@@ -455,7 +482,6 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     ATileIter it;
     for (it.init(p); it.valid(p); it.next(p), ++g) {
       if (g >= 2) FB_T(1, mbar_wait(&a_done[g & 1], ((g - 2) >> 1) & 1));  // accumulator drained by a-tile g-2's epilogue
-      if (g >= 1) FB_T(21, mbar_wait(&ring_free[(g - 1) & (kRing - 1)], ((g - 1) >> 2) & 1));
       const uint32_t tm_d = tmem_base + p.tm_a + (uint32_t)(g & 1) * p.tm_ab_stride;
       for (int q = 0; q < spt; ++q) {
         FB_T(2, mbar_wait(&x_full[slot], xpar));
@@ -497,6 +523,8 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       const uint32_t dst = ring_s + (uint32_t)pos * p.tile_bytes;
       const uint32_t dst2 = pos == 0 ? ring_s + (uint32_t)kRing * p.tile_bytes : 0u;
       FB_T(7, mbar_wait(&a_full[g & 1], (g >> 1) & 1));
+      // ring slot g & 3 still holds a-tile g-4 until every b-tile that reads it (issued through step g-1) has completed
+      if (g >= 1) FB_T(21, mbar_wait(&ring_free[(g - 1) & (kRing - 1)], ((g - 1) >> 2) & 1));
       const long long w0 = kDbg ? clock64() : 0;
       tc_fence_after();
       fb_convert_rows(lane_taddr + (uint32_t)(g & 1) * p.tm_ab_stride, p.d16, dst, dst2, p.a_row_bytes, swz_mask, row,
@@ -545,7 +573,7 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const int quarter = cw & 3, grp = cw >> 2;
     const uint32_t epi_row_bytes = p.epi_n * 2;
     const uint32_t swz_mask = epi_row_bytes == 128 ? 7u : (epi_row_bytes == 64 ? 3u : 1u);
-    const uint32_t lane_taddr = tmem_base + p.tm_c + (uint32_t)grp * p.tm_c_stride + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t lane_taddr = tmem_base + p.tm_c + (uint32_t)(grp * p.c_bufs) * p.tm_c_stride + ((uint32_t)(quarter * 32) << 16);
     const uint32_t slab_bytes = 32 * epi_row_bytes;
     const int nb = p.epi_bufs, chunks = p.epi_chunks;
     uint8_t* my_bufs = smem + p.off_epi + (size_t)cw * nb * slab_bytes;
@@ -604,7 +632,8 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     while (seek(it, gbx)) {
       int xs0, y, tn;
       const bool live = box_of(it.n, it.m0 + it.j - 2, xs0, y, tn);
-      FB_T(11, mbar_wait(&c_full[grp], tcount & 1));
+      const int cbuf = p.c_bufs == 2 ? (tcount & 1) : 0, cphase = p.c_bufs == 2 ? (tcount >> 1) : tcount;
+      FB_T(11, mbar_wait(&c_full[grp * 2 + cbuf], cphase & 1));
       if (kDbg) dbg_acc[17] += 1;
       tc_fence_after();
       for (int c = 0; c < chunks; ++c) {
@@ -614,7 +643,7 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const long long w0 = kDbg ? clock64() : 0;
         const int col0 = c * p.epi_n;
         if (live)
-          epi_convert_chunk<true>(lane_taddr + col0, p.epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane,
+          epi_convert_chunk<true>(lane_taddr + (uint32_t)cbuf * p.tm_c_stride + col0, p.epi_n, smem_u32(buf), epi_row_bytes, swz_mask, lane,
                                   sb_s + col0 * 8, 0.f);
         fence_proxy_async_smem();
         __syncwarp();
@@ -632,7 +661,7 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&c_empty[grp]);
+      if (lane == 0) mbar_arrive(&c_empty[grp * 2 + cbuf]);
       ++tcount;
       ++gbx;
       it.next(p);
@@ -650,6 +679,84 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   if (warp == kMmaWarp) {
     __syncwarp();
     tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------- TMA rate probe
+// Every CTA streams `tiles` consecutive 128-row tiles of a [n, t, h, w, c] bf16 tensor into a ring of `stages`
+// 16 KiB-or-less slots and frees each slot as soon as it is full (no consumer work): cycles per CTA -> bytes per
+// cycle per SM of the load path alone.  mode 0: tiled 5-D boxes [kc, RP, box_rows] as the fused block loads them
+// (RP > w: out-of-bounds slots zero-filled), kt boxes per tile position (frames t-1, t, t+1 ...); mode 1: plain 2-D
+// boxes [kc, 128] over the flattened pixel list (a GEMM operand tile).
+struct TmaProbeParams {
+  int mode, kt, kc, cchunks, RP, rp_rows, box_rows, H, T, FP, tiles_per_clip, tiles, stages, n_clips;
+  uint32_t chunk_bytes, box_bytes;
+  long long* clk;
+};
+
+__global__ void __launch_bounds__(64, 1)
+tma_rate_probe_kernel(const __grid_constant__ CUtensorMap map5, const __grid_constant__ CUtensorMap map2,
+                      const __grid_constant__ TmaProbeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (uint32_t)p.stages * p.chunk_bytes);
+  uint64_t* empty = full + p.stages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  const int total_tiles = p.tiles_per_clip * p.n_clips;
+  const int m_first = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
+  if (threadIdx.x == 0) {
+    int slot = 0;
+    uint32_t par = 1;
+    for (int i = 0; i < p.tiles; ++i) {
+      const int mt = (m_first + i) % total_tiles;
+      const int n = mt / p.tiles_per_clip, m = mt - n * p.tiles_per_clip;
+      for (int dt = 0; dt < p.kt; ++dt) {
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          mbar_wait(&empty[slot], par);
+          mbar_expect_tx(&full[slot], p.chunk_bytes);
+          uint8_t* dst = smem + (uint32_t)slot * p.chunk_bytes;
+          if (p.mode == 0) {
+            const int r0 = m * p.rp_rows;
+            for (int b = 0; b < p.rp_rows / p.box_rows; ++b) {
+              const int r = r0 + b * p.box_rows;
+              tma_load_5d(dst + b * p.box_bytes, &map5, &full[slot], cc * p.kc, 0, r % p.FP, r / p.FP + dt - (p.kt >> 1), n);
+            }
+          } else if (p.mode == 2) {
+            const int f0 = m * 128;
+            tma_load_im2col_5d(dst, &map5, &full[slot], cc * p.kc, f0 % p.RP, (f0 / p.RP) % p.FP, f0 / (p.RP * p.FP) - (p.kt >> 1), n,
+                               0, 0, (uint16_t)dt);
+          } else {
+            tma_load_2d(dst, &map2, &full[slot], cc * p.kc, mt * 128 + dt * 4096);
+          }
+          if (++slot == p.stages) {
+            slot = 0;
+            par ^= 1;
+          }
+        }
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    int slot = 0;
+    uint32_t par = 0;
+    const int loads = p.tiles * p.kt * p.cchunks;
+    for (int i = 0; i < loads; ++i) {
+      mbar_wait(&full[slot], par);
+      mbar_arrive(&empty[slot]);
+      if (++slot == p.stages) {
+        slot = 0;
+        par ^= 1;
+      }
+    }
+    p.clk[blockIdx.x] = clock64() - t0;
   }
 }
 
@@ -760,7 +867,8 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
   p.tm_a = 0;
   p.tm_b = 2 * p.tm_ab_stride;
   p.tm_c = 4 * p.tm_ab_stride;
-  const uint32_t need_cols = 4 * p.tm_ab_stride + 2 * p.tm_c_stride;
+  p.c_bufs = (4 * p.tm_ab_stride + 4 * p.tm_c_stride <= 512) ? 2 : 1;
+  const uint32_t need_cols = 4 * p.tm_ab_stride + 2 * p.c_bufs * p.tm_c_stride;
   VSB_CHECK_ARG(need_cols <= 512, "accumulators need %u TMEM columns (> 512)", need_cols);
   p.tmem_cols = 32;
   while (p.tmem_cols < need_cols) p.tmem_cols <<= 1;
@@ -811,6 +919,9 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
   p.cps = cps;
   p.slots_per_tile = p.chunks_per_tile / cps;
   p.stage_bytes = (uint32_t)cps * p.chunk_bytes;
+  // im2col-mode x loads when the padded bounding box fits the TMA corner range (measured: tiled 5-D boxes with
+  // out-of-bounds slots run at 10 - 21 B/clk/SM, one im2col load per 16 KiB chunk at the 2-D rate)
+  p.x_im2col = (RP - d->w <= 15 && FP - d->h <= 15 && !getenv("VSB_FUSED_TILED_X")) ? 1 : 0;
   p.pf_dist = getenv("VSB_FUSED_PF") ? atoi(getenv("VSB_FUSED_PF")) : 0;  // measured: the TMA unit is the bound, prefetches only add to it
   p.off_wa = (uint32_t)stages * p.stage_bytes;
   p.off_wb = p.off_wa + p.chunks_per_tile * p.wa_block_bytes;
@@ -858,7 +969,15 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
     cuuint64_t str[4] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->w * d->x_pitch * 2,
                          (cuuint64_t)d->h * d->w * d->x_pitch * 2, (cuuint64_t)d->t * d->h * d->w * d->x_pitch * 2};
     cuuint32_t box[5] = {(cuuint32_t)p.kc, (cuuint32_t)RP, (cuuint32_t)box_rows, 1, 1};
-    rc = fb_encode(&plan->map_x, d->x, 5, dims, str, box, swizzle_for((int)p.x_row_bytes), "block input");
+    if (p.x_im2col) {
+      const int lower[3] = {0, 0, -(d->kt >> 1)};
+      const int upper[3] = {RP - d->w, FP - d->h, (d->kt >> 1) - (d->kt - 1)};
+      const int one3[3] = {1, 1, 1};
+      rc = encode_im2col_map(&plan->map_x, d->x, d->n, d->t, d->h, d->w, d->c, d->x_pitch, lower, upper, one3, p.kc, 128,
+                             swizzle_for((int)p.x_row_bytes));
+    } else {
+      rc = fb_encode(&plan->map_x, d->x, 5, dims, str, box, swizzle_for((int)p.x_row_bytes), "block input");
+    }
     if (rc != VSB_OK) FB_FAIL(rc);
   }
   {
@@ -947,5 +1066,59 @@ extern "C" int vsb_bottleneck_plan_info(const vsb_bottleneck_plan* plan, long lo
   out8[5] = (long long)plan->smem_bytes;
   out8[6] = p.tiles_per_clip;
   out8[7] = p.tmem_cols;
+  return VSB_OK;
+}
+
+// TMA load-path probe (see tma_rate_probe_kernel): x bf16 [n, t, h, w, c] dense; clk int64 [grid] cycles per CTA.
+extern "C" int vsb_debug_tma_rate(const void* x, int n, int t, int h, int w, int c, int mode, int kt, int box_rows,
+                                  int stages, int tiles, int grid, long long* clk, void* stream) {
+  VSB_CHECK_ARG(x && clk && n > 0 && t > 0 && h > 0 && w > 0 && c % 16 == 0 && tiles > 0 && grid > 0, "bad argument");
+  int rc = load_driver_entry_points();
+  if (rc != VSB_OK) return rc;
+  TmaProbeParams p{};
+  p.mode = mode; p.kt = kt; p.n_clips = n; p.H = h; p.T = t;
+  p.kc = c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16);
+  p.cchunks = c / p.kc;
+  int RP = 8;
+  while (RP < w + 1) RP <<= 1;
+  p.RP = RP;
+  p.rp_rows = 128 / RP;
+  VSB_CHECK_ARG(box_rows >= 1 && p.rp_rows % box_rows == 0, "box_rows must divide the tile rows");
+  p.box_rows = box_rows;
+  p.FP = ceil_div(h + 1, box_rows) * box_rows;
+  while (((long long)t * p.FP * RP) % 128) p.FP += box_rows;
+  p.tiles_per_clip = mode != 1 ? (int)((long long)t * p.FP * RP / 128) : (int)((long long)t * h * w / 128);
+  p.tiles = tiles; p.stages = stages;
+  p.chunk_bytes = 128u * p.kc * 2;
+  p.box_bytes = (uint32_t)box_rows * RP * p.kc * 2;
+  p.clk = clk;
+  CUtensorMap m5, m2;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)t, (cuuint64_t)n};
+    cuuint64_t str[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2, (cuuint64_t)t * h * w * c * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.kc, (cuuint32_t)RP, (cuuint32_t)box_rows, 1, 1};
+    if (mode == 2) {
+      const int lower[3] = {0, 0, -(kt >> 1)};
+      const int upper[3] = {RP - w, p.FP - h, (kt >> 1) - (kt - 1)};
+      const int one3[3] = {1, 1, 1};
+      VSB_CHECK_ARG(RP - w <= 15 && p.FP - h <= 15, "padded box outside the im2col corner range");
+      rc = encode_im2col_map(&m5, x, n, t, h, w, c, c, lower, upper, one3, p.kc, 128, swizzle_for(p.kc * 2));
+    } else {
+      rc = fb_encode(&m5, x, 5, dims, str, box, swizzle_for(p.kc * 2), "probe 5d");
+    }
+    if (rc != VSB_OK) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)n * t * h * w};
+    cuuint64_t str[1] = {(cuuint64_t)c * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.kc, 128};
+    rc = fb_encode(&m2, x, 2, dims, str, box, swizzle_for(p.kc * 2), "probe 2d");
+    if (rc != VSB_OK) return rc;
+  }
+  const size_t smem = (size_t)stages * p.chunk_bytes + 2048 + 1024;
+  VSB_CHECK_ARG(smem <= 227 * 1024, "ring too large");
+  VSB_CHECK_CUDA(cudaFuncSetAttribute(tma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  tma_rate_probe_kernel<<<grid, 64, smem, static_cast<cudaStream_t>(stream)>>>(m5, m2, p);
+  VSB_CHECK_LAUNCH("tma_rate_probe_kernel");
   return VSB_OK;
 }

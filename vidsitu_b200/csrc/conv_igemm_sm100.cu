@@ -479,7 +479,7 @@ CUtensorMapSwizzle swizzle_for(int row_bytes) {
 }
 
 // (C,W,H,D,N) im2col map over a bf16 NTHWC tensor.
-static int encode_im2col_map(CUtensorMap* map, const void* base, int n, int t, int h, int w, int c, int pitch,
+int encode_im2col_map(CUtensorMap* map, const void* base, int n, int t, int h, int w, int c, int pitch,
                              const int lower[3], const int upper[3], const int stride_whd[3], int chan_box,
                              int pixel_box, CUtensorMapSwizzle swz) {
   cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)t, (cuuint64_t)n};

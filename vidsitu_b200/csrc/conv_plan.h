@@ -89,6 +89,9 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 extern EncodeTiledFn g_encode_tiled;
 int load_driver_entry_points();
 CUtensorMapSwizzle swizzle_for(int row_bytes);
+// (C,W,H,D,N) im2col-mode map over a bf16 NTHWC tensor (conv_igemm_sm100.cu); lower / upper / stride are (w, h, d)
+int encode_im2col_map(CUtensorMap* map, const void* base, int n, int t, int h, int w, int c, int pitch, const int lower[3],
+                      const int upper[3], const int stride_whd[3], int chan_box, int pixel_box, CUtensorMapSwizzle swz);
 
 // window algorithm: returns VSB_OK when the plan was built, 1 when the conv is outside the
 // algorithm's domain (caller falls back to im2col), a negative vsb_status on error

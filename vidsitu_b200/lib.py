@@ -119,6 +119,7 @@ def load() -> C.CDLL:
     lib.vsb_debug_umma_rate2.argtypes = [i, i, i, i, i, i, i, i, vp, vp]
     lib.vsb_debug_conv_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.vsb_debug_conv_plan_info.argtypes = [vp, C.POINTER(C.c_longlong)]
+    lib.vsb_debug_tma_rate.argtypes = [vp, i, i, i, i, i, i, i, i, i, i, i, vp, vp]
     lib.vsb_debug_bottleneck_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
     for name in ("vsb_pack_frames", "vsb_bottleneck_plan_create", "vsb_bottleneck_run", "vsb_bottleneck_plan_info",
                  "vsb_conv3d_plan_create", "vsb_conv3d_run", "vsb_conv3d_plan_out_shape",
@@ -126,7 +127,7 @@ def load() -> C.CDLL:
                  "vsb_score_rows", "vsb_transpose_pad",
                  "vsb_nthwc_to_ncthw_f32", "vsb_ncthw_f32_to_nthwc", "vsb_debug_im2col_probe",
                  "vsb_debug_umma_semantics", "vsb_debug_umma_rate", "vsb_debug_umma_rate2", "vsb_debug_conv_stats", "vsb_debug_conv_plan_info",
-                 "vsb_debug_bottleneck_stats"):
+                 "vsb_debug_bottleneck_stats", "vsb_debug_tma_rate"):
         getattr(lib, name).restype = i
     if lib.vsb_abi_version() != 5:
         raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 5")
