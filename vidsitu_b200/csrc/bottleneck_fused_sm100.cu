@@ -30,6 +30,7 @@
 #include <cuda.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <new>
@@ -45,8 +46,9 @@ namespace {
 constexpr int kRing = 4;  // a-tiles in the ring (power of two) + 1 mirror tile
 constexpr int kMaxBoxes = 16;
 constexpr int kMaxStages = 24;
-constexpr int kBEpiWarp0 = 4, kCEpiWarp0 = 8, kProducerWarp = 16, kMmaWarp = 17, kMmaAWarp = 18;
-constexpr int kThreads = 19 * 32;
+constexpr int kBEpiWarp0 = 4, kCEpiWarp0 = 8, kProducerWarp = 16, kMmaWarp = 17, kMmaAWarp = 18, kProducer2Warp0 = 19;
+constexpr int kXProducers = 2;  // warps that copy x chunks in cp.async mode: kProducerWarp and one more (20 warps: 96 registers)
+constexpr int kThreads = 20 * 32;
 constexpr int kCEpiWarps = 8;
 constexpr int kMaxEpiBufs = 3;
 #ifndef FB_PRETEST
@@ -75,6 +77,9 @@ struct FusedParams {
   int cps, slots_per_tile;
   int pf_dist;                  // L2 prefetch distance of the x loads, in tiles (0 = off)
   int x_im2col;                 // x chunks by ONE im2col-mode TMA load each (else tiled boxes of box_rows flat rows)
+  int x_cpasync;                // x chunks by per-thread cp.async copies (two producer warps), not by the TMA unit
+  const uint8_t* x;             // block input (cp.async mode)
+  int x_pitch;
   uint32_t stage_bytes;
   // shared-memory layout (bytes from the 1 KiB-aligned base)
   uint32_t off_wa, off_wb, off_wc, off_ring, off_p, off_epi, off_bar, off_tab;
@@ -234,7 +239,7 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     tma_prefetch_desc(&map_res);
     tma_prefetch_desc(&map_out);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&x_full[s], 1);
+      mbar_init(&x_full[s], p.x_cpasync ? 32 * kXProducers : 1);
       mbar_init(&x_empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -288,9 +293,8 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kProducerWarp) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer (one thread)
+  if (warp == kProducerWarp || warp >= kProducer2Warp0) {
+    if (warp == kProducerWarp && lane == 0) {
       // resident weights: Wa as chunks_per_tile blocks [d16 rows x kc], Wb as 9 tap blocks [d16 x d16], Wc [cout x d16]
       // (Wb / Wc boxes are a_row_bytes wide: when that is more than d16 channels the extra K columns are never read)
       mbar_expect_tx(w_bar, (uint32_t)p.chunks_per_tile * (uint32_t)p.d16 * p.x_row_bytes +
@@ -300,38 +304,85 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       for (int tap = 0; tap < 9; ++tap)
         tma_load_2d(smem + p.off_wb + tap * p.wb_block_bytes, &map_wb, w_bar, tap * p.d16, 0);
       tma_load_2d(smem + p.off_wc, &map_wc, w_bar, 0, 0);
-
+    }
+    __syncwarp();
+    const int S = p.stages, cch = p.cchunks, kc = p.kc, cps = p.cps, cpt = p.chunks_per_tile;
+    if (p.x_cpasync) {
+      // ---------------------------------------------------------- x producer, cp.async mode (two whole warps)
+      // The TMA unit is the bound of this kernel when it also has to move x (measured: ~25 B/clk/SM for x + residual
+      // + output); here x goes through the LSU instead: every lane copies 16-byte pieces of chunk rows (coalesced:
+      // 32 lanes = 32 / pieces-per-row consecutive slots), swizzling the destination as the TMA unit would and
+      // zero-filling the padding slots (src-size 0).  Chunk q of a tile is copied by producer q % 2.
+      const int pidx = warp == kProducerWarp ? 0 : warp - kProducer2Warp0 + 1;
+      const uint32_t rb = p.x_row_bytes, swz_mask = rb == 128 ? 7u : (rb == 64 ? 3u : 1u);
+      const int ppr = (int)(rb >> 4), rpi = 32 / ppr;          // 16-byte pieces per row, rows per warp instruction
+      const int piece = lane % ppr;
+      const int row_first = pidx * (128 / kXProducers) + lane / ppr;   // this producer copies rows [pidx * 64, +64) of every chunk
+      const int iters = (128 / kXProducers) / rpi;
+      const int pt = p.kt >> 1;
+      const long long pitch2 = (long long)p.x_pitch * 2;
+      const long long d_row = (long long)(p.W - p.RP) * pitch2;            // image row wrap (xs -= RP, ++y)
+      const long long d_frame = (long long)(p.H - p.FP) * p.W * pitch2;    // frame wrap (y: FP -> 0, ++t)
+      const long long d_step = (long long)rpi * pitch2;
+      const long long frame_bytes = (long long)p.H * p.W * pitch2;
+      const int RP = p.RP, FP = p.FP, W = p.W, H = p.H, T = p.T;
       int slot = 0;
-      uint32_t parity = 1;  // first pass over the ring: slots are free
-      const int S = p.stages, nbox = p.boxes_per_tile, cch = p.cchunks, kc = p.kc, cps = p.cps;
-      const int FP = p.FP, pt = p.kt >> 1, cpt = p.chunks_per_tile, kt_ = p.kt;
-      // L2 prefetch cursor, pf_dist a-tiles ahead of the loads: the newest frame of a tile (dt = kt-1) is the one no
-      // earlier tile has touched (the others were loaded ~tiles_per_frame tiles ago and sit in the L2); fetching it
-      // early turns the ring's DRAM-latency loads into L2 hits (the ring only holds ~2 tiles of x)
-      ATileIter pf;
-      pf.init(p);
-      auto prefetch_tile = [&](const ATileIter& a) {
-        const int r0p = a.m() * p.rows_per_tile + p.row_bias;
-        const int dt0 = a.j == 0 ? 0 : kt_ - 1;  // the first tile of a walk has seen no frame yet
-        for (int b = 0; b < nbox; ++b) {
-          const int r = r0p + b * p.box_rows;
-          const int tq = r / FP;
-          const int t = tq - p.row_bias / FP, y = r - tq * FP;
-          if (y >= p.H) continue;
-          for (int dt = dt0; dt < kt_; ++dt) {
-            const int tt = t + dt - pt;
-            if (tt < 0 || tt >= p.T) continue;
-            for (int cc2 = 0; cc2 < cch; ++cc2) tma_prefetch_5d(&map_x, cc2 * kc, 0, y, tt, a.n);
-          }
-        }
-      };
-      for (int i = 0; i < p.pf_dist && pf.valid(p); ++i, pf.next(p)) prefetch_tile(pf);
+      uint32_t parity = 1;
       ATileIter it;
       for (it.init(p); it.valid(p); it.next(p)) {
-        if (p.pf_dist > 0 && pf.valid(p)) {
-          prefetch_tile(pf);
-          pf.next(p);
+        const int m = it.m();
+        const bool outside = m < 0 || m >= p.tiles_per_clip;
+        // (xs, y, t) and byte offset of this lane's first row; later rows advance by rpi slots
+        const int f0 = (outside ? 0 : m * 128) + row_first;
+        const int xs0 = f0 & (RP - 1), r0 = f0 >> p.rp_shift;
+        const int t0 = r0 / FP, y0 = r0 - t0 * FP;
+        const long long g0 = ((((long long)it.n * T + t0) * H + y0) * W + xs0) * pitch2 + piece * 16;
+        for (int q = 0; q < cpt; q += cps) {
+          FB_T(0, mbar_wait(&x_empty[slot], parity));
+          if (outside) {
+            mbar_arrive(&x_full[slot]);   // every slot of the tile is padding: nothing to copy
+          } else {
+            const uint32_t slot_s = smem_u32(smem) + (uint32_t)slot * p.stage_bytes;
+            for (int c = 0; c < cps; ++c) {
+              const int qq = q + c;
+              const int dt = qq / cch, cc = qq - dt * cch;
+              const uint32_t dst_s = slot_s + (uint32_t)c * p.chunk_bytes;
+              uint32_t off = (uint32_t)row_first * rb + (uint32_t)piece * 16u;
+              int xs = xs0, y = y0, tt = t0 + dt - pt;
+              long long g = g0 + (long long)(dt - pt) * frame_bytes + (long long)(cc * kc) * 2;
+#pragma unroll 2
+              for (int i = 0; i < iters; ++i) {
+                const bool ok = xs < W && y < H && (unsigned)tt < (unsigned)T;
+                cp_async16(dst_s + (off ^ (((off >> 7) & swz_mask) << 4)), p.x + (ok ? g : 0ll), ok ? 16u : 0u);
+                off += (uint32_t)rpi * rb;
+                xs += rpi;
+                g += d_step;
+                while (xs >= RP) {
+                  xs -= RP;
+                  g += d_row;
+                  if (++y == FP) {
+                    y = 0;
+                    ++tt;
+                    g += d_frame;
+                  }
+                }
+              }
+            }
+            cp_async_arrive_noinc(&x_full[slot]);   // fires when this lane's copies of the slot have landed
+          }
+          if (++slot == S) {
+            slot = 0;
+            parity ^= 1;
+          }
         }
+      }
+    } else if (warp == kProducerWarp && lane == 0) {
+      // ------------------------------------------------------------ x producer, TMA mode (one thread)
+      int slot = 0;
+      uint32_t parity = 1;  // first pass over the ring: slots are free
+      const int nbox = p.boxes_per_tile, FP = p.FP, pt = p.kt >> 1;
+      ATileIter it;
+      for (it.init(p); it.valid(p); it.next(p)) {
         const int r0 = it.m() * p.rows_per_tile + p.row_bias;  // >= 0
         int bt[kMaxBoxes], by[kMaxBoxes];
         for (int b = 0; b < nbox; ++b) {
@@ -486,6 +537,7 @@ bottleneck_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       for (int q = 0; q < spt; ++q) {
         FB_T(2, mbar_wait(&x_full[slot], xpar));
         const long long i0 = kDbg ? clock64() : 0;
+        if (p.x_cpasync) fence_proxy_async_smem();   // cp.async wrote the chunk through the generic proxy
         tc_fence_after();
         if (elect_one()) {
           fb_issue(tm_d, x_hi, x_hi, xring_lo + (uint32_t)slot * stage_lo, wa_lo + (uint32_t)(q * cps) * wa_blk_lo, tab_a, n_a,
@@ -922,7 +974,12 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
   // im2col-mode x loads when the padded bounding box fits the TMA corner range (measured: tiled 5-D boxes with
   // out-of-bounds slots run at 10 - 21 B/clk/SM, one im2col load per 16 KiB chunk at the 2-D rate)
   p.x_im2col = (RP - d->w <= 15 && FP - d->h <= 15 && !getenv("VSB_FUSED_TILED_X")) ? 1 : 0;
-  p.pf_dist = getenv("VSB_FUSED_PF") ? atoi(getenv("VSB_FUSED_PF")) : 0;  // measured: the TMA unit is the bound, prefetches only add to it
+  // cp.async x producers are an experiment kept for the record (VSB_FUSED_X=cpasync): two warps of 16-byte copies
+  // sustain only ~7 B/clk/SM (too few copies in flight), against ~23 B/clk/SM of im2col TMA loads
+  p.x_cpasync = getenv("VSB_FUSED_X") ? (strcmp(getenv("VSB_FUSED_X"), "cpasync") == 0) : 0;
+  p.x = static_cast<const uint8_t*>(d->x);
+  p.x_pitch = d->x_pitch;
+  p.pf_dist = 0;
   p.off_wa = (uint32_t)stages * p.stage_bytes;
   p.off_wb = p.off_wa + p.chunks_per_tile * p.wa_block_bytes;
   p.off_wc = p.off_wb + 9 * p.wb_block_bytes;

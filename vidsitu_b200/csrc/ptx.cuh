@@ -113,6 +113,15 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const void* map, uint64_
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// Ampere-style asynchronous 16-byte copy global -> shared, L1 bypassed; src_bytes < 16 zero-fills the rest (0: all
+// zeros, the source is not read).  Completion is tracked per thread: cp_async_arrive_noinc makes an mbarrier arrival
+// (counted against the barrier's expected count) fire once every copy this thread issued before it has landed.
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // L2 prefetch of a tiled-mode 5-D box (no shared memory, no barrier): later loads of the box hit the L2
 __device__ __forceinline__ void tma_prefetch_5d(const void* map, int c0, int c1, int c2, int c3, int c4) {
   asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
