@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VSB_ABI_VERSION 5
+#define VSB_ABI_VERSION 6
 
 typedef enum vsb_status {
   VSB_OK = 0,
@@ -133,6 +133,24 @@ typedef struct vsb_conv_desc {
    * out_i = in_i . W_i^T - the two einsums of the non-local block with phi_i / g_i^T as W_i
    * (nonlocal_helper.py:123-141).  `wgt` must hold (n-1) * wgt_clip_rows + cout rows.  0 = one matrix.   */
   int wgt_clip_rows;
+  /* Tile-granular chaining of two consecutive launches of a stream (bf16, one-SM im2col kernel; ABI v6).
+   * A ResBlock's last conv and the next block's first 1x1x1 conv (resnet_helper.py:352-358 followed by :225-229)
+   * then run CO-RESIDENT on every SM and the second reads each 128-pixel tile of `out` from the L2 right after the
+   * first wrote it, instead of re-reading the whole tensor from HBM one launch later.
+   *   producer (tile_signal != NULL): every epilogue warp adds 1 to tile_signal[m] (release, gpu scope) once its
+   *     rows of output tile m = rows [128 m, 128 m + 128) are complete in global memory: the counter of a finished
+   *     tile is 8 * (cout / block_n).
+   *   consumer (tile_wait != NULL; 1x1x1 stride 1, one column block, input = the producer's output): loads tile m
+   *     once tile_wait[m] >= tile_wait_count, then resets tile_wait[m] to 0; it does NOT wait for the previous
+   *     kernel as a whole (programmatic dependent launch), so it must be launched right after its producer on the
+   *     same stream and must not write memory that the producer or anything before it still reads.
+   * Counters are caller-owned device memory (one uint32 per 128-row tile), zero before the first use.          */
+  unsigned int* tile_signal;
+  unsigned int* tile_wait;
+  int tile_wait_count;
+  /* bf16 im2col algorithm: at most this many CTAs (0 = automatic: every SM, twice when two CTAs fit).  A chained
+   * pair splits the SMs' CTA slots between producer and consumer with it.                                    */
+  int grid_limit;
 } vsb_conv_desc;
 
 #define VSB_PLAN_STREAM_WEIGHTS 1 /* im2col: never keep the weight block resident in shared memory      */

@@ -1,5 +1,6 @@
 // Library-level entry points: ABI version, thread-local error text, launch counter.
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -14,6 +15,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VSB_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }

@@ -109,6 +109,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kProducerWarp = kEW, kMmaWarp = kEW + 1;
+  pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel (ptx.cuh)
   constexpr uint32_t row_bytes = KK * 32;
   constexpr int kchunk = KK * 16;
   constexpr uint32_t a_chunk_bytes = kBlockM * row_bytes;
@@ -186,6 +187,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           tma2_load_2d(bres + g * b_chunk_bytes, &map_b, bres_leader, g * kchunk,
                        n_tile * p.block_n + (int)rank * (int)half_n);
       }
+      pdl_wait();  // activations are the previous kernels' outputs
       const uint32_t chunk_tx_eff = b_resident ? 2u * a_chunk_bytes : chunk_tx;
       const int total_chunks = p.total_chunks, stages = p.stages;
       const int cin = p.cin, fkw = p.kw, fkh = p.kh, block_n = p.block_n;
@@ -345,6 +347,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       pf_skip();
     };
+    pdl_wait();  // residual loads read, and the stores overwrite, memory the previous kernel may still be using
     if (lane == 0) {
       pf_skip();
       for (int i = 0; i < nb - 1 && pf_pm < pm_tiles; ++i) arm_next();
@@ -420,23 +423,11 @@ int igemm2_launch(const vsb_conv_plan* plan, cudaStream_t stream) {
     set_error("cudaFuncSetAttribute(conv_igemm2_kernel) failed: %s", cudaGetErrorString(attr_err));
     return VSB_ERR_CUDA;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(plan->grid, 1, 1);
-  cfg.blockDim = dim3((kEW + 2) * 32, 1, 1);
-  cfg.dynamicSmemBytes = plan->smem_bytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   cudaError_t e = plan->params.kchunk == 64
-                      ? cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<4>, plan->map_a, plan->map_b, plan->map_out,
-                                           plan->map_res, plan->map_a2, plan->params)
-                      : cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<2>, plan->map_a, plan->map_b, plan->map_out,
-                                           plan->map_res, plan->map_a2, plan->params);
+                      ? launch_pdl(conv_igemm2_kernel<4>, plan->grid, (kEW + 2) * 32, plan->smem_bytes, stream, 2, plan->map_a,
+                                   plan->map_b, plan->map_out, plan->map_res, plan->map_a2, plan->params)
+                      : launch_pdl(conv_igemm2_kernel<2>, plan->grid, (kEW + 2) * 32, plan->smem_bytes, stream, 2, plan->map_a,
+                                   plan->map_b, plan->map_out, plan->map_res, plan->map_a2, plan->params);
   if (e != cudaSuccess) {
     set_error("launch of conv_igemm2_kernel failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

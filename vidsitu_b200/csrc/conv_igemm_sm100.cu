@@ -67,6 +67,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kEpiWarps = EW, kProducerWarp = EW, kMmaWarp = EW + 1;
+  pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel (it waits for our completion itself)
 
   const uint32_t row_bytes = p.kchunk * 2;
   const uint32_t a_chunk_bytes = kBlockM * row_bytes;
@@ -135,6 +136,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int g = 0; g < p.total_chunks; ++g)
           tma_load_2d(bres + g * b_chunk_bytes, &map_b, bres_bar, g * p.kchunk, n_tile * p.block_n);
       }
+      // activations are the previous kernels' outputs (weights, scale / bias are constants).  A chained consumer
+      // (tile_wait) runs next to its producer instead and waits tile by tile below.
+      unsigned int* const tile_wait = p.tile_wait;
+      if (!tile_wait) pdl_wait();
       const bool b_resident = p.b_resident != 0;
       const uint32_t stage_tx = b_resident ? a_chunk_bytes : a_chunk_bytes + b_chunk_bytes;
       const int cps = 4 / KK, kchunk = 16 * KK;
@@ -149,6 +154,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const bool rev = p.reverse != 0;
       for (int mt_ = m_tile0; mt_ < m_tiles; mt_ += m_tile_step) {
         const int mt = rev ? m_tiles - 1 - mt_ : mt_;
+        if (tile_wait) tile_counter_wait_reset(tile_wait + mt, p.tile_wait_count);  // the producer kernel finished tile mt
         int m0 = mt * kBlockM, wrow0 = 0;
         if (clip_rows) {  // per-clip weights: tile lt of clip cb (its last tile runs into the next clip: never stored)
           const int cb = mt / clip_tiles;
@@ -339,11 +345,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       pf_skip();
     };
+    // residual loads read, and the stores overwrite, memory the previous kernel may still be using (a chained
+    // consumer's first store follows its first tile counter, i.e. the producer's own wait)
+    if (!p.tile_wait) pdl_wait();
     if (lane == 0) {
       pf_skip();
       for (int i = 0; i < nb - 1 && pf_mt < m_tiles; ++i) arm_next();
     }
     __syncwarp();
+    int sig_mt = -1, sig_stores = 0, gq_stores = 0;  // lane 0: tile to publish next, store groups issued up to it / so far
     int b = 0;            // staging slab of this warp's current chunk (ring of nb)
     uint32_t bpar = 0;    // parity of that slab's ready barrier
     int gq = 0;           // global chunk counter of the CTA (all tiles, all chunks)
@@ -384,6 +394,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tma_store_2d(&map_out, buf, nbase + col0, m0 + row_in_tile);  // rows >= m_total are clipped by the TMA unit
           }
           tma_store_commit();
+          ++gq_stores;
           // arm the slab of this warp's chunk q + nb - 1 (the one chunk q - 1 used): its store must have read it
           if (pf_mt < m_tiles) {
             IG_T(7, tma_store_wait_read1());
@@ -399,9 +410,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // every tcgen05.ld this warp issues for the accumulator has completed: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        mbar_arrive(&tmem_empty[acc]);
+        if (p.tile_signal) {
+          // publish this warp's rows of the PREVIOUS tile to the chained consumer kernel: its store groups are the
+          // ones older than the groups of the tile just issued, so waiting for them does not stall this warp
+          if (sig_mt >= 0) {
+            tma_store_wait_pending(gq_stores - sig_stores);
+            fence_proxy_async_all();
+            red_release_gpu_add(p.tile_signal + sig_mt, 1u);
+          }
+          sig_mt = mt;
+          sig_stores = gq_stores;
+        }
+      }
     }
-    if (lane == 0) tma_store_wait_all();  // this warp's output bytes are in global memory before the CTA exits
+    if (lane == 0) {
+      tma_store_wait_all();  // this warp's output bytes are in global memory before the CTA exits
+      if (p.tile_signal && sig_mt >= 0) {
+        fence_proxy_async_all();
+        red_release_gpu_add(p.tile_signal + sig_mt, 1u);
+      }
+    }
   }
 
   if (kDbg && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == 0)) {
@@ -622,9 +652,20 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   int kchunk = d->kchunk;
   if (!kchunk) kchunk = (d->cin % 64 == 0) ? 64 : ((d->cin % 32 == 0) ? 32 : 16);
   if ((kchunk != 16 && kchunk != 32 && kchunk != 64) || d->cin % kchunk) FAIL(VSB_ERR_INVALID, "bad kchunk %d for cin %d", kchunk, d->cin);
+  // tile-granular chaining: producer and consumer share every SM (each <= half of the shared memory and of TMEM)
+  const bool chained = d->tile_signal != nullptr || d->tile_wait != nullptr;
+  if (chained) {
+    if (d->wgt_clip_rows || d->out_f16 || (d->flags & (VSB_PLAN_TWO_SM | VSB_PLAN_TWO_SM_RESIDENT)))
+      FAIL(VSB_ERR_INVALID, "tile chaining needs the plain one-SM im2col kernel");
+    if (d->tile_wait && (d->kt * d->kh * d->kw != 1 || d->st * d->sh * d->sw != 1 || d->tile_wait_count <= 0 || d->in2 || d->residual))
+      FAIL(VSB_ERR_INVALID, "a chained consumer is a 1x1x1 stride-1 conv without residual / second source (tile_wait_count > 0)");
+    if ((reinterpret_cast<uintptr_t>(d->tile_signal) | reinterpret_cast<uintptr_t>(d->tile_wait)) & 3)
+      FAIL(VSB_ERR_ALIGN, "tile counters must be 4-byte aligned");
+  }
   int block_n = d->block_n;
+  if (chained && block_n > 128) FAIL(VSB_ERR_INVALID, "tile chaining: block_n <= 128 (two kernels share the 512 TMEM columns)");
   if (!block_n) {
-    block_n = 256;
+    block_n = chained ? 128 : 256;
     while (block_n > 16 && d->cout % block_n) block_n >>= 1;
     if (block_n < 64 && d->cout > 64) {
       // no power-of-two column block (e.g. the 784 keys of a res3 non-local block as output channels):
@@ -697,19 +738,20 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
         // 512 TMEM columns or 16 epilogue warps => one CTA per SM anyway: use the whole shared memory;
         // otherwise try to leave room for two CTAs per SM and fall back to one big CTA when that starves
         // the pipeline
-        long long budget = ((sp.tmem_cols == 512 || epi_warps == 16) ? 227 : 113) * 1024 - fixed;
+        long long budget = ((sp.tmem_cols == 512 || epi_warps == 16) && !chained ? 227 : 113) * 1024 - fixed;
         stages = budget > 0 ? (int)(budget / sp.stage_bytes) : 0;
-        if (stages < 3 && stages < 2 * num_kstages) stages = (int)((227 * 1024 - fixed) / sp.stage_bytes);
+        if (stages < 3 && stages < 2 * num_kstages && !chained) stages = (int)((227 * 1024 - fixed) / sp.stage_bytes);
         if (stages > 8) stages = 8;
       }
       if (stages > 16) stages = 16;
       // a caller-given depth that does not fit is shortened rather than rejected
-      while (d->stages && stages > 2 && (long long)stages * sp.stage_bytes + fixed > 227 * 1024) --stages;
+      while (d->stages && stages > 2 && (long long)stages * sp.stage_bytes + fixed > (chained ? 113 : 227) * 1024) --stages;
       if (stages > num_kstages * 2) stages = num_kstages * 2;
       sp.stages = stages;
       sp.smem_bytes = (size_t)((stages > 0 ? stages : 0) * (long long)sp.stage_bytes + fixed);
-      if (stages >= 3 && sp.smem_bytes <= 227 * 1024) { sp.fits = true; break; }
-      if (stages >= 1 && sp.smem_bytes <= 227 * 1024 && (sp.epi_bufs == 2 || stages >= 2 * num_kstages)) { sp.fits = true; break; }
+      const size_t smem_cap = (size_t)(chained ? 113 : 227) * 1024;
+      if (stages >= 3 && sp.smem_bytes <= smem_cap) { sp.fits = true; break; }
+      if (stages >= 1 && sp.smem_bytes <= smem_cap && (sp.epi_bufs == 2 || stages >= 2 * num_kstages)) { sp.fits = true; break; }
       if (sp.epi_bufs > 2) {
         sp.epi_bufs = 2;  // give the shared memory back to the main-loop pipeline
         continue;
@@ -745,6 +787,8 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   if (block_n % (sp.epi_n ? sp.epi_n : 1) || !sp.epi_n) FAIL(VSB_ERR_INVALID, "block_n %d is not a multiple of the epilogue chunk", block_n);
   if (!sp.fits) FAIL(VSB_ERR_INVALID, "pipeline (%d stages x %d bytes) does not fit in shared memory", sp.stages, sp.stage_bytes);
   const int n_tiles = d->cout / block_n;
+  if (d->tile_wait && n_tiles != 1) FAIL(VSB_ERR_INVALID, "a chained consumer needs one column block (cout %d <= 128)", d->cout);
+  if (chained && sp.tmem_cols > 256) FAIL(VSB_ERR_INVALID, "tile chaining: the plan needs %u TMEM columns (> 256)", sp.tmem_cols);
   const uint32_t tmem_cols = sp.tmem_cols;
   const long long bres_bytes = sp.bres_bytes;
   const int stage_bytes = sp.stage_bytes, stages = sp.stages, epi_n = sp.epi_n, epi_bufs = sp.epi_bufs;
@@ -844,12 +888,21 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   p.relu = d->relu;
   p.out_f16 = d->out_f16 ? 1 : 0;
   p.reverse = (d->flags & VSB_PLAN_REVERSE) ? 1 : 0;
+  p.tile_signal = d->tile_signal;
+  p.tile_wait = d->tile_wait;
+  p.tile_wait_count = (unsigned)d->tile_wait_count;
   p.dbg = nullptr;
   if (getenv("VSB_WIN_DEBUG")) {  // debug only: the one place the library allocates device memory
     if (cudaMalloc(&p.dbg, 16 * sizeof(long long)) == cudaSuccess) (void)cudaMemset(p.dbg, 0, 16 * sizeof(long long));
     else p.dbg = nullptr;
   }
   plan->smem_bytes = smem_bytes;
+#define FAIL2(code, ...)    \
+  do {                      \
+    set_error(__VA_ARGS__); \
+    delete plan;            \
+    return code;            \
+  } while (0)
   int ctas_per_sm = (int)(512 / tmem_cols);
   const int by_smem = (int)((227 * 1024) / smem_bytes);
   if (ctas_per_sm > by_smem) ctas_per_sm = by_smem;
@@ -863,7 +916,9 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   }
   long long grid = (long long)sms * ctas_per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
+  if (d->grid_limit > 0 && grid > d->grid_limit) grid = d->grid_limit;
   grid -= grid % p.n_tiles;  // every CTA owns one column block (total_tiles is a multiple of n_tiles too)
+  if (grid < p.n_tiles) FAIL2(VSB_ERR_INVALID, "grid_limit %d is below the %d column blocks", d->grid_limit, p.n_tiles);
   plan->grid = (unsigned)grid;
   plan->desc.block_n = block_n;
   plan->desc.kchunk = kchunk;
@@ -876,7 +931,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   static const bool no_two_sm_env = getenv("VSB_NO_TWO_SM") != nullptr;
   // (64-byte rows, i.e. the pixel-grouped stems: 2 - 4 % faster in pairs once a ring stage carries two chunks;
   // with one chunk = two MMAs per stage the issuer was the bottleneck: 0.46 vs 0.42 ms)
-  const bool two_sm_auto = !no_two_sm_env && !(d->flags & VSB_PLAN_ONE_SM) && !d->out_f16 && !d->wgt_clip_rows && block_n == 256 && (kchunk == 64 || kchunk == 32) &&
+  const bool two_sm_auto = !no_two_sm_env && !chained && !(d->flags & VSB_PLAN_ONE_SM) && !d->out_f16 && !d->wgt_clip_rows && block_n == 256 && (kchunk == 64 || kchunk == 32) &&
                            total_chunks >= 8 && p.total_tiles / p.n_tiles >= 16;
   if (((d->flags & (VSB_PLAN_TWO_SM | VSB_PLAN_TWO_SM_RESIDENT)) || two_sm_auto) && !d->out_f16 && !d->wgt_clip_rows && (kchunk == 64 || kchunk == 32) && !b_resident &&
       block_n % 16 == 0 && block_n >= 32 && epi_warps == 8 && p.total_tiles / p.n_tiles >= 2) {
@@ -949,11 +1004,11 @@ extern "C" int vsb_conv3d_run(const vsb_conv_plan* plan, void* stream) {
 #define VSB_IG_LAUNCH(KK, DBG)                                                                              \
   do {                                                                                                      \
     if (plan->params.epi_warps == 16)                                                                       \
-      conv_igemm_kernel<KK, DBG, 16><<<plan->grid, 18 * 32, plan->smem_bytes, s>>>(                         \
-          plan->map_a, plan->map_b, plan->map_out, plan->map_res, plan->map_a2, plan->params);              \
+      (void)launch_pdl(conv_igemm_kernel<KK, DBG, 16>, plan->grid, 18 * 32, plan->smem_bytes, s, 1,         \
+                       plan->map_a, plan->map_b, plan->map_out, plan->map_res, plan->map_a2, plan->params); \
     else                                                                                                    \
-      conv_igemm_kernel<KK, DBG, 8><<<plan->grid, 10 * 32, plan->smem_bytes, s>>>(                          \
-          plan->map_a, plan->map_b, plan->map_out, plan->map_res, plan->map_a2, plan->params);              \
+      (void)launch_pdl(conv_igemm_kernel<KK, DBG, 8>, plan->grid, 10 * 32, plan->smem_bytes, s, 1,          \
+                       plan->map_a, plan->map_b, plan->map_out, plan->map_res, plan->map_a2, plan->params); \
   } while (0)
   const bool dbg = plan->params.dbg != nullptr;
   switch (plan->params.kchunk) {

@@ -32,6 +32,10 @@ struct IgemmParams {
   int clip_rows;       // output pixels per clip (0 = one weight matrix for all clips)
   int clip_tiles;      // m-tiles per clip = ceil(clip_rows / 128)
   int wgt_clip_rows;   // weight rows between consecutive clips' matrices
+  // tile-granular chaining (vsb_conv_desc.tile_signal / tile_wait): counters per 128-row output tile
+  unsigned int* tile_signal;  // producer: every epilogue warp adds 1 once its rows of the tile are in global memory
+  unsigned int* tile_wait;    // consumer: tile m is loaded once tile_wait[m] >= tile_wait_count (then reset to 0)
+  unsigned int tile_wait_count;
   long long* dbg;  // role timeline counters (VSB_WIN_DEBUG), else null
 };
 

@@ -68,6 +68,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ WinParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel (ptx.cuh)
 
   const uint32_t epi_row_bytes = p.epi_n * 2;
   uint8_t* bres = smem + p.off_b;
@@ -152,6 +153,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
       for (int kt = 0, g = 0; kt < KT; ++kt)
         for (int j = 0; j < p.b_blocks_per_frame; ++j, ++g)
           tma_load_2d(bres + g * p.b_block_bytes, &map_b, bres_bar, kt * p.k_per_frame + j * 64, 0);
+      pdl_wait();  // activations are the previous kernels' outputs (the resident weights above are constants)
       const CUtensorMap* m0 = p.sub_map[0] ? &map_in1 : &map_in0;
       const CUtensorMap* m1 = p.sub_map[1] ? &map_in1 : &map_in0;
       const int nframes = p.tsc ? p.t_in : L + KT - 1;  // temporal-scatter walks the real input frames only
@@ -433,6 +435,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_consta
         if (tsplit) pf_next_tile();  // skip the other group's tile
       }
     };
+    pdl_wait();  // residual loads read, and the stores overwrite, memory the previous kernel may still be using
     if (lane == 0) {
       for (int i = 0; i < nb - 1 && pf.run < p.total_runs; ++i) arm_next();
     }
@@ -777,11 +780,11 @@ int win_plan_build(vsb_conv_plan* plan, const vsb_conv_desc* d, int to, int ho, 
 
 int win_plan_launch(const vsb_conv_plan* plan, cudaStream_t stream) {
   if (plan->win.dbg)
-    conv_win_kernel<true><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->map_a, plan->map_a1, plan->map_b,
-                                                                              plan->map_out, plan->map_res, plan->win);
+    (void)launch_pdl(conv_win_kernel<true>, plan->grid, kThreads, plan->smem_bytes, stream, 1, plan->map_a, plan->map_a1,
+                     plan->map_b, plan->map_out, plan->map_res, plan->win);
   else
-    conv_win_kernel<false><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(
-        plan->map_a, plan->map_a1, plan->map_b, plan->map_out, plan->map_res, plan->win);
+    (void)launch_pdl(conv_win_kernel<false>, plan->grid, kThreads, plan->smem_bytes, stream, 1, plan->map_a, plan->map_a1,
+                     plan->map_b, plan->map_out, plan->map_res, plan->win);
   VSB_CHECK_LAUNCH("conv_win_kernel");
   return VSB_OK;
 }

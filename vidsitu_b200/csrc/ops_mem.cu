@@ -60,6 +60,23 @@ pack_frames_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, i
   const long long total = (long long)n * t_out * chunks_per_frame;
   const int h = frame_px / w;
   int buf = 0;
+  // Software pipeline: the 16 bytes of chunk u + gridDim.x are requested (into a register) before chunk u is
+  // converted, so every thread keeps a load in flight across the barrier and the convert / store phase.
+  auto chunk_src = [&](long long u, int& npx) -> const uint4* {
+    const int chunk = (int)(u % chunks_per_frame);
+    const long long f = u / chunks_per_frame;
+    const int to = (int)(f % t_out);
+    const long long clip = f / t_out;
+    const int px0 = chunk << 10;
+    npx = min(1024, frame_px - px0);  // multiple of 16
+    return reinterpret_cast<const uint4*>(frames + ((clip * t_in + idx.v[to]) * (long long)frame_px + px0) * 3);
+  };
+  uint4 stage = make_uint4(0, 0, 0, 0);
+  if ((long long)blockIdx.x < total) {
+    int npx0;
+    const uint4* src = chunk_src(blockIdx.x, npx0);
+    if ((int)threadIdx.x * 16 < npx0 * 3) stage = __ldg(src + threadIdx.x);
+  }
   for (long long u = blockIdx.x; u < total; u += gridDim.x, buf ^= 1) {
     const int chunk = (int)(u % chunks_per_frame);
     const long long f = u / chunks_per_frame;
@@ -67,10 +84,13 @@ pack_frames_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, i
     const long long clip = f / t_out;
     const int px0 = chunk << 10;
     const int npx = min(1024, frame_px - px0);  // multiple of 16
-    const uint8_t* src = frames + ((clip * t_in + idx.v[to]) * (long long)frame_px + px0) * 3;
-    if ((int)threadIdx.x * 16 < npx * 3)
-      *reinterpret_cast<uint4*>(raw[buf] + threadIdx.x * 16) = __ldg(reinterpret_cast<const uint4*>(src) + threadIdx.x);
+    if ((int)threadIdx.x * 16 < npx * 3) *reinterpret_cast<uint4*>(raw[buf] + threadIdx.x * 16) = stage;
     __syncthreads();  // also orders the LUT fill; the other buffer is free: its readers passed the previous barrier
+    if (u + gridDim.x < total) {
+      int npx1;
+      const uint4* src = chunk_src(u + gridDim.x, npx1);
+      if ((int)threadIdx.x * 16 < npx1 * 3) stage = __ldg(src + threadIdx.x);
+    }
     OutT* dst_frame = out + ((clip * t_out + to) * (long long)h) * out_w * 4;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

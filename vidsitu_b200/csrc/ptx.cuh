@@ -23,6 +23,40 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor
+// in the stream is still running: everything before pdl_wait() (barrier init, TMEM allocation, loads of
+// constant data such as weights) overlaps the predecessor's tail; pdl_wait() returns once the predecessor
+// grid has completed and its memory operations are visible.  Every thread that reads or writes memory the
+// predecessor touches must call it.  pdl_launch_dependents() lets the successor's CTAs be scheduled as soon
+// as SM resources free up (it does NOT signal data readiness).  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------ tile counters in global memory (kernel chaining)
+// A producer kernel publishes finished output tiles to a co-resident consumer kernel through counters in
+// global memory.  Both sides move the tile itself with TMA (async proxy), the counter with generic accesses:
+// fence.proxy.async orders the two proxies on each side of the release / acquire pair.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded wait for *p >= target (a protocol bug ends in a trap, never in a hung GPU), then reset to 0.
+__device__ __forceinline__ void tile_counter_wait_reset(unsigned int* p, unsigned int target) {
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(p) < target) {
+    __nanosleep(64);
+    if (++spins > (1u << 23)) __trap();
+  }
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(0u) : "memory");
+  fence_proxy_async_all();
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -152,6 +186,21 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// wait until at most `n` of the most recent store groups of this thread are still in flight (their global writes
+// included); the instruction takes an immediate, hence the switch (n > 8 waits for 8)
+__device__ __forceinline__ void tma_store_wait_pending(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.bulk.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.bulk.wait_group 6;" ::: "memory"); break;
+    case 7: asm volatile("cp.async.bulk.wait_group 7;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group 8;" ::: "memory"); break;
+  }
 }
 // at most the most recent store group may still be reading its shared-memory source
 __device__ __forceinline__ void tma_store_wait_read1() {

@@ -114,6 +114,7 @@ class ClipEngine:
         self.op_bytes: Dict[str, float] = {}
         self.op_sig: Dict[str, str] = {}
         self.fused_shortcuts: List[str] = []   # branch1 convs computed inside their block's last conv
+        self.chained: List[tuple] = []  # (last conv of a block, first conv of the next) run as chained launches
         self.fused_blocks: List[str] = []      # identity blocks that run as one fused a-b-c launch
         self.crop = spec.crop
         if self.crop % 16:
@@ -316,7 +317,10 @@ class ClipEngine:
             return None
 
     def _conv(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act] = None, relu: Optional[bool] = None,
-              reverse: bool = False):
+              reverse: bool = False, chain: Optional[dict] = None):
+        """Plans one conv launch and appends it to the trunk.  `chain` (tile-granular chaining, _chain_kwargs):
+        ConvPlan keywords tile_signal / tile_wait; the launch is then returned instead of appended (the caller
+        emits producer and consumer as one trunk op)."""
         if x.c_real != cs.cin:
             raise VsbError(f"{cs.key}: input has {x.c_real} channels, conv expects {cs.cin}")
         sig = self._sig(cs, x, out, residual)
@@ -324,10 +328,15 @@ class ClipEngine:
         tune = {k: v for k, v in self._tune(cs.key, sig).items() if k in _PLAN_KNOBS}
         rev_flag = 128 if (reverse and self.alternate and self.dtype == VSB_BF16) else 0   # VSB_PLAN_REVERSE
         tune["flags"] = int(tune.get("flags", 0)) | rev_flag
+        if chain:
+            tune = self._chain_tune(tune, rev_flag)
+            tune.update(chain)
         relu = cs.relu if relu is None else relu
         wt = self._tensor(cs.key + ".weight")
-        plan = self._window_plan(cs, x, out, residual, relu, wt, rev_flag=rev_flag)
+        plan = self._window_plan(cs, x, out, residual, relu, wt, rev_flag=rev_flag) if not chain else None
         j = self._group_factor(cs, x, out, residual) if plan is None else 0
+        if chain and j > 1:
+            raise VsbError(f"{cs.key}: tile chaining is for ungrouped layers")
         bn = tune.get("block_n", 0)
         if bn and ((max(j, 1) * out.c) % bn or bn > max(j, 1) * out.c):
             tune.pop("block_n")     # a table / "*" entry that does not fit this layer: automatic
@@ -356,9 +365,23 @@ class ClipEngine:
         m = out.pixels
         es = 2 if self.dtype == VSB_BF16 else 4
         self.op_bytes[cs.key] = es * (x.pixels * x.c + m * out.c * (2 if residual is not None else 1))
-        self.trunk_ops.append((cs.key, plan.run, float(m) * cs.flops_per_out_pixel))
+        op = (cs.key, plan.run, float(m) * cs.flops_per_out_pixel)
+        if chain:
+            return op, plan
+        self.trunk_ops.append(op)
 
-    def _conv_with_shortcut(self, c: ConvSpec, b: Act, br: ConvSpec, x: Act, out: Act, reverse: bool = False) -> bool:
+    @staticmethod
+    def _chain_tune(tune: dict, rev_flag: int) -> dict:
+        """Plan knobs of a chained launch: the one-SM kernel, column blocks of at most 128 channels (two CTAs of
+        different kernels share the 512 TMEM columns of an SM)."""
+        t = {k: v for k, v in tune.items() if k in ("stages", "epi_n", "epi_bufs")}
+        t["flags"] = rev_flag | 32 | (int(tune.get("flags", 0)) & 1)   # VSB_PLAN_ONE_SM, keep STREAM_WEIGHTS
+        if tune.get("block_n", 0) and tune["block_n"] <= 128:
+            t["block_n"] = tune["block_n"]
+        return t
+
+    def _conv_with_shortcut(self, c: ConvSpec, b: Act, br: ConvSpec, x: Act, out: Act, reverse: bool = False,
+                            chain: Optional[dict] = None):
         """relu(BN1(branch1(x)) + BN_c(c(b)))  (resnet_helper.py:352-358) as ONE launch: the strided 1x1x1
         projection shortcut is a second K segment of the block's last conv (vsb_conv_desc.in2), so its
         [M, 4*dim_inner] result is never written to HBM and never re-read as a residual.  Both frozen
@@ -369,10 +392,22 @@ class ClipEngine:
             return False
         if tuple(c.kernel) != (1, 1, 1) or tuple(br.kernel) != (1, 1, 1) or tuple(c.stride) != (1, 1, 1) or br.stride[0] != 1:
             return False
-        if b.c % 64 or b.pitch != b.c or b.c_off or x.c_off or x.c_real != br.cin or x.c < 64 or out.c % 16:
+        if b.pitch != b.c or b.c_off or x.c_off or x.c_real != br.cin or out.c % 16:
             return False
         kchunk = 64
-        k2 = round_up(x.c, kchunk)
+        # Thin layers (the Fast pathway: 8 .. 32 bottleneck channels) are restated on J-pixel groups like the
+        # single convs (weights.group_conv_weight): J * b.c = 64 channels = one K chunk; the strided shortcut
+        # reads groups of J * stride_w block-input pixels (zero weights on the pixels the stride skips).
+        j, sw = 1, br.stride[2]
+        if b.c % 64 or x.c < 64:
+            dense = lambda a: a.pitch == a.c and a.c_off == 0
+            j = 64 // b.c if b.c and 64 % b.c == 0 else 0
+            if (j < 2 or self._tune(c.key).get("fuse_shortcut_grouped", True) is False
+                    or not (dense(b) and dense(x) and dense(out)) or j * out.c > 256
+                    or out.w % j or x.w % (j * sw) or out.w // j != x.w // (j * sw) or b.w != out.w):
+                return False
+        g = j * sw
+        k2 = round_up(g * x.c if j > 1 else x.c, kchunk)
 
         def make():
             s_c, b_c = self._affine(c, out.c)
@@ -382,20 +417,44 @@ class ClipEngine:
             safe = torch.where(s == 0, torch.ones_like(s), s)
             r_c = torch.where(s == 0, torch.zeros_like(s), s_c / safe)
             r_1 = torch.where(s == 0, torch.zeros_like(s), s_1 / safe)
-            w_c = pack_conv_weight(self._tensor(c.key + ".weight"), b.c, out.c, torch.float32).reshape(out.c, b.c)
-            w_1 = pack_conv_weight(self._tensor(br.key + ".weight"), k2, out.c, torch.float32).reshape(out.c, k2)
-            w = torch.cat([w_c * r_c[:, None], w_1 * r_1[:, None]], dim=1).to(self.tdt)
-            return self._up(w), self._up(s), self._up(b_c + b_1)
-        w, s, b_sum = self._memo((c.key, "dual", b.c, k2, out.c), make)
+            if j == 1:
+                w_c = pack_conv_weight(self._tensor(c.key + ".weight"), b.c, out.c, torch.float32).reshape(out.c, b.c)
+                w_1 = pack_conv_weight(self._tensor(br.key + ".weight"), k2, out.c, torch.float32).reshape(out.c, k2)
+                w = torch.cat([w_c * r_c[:, None], w_1 * r_1[:, None]], dim=1).to(self.tdt)
+                return self._up(w), self._up(s), self._up(b_c + b_1)
+            w_c, ngt_c, plo_c = group_conv_weight(self._tensor(c.key + ".weight"), b.c, out.c, j, 1, 0, torch.float32)
+            w_1, ngt_1, plo_1 = group_conv_weight(self._tensor(br.key + ".weight"), x.c, out.c, j, sw, 0, torch.float32)
+            if ngt_c != 1 or ngt_1 != 1 or plo_c or plo_1:
+                return None
+            w_c = w_c.reshape(j * out.c, j * b.c) * r_c.repeat(j)[:, None]
+            w_1 = torch.nn.functional.pad(w_1.reshape(j * out.c, g * x.c), (0, k2 - g * x.c)) * r_1.repeat(j)[:, None]
+            w = torch.cat([w_c, w_1], dim=1).to(self.tdt)
+            return self._up(w), self._up(s.repeat(j)), self._up((b_c + b_1).repeat(j))
+        made = self._memo((c.key, "dual", b.c, k2, out.c, j), make)
+        if made is None:
+            return False
+        w, s, b_sum = made
         sig = self._sig(c, b, out, None, x)
         self.op_sig[c.key] = sig
         tune = {k: v for k, v in self._tune(c.key, sig).items() if k in _PLAN_KNOBS and k != "kchunk"}
-        if tune.get("block_n", 0) and (out.c % tune["block_n"] or tune["block_n"] > out.c):
+        if tune.get("block_n", 0) and ((j * out.c) % tune["block_n"] or tune["block_n"] > j * out.c):
             tune.pop("block_n")
         tune["flags"] = int(tune.get("flags", 0)) | (128 if (reverse and self.alternate) else 0)
+        if chain:
+            if j > 1:
+                return False
+            tune = self._chain_tune(tune, 128 if (reverse and self.alternate) else 0)
+            tune.update(chain)
+        if j == 1:
+            bg, xg, og, stride2 = b, x, out, br.stride
+        else:
+            bg = Act(b.buf, b.n, b.t, b.h, b.w // j, j * b.c, j * b.c)
+            xg = Act(x.buf, x.n, x.t, x.h, x.w // g, g * x.c, g * x.c)
+            og = Act(out.buf, out.n, out.t, out.h, out.w // j, j * out.c, j * out.c)
+            stride2 = (br.stride[0], br.stride[1], 1)
         try:
-            plan = ConvPlan(self.dtype, b, w, out.c, c.kernel, c.stride, c.pad, None, s, b_sum, out, None, True,
-                            kchunk=kchunk, x2=x, stride2=br.stride, **tune)
+            plan = ConvPlan(self.dtype, bg, w, og.c, c.kernel, c.stride, c.pad, None, s, b_sum, og, None, True,
+                            kchunk=kchunk, x2=xg, stride2=stride2, **tune)
         except VsbError:
             if self._tune(c.key).get("fuse_shortcut") is True:
                 raise
@@ -403,8 +462,11 @@ class ClipEngine:
         self._keep.append(plan)
         m = out.pixels
         self.op_bytes[c.key] = 2 * (b.pixels * b.c + m * x.c + m * out.c)
-        self.trunk_ops.append((c.key, plan.run, float(m) * (c.flops_per_out_pixel + br.flops_per_out_pixel)))
+        op = (c.key, plan.run, float(m) * (c.flops_per_out_pixel + br.flops_per_out_pixel))
         self.fused_shortcuts.append(br.key)
+        if chain:
+            return op, plan
+        self.trunk_ops.append(op)
         return True
 
     def _stem(self, p: int, x: Act) -> Act:
@@ -488,7 +550,9 @@ class ClipEngine:
         # opt-in (tune fuse_block / VSB_FUSE_BLOCK=1): measured on B200 the fused launch is at parity with the three
         # launches on the thin Fast pathway (it is bound by the TMA unit and the single MMA-issuing thread, not by HBM)
         # and, owning the whole SM, it no longer overlaps the Slow pathway's kernels: 11.53 vs 11.39 ms per step
-        if str(tn.get("fuse_block", os.environ.get("VSB_FUSE_BLOCK", "0"))) not in ("1", "True"):
+        env = os.environ.get("VSB_FUSE_BLOCK", "0")   # "1" = every eligible block, or a list of block-name prefixes
+        env_on = env == "1" or any(blk.prefix.startswith(pre) for pre in env.split(",") if len(pre) > 1)
+        if str(tn.get("fuse_block", "1" if env_on else "0")) not in ("1", "True"):
             return None
         a, b, c = blk.a, blk.b, blk.c
         if (tuple(a.kernel[1:]) != (1, 1) or a.kernel[0] not in (1, 3) or tuple(b.kernel) != (1, 3, 3)
@@ -538,27 +602,69 @@ class ClipEngine:
         self._free(x)
         return y
 
-    def _block(self, x: Act, blk: BlockSpec, out_pitch: Optional[int]) -> Act:
+    def _chain_ok(self, blk: BlockSpec, nxt: Optional[BlockSpec], out_pitch: Optional[int]) -> bool:
+        """Tile-granular chaining of this block's last conv with the next block's first (vsb_conv_desc.tile_signal /
+        tile_wait): the next `a` must be a 1x1x1 stride-1 conv of at most 128 stored channels over this block's
+        dense output.  Opt-in (VSB_CHAIN=1 / tune {"*": {"chain": True}}): measured on B200 the chained pairs
+        lose to two full-width launches (12.1 vs 11.2 ms per SF50 batch-64 step, profiles/r02_ab_knobs.txt):
+        the consumer's CTAs take shared memory and TMEM from the producer, and the tile it waits for is
+        ~3000 clk of store latency away, so the SM slots it owns mostly spin."""
+        if nxt is None or self.dtype != VSB_BF16 or blk.nonlocal_ is not None or out_pitch is not None:
+            return False
+        if str(self._tune(blk.prefix).get("chain", os.environ.get("VSB_CHAIN", "0"))) not in ("1", "True"):
+            return False
+        a = nxt.a
+        if tuple(a.kernel) != (1, 1, 1) or tuple(a.stride) != (1, 1, 1) or tuple(a.pad) != (0, 0, 0):
+            return False
+        if tuple(blk.c.kernel) != (1, 1, 1) or tuple(blk.c.stride) != (1, 1, 1):
+            return False
+        # pixel-grouped (thin) layers stay on their own plans: _group_factor groups inputs below 64 channels
+        return (self._store(a.cout) <= 128 and self._store(a.cout) >= 64 and self._store(blk.c.cin) >= 64
+                and self._store(blk.c.cout) >= 64 and self._store(blk.c.cout) % 128 == 0)
+
+    def _block(self, x: Act, blk: BlockSpec, out_pitch: Optional[int], nxt: Optional[BlockSpec] = None,
+               a_pre: Optional[Act] = None) -> Tuple[Act, Optional[Act]]:
+        """One ResBlock.  Returns (block output, a_next): a_next is the output of the NEXT block's conv `a` when
+        it was chained to this block's last conv (then the next call gets it as a_pre and skips its own `a`)."""
         n = x.n
         pw = self._pools.index(self._pool)
         d = self._rev[pw]              # a and c walk in direction d, b against it; the next block flips
         self._rev[pw] = not d
-        fused = self._fused_block(x, blk, out_pitch)
-        if fused is not None:
-            return fused
-        ta, ha, wa = self._out_dims(x, blk.a)
-        a = self._alloc(n, ta, ha, wa, blk.a.cout)
-        self._conv(blk.a, x, a, reverse=d)
+        if a_pre is None:
+            fused = self._fused_block(x, blk, out_pitch)
+            if fused is not None:
+                return fused, None
+            ta, ha, wa = self._out_dims(x, blk.a)
+            a = self._alloc(n, ta, ha, wa, blk.a.cout)
+            self._conv(blk.a, x, a, reverse=d)
+        else:
+            a = a_pre
         tb, hb, wb = self._out_dims(a, blk.b)
         b = self._alloc(n, tb, hb, wb, blk.b.cout)
         self._conv(blk.b, a, b, reverse=not d)
         self._free(a)
+        # chained pair: the next block's `a` runs next to this block's `c`, tile by tile (its buffer is taken
+        # BEFORE b is released: it is written while c still reads b)
+        chain_on = self._chain_ok(blk, nxt, out_pitch)
+        flags = a_next = None
+        if chain_on:
+            flags = torch.zeros((n * tb * hb * wb + 127) // 128, dtype=torch.int32, device=self.device)
+            a_next = self._alloc(n, tb, hb, wb, nxt.a.cout)
+        # CTA slots (two per SM) are split between producer and consumer: the producer moves ~2x the bytes
+        slots = 2 * torch.cuda.get_device_properties(self.device).multi_processor_count
+        share = float(self._tune(blk.prefix).get("chain_share", os.environ.get("VSB_CHAIN_SHARE", "0.72")))
+        g_c = max(8, int(slots * share) // 8 * 8)
+        chain = {"tile_signal": flags, "grid_limit": g_c} if chain_on else None
         sc = None
         y = None
+        c_op = None
         if blk.branch1 is not None:
             y = self._alloc(n, tb, hb, wb, blk.c.cout, pitch=out_pitch)
-            if self._conv_with_shortcut(blk.c, b, blk.branch1, x, y, reverse=d):
+            r = self._conv_with_shortcut(blk.c, b, blk.branch1, x, y, reverse=d, chain=chain)
+            if r:
                 res = None
+                if chain_on:
+                    c_op = r
             else:
                 self._free(y)
                 y = None
@@ -571,12 +677,25 @@ class ClipEngine:
             y = self._alloc(n, tb, hb, wb, blk.c.cout, pitch=out_pitch)
         # relu(shortcut + BN(c(.)))   resnet_helper.py:352-358
         if res is not None:
-            self._conv(blk.c, b, y, residual=res, relu=True, reverse=d)
+            r = self._conv(blk.c, b, y, residual=res, relu=True, reverse=d, chain=chain)
+            if chain_on:
+                c_op = r
+        if chain_on:
+            (c_name, c_run, c_flops), c_plan = c_op
+            count = 8 * (self._store(blk.c.cout) // c_plan.info()["block_n"])
+            (a_name, a_run, a_flops), _ = self._conv(nxt.a, y, a_next, reverse=d,
+                                                     chain={"tile_wait": flags, "tile_wait_count": count,
+                                                            "grid_limit": slots - c_plan.info()["grid"]})
+            # one trunk op: the consumer must directly follow its producer on the stream (it consumes the tile
+            # counters the producer raises and resets them)
+            self.op_bytes[c_name + "+" + a_name] = self.op_bytes[c_name] + self.op_bytes[a_name]
+            self.trunk_ops.append((c_name + "+" + a_name, lambda: (c_run(), a_run()), c_flops + a_flops))
+            self.chained.append((c_name, a_name, c_run, a_run, c_plan))
         self._free(b)
         if sc is not None:
             self._free(sc)
         self._free(x)
-        return y
+        return y, a_next
 
     def _nonlocal(self, x: Act, nl: NonlocalSpec, out_pitch: Optional[int]) -> Act:
         n = x.n
@@ -662,9 +781,11 @@ class ClipEngine:
         return True
 
     def _stage(self, x: Act, blocks: List[BlockSpec], out_pitch: Optional[int]) -> Act:
+        a_pre = None
         for i, blk in enumerate(blocks):
             last = i == len(blocks) - 1
-            x = self._block(x, blk, out_pitch if (last and blk.nonlocal_ is None) else None)
+            x, a_pre = self._block(x, blk, out_pitch if (last and blk.nonlocal_ is None) else None,
+                                   nxt=None if last else blocks[i + 1], a_pre=a_pre)
             if blk.nonlocal_ is not None:
                 x = self._nonlocal(x, blk.nonlocal_, out_pitch if last else None)
         return x

@@ -48,6 +48,8 @@ class ConvDesc(C.Structure):
         ("t2", C.c_int), ("h2", C.c_int), ("w2", C.c_int), ("cin2", C.c_int), ("in2_pitch", C.c_int),
         ("st2", C.c_int), ("sh2", C.c_int), ("sw2", C.c_int),
         ("epi_n", C.c_int), ("epi_bufs", C.c_int), ("flags", C.c_int), ("out_f16", C.c_int), ("wgt_clip_rows", C.c_int),
+        ("tile_signal", C.c_void_p), ("tile_wait", C.c_void_p), ("tile_wait_count", C.c_int),
+        ("grid_limit", C.c_int),
     ]
 
 
@@ -129,8 +131,8 @@ def load() -> C.CDLL:
                  "vsb_debug_umma_semantics", "vsb_debug_umma_rate", "vsb_debug_umma_rate2", "vsb_debug_conv_stats", "vsb_debug_conv_plan_info",
                  "vsb_debug_bottleneck_stats", "vsb_debug_tma_rate"):
         getattr(lib, name).restype = i
-    if lib.vsb_abi_version() != 5:
-        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 5")
+    if lib.vsb_abi_version() != 6:
+        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 6")
     _lib = lib
     return lib
 

@@ -68,9 +68,10 @@ class ConvPlan:
                  relu: bool = False, block_n: int = 0, kchunk: int = 0, stages: int = 0, algo: int = 0,
                  kw_ranges: Optional[Sequence[Sequence[int]]] = None, x2: Optional[Act] = None,
                  stride2: Sequence[int] = (1, 1, 1), epi_n: int = 0, epi_bufs: int = 0, flags: int = 0, out_f16: bool = False,
-                 wgt_clip_rows: int = 0):
+                 wgt_clip_rows: int = 0, tile_signal: Optional[torch.Tensor] = None,
+                 tile_wait: Optional[torch.Tensor] = None, tile_wait_count: int = 0, grid_limit: int = 0):
         _require_cuda(x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None,
-                      x2.buf if x2 is not None else None)
+                      x2.buf if x2 is not None else None, tile_signal, tile_wait)
         pad_hi = pad_lo if pad_hi is None else pad_hi
         d = ConvDesc()
         d.dtype = dtype
@@ -94,6 +95,14 @@ class ConvPlan:
         d.epi_n, d.epi_bufs, d.flags = epi_n, epi_bufs, flags
         d.out_f16 = int(out_f16)
         d.wgt_clip_rows = int(wgt_clip_rows)
+        # tile-granular chaining with the next / previous launch (vsb_conv_desc.tile_signal / tile_wait)
+        for t in (tile_signal, tile_wait):
+            if t is not None and (t.dtype != torch.int32 or t.numel() * 128 < out.pixels):
+                raise VsbError("tile counters: one int32 per 128 output rows")
+        d.tile_signal = tile_signal.data_ptr() if tile_signal is not None else None
+        d.tile_wait = tile_wait.data_ptr() if tile_wait is not None else None
+        d.tile_wait_count = int(tile_wait_count)
+        d.grid_limit = int(grid_limit)
         k_per_tap_row = x.c * d.kw
         if kw_ranges is not None:
             if len(kw_ranges) != d.kw or d.kw > 8:
@@ -123,7 +132,7 @@ class ConvPlan:
         elif wgt.numel() != cout * (d.kt * d.kh * k_per_tap_row + k2):
             raise VsbError(f"packed weight has {wgt.numel()} elements, expected {cout}x({d.kt * d.kh}x{k_per_tap_row}+{k2})")
         self._keep = (x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None,
-                      x2.buf if x2 is not None else None)
+                      x2.buf if x2 is not None else None, tile_signal, tile_wait)
         self._h = C.c_void_p()
         self._lib = _l.load()
         check(self._lib.vsb_conv3d_plan_create(C.byref(d), C.byref(self._h)), "vsb_conv3d_plan_create")
