@@ -410,7 +410,7 @@ def main():
                        f"synthetic event clips ({t_frames}x224x224) per GPU", "clips_per_gpu_per_step": B, "model": args.model,
                        "weights": "random-init (seed 0) + seeded BatchNorm statistics",
                        "l2": "inputs larger than L2: 2 alternating 308 MB uint8 frame batches per GPU, "
-                             "activations >> 126 MB", "cuda_graph": True, "pack_overlap": nslots > 1,
+                             "activations >> 126 MB", "cuda_graph": True, "replay": ("clip program: one vsb_program_run per step (C ABI v7, graph captured inside the library)" if eng._use_program() else "torch CUDA graph of the Python launch loop"), "pack_overlap": nslots > 1,
                        "parallelism": f"clip-sharded x{world}, features all-gathered each step" if world > 1 else "single GPU",
                        "host_placement": {"rank0_cpus": (f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else None),
                                           "numa_nodes": nodes}},

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VSB_ABI_VERSION 6
+#define VSB_ABI_VERSION 7
 
 typedef enum vsb_status {
   VSB_OK = 0,
@@ -277,6 +277,71 @@ int vsb_nthwc_to_ncthw_f32(const void* in, int n, int thw, int c, int in_pitch, 
  * pixel offset x_off of output rows of out_w pixels (see vsb_pack_frames).    */
 int vsb_ncthw_f32_to_nthwc(const float* in, int n, int c, long long thw, int w, void* out, int c_pad, int out_w,
                            int x_off, int dtype, void* stream);
+
+/* ------------------------------------------------------------- clip programs (ABI v7)
+ * The model-level entry points: ONE handle for the whole forward of SFBase.forward_encoder (+ proj_head) at a
+ * fixed batch size (vidsitu_code/mdl_sf_base.py:182-216; SlowFast.forward, SlowFast/slowfast/models/
+ * video_model_builder.py:383-396), i.e. the create / workspace_bytes / forward triple a non-Python host binds.
+ *
+ *   build   vsb_program_create, then one vsb_program_add_* per launch IN PROGRAM ORDER.  Every add mirrors the
+ *           per-op entry point above with (stream) replaced by (lane, name): lane 0 = the caller's stream (Slow
+ *           pathway, head), lane 1 = the program's own side stream (Fast pathway and the lateral convs, which
+ *           video_model_builder.py:124-131 makes the only meeting points); vsb_program_add_sync(from, to) makes
+ *           lane `to` wait for everything lane `from` has been given so far.  A program that uses lane 1 must
+ *           fork (sync 0 -> 1) before its first lane-1 op and join (sync 1 -> 0) after its last.
+ *           Conv / bottleneck plans are borrowed: they must outlive the program.
+ *           (vidsitu_b200/engine.py::ClipEngine.build_program is the planner that emits these calls.)
+ *   run     vsb_program_run: the whole forward, one call.  vsb_program_capture first runs the program once
+ *           eagerly, then records it into a CUDA graph that every later vsb_program_run replays.
+ *   save    vsb_program_add_region names the device allocations the ops point into - CONST regions (packed
+ *           weights, folded BatchNorm scale / bias: contents are saved) and SCRATCH regions (activations, inputs,
+ *           outputs: size only, zero-filled at load) - and vsb_program_save writes a relocatable file.
+ *   load    vsb_program_load rebuilds the program in any process: regions are laid out 1 KiB-aligned in
+ *           `device_mem` (vsb_program_file_device_bytes bytes; NULL = the library allocates and owns it), constants
+ *           are uploaded, plans and TMA descriptors re-created for the new addresses.  vsb_program_region
+ *           returns where a named region lives ("frames": uint8 [n, t, h, w, 3] input; "feats": fp32 [n, D];
+ *           "logits": fp32 [n, V] when the program has a projection head): the host copies frames in, calls
+ *           vsb_program_run, copies features out.  See INTEGRATION.md for a complete C host.                 */
+typedef struct vsb_program vsb_program;
+#define VSB_REGION_CONST 0
+#define VSB_REGION_SCRATCH 1
+
+int vsb_program_create(vsb_program** prog);
+void vsb_program_destroy(vsb_program* prog);
+int vsb_program_add_region(vsb_program* prog, const char* name, void* ptr, unsigned long long bytes, int kind);
+int vsb_program_region(const vsb_program* prog, const char* name, void** ptr, unsigned long long* bytes);
+int vsb_program_num_ops(const vsb_program* prog);       /* launches + syncs */
+int vsb_program_num_launches(const vsb_program* prog);  /* kernels per vsb_program_run */
+unsigned long long vsb_program_device_bytes(const vsb_program* prog); /* sum of the registered regions, 1 KiB-aligned */
+
+int vsb_program_add_conv(vsb_program* prog, const vsb_conv_plan* plan, int lane, const char* name);
+int vsb_program_add_bottleneck(vsb_program* prog, const vsb_bottleneck_plan* plan, const vsb_bottleneck_desc* desc,
+                               int lane, const char* name);
+int vsb_program_add_pack_frames(vsb_program* prog, const uint8_t* frames, int n, int t_in, int h, int w, const int* idx,
+                                int t_out, const float* mean3, const float* std3, int reverse_channels, void* out,
+                                int c_pad, int out_w, int x_off, int dtype, int lane, const char* name);
+int vsb_program_add_maxpool3d(vsb_program* prog, const void* in, int n, int t, int h, int w, int c, int in_pitch,
+                              void* out, int out_pitch, int c_out, int kt, int kh, int kw, int st, int sh, int sw,
+                              int pt, int ph, int pw, int dtype, int lane, const char* name);
+int vsb_program_add_global_avgpool(vsb_program* prog, const void* in, int n, int thw, int c, int in_pitch, float* feats,
+                                   int feat_pitch, int feat_off, int dtype, int lane, const char* name);
+int vsb_program_add_linear(vsb_program* prog, const float* x, int n, int din, const float* w, const float* b, float* y,
+                           int dout, int relu, int lane, const char* name);
+int vsb_program_add_nonlocal_attention(vsb_program* prog, const void* theta, int theta_pitch, const void* phi,
+                                       int phi_pitch, const void* g, int g_pitch, void* out, int out_pitch, int n,
+                                       int tq, int tk, int c, int softmax, int dtype, int lane, const char* name);
+int vsb_program_add_score_rows(vsb_program* prog, void* scores, long long rows, int valid, int width, int pitch,
+                               int softmax, int lane, const char* name);
+int vsb_program_add_transpose_pad(vsb_program* prog, const void* in, int in_pitch, void* out, int n, int rows, int cols,
+                                  int out_pitch, int lane, const char* name);
+int vsb_program_add_sync(vsb_program* prog, int from_lane, int to_lane);
+
+int vsb_program_run(vsb_program* prog, void* stream);
+int vsb_program_capture(vsb_program* prog, void* stream);
+
+int vsb_program_save(const vsb_program* prog, const char* path);
+int vsb_program_file_device_bytes(const char* path, unsigned long long* bytes);
+int vsb_program_load(const char* path, void* device_mem, unsigned long long device_bytes, vsb_program** prog);
 
 #ifdef __cplusplus
 }

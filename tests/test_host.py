@@ -19,7 +19,7 @@ from vidsitu_b200.weights import fold_bn, pack_conv_weight, stem_quad_weight
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = L.load()
-    assert lib.vsb_abi_version() == 6
+    assert lib.vsb_abi_version() == 7
     declared = set()
     for hdr in ("vidsitu_b200.h", "vidsitu_b200_debug.h"):
         src = open(os.path.join(ROOT, "include", hdr)).read()
@@ -326,3 +326,28 @@ def test_loading_weights_through_sf_mdl_invalidates_prepared_engines():
     model._prep[("bf16", "cuda:0")] = {"stale": 1}
     model.sf_mdl.float()
     assert not model._prep
+
+
+def test_program_handle_host_side_behaviour(tmp_path):
+    """Clip programs (C ABI v7): the parts that need no GPU - create / destroy, counters, error reporting of the
+    region lookup and of the file reader (a non-program file is refused with a message, never crashes)."""
+    import ctypes as C
+    lib = L.load()
+    h = C.c_void_p()
+    assert lib.vsb_program_create(C.byref(h)) == 0 and h.value
+    assert lib.vsb_program_num_ops(h) == 0 and lib.vsb_program_num_launches(h) == 0
+    assert lib.vsb_program_device_bytes(h) == 0
+    ptr, nbytes = C.c_void_p(), C.c_ulonglong()
+    assert lib.vsb_program_region(h, b"feats", C.byref(ptr), C.byref(nbytes)) != 0
+    assert b"no region 'feats'" in lib.vsb_last_error()
+    assert lib.vsb_program_add_region(h, b"x", None, 16, 0) != 0          # null pointer
+    assert lib.vsb_program_add_sync(h, 0, 0) != 0                         # a sync joins two different lanes
+    assert lib.vsb_program_add_maxpool3d(h, None, 1, 1, 1, 1, 1, 1, None, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 2, b"p") != 0
+    assert b"lane" in lib.vsb_last_error()
+    lib.vsb_program_destroy(h)
+    bad = tmp_path / "bad.vsbprog"
+    bad.write_bytes(b"not a program" * 10)
+    assert lib.vsb_program_file_device_bytes(str(bad).encode(), C.byref(nbytes)) != 0
+    assert b"not a vidsitu_b200 program file" in lib.vsb_last_error()
+    out = C.c_void_p()
+    assert lib.vsb_program_load(str(tmp_path / "missing").encode(), None, 0, C.byref(out)) != 0 and not out.value

@@ -53,6 +53,7 @@ class _Pool:
         self.device = device
         self.dtype = elem_dtype
         self.free: List[torch.Tensor] = []
+        self.all: List[torch.Tensor] = []     # every buffer ever handed out (scratch regions of a saved program)
         self.total_bytes = 0
 
     def take(self, numel: int) -> torch.Tensor:
@@ -64,10 +65,30 @@ class _Pool:
             return self.free.pop(best)
         buf = torch.empty(numel, dtype=self.dtype, device=self.device)
         self.total_bytes += buf.numel() * buf.element_size()
+        self.all.append(buf)
         return buf
 
     def give(self, buf: torch.Tensor) -> None:
         self.free.append(buf)
+
+
+class _SlotLaunch:
+    """The stem conv of one pathway: one plan per input slot (the slots differ only in the input buffer), the
+    launch runs the plan of the slot selected at launch / capture / program-build time."""
+
+    def __init__(self, engine: "ClipEngine", plans: List[ConvPlan]):
+        self.engine = engine
+        self.plans = plans
+
+    def __call__(self) -> None:
+        self.plans[self.engine._slot].run()
+
+    def emit(self, prog, lane: int, name: str) -> None:
+        self.plans[self.engine._slot].emit(prog, lane, name)
+
+    @property
+    def _keep(self):
+        return self.plans[self.engine._slot]._keep
 
 
 class ClipEngine:
@@ -96,6 +117,11 @@ class ClipEngine:
         self._pools = [_Pool(self.device, self.tdt) for _ in range(max(1, spec.num_pathways))]
         self._pool = self._pools[0]
         self._graph = None
+        self._programs = None      # one captured clip program per input slot (replay through the C ABI)
+        self.frames_in = None      # static uint8 frame buffer of an exported program
+        # replay path: "program" = ONE C call per forward (vsb_program_run on a CUDA graph captured inside the
+        # library), "torch" = a torch.cuda.CUDAGraph of the Python launch loop
+        self.replay_mode = str(self.tune.get("*", {}).get("replay", os.environ.get("VSB_REPLAY", "program")))
         self._main_stream = None
         self.two_streams = (spec.num_pathways == 2 and dtype == VSB_BF16
                             and str(self.tune.get("*", {}).get("streams", os.environ.get("VSB_STREAMS", "2"))) == "2")
@@ -149,7 +175,7 @@ class ClipEngine:
         off = 0
         for p, x in enumerate(self.trunk_out):
             self.head_ops.append((f"head.pathway{p}_avgpool",
-                                  (lambda x=x, off=off: ops.global_avgpool(x, self.feats, off, self.dtype)), 0.0))
+                                  ops.global_avgpool_call(x, self.feats, off, self.dtype), 0.0))
             off += x.c_real
         self.logits = None
         if proj_head is not None:
@@ -158,9 +184,9 @@ class ClipEngine:
             self._keep += [w0, b0, w1, b1]
             self.hidden = torch.zeros((self.n, w0.shape[0]), dtype=torch.float32, device=self.device)
             self.logits = torch.zeros((self.n, w1.shape[0]), dtype=torch.float32, device=self.device)
-            self.head_ops.append(("proj_head.0", lambda: ops.linear(self.feats, w0, b0, self.hidden, True),
+            self.head_ops.append(("proj_head.0", ops.linear_call(self.feats, w0, b0, self.hidden, True),
                                   2.0 * self.n * w0.numel()))
-            self.head_ops.append(("proj_head.2", lambda: ops.linear(self.hidden, w1, b1, self.logits, False),
+            self.head_ops.append(("proj_head.2", ops.linear_call(self.hidden, w1, b1, self.logits, False),
                                   2.0 * self.n * w1.numel()))
         self._t = None  # drop the reference-layout tensors
 
@@ -267,8 +293,13 @@ class ClipEngine:
         tn = self._tune(cs.key, self._sig(cs, x, out, residual))
         if self.dtype != VSB_BF16 or tn.get("algo", "auto") == "im2col":
             return None
-        if cs.kernel[1] * cs.kernel[2] == 1 or cs.stride[0] != 1 or x.h < 14:
+        if cs.stride[0] != 1 or x.h < 14:
             return None
+        if cs.kernel[1] * cs.kernel[2] == 1:
+            # kt x 1 x 1 (the Fast pathway's temporal `a` convs): the ring of frame windows reads every input frame
+            # once, the im2col kernel once per temporal tap (through L2).  VSB_WIN_TEMPORAL=1 / tune win_temporal
+            if cs.kernel[0] == 1 or str(tn.get("win_temporal", os.environ.get("VSB_WIN_TEMPORAL", "0"))) not in ("1", "True"):
+                return None
         dense = lambda a: a is None or (a.pitch == a.c and a.c_off == 0)
         sw = cs.stride[2]
         if j is None:
@@ -481,7 +512,7 @@ class ClipEngine:
         self._keep += plans
         es = 2 if self.dtype == VSB_BF16 else 4
         self.op_bytes[cs.key] = es * (x.pixels * 4 + y.pixels * cs.cout)
-        self.trunk_ops.append((cs.key, lambda: plans[self._slot].run(), float(y.pixels) * cs.flops_per_out_pixel))
+        self.trunk_ops.append((cs.key, _SlotLaunch(self, plans), float(y.pixels) * cs.flops_per_out_pixel))
         return y
 
     def _stem_plan(self, cs: ConvSpec, x: Act, y: Act, to: int, ho: int, wo: int) -> ConvPlan:
@@ -536,7 +567,7 @@ class ClipEngine:
         y = self._alloc(x.n, to, ho, wo, x.c_real, pitch=pitch, min_c=min_c)
         es = 2 if self.dtype == VSB_BF16 else 4
         self.op_bytes[name] = es * (x.pixels * x.c_real + y.pixels * y.c)
-        self.trunk_ops.append((name, lambda: ops.maxpool3d(x, y, kernel, stride, pad, self.dtype), 0.0))
+        self.trunk_ops.append((name, ops.maxpool3d_call(x, y, kernel, stride, pad, self.dtype), 0.0))
         return y
 
     def _fused_block(self, x: Act, blk: BlockSpec, out_pitch: Optional[int]) -> Optional[Act]:
@@ -720,7 +751,7 @@ class ClipEngine:
         tq, tk = x.t * x.h * x.w, xp.t * xp.h * xp.w
         if not self._nonlocal_gemms(nl, theta, phi, g, att, tq, tk):
             self.trunk_ops.append((nl.prefix + ".attention",
-                                   lambda: ops.nonlocal_attention(theta, phi, g, att, nl.softmax, self.dtype),
+                                   ops.nonlocal_attention_call(theta, phi, g, att, nl.softmax, self.dtype),
                                    4.0 * n * tq * tk * nl.dim_inner))
         y = self._alloc(n, x.t, x.h, x.w, nl.dim, pitch=out_pitch)
         # x + BN(conv_out(.)), no ReLU   nonlocal_helper.py:145-148
@@ -769,10 +800,10 @@ class ClipEngine:
         run_scores, run_out = plan_s.run, plan_y.run
 
         fl = 2.0 * n * tq * tk * c
-        self.trunk_ops.append((nl.prefix + ".g_transpose", lambda: ops.transpose_pad(g, g_t, kp), 0.0))
+        self.trunk_ops.append((nl.prefix + ".g_transpose", ops.transpose_pad_call(g, g_t, kp), 0.0))
         self.trunk_ops.append((nl.prefix + ".scores", run_scores, fl))
         self.trunk_ops.append((nl.prefix + ".softmax",
-                               lambda: ops.score_rows(scores, n * tq, tk, kp, kp, nl.softmax), 0.0))
+                               ops.score_rows_call(scores, n * tq, tk, kp, kp, nl.softmax), 0.0))
         self.trunk_ops.append((nl.prefix + ".attention_out", run_out, fl))
         self._pool.give(scores)
         self._pool.give(g_t)
@@ -937,14 +968,46 @@ class ClipEngine:
         with self._guard():
             self._run()
 
-    def _run(self) -> None:
-        """One forward.  SlowFast nets run their two pathways on two streams (fork after the inputs are
-        packed, join before the projection head): the pathways only meet at the lateral convs
-        (video_model_builder.py:124-131), which wait for the slow stage they write into and are waited
-        for by the next slow stage.  Stream order inside a pathway is the program order."""
+    def _schedule(self):
+        """The forward as a sequence of ("op", lane, name, launch) and ("sync", from_lane, to_lane) items - consumed
+        by the eager / torch-graph run (_run: lanes are torch streams) and by build_program (lanes of a C clip
+        program).  SlowFast nets run their two pathways on two lanes (fork after the inputs are packed, join before
+        the projection head): the pathways only meet at the lateral convs (video_model_builder.py:124-131), which
+        wait for the slow stage they write into and are waited for by the next slow stage.  Order inside a lane
+        is the program order."""
         if not self.two_streams:
-            self.run_trunk()
-            self.run_head()
+            for name, fn, _ in self.trunk_ops + self.head_ops:
+                yield ("op", 0, name, fn)
+            return
+        yield ("sync", 0, 1)
+        prev_fuse = False
+        for name, fn, _ in self.trunk_ops:
+            sid = self._op_stream(name)
+            is_fuse = "_fuse" in name
+            if is_fuse and not self.early_lateral:
+                yield ("sync", 0, 1)          # pooled concat buffer: wait until the slow stage has made it live
+            elif sid == 0 and prev_fuse:
+                yield ("sync", 1, 0)          # the next slow stage reads the concatenated channels
+            yield ("op", sid, name, fn)
+            if sid == 0:
+                prev_fuse = False
+            elif is_fuse:
+                prev_fuse = True
+        joined = False
+        for name, fn, _ in self.head_ops:
+            if name.startswith("proj_head") and not joined:
+                yield ("sync", 1, 0)
+                joined = True
+            yield ("op", 1 if (self._op_stream(name) == 1 and not joined) else 0, name, fn)
+        if not joined:
+            yield ("sync", 1, 0)
+
+    def _run(self) -> None:
+        """One forward, launch by launch from Python (eager runs, per-op timing, torch graph capture)."""
+        if not self.two_streams:
+            for _, _, name, fn in self._schedule():
+                with self._range(name):
+                    fn()
             return
         origin = torch.cuda.current_stream()
         prio = int(self.tune.get("*", {}).get("prio", os.environ.get("VSB_STREAM_PRIO", "0")))
@@ -953,54 +1016,122 @@ class ClipEngine:
             # fills in; prio 2: the other way round; 0: Slow on the caller's stream, both default priority
             self._side_stream = torch.cuda.Stream(self.device, priority=-1 if prio == 2 else 0)
             self._main_stream = torch.cuda.Stream(self.device, priority=-1) if prio == 1 else None
-        side = self._side_stream
         main = self._main_stream if self._main_stream is not None else origin
         if main is not origin:
             main.wait_stream(origin)
-        streams = (main, side)
-
-        def sync(src: int, dst: int) -> None:
-            ev = torch.cuda.Event()
-            ev.record(streams[src])
-            streams[dst].wait_event(ev)
-
-        sync(0, 1)
-        prev_fuse = False
-        for name, fn, _ in self.trunk_ops:
-            sid = self._op_stream(name)
-            is_fuse = "_fuse" in name
-            if is_fuse and not self.early_lateral:
-                sync(0, 1)          # pooled concat buffer: wait until the slow stage has made it live
-            elif sid == 0 and prev_fuse:
-                sync(1, 0)          # the next slow stage reads the concatenated channels
-            if sid == 0:
-                with torch.cuda.stream(main), self._range(name):
-                    fn()
-                if prev_fuse:
-                    prev_fuse = False
+        streams = (main, self._side_stream)
+        for item in self._schedule():
+            if item[0] == "sync":
+                ev = torch.cuda.Event()
+                ev.record(streams[item[1]])
+                streams[item[2]].wait_event(ev)
             else:
-                with torch.cuda.stream(side), self._range(name):
+                _, lane, name, fn = item
+                with torch.cuda.stream(streams[lane]), self._range(name):
                     fn()
-                if is_fuse:
-                    prev_fuse = True
-        for name, fn, _ in self.head_ops:
-            if name.startswith("proj_head") and side is not None:
-                sync(1, 0)
-                side = None
-            if self._op_stream(name) == 1 and side is not None:
-                with torch.cuda.stream(side):
-                    fn()
-            else:
-                with torch.cuda.stream(main):
-                    fn()
-        if side is not None:
-            sync(1, 0)
         if main is not origin:
             origin.wait_stream(main)
 
-    def capture(self) -> None:
+    # ------------------------------------------------------------------ clip programs (C ABI v7)
+    @staticmethod
+    def _emit(fn, prog: "ops.Program", lane: int, name: str) -> None:
+        target = fn if hasattr(fn, "emit") else getattr(fn, "__self__", None)
+        if target is None or not hasattr(target, "emit"):
+            raise VsbError(f"{name}: this launch cannot be recorded into a clip program")
+        target.emit(prog, lane, name)
+
+    def _pack_calls(self, frames: torch.Tensor) -> List[Tuple[str, "ops.Call"]]:
+        spec = self.spec
+        idxs = [self.slow_idx, self.fast_idx] if spec.num_pathways == 2 else [self.fast_idx]
+        return [(f"pack.pathway{p}", ops.pack_frames_call(frames, idx, spec.mean, spec.std, self.inputs[p], self.dtype,
+                                                          spec.reverse_input_channel, self.x_off))
+                for p, idx in enumerate(idxs)]
+
+    def build_program(self, slot: Optional[int] = None, with_pack: bool = False) -> "ops.Program":
+        """The forward of this engine as ONE C handle (include/vidsitu_b200.h: vsb_program_*): every launch of
+        _schedule() recorded with its lane, plans borrowed from the engine.  `with_pack`: the program starts with
+        the pack launches reading the engine's static uint8 frame buffer (self.frames_in, region "frames")."""
         with self._guard():
-            self._capture()
+            prog = ops.Program()
+            keep = self._slot
+            if slot is not None:
+                self.select_slot(slot)
+            try:
+                if with_pack:
+                    if self.frames_in is None:
+                        self.frames_in = torch.zeros((self.n, self.spec.num_frames, self.crop, self.crop, 3),
+                                                     dtype=torch.uint8, device=self.device)
+                    for name, call in self._pack_calls(self.frames_in):
+                        call.emit(prog, 0, name)
+                for item in self._schedule():
+                    if item[0] == "sync":
+                        prog.sync(item[1], item[2])
+                    else:
+                        self._emit(item[3], prog, item[1], item[2])
+            finally:
+                self._slot = keep
+            prog.keep(self)
+            return prog
+
+    def export_program(self, path: str) -> "ops.Program":
+        """Save the whole forward (pack -> trunk -> head) as a relocatable program file that any host process can
+        load and run through the C ABI alone (vsb_program_load / vsb_program_region / vsb_program_run): packed
+        weights and folded BatchNorm travel as constant regions, activations as sized scratch regions; the host
+        writes uint8 frames into region "frames" and reads fp32 region "feats" (and "logits")."""
+        prog = self.build_program(slot=0, with_pack=True)
+        scratch: Dict[int, Tuple[str, torch.Tensor]] = {}
+
+        def reg(name: str, t: Optional[torch.Tensor]) -> None:
+            if t is not None:
+                scratch.setdefault(t.untyped_storage().data_ptr(), (name, t))
+
+        reg("frames", self.frames_in)
+        reg("feats", self.feats)
+        reg("logits", self.logits)
+        reg("hidden", getattr(self, "hidden", None))
+        for p, a in enumerate(self.input_sets[0]):
+            reg(f"input.pathway{p}", a.buf)
+        for i, b in enumerate(b for pool in self._pools for b in pool.all):
+            reg(f"act{i}", b)
+        for i, b in enumerate(self._dedicated):
+            reg(f"concat{i}", b)
+        consts: Dict[int, torch.Tensor] = {}
+        launches = [fn for item in self._schedule() if item[0] == "op" for fn in (item[3],)]
+        launches += [c for _, c in self._pack_calls(self.frames_in)]
+        for fn in launches:
+            owner = fn if hasattr(fn, "_keep") else getattr(fn, "__self__", None)
+            for t in getattr(owner, "_keep", ()):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    sp = t.untyped_storage().data_ptr()
+                    if sp not in scratch:
+                        consts.setdefault(sp, t)
+
+        def whole(t: torch.Tensor) -> torch.Tensor:
+            st = t.untyped_storage()
+            return torch.empty(0, dtype=torch.uint8, device=t.device).set_(st, 0, (st.nbytes(),), (1,))
+
+        for name, t in scratch.values():
+            prog.add_region(name, whole(t), ops.Program.SCRATCH)
+        for i, t in enumerate(consts.values()):
+            prog.add_region(f"const{i}", whole(t), ops.Program.CONST)
+        prog.save(path)
+        return prog
+
+    def _use_program(self) -> bool:
+        return self.replay_mode == "program" and not self.chained
+
+    def capture(self) -> None:
+        """Record the forward once for replay(): as clip programs captured inside the library (default), or as
+        torch CUDA graphs of the Python launch loop (replay_mode "torch")."""
+        with self._guard():
+            if self._use_program():
+                if self._programs is None:
+                    progs = [self.build_program(slot=i) for i in range(len(self.input_sets))]
+                    for p in progs:
+                        p.capture()
+                    self._programs = progs
+            elif self._graph is None:
+                self._capture()
 
     def _capture(self) -> None:
         """Capture trunk + head once into a CUDA graph (inputs/outputs are static buffers)."""
@@ -1021,12 +1152,14 @@ class ClipEngine:
         self._slot = keep
 
     def replay(self, slot: Optional[int] = None) -> None:
-        if self._graph is None:
-            self.capture()
         if slot is not None:
             self.select_slot(slot)
+        self.capture()
         with self._guard():
-            self._graph[self._slot].replay()
+            if self._use_program():
+                self._programs[self._slot].run()     # ONE C call: vsb_program_run
+            else:
+                self._graph[self._slot].replay()
 
     @property
     def num_launches(self) -> int:

@@ -131,8 +131,38 @@ def load() -> C.CDLL:
                  "vsb_debug_umma_semantics", "vsb_debug_umma_rate", "vsb_debug_umma_rate2", "vsb_debug_conv_stats", "vsb_debug_conv_plan_info",
                  "vsb_debug_bottleneck_stats", "vsb_debug_tma_rate"):
         getattr(lib, name).restype = i
-    if lib.vsb_abi_version() != 6:
-        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 6")
+    # clip programs (ABI v7): every vsb_program_add_<op> takes (program, <the op's arguments without the stream>,
+    # lane, name)
+    cp, ull = C.c_char_p, C.c_ulonglong
+    lib.vsb_program_create.argtypes = [C.POINTER(vp)]
+    lib.vsb_program_destroy.argtypes = [vp]
+    lib.vsb_program_destroy.restype = None
+    lib.vsb_program_add_region.argtypes = [vp, cp, vp, ull, i]
+    lib.vsb_program_region.argtypes = [vp, cp, C.POINTER(vp), C.POINTER(ull)]
+    lib.vsb_program_num_ops.argtypes = [vp]
+    lib.vsb_program_num_launches.argtypes = [vp]
+    lib.vsb_program_device_bytes.argtypes = [vp]
+    lib.vsb_program_device_bytes.restype = ull
+    lib.vsb_program_add_conv.argtypes = [vp, vp, i, cp]
+    lib.vsb_program_add_bottleneck.argtypes = [vp, vp, C.POINTER(BottleneckDesc), i, cp]
+    for op in ("pack_frames", "maxpool3d", "global_avgpool", "linear", "nonlocal_attention", "score_rows",
+               "transpose_pad"):
+        getattr(lib, "vsb_program_add_" + op).argtypes = [vp] + list(getattr(lib, "vsb_" + op).argtypes[:-1]) + [i, cp]
+    lib.vsb_program_add_sync.argtypes = [vp, i, i]
+    lib.vsb_program_run.argtypes = [vp, vp]
+    lib.vsb_program_capture.argtypes = [vp, vp]
+    lib.vsb_program_save.argtypes = [vp, cp]
+    lib.vsb_program_file_device_bytes.argtypes = [cp, C.POINTER(ull)]
+    lib.vsb_program_load.argtypes = [cp, vp, ull, C.POINTER(vp)]
+    for name in ("vsb_program_create", "vsb_program_add_region", "vsb_program_region", "vsb_program_num_ops",
+                 "vsb_program_num_launches", "vsb_program_add_conv", "vsb_program_add_bottleneck",
+                 "vsb_program_add_pack_frames", "vsb_program_add_maxpool3d", "vsb_program_add_global_avgpool",
+                 "vsb_program_add_linear", "vsb_program_add_nonlocal_attention", "vsb_program_add_score_rows",
+                 "vsb_program_add_transpose_pad", "vsb_program_add_sync", "vsb_program_run", "vsb_program_capture",
+                 "vsb_program_save", "vsb_program_file_device_bytes", "vsb_program_load"):
+        getattr(lib, name).restype = i
+    if lib.vsb_abi_version() != 7:
+        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 7")
     _lib = lib
     return lib
 

@@ -59,6 +59,98 @@ class Act:
         return v[..., self.c_off: self.c_off + self.c_real]
 
 
+class Call:
+    """One C-ABI launch with its arguments marshalled once (include/vidsitu_b200.h: vsb_<op>(args..., stream)).
+    Calling it launches on torch's current stream; emit() appends it to a clip program
+    (vsb_program_add_<op>(program, args..., lane, name))."""
+
+    def __init__(self, op: str, args: tuple, keep: tuple = ()):
+        self.op = op
+        self.args = args
+        self._keep = keep          # tensors / ctypes arrays the arguments point into
+        self._fn = getattr(_l.load(), "vsb_" + op)
+
+    def __call__(self) -> None:
+        check(self._fn(*self.args, _stream_ptr()), "vsb_" + self.op)
+
+    def emit(self, prog: "Program", lane: int, name: str) -> None:
+        check(getattr(_l.load(), "vsb_program_add_" + self.op)(prog.handle, *self.args, lane, name.encode()),
+              "vsb_program_add_" + self.op)
+        prog.keep(self)
+
+
+class Program:
+    """A clip program (include/vidsitu_b200.h, ABI v7): the whole forward as ONE C handle - built by
+    ClipEngine.build_program, replayed by vsb_program_run (optionally as a CUDA graph captured inside the library),
+    saved to / loaded from a relocatable file that any host process can run without Python."""
+
+    CONST, SCRATCH = 0, 1
+
+    def __init__(self, handle: Optional[int] = None):
+        self._lib = _l.load()
+        self._h = C.c_void_p(handle)
+        self._keep: list = []
+        if handle is None:
+            check(self._lib.vsb_program_create(C.byref(self._h)), "vsb_program_create")
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def keep(self, obj) -> None:
+        self._keep.append(obj)     # plans and buffers are borrowed by the C side
+
+    def sync(self, src: int, dst: int) -> None:
+        check(self._lib.vsb_program_add_sync(self._h, src, dst), "vsb_program_add_sync")
+
+    def add_region(self, name: str, t: torch.Tensor, kind: int) -> None:
+        _require_cuda(t)
+        check(self._lib.vsb_program_add_region(self._h, name.encode(), t.data_ptr(), t.numel() * t.element_size(), kind),
+              "vsb_program_add_region")
+        self._keep.append(t)
+
+    def region(self, name: str):
+        """(device pointer, bytes) of a named region."""
+        ptr, nbytes = C.c_void_p(), C.c_ulonglong()
+        check(self._lib.vsb_program_region(self._h, name.encode(), C.byref(ptr), C.byref(nbytes)), "vsb_program_region")
+        return int(ptr.value), int(nbytes.value)
+
+    @property
+    def num_ops(self) -> int:
+        return int(self._lib.vsb_program_num_ops(self._h))
+
+    @property
+    def num_launches(self) -> int:
+        return int(self._lib.vsb_program_num_launches(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.vsb_program_device_bytes(self._h))
+
+    def run(self) -> None:
+        check(self._lib.vsb_program_run(self._h, _stream_ptr()), "vsb_program_run")
+
+    def capture(self) -> None:
+        check(self._lib.vsb_program_capture(self._h, _stream_ptr()), "vsb_program_capture")
+
+    def save(self, path: str) -> None:
+        check(self._lib.vsb_program_save(self._h, str(path).encode()), "vsb_program_save")
+
+    @classmethod
+    def load(cls, path: str) -> "Program":
+        """Rebuild a saved program in library-owned device memory (current device)."""
+        lib = _l.load()
+        h = C.c_void_p()
+        check(lib.vsb_program_load(str(path).encode(), None, 0, C.byref(h)), "vsb_program_load")
+        return cls(h.value)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.vsb_program_destroy(h)
+            h.value = None
+
+
 class ConvPlan:
     """One planned conv launch (TMA descriptors are encoded once, at plan time)."""
 
@@ -147,6 +239,10 @@ class ConvPlan:
     def run(self) -> None:
         check(self._lib.vsb_conv3d_run(self._h, _stream_ptr()), "vsb_conv3d_run")
 
+    def emit(self, prog: "Program", lane: int, name: str) -> None:
+        check(self._lib.vsb_program_add_conv(prog.handle, self._h, lane, name.encode()), "vsb_program_add_conv")
+        prog.keep(self)
+
     def info(self) -> dict:
         """How the plan runs (debug / tests): algorithm, mode, pipeline depth, grid, shared memory."""
         out = (C.c_longlong * 8)()
@@ -191,12 +287,18 @@ class BottleneckPlan:
         dsc.sa, dsc.ba, dsc.sb, dsc.bb, dsc.sc, dsc.bc = (t.data_ptr() for t in (sa, ba, sb, bb, sc, bc))
         dsc.stages, dsc.walk_len, dsc.grid = stages, walk_len, grid
         self._keep = (x.buf, out.buf, wa, wb, wc, sa, ba, sb, bb, sc, bc)
+        self._desc = dsc
         self._h = C.c_void_p()
         self._lib = _l.load()
         check(self._lib.vsb_bottleneck_plan_create(C.byref(dsc), C.byref(self._h)), "vsb_bottleneck_plan_create")
 
     def run(self) -> None:
         check(self._lib.vsb_bottleneck_run(self._h, _stream_ptr()), "vsb_bottleneck_run")
+
+    def emit(self, prog: "Program", lane: int, name: str) -> None:
+        check(self._lib.vsb_program_add_bottleneck(prog.handle, self._h, C.byref(self._desc), lane, name.encode()),
+              "vsb_program_add_bottleneck")
+        prog.keep(self)
 
     def info(self) -> dict:
         out = (C.c_longlong * 8)()
@@ -221,6 +323,11 @@ def pack_frames(frames: torch.Tensor, idx: Sequence[int], mean: Sequence[float],
                 out: Act, dtype: int, reverse_channels: bool = False, x_off: int = 0) -> None:
     """frames uint8 [n, t_in, h, w, 3] -> out [n, len(idx), h, out.w, 4] (normalised, temporally subsampled),
     frame columns written at pixel offset x_off of each (possibly wider, zero-bordered) output row."""
+    pack_frames_call(frames, idx, mean, std, out, dtype, reverse_channels, x_off)()
+
+
+def pack_frames_call(frames: torch.Tensor, idx: Sequence[int], mean: Sequence[float], std: Sequence[float],
+                     out: Act, dtype: int, reverse_channels: bool = False, x_off: int = 0) -> Call:
     _require_cuda(frames, out.buf)
     if frames.dtype != torch.uint8 or frames.dim() != 5 or frames.shape[-1] != 3 or not frames.is_contiguous():
         raise VsbError("frames must be a contiguous uint8 [n, t, h, w, 3] tensor")
@@ -230,9 +337,8 @@ def pack_frames(frames: torch.Tensor, idx: Sequence[int], mean: Sequence[float],
     idx_arr = (C.c_int * len(idx))(*[int(i) for i in idx])
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
-    check(_l.load().vsb_pack_frames(frames.data_ptr(), n, t_in, h, w, idx_arr, len(idx), m, s,
-                                    int(reverse_channels), out.ptr, 4, out.w, x_off, dtype, _stream_ptr()),
-          "vsb_pack_frames")
+    return Call("pack_frames", (frames.data_ptr(), n, t_in, h, w, idx_arr, len(idx), m, s, int(reverse_channels),
+                                out.ptr, 4, out.w, x_off, dtype), (frames, out.buf, idx_arr, m, s))
 
 
 def ncthw_to_act(x: torch.Tensor, out: Act, dtype: int, x_off: int = 0) -> None:
@@ -248,21 +354,33 @@ def ncthw_to_act(x: torch.Tensor, out: Act, dtype: int, x_off: int = 0) -> None:
 
 
 def maxpool3d(x: Act, out: Act, kernel, stride, pad, dtype: int) -> None:
+    maxpool3d_call(x, out, kernel, stride, pad, dtype)()
+
+
+def maxpool3d_call(x: Act, out: Act, kernel, stride, pad, dtype: int) -> Call:
     _require_cuda(x.buf, out.buf)
-    check(_l.load().vsb_maxpool3d(x.ptr, x.n, x.t, x.h, x.w, x.c_real, x.pitch, out.ptr, out.pitch, out.c,
-                                  kernel[0], kernel[1], kernel[2], stride[0], stride[1], stride[2],
-                                  pad[0], pad[1], pad[2], dtype, _stream_ptr()), "vsb_maxpool3d")
+    return Call("maxpool3d", (x.ptr, x.n, x.t, x.h, x.w, x.c_real, x.pitch, out.ptr, out.pitch, out.c,
+                              kernel[0], kernel[1], kernel[2], stride[0], stride[1], stride[2],
+                              pad[0], pad[1], pad[2], dtype), (x.buf, out.buf))
 
 
 def global_avgpool(x: Act, feats: torch.Tensor, feat_off: int, dtype: int) -> None:
+    global_avgpool_call(x, feats, feat_off, dtype)()
+
+
+def global_avgpool_call(x: Act, feats: torch.Tensor, feat_off: int, dtype: int) -> Call:
     _require_cuda(x.buf, feats)
     if feats.dtype != torch.float32 or feats.dim() != 2 or feats.shape[0] != x.n:
         raise VsbError("feats must be float32 [n, D]")
-    check(_l.load().vsb_global_avgpool(x.ptr, x.n, x.t * x.h * x.w, x.c_real, x.pitch, feats.data_ptr(),
-                                       feats.stride(0), feat_off, dtype, _stream_ptr()), "vsb_global_avgpool")
+    return Call("global_avgpool", (x.ptr, x.n, x.t * x.h * x.w, x.c_real, x.pitch, feats.data_ptr(), feats.stride(0),
+                                   feat_off, dtype), (x.buf, feats))
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], y: torch.Tensor, relu: bool) -> None:
+    linear_call(x, w, b, y, relu)()
+
+
+def linear_call(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], y: torch.Tensor, relu: bool) -> Call:
     _require_cuda(x, w, y)
     for t in (x, w, y):
         if t.dtype != torch.float32 or not t.is_contiguous():
@@ -271,8 +389,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], y: torch
     dout = w.shape[0]
     if w.shape[1] != din or tuple(y.shape) != (n, dout):
         raise VsbError("linear shape mismatch")
-    check(_l.load().vsb_linear(x.data_ptr(), n, din, w.data_ptr(), b.data_ptr() if b is not None else None,
-                               y.data_ptr(), dout, int(relu), _stream_ptr()), "vsb_linear")
+    return Call("linear", (x.data_ptr(), n, din, w.data_ptr(), b.data_ptr() if b is not None else None,
+                           y.data_ptr(), dout, int(relu)), (x, w, b, y))
 
 
 def softmax_topk(logits: torch.Tensor, k: int = 5):
@@ -294,12 +412,16 @@ def softmax_topk(logits: torch.Tensor, k: int = 5):
 
 
 def nonlocal_attention(theta: Act, phi: Act, g: Act, out: Act, softmax: bool, dtype: int) -> None:
+    nonlocal_attention_call(theta, phi, g, out, softmax, dtype)()
+
+
+def nonlocal_attention_call(theta: Act, phi: Act, g: Act, out: Act, softmax: bool, dtype: int) -> Call:
     _require_cuda(theta.buf, phi.buf, g.buf, out.buf)
     tq = theta.t * theta.h * theta.w
     tk = phi.t * phi.h * phi.w
-    check(_l.load().vsb_nonlocal_attention(theta.ptr, theta.pitch, phi.ptr, phi.pitch, g.ptr, g.pitch, out.ptr,
-                                           out.pitch, theta.n, tq, tk, theta.c_real, int(softmax), dtype,
-                                           _stream_ptr()), "vsb_nonlocal_attention")
+    return Call("nonlocal_attention", (theta.ptr, theta.pitch, phi.ptr, phi.pitch, g.ptr, g.pitch, out.ptr, out.pitch,
+                                       theta.n, tq, tk, theta.c_real, int(softmax), dtype),
+                (theta.buf, phi.buf, g.buf, out.buf))
 
 
 def act_to_ncthw(x: Act, dtype: int) -> torch.Tensor:
@@ -313,14 +435,20 @@ def act_to_ncthw(x: Act, dtype: int) -> torch.Tensor:
 
 def score_rows(scores: torch.Tensor, rows: int, valid: int, width: int, pitch: int, softmax: bool) -> None:
     """In place on bf16 scores [rows, pitch]: softmax over columns [0, valid) (or unchanged), zeros in [valid, width)."""
+    score_rows_call(scores, rows, valid, width, pitch, softmax)()
+
+
+def score_rows_call(scores: torch.Tensor, rows: int, valid: int, width: int, pitch: int, softmax: bool) -> Call:
     _require_cuda(scores)
-    check(_l.load().vsb_score_rows(scores.data_ptr(), rows, valid, width, pitch, int(softmax), _stream_ptr()),
-          "vsb_score_rows")
+    return Call("score_rows", (scores.data_ptr(), rows, valid, width, pitch, int(softmax)), (scores,))
 
 
 def transpose_pad(src: Act, out: torch.Tensor, out_pitch: int) -> None:
     """bf16 [n, keys, c] (pitch) -> out [n, c, out_pitch], zero-padded along keys."""
+    transpose_pad_call(src, out, out_pitch)()
+
+
+def transpose_pad_call(src: Act, out: torch.Tensor, out_pitch: int) -> Call:
     _require_cuda(src.buf, out)
     keys = src.t * src.h * src.w
-    check(_l.load().vsb_transpose_pad(src.ptr, src.pitch, out.data_ptr(), src.n, keys, src.c, out_pitch,
-                                      _stream_ptr()), "vsb_transpose_pad")
+    return Call("transpose_pad", (src.ptr, src.pitch, out.data_ptr(), src.n, keys, src.c, out_pitch), (src.buf, out))
