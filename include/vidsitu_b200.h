@@ -215,6 +215,32 @@ void vsb_bottleneck_plan_destroy(vsb_bottleneck_plan* plan);
  * bytes, tiles per clip, TMEM columns} */
 int vsb_bottleneck_plan_info(const vsb_bottleneck_plan* plan, long long* out8);
 
+/* ------------------------------------------------- fused 1x7x7 stem: conv + BN + ReLU + max-pool (ABI v7)
+ * Replaces, in ONE launch, ResNetBasicStem.forward for the [1,7,7] stems (SlowFast/slowfast/models/
+ * stem_helper.py:157-178: Conv3d kernel [1,7,7] stride [1,2,2] pad [0,3,3] + frozen BatchNorm3d + ReLU +
+ * MaxPool3d kernel [1,3,3] stride [1,2,2] pad [0,1,1]) with 3 input and 64 output channels: the Slow pathway of
+ * SlowFast, Slow-only and C2D.  bf16.  The conv output never reaches HBM.
+ *   in     [frames, h, w_buf, 4] packed frames as vsb_pack_frames writes them with x_off = 3 (image pixel x at
+ *          buffer pixel x + 3; pixels outside the image and channel 3 are zero); h, w multiples of 32,
+ *          w_buf >= w + 8;  frames = clips * T
+ *   wgt    [64][7][8][4] bf16: wgt[co][kh][kw][c] = W[co][c][0][kh][kw] for kw < 7, c < 3, else 0
+ *   out    [frames, h/4, w/4, out_pitch]: channels [0, 64) are written (zeroed, then max-combined), the rest of
+ *          each pixel (the lateral connection's channel slice) is left untouched                       */
+typedef struct vsb_stem_pool_desc {
+  const void* in;
+  int frames, h, w, w_buf;
+  const void* wgt;
+  const float* scale;           /* [64] folded BatchNorm */
+  const float* bias;            /* [64]                  */
+  void* out;
+  int out_pitch;
+} vsb_stem_pool_desc;
+typedef struct vsb_stem_pool_plan vsb_stem_pool_plan;
+int vsb_stem_pool_plan_create(const vsb_stem_pool_desc* desc, vsb_stem_pool_plan** plan);
+int vsb_stem_pool_run(const vsb_stem_pool_plan* plan, void* stream);   /* 2 launches: zero-fill + fused kernel */
+void vsb_stem_pool_plan_destroy(vsb_stem_pool_plan* plan);
+int vsb_stem_pool_plan_desc(const vsb_stem_pool_plan* plan, vsb_stem_pool_desc* desc);
+
 /* --------------------------------------------------------------- max-pool
  * Replaces nn.MaxPool3d (stem_helper.py:169-171, video_model_builder.py:235-241,
  * nonlocal_helper.py:98-103).  Implicit -inf padding as in PyTorch.  Channels
@@ -317,6 +343,7 @@ unsigned long long vsb_program_device_bytes(const vsb_program* prog); /* sum of 
 int vsb_program_add_conv(vsb_program* prog, const vsb_conv_plan* plan, int lane, const char* name);
 int vsb_program_add_bottleneck(vsb_program* prog, const vsb_bottleneck_plan* plan, const vsb_bottleneck_desc* desc,
                                int lane, const char* name);
+int vsb_program_add_stem_pool(vsb_program* prog, const vsb_stem_pool_plan* plan, int lane, const char* name);
 int vsb_program_add_pack_frames(vsb_program* prog, const uint8_t* frames, int n, int t_in, int h, int w, const int* idx,
                                 int t_out, const float* mean3, const float* std3, int reverse_channels, void* out,
                                 int c_pad, int out_w, int x_off, int dtype, int lane, const char* name);

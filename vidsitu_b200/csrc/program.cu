@@ -38,6 +38,7 @@ enum OpKind : int {
   OP_SCORE_ROWS = 8,
   OP_TRANSPOSE_PAD = 9,
   OP_SYNC = 10,
+  OP_STEM_POOL = 11,
 };
 
 struct PackArgs {
@@ -98,6 +99,7 @@ struct SyncArgs {
 union OpArgs {
   vsb_conv_desc conv;
   vsb_bottleneck_desc bott;
+  vsb_stem_pool_desc stem;
   PackArgs pack;
   PoolArgs pool;
   AvgArgs avg;
@@ -116,6 +118,7 @@ struct Op {
   // run-time state (never saved)
   const vsb_conv_plan* conv;
   const vsb_bottleneck_plan* bott;
+  const vsb_stem_pool_plan* stem;
   bool owns_plan;
   cudaEvent_t ev;
 };
@@ -136,6 +139,8 @@ const size_t kBottPtrs[] = {PF(vsb_bottleneck_desc, x),  PF(vsb_bottleneck_desc,
                             PF(vsb_bottleneck_desc, wb), PF(vsb_bottleneck_desc, wc),  PF(vsb_bottleneck_desc, sa),
                             PF(vsb_bottleneck_desc, ba), PF(vsb_bottleneck_desc, sb),  PF(vsb_bottleneck_desc, bb),
                             PF(vsb_bottleneck_desc, sc), PF(vsb_bottleneck_desc, bc)};
+const size_t kStemPtrs[] = {PF(vsb_stem_pool_desc, in), PF(vsb_stem_pool_desc, wgt), PF(vsb_stem_pool_desc, scale),
+                            PF(vsb_stem_pool_desc, bias), PF(vsb_stem_pool_desc, out)};
 const size_t kPackPtrs[] = {PF(PackArgs, frames), PF(PackArgs, out)};
 const size_t kPoolPtrs[] = {PF(PoolArgs, in), PF(PoolArgs, out)};
 const size_t kAvgPtrs[] = {PF(AvgArgs, in), PF(AvgArgs, feats)};
@@ -155,6 +160,7 @@ PtrTable ptr_table(int kind) {
   switch (kind) {
     case OP_CONV: return TBL(kConvPtrs, vsb_conv_desc);
     case OP_BOTTLENECK: return TBL(kBottPtrs, vsb_bottleneck_desc);
+    case OP_STEM_POOL: return TBL(kStemPtrs, vsb_stem_pool_desc);
     case OP_PACK: return TBL(kPackPtrs, PackArgs);
     case OP_MAXPOOL: return TBL(kPoolPtrs, PoolArgs);
     case OP_AVGPOOL: return TBL(kAvgPtrs, AvgArgs);
@@ -209,6 +215,7 @@ int run_op(const Op& op, cudaStream_t s) {
   switch (op.kind) {
     case OP_CONV: return vsb_conv3d_run(op.conv, st);
     case OP_BOTTLENECK: return vsb_bottleneck_run(op.bott, st);
+    case OP_STEM_POOL: return vsb_stem_pool_run(op.stem, st);
     case OP_PACK: {
       const PackArgs& a = op.a.pack;
       return vsb_pack_frames(a.frames, a.n, a.t_in, a.h, a.w, a.idx, a.t_out, a.mean, a.std, a.reverse, a.out, a.c_pad,
@@ -319,6 +326,7 @@ extern "C" void vsb_program_destroy(vsb_program* p) {
     if (op.ev) (void)cudaEventDestroy(op.ev);
     if (op.owns_plan && op.conv) vsb_conv3d_plan_destroy(const_cast<vsb_conv_plan*>(op.conv));
     if (op.owns_plan && op.bott) vsb_bottleneck_plan_destroy(const_cast<vsb_bottleneck_plan*>(op.bott));
+    if (op.owns_plan && op.stem) vsb_stem_pool_plan_destroy(const_cast<vsb_stem_pool_plan*>(op.stem));
   }
   if (p->side) (void)cudaStreamDestroy(p->side);
   if (p->owned_mem) (void)cudaFree(p->owned_mem);
@@ -360,7 +368,7 @@ extern "C" int vsb_program_num_ops(const vsb_program* p) { return p ? (int)p->op
 extern "C" int vsb_program_num_launches(const vsb_program* p) {
   int n = 0;
   if (p)
-    for (const Op& op : p->ops) n += op.kind != OP_SYNC;
+    for (const Op& op : p->ops) n += op.kind == OP_SYNC ? 0 : (op.kind == OP_STEM_POOL ? 2 : 1);
   return n;
 }
 
@@ -387,6 +395,18 @@ extern "C" int vsb_program_add_bottleneck(vsb_program* p, const vsb_bottleneck_p
   if (!op) return VSB_ERR_INVALID;
   op->a.bott = *desc;
   op->bott = plan;
+  return VSB_OK;
+}
+
+extern "C" int vsb_program_add_stem_pool(vsb_program* p, const vsb_stem_pool_plan* plan, int lane, const char* name) {
+  VSB_CHECK_ARG(plan, "null plan");
+  vsb_stem_pool_desc d;
+  int rc = vsb_stem_pool_plan_desc(plan, &d);
+  if (rc != VSB_OK) return rc;
+  Op* op = push_op(p, OP_STEM_POOL, lane, name);
+  if (!op) return VSB_ERR_INVALID;
+  op->a.stem = d;
+  op->stem = plan;
   return VSB_OK;
 }
 
@@ -700,6 +720,16 @@ extern "C" int vsb_program_load(const char* path, void* device_mem, unsigned lon
         return rc;  // vsb_conv3d_plan_create set the error text
       }
       q.conv = plan;
+      q.owns_plan = true;
+    } else if (q.kind == OP_STEM_POOL) {
+      vsb_stem_pool_plan* plan = nullptr;
+      rc = vsb_stem_pool_plan_create(&q.a.stem, &plan);
+      if (rc != VSB_OK) {
+        fclose(f);
+        vsb_program_destroy(p);
+        return rc;
+      }
+      q.stem = plan;
       q.owns_plan = true;
     } else if (q.kind == OP_BOTTLENECK) {
       vsb_bottleneck_plan* plan = nullptr;

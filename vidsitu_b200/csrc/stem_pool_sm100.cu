@@ -1,0 +1,384 @@
+// Fused 1x7x7 stride-2 stem: Conv3d + frozen BatchNorm + ReLU + MaxPool3d 1x3x3 stride 2 in ONE kernel.
+//
+// Reference ops replaced: ResNetBasicStem.forward (SlowFast/slowfast/models/stem_helper.py:157-178: conv [1,7,7]
+// stride [1,2,2] pad [0,3,3] -> BN -> ReLU -> MaxPool3d [1,3,3] stride [1,2,2] pad [0,1,1]) of the Slow pathway
+// (and of the Slow-only / C2D nets), on the packed bf16 frames vsb_pack_frames writes.  The conv output
+// (822 MB per 64 SlowFast clips) never reaches HBM: it is pooled out of shared memory.
+//
+// Formulation.  The packed input keeps 4 channels per pixel and a 3-pixel zero border on the left of every row, so
+// the 7 taps of one filter row of output column c start at buffer pixel 2c: 8 pixels x 4 channels = 32 bf16 = one
+// 64-byte K slot, and consecutive output columns' slots start 16 bytes apart.  A TMA tensor map whose W stride
+// (16 B) is smaller than its innermost extent (64 B) therefore delivers the im2col row of every output pixel
+// straight into shared memory (the overlap costs nothing: the bytes come out of L2 once per slot).  K = 7 filter
+// rows x 32, of which 7 x 7 x 3 = 147 carry weights (1.5x padding instead of the 4.6x of the pixel-group
+// restatement), N = 64, weights (28 KB) resident.
+//
+// Tile = 8 x 16 output pixels of one frame (M = 128).  Input rows are split by parity into two sub-windows
+// (odd rows feed the even filter rows kh = 0,2,4,6, even rows the odd ones) so that filter row kh of output row r
+// is sub-window row r + kh/2: every tap is the same 128-row UMMA operand with its start address advanced by
+// (kh/2) x 16 slots = a multiple of 1 KiB (the window trick of conv_win_sm100.cu in 2-D).  21 KB of shared memory
+// per tile instead of the 56 KB an im2col tile of 128 pixels needs.
+//
+// Epilogue: TMEM -> scale/bias/ReLU -> bf16 -> the 8 x 16 x 64 conv tile in shared memory -> 3x3/s2 max over it.
+// Pooled outputs whose window lies inside the tile (or hangs over the image edge: -inf padding) are stored;
+// the ones on the tile's seams (first pooled row / column needs the previous tile's last conv row / column, and
+// this tile's last conv row / column belongs to the next tile's first pooled output) are combined across tiles with
+// red.global.max.bf16x2 on a zero-initialised output: post-ReLU values are >= 0, so 0 is the identity, and
+// bf16 rounding is monotonic, so max(round(x)) == round(max(x)) bit for bit.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <stdlib.h>
+
+#include <new>
+
+#include "common.h"
+#include "conv_plan.h"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace vsb {
+namespace {
+
+constexpr int kCout = 64;
+constexpr int kTaps = 7;
+constexpr int kTileH = 8, kTileW = 16;
+constexpr int kStages = 4;
+constexpr int kAcc = 4;
+constexpr int kGroups = 4;                                 // epilogue groups of 4 warps, taking alternate tiles
+constexpr int kEpiWarps = 4 * kGroups;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr uint32_t kWBytes = kTaps * kCout * 64;           // 28672
+constexpr uint32_t kSub0Rows = 11, kSub1Rows = 10;         // odd-row window (4 taps), even-row window (3 taps)
+constexpr uint32_t kSub0Bytes = kSub0Rows * kTileW * 64;   // 11264
+constexpr uint32_t kSub1Bytes = kSub1Rows * kTileW * 64;   // 10240
+constexpr uint32_t kStageBytes = 22528;                    // both sub-windows, 1 KiB-aligned
+constexpr uint32_t kTileBytes = 128 * 128;                 // conv tile staging: 128 pixels x 64 bf16
+constexpr uint32_t kOffW = 0;
+constexpr uint32_t kOffE = kWBytes;
+constexpr uint32_t kOffS = kOffE + kStages * kStageBytes;
+constexpr uint32_t kOffSB = kOffS + kGroups * kTileBytes;
+constexpr uint32_t kOffBar = kOffSB + kCout * 8;
+constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;      // + alignment slack
+
+struct StemParams {
+  int frames, ho, wo;          // conv output extent per frame
+  int ph, pw;                  // pooled extent per frame
+  int tiles_h, tiles_w;        // tiles per frame
+  long long total_tiles;
+  const float* scale;
+  const float* bias;
+  __nv_bfloat16* out;
+  int out_pitch;
+  int dbg;   // timing experiments only (VSB_STEM_DBG): 1 = plain stores instead of red, 2 = no pooling phase
+};
+
+__device__ __forceinline__ void red_max_bf16x2_v4(void* gptr, uint4 v) {
+  asm volatile("red.global.max.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a), y = *reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162 m = __hmax2(x, y);
+  return *reinterpret_cast<uint32_t*>(&m);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+stem_pool_kernel(const __grid_constant__ CUtensorMap map_odd, const __grid_constant__ CUtensorMap map_even,
+                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* full = bars;                  // [kStages] window landed
+  uint64_t* empty = bars + kStages;       // [kStages] window consumed by the MMAs
+  uint64_t* tmem_full = bars + 2 * kStages;        // [kAcc]
+  uint64_t* tmem_empty = bars + 2 * kStages + kAcc;  // [kAcc]
+  uint64_t* wbar = bars + 2 * kStages + 2 * kAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAcc + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < kAcc; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kAcc * kCout);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_frame = p.tiles_h * p.tiles_w;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&map_odd);
+      tma_prefetch_desc(&map_even);
+      tma_prefetch_desc(&map_w);
+      mbar_expect_tx(wbar, kWBytes);
+      for (int kh = 0; kh < kTaps; ++kh) tma_load_2d(smem + kOffW + kh * (kCout * 64), &map_w, wbar, kh * 32, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int f = (int)(tile / tiles_per_frame);
+        const int rem = (int)(tile - (long long)f * tiles_per_frame);
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        const int r0 = th * kTileH, c0 = tw * kTileW;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* e = smem + kOffE + stage * kStageBytes;
+        mbar_expect_tx(&full[stage], kSub0Bytes + kSub1Bytes);
+        // odd input rows 2(r0 - 2 + m) + 1, m = 0..10 (filter rows 0,2,4,6); even rows 2(r0 - 1 + m), m = 0..9 (1,3,5)
+        tma_load_4d(e, &map_odd, &full[stage], 0, c0, r0 - 2, f);
+        tma_load_4d(e + kSub0Bytes, &map_even, &full[stage], 0, c0, r0 - 1, f);
+        if (++stage == kStages) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, kCout);
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      const uint32_t w_s = smem_u32(smem + kOffW);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t e_s = smem_u32(smem + kOffE + stage * kStageBytes);
+        const uint32_t d = tmem_base + acc * kCout;
+#pragma unroll
+        for (int kh = 0; kh < kTaps; ++kh) {
+          const uint32_t a_s = e_s + ((kh & 1) ? kSub0Bytes : 0u) + (uint32_t)(kh >> 1) * (kTileW * 64);
+          const uint32_t b_s = w_s + kh * (kCout * 64);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            umma_bf16(d, umma_smem_desc(a_s + ks * 32, 64), umma_smem_desc(b_s + ks * 32, 64), idesc, (kh | ks) != 0);
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&tmem_full[acc]);
+        if (++stage == kStages) stage = 0, phase ^= 1;
+        if (++acc == kAcc) acc = 0, acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: BN + ReLU + 3x3/s2 max-pool
+    // kGroups groups of four warps (one per TMEM lane quarter) take alternate tiles: one warp per scheduler cannot
+    // hide the latency of the ~650 dependent-ish instructions a tile costs each thread (measured: 4260 clk per tile
+    // with one group, the MMA side needs ~1200)
+    const int ew = warp - 2;                   // 0 .. kEpiWarps-1
+    const int group = ew >> 2;
+    const int et = (ew & 3) * 32 + lane;       // thread of the group, 0..127
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;       // GEMM row = conv pixel (row >> 4, row & 15) of the tile
+    float2* sb = reinterpret_cast<float2*>(smem + kOffSB);
+    if (group == 0 && et < kCout) sb[et] = make_float2(p.scale[et], p.bias[et]);
+    named_bar_sync(1, kEpiWarps * 32);
+    const uint32_t s_tile = smem_u32(smem + kOffS) + group * kTileBytes;
+    const int bar_id = 2 + group;
+    long long j = group;                       // CTA-local tile counter: tile j uses accumulator j % kAcc
+    for (long long tile = blockIdx.x + (long long)group * gridDim.x; tile < p.total_tiles;
+         tile += (long long)kGroups * gridDim.x, j += kGroups) {
+      const int acc = (int)(j % kAcc);
+      const uint32_t acc_phase = (uint32_t)((j / kAcc) & 1);
+      const int f = (int)(tile / tiles_per_frame);
+      const int rem = (int)(tile - (long long)f * tiles_per_frame);
+      const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kCout;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(taddr + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {   // 16-byte chunk = 8 channels
+          uint32_t o[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int cidx = half * 32 + ch * 8 + jj * 2;
+            const float2 s0 = sb[cidx], s1 = sb[cidx + 1];
+            const float x0 = fmaxf(fmaf(__uint_as_float(v[ch * 8 + jj * 2]), s0.x, s0.y), 0.f);
+            const float x1 = fmaxf(fmaf(__uint_as_float(v[ch * 8 + jj * 2 + 1]), s1.x, s1.y), 0.f);
+            o[jj] = pack_bf16x2(x0, x1);
+          }
+          const int chunk = half * 4 + ch;
+          sts128(s_tile + row * 128 + ((chunk ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      named_bar_sync(bar_id, 128);   // the whole conv tile is in shared memory
+      // pooled rows 4 th + pl (pl = 0..4), columns 8 tw + ql (ql = 0..8), 8 chunks of 8 channels each
+      for (int item = et; item < ((p.dbg & 2) ? 0 : 5 * 9 * 8); item += 128) {
+        const int k = item & 7, pq = item >> 3;
+        const int pl = pq / 9, ql = pq - pl * 9;
+        const int pg = th * 4 + pl, qg = tw * 8 + ql;
+        if (pg >= p.ph || qg >= p.pw) continue;
+        uint4 m = make_uint4(0, 0, 0, 0);   // post-ReLU values are >= 0
+#pragma unroll
+        for (int dr = 0; dr < 3; ++dr) {
+          const int r = 2 * pl - 1 + dr;
+          if (r < 0 || r >= kTileH) continue;
+#pragma unroll
+          for (int dc = 0; dc < 3; ++dc) {
+            const int c = 2 * ql - 1 + dc;
+            if (c < 0 || c >= kTileW) continue;
+            const int i = r * kTileW + c;
+            const uint4 x = lds128(s_tile + i * 128 + ((k ^ (i & 7)) << 4));
+            m.x = hmax2_u32(m.x, x.x);
+            m.y = hmax2_u32(m.y, x.y);
+            m.z = hmax2_u32(m.z, x.z);
+            m.w = hmax2_u32(m.w, x.w);
+          }
+        }
+        __nv_bfloat16* dst = p.out + (((long long)f * p.ph + pg) * p.pw + qg) * p.out_pitch + k * 8;
+        // seam outputs get contributions from two or four tiles; image-edge outputs (pl == 0 in the first tile
+        // row, ql == 0 in the first tile column) are complete: the missing row / column is -inf padding
+        const bool seam = (pl == 0 && th > 0) || pl == 4 || (ql == 0 && tw > 0) || ql == 8;
+        if (seam && !(p.dbg & 1))
+          red_max_bf16x2_v4(dst, m);
+        else
+          *reinterpret_cast<uint4*>(dst) = m;
+      }
+      named_bar_sync(bar_id, 128);   // the group's staging tile may be overwritten
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kAcc * kCout);
+  }
+}
+
+// zero the first `chunks` 16-byte chunks of every pixel of a [pixels, pitch_chunks * 16 B] tensor
+__global__ void zero_channels_kernel(uint4* out, long long pixels, int chunks, int pitch_chunks) {
+  const long long total = pixels * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long px = i / chunks;
+    const int k = (int)(i - px * chunks);
+    out[px * pitch_chunks + k] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+}  // namespace
+}  // namespace vsb
+
+using namespace vsb;
+
+struct vsb_stem_pool_plan {
+  vsb_stem_pool_desc desc;
+  CUtensorMap map_odd, map_even, map_w;
+  StemParams params;
+  unsigned grid;
+};
+
+static int sp_encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                     const cuuint32_t* box, const char* what) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed (CUresult %d)", what, (int)r);
+    return VSB_ERR_CUDA;
+  }
+  return VSB_OK;
+}
+
+extern "C" int vsb_stem_pool_plan_create(const vsb_stem_pool_desc* d, vsb_stem_pool_plan** out) {
+  VSB_CHECK_ARG(d && out, "null argument");
+  *out = nullptr;
+  VSB_CHECK_ARG(d->in && d->wgt && d->scale && d->bias && d->out, "null tensor");
+  VSB_CHECK_ARG(d->frames > 0 && d->h > 0 && d->w > 0, "bad extent");
+  VSB_CHECK_ARG(d->h % 32 == 0 && d->w % 32 == 0, "fused stem: frame height and width must be multiples of 32 (got %d x %d)", d->h, d->w);
+  VSB_CHECK_ARG(d->w_buf >= d->w + 8, "fused stem: input rows need 3 zero pixels before and 5 after the image (w_buf >= w + 8)");
+  VSB_CHECK_ARG(d->out_pitch >= kCout && d->out_pitch % 8 == 0, "out_pitch must be a multiple of 8 and >= 64");
+  VSB_CHECK_ARG(((uintptr_t)d->in | (uintptr_t)d->wgt | (uintptr_t)d->out) % 16 == 0, "tensors must be 16-byte aligned");
+  int rc = load_driver_entry_points();
+  if (rc != VSB_OK) return rc;
+  vsb_stem_pool_plan* plan = new (std::nothrow) vsb_stem_pool_plan();
+  VSB_CHECK_ARG(plan, "out of host memory");
+  plan->desc = *d;
+  const int ho = d->h / 2, wo = d->w / 2;
+  const unsigned long long row_bytes = (unsigned long long)d->w_buf * 8, frame_bytes = row_bytes * d->h;
+  const unsigned long long slots = ((unsigned long long)d->w_buf * 4 - 32) / 8 + 1;  // 64-byte slots at 16-byte steps
+  {
+    // overlapping view: [32 channels-of-8-pixels][slot, 16 B apart][row of one parity][frame]
+    cuuint64_t dims[4] = {32, slots, (cuuint64_t)(d->h / 2), (cuuint64_t)d->frames};
+    cuuint64_t strides[3] = {16, 2 * row_bytes, frame_bytes};
+    cuuint32_t box0[4] = {32, (cuuint32_t)kTileW, kSub0Rows, 1}, box1[4] = {32, (cuuint32_t)kTileW, kSub1Rows, 1};
+    rc = sp_encode(&plan->map_odd, (const char*)d->in + row_bytes, 4, dims, strides, box0, "stem input, odd rows");
+    if (rc == VSB_OK) rc = sp_encode(&plan->map_even, d->in, 4, dims, strides, box1, "stem input, even rows");
+  }
+  if (rc == VSB_OK) {
+    cuuint64_t dims[2] = {(cuuint64_t)kTaps * 32, (cuuint64_t)kCout};
+    cuuint64_t strides[1] = {(cuuint64_t)kTaps * 32 * 2};
+    cuuint32_t box[2] = {32, (cuuint32_t)kCout};
+    rc = sp_encode(&plan->map_w, d->wgt, 2, dims, strides, box, "stem weights");
+  }
+  if (rc != VSB_OK) {
+    delete plan;
+    return rc;
+  }
+  StemParams& p = plan->params;
+  p.frames = d->frames, p.ho = ho, p.wo = wo;
+  p.ph = ho / 2, p.pw = wo / 2;
+  p.tiles_h = ho / kTileH, p.tiles_w = wo / kTileW;
+  p.total_tiles = (long long)d->frames * p.tiles_h * p.tiles_w;
+  p.scale = d->scale, p.bias = d->bias;
+  p.out = (__nv_bfloat16*)d->out;
+  p.out_pitch = d->out_pitch;
+  p.dbg = getenv("VSB_STEM_DBG") ? atoi(getenv("VSB_STEM_DBG")) : 0;
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e != cudaSuccess) {
+    delete plan;
+    set_error("fused stem plan: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return VSB_ERR_CUDA;
+  }
+  plan->grid = (unsigned)(p.total_tiles < sms ? p.total_tiles : sms);
+  *out = plan;
+  return VSB_OK;
+}
+
+extern "C" int vsb_stem_pool_run(const vsb_stem_pool_plan* plan, void* stream) {
+  VSB_CHECK_ARG(plan, "null plan");
+  cudaStream_t s = (cudaStream_t)stream;
+  const StemParams& p = plan->params;
+  const long long pixels = (long long)p.frames * p.ph * p.pw;
+  zero_channels_kernel<<<1184, 256, 0, s>>>(reinterpret_cast<uint4*>(p.out), pixels, kCout / 8, p.out_pitch / 8);
+  VSB_CHECK_LAUNCH("zero_channels_kernel");
+  stem_pool_kernel<<<plan->grid, kThreads, kSmemBytes, s>>>(plan->map_odd, plan->map_even, plan->map_w, p);
+  VSB_CHECK_LAUNCH("stem_pool_kernel");
+  return VSB_OK;
+}
+
+extern "C" void vsb_stem_pool_plan_destroy(vsb_stem_pool_plan* plan) { delete plan; }
+
+extern "C" int vsb_stem_pool_plan_desc(const vsb_stem_pool_plan* plan, vsb_stem_pool_desc* out) {
+  VSB_CHECK_ARG(plan && out, "null argument");
+  *out = plan->desc;
+  return VSB_OK;
+}

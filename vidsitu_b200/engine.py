@@ -76,9 +76,10 @@ class _SlotLaunch:
     """The stem conv of one pathway: one plan per input slot (the slots differ only in the input buffer), the
     launch runs the plan of the slot selected at launch / capture / program-build time."""
 
-    def __init__(self, engine: "ClipEngine", plans: List[ConvPlan]):
+    def __init__(self, engine: "ClipEngine", plans: list, launches: int = 1):
         self.engine = engine
         self.plans = plans
+        self.launches = launches    # kernels per run (the fused stem zero-fills its output first)
 
     def __call__(self) -> None:
         self.plans[self.engine._slot].run()
@@ -142,6 +143,7 @@ class ClipEngine:
         self.fused_shortcuts: List[str] = []   # branch1 convs computed inside their block's last conv
         self.chained: List[tuple] = []  # (last conv of a block, first conv of the next) run as chained launches
         self.fused_blocks: List[str] = []      # identity blocks that run as one fused a-b-c launch
+        self.fused_stems: List[str] = []       # stems that run conv + BN + ReLU + max-pool as one kernel
         self.crop = spec.crop
         if self.crop % 16:
             raise VsbError("crop size must be a multiple of 16")
@@ -515,6 +517,39 @@ class ClipEngine:
         self.trunk_ops.append((cs.key, _SlotLaunch(self, plans), float(y.pixels) * cs.flops_per_out_pixel))
         return y
 
+    def _fused_stem(self, p: int, pitch: Optional[int]) -> Optional[Act]:
+        """[1,7,7] stems with 64 output channels (Slow pathway, Slow-only, C2D): conv + BN + ReLU + max-pool as ONE
+        kernel (vsb_stem_pool_*, stem_pool_sm100.cu) - the conv output never reaches HBM.  Returns the pooled
+        activation, or None when the stem is outside the kernel's domain (then conv and pool run separately)."""
+        st = self.spec.stems[p]
+        cs = st.conv
+        if self.dtype != VSB_BF16 or self.x_off != 3 or self.crop % 32:
+            return None
+        if str(self._tune(cs.key).get("fuse_stem", os.environ.get("VSB_FUSE_STEM", "1"))) not in ("1", "True"):
+            return None
+        if (tuple(cs.kernel) != (1, 7, 7) or tuple(cs.stride) != (1, 2, 2) or tuple(cs.pad) != (0, 3, 3) or cs.cout != 64
+                or cs.cin != 3 or tuple(st.pool_kernel) != (1, 3, 3) or tuple(st.pool_stride) != (1, 2, 2)
+                or tuple(st.pool_pad) != (0, 1, 1) or cs.has_bias):
+            return None
+        x0 = self.input_sets[0][p]
+        n, t = x0.n, x0.t
+
+        def make():
+            w = self._tensor(cs.key + ".weight")                     # [64, 3, 1, 7, 7]
+            q = torch.zeros((64, 7, 8, 4), dtype=torch.float32)
+            q[:, :, :7, :3] = w[:, :, 0].permute(0, 2, 3, 1)         # [co, kh, kw, c]
+            return self._up(q.to(self.tdt))
+        wq = self._memo((cs.key, "stem_pool"), make)
+        scale, bias = self._sb(cs, 64)
+        y = self._alloc(n, t, self.crop // 4, self.crop // 4, 64, pitch=pitch, min_c=16)
+        plans = [ops.StemPoolPlan(inputs[p], self.x_off, wq, scale, bias, y, self.crop) for inputs in self.input_sets]
+        self._keep += plans
+        name = cs.key + "+pool"
+        self.op_bytes[name] = 2.0 * (x0.pixels * 4 + y.pixels * 64)
+        self.trunk_ops.append((name, _SlotLaunch(self, plans, launches=2), float(n * t * (self.crop // 2) ** 2) * cs.flops_per_out_pixel))
+        self.fused_stems.append(cs.key)
+        return y
+
     def _stem_plan(self, cs: ConvSpec, x: Act, y: Act, to: int, ho: int, wo: int) -> ConvPlan:
         n, t = x.n, x.t
         wt = self._tensor(cs.key + ".weight")
@@ -828,10 +863,14 @@ class ClipEngine:
         # s1: stem conv + BN + ReLU + max-pool per pathway (stem_helper.py:173-178)
         for p in range(npw):
             self._pool = self._pools[p]
-            y = self._stem(p, self.inputs[p])
             st = spec.stems[p]
             fuse = spec.fuses[0] if p == 0 else None
-            pitch = self._store(y.c_real) + fuse.cout if fuse is not None else None
+            pitch = self._store(st.conv.cout) + fuse.cout if fuse is not None else None
+            fused = self._fused_stem(p, pitch)
+            if fused is not None:
+                xs.append(fused)
+                continue
+            y = self._stem(p, self.inputs[p])
             # (16 channels at least: the lateral conv reads this tensor un-grouped, 16 = one MMA K step)
             xs.append(self._maxpool(f"s1.pathway{p}_stem.pool_layer", y, st.pool_kernel, st.pool_stride, st.pool_pad,
                                     pitch, min_c=16))
@@ -1163,7 +1202,7 @@ class ClipEngine:
 
     @property
     def num_launches(self) -> int:
-        return len(self.trunk_ops) + len(self.head_ops)
+        return sum(getattr(fn, "launches", 1) for _, fn, _ in self.trunk_ops + self.head_ops)
 
     @property
     def conv_flops(self) -> float:

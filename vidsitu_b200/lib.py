@@ -71,6 +71,18 @@ class BottleneckDesc(C.Structure):
     ]
 
 
+class StemPoolDesc(C.Structure):
+    """Mirror of `vsb_stem_pool_desc` (include/vidsitu_b200.h)."""
+
+    _fields_ = [
+        ("in_", C.c_void_p),
+        ("frames", C.c_int), ("h", C.c_int), ("w", C.c_int), ("w_buf", C.c_int),
+        ("wgt", C.c_void_p), ("scale", C.c_void_p), ("bias", C.c_void_p),
+        ("out", C.c_void_p),
+        ("out_pitch", C.c_int),
+    ]
+
+
 def lib_path() -> Path:
     env = os.environ.get("VIDSITU_B200_LIB")
     return Path(env) if env else Path(__file__).resolve().parent / _LIB_NAME
@@ -148,13 +160,20 @@ def load() -> C.CDLL:
     for op in ("pack_frames", "maxpool3d", "global_avgpool", "linear", "nonlocal_attention", "score_rows",
                "transpose_pad"):
         getattr(lib, "vsb_program_add_" + op).argtypes = [vp] + list(getattr(lib, "vsb_" + op).argtypes[:-1]) + [i, cp]
+    lib.vsb_stem_pool_plan_create.argtypes = [C.POINTER(StemPoolDesc), C.POINTER(vp)]
+    lib.vsb_stem_pool_run.argtypes = [vp, vp]
+    lib.vsb_stem_pool_plan_destroy.argtypes = [vp]
+    lib.vsb_stem_pool_plan_destroy.restype = None
+    lib.vsb_stem_pool_plan_desc.argtypes = [vp, C.POINTER(StemPoolDesc)]
+    lib.vsb_program_add_stem_pool.argtypes = [vp, vp, i, cp]
     lib.vsb_program_add_sync.argtypes = [vp, i, i]
     lib.vsb_program_run.argtypes = [vp, vp]
     lib.vsb_program_capture.argtypes = [vp, vp]
     lib.vsb_program_save.argtypes = [vp, cp]
     lib.vsb_program_file_device_bytes.argtypes = [cp, C.POINTER(ull)]
     lib.vsb_program_load.argtypes = [cp, vp, ull, C.POINTER(vp)]
-    for name in ("vsb_program_create", "vsb_program_add_region", "vsb_program_region", "vsb_program_num_ops",
+    for name in ("vsb_stem_pool_plan_create", "vsb_stem_pool_run", "vsb_stem_pool_plan_desc", "vsb_program_add_stem_pool",
+                 "vsb_program_create", "vsb_program_add_region", "vsb_program_region", "vsb_program_num_ops",
                  "vsb_program_num_launches", "vsb_program_add_conv", "vsb_program_add_bottleneck",
                  "vsb_program_add_pack_frames", "vsb_program_add_maxpool3d", "vsb_program_add_global_avgpool",
                  "vsb_program_add_linear", "vsb_program_add_nonlocal_attention", "vsb_program_add_score_rows",

@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import lib as _l
-from .lib import VSB_BF16, VSB_F32, BottleneckDesc, ConvDesc, VsbError, check
+from .lib import VSB_BF16, VSB_F32, BottleneckDesc, ConvDesc, StemPoolDesc, VsbError, check
 
 TORCH_DTYPE = {VSB_BF16: torch.bfloat16, VSB_F32: torch.float32}
 
@@ -316,6 +316,46 @@ class BottleneckPlan:
         h = getattr(self, "_h", None)
         if h is not None and h.value:
             self._lib.vsb_bottleneck_plan_destroy(h)
+            h.value = None
+
+
+class StemPoolPlan:
+    """One planned fused [1,7,7] stem (vsb_stem_pool_*): conv + frozen BN + ReLU + 1x3x3/s2 max-pool of the packed
+    bf16 frames in one kernel (stem_helper.py:157-178); `out` receives the pooled [frames, h/4, w/4, 64] channels."""
+
+    def __init__(self, x: Act, x_off: int, wgt: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, out: Act, w: int):
+        _require_cuda(x.buf, wgt, scale, bias, out.buf)
+        if x_off != 3 or x.pitch != 4 or x.c_off:
+            raise VsbError("fused stem: input must be the packed 4-channel frames with a 3-pixel left border")
+        if wgt.dtype != torch.bfloat16 or wgt.numel() != 64 * 7 * 32 or not wgt.is_contiguous():
+            raise VsbError("fused stem: weights must be contiguous bf16 [64, 7, 8, 4]")
+        for t in (scale, bias):
+            if t.dtype != torch.float32 or t.numel() != 64 or not t.is_contiguous():
+                raise VsbError("fused stem: scale / bias must be contiguous float32 [64]")
+        if (out.n, out.t, out.h, out.w) != (x.n, x.t, x.h // 4, w // 4) or out.c != 64:
+            raise VsbError("fused stem: output must be [n, t, h/4, w/4] with 64 stored channels")
+        d = StemPoolDesc()
+        d.in_ = x.ptr
+        d.frames, d.h, d.w, d.w_buf = x.n * x.t, x.h, w, x.w
+        d.wgt, d.scale, d.bias = wgt.data_ptr(), scale.data_ptr(), bias.data_ptr()
+        d.out, d.out_pitch = out.ptr, out.pitch
+        self._keep = (x.buf, wgt, scale, bias, out.buf)
+        self._h = C.c_void_p()
+        self._lib = _l.load()
+        check(self._lib.vsb_stem_pool_plan_create(C.byref(d), C.byref(self._h)), "vsb_stem_pool_plan_create")
+        self.flops = 2.0 * d.frames * (d.h // 2) * (w // 2) * 64 * 7 * 32
+
+    def run(self) -> None:
+        check(self._lib.vsb_stem_pool_run(self._h, _stream_ptr()), "vsb_stem_pool_run")
+
+    def emit(self, prog: "Program", lane: int, name: str) -> None:
+        check(self._lib.vsb_program_add_stem_pool(prog.handle, self._h, lane, name.encode()), "vsb_program_add_stem_pool")
+        prog.keep(self)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.vsb_stem_pool_plan_destroy(h)
             h.value = None
 
 
