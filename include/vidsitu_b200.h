@@ -151,6 +151,10 @@ typedef struct vsb_conv_desc {
   /* bf16 im2col algorithm: at most this many CTAs (0 = automatic: every SM, twice when two CTAs fit).  A chained
    * pair splits the SMs' CTA slots between producer and consumer with it.                                    */
   int grid_limit;
+  /* bf16 path, one-SM im2col kernel, no residual / second source: `in` and `wgt` hold IEEE half instead of bf16
+   * (ABI v7).  The score product of the non-local block: theta and phi enter the exponent of the softmax, so
+   * their rounding (2^-9 relative in bf16) becomes a RELATIVE error of every attention weight; half gives 2^-12. */
+  int in_f16;
 } vsb_conv_desc;
 
 #define VSB_PLAN_STREAM_WEIGHTS 1 /* im2col: never keep the weight block resident in shared memory      */
@@ -215,15 +219,18 @@ void vsb_bottleneck_plan_destroy(vsb_bottleneck_plan* plan);
  * bytes, tiles per clip, TMEM columns} */
 int vsb_bottleneck_plan_info(const vsb_bottleneck_plan* plan, long long* out8);
 
-/* ------------------------------------------------- fused 1x7x7 stem: conv + BN + ReLU + max-pool (ABI v7)
- * Replaces, in ONE launch, ResNetBasicStem.forward for the [1,7,7] stems (SlowFast/slowfast/models/
- * stem_helper.py:157-178: Conv3d kernel [1,7,7] stride [1,2,2] pad [0,3,3] + frozen BatchNorm3d + ReLU +
- * MaxPool3d kernel [1,3,3] stride [1,2,2] pad [0,1,1]) with 3 input and 64 output channels: the Slow pathway of
- * SlowFast, Slow-only and C2D.  bf16.  The conv output never reaches HBM.
+/* ------------------------------------------------- fused [kt,7,7] stem: conv + BN + ReLU + max-pool (ABI v7)
+ * Replaces, in ONE launch, ResNetBasicStem.forward for the 64-channel stems (SlowFast/slowfast/models/
+ * stem_helper.py:157-178: Conv3d kernel [kt,7,7] stride [1,2,2] pad [kt/2,3,3] + frozen BatchNorm3d + ReLU +
+ * MaxPool3d kernel [1,3,3] stride [1,2,2] pad [0,1,1]) with 3 input and 64 output channels: kt = 1 - the Slow
+ * pathway of SlowFast, Slow-only and C2D; kt = 5 - I3D.  bf16.  The conv output never reaches HBM.
  *   in     [frames, h, w_buf, 4] packed frames as vsb_pack_frames writes them with x_off = 3 (image pixel x at
  *          buffer pixel x + 3; pixels outside the image and channel 3 are zero); h, w multiples of 32,
  *          w_buf >= w + 8;  frames = clips * T
- *   wgt    [64][7][8][4] bf16: wgt[co][kh][kw][c] = W[co][c][0][kh][kw] for kw < 7, c < 3, else 0
+ *   wgt    kt = 1: [64][7][8][4] bf16: wgt[co][kh][kw][c] = W[co][c][0][kh][kw] for kw < 7, c < 3, else 0;
+ *          kt = 5: [5 * 64][7][8][4], the same block per temporal tap, in the tap order 0, 2, 1, 4, 3 (the kernel
+ *          multiplies taps (2,1) and (4,3) as stacked pairs)
+ *   t      kt = 5 only: frames per clip (temporal taps do not cross clips): 3..8 or a multiple of 8
  *   out    [frames, h/4, w/4, out_pitch]: channels [0, 64) are written (zeroed, then max-combined), the rest of
  *          each pixel (the lateral connection's channel slice) is left untouched                       */
 typedef struct vsb_stem_pool_desc {
@@ -234,6 +241,8 @@ typedef struct vsb_stem_pool_desc {
   const float* bias;            /* [64]                  */
   void* out;
   int out_pitch;
+  int kt;                       /* temporal taps: 1 or 5 */
+  int t;                        /* frames per clip (kt = 5) */
 } vsb_stem_pool_desc;
 typedef struct vsb_stem_pool_plan vsb_stem_pool_plan;
 int vsb_stem_pool_plan_create(const vsb_stem_pool_desc* desc, vsb_stem_pool_plan** plan);

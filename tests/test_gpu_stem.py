@@ -13,13 +13,15 @@ pytestmark = pytest.mark.gpu
 def _torch_stem(x_bf16_ncthw, w, scale, bias):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    y = torch.nn.functional.conv3d(x_bf16_ncthw.float(), w.bfloat16().float(), None, (1, 2, 2), (0, 3, 3))
+    y = torch.nn.functional.conv3d(x_bf16_ncthw.float(), w.bfloat16().float(), None, (1, 2, 2), (w.shape[2] // 2, 3, 3))
     y = torch.relu(y * scale.view(1, -1, 1, 1, 1) + bias.view(1, -1, 1, 1, 1)).bfloat16().float()
     return torch.nn.functional.max_pool3d(y, (1, 3, 3), (1, 2, 2), (0, 1, 1))
 
 
-@pytest.mark.parametrize("crop,n,t,pitch", [(64, 2, 3, 64), (224, 1, 2, 80), (96, 3, 1, 72)])
-def test_fused_stem_matches_torch(crop, n, t, pitch):
+@pytest.mark.parametrize("crop,n,t,pitch,kt", [(64, 2, 3, 64, 1), (224, 1, 2, 80, 1), (96, 3, 1, 72, 1),
+                                               (64, 2, 8, 64, 5), (96, 3, 3, 64, 5), (64, 1, 16, 72, 5), (224, 2, 8, 64, 5),
+                                               (224, 8, 8, 80, 5), (224, 24, 1, 64, 1)])   # several runs / tiles per CTA
+def test_fused_stem_matches_torch(crop, n, t, pitch, kt):
     from vidsitu_b200 import ops
     from vidsitu_b200.lib import VSB_BF16
     from vidsitu_b200.ops import Act
@@ -27,21 +29,23 @@ def test_fused_stem_matches_torch(crop, n, t, pitch):
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(crop + n)
     frames = torch.randint(0, 256, (n, t, crop, crop, 3), dtype=torch.uint8, generator=g).to(dev)
-    w = (torch.randn((64, 3, 1, 7, 7), generator=g) * 0.1).to(dev)
+    w = (torch.randn((64, 3, kt, 7, 7), generator=g) * 0.1).to(dev)
     scale = (torch.rand(64, generator=g) + 0.5).to(dev)
     bias = (torch.randn(64, generator=g) * 0.3).to(dev)
     mean, std = [0.45, 0.45, 0.45], [0.225, 0.225, 0.225]
     w_buf = crop + 16
     xin = Act(torch.zeros(n * t * crop * w_buf * 4, dtype=torch.bfloat16, device=dev), n, t, crop, w_buf, 4, 4, c_real=3)
     ops.pack_frames(frames, list(range(t)), mean, std, xin, VSB_BF16, False, 3)
-    q = torch.zeros((64, 7, 8, 4), dtype=torch.float32, device=dev)
-    q[:, :, :7, :3] = w[:, :, 0].permute(0, 2, 3, 1)
+    order = (0,) if kt == 1 else (0, 2, 1, 4, 3)
+    q = torch.zeros((len(order), 64, 7, 8, 4), dtype=torch.float32, device=dev)
+    for i, k in enumerate(order):
+        q[i, :, :, :7, :3] = w[:, :, k].permute(0, 2, 3, 1)
     wq = q.bfloat16().contiguous()
     po = crop // 4
     # the untouched channel slice [64, pitch) must survive (it belongs to the lateral connection)
     out_buf = torch.full((n * t * po * po * pitch,), 7.0, dtype=torch.bfloat16, device=dev)
     out = Act(out_buf, n, t, po, po, 64, pitch)
-    plan = ops.StemPoolPlan(xin, 3, wq, scale, bias, out, crop)
+    plan = ops.StemPoolPlan(xin, 3, wq, scale, bias, out, crop, kt=kt)
     plan.run()
     plan.run()     # idempotent: the output is zero-filled inside the run
     torch.cuda.synchronize()
@@ -56,10 +60,11 @@ def test_fused_stem_matches_torch(crop, n, t, pitch):
     assert float((err > 0).float().mean()) < 0.02
 
 
-def test_engine_with_fused_stem_matches_unfused_engine():
+@pytest.mark.parametrize("name", ["slow_fast_nl_r50_8x8", "i3d_r50_8x8"])
+def test_engine_with_fused_stem_matches_unfused_engine(name):
     feats = {}
     for fuse in (True, False):
-        model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=5, crop=64, tune={"*": {"fuse_stem": fuse}})
+        model, cfg, _ = build_model(name, seed=5, crop=64, tune={"*": {"fuse_stem": fuse}})
         model = model.cuda()
         eng = model._engine(2, torch.device("cuda"))
         assert (len(eng.fused_stems) == 1) == fuse

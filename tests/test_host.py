@@ -221,7 +221,7 @@ def test_ctypes_conv_desc_matches_the_c_header(tmp_path):
     import ctypes as C
     import subprocess
     fields = ["dtype", "wgt", "cout", "scale", "out_pitch", "block_n", "algo", "kw_c_hi", "in2", "sw2", "epi_n",
-              "epi_bufs", "flags", "out_f16", "wgt_clip_rows"]
+              "epi_bufs", "flags", "out_f16", "wgt_clip_rows", "tile_wait", "grid_limit", "in_f16"]
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vidsitu_b200.h"\nint main(void){'
                    'printf("%zu", sizeof(vsb_conv_desc));'

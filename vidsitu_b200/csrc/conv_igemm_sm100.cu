@@ -602,6 +602,12 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
     delete plan;
     return VSB_ERR_INVALID;
   }
+  if (d->in_f16 && (d->dtype != VSB_BF16 || d->algo == 2 || d->residual || d->in2 ||
+                    (d->flags & (VSB_PLAN_TWO_SM | VSB_PLAN_TWO_SM_RESIDENT)))) {
+    set_error("in_f16 needs the one-SM im2col algorithm of the 16-bit path without residual / second source");
+    delete plan;
+    return VSB_ERR_INVALID;
+  }
   if (d->out_f16 && (d->algo == 2 || d->residual || d->in2)) {
     set_error("out_f16 needs the im2col algorithm without residual / second source");
     delete plan;
@@ -881,7 +887,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   p.wgt_clip_rows = d->wgt_clip_rows;
   p.total_tiles = clip_rows ? d->n * p.clip_tiles * p.n_tiles : (int)(ceil_div_ll(m_total, kBlockM) * p.n_tiles);
   p.epi_n = epi_n; p.epi_chunks = block_n / epi_n;
-  p.idesc = umma_idesc_bf16(kBlockM, block_n);
+  p.idesc = d->in_f16 ? umma_idesc_f16(kBlockM, block_n) : umma_idesc_bf16(kBlockM, block_n);
   p.tmem_cols = tmem_cols;
   p.scale = d->scale; p.bias = d->bias;
   p.has_residual = d->residual != nullptr;
@@ -931,7 +937,7 @@ extern "C" int vsb_conv3d_plan_create(const vsb_conv_desc* d, vsb_conv_plan** ou
   static const bool no_two_sm_env = getenv("VSB_NO_TWO_SM") != nullptr;
   // (64-byte rows, i.e. the pixel-grouped stems: 2 - 4 % faster in pairs once a ring stage carries two chunks;
   // with one chunk = two MMAs per stage the issuer was the bottleneck: 0.46 vs 0.42 ms)
-  const bool two_sm_auto = !no_two_sm_env && !chained && !(d->flags & VSB_PLAN_ONE_SM) && !d->out_f16 && !d->wgt_clip_rows && block_n == 256 && (kchunk == 64 || kchunk == 32) &&
+  const bool two_sm_auto = !no_two_sm_env && !chained && !d->in_f16 && !(d->flags & VSB_PLAN_ONE_SM) && !d->out_f16 && !d->wgt_clip_rows && block_n == 256 && (kchunk == 64 || kchunk == 32) &&
                            total_chunks >= 8 && p.total_tiles / p.n_tiles >= 16;
   if (((d->flags & (VSB_PLAN_TWO_SM | VSB_PLAN_TWO_SM_RESIDENT)) || two_sm_auto) && !d->out_f16 && !d->wgt_clip_rows && (kchunk == 64 || kchunk == 32) && !b_resident &&
       block_n % 16 == 0 && block_n >= 32 && epi_warps == 8 && p.total_tiles / p.n_tiles >= 2) {

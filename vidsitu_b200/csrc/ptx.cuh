@@ -277,6 +277,11 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// the same with IEEE-half operands (A / B format 0)
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

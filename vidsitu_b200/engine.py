@@ -350,7 +350,7 @@ class ClipEngine:
             return None
 
     def _conv(self, cs: ConvSpec, x: Act, out: Act, residual: Optional[Act] = None, relu: Optional[bool] = None,
-              reverse: bool = False, chain: Optional[dict] = None):
+              reverse: bool = False, chain: Optional[dict] = None, out_f16: bool = False):
         """Plans one conv launch and appends it to the trunk.  `chain` (tile-granular chaining, _chain_kwargs):
         ConvPlan keywords tile_signal / tile_wait; the launch is then returned instead of appended (the caller
         emits producer and consumer as one trunk op)."""
@@ -366,7 +366,7 @@ class ClipEngine:
             tune.update(chain)
         relu = cs.relu if relu is None else relu
         wt = self._tensor(cs.key + ".weight")
-        plan = self._window_plan(cs, x, out, residual, relu, wt, rev_flag=rev_flag) if not chain else None
+        plan = self._window_plan(cs, x, out, residual, relu, wt, rev_flag=rev_flag) if not (chain or out_f16) else None
         j = self._group_factor(cs, x, out, residual) if plan is None else 0
         if chain and j > 1:
             raise VsbError(f"{cs.key}: tile chaining is for ungrouped layers")
@@ -393,7 +393,9 @@ class ClipEngine:
             w = self._memo((cs.key, "plain", x.c, out.c), lambda: self._up(pack_conv_weight(wt, x.c, out.c, self.tdt)))
             scale, bias = self._sb(cs, out.c)
             plan = ConvPlan(self.dtype, x, w, out.c, cs.kernel, cs.stride, cs.pad, None, scale, bias, out, residual,
-                            relu, **tune)
+                            relu, out_f16=out_f16, **tune)
+        if out_f16 and (j > 1 or self.dtype != VSB_BF16 or residual is not None):
+            raise VsbError(f"{cs.key}: half outputs are for plain bf16-path convs without residual")
         self._keep.append(plan)
         m = out.pixels
         es = 2 if self.dtype == VSB_BF16 else 4
@@ -518,7 +520,7 @@ class ClipEngine:
         return y
 
     def _fused_stem(self, p: int, pitch: Optional[int]) -> Optional[Act]:
-        """[1,7,7] stems with 64 output channels (Slow pathway, Slow-only, C2D): conv + BN + ReLU + max-pool as ONE
+        """[1,7,7] / [5,7,7] stems with 64 output channels (Slow pathway, Slow-only, C2D / I3D): conv + BN + ReLU + max-pool as ONE
         kernel (vsb_stem_pool_*, stem_pool_sm100.cu) - the conv output never reaches HBM.  Returns the pooled
         activation, or None when the stem is outside the kernel's domain (then conv and pool run separately)."""
         st = self.spec.stems[p]
@@ -527,22 +529,29 @@ class ClipEngine:
             return None
         if str(self._tune(cs.key).get("fuse_stem", os.environ.get("VSB_FUSE_STEM", "1"))) not in ("1", "True"):
             return None
-        if (tuple(cs.kernel) != (1, 7, 7) or tuple(cs.stride) != (1, 2, 2) or tuple(cs.pad) != (0, 3, 3) or cs.cout != 64
+        kt = cs.kernel[0]
+        if (kt not in (1, 5) or tuple(cs.kernel[1:]) != (7, 7) or tuple(cs.stride) != (1, 2, 2)
+                or tuple(cs.pad) != (kt // 2, 3, 3) or cs.cout != 64
                 or cs.cin != 3 or tuple(st.pool_kernel) != (1, 3, 3) or tuple(st.pool_stride) != (1, 2, 2)
                 or tuple(st.pool_pad) != (0, 1, 1) or cs.has_bias):
             return None
         x0 = self.input_sets[0][p]
         n, t = x0.n, x0.t
+        if kt == 5 and (t < 3 or (t > 8 and t % 8)):
+            return None
 
         def make():
-            w = self._tensor(cs.key + ".weight")                     # [64, 3, 1, 7, 7]
-            q = torch.zeros((64, 7, 8, 4), dtype=torch.float32)
-            q[:, :, :7, :3] = w[:, :, 0].permute(0, 2, 3, 1)         # [co, kh, kw, c]
+            w = self._tensor(cs.key + ".weight")                     # [64, 3, kt, 7, 7]
+            order = (0,) if kt == 1 else (0, 2, 1, 4, 3)             # the kernel multiplies taps (2,1), (4,3) as pairs
+            q = torch.zeros((len(order), 64, 7, 8, 4), dtype=torch.float32)
+            for i, k in enumerate(order):
+                q[i, :, :, :7, :3] = w[:, :, k].permute(0, 2, 3, 1)  # [co, kh, kw, c]
             return self._up(q.to(self.tdt))
         wq = self._memo((cs.key, "stem_pool"), make)
         scale, bias = self._sb(cs, 64)
         y = self._alloc(n, t, self.crop // 4, self.crop // 4, 64, pitch=pitch, min_c=16)
-        plans = [ops.StemPoolPlan(inputs[p], self.x_off, wq, scale, bias, y, self.crop) for inputs in self.input_sets]
+        plans = [ops.StemPoolPlan(inputs[p], self.x_off, wq, scale, bias, y, self.crop, kt=kt)
+                 for inputs in self.input_sets]
         self._keep += plans
         name = cs.key + "+pool"
         self.op_bytes[name] = 2.0 * (x0.pixels * 4 + y.pixels * 64)
@@ -765,12 +774,16 @@ class ClipEngine:
 
     def _nonlocal(self, x: Act, nl: NonlocalSpec, out_pitch: Optional[int]) -> Act:
         n = x.n
-        theta = self._alloc(n, x.t, x.h, x.w, nl.dim_inner)
-        self._conv(nl.theta, x, theta)
         if nl.pool is not None:
             xp = self._maxpool(nl.prefix + ".pool", x, nl.pool, nl.pool, (0, 0, 0))
         else:
             xp = x
+        # tensor-core route: theta and phi are written (and multiplied) as IEEE half - they enter the exponent of the
+        # softmax, where their bf16 rounding would be a relative error of every attention weight
+        half = (self._nl_gemm_ok(nl, self._store(nl.dim_inner), xp.t * xp.h * xp.w)
+                and self._tune(nl.prefix).get("nl_f16", True) is not False)
+        theta = self._alloc(n, x.t, x.h, x.w, nl.dim_inner)
+        self._conv(nl.theta, x, theta, out_f16=half)
         phi = self._alloc(n, xp.t, xp.h, xp.w, nl.dim_inner)
         if self.dtype == VSB_BF16:
             # the tensor-core route reads phi_i as a weight matrix of round_up(keys, 16) rows: slack after the last clip
@@ -778,13 +791,13 @@ class ClipEngine:
             phi = Act(self._pool.take(phi.pixels * phi.pitch + 16 * phi.pitch), n, xp.t, xp.h, xp.w, phi.c, phi.pitch, 0,
                       phi.c_real)
         g = self._alloc(n, xp.t, xp.h, xp.w, nl.dim_inner)
-        self._conv(nl.phi, xp, phi)
+        self._conv(nl.phi, xp, phi, out_f16=half)
         self._conv(nl.g, xp, g)
         if xp is not x:
             self._free(xp)
         att = self._alloc(n, x.t, x.h, x.w, nl.dim_inner)
         tq, tk = x.t * x.h * x.w, xp.t * xp.h * xp.w
-        if not self._nonlocal_gemms(nl, theta, phi, g, att, tq, tk):
+        if not self._nonlocal_gemms(nl, theta, phi, g, att, tq, tk, half):
             self.trunk_ops.append((nl.prefix + ".attention",
                                    ops.nonlocal_attention_call(theta, phi, g, att, nl.softmax, self.dtype),
                                    4.0 * n * tq * tk * nl.dim_inner))
@@ -795,25 +808,33 @@ class ClipEngine:
             self._free(a)
         return y
 
-    def _nonlocal_gemms(self, nl: NonlocalSpec, theta: Act, phi: Act, g: Act, att: Act, tq: int, tk: int) -> bool:
-        """The two einsums of Nonlocal.forward (nonlocal_helper.py:123-141) on the tensor cores: per clip,
-        scores_i = theta_i . phi_i^T is a 1x1x1 conv of theta_i whose WEIGHTS are phi_i ([keys, c], the softmax
-        scale c^-1/2 - or 1/keys - in the epilogue), vsb_score_rows normalises the rows and zeroes the K padding,
-        and out_i = P_i . g_i is a 1x1x1 conv of P_i whose weights are g_i^T ([c, keys], vsb_transpose_pad).
-        Returns False when the block is outside this route (fp32 mode, odd shapes): the CUDA-core kernel runs."""
+    def _nl_gemm_ok(self, nl: NonlocalSpec, c: int, tk: int) -> bool:
+        """Is this non-local block inside the tensor-core route (_nonlocal_gemms)?"""
         if self.dtype != VSB_BF16 or self._tune(nl.prefix).get("nl_gemm", True) is False:
             return False
-        c = theta.c
-        dense = all(a.pitch == a.c and a.c_off == 0 for a in (theta, phi, g, att))
-        if not dense or c % 64 or phi.c != c or g.c != c or att.c != c or tk % 2:
+        if c % 64 or tk % 2:
             return False
         if not nl.softmax:
             # "dot_product" instantiation: no VidSitu config places such a block (Kinetics_c2_SLOW_8x8_R50.yaml has
             # none), so the batched route was never measured with it - it stays on the CUDA-core kernel
             return False
-        if tk < 128:
-            # few keys (small crops): bf16 probabilities do not average out (max error 0.0100 vs 0.0070 of the feature
-            # scale on the crop-64 fixture) and the CUDA-core kernel costs nothing at this size
+        # few keys (small crops): bf16 probabilities do not average out (max error 0.0100 vs 0.0070 of the feature
+        # scale on the crop-64 fixture) and the CUDA-core kernel costs nothing at this size
+        return tk >= 128
+
+    def _nonlocal_gemms(self, nl: NonlocalSpec, theta: Act, phi: Act, g: Act, att: Act, tq: int, tk: int,
+                        half: bool = False) -> bool:
+        """The two einsums of Nonlocal.forward (nonlocal_helper.py:123-141) on the tensor cores: per clip,
+        scores_i = theta_i . phi_i^T is a 1x1x1 conv of theta_i whose WEIGHTS are phi_i ([keys, c], the softmax
+        scale c^-1/2 - or 1/keys - in the epilogue), vsb_score_rows normalises the rows and zeroes the K padding,
+        and out_i = P_i . g_i is a 1x1x1 conv of P_i whose weights are g_i^T ([c, keys], vsb_transpose_pad).
+        `half`: theta and phi hold IEEE half (vsb_conv_desc.in_f16).
+        Returns False when the block is outside this route (fp32 mode, odd shapes): the CUDA-core kernel runs."""
+        c = theta.c
+        dense = all(a.pitch == a.c and a.c_off == 0 for a in (theta, phi, g, att))
+        if not self._nl_gemm_ok(nl, c, tk) or not dense or phi.c != c or g.c != c or att.c != c:
+            if half:
+                raise VsbError(f"{nl.prefix}: theta / phi were planned as half but the block left the tensor-core route")
             return False
         n = theta.n
         kc, kp = round_up(tk, 16), round_up(tk, 64)
@@ -828,7 +849,7 @@ class ClipEngine:
         # one launch per product: clip i's weight matrix starts tk (resp. c) rows after clip i-1's
         plan_s = ConvPlan(self.dtype, theta, phi.buf, kc, (1, 1, 1), (1, 1, 1), (0, 0, 0), None, s_scale, s_bias,
                           Act(scores, n, t, h, w, kc, kp), None, False, out_f16=True,   # half scores: 11 mantissa bits into exp()
-                          wgt_clip_rows=tk)
+                          wgt_clip_rows=tk, in_f16=half)
         plan_y = ConvPlan(self.dtype, Act(scores, n, t, h, w, kp, kp), g_t, c, (1, 1, 1), (1, 1, 1), (0, 0, 0), None,
                           y_scale, y_bias, att, None, False, wgt_clip_rows=c)
         self._keep += [plan_s, plan_y, s_scale, s_bias, y_scale, y_bias, scores, g_t]

@@ -49,7 +49,7 @@ class ConvDesc(C.Structure):
         ("st2", C.c_int), ("sh2", C.c_int), ("sw2", C.c_int),
         ("epi_n", C.c_int), ("epi_bufs", C.c_int), ("flags", C.c_int), ("out_f16", C.c_int), ("wgt_clip_rows", C.c_int),
         ("tile_signal", C.c_void_p), ("tile_wait", C.c_void_p), ("tile_wait_count", C.c_int),
-        ("grid_limit", C.c_int),
+        ("grid_limit", C.c_int), ("in_f16", C.c_int),
     ]
 
 
@@ -80,6 +80,7 @@ class StemPoolDesc(C.Structure):
         ("wgt", C.c_void_p), ("scale", C.c_void_p), ("bias", C.c_void_p),
         ("out", C.c_void_p),
         ("out_pitch", C.c_int),
+        ("kt", C.c_int), ("t", C.c_int),
     ]
 
 

@@ -161,7 +161,8 @@ class ConvPlan:
                  kw_ranges: Optional[Sequence[Sequence[int]]] = None, x2: Optional[Act] = None,
                  stride2: Sequence[int] = (1, 1, 1), epi_n: int = 0, epi_bufs: int = 0, flags: int = 0, out_f16: bool = False,
                  wgt_clip_rows: int = 0, tile_signal: Optional[torch.Tensor] = None,
-                 tile_wait: Optional[torch.Tensor] = None, tile_wait_count: int = 0, grid_limit: int = 0):
+                 tile_wait: Optional[torch.Tensor] = None, tile_wait_count: int = 0, grid_limit: int = 0,
+                 in_f16: bool = False):
         _require_cuda(x.buf, wgt, scale, bias, out.buf, residual.buf if residual is not None else None,
                       x2.buf if x2 is not None else None, tile_signal, tile_wait)
         pad_hi = pad_lo if pad_hi is None else pad_hi
@@ -195,6 +196,7 @@ class ConvPlan:
         d.tile_wait = tile_wait.data_ptr() if tile_wait is not None else None
         d.tile_wait_count = int(tile_wait_count)
         d.grid_limit = int(grid_limit)
+        d.in_f16 = int(in_f16)
         k_per_tap_row = x.c * d.kw
         if kw_ranges is not None:
             if len(kw_ranges) != d.kw or d.kw > 8:
@@ -323,12 +325,13 @@ class StemPoolPlan:
     """One planned fused [1,7,7] stem (vsb_stem_pool_*): conv + frozen BN + ReLU + 1x3x3/s2 max-pool of the packed
     bf16 frames in one kernel (stem_helper.py:157-178); `out` receives the pooled [frames, h/4, w/4, 64] channels."""
 
-    def __init__(self, x: Act, x_off: int, wgt: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, out: Act, w: int):
+    def __init__(self, x: Act, x_off: int, wgt: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, out: Act, w: int,
+                 kt: int = 1):
         _require_cuda(x.buf, wgt, scale, bias, out.buf)
         if x_off != 3 or x.pitch != 4 or x.c_off:
             raise VsbError("fused stem: input must be the packed 4-channel frames with a 3-pixel left border")
-        if wgt.dtype != torch.bfloat16 or wgt.numel() != 64 * 7 * 32 or not wgt.is_contiguous():
-            raise VsbError("fused stem: weights must be contiguous bf16 [64, 7, 8, 4]")
+        if wgt.dtype != torch.bfloat16 or wgt.numel() != kt * 64 * 7 * 32 or not wgt.is_contiguous():
+            raise VsbError("fused stem: weights must be contiguous bf16 [kt * 64, 7, 8, 4]")
         for t in (scale, bias):
             if t.dtype != torch.float32 or t.numel() != 64 or not t.is_contiguous():
                 raise VsbError("fused stem: scale / bias must be contiguous float32 [64]")
@@ -339,11 +342,12 @@ class StemPoolPlan:
         d.frames, d.h, d.w, d.w_buf = x.n * x.t, x.h, w, x.w
         d.wgt, d.scale, d.bias = wgt.data_ptr(), scale.data_ptr(), bias.data_ptr()
         d.out, d.out_pitch = out.ptr, out.pitch
+        d.kt, d.t = kt, x.t
         self._keep = (x.buf, wgt, scale, bias, out.buf)
         self._h = C.c_void_p()
         self._lib = _l.load()
         check(self._lib.vsb_stem_pool_plan_create(C.byref(d), C.byref(self._h)), "vsb_stem_pool_plan_create")
-        self.flops = 2.0 * d.frames * (d.h // 2) * (w // 2) * 64 * 7 * 32
+        self.flops = 2.0 * d.frames * (d.h // 2) * (w // 2) * 64 * 7 * 32 * kt
 
     def run(self) -> None:
         check(self._lib.vsb_stem_pool_run(self._h, _stream_ptr()), "vsb_stem_pool_run")
