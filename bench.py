@@ -417,7 +417,8 @@ def main():
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "cpu_baseline_note": None if cpu_baseline is not None else "measured on rank 0 at N=1 only (see --impl reference)",
-            "gpu_baseline": gpu_baseline, "fused_blocks": len(getattr(eng, "fused_blocks", [])), "clocks": clocks,
+            "gpu_baseline": gpu_baseline, "fused_blocks": len(getattr(eng, "fused_blocks", [])),
+            "fused_stems": list(getattr(eng, "fused_stems", [])), "clocks": clocks,
         }))
     if world > 1:
         dist.destroy_process_group()

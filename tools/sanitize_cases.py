@@ -38,6 +38,43 @@ for name in ("w_sp3_64_64_7_wrap", "w_g_sp3_32_32_J2", "w_stem_fast_J4_tsc_T2", 
 fused = {c[0]: c for c in GF.CASES}
 for name in ("tiny_7x7", "crop64_s4", "walk3_grid3", "pitched"):
     report("fused/" + name, GF.run_case(fused[name]))
+# fused stems (kt = 1 and the temporal-scatter kt = 5 kernel) and a whole forward through a clip program
+from vidsitu_b200 import ops as _ops
+from vidsitu_b200.lib import VSB_BF16 as _BF16
+for kt, t in ((1, 2), (5, 8)):
+    n, crop = 1, 64
+    g = torch.Generator().manual_seed(kt)
+    fr = torch.randint(0, 256, (n, t, crop, crop, 3), dtype=torch.uint8, generator=g).cuda()
+    xin = _ops.Act(torch.zeros(n * t * crop * (crop + 16) * 4, dtype=torch.bfloat16, device="cuda"), n, t, crop, crop + 16, 4, 4, c_real=3)
+    _ops.pack_frames(fr, list(range(t)), [0.45] * 3, [0.225] * 3, xin, _BF16, False, 3)
+    w = (torch.randn((64, 3, kt, 7, 7), generator=g) * 0.1).cuda()
+    order = (0,) if kt == 1 else (0, 2, 1, 4, 3)
+    q = torch.zeros((len(order), 64, 7, 8, 4), device="cuda")
+    for i, k in enumerate(order):
+        q[i, :, :, :7, :3] = w[:, :, k].permute(0, 2, 3, 1)
+    out = _ops.Act(torch.zeros(n * t * 16 * 16 * 64, dtype=torch.bfloat16, device="cuda"), n, t, 16, 16, 64, 64)
+    plan = _ops.StemPoolPlan(xin, 3, q.bfloat16().contiguous(), torch.ones(64, device="cuda"), torch.zeros(64, device="cuda"), out, crop, kt=kt)
+    plan.run()
+    torch.cuda.synchronize()
+    x = xin.nthwc()[:, :, :, 3:3 + crop, :].permute(0, 4, 1, 2, 3).float()
+    y = torch.relu(torch.nn.functional.conv3d(x, w.bfloat16().float(), None, (1, 2, 2), (kt // 2, 3, 3))).bfloat16().float()
+    ref = torch.nn.functional.max_pool3d(y, (1, 3, 3), (1, 2, 2), (0, 1, 1)).permute(0, 2, 3, 4, 1)
+    err = float((out.buf.view(n, t, 16, 16, 64).float() - ref).abs().max())
+    report(f"stem_pool/kt{kt}", {"ok": err <= 0.05 * float(ref.abs().max()), "max_abs_err": err})
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from common import build_model, synthetic_frames
+model, cfg, _ = build_model("slow_fast_nl_r50_8x8", seed=1, crop=64)
+model = model.cuda()
+eng = model._engine(1, torch.device("cuda"))
+eng.load_frames(synthetic_frames(1, 32, 64, seed=2).cuda())
+eng.run()
+torch.cuda.synchronize()
+want = eng.feats.clone()
+prog = eng.build_program()
+eng.feats.zero_()
+prog.run()
+torch.cuda.synchronize()
+report("program/sf50_crop64", {"ok": bool(torch.equal(eng.feats, want)), "max_abs_err": float((eng.feats - want).abs().max())})
 if "--mem" in sys.argv:
     for k, v in G.run_mem_checks().items():
         report("mem/" + k, v)
