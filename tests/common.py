@@ -53,3 +53,34 @@ def torch_bf16_comparator(model, cfg, frames_cpu: torch.Tensor):
           for x in O.clips_from_frames(frames_cpu, cfg.sf_mdl)]
     _, pooled, logits = O.sfbase_forward(sd, cfg.sf_mdl, xs)
     return pooled.float().cpu().numpy(), logits.float().cpu().numpy()
+
+
+def synthetic_image(h: int, w: int, kind: str = "noisy", seed: int = 0):
+    """uint8 [h, w, 3]: smooth colour gradients, optionally with noise (so that every AC coefficient is exercised)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([128 + 100 * np.sin(xx / 9.0 + yy / 17.0), 128 + 90 * np.cos(xx / 13.0 - yy / 7.0),
+                     (xx * 3 + yy * 5) % 256], -1).astype(np.float64)
+    if kind == "noisy":
+        base = base + rng.normal(0, 40, base.shape)
+    return np.clip(base, 0, 255).astype(np.uint8)
+
+
+# (height, width, quality, PIL subsampling: 0 = 4:4:4, 1 = 4:2:2, 2 = 4:2:0, kind) - odd sizes, partial MCUs, the
+# ffmpeg-like case (4:2:0, high quality, 16:9)
+JPEG_CASES = [(64, 80, 95, 2, "smooth"), (77, 53, 90, 2, "noisy"), (48, 64, 75, 0, "noisy"), (50, 70, 85, 1, "smooth"),
+              (120, 160, 98, 2, "noisy"), (33, 47, 60, 2, "noisy"), (16, 16, 100, 2, "noisy"), (90, 122, 92, 1, "noisy"),
+              (360, 640, 96, 2, "noisy"), (240, 426, 93, 2, "smooth")]
+
+
+def jpeg_bytes(h: int, w: int, quality: int, subsampling: int, kind: str, seed: int = 0, gray: bool = False) -> bytes:
+    import io
+    from PIL import Image
+    a = synthetic_image(h, w, kind, seed)
+    buf = io.BytesIO()
+    if gray:
+        Image.fromarray(a[..., 0]).save(buf, "JPEG", quality=quality)
+    else:
+        Image.fromarray(a).save(buf, "JPEG", quality=quality, subsampling=subsampling)
+    return buf.getvalue()

@@ -188,3 +188,57 @@ def test_caffe2_checkpoint_loads_into_a_sub_batchnorm_model(tmp_path):
         else:
             assert np.array_equal(sd[k].numpy(), a), k
     assert checked > 200
+
+
+# ---------------------------------------------------------------- frame ingest oracle against Pillow
+def _pil_rgb(data: bytes):
+    import io
+    from PIL import Image
+    return np.array(Image.open(io.BytesIO(data)).convert("RGB"))
+
+
+@pytest.mark.parametrize("case", __import__("common").JPEG_CASES)
+def test_jpeg_decode_oracle_is_bit_exact_with_pillow(case):
+    """oracle/image_oracle.py::decode_jpeg (Huffman + islow IDCT + fancy upsampling + YCbCr tables) equals
+    `Image.open(..).convert("RGB")` (libjpeg-turbo) bit for bit: 4:4:4 / 4:2:2 / 4:2:0, odd sizes, partial MCUs."""
+    from common import jpeg_bytes
+    from oracle import image_oracle as IO
+    data = jpeg_bytes(*case)
+    assert np.array_equal(IO.decode_jpeg(data), _pil_rgb(data))
+
+
+def test_jpeg_decode_oracle_grayscale_restart_markers_and_refusals():
+    import io
+    from PIL import Image
+    from common import jpeg_bytes, synthetic_image
+    from oracle import image_oracle as IO
+    data = jpeg_bytes(40, 56, 90, 2, "noisy", gray=True)
+    assert np.array_equal(IO.decode_jpeg(data), _pil_rgb(data))
+    buf = io.BytesIO()
+    Image.fromarray(synthetic_image(70, 90, "noisy", 3)).save(buf, "JPEG", quality=88, subsampling=2, restart_marker_blocks=3)
+    assert np.array_equal(IO.decode_jpeg(buf.getvalue()), _pil_rgb(buf.getvalue()))
+    buf = io.BytesIO()
+    Image.fromarray(synthetic_image(64, 64, "noisy", 4)).save(buf, "JPEG", quality=88, progressive=True)
+    with pytest.raises(IO.JpegUnsupported):
+        IO.decode_jpeg(buf.getvalue())
+
+
+@pytest.mark.parametrize("shape", [(360, 640), (240, 320), (224, 224), (80, 100), (500, 333), (224, 640), (37, 53)])
+def test_resize_oracle_is_bit_exact_with_pillow(shape):
+    """resize_bicubic_u8 == `img.resize((224, 224))` (Pillow's default BICUBIC, fixed-point two-pass)."""
+    from PIL import Image
+    from common import synthetic_image
+    from oracle import image_oracle as IO
+    img = synthetic_image(*shape, "noisy", seed=shape[0])
+    assert np.array_equal(IO.resize_bicubic_u8(img, 224, 224), np.array(Image.fromarray(img).resize((224, 224))))
+
+
+def test_read_img_oracle_matches_the_reference_reader(tmp_path):
+    """decode + resize == VsituDS.read_img (dat_loader.py:183-191) on a file, through the package's host reader."""
+    from common import jpeg_bytes
+    from oracle import image_oracle as IO
+    from vidsitu_b200 import frames_io
+    data = jpeg_bytes(360, 640, 96, 2, "noisy", seed=9)
+    p = tmp_path / "f.jpg"
+    p.write_bytes(data)
+    assert np.array_equal(IO.read_img(data), frames_io.read_img(p))
