@@ -313,6 +313,30 @@ int vsb_nthwc_to_ncthw_f32(const void* in, int n, int thw, int c, int in_pitch, 
 int vsb_ncthw_f32_to_nthwc(const float* in, int n, int c, long long thw, int w, void* out, int c_pad, int out_w,
                            int x_off, int dtype, void* stream);
 
+/* ------------------------------------------------------------- frame ingest (ABI v7)
+ * Replaces VsituDS.read_img (vidsitu_code/dat_loader.py:183-191):
+ *     Image.open(path).convert("RGB").resize((224, 224))  ->  uint8 [224, 224, 3]
+ * with the pixels produced ON THE DEVICE, bit-identical to Pillow / libjpeg(-turbo): the host only parses the headers
+ * and decodes the (inherently sequential) Huffman segment into quantised coefficient blocks; dequantisation, the
+ * "islow" integer IDCT, fancy chroma upsampling, YCbCr -> RGB and Pillow's fixed-point BICUBIC resampling are kernels.
+ * Decoded: baseline / extended-sequential Huffman JPEGs, 8 bit, grayscale or YCbCr 4:4:4 / 4:2:2 / 4:2:0, with or
+ * without restart markers (the dataset's frames are ffmpeg MJPEG 4:2:0, prep_data/dwn_yt.py:229-250).  Anything else
+ * (progressive, arithmetic coding, CMYK, other sampling) is refused with VSB_ERR_INVALID: the caller decodes such a
+ * file on the host.
+ * A decoder owns its workspaces (pinned host staging, device planes) for frames of up to max_width x max_height; it is
+ * not thread-safe - one decoder per host thread.  `out` is device memory, [out_h, out_w, 3] uint8; the call returns once
+ * the host part is done, the device part is enqueued on `stream`.                                              */
+typedef struct vsb_jpeg_decoder vsb_jpeg_decoder;
+int vsb_jpeg_info(const uint8_t* jpeg, unsigned long long bytes, int* width, int* height, int* components, int* h_samp,
+                  int* v_samp);
+int vsb_jpeg_decoder_create(int max_width, int max_height, vsb_jpeg_decoder** dec);
+void vsb_jpeg_decoder_destroy(vsb_jpeg_decoder* dec);
+int vsb_jpeg_decode_resize(vsb_jpeg_decoder* dec, const uint8_t* jpeg, unsigned long long bytes, uint8_t* out, int out_h,
+                           int out_w, void* stream);
+/* the resampling alone: device uint8 [h, w, 3] -> [out_h, out_w, 3], == PIL.Image.resize((out_w, out_h)) */
+int vsb_resize_bicubic_u8(vsb_jpeg_decoder* dec, const uint8_t* in, int h, int w, uint8_t* out, int out_h, int out_w,
+                          void* stream);
+
 /* ------------------------------------------------------------- clip programs (ABI v7)
  * The model-level entry points: ONE handle for the whole forward of SFBase.forward_encoder (+ proj_head) at a
  * fixed batch size (vidsitu_code/mdl_sf_base.py:182-216; SlowFast.forward, SlowFast/slowfast/models/

@@ -1,0 +1,88 @@
+"""Frame ingest on the GPU (vsb_jpeg_*, csrc/jpeg_ingest.cu): bit-exact against Pillow - the
+reference's reader `Image.open(p).convert("RGB").resize((224, 224))` (dat_loader.py:183-191) - and against the numpy
+oracle, on 4:4:4 / 4:2:2 / 4:2:0 / grayscale files, odd sizes, restart markers; refusals are loud."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from common import JPEG_CASES, jpeg_bytes, synthetic_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _pil_read_img(data: bytes, size: int = 224):
+    from PIL import Image
+    return np.array(Image.open(io.BytesIO(data)).convert("RGB").resize((size, size)))
+
+
+@pytest.fixture(scope="module")
+def decoder():
+    from vidsitu_b200.jpeg import JpegDecoder
+    return JpegDecoder(1920, 1088)
+
+
+@pytest.mark.parametrize("case", JPEG_CASES)
+def test_decode_resize_is_bit_exact_with_the_reference_reader(decoder, case):
+    from oracle import image_oracle as IO
+    data = jpeg_bytes(*case)
+    out = torch.empty((224, 224, 3), dtype=torch.uint8, device="cuda")
+    decoder.decode_resize(data, out)
+    got = out.cpu().numpy()
+    assert np.array_equal(got, _pil_read_img(data))
+    assert np.array_equal(got, IO.read_img(data))
+
+
+def test_native_size_decode_grayscale_and_restart_markers(decoder):
+    from PIL import Image
+    for data in (jpeg_bytes(40, 56, 90, 2, "noisy", gray=True), jpeg_bytes(224, 224, 97, 2, "noisy", seed=5)):
+        w, h = Image.open(io.BytesIO(data)).size
+        out = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+        decoder.decode_resize(data, out)           # no resampling: the decoder's pixels themselves
+        assert np.array_equal(out.cpu().numpy(), np.array(Image.open(io.BytesIO(data)).convert("RGB")))
+    buf = io.BytesIO()
+    Image.fromarray(synthetic_image(170, 290, "noisy", 3)).save(buf, "JPEG", quality=88, subsampling=2, restart_marker_blocks=3)
+    out = torch.empty((224, 224, 3), dtype=torch.uint8, device="cuda")
+    decoder.decode_resize(buf.getvalue(), out)
+    assert np.array_equal(out.cpu().numpy(), _pil_read_img(buf.getvalue()))
+
+
+def test_back_to_back_frames_of_different_sizes(decoder):
+    """The decoder's staging slots and resampling tables are reused across calls without a synchronisation by the
+    caller: decode many frames of alternating sizes, check them all at the end."""
+    cases = [(360, 640, 96, 2, "noisy"), (240, 426, 93, 2, "smooth"), (360, 640, 90, 2, "smooth"), (120, 160, 98, 2, "noisy")] * 3
+    datas = [jpeg_bytes(*c, seed=i) for i, c in enumerate(cases)]
+    out = torch.empty((len(datas), 224, 224, 3), dtype=torch.uint8, device="cuda")
+    for i, d in enumerate(datas):
+        decoder.decode_resize(d, out[i])
+    got = out.cpu().numpy()
+    for i, d in enumerate(datas):
+        assert np.array_equal(got[i], _pil_read_img(d)), i
+
+
+@pytest.mark.parametrize("shape", [(360, 640), (224, 640), (500, 333), (37, 53), (224, 224)])
+def test_resize_alone_is_bit_exact_with_pillow(decoder, shape):
+    from PIL import Image
+    img = synthetic_image(*shape, "noisy", seed=shape[1])
+    out = torch.empty((224, 224, 3), dtype=torch.uint8, device="cuda")
+    decoder.resize(torch.from_numpy(img).cuda(), out)
+    assert np.array_equal(out.cpu().numpy(), np.array(Image.fromarray(img).resize((224, 224))))
+
+
+def test_unsupported_files_are_refused_loudly(decoder):
+    from PIL import Image
+    from vidsitu_b200.lib import VsbError
+    out = torch.empty((224, 224, 3), dtype=torch.uint8, device="cuda")
+    buf = io.BytesIO()
+    Image.fromarray(synthetic_image(64, 64, "noisy", 4)).save(buf, "JPEG", quality=88, progressive=True)
+    with pytest.raises(VsbError, match="baseline"):
+        decoder.decode_resize(buf.getvalue(), out)
+    with pytest.raises(VsbError, match="not a JPEG"):
+        decoder.decode_resize(b"\x89PNG\r\n\x1a\n" + bytes(64), out)
+    good = jpeg_bytes(64, 80, 95, 2, "smooth")
+    with pytest.raises(VsbError):
+        decoder.decode_resize(good[: len(good) // 3], out)          # truncated inside the headers / tables
+    with pytest.raises(VsbError, match="decoder was created for"):
+        from vidsitu_b200.jpeg import JpegDecoder
+        JpegDecoder(32, 32).decode_resize(good, out)

@@ -351,3 +351,23 @@ def test_program_handle_host_side_behaviour(tmp_path):
     assert b"not a vidsitu_b200 program file" in lib.vsb_last_error()
     out = C.c_void_p()
     assert lib.vsb_program_load(str(tmp_path / "missing").encode(), None, 0, C.byref(out)) != 0 and not out.value
+
+
+def test_jpeg_header_parser_needs_no_gpu():
+    """vsb_jpeg_info (the host half of the GPU frame ingest): geometry and sampling of the files it accepts, a
+    message for the ones it refuses."""
+    import io
+    from PIL import Image
+    from common import jpeg_bytes, synthetic_image
+    from vidsitu_b200.jpeg import jpeg_info
+    from vidsitu_b200.lib import VsbError
+    assert jpeg_info(jpeg_bytes(77, 53, 90, 2, "noisy")) == (53, 77, 3, 2, 2)
+    assert jpeg_info(jpeg_bytes(50, 70, 85, 1, "smooth")) == (70, 50, 3, 2, 1)
+    assert jpeg_info(jpeg_bytes(48, 64, 75, 0, "noisy")) == (64, 48, 3, 1, 1)
+    assert jpeg_info(jpeg_bytes(40, 56, 90, 2, "noisy", gray=True))[:3] == (56, 40, 1)
+    buf = io.BytesIO()
+    Image.fromarray(synthetic_image(64, 64, "noisy", 4)).save(buf, "JPEG", quality=88, progressive=True)
+    with pytest.raises(VsbError, match="baseline"):
+        jpeg_info(buf.getvalue())
+    with pytest.raises(VsbError, match="not a JPEG"):
+        jpeg_info(b"GIF89a" + bytes(32))
