@@ -86,3 +86,41 @@ def test_unsupported_files_are_refused_loudly(decoder):
     with pytest.raises(VsbError, match="decoder was created for"):
         from vidsitu_b200.jpeg import JpegDecoder
         JpegDecoder(32, 32).decode_resize(good, out)
+
+
+def test_feature_dump_cli_with_gpu_decode_writes_the_same_files(tmp_path):
+    """tools/extract_features.py --gpu-decode (JPEGs decoded and resized on the device by DeviceVideoLoader) writes
+    byte-identical .npy files to the PIL-in-DataLoader path: the decoded frames are bit-equal, so are the features."""
+    import json
+    import os
+    import sys
+    from PIL import Image
+    from common import ROOT, synthetic_image
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import extract_features as X
+    from vidsitu_b200 import frames_io as F
+    names = ["v_a_seg_0", "v_b_seg_1", "v_c_seg_2"]
+    for vi, v in enumerate(names):
+        d = tmp_path / "frames" / v
+        d.mkdir(parents=True)
+        for ix in range(1, 301):
+            img = synthetic_image(90, 160, "noisy" if ix % 2 else "smooth", seed=vi * 1000 + ix)
+            Image.fromarray(img).save(d / f"{v}_{ix:06d}.jpg", quality=94, subsampling=2)
+    (tmp_path / "split.json").write_text(json.dumps(names))
+    outs = {}
+    for mode in ("host", "gpu"):
+        torch.manual_seed(33)
+        rc = X.main(["--frames-dir", str(tmp_path / "frames"), "--split-file", str(tmp_path / "split.json"),
+                     "--out-dir", str(tmp_path / f"feats_{mode}"), "--mdl-name-used", "m", "--crop", "64",
+                     "--videos-per-batch", "2", "--workers", "0" if mode == "host" else "3"]
+                    + (["--gpu-decode"] if mode == "gpu" else []))
+        assert rc == 0
+        outs[mode] = {v: (tmp_path / f"feats_{mode}" / "m" / f"{v}_feats.npy").read_bytes() for v in names}
+    assert outs["host"] == outs["gpu"]
+    # and the loader's frames themselves equal the host reader's
+    dl = F.DeviceVideoLoader(tmp_path / "frames", names, 32, 2, size=64, videos_per_batch=3, workers=2)
+    (frames, idxs), = list(dl)
+    assert idxs == [0, 1, 2] and dl.host_fallbacks == 0
+    needed = F.needed_frames(32, 2)
+    ref = F.load_video(tmp_path / "frames", names[1], needed, 64)
+    assert torch.equal(frames[1].cpu(), ref)

@@ -26,7 +26,7 @@ from torch.utils.data import DataLoader  # noqa: E402
 from vidsitu_b200 import checkpoint  # noqa: E402
 from vidsitu_b200.config import make_cfg, make_comm  # noqa: E402
 from vidsitu_b200.feat_io import FeatureWriter  # noqa: E402
-from vidsitu_b200.frames_io import VideoFrames, collate_videos, read_vseg_list  # noqa: E402
+from vidsitu_b200.frames_io import DeviceVideoLoader, VideoFrames, collate_videos, read_vseg_list  # noqa: E402
 from vidsitu_b200.sf_base import SFBase  # noqa: E402
 
 
@@ -43,6 +43,9 @@ def main(argv=None) -> int:
     ap.add_argument("--videos-per-batch", type=int, default=8)
     ap.add_argument("--workers", type=int, default=4, help="cfg.train.nwv")
     ap.add_argument("--crop", type=int, default=224)
+    ap.add_argument("--gpu-decode", action="store_true",
+                    help="decode + resize the JPEGs on the GPU (bit-identical to the PIL reader; --workers host threads "
+                         "do the Huffman part) instead of PIL in DataLoader workers")
     args = ap.parse_args(argv)
 
     cfg = make_cfg(args.sf_mdl_name)
@@ -62,19 +65,25 @@ def main(argv=None) -> int:
 
     vsegs = read_vseg_list(args.split_file)
     d = cfg.sf_mdl.DATA
-    ds = VideoFrames(args.frames_dir, vsegs, d.NUM_FRAMES, d.SAMPLING_RATE, d.TARGET_FPS, size=args.crop)
-    dl = DataLoader(ds, batch_size=args.videos_per_batch, shuffle=False, num_workers=args.workers,
-                    collate_fn=collate_videos, pin_memory=True, drop_last=False)
+    if args.gpu_decode:
+        dl = DeviceVideoLoader(args.frames_dir, vsegs, d.NUM_FRAMES, d.SAMPLING_RATE, d.TARGET_FPS, size=args.crop,
+                               videos_per_batch=args.videos_per_batch, workers=max(1, args.workers))
+    else:
+        ds = VideoFrames(args.frames_dir, vsegs, d.NUM_FRAMES, d.SAMPLING_RATE, d.TARGET_FPS, size=args.crop)
+        dl = DataLoader(ds, batch_size=args.videos_per_batch, shuffle=False, num_workers=args.workers,
+                        collate_fn=collate_videos, pin_memory=True, drop_last=False)
     t0 = time.time()
     done = 0
     with FeatureWriter(args.out_dir, args.mdl_name_used) as writer:
         for frames, idxs in dl:
             feats = mdl.extract_video_features(frames.cuda(non_blocking=True))      # [B, 5, D] fp32
+            if args.gpu_decode:
+                torch.cuda.current_stream().synchronize()    # the batch's frame tensor is dropped on the next iteration
             writer.put(feats, [vsegs[i] for i in idxs])
             done += len(idxs)
     dt = time.time() - t0
     print(f"{done} videos ({5 * done} event clips) -> {writer.out_dir} in {dt:.1f} s ({5 * done / max(dt, 1e-9):.1f} clips/s "
-          f"including JPEG decode)")
+          f"including JPEG decode" + (f" on the GPU, {dl.host_fallbacks} files through PIL)" if args.gpu_decode else ")"))
     return 0
 
 

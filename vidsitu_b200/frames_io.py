@@ -93,3 +93,82 @@ class VideoFrames(Dataset):
 def collate_videos(batch):
     frames = torch.stack([b[0] for b in batch])
     return frames, [b[1] for b in batch]
+
+
+# ------------------------------------------------------------------------------------ GPU decode
+class DeviceVideoLoader:
+    """Whole videos decoded ON THE GPU: the counterpart of DataLoader(VideoFrames) for `--gpu-decode`.
+
+    `workers` host threads each own a `jpeg.JpegDecoder` and a CUDA stream; a thread reads the JPEG files of one video,
+    Huffman-decodes them (in the library, outside the GIL) and enqueues IDCT / upsampling / colour conversion / the
+    PIL-exact resize on its stream, straight into the video's uint8 `[total, size, size, 3]` device tensor - no pixel
+    ever crosses PCIe.  Files the GPU path refuses (progressive, CMYK, ...) go through the reference's PIL reader
+    (`read_img`) and are counted in `host_fallbacks`.  Iterating yields `(frames [B, total, size, size, 3] cuda uint8,
+    [video indices])`, ready on the CURRENT stream."""
+
+    def __init__(self, video_frms_tdir, vseg_lst: Sequence[str], num_frames: int, sampling_rate: int, fps: int = 30,
+                 size: int = 224, total: int = VIDEO_FRAMES, videos_per_batch: int = 8, workers: int = 4,
+                 device=None, max_width: int = 1920, max_height: int = 1088):
+        import threading
+        self.tdir = Path(video_frms_tdir)
+        self.vseg_lst = list(vseg_lst)
+        self.size, self.total = int(size), int(total)
+        self.needed = needed_frames(num_frames, sampling_rate, fps, total)
+        self.videos_per_batch = int(videos_per_batch)
+        self.workers = max(1, int(workers))
+        self.device = torch.device(device if device is not None else "cuda")
+        self.max_wh = (int(max_width), int(max_height))
+        self.host_fallbacks = 0
+        self._tls = threading.local()
+        self._lock = threading.Lock()
+
+    def __len__(self) -> int:
+        return (len(self.vseg_lst) + self.videos_per_batch - 1) // self.videos_per_batch
+
+    def _state(self):
+        from .jpeg import JpegDecoder
+        st = getattr(self._tls, "st", None)
+        if st is None:
+            st = (JpegDecoder(self.max_wh[0], self.max_wh[1], self.device), torch.cuda.Stream(self.device))
+            self._tls.st = st
+        return st
+
+    def _decode_video(self, vseg: str, out: torch.Tensor) -> "torch.cuda.Event":
+        from .lib import VsbError
+        dec, stream = self._state()
+        paths = frame_paths(self.tdir, vseg, self.total)
+        with torch.cuda.device(self.device), torch.cuda.stream(stream):
+            for i in self.needed:
+                if not paths[i].exists():
+                    raise AssertionError(f"{paths[i]} doesn't exist")
+                data = paths[i].read_bytes()
+                try:
+                    dec.decode_resize(data, out[i])
+                except VsbError:
+                    out[i].copy_(torch.from_numpy(read_img(paths[i], self.size)), non_blocking=False)
+                    with self._lock:
+                        self.host_fallbacks += 1
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return ev
+
+    def __iter__(self):
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=self.workers) as pool:
+            pending = None
+            for b0 in range(0, len(self.vseg_lst), self.videos_per_batch):
+                idxs = list(range(b0, min(b0 + self.videos_per_batch, len(self.vseg_lst))))
+                frames = torch.zeros((len(idxs), self.total, self.size, self.size, 3), dtype=torch.uint8,
+                                     device=self.device)
+                torch.cuda.current_stream(self.device).synchronize()     # the zero fill precedes the workers' writes
+                futs = [pool.submit(self._decode_video, self.vseg_lst[i], frames[k]) for k, i in enumerate(idxs)]
+                if pending is not None:
+                    yield self._finish(*pending)
+                pending = (frames, idxs, futs)
+            if pending is not None:
+                yield self._finish(*pending)
+
+    def _finish(self, frames, idxs, futs):
+        for f in futs:
+            torch.cuda.current_stream(self.device).wait_event(f.result())
+        return frames, idxs
