@@ -333,6 +333,18 @@ int vsb_jpeg_decoder_create(int max_width, int max_height, vsb_jpeg_decoder** de
 void vsb_jpeg_decoder_destroy(vsb_jpeg_decoder* dec);
 int vsb_jpeg_decode_resize(vsb_jpeg_decoder* dec, const uint8_t* jpeg, unsigned long long bytes, uint8_t* out, int out_h,
                            int out_w, void* stream);
+/* Batched, FULLY on-device variant: the Huffman segments are decoded on the GPU too, one warp per frame (a batch of a
+ * feature-extraction run holds hundreds of independent frames; within a frame the code stream is sequential).  The
+ * host parses headers and stages the file bytes; no coefficient and no pixel crosses PCIe.  jpegs[i] / bytes[i]: the
+ * i-th file in host memory; outs[i]: its device destination, uint8 [out_h, out_w, 3]; status[i] (host) receives VSB_OK
+ * or VSB_ERR_INVALID (refused or corrupt file: its output is untouched and the caller decodes it on the host).  Same
+ * bits as vsb_jpeg_decode_resize.  Workspaces grow on demand and are owned by the handle; the call returns after the
+ * batch has completed on `stream` (the verdicts are part of the result).                                       */
+typedef struct vsb_jpeg_batch vsb_jpeg_batch;
+int vsb_jpeg_batch_create(vsb_jpeg_batch** batch);
+void vsb_jpeg_batch_destroy(vsb_jpeg_batch* batch);
+int vsb_jpeg_batch_decode_resize(vsb_jpeg_batch* batch, const uint8_t* const* jpegs, const unsigned long long* bytes, int n,
+                                 uint8_t* const* outs, int out_h, int out_w, int* status, void* stream);
 /* the resampling alone: device uint8 [h, w, 3] -> [out_h, out_w, 3], == PIL.Image.resize((out_w, out_h)) */
 int vsb_resize_bicubic_u8(vsb_jpeg_decoder* dec, const uint8_t* in, int h, int w, uint8_t* out, int out_h, int out_w,
                           void* stream);

@@ -124,3 +124,35 @@ def test_feature_dump_cli_with_gpu_decode_writes_the_same_files(tmp_path):
     needed = F.needed_frames(32, 2)
     ref = F.load_video(tmp_path / "frames", names[1], needed, 64)
     assert torch.equal(frames[1].cpu(), ref)
+
+
+def test_fully_on_device_batch_decode_is_bit_exact_and_reports_refusals():
+    """vsb_jpeg_batch_*: Huffman on the GPU too (one warp per frame).  A mixed batch - every sampling mode, odd sizes,
+    grayscale, restart markers, plus a progressive file, a truncated file and garbage - against Pillow; the refused
+    ones are reported and leave their outputs untouched."""
+    from PIL import Image
+    from vidsitu_b200.jpeg import JpegBatchDecoder
+    datas = [jpeg_bytes(*c, seed=i) for i, c in enumerate(JPEG_CASES)]
+    datas.append(jpeg_bytes(40, 56, 90, 2, "noisy", gray=True))
+    buf = io.BytesIO()
+    Image.fromarray(synthetic_image(170, 290, "noisy", 3)).save(buf, "JPEG", quality=88, subsampling=2, restart_marker_blocks=3)
+    datas.append(buf.getvalue())
+    n_good = len(datas)
+    buf = io.BytesIO()
+    Image.fromarray(synthetic_image(64, 64, "noisy", 4)).save(buf, "JPEG", quality=88, progressive=True)
+    datas += [buf.getvalue(), datas[4][: len(datas[4]) // 2], b"GIF89a" + bytes(100)]
+    out = torch.full((len(datas), 224, 224, 3), 7, dtype=torch.uint8, device="cuda")
+    dec = JpegBatchDecoder()
+    ok = dec.decode_resize(datas, list(out))
+    assert ok == [True] * n_good + [False] * 3
+    got = out.cpu().numpy()
+    for i in range(n_good):
+        assert np.array_equal(got[i], _pil_read_img(datas[i])), i
+    assert (got[n_good:] == 7).all()
+    # a second, larger batch through the same handle (workspaces grow), frames of one video
+    datas = [jpeg_bytes(360, 640, 95, 2, "noisy" if i % 3 else "smooth", seed=100 + i) for i in range(40)]
+    out = torch.empty((40, 224, 224, 3), dtype=torch.uint8, device="cuda")
+    assert all(dec.decode_resize(datas, list(out)))
+    got = out.cpu().numpy()
+    for i in (0, 7, 39):
+        assert np.array_equal(got[i], _pil_read_img(datas[i])), i

@@ -759,3 +759,561 @@ extern "C" int vsb_resize_bicubic_u8(vsb_jpeg_decoder* dec, const uint8_t* in, i
   VSB_CHECK_ARG((size_t)h * out_w <= dec->max_pixels, "image larger than the decoder's workspace");
   return resize_rgb(dec, in, h, w, out, out_h, out_w, (cudaStream_t)stream);
 }
+
+// ====================================================================================================================
+// Batched, fully-on-device decode: the Huffman segment too.
+//
+// One frame's entropy-coded segment is sequential, but a feature-extraction batch holds hundreds to thousands of
+// independent frames (5 events x 32 frames x videos): ONE WARP PER FRAME walks its bit stream (lane 0 decodes from
+// shared-memory copies of the frame's Huffman tables, the whole warp fetches the tables), a few hundred warps in
+// flight hide each other's latency.  The host only parses headers (tables, geometry) and copies the file bytes to
+// pinned memory; no pixel and no coefficient crosses PCIe.  The pixel stages are the kernels above, launched once per
+// batch over (frame, block / pixel) grids.  Same arithmetic, same bits as Pillow.
+namespace {
+
+struct HuffDev {  // a HuffTable as the device decoder reads it (4-byte aligned)
+  unsigned short look[512];
+  int maxcode[18];
+  int valptr[17];
+  int mincode[17];
+  unsigned char symbols[256];
+};
+
+struct FrameDesc {
+  // entropy decode
+  long long data_off;    // first byte of the entropy-coded segment in the batch's byte buffer
+  long long data_len;    // bytes from there to the end of the file
+  int tab[3][2];         // per component: index of its DC / AC table among the frame's 4 uploaded tables
+  int ncomp, mcux, mcuy, restart;
+  int hs[3], vs[3];
+  long long coef_off[3];  // int16 elements
+  // pixel stages
+  IdctParams ip;
+  ColorParams cp;
+  int qt_base;            // first of the frame's 4 quantisation tables (x 64 entries)
+  long long rgb_off, tmp_off;
+  unsigned char* out;
+  const int* bounds_h;
+  const int* kk_h;
+  const int* bounds_v;
+  const int* kk_v;
+  int ksize_h, ksize_v;
+  int valid;              // 0: refused by the host parser (nothing is launched for it)
+};
+
+struct DevBits {
+  const unsigned char* d;
+  long long n, pos;
+  unsigned long long buf;
+  int bits;
+  bool hit_marker;
+  int fake_bytes;
+  __device__ __forceinline__ void fill() {
+    while (bits <= 56) {
+      unsigned b = 0;
+      if (!hit_marker && pos < n) {
+        b = d[pos];
+        if (b == 0xFF) {
+          const unsigned nx = pos + 1 < n ? d[pos + 1] : 0xD9;
+          if (nx == 0) {
+            pos += 2;
+          } else {
+            hit_marker = true;
+            b = 0;
+            ++fake_bytes;
+          }
+        } else {
+          ++pos;
+        }
+      } else {
+        ++fake_bytes;
+      }
+      buf |= (unsigned long long)b << (56 - bits);
+      bits += 8;
+    }
+  }
+  __device__ __forceinline__ unsigned peek(int k) const { return (unsigned)(buf >> (64 - k)); }
+  __device__ __forceinline__ void drop(int k) {
+    buf <<= k;
+    bits -= k;
+  }
+  __device__ __forceinline__ bool overran() const { return bits < 8 * fake_bytes; }
+};
+
+__device__ __forceinline__ int dev_huff(DevBits& br, const HuffDev& t) {
+  if (br.bits < 16) br.fill();
+  const unsigned short e = t.look[br.peek(9)];
+  if (e) {
+    br.drop(e >> 8);
+    return e & 255;
+  }
+  int code = (int)br.peek(10), len = 10;
+  while (len <= 16 && code > t.maxcode[len]) {
+    ++len;
+    code = (int)br.peek(len);
+  }
+  if (len > 16) return -1;
+  br.drop(len);
+  return t.symbols[t.valptr[len] + code - t.mincode[len]];
+}
+
+__device__ __forceinline__ int dev_receive(DevBits& br, int s) {
+  if (br.bits < s) br.fill();
+  const int v = (int)br.peek(s);
+  br.drop(s);
+  return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+}
+
+__constant__ unsigned char kZigzagDev[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                              41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                              30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+constexpr int kHuffWarps = 4;
+
+// status: 0 = decoded, 1 = corrupt / truncated data
+__global__ void __launch_bounds__(kHuffWarps * 32)
+jpeg_huffman_kernel(const unsigned char* __restrict__ bytes, const HuffDev* __restrict__ tables, const FrameDesc* __restrict__ frames,
+                    int nframes, short* __restrict__ coef, int* __restrict__ status) {
+  __shared__ HuffDev tabs[kHuffWarps][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * kHuffWarps + warp;
+  if (f >= nframes) return;
+  const FrameDesc& fd = frames[f];
+  if (!fd.valid) return;
+  {
+    const unsigned int* src = reinterpret_cast<const unsigned int*>(tables + (long long)f * 4);
+    unsigned int* dst = reinterpret_cast<unsigned int*>(&tabs[warp][0]);
+    for (int i = lane; i < (int)(4 * sizeof(HuffDev) / 4); i += 32) dst[i] = src[i];
+  }
+  __syncwarp();
+  if (lane != 0) return;
+  DevBits br;
+  br.d = bytes + fd.data_off;
+  br.n = fd.data_len;
+  br.pos = 0;
+  br.buf = 0;
+  br.bits = 0;
+  br.hit_marker = false;
+  br.fake_bytes = 0;
+  int pred[3] = {0, 0, 0};
+  int bad = 0;
+  long long count = 0;
+  for (int my = 0; my < fd.mcuy && !bad; ++my) {
+    for (int mx = 0; mx < fd.mcux && !bad; ++mx, ++count) {
+      if (fd.restart && count && count % fd.restart == 0) {
+        long long p = br.pos;
+        while (p + 1 < br.n && !(br.d[p] == 0xFF && br.d[p + 1] >= 0xD0 && br.d[p + 1] <= 0xD7)) ++p;
+        if (p + 1 >= br.n || br.overran()) {
+          bad = 1;
+          break;
+        }
+        br.pos = p + 2;
+        br.buf = 0;
+        br.bits = 0;
+        br.hit_marker = false;
+        br.fake_bytes = 0;
+        pred[0] = pred[1] = pred[2] = 0;
+      }
+      for (int c = 0; c < fd.ncomp && !bad; ++c) {
+        const HuffDev& dct = tabs[warp][fd.tab[c][0]];
+        const HuffDev& act = tabs[warp][fd.tab[c][1]];
+        const int bw = fd.mcux * fd.hs[c];
+        for (int by = 0; by < fd.vs[c] && !bad; ++by)
+          for (int bx = 0; bx < fd.hs[c] && !bad; ++bx) {
+            short* blk = coef + fd.coef_off[c] + ((long long)(my * fd.vs[c] + by) * bw + (mx * fd.hs[c] + bx)) * 64;
+            int s = dev_huff(br, dct);
+            if (s < 0 || s > 15) {
+              bad = 1;
+              break;
+            }
+            if (s) pred[c] += dev_receive(br, s);
+            blk[0] = (short)pred[c];
+            for (int k = 1; k < 64;) {
+              const int rs = dev_huff(br, act);
+              if (rs < 0) {
+                bad = 1;
+                break;
+              }
+              const int r = rs >> 4;
+              s = rs & 15;
+              if (s == 0) {
+                if (r != 15) break;
+                k += 16;
+                continue;
+              }
+              k += r;
+              if (k > 63) {
+                bad = 1;
+                break;
+              }
+              blk[kZigzagDev[k]] = (short)dev_receive(br, s);
+              ++k;
+            }
+          }
+      }
+    }
+  }
+  if (!bad && br.overran()) bad = 1;
+  status[f] = bad;
+}
+
+// the pixel stages over a batch: blockIdx.y (idct) / blockIdx.z (colour, resize) = frame
+__global__ void __launch_bounds__(256)
+jpeg_idct_batch_kernel(const short* __restrict__ coef, const unsigned short* __restrict__ qt, unsigned char* __restrict__ planes,
+                       const FrameDesc* __restrict__ frames, const int* __restrict__ status) {
+  __shared__ int ws[32][8][9];
+  const FrameDesc& fd = frames[blockIdx.y];
+  const bool live = fd.valid && status[blockIdx.y] == 0;
+  const IdctParams& p = fd.ip;
+  const int lb = threadIdx.x >> 3, j = threadIdx.x & 7;
+  const int b = blockIdx.x * 32 + lb;
+  const bool on = live && b < p.block_start[p.ncomp];
+  int c = 0, bi = 0;
+  if (on) {
+    c = b >= p.block_start[2] ? 2 : (b >= p.block_start[1] ? 1 : 0);
+    bi = b - p.block_start[c];
+    const short* blk = coef + p.pl[c].coef_off + (long long)bi * 64;
+    const unsigned short* q = qt + (long long)(fd.qt_base + p.pl[c].qt) * 64;
+    int x[8], o[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) x[r] = (int)blk[r * 8 + j] * (int)q[r * 8 + j];
+    idct8(x, o, 13 - 2);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ws[lb][r][j] = o[r];
+  }
+  __syncthreads();
+  if (on) {
+    const PlaneDesc pd = p.pl[c];
+    const int by = bi / pd.bw, bx = bi - by * pd.bw;
+    int x[8], o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = ws[lb][j][k];
+    idct8(x, o, 13 + 2 + 3);
+    unsigned char px[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) px[k] = range_limit(o[k]);
+    unsigned char* dst = planes + pd.plane_off + ((long long)(by * 8 + j) * (pd.bw * 8) + bx * 8);
+    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(px);
+  }
+}
+
+__device__ __forceinline__ void color_pixel(const unsigned char* planes, unsigned char* dst, const ColorParams& p, int x, int y) {
+  const int yv = planes[p.off[0] + (long long)y * p.pitch[0] + x];
+  if (p.ncomp == 1) {
+    dst[0] = dst[1] = dst[2] = (unsigned char)yv;
+    return;
+  }
+  int cc[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const unsigned char* pl = planes + p.off[1 + k];
+    const int pitch = p.pitch[1 + k];
+    if (p.hmax == 1) {
+      cc[k] = pl[(long long)y * pitch + x];
+    } else if (p.vmax == 1) {
+      const unsigned char* row = pl + (long long)y * pitch;
+      const int c = x >> 1, v = row[c];
+      if (x & 1)
+        cc[k] = c == p.cw - 1 ? v : (3 * v + row[c + 1] + 2) >> 2;
+      else
+        cc[k] = c == 0 ? v : (3 * v + row[c - 1] + 1) >> 2;
+    } else {
+      const int r = y >> 1;
+      int ro = (y & 1) ? r + 1 : r - 1;
+      ro = ro < 0 ? 0 : (ro > p.ch - 1 ? p.ch - 1 : ro);
+      const unsigned char* row0 = pl + (long long)r * pitch;
+      const unsigned char* row1 = pl + (long long)ro * pitch;
+      const int c = x >> 1, cs = colsum(row0, row1, c);
+      if (x & 1)
+        cc[k] = c == p.cw - 1 ? (cs * 4 + 7) >> 4 : (cs * 3 + colsum(row0, row1, c + 1) + 7) >> 4;
+      else
+        cc[k] = c == 0 ? (cs * 4 + 8) >> 4 : (cs * 3 + colsum(row0, row1, c - 1) + 8) >> 4;
+    }
+  }
+  const int cb = cc[0] - 128, cr = cc[1] - 128;
+  const int r = yv + ((91881 * cr + 32768) >> 16);
+  const int b = yv + ((116130 * cb + 32768) >> 16);
+  const int g = yv + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+  dst[0] = (unsigned char)min(max(r, 0), 255);
+  dst[1] = (unsigned char)min(max(g, 0), 255);
+  dst[2] = (unsigned char)min(max(b, 0), 255);
+}
+
+__global__ void __launch_bounds__(256)
+jpeg_color_batch_kernel(const unsigned char* __restrict__ planes, unsigned char* __restrict__ rgb,
+                        const FrameDesc* __restrict__ frames, const int* __restrict__ status) {
+  const FrameDesc& fd = frames[blockIdx.z];
+  if (!fd.valid || status[blockIdx.z]) return;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= fd.cp.w || y >= fd.cp.h) return;
+  color_pixel(planes, rgb + fd.rgb_off + ((long long)y * fd.cp.w + x) * 3, fd.cp, x, y);
+}
+
+// pass 0: horizontal (rgb [h, w, 3] -> tmp [h, out_w, 3], or straight to out when h == out_h); pass 1: vertical
+__global__ void __launch_bounds__(256)
+resample_batch_kernel(const unsigned char* __restrict__ rgb, unsigned char* __restrict__ tmp, const FrameDesc* __restrict__ frames,
+                      const int* __restrict__ status, int pass, int out_h, int out_w) {
+  const FrameDesc& fd = frames[blockIdx.z];
+  if (!fd.valid || status[blockIdx.z]) return;
+  const int h = fd.cp.h, w = fd.cp.w;
+  const int o = blockIdx.y;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const unsigned char* in;
+  unsigned char* out;
+  const int* bounds;
+  const int* kk;
+  int ksize;
+  long long inner, in_so, in_si, out_so, out_si;
+  if (pass == 0) {
+    if (w == out_w) return;
+    in = rgb + fd.rgb_off;
+    out = h != out_h ? tmp + fd.tmp_off : fd.out;
+    bounds = fd.bounds_h, kk = fd.kk_h, ksize = fd.ksize_h;
+    inner = h, in_so = 3, in_si = (long long)w * 3, out_so = 3, out_si = (long long)out_w * 3;
+    if (o >= out_w) return;
+  } else {
+    if (h == out_h) {
+      if (w == out_w) {  // neither pass resamples: copy
+        if (o < out_h && idx < (long long)out_w * 3) fd.out[(long long)o * out_w * 3 + idx] = rgb[fd.rgb_off + (long long)o * w * 3 + idx];
+      }
+      return;
+    }
+    in = w != out_w ? tmp + fd.tmp_off : rgb + fd.rgb_off;
+    out = fd.out;
+    bounds = fd.bounds_v, kk = fd.kk_v, ksize = fd.ksize_v;
+    inner = out_w, in_so = (long long)out_w * 3, in_si = 3, out_so = (long long)out_w * 3, out_si = 3;
+    if (o >= out_h) return;
+  }
+  if (idx >= inner * 3) return;
+  const long long i = idx / 3;
+  const int ch = (int)(idx - i * 3);
+  const int first = bounds[2 * o], cnt = bounds[2 * o + 1];
+  const int* k = kk + (long long)o * ksize;
+  const unsigned char* src = in + first * in_so + i * in_si + ch;
+  int acc = 1 << 21;
+  for (int t = 0; t < cnt; ++t) acc += (int)src[t * in_so] * k[t];
+  acc >>= 22;
+  out[o * out_so + i * out_si + ch] = (unsigned char)min(max(acc, 0), 255);
+}
+
+template <typename T>
+int grow(T** ptr, size_t* cap, size_t need, bool pinned) {
+  if (need <= *cap) return VSB_OK;
+  if (*ptr) {
+    if (pinned) (void)cudaFreeHost(*ptr);
+    else (void)cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+  }
+  need += need / 4;  // headroom: batches of one video differ a little in size
+  cudaError_t e = pinned ? cudaMallocHost((void**)ptr, need * sizeof(T)) : cudaMalloc((void**)ptr, need * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("jpeg batch: allocating %zu bytes failed: %s", need * sizeof(T), cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return VSB_ERR_CUDA;
+  }
+  *cap = need;
+  return VSB_OK;
+}
+
+}  // namespace
+
+struct vsb_jpeg_batch {
+  // pinned host staging
+  unsigned char* h_bytes = nullptr; size_t h_bytes_cap = 0;
+  FrameDesc* h_frames = nullptr;    size_t h_frames_cap = 0;
+  HuffDev* h_tabs = nullptr;        size_t h_tabs_cap = 0;
+  unsigned short* h_qt = nullptr;   size_t h_qt_cap = 0;
+  int* h_status = nullptr;          size_t h_status_cap = 0;
+  // device
+  unsigned char* d_bytes = nullptr; size_t d_bytes_cap = 0;
+  FrameDesc* d_frames = nullptr;    size_t d_frames_cap = 0;
+  HuffDev* d_tabs = nullptr;        size_t d_tabs_cap = 0;
+  unsigned short* d_qt = nullptr;   size_t d_qt_cap = 0;
+  int* d_status = nullptr;          size_t d_status_cap = 0;
+  short* d_coef = nullptr;          size_t d_coef_cap = 0;
+  unsigned char* d_planes = nullptr; size_t d_planes_cap = 0;
+  unsigned char* d_rgb = nullptr;   size_t d_rgb_cap = 0;
+  unsigned char* d_tmp = nullptr;   size_t d_tmp_cap = 0;
+  std::vector<ResizeTables> tables;  // resampling tables by (input size, output size)
+};
+
+namespace {
+const ResizeTables* batch_tables(vsb_jpeg_batch* b, int in_size, int out_size) {
+  for (const ResizeTables& t : b->tables)
+    if (t.in_size == in_size && t.out_size == out_size) return &t;
+  std::vector<int> bounds, kk;
+  ResizeTables t;
+  t.ksize = precompute_coeffs(in_size, out_size, bounds, kk);
+  if (cudaMalloc((void**)&t.bounds, bounds.size() * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void**)&t.kk, kk.size() * sizeof(int)) != cudaSuccess ||
+      cudaMemcpy(t.bounds, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(t.kk, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("jpeg batch: resampling tables: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  t.in_size = in_size;
+  t.out_size = out_size;
+  b->tables.push_back(t);
+  return &b->tables.back();
+}
+
+void copy_table(HuffDev& dst, const HuffTable& src) {
+  memcpy(dst.look, src.look, sizeof(dst.look));
+  memcpy(dst.maxcode, src.maxcode, sizeof(dst.maxcode));
+  memcpy(dst.valptr, src.valptr, sizeof(dst.valptr));
+  memcpy(dst.mincode, src.mincode, sizeof(dst.mincode));
+  memcpy(dst.symbols, src.symbols, sizeof(dst.symbols));
+}
+}  // namespace
+
+extern "C" int vsb_jpeg_batch_create(vsb_jpeg_batch** out) {
+  VSB_CHECK_ARG(out, "null argument");
+  *out = new (std::nothrow) vsb_jpeg_batch();
+  VSB_CHECK_ARG(*out, "out of host memory");
+  return VSB_OK;
+}
+
+extern "C" void vsb_jpeg_batch_destroy(vsb_jpeg_batch* b) {
+  if (!b) return;
+  void* pinned[] = {b->h_bytes, b->h_frames, b->h_tabs, b->h_qt, b->h_status};
+  for (void* p : pinned)
+    if (p) (void)cudaFreeHost(p);
+  void* dev[] = {b->d_bytes, b->d_frames, b->d_tabs, b->d_qt, b->d_status, b->d_coef, b->d_planes, b->d_rgb, b->d_tmp};
+  for (void* p : dev)
+    if (p) (void)cudaFree(p);
+  for (ResizeTables& t : b->tables) {
+    if (t.bounds) (void)cudaFree(t.bounds);
+    if (t.kk) (void)cudaFree(t.kk);
+  }
+  delete b;
+}
+
+extern "C" int vsb_jpeg_batch_decode_resize(vsb_jpeg_batch* b, const uint8_t* const* jpegs, const unsigned long long* bytes,
+                                            int n, uint8_t* const* outs, int out_h, int out_w, int* status, void* stream) {
+  VSB_CHECK_ARG(b && jpegs && bytes && outs && status && n > 0 && out_h > 0 && out_w > 0, "null argument or empty batch");
+  cudaStream_t s = (cudaStream_t)stream;
+  // ---- host: headers -> per-frame descriptors, workspace layout
+  std::vector<JpegHeader> hdr((size_t)n);
+  size_t nbytes = 0, ncoef = 0, nplanes = 0, nrgb = 0, ntmp = 0;
+  int rc = grow(&b->h_frames, &b->h_frames_cap, (size_t)n, true);
+  if (rc == VSB_OK) rc = grow(&b->h_tabs, &b->h_tabs_cap, (size_t)n * 4, true);
+  if (rc == VSB_OK) rc = grow(&b->h_qt, &b->h_qt_cap, (size_t)n * 4 * 64, true);
+  if (rc == VSB_OK) rc = grow(&b->h_status, &b->h_status_cap, (size_t)n, true);
+  if (rc != VSB_OK) return rc;
+  memset(b->h_frames, 0, (size_t)n * sizeof(FrameDesc));
+  memset(b->h_tabs, 0, (size_t)n * 4 * sizeof(HuffDev));
+  int max_blocks = 0, max_w = 0, max_h = 0, n_valid = 0;
+  for (int f = 0; f < n; ++f) {
+    FrameDesc& fd = b->h_frames[f];
+    status[f] = VSB_ERR_INVALID;
+    if (!jpegs[f] || !outs[f] || parse_header(jpegs[f], (size_t)bytes[f], hdr[f]) != VSB_OK) continue;  // refused: the caller's fallback
+    const JpegHeader& h = hdr[f];
+    fd.valid = 1;
+    ++n_valid;
+    fd.data_off = (long long)nbytes;
+    fd.data_len = (long long)(bytes[f] - h.scan_start);
+    nbytes += (size_t)fd.data_len;
+    fd.ncomp = h.ncomp, fd.mcux = h.mcux, fd.mcuy = h.mcuy, fd.restart = h.restart;
+    // the frame's (up to) four Huffman tables: slots 0 / 1 = DC / AC of component 0, 2 / 3 = of the chroma components
+    for (int c = 0; c < h.ncomp; ++c) {
+      fd.hs[c] = h.comp[c].hs, fd.vs[c] = h.comp[c].vs;
+      const int slot = c == 0 ? 0 : 2;
+      if (c == 2 && (h.comp[2].td != h.comp[1].td || h.comp[2].ta != h.comp[1].ta)) {
+        fd.valid = 0;  // three distinct table pairs: outside the batch path (never produced by the usual encoders)
+        break;
+      }
+      fd.tab[c][0] = slot, fd.tab[c][1] = slot + 1;
+      copy_table(b->h_tabs[(size_t)f * 4 + slot], h.dc[h.comp[c].td]);
+      copy_table(b->h_tabs[(size_t)f * 4 + slot + 1], h.ac[h.comp[c].ta]);
+    }
+    if (!fd.valid) {
+      --n_valid;
+      nbytes -= (size_t)fd.data_len;
+      continue;
+    }
+    memcpy(b->h_qt + (size_t)f * 256, h.qt, sizeof(h.qt));
+    fd.qt_base = f * 4;
+    fd.ip.ncomp = h.ncomp;
+    for (int c = 0; c < h.ncomp; ++c) {
+      const int bw = h.mcux * h.comp[c].hs, bh = h.mcuy * h.comp[c].vs;
+      fd.coef_off[c] = (long long)ncoef;
+      fd.ip.pl[c].coef_off = (long long)ncoef;
+      fd.ip.pl[c].plane_off = (long long)nplanes;
+      fd.ip.pl[c].bw = bw, fd.ip.pl[c].bh = bh, fd.ip.pl[c].qt = h.comp[c].tq;
+      fd.ip.block_start[c + 1] = fd.ip.block_start[c] + bw * bh;
+      fd.cp.off[c] = (long long)nplanes;
+      fd.cp.pitch[c] = bw * 8;
+      ncoef += (size_t)bw * bh * 64;
+      nplanes += align256((size_t)bw * bh * 64);
+    }
+    for (int c = h.ncomp; c < 3; ++c) fd.ip.block_start[c + 1] = fd.ip.block_start[c];
+    if (fd.ip.block_start[h.ncomp] > max_blocks) max_blocks = fd.ip.block_start[h.ncomp];
+    fd.cp.w = h.width, fd.cp.h = h.height, fd.cp.ncomp = h.ncomp, fd.cp.hmax = h.hmax, fd.cp.vmax = h.vmax;
+    fd.cp.cw = (h.width + h.hmax - 1) / h.hmax;
+    fd.cp.ch = (h.height + h.vmax - 1) / h.vmax;
+    if (h.width > max_w) max_w = h.width;
+    if (h.height > max_h) max_h = h.height;
+    fd.rgb_off = (long long)nrgb;
+    nrgb += align256((size_t)h.width * h.height * 3);
+    fd.tmp_off = (long long)ntmp;
+    ntmp += align256((size_t)h.height * out_w * 3);
+    fd.out = outs[f];
+    if (h.width != out_w) {
+      const ResizeTables* t = batch_tables(b, h.width, out_w);
+      if (!t) return VSB_ERR_CUDA;
+      fd.bounds_h = t->bounds, fd.kk_h = t->kk, fd.ksize_h = t->ksize;
+    }
+    if (h.height != out_h) {
+      const ResizeTables* t = batch_tables(b, h.height, out_h);
+      if (!t) return VSB_ERR_CUDA;
+      fd.bounds_v = t->bounds, fd.kk_v = t->kk, fd.ksize_v = t->ksize;
+    }
+  }
+  if (n_valid == 0) return VSB_OK;  // every frame was refused: status[] says so
+  // ---- workspaces (grow-only; a reallocation waits for the device)
+  const bool realloc = nbytes > b->d_bytes_cap || (size_t)n > b->d_frames_cap || ncoef > b->d_coef_cap || nplanes > b->d_planes_cap ||
+                       nrgb > b->d_rgb_cap || ntmp > b->d_tmp_cap || nbytes > b->h_bytes_cap;
+  if (realloc) VSB_CHECK_CUDA(cudaDeviceSynchronize());
+  rc = grow(&b->h_bytes, &b->h_bytes_cap, nbytes, true);
+  if (rc == VSB_OK) rc = grow(&b->d_bytes, &b->d_bytes_cap, nbytes, false);
+  if (rc == VSB_OK) rc = grow(&b->d_frames, &b->d_frames_cap, (size_t)n, false);
+  if (rc == VSB_OK) rc = grow(&b->d_tabs, &b->d_tabs_cap, (size_t)n * 4, false);
+  if (rc == VSB_OK) rc = grow(&b->d_qt, &b->d_qt_cap, (size_t)n * 256, false);
+  if (rc == VSB_OK) rc = grow(&b->d_status, &b->d_status_cap, (size_t)n, false);
+  if (rc == VSB_OK) rc = grow(&b->d_coef, &b->d_coef_cap, ncoef, false);
+  if (rc == VSB_OK) rc = grow(&b->d_planes, &b->d_planes_cap, nplanes, false);
+  if (rc == VSB_OK) rc = grow(&b->d_rgb, &b->d_rgb_cap, nrgb, false);
+  if (rc == VSB_OK) rc = grow(&b->d_tmp, &b->d_tmp_cap, ntmp ? ntmp : 1, false);
+  if (rc != VSB_OK) return rc;
+  for (int f = 0; f < n; ++f)
+    if (b->h_frames[f].valid)
+      memcpy(b->h_bytes + b->h_frames[f].data_off, jpegs[f] + hdr[f].scan_start, (size_t)b->h_frames[f].data_len);
+  // ---- device
+  VSB_CHECK_CUDA(cudaMemcpyAsync(b->d_bytes, b->h_bytes, nbytes, cudaMemcpyHostToDevice, s));
+  VSB_CHECK_CUDA(cudaMemcpyAsync(b->d_frames, b->h_frames, (size_t)n * sizeof(FrameDesc), cudaMemcpyHostToDevice, s));
+  VSB_CHECK_CUDA(cudaMemcpyAsync(b->d_tabs, b->h_tabs, (size_t)n * 4 * sizeof(HuffDev), cudaMemcpyHostToDevice, s));
+  VSB_CHECK_CUDA(cudaMemcpyAsync(b->d_qt, b->h_qt, (size_t)n * 256 * sizeof(unsigned short), cudaMemcpyHostToDevice, s));
+  VSB_CHECK_CUDA(cudaMemsetAsync(b->d_coef, 0, ncoef * sizeof(short), s));
+  VSB_CHECK_CUDA(cudaMemsetAsync(b->d_status, 0, (size_t)n * sizeof(int), s));
+  jpeg_huffman_kernel<<<(n + kHuffWarps - 1) / kHuffWarps, kHuffWarps * 32, 0, s>>>(b->d_bytes, b->d_tabs, b->d_frames, n, b->d_coef,
+                                                                                    b->d_status);
+  VSB_CHECK_LAUNCH("jpeg_huffman_kernel");
+  jpeg_idct_batch_kernel<<<dim3((unsigned)((max_blocks + 31) / 32), (unsigned)n), 256, 0, s>>>(b->d_coef, b->d_qt, b->d_planes, b->d_frames,
+                                                                                              b->d_status);
+  VSB_CHECK_LAUNCH("jpeg_idct_batch_kernel");
+  jpeg_color_batch_kernel<<<dim3((unsigned)((max_w + 255) / 256), (unsigned)max_h, (unsigned)n), 256, 0, s>>>(b->d_planes, b->d_rgb,
+                                                                                                             b->d_frames, b->d_status);
+  VSB_CHECK_LAUNCH("jpeg_color_batch_kernel");
+  resample_batch_kernel<<<dim3((unsigned)(((long long)max_h * 3 + 255) / 256), (unsigned)out_w, (unsigned)n), 256, 0, s>>>(
+      b->d_rgb, b->d_tmp, b->d_frames, b->d_status, 0, out_h, out_w);
+  VSB_CHECK_LAUNCH("resample_batch_kernel");
+  resample_batch_kernel<<<dim3((unsigned)(((long long)out_w * 3 + 255) / 256), (unsigned)out_h, (unsigned)n), 256, 0, s>>>(
+      b->d_rgb, b->d_tmp, b->d_frames, b->d_status, 1, out_h, out_w);
+  VSB_CHECK_LAUNCH("resample_batch_kernel");
+  VSB_CHECK_CUDA(cudaMemcpyAsync(b->h_status, b->d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  VSB_CHECK_CUDA(cudaStreamSynchronize(s));  // the per-frame verdicts are part of the result
+  for (int f = 0; f < n; ++f)
+    if (b->h_frames[f].valid) status[f] = b->h_status[f] ? VSB_ERR_INVALID : VSB_OK;
+  return VSB_OK;
+}

@@ -8,7 +8,7 @@ the reference's PIL reader for such files catch it (frames_io.load_video_device 
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -61,4 +61,46 @@ class JpegDecoder:
         h = getattr(self, "_h", None)
         if h is not None and h.value:
             self._lib.vsb_jpeg_decoder_destroy(h)
+            h.value = None
+
+
+class JpegBatchDecoder:
+    """The fully-on-device path (vsb_jpeg_batch_*): the Huffman segments of a whole batch of files are decoded on the
+    GPU, one warp per frame; the host parses headers and stages bytes.  Same pixels as JpegDecoder / Pillow."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise VsbError("JpegBatchDecoder needs a CUDA device (the host-only reader is frames_io.read_img)")
+        self.device = torch.device(device if device is not None else "cuda")
+        self._lib = _l.load()
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self._lib.vsb_jpeg_batch_create(C.byref(self._h)), "vsb_jpeg_batch_create")
+
+    def decode_resize(self, datas: Sequence[bytes], outs: Sequence[torch.Tensor]) -> List[bool]:
+        """Decode datas[i] into outs[i] (CUDA uint8 [h, w, 3] views of one size, each contiguous).  Returns per-file
+        success; a refused / corrupt file leaves its output untouched.  Completes before returning."""
+        n = len(datas)
+        if n == 0:
+            return []
+        if len(outs) != n:
+            raise VsbError("one output per file")
+        oh, ow = int(outs[0].shape[0]), int(outs[0].shape[1])
+        for t in outs:
+            if (not t.is_cuda or t.dtype != torch.uint8 or tuple(t.shape) != (oh, ow, 3) or not t.is_contiguous()):
+                raise VsbError("outs must be contiguous CUDA uint8 [h, w, 3] tensors of one size")
+        ptrs = (C.c_char_p * n)(*datas)
+        sizes = (C.c_ulonglong * n)(*[len(d) for d in datas])
+        dsts = (C.c_void_p * n)(*[t.data_ptr() for t in outs])
+        status = (C.c_int * n)()
+        with torch.cuda.device(self.device):
+            check(self._lib.vsb_jpeg_batch_decode_resize(self._h, ptrs, sizes, n, dsts, oh, ow, status,
+                                                         torch.cuda.current_stream().cuda_stream),
+                  "vsb_jpeg_batch_decode_resize")
+        return [status[i] == 0 for i in range(n)]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.vsb_jpeg_batch_destroy(h)
             h.value = None

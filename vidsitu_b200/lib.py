@@ -173,13 +173,18 @@ def load() -> C.CDLL:
     lib.vsb_jpeg_decoder_destroy.restype = None
     lib.vsb_jpeg_decode_resize.argtypes = [vp, vp, ull, vp, i, i, vp]
     lib.vsb_resize_bicubic_u8.argtypes = [vp, vp, i, i, vp, i, i, vp]
+    lib.vsb_jpeg_batch_create.argtypes = [C.POINTER(vp)]
+    lib.vsb_jpeg_batch_destroy.argtypes = [vp]
+    lib.vsb_jpeg_batch_destroy.restype = None
+    lib.vsb_jpeg_batch_decode_resize.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(ull), i, C.POINTER(vp), i, i,
+                                                 C.POINTER(i), vp]
     lib.vsb_program_add_sync.argtypes = [vp, i, i]
     lib.vsb_program_run.argtypes = [vp, vp]
     lib.vsb_program_capture.argtypes = [vp, vp]
     lib.vsb_program_save.argtypes = [vp, cp]
     lib.vsb_program_file_device_bytes.argtypes = [cp, C.POINTER(ull)]
     lib.vsb_program_load.argtypes = [cp, vp, ull, C.POINTER(vp)]
-    for name in ("vsb_jpeg_info", "vsb_jpeg_decoder_create", "vsb_jpeg_decode_resize", "vsb_resize_bicubic_u8",
+    for name in ("vsb_jpeg_batch_create", "vsb_jpeg_batch_decode_resize", "vsb_jpeg_info", "vsb_jpeg_decoder_create", "vsb_jpeg_decode_resize", "vsb_resize_bicubic_u8",
                  "vsb_stem_pool_plan_create", "vsb_stem_pool_run", "vsb_stem_pool_plan_desc", "vsb_program_add_stem_pool",
                  "vsb_program_create", "vsb_program_add_region", "vsb_program_region", "vsb_program_num_ops",
                  "vsb_program_num_launches", "vsb_program_add_conv", "vsb_program_add_bottleneck",
