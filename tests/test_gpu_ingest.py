@@ -108,22 +108,31 @@ def test_feature_dump_cli_with_gpu_decode_writes_the_same_files(tmp_path):
             Image.fromarray(img).save(d / f"{v}_{ix:06d}.jpg", quality=94, subsampling=2)
     (tmp_path / "split.json").write_text(json.dumps(names))
     outs = {}
-    for mode in ("host", "gpu"):
+    for mode in ("host", "device", "hybrid"):
         torch.manual_seed(33)
         rc = X.main(["--frames-dir", str(tmp_path / "frames"), "--split-file", str(tmp_path / "split.json"),
                      "--out-dir", str(tmp_path / f"feats_{mode}"), "--mdl-name-used", "m", "--crop", "64",
                      "--videos-per-batch", "2", "--workers", "0" if mode == "host" else "3"]
-                    + (["--gpu-decode"] if mode == "gpu" else []))
+                    + (["--gpu-decode", mode] if mode != "host" else []))
         assert rc == 0
         outs[mode] = {v: (tmp_path / f"feats_{mode}" / "m" / f"{v}_feats.npy").read_bytes() for v in names}
-    assert outs["host"] == outs["gpu"]
+    assert outs["host"] == outs["device"] == outs["hybrid"]
     # and the loader's frames themselves equal the host reader's
-    dl = F.DeviceVideoLoader(tmp_path / "frames", names, 32, 2, size=64, videos_per_batch=3, workers=2)
-    (frames, idxs), = list(dl)
-    assert idxs == [0, 1, 2] and dl.host_fallbacks == 0
     needed = F.needed_frames(32, 2)
     ref = F.load_video(tmp_path / "frames", names[1], needed, 64)
-    assert torch.equal(frames[1].cpu(), ref)
+    for mode in ("device", "hybrid"):
+        dl = F.DeviceVideoLoader(tmp_path / "frames", names, 32, 2, size=64, videos_per_batch=3, workers=2, mode=mode)
+        (frames, idxs), = list(dl)
+        assert idxs == [0, 1, 2] and dl.host_fallbacks == 0
+        assert torch.equal(frames[1].cpu(), ref), mode
+    # a progressive file in the middle of a video goes through the reference's reader, and is counted
+    Image.fromarray(synthetic_image(90, 160, "noisy", 5)).save(tmp_path / "frames" / names[0] / f"{names[0]}_{needed[3] + 1:06d}.jpg",
+                                                              quality=90, progressive=True)
+    ref0 = F.load_video(tmp_path / "frames", names[0], needed, 64)
+    for mode in ("device", "hybrid"):
+        dl = F.DeviceVideoLoader(tmp_path / "frames", names[:1], 32, 2, size=64, videos_per_batch=1, workers=2, mode=mode)
+        (frames, _), = list(dl)
+        assert dl.host_fallbacks == 1 and torch.equal(frames[0].cpu(), ref0), mode
 
 
 def test_fully_on_device_batch_decode_is_bit_exact_and_reports_refusals():

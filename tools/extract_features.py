@@ -43,9 +43,10 @@ def main(argv=None) -> int:
     ap.add_argument("--videos-per-batch", type=int, default=8)
     ap.add_argument("--workers", type=int, default=4, help="cfg.train.nwv")
     ap.add_argument("--crop", type=int, default=224)
-    ap.add_argument("--gpu-decode", action="store_true",
-                    help="decode + resize the JPEGs on the GPU (bit-identical to the PIL reader; --workers host threads "
-                         "do the Huffman part) instead of PIL in DataLoader workers")
+    ap.add_argument("--gpu-decode", nargs="?", const="device", default="", choices=["device", "hybrid"],
+                    help="decode + resize the JPEGs on the GPU, bit-identical to the PIL reader, instead of PIL in "
+                         "DataLoader workers: 'device' (default) = Huffman segments on the GPU too, one library call per "
+                         "batch; 'hybrid' = --workers host threads do the Huffman part")
     args = ap.parse_args(argv)
 
     cfg = make_cfg(args.sf_mdl_name)
@@ -67,7 +68,7 @@ def main(argv=None) -> int:
     d = cfg.sf_mdl.DATA
     if args.gpu_decode:
         dl = DeviceVideoLoader(args.frames_dir, vsegs, d.NUM_FRAMES, d.SAMPLING_RATE, d.TARGET_FPS, size=args.crop,
-                               videos_per_batch=args.videos_per_batch, workers=max(1, args.workers))
+                               videos_per_batch=args.videos_per_batch, workers=max(1, args.workers), mode=args.gpu_decode)
     else:
         ds = VideoFrames(args.frames_dir, vsegs, d.NUM_FRAMES, d.SAMPLING_RATE, d.TARGET_FPS, size=args.crop)
         dl = DataLoader(ds, batch_size=args.videos_per_batch, shuffle=False, num_workers=args.workers,

@@ -34,6 +34,21 @@ for w in (1, 2, 4, 8, 16):
         torch.cuda.synchronize()
     res[f"gpu_path_{w}_threads_fps"] = round(N / (time.time() - t0), 1)
     del decs
+from vidsitu_b200.jpeg import JpegBatchDecoder
+bd = JpegBatchDecoder()
+for nb in (160, 480, 960, 1920):
+    batch = [datas[i % K] for i in range(nb)]
+    o = torch.empty((nb, 224, 224, 3), dtype=torch.uint8, device="cuda")
+    outs = list(o)
+    assert all(bd.decode_resize(batch, outs))     # warm-up (workspaces grow)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    reps = max(1, 1920 // nb)
+    for _ in range(reps):
+        bd.decode_resize(batch, outs)
+    torch.cuda.synchronize()
+    res[f"gpu_huffman_batch_{nb}_fps"] = round(nb * reps / (time.time() - t0), 1)
+    res[f"gpu_huffman_batch_{nb}_bit_exact"] = bool(np.array_equal(o[5].cpu().numpy(), np.array(Image.open(io.BytesIO(batch[5])).convert("RGB").resize((224, 224)))))
 ref = np.array(Image.open(io.BytesIO(datas[5])).convert("RGB").resize((224, 224)))
 res["bit_exact"] = bool(np.array_equal(out[5].cpu().numpy(), ref))
 res["host_cpus"] = os.cpu_count()

@@ -99,17 +99,21 @@ def collate_videos(batch):
 class DeviceVideoLoader:
     """Whole videos decoded ON THE GPU: the counterpart of DataLoader(VideoFrames) for `--gpu-decode`.
 
-    `workers` host threads each own a `jpeg.JpegDecoder` and a CUDA stream; a thread reads the JPEG files of one video,
-    Huffman-decodes them (in the library, outside the GIL) and enqueues IDCT / upsampling / colour conversion / the
-    PIL-exact resize on its stream, straight into the video's uint8 `[total, size, size, 3]` device tensor - no pixel
-    ever crosses PCIe.  Files the GPU path refuses (progressive, CMYK, ...) go through the reference's PIL reader
-    (`read_img`) and are counted in `host_fallbacks`.  Iterating yields `(frames [B, total, size, size, 3] cuda uint8,
-    [video indices])`, ready on the CURRENT stream."""
+    mode "device" (default): `jpeg.JpegBatchDecoder` - the JPEG files of a loader batch (videos_per_batch x ~150 needed
+    frames) are read by `workers` I/O threads and decoded in ONE library call, Huffman segments included (one warp
+    per frame), straight into the videos' uint8 `[total, size, size, 3]` device tensors.
+    mode "hybrid": `workers` host threads each own a `jpeg.JpegDecoder` and a CUDA stream and Huffman-decode their
+    videos' files on the host (in the library, outside the GIL); the pixel stages run on the device.
+    Either way no pixel crosses PCIe and the frames are bit-identical to the reference's PIL reader.  Files the GPU
+    path refuses (progressive, CMYK, ...) go through that reader (`read_img`) and are counted in `host_fallbacks`.
+    Iterating yields `(frames [B, total, size, size, 3] cuda uint8, [video indices])`, ready on the CURRENT stream."""
 
     def __init__(self, video_frms_tdir, vseg_lst: Sequence[str], num_frames: int, sampling_rate: int, fps: int = 30,
                  size: int = 224, total: int = VIDEO_FRAMES, videos_per_batch: int = 8, workers: int = 4,
-                 device=None, max_width: int = 1920, max_height: int = 1088):
+                 device=None, max_width: int = 1920, max_height: int = 1088, mode: str = "device"):
         import threading
+        if mode not in ("device", "hybrid"):
+            raise ValueError("mode must be 'device' or 'hybrid'")
         self.tdir = Path(video_frms_tdir)
         self.vseg_lst = list(vseg_lst)
         self.size, self.total = int(size), int(total)
@@ -118,13 +122,16 @@ class DeviceVideoLoader:
         self.workers = max(1, int(workers))
         self.device = torch.device(device if device is not None else "cuda")
         self.max_wh = (int(max_width), int(max_height))
+        self.mode = mode
         self.host_fallbacks = 0
         self._tls = threading.local()
         self._lock = threading.Lock()
+        self._batch = None
 
     def __len__(self) -> int:
         return (len(self.vseg_lst) + self.videos_per_batch - 1) // self.videos_per_batch
 
+    # ---- hybrid: one decoder + stream per host thread
     def _state(self):
         from .jpeg import JpegDecoder
         st = getattr(self._tls, "st", None)
@@ -133,24 +140,43 @@ class DeviceVideoLoader:
             self._tls.st = st
         return st
 
+    def _paths(self, vseg: str):
+        paths = frame_paths(self.tdir, vseg, self.total)
+        for i in self.needed:
+            if not paths[i].exists():
+                raise AssertionError(f"{paths[i]} doesn't exist")     # read_file_with_assertion semantics
+        return paths
+
+    def _host_frame(self, path, dst: torch.Tensor) -> None:
+        dst.copy_(torch.from_numpy(read_img(path, self.size)))
+        with self._lock:
+            self.host_fallbacks += 1
+
     def _decode_video(self, vseg: str, out: torch.Tensor) -> "torch.cuda.Event":
         from .lib import VsbError
         dec, stream = self._state()
-        paths = frame_paths(self.tdir, vseg, self.total)
+        paths = self._paths(vseg)
         with torch.cuda.device(self.device), torch.cuda.stream(stream):
             for i in self.needed:
-                if not paths[i].exists():
-                    raise AssertionError(f"{paths[i]} doesn't exist")
-                data = paths[i].read_bytes()
                 try:
-                    dec.decode_resize(data, out[i])
+                    dec.decode_resize(paths[i].read_bytes(), out[i])
                 except VsbError:
-                    out[i].copy_(torch.from_numpy(read_img(paths[i], self.size)), non_blocking=False)
-                    with self._lock:
-                        self.host_fallbacks += 1
+                    self._host_frame(paths[i], out[i])
             ev = torch.cuda.Event()
             ev.record(stream)
         return ev
+
+    # ---- device: the whole loader batch in one call
+    def _decode_batch(self, pool, idxs, frames: torch.Tensor) -> None:
+        from .jpeg import JpegBatchDecoder
+        if self._batch is None:
+            self._batch = JpegBatchDecoder(self.device)
+        jobs = [(k, i, p[i]) for k, v in enumerate(idxs) for p in (self._paths(self.vseg_lst[v]),) for i in self.needed]
+        datas = list(pool.map(lambda j: j[2].read_bytes(), jobs))
+        ok = self._batch.decode_resize(datas, [frames[k, i] for k, i, _ in jobs])
+        for good, (k, i, path) in zip(ok, jobs):
+            if not good:
+                self._host_frame(path, frames[k, i])
 
     def __iter__(self):
         from concurrent.futures import ThreadPoolExecutor
@@ -160,6 +186,11 @@ class DeviceVideoLoader:
                 idxs = list(range(b0, min(b0 + self.videos_per_batch, len(self.vseg_lst))))
                 frames = torch.zeros((len(idxs), self.total, self.size, self.size, 3), dtype=torch.uint8,
                                      device=self.device)
+                if self.mode == "device":
+                    with torch.cuda.device(self.device):
+                        self._decode_batch(pool, idxs, frames)       # completes before returning
+                    yield frames, idxs
+                    continue
                 torch.cuda.current_stream(self.device).synchronize()     # the zero fill precedes the workers' writes
                 futs = [pool.submit(self._decode_video, self.vseg_lst[i], frames[k]) for k, i in enumerate(idxs)]
                 if pending is not None:
