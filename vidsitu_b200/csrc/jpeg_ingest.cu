@@ -809,6 +809,24 @@ struct DevBits {
   bool hit_marker;
   int fake_bytes;
   __device__ __forceinline__ void fill() {
+    // fast path: eight stream bytes in one go when none of them is 0xFF (stuffing / markers take the byte loop).
+    // `d` is 8-byte aligned and the buffer has 16 bytes of slack behind the last segment.
+    if (!hit_marker && pos + 8 <= n && bits <= 56) {
+      const unsigned long long* w = reinterpret_cast<const unsigned long long*>(d) + (pos >> 3);
+      const int sh = (int)(pos & 7) * 8;
+      unsigned long long u = w[0] >> sh;
+      if (sh) u |= w[1] << (64 - sh);
+      const unsigned long long v = ~u;
+      if (((v - 0x0101010101010101ull) & ~v & 0x8080808080808080ull) == 0) {
+        const unsigned lo = (unsigned)u, hi = (unsigned)(u >> 32);
+        const unsigned long long be = ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+        const int k = (64 - bits) >> 3;  // 1..8 whole bytes fit
+        buf |= (be >> (64 - 8 * k)) << (64 - bits - 8 * k);
+        bits += 8 * k;
+        pos += k;
+        return;
+      }
+    }
     while (bits <= 56) {
       unsigned b = 0;
       if (!hit_marker && pos < n) {
@@ -1211,6 +1229,8 @@ extern "C" int vsb_jpeg_batch_decode_resize(vsb_jpeg_batch* b, const uint8_t* co
     const JpegHeader& h = hdr[f];
     fd.valid = 1;
     ++n_valid;
+    nbytes = (nbytes + 7) & ~(size_t)7;  // the device bit reader fetches aligned 8-byte words
+    const size_t frame_first = nbytes;
     fd.data_off = (long long)nbytes;
     fd.data_len = (long long)(bytes[f] - h.scan_start);
     nbytes += (size_t)fd.data_len;
@@ -1229,7 +1249,7 @@ extern "C" int vsb_jpeg_batch_decode_resize(vsb_jpeg_batch* b, const uint8_t* co
     }
     if (!fd.valid) {
       --n_valid;
-      nbytes -= (size_t)fd.data_len;
+      nbytes = frame_first;
       continue;
     }
     memcpy(b->h_qt + (size_t)f * 256, h.qt, sizeof(h.qt));
@@ -1272,9 +1292,10 @@ extern "C" int vsb_jpeg_batch_decode_resize(vsb_jpeg_batch* b, const uint8_t* co
   }
   if (n_valid == 0) return VSB_OK;  // every frame was refused: status[] says so
   // ---- workspaces (grow-only; a reallocation waits for the device)
-  const bool realloc = nbytes > b->d_bytes_cap || (size_t)n > b->d_frames_cap || ncoef > b->d_coef_cap || nplanes > b->d_planes_cap ||
-                       nrgb > b->d_rgb_cap || ntmp > b->d_tmp_cap || nbytes > b->h_bytes_cap;
+  const bool realloc = nbytes + 64 > b->d_bytes_cap || (size_t)n > b->d_frames_cap || ncoef > b->d_coef_cap || nplanes > b->d_planes_cap ||
+                       nrgb > b->d_rgb_cap || ntmp > b->d_tmp_cap || nbytes + 64 > b->h_bytes_cap;
   if (realloc) VSB_CHECK_CUDA(cudaDeviceSynchronize());
+  nbytes += 64;  // slack behind the last segment (word-wise fetches)
   rc = grow(&b->h_bytes, &b->h_bytes_cap, nbytes, true);
   if (rc == VSB_OK) rc = grow(&b->d_bytes, &b->d_bytes_cap, nbytes, false);
   if (rc == VSB_OK) rc = grow(&b->d_frames, &b->d_frames_cap, (size_t)n, false);
