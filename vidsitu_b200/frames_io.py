@@ -167,12 +167,16 @@ class DeviceVideoLoader:
         return ev
 
     # ---- device: the whole loader batch in one call
-    def _decode_batch(self, pool, idxs, frames: torch.Tensor) -> None:
+    def _read_batch(self, pool, idxs):
+        """Start reading the JPEG files of a loader batch on the I/O threads: (jobs, futures of the file bytes)."""
+        jobs = [(k, i, p[i]) for k, v in enumerate(idxs) for p in (self._paths(self.vseg_lst[v]),) for i in self.needed]
+        return jobs, [pool.submit(j[2].read_bytes) for j in jobs]
+
+    def _decode_batch(self, jobs, futs, frames: torch.Tensor) -> None:
         from .jpeg import JpegBatchDecoder
         if self._batch is None:
             self._batch = JpegBatchDecoder(self.device)
-        jobs = [(k, i, p[i]) for k, v in enumerate(idxs) for p in (self._paths(self.vseg_lst[v]),) for i in self.needed]
-        datas = list(pool.map(lambda j: j[2].read_bytes(), jobs))
+        datas = [f.result() for f in futs]
         ok = self._batch.decode_resize(datas, [frames[k, i] for k, i, _ in jobs])
         for good, (k, i, path) in zip(ok, jobs):
             if not good:
@@ -180,17 +184,25 @@ class DeviceVideoLoader:
 
     def __iter__(self):
         from concurrent.futures import ThreadPoolExecutor
+        batches = [list(range(b0, min(b0 + self.videos_per_batch, len(self.vseg_lst))))
+                   for b0 in range(0, len(self.vseg_lst), self.videos_per_batch)]
         with ThreadPoolExecutor(max_workers=self.workers) as pool:
+            if self.mode == "device":
+                # the files of batch k + 1 are read while batch k is decoded (and while the caller's CNN runs on it)
+                reads = self._read_batch(pool, batches[0]) if batches else None
+                for bi, idxs in enumerate(batches):
+                    jobs, futs = reads
+                    reads = self._read_batch(pool, batches[bi + 1]) if bi + 1 < len(batches) else None
+                    frames = torch.zeros((len(idxs), self.total, self.size, self.size, 3), dtype=torch.uint8,
+                                         device=self.device)
+                    with torch.cuda.device(self.device):
+                        self._decode_batch(jobs, futs, frames)       # completes before returning
+                    yield frames, idxs
+                return
             pending = None
-            for b0 in range(0, len(self.vseg_lst), self.videos_per_batch):
-                idxs = list(range(b0, min(b0 + self.videos_per_batch, len(self.vseg_lst))))
+            for idxs in batches:
                 frames = torch.zeros((len(idxs), self.total, self.size, self.size, 3), dtype=torch.uint8,
                                      device=self.device)
-                if self.mode == "device":
-                    with torch.cuda.device(self.device):
-                        self._decode_batch(pool, idxs, frames)       # completes before returning
-                    yield frames, idxs
-                    continue
                 torch.cuda.current_stream(self.device).synchronize()     # the zero fill precedes the workers' writes
                 futs = [pool.submit(self._decode_video, self.vseg_lst[i], frames[k]) for k, i in enumerate(idxs)]
                 if pending is not None:
