@@ -165,3 +165,42 @@ def test_fully_on_device_batch_decode_is_bit_exact_and_reports_refusals():
     got = out.cpu().numpy()
     for i in (0, 7, 39):
         assert np.array_equal(got[i], _pil_read_img(datas[i])), i
+
+
+def test_corrupt_scan_data_never_crashes_the_device_decoder():
+    """Random byte damage inside the entropy-coded segment: every file either decodes or is reported as refused, the
+    device never faults, and a clean batch through the same handle afterwards is still bit-exact."""
+    from vidsitu_b200.jpeg import JpegBatchDecoder, JpegDecoder
+    rng = np.random.default_rng(11)
+    base = [jpeg_bytes(*c, seed=50 + i) for i, c in enumerate(JPEG_CASES[:6])]
+    damaged = []
+    for i in range(48):
+        d = bytearray(base[i % len(base)])
+        lo = len(d) // 3                      # behind the headers
+        for _ in range(int(rng.integers(1, 12))):
+            d[int(rng.integers(lo, len(d) - 2))] = int(rng.integers(0, 256))
+        if i % 5 == 0:
+            del d[int(rng.integers(lo, len(d))):]     # and a truncation
+        damaged.append(bytes(d))
+    out = torch.zeros((len(damaged), 64, 64, 3), dtype=torch.uint8, device="cuda")
+    dec = JpegBatchDecoder()
+    ok = dec.decode_resize(damaged, list(out))
+    torch.cuda.synchronize()
+    assert len(ok) == len(damaged) and any(ok) and not all(ok)
+    hyb = JpegDecoder(640, 640)
+    from vidsitu_b200.lib import VsbError
+    for i, d in enumerate(damaged[:16]):      # the hybrid path agrees on which files are decodable, and on their pixels
+        o = torch.zeros((64, 64, 3), dtype=torch.uint8, device="cuda")
+        try:
+            hyb.decode_resize(d, o)
+            good = True
+        except VsbError:
+            good = False
+        assert good == ok[i], i
+        if good:
+            assert torch.equal(o, out[i]), i
+    clean = torch.empty((len(base), 224, 224, 3), dtype=torch.uint8, device="cuda")
+    assert all(dec.decode_resize(base, list(clean)))
+    got = clean.cpu().numpy()
+    for i, d in enumerate(base):
+        assert np.array_equal(got[i], _pil_read_img(d)), i

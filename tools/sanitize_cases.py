@@ -75,6 +75,22 @@ eng.feats.zero_()
 prog.run()
 torch.cuda.synchronize()
 report("program/sf50_crop64", {"ok": bool(torch.equal(eng.feats, want)), "max_abs_err": float((eng.feats - want).abs().max())})
+# frame ingest: hybrid and fully-on-device JPEG decode (4:2:0, odd size; 4:4:4) against Pillow
+import io as _io
+import numpy as _np
+from PIL import Image as _Image
+from common import jpeg_bytes as _jpeg_bytes
+from vidsitu_b200.jpeg import JpegBatchDecoder as _JB, JpegDecoder as _JD
+_datas = [_jpeg_bytes(77, 53, 90, 2, "noisy"), _jpeg_bytes(48, 64, 75, 0, "noisy"), _jpeg_bytes(50, 70, 85, 1, "smooth")]
+_out = torch.zeros((3, 32, 32, 3), dtype=torch.uint8, device="cuda")
+_okb = _JB().decode_resize(_datas, list(_out))
+torch.cuda.synchronize()
+_ref = [_np.array(_Image.open(_io.BytesIO(d)).convert("RGB").resize((32, 32))) for d in _datas]
+report("jpeg/device_batch", {"ok": all(_okb) and all(_np.array_equal(_out[i].cpu().numpy(), _ref[i]) for i in range(3))})
+_o1 = torch.zeros((32, 32, 3), dtype=torch.uint8, device="cuda")
+_JD(128, 128).decode_resize(_datas[0], _o1)
+torch.cuda.synchronize()
+report("jpeg/hybrid", {"ok": bool(_np.array_equal(_o1.cpu().numpy(), _ref[0]))})
 if "--mem" in sys.argv:
     for k, v in G.run_mem_checks().items():
         report("mem/" + k, v)
