@@ -72,7 +72,6 @@ struct StemParams {
   int out_pitch;
   int t_clip;                  // kt = 5 kernel: frames per clip (temporal taps never cross clips)
   long long total_runs;        // kt = 5 kernel: clips * tiles per frame
-  int dbg;   // timing experiments only (VSB_STEM_DBG): 1 = plain stores instead of red, 2 = no pooling phase
 };
 
 __device__ __forceinline__ void red_max_bf16x2_v4(void* gptr, uint4 v) {
@@ -123,7 +122,7 @@ __device__ __forceinline__ void epilogue_tile(const StemParams& p, const float2*
   if (lane == 0) mbar_arrive(empty_bar);
   named_bar_sync(bar_id, 128);   // the whole conv tile is in shared memory
   // pooled rows 4 th + pl (pl = 0..4), columns 8 tw + ql (ql = 0..8), 8 chunks of 8 channels each
-  for (int item = et; item < ((p.dbg & 2) ? 0 : 5 * 9 * 8); item += 128) {
+  for (int item = et; item < 5 * 9 * 8; item += 128) {
     const int k = item & 7, pq = item >> 3;
     const int pl = pq / 9, ql = pq - pl * 9;
     const int pg = th * 4 + pl, qg = tw * 8 + ql;
@@ -149,7 +148,7 @@ __device__ __forceinline__ void epilogue_tile(const StemParams& p, const float2*
     // seam outputs get contributions from two or four tiles; image-edge outputs (pl == 0 in the first tile
     // row, ql == 0 in the first tile column) are complete: the missing row / column is -inf padding
     const bool seam = (pl == 0 && th > 0) || pl == 4 || (ql == 0 && tw > 0) || ql == 8;
-    if (seam && !(p.dbg & 1))
+    if (seam)
       red_max_bf16x2_v4(dst, m);
     else
       *reinterpret_cast<uint4*>(dst) = m;
@@ -558,7 +557,6 @@ extern "C" int vsb_stem_pool_plan_create(const vsb_stem_pool_desc* d, vsb_stem_p
   p.out_pitch = d->out_pitch;
   p.t_clip = d->kt == 5 ? d->t : 1;
   p.total_runs = (long long)(d->frames / p.t_clip) * p.tiles_h * p.tiles_w;
-  p.dbg = getenv("VSB_STEM_DBG") ? atoi(getenv("VSB_STEM_DBG")) : 0;
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
