@@ -31,7 +31,7 @@ def main():
     from common import build_model
     from vidsitu_b200 import frames_io as F
     V = int(os.environ.get("VIDEOS", "96"))
-    B = 8
+    B = int(os.environ.get("VPB", "8"))
     needed = F.needed_frames(32, 2)
     res = {"videos": V, "frames_per_video": len(needed), "frame": "640x360 4:2:0 quality 90", "host_cpus": os.cpu_count(),
            "videos_per_batch": B}
