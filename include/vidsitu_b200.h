@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VSB_ABI_VERSION 7
+#define VSB_ABI_VERSION 8
 
 typedef enum vsb_status {
   VSB_OK = 0,
@@ -207,8 +207,14 @@ typedef struct vsb_bottleneck_desc {
   const float* sa; const float* ba;
   const float* sb; const float* bb;
   const float* sc; const float* bc;
-  /* tuning, 0 = automatic: x ring depth, tiles per walk, CTAs */
+  /* tuning, 0 = automatic: x ring depth, tiles per walk (algo 1: rows per strip), CTAs */
   int stages, walk_len, grid;
+  /* ABI v8.  0 = tcgen05 flat-raster kernel (bottleneck_fused_sm100.cu).  1 = warp-level MMA walk kernel for THIN
+   * blocks (bottleneck_thin_sm100.cu): d = 8 or 16 UNGROUPED stored channels, c = 4 d, x dense (x_pitch == c); a CTA
+   * walks a strip of rows through time, every frame of the strip is fetched once by one bulk copy, the three convs
+   * run on mma.sync fragments (the Fast pathway's res2 / res3, where a tcgen05.mma would be N <= 64 wide and
+   * issue-bound).  Same tensors, weight layouts and rounding points as algo 0. */
+  int algo;
 } vsb_bottleneck_desc;
 
 typedef struct vsb_bottleneck_plan vsb_bottleneck_plan;

@@ -314,13 +314,37 @@ def test_fused_blocks_inside_the_network():
     frames = synthetic_frames(m["clips"], 32, m["crop"], seed=1234 + m["seed"]).cuda()
     outs = {}
     for fuse in ("0", "1"):
-        model, cfg, _ = build_model(m["sf_mdl_name"], seed=m["seed"], crop=m["crop"], tune={"*": {"fuse_block": fuse}})
+        model, cfg, _ = build_model(m["sf_mdl_name"], seed=m["seed"], crop=m["crop"],
+                                    tune={"*": {"fuse_block": fuse, "thin_block": False}})
         model = model.cuda()
         outs[fuse] = model.extract_features(frames).cpu().numpy()
         eng = model._engine(m["clips"], frames.device)
         assert (len(eng.fused_blocks) > 0) == (fuse == "1"), eng.fused_blocks
     assert_bf16_close(outs["1"], g["pooled"], "fused-block engine pooled")
     assert cosine(outs["1"], outs["0"]) >= 0.99999
+
+
+def test_thin_blocks_inside_the_network():
+    """Engine with the identity blocks of the Fast pathway's res2 / res3 on the warp-MMA walk kernel (vsb_bottleneck_*
+    algo 1, the default) against the three-launch engine: both within the bf16 tolerance of the reference's outputs,
+    and as close to each other as two bf16 roundings of the same sums can be."""
+    for case in ("sf50_n2_64", "sf50_n5_224"):
+        if case not in META:
+            continue
+        m = META[case]
+        g = np.load(os.path.join(GOLD, case + ".npz"))
+        frames = synthetic_frames(m["clips"], 32, m["crop"], seed=1234 + m["seed"]).cuda()
+        outs = {}
+        for thin in (False, True):
+            model, cfg, _ = build_model(m["sf_mdl_name"], seed=m["seed"], crop=m["crop"], tune={"*": {"thin_block": thin}})
+            model = model.cuda()
+            outs[thin] = model.extract_features(frames).cpu().numpy()
+            eng = model._engine(m["clips"], frames.device)
+            assert (len(eng.fused_blocks) > 0) == thin, eng.fused_blocks
+            if thin:
+                assert any(".pathway1_" in b for b in eng.fused_blocks)
+        assert_bf16_close(outs[True], g["pooled"], "thin-block engine pooled")
+        assert cosine(outs[True], outs[False]) >= 0.99999
 
 
 def test_extract_features_returns_a_copy():

@@ -19,7 +19,7 @@ from vidsitu_b200.weights import fold_bn, pack_conv_weight, stem_quad_weight
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = L.load()
-    assert lib.vsb_abi_version() == 7
+    assert lib.vsb_abi_version() == 8
     declared = set()
     for hdr in ("vidsitu_b200.h", "vidsitu_b200_debug.h"):
         src = open(os.path.join(ROOT, "include", hdr)).read()

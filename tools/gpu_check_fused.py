@@ -47,6 +47,23 @@ CASES = [
     ("pitched", 2, 4, 14, 14, 64, 16, 3, {}, 96, 80),
     ("c256_d64_kt1_small", 1, 2, 14, 14, 256, 64, 1, {}, 0, 0),
     ("many_tiles", 8, 32, 28, 28, 64, 16, 3, {}, 0, 0),
+    # algo 1: the warp-MMA walk kernel (bottleneck_thin_sm100.cu), ungrouped thin blocks d = 8 / 16, c = 4 d
+    ("thin_s2_like", 2, 8, 56, 56, 32, 8, 3, dict(algo=1), 0, 0),
+    ("thin_s3_like", 2, 8, 28, 28, 64, 16, 3, dict(algo=1), 0, 0),
+    ("thin_tiny_7x7", 3, 8, 7, 7, 64, 16, 3, dict(algo=1), 0, 0),
+    ("thin_odd_13x11_d8", 2, 5, 13, 11, 32, 8, 3, dict(algo=1), 0, 0),
+    ("thin_odd_13x11_d16", 2, 5, 13, 11, 64, 16, 3, dict(algo=1), 0, 0),
+    ("thin_kt1_d8", 2, 4, 28, 28, 32, 8, 1, dict(algo=1), 0, 0),
+    ("thin_kt1_d16", 2, 4, 14, 14, 64, 16, 1, dict(algo=1), 0, 0),
+    ("thin_t1", 2, 1, 14, 14, 32, 8, 3, dict(algo=1), 0, 0),
+    ("thin_t2", 2, 2, 14, 14, 64, 16, 3, dict(algo=1), 0, 0),
+    ("thin_rows3_grid5", 2, 8, 28, 28, 64, 16, 3, dict(algo=1, walk_len=3, grid=5), 0, 0),
+    ("thin_rows5_grid3_d8", 3, 6, 28, 28, 32, 8, 3, dict(algo=1, walk_len=5, grid=3), 0, 0),
+    ("thin_slots4", 2, 8, 28, 28, 64, 16, 3, dict(algo=1, stages=4), 0, 0),
+    ("thin_pitched_out", 2, 4, 14, 14, 64, 16, 3, dict(algo=1), 0, 80),
+    ("thin_crop64_s2", 2, 32, 16, 16, 32, 8, 3, dict(algo=1), 0, 0),
+    ("thin_crop64_s3", 2, 32, 8, 8, 64, 16, 3, dict(algo=1), 0, 0),
+    ("thin_many_steps", 8, 32, 28, 28, 64, 16, 3, dict(algo=1), 0, 0),
 ]
 
 # full-size blocks of SlowFast-R50 8x8, batch 64 (Fast pathway res2 on 2-pixel groups, res3, res4)
@@ -55,6 +72,10 @@ BENCH_CASES = [
     ("bench_fast_s2_plain", 64, 32, 56, 56, 32, 16, 3, {}, 0, 0),
     ("bench_fast_s3", 64, 32, 28, 28, 64, 16, 3, {}, 0, 0),
     ("bench_fast_s4", 64, 32, 14, 14, 128, 32, 3, {}, 0, 0),
+    ("bench_thin_s2", 64, 32, 56, 56, 32, 8, 3, dict(algo=1), 0, 0),
+    ("bench_thin_s3", 64, 32, 28, 28, 64, 16, 3, dict(algo=1), 0, 0),
+    ("bench_thin_s2_slots4", 64, 32, 56, 56, 32, 8, 3, dict(algo=1, stages=4), 0, 0),
+    ("bench_thin_s2_rows7", 64, 32, 56, 56, 32, 8, 3, dict(algo=1, walk_len=7), 0, 0),
 ]
 
 
@@ -150,6 +171,8 @@ def child(args):
     report["device"] = torch.cuda.get_device_name(0)
     try:
         cases = [(c, False) for c in CASES] + ([(c, True) for c in BENCH_CASES] if args.bench else [])
+        if args.only:
+            cases = [cb for cb in cases if args.only in cb[0][0]]
         for case, bench in cases:
             if case[0] in report["fused"]:
                 continue
@@ -180,6 +203,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/check_fused.json")
     ap.add_argument("--bench", action="store_true")
     ap.add_argument("--child", action="store_true")
+    ap.add_argument("--only", default="", help="run only the cases whose name contains this string")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     if args.child:
@@ -188,6 +212,8 @@ def main():
         os.remove(args.out)
     for attempt in range(30):
         cmd = [sys.executable, os.path.abspath(__file__), "--child", "--out", args.out] + (["--bench"] if args.bench else [])
+        if args.only:
+            cmd += ["--only", args.only]
         try:
             rc = subprocess.run(cmd, timeout=300).returncode
         except subprocess.TimeoutExpired:

@@ -35,6 +35,7 @@
 #include <mutex>
 #include <new>
 
+#include "bottleneck_thin.h"
 #include "common.h"
 #include "conv_plan.h"
 #include "epilogue.cuh"
@@ -819,6 +820,7 @@ using namespace vsb;
 
 struct vsb_bottleneck_plan {
   vsb_bottleneck_desc desc;
+  ThinPlan* thin = nullptr;  // algo 1: the warp-MMA walk kernel owns the launch (bottleneck_thin_sm100.cu)
   CUtensorMap map_x, map_wa, map_wb, map_wc, map_res, map_out;
   FusedParams params;
   size_t smem_bytes;
@@ -845,6 +847,25 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
   VSB_CHECK_ARG(d->sa && d->ba && d->sb && d->bb && d->sc && d->bc, "null scale / bias pointer");
   VSB_CHECK_ARG(d->n > 0 && d->t > 0 && d->h > 0 && d->w > 0, "non-positive extent");
   VSB_CHECK_ARG(d->kt == 1 || d->kt == 3, "kt must be 1 or 3");
+  VSB_CHECK_ARG(d->algo == 0 || d->algo == 1, "algo must be 0 (tcgen05 flat raster) or 1 (warp-MMA walk)");
+  if (d->algo == 1) {
+    VSB_CHECK_ARG(((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->out) |
+                    reinterpret_cast<uintptr_t>(d->wa) | reinterpret_cast<uintptr_t>(d->wb) |
+                    reinterpret_cast<uintptr_t>(d->wc)) & 15) == 0, "tensor pointers must be 16-byte aligned");
+    ThinPlan* thin = nullptr;
+    const int rc = thin_plan_create(d, &thin);
+    if (rc != VSB_OK) return rc;
+    vsb_bottleneck_plan* plan = new (std::nothrow) vsb_bottleneck_plan();
+    if (!plan) {
+      thin_plan_destroy(thin);
+      set_error("out of host memory");
+      return VSB_ERR_INVALID;
+    }
+    plan->desc = *d;
+    plan->thin = thin;
+    *out_plan = plan;
+    return VSB_OK;
+  }
   VSB_CHECK_ARG(d->d == 16 || d->d == 32 || d->d == 64, "bottleneck width (stored) must be 16, 32 or 64");
   VSB_CHECK_ARG(d->c % 16 == 0 && d->c >= 16 && d->c <= 256, "block width (stored) must be a multiple of 16 in [16, 256]");
   VSB_CHECK_ARG(d->x_pitch >= d->c && d->out_pitch >= d->c && d->x_pitch % 8 == 0 && d->out_pitch % 8 == 0,
@@ -1091,6 +1112,7 @@ extern "C" int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* d, vsb_bott
 
 extern "C" int vsb_bottleneck_run(const vsb_bottleneck_plan* plan, void* stream) {
   VSB_CHECK_ARG(plan, "null plan");
+  if (plan->thin) return thin_run(plan->thin, stream);
   if (plan->params.dbg)
     bottleneck_fused_kernel<true><<<plan->grid, kThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(
         plan->map_x, plan->map_wa, plan->map_wb, plan->map_wc, plan->map_res, plan->map_out, plan->params);
@@ -1101,10 +1123,14 @@ extern "C" int vsb_bottleneck_run(const vsb_bottleneck_plan* plan, void* stream)
   return VSB_OK;
 }
 
-extern "C" void vsb_bottleneck_plan_destroy(vsb_bottleneck_plan* plan) { delete plan; }
+extern "C" void vsb_bottleneck_plan_destroy(vsb_bottleneck_plan* plan) {
+  if (plan && plan->thin) thin_plan_destroy(plan->thin);
+  delete plan;
+}
 
 extern "C" int vsb_debug_bottleneck_stats(const vsb_bottleneck_plan* plan, long long* out32) {
   VSB_CHECK_ARG(plan && out32, "null argument");
+  VSB_CHECK_ARG(!plan->thin, "the warp-MMA kernel keeps no role timeline");
   VSB_CHECK_ARG(plan->params.dbg, "plan was not created with VSB_FUSED_DEBUG=1");
   VSB_CHECK_CUDA(cudaDeviceSynchronize());
   VSB_CHECK_CUDA(cudaMemcpy(out32, plan->params.dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -1114,6 +1140,10 @@ extern "C" int vsb_debug_bottleneck_stats(const vsb_bottleneck_plan* plan, long 
 
 extern "C" int vsb_bottleneck_plan_info(const vsb_bottleneck_plan* plan, long long* out8) {
   VSB_CHECK_ARG(plan && out8, "null argument");
+  if (plan->thin) {  // {rows per strip, strips per frame, ring slots, frame steps per CTA, grid, smem bytes, a tiles * 1000 + bc tiles, 0}
+    thin_plan_info(plan->thin, out8);
+    return VSB_OK;
+  }
   const FusedParams& p = plan->params;
   out8[0] = p.RP;
   out8[1] = p.FP;

@@ -1,0 +1,612 @@
+// Fused identity bottleneck for THIN blocks (bottleneck width d = 8 or 16, block width c = 4 d: the Fast pathway's
+// res2 / res3 of SlowFast), algo 1 of vsb_bottleneck_*:  out = relu(x + BN_c(c(relu(BN_b(b(relu(BN_a(a(x)))))))))
+// in ONE launch, with the matrix products on WARP-LEVEL tensor-core MMAs (mma.sync m16n8k16 / m16n8k8, bf16 in,
+// fp32 accumulate) instead of tcgen05.
+//
+// Reference ops replaced: BottleneckTransform a -> b -> c (SlowFast/slowfast/models/resnet_helper.py:225-240) and the
+// identity ResBlock around it (resnet_helper.py:352-358), as bottleneck_fused_sm100.cu (algo 0).
+//
+// Why not tcgen05 here.  With 8 / 16 output channels a tcgen05.mma is N <= 64 wide whatever the restatement, i.e. at
+// the ~60-clk issue floor of one elected thread (profiles/r02_umma_commit_pitch_shift_rate.json), and the x tiles of
+// the flat-raster kernel move as 5-D TMA boxes at 10 - 21 B/clk/SM: algo 0 is bound by issue, not by HBM, and ends at
+// parity with the three launches.  A warp-level MMA is exactly 8 channels wide, sixteen warps issue independently,
+// and the operands are plain shared-memory / register fragments.
+//
+// Schedule.  A CTA owns a strip of R output rows of one clip (full width) and WALKS it through time.  Per frame the
+// strip plus one halo row above and below is ONE contiguous range of the NTHWC tensor, fetched by a single
+// cp.async.bulk (no tensor map) into a ring of S frame slots; every frame is fetched once and used by the three
+// temporal taps of `a` and by the residual.  Warp roles (17 warps):
+//   a-warps  0-7  : a[t] = relu(BN(sum_taps x[t + tap - 1] . Wa[tap])) for the strip + halo rows, 16-pixel MMA tiles,
+//                   Wa fragments resident in registers; result -> bf16 -> one of two a-tile buffers in shared memory
+//                   laid out (R + 2) x (W + 2) pixels with a zero border (= the padding of the 3x3 conv)
+//   bc-warps 8-15 : b = relu(BN(sum_taps a[.. + dy, .. + dx] . Wb[tap])) from the a-tile buffer (every tap is a shifted
+//                   shared-memory read), the b accumulator fragment IS the A fragment of c (no exchange), c 32 channels
+//                   at a time, + BN + residual (x[t] from the ring) + ReLU -> 16-byte global stores
+//   warp 16       : producer (one lane): waits for a free slot, arms the slot's mbarrier, issues the bulk copy
+// The two a-tile buffers let the a-warps run one frame ahead of the bc-warps.  All handshakes are mbarriers with
+// bounded waits (a protocol bug traps, it never hangs the GPU).
+//
+// Channel permutation.  The K order of `a` and the N order of `c` are free as long as weights and activations agree,
+// so thread (g, t) of a warp owns, for pixel rows g and g + 8, the 16-byte pieces [8 (4 q + t), + 8) of the pixel's
+// channels (q = 0 .. c / 32 - 1): its x fragments are 128-bit shared loads, its residual is already in the layout of
+// the c accumulator, and its output is one 16-byte store per 32 channels; the weight fragments are gathered with the
+// same permutation once per CTA.  Pixel rows of 128 bytes and more would make two pixel rows of a quarter-warp hit
+// the same banks: lanes with odd g fetch the pieces of q and q ^ 1 in swapped order and swap them back in registers.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <new>
+
+#include "bottleneck_thin.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vsb {
+
+namespace {
+constexpr int kAWarps = 8, kBCWarps = 8;
+constexpr int kProducerWarp = kAWarps + kBCWarps;
+constexpr int kThinThreads = (kAWarps + kBCWarps + 1) * 32;
+constexpr int kMaxSlots = 8;
+}  // namespace
+
+struct ThinParams {
+  const uint8_t* x;
+  uint8_t* out;
+  const __nv_bfloat16 *wa, *wb, *wc;
+  const float *sa, *ba, *sb, *bb, *sc, *bc;
+  int n, T, H, W;
+  int R, row_tiles;
+  uint32_t out_pitch_bytes;
+  int S;
+  uint32_t slot_bytes, row_bytes;
+  int a_px, a_tiles, bc_px, bc_tiles;
+  uint32_t a_pitch, a_buf_bytes;
+  uint32_t off_abuf, off_sbc, off_bar;
+  uint32_t magic_w;  // floor(2^24 / W) + 1: px / W == (px * magic_w) >> 24 for px < 2^24 / W
+  long long total_steps;
+  int steps_per_cta;
+};
+
+namespace {
+
+__device__ __forceinline__ uint32_t t_lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 t_lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 t_lds128f(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void t_sts32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void t_stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// D (16 x 8, fp32) += A (16 x 16, bf16, row) . B (16 x 8, bf16, col)
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// D (16 x 8, fp32) += A (16 x 8, bf16, row) . B (8 x 8, bf16, col)
+__device__ __forceinline__ void mma1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+}
+// contiguous global -> shared copy by the TMA unit (no tensor map), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint32_t sel(bool c, uint32_t a, uint32_t b) { return c ? a : b; }
+
+// The 16-byte pieces (q = 0 .. NQ-1) of one pixel row for thread t: v[q] = bytes [64 q + 16 t, + 16) of the pixel.
+template <int NQ>
+__device__ __forceinline__ void load_pieces(uint32_t px_addr, int t, bool odd, uint4 (&v)[NQ]) {
+  if (NQ == 1) {
+    v[0] = t_lds128(px_addr + 16 * t);
+  } else {
+#pragma unroll
+    for (int m = 0; m < NQ / 2; ++m) {
+      const uint32_t base = px_addr + 128 * m + 16 * t;
+      const uint4 first = t_lds128(base + (odd ? 64u : 0u));
+      const uint4 second = t_lds128(base + (odd ? 0u : 64u));
+      v[2 * m].x = sel(odd, second.x, first.x); v[2 * m].y = sel(odd, second.y, first.y);
+      v[2 * m].z = sel(odd, second.z, first.z); v[2 * m].w = sel(odd, second.w, first.w);
+      v[2 * m + 1].x = sel(odd, first.x, second.x); v[2 * m + 1].y = sel(odd, first.y, second.y);
+      v[2 * m + 1].z = sel(odd, first.z, second.z); v[2 * m + 1].w = sel(odd, first.w, second.w);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t piece_reg(const uint4& v, int i) {
+  return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+// One walk = the frames [t0, t1) of one (clip, row strip) unit that a CTA processes back to back; the frames
+// [f_lo, f_hi] are fetched for it (one halo frame on either side for the temporal taps), in this order.
+struct ThinWalk {
+  long long cur, end;
+  int n, r0, t0, t1, f_lo, f_hi;
+  uint32_t l0;  // load index of frame f_lo (running count of fetched frames of this CTA)
+  __device__ __forceinline__ void init(const ThinParams& p) {
+    cur = (long long)blockIdx.x * p.steps_per_cta;
+    end = cur + p.steps_per_cta < p.total_steps ? cur + p.steps_per_cta : p.total_steps;
+    l0 = 0;
+  }
+  template <int HT>
+  __device__ __forceinline__ bool load(const ThinParams& p) {
+    if (cur >= end) return false;
+    const long long unit = cur / p.T;
+    t0 = (int)(cur - unit * p.T);
+    long long len = end - cur;
+    if (len > p.T - t0) len = p.T - t0;
+    t1 = t0 + (int)len;
+    n = (int)(unit / p.row_tiles);
+    r0 = (int)(unit - (long long)n * p.row_tiles) * p.R;
+    f_lo = t0 - HT > 0 ? t0 - HT : 0;
+    f_hi = t1 - 1 + HT < p.T - 1 ? t1 - 1 + HT : p.T - 1;
+    return true;
+  }
+  __device__ __forceinline__ void next() {
+    l0 += (uint32_t)(f_hi - f_lo + 1);
+    cur += t1 - t0;
+  }
+};
+
+}  // namespace
+
+template <int D, int KT>
+__global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const ThinParams p) {
+  constexpr int C = 4 * D;        // block width
+  constexpr int NQ = D / 8;       // 32-channel groups of the block width = 8-channel slices of the bottleneck width
+  constexpr int NTD = D / 8;      // 8-column MMA tiles of the bottleneck width
+  constexpr int HT = KT / 2;
+  constexpr int CB = C * 2;       // bytes per x pixel
+  constexpr int NSL = 9 * NQ;     // 8-channel K slices of conv b (tap-major)
+  constexpr int NP = (NSL + 1) / 2;
+  constexpr int KSC = D >= 16 ? D / 16 : 1;  // K steps of conv c
+
+  extern __shared__ uint8_t thin_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(thin_smem_raw) + 127) & ~uintptr_t(127));
+  const uint32_t ring_s = smem_u32(smem);
+  const uint32_t abuf_s = ring_s + p.off_abuf;
+  const uint32_t sbc_s = ring_s + p.off_sbc;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* empty = full + kMaxSlots;
+  uint64_t* a_full = empty + kMaxSlots;
+  uint64_t* a_empty = a_full + 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const bool odd = (g & 1) != 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kAWarps + kBCWarps);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&a_full[b], kAWarps);
+      mbar_init(&a_empty[b], kBCWarps);
+    }
+    fence_mbar_init();
+  }
+  // zero both a-tile buffers once: the border columns are never written again
+  for (uint32_t i = threadIdx.x * 16; i < 2 * p.a_buf_bytes; i += kThinThreads * 16)
+    *reinterpret_cast<uint4*>(smem + p.off_abuf + i) = make_uint4(0, 0, 0, 0);
+  // (scale, bias) of conv c in the order the c epilogue reads them: entry (q * 4 + i) * 4 + t = channels
+  // 8 (4 q + t) + 2 i, + 1
+  for (int e = threadIdx.x; e < NQ * 16; e += kThinThreads) {
+    const int tt = e & 3, i = (e >> 2) & 3, q = e >> 4;
+    const int ch = 8 * (4 * q + tt) + 2 * i;
+    reinterpret_cast<float4*>(smem + p.off_sbc)[e] = make_float4(p.sc[ch], p.bc[ch], p.sc[ch + 1], p.bc[ch + 1]);
+  }
+  __syncthreads();
+
+  ThinWalk wk;
+  wk.init(p);
+
+  if (warp == kProducerWarp) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t slot = 0, round = 0;  // load index L = round * S + slot
+      while (wk.load<HT>(p)) {
+        const int row_lo = wk.r0 - 1 > 0 ? wk.r0 - 1 : 0;
+        const int row_hi = wk.r0 + p.R + 1 < p.H ? wk.r0 + p.R + 1 : p.H;
+        const uint32_t bytes = (uint32_t)(row_hi - row_lo) * p.row_bytes;
+        const uint32_t dst_off = (uint32_t)(row_lo - (wk.r0 - 1)) * p.row_bytes;
+        for (int f = wk.f_lo; f <= wk.f_hi; ++f) {
+          if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+          const uint8_t* src = p.x + (((long long)wk.n * p.T + f) * p.H + row_lo) * (long long)p.row_bytes;
+          mbar_expect_tx(&full[slot], bytes);
+          bulk_g2s(ring_s + slot * p.slot_bytes + dst_off, src, bytes, &full[slot]);
+          if (++slot == (uint32_t)p.S) {
+            slot = 0;
+            ++round;
+          }
+        }
+        wk.next();
+      }
+    }
+  } else if (warp < kAWarps) {
+    // ------------------------------------------------------------------ conv a
+    // weight fragments: step (tap, q, h) of K, column tile nt: b0 = Wa[8 nt + g][tap][8 (4 q + t) + 4 h + {0, 1}],
+    // b1 = the next two channels
+    uint2 wa_f[KT][NQ][2][NTD];
+#pragma unroll
+    for (int tap = 0; tap < KT; ++tap)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int nt = 0; nt < NTD; ++nt)
+            wa_f[tap][q][h][nt] = *reinterpret_cast<const uint2*>(
+                p.wa + ((size_t)(8 * nt + g) * KT + tap) * C + 8 * (4 * q + t4) + 4 * h);
+    float4 sa_f[NTD];  // (scale, bias) of channels 8 nt + 2 t, + 1
+#pragma unroll
+    for (int nt = 0; nt < NTD; ++nt) {
+      const int ch = 8 * nt + 2 * t4;
+      sa_f[nt] = make_float4(p.sa[ch], p.ba[ch], p.sa[ch + 1], p.ba[ch + 1]);
+    }
+    uint32_t istep = 0;
+    while (wk.load<HT>(p)) {
+      for (int t = wk.t0; t < wk.t1; ++t, ++istep) {
+        const uint32_t b = istep & 1;
+        if (istep >= 2) mbar_wait(&a_empty[b], ((istep >> 1) - 1) & 1);
+        uint32_t slot_s[KT];
+        bool have[KT];
+#pragma unroll
+        for (int tap = 0; tap < KT; ++tap) {
+          const int f = t + tap - HT;
+          have[tap] = f >= 0 && f < p.T;
+          slot_s[tap] = ring_s;
+          if (have[tap]) {
+            const uint32_t L = wk.l0 + (uint32_t)(f - wk.f_lo);
+            const uint32_t slot = L % (uint32_t)p.S;
+            mbar_wait(&full[slot], (L / (uint32_t)p.S) & 1);
+            slot_s[tap] = ring_s + slot * p.slot_bytes;
+          }
+        }
+        const uint32_t dst_s = abuf_s + b * p.a_buf_bytes;
+        for (int tile = warp; tile < p.a_tiles; tile += kAWarps) {
+          const int px_g = tile * 16 + g, px_h = px_g + 8;
+          const int pc_g = px_g < p.a_px ? px_g : p.a_px - 1, pc_h = px_h < p.a_px ? px_h : p.a_px - 1;
+          float acc[NTD][4];
+#pragma unroll
+          for (int nt = 0; nt < NTD; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+          for (int tap = 0; tap < KT; ++tap) {
+            if (!have[tap]) continue;
+            uint4 vg[NQ], vh[NQ];
+            load_pieces<NQ>(slot_s[tap] + (uint32_t)pc_g * CB, t4, odd, vg);
+            load_pieces<NQ>(slot_s[tap] + (uint32_t)pc_h * CB, t4, odd, vh);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int nt = 0; nt < NTD; ++nt)
+                  mma16816(acc[nt], piece_reg(vg[q], 2 * h), piece_reg(vh[q], 2 * h), piece_reg(vg[q], 2 * h + 1),
+                           piece_reg(vh[q], 2 * h + 1), wa_f[tap][q][h][nt].x, wa_f[tap][q][h][nt].y);
+          }
+          // BN + ReLU -> bf16 -> a-tile buffer; rows outside the image are the zero padding of conv b
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int px = half ? px_h : px_g;
+            if (px < p.a_px) {
+              const int rr = (int)(((uint32_t)px * p.magic_w) >> 24);
+              const int col = px - rr * p.W;
+              const int row = wk.r0 - 1 + rr;
+              const bool inside = row >= 0 && row < p.H;
+              const uint32_t dst = dst_s + (uint32_t)(rr * (p.W + 2) + col + 1) * p.a_pitch + 4 * t4;
+#pragma unroll
+              for (int nt = 0; nt < NTD; ++nt) {
+                const float v0 = fmaxf(fmaf(acc[nt][2 * half], sa_f[nt].x, sa_f[nt].y), 0.f);
+                const float v1 = fmaxf(fmaf(acc[nt][2 * half + 1], sa_f[nt].z, sa_f[nt].w), 0.f);
+                t_sts32(dst + 16 * nt, inside ? pack_bf16x2(v0, v1) : 0u);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_full[b]);
+          // frames conv a no longer needs
+          const int f_done = t - HT;
+          if (f_done >= wk.f_lo) mbar_arrive(&empty[(wk.l0 + (uint32_t)(f_done - wk.f_lo)) % (uint32_t)p.S]);
+          if (t == wk.t1 - 1)
+            for (int f = (f_done + 1 > wk.f_lo ? f_done + 1 : wk.f_lo); f <= wk.f_hi; ++f)
+              mbar_arrive(&empty[(wk.l0 + (uint32_t)(f - wk.f_lo)) % (uint32_t)p.S]);
+        }
+      }
+      wk.next();
+    }
+  } else {
+    // ------------------------------------------------------------------ conv b, conv c, residual, store
+    const int bw = warp - kAWarps;
+    // conv b: K slices s = tap * NQ + q of 8 channels, two per MMA: b0 = Wb[8 nt + g][tap][8 q + 2 t, + 1]
+    uint2 wb_f[NP][NTD];
+#pragma unroll
+    for (int pr = 0; pr < NP; ++pr)
+#pragma unroll
+      for (int nt = 0; nt < NTD; ++nt) {
+        const int s0 = 2 * pr, s1 = 2 * pr + 1;
+        const __nv_bfloat16* row = p.wb + (size_t)(8 * nt + g) * 9 * D;
+        wb_f[pr][nt].x = *reinterpret_cast<const uint32_t*>(row + (s0 / NQ) * D + 8 * (s0 % NQ) + 2 * t4);
+        wb_f[pr][nt].y = s1 < NSL ? *reinterpret_cast<const uint32_t*>(row + (s1 / NQ) * D + 8 * (s1 % NQ) + 2 * t4) : 0u;
+      }
+    // conv c: column tile (q, i) holds the output channels 8 (4 q + n / 2) + 2 i + n % 2 in its column n
+    uint2 wc_f[NQ][4][KSC];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int ks = 0; ks < KSC; ++ks) {
+          const int co = 8 * (4 * q + (g >> 1)) + 2 * i + (g & 1);
+          const __nv_bfloat16* row = p.wc + (size_t)co * D + 16 * ks + 2 * t4;
+          wc_f[q][i][ks].x = *reinterpret_cast<const uint32_t*>(row);
+          wc_f[q][i][ks].y = D >= 16 ? *reinterpret_cast<const uint32_t*>(row + 8) : 0u;
+        }
+    float4 sb_f[NTD];
+#pragma unroll
+    for (int nt = 0; nt < NTD; ++nt) {
+      const int ch = 8 * nt + 2 * t4;
+      sb_f[nt] = make_float4(p.sb[ch], p.bb[ch], p.sb[ch + 1], p.bb[ch + 1]);
+    }
+    const int wp2 = p.W + 2;
+    uint32_t istep = 0;
+    while (wk.load<HT>(p)) {
+      for (int t = wk.t0; t < wk.t1; ++t, ++istep) {
+        const uint32_t b = istep & 1;
+        mbar_wait(&a_full[b], (istep >> 1) & 1);
+        const uint32_t L = wk.l0 + (uint32_t)(t - wk.f_lo);
+        const uint32_t slot = L % (uint32_t)p.S;
+        mbar_wait(&full[slot], (L / (uint32_t)p.S) & 1);
+        const uint32_t xs = ring_s + slot * p.slot_bytes;
+        const uint32_t src_s = abuf_s + b * p.a_buf_bytes;
+        uint8_t* out_frame = p.out + (((long long)wk.n * p.T + t) * p.H + wk.r0) * (long long)p.W * p.out_pitch_bytes;
+        for (int tile = bw; tile < p.bc_tiles; tile += kBCWarps) {
+          int px[2] = {tile * 16 + g, tile * 16 + g + 8};
+          bool valid[2];
+          uint32_t ctr[2], res_s[2], out_off[2];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const bool in_tile = px[half] < p.bc_px;
+            const int pc = in_tile ? px[half] : p.bc_px - 1;
+            const int rr = (int)(((uint32_t)pc * p.magic_w) >> 24);
+            const int col = pc - rr * p.W;
+            valid[half] = in_tile && wk.r0 + rr < p.H;
+            ctr[half] = src_s + (uint32_t)((rr + 1) * wp2 + col + 1) * p.a_pitch + 4 * t4;
+            res_s[half] = xs + (uint32_t)((rr + 1) * p.W + col) * CB;
+            out_off[half] = (uint32_t)(rr * p.W + col) * p.out_pitch_bytes;
+          }
+          float accb[NTD][4];
+#pragma unroll
+          for (int nt = 0; nt < NTD; ++nt) accb[nt][0] = accb[nt][1] = accb[nt][2] = accb[nt][3] = 0.f;
+#pragma unroll
+          for (int pr = 0; pr < NP; ++pr) {
+            const int s0 = 2 * pr, s1 = 2 * pr + 1;
+            const int tap0 = s0 / NQ, q0 = s0 % NQ;
+            const int sh0 = ((tap0 / 3 - 1) * wp2 + (tap0 % 3 - 1)) * (int)p.a_pitch + 16 * q0;
+            const uint32_t a0 = t_lds32(ctr[0] + sh0), a1 = t_lds32(ctr[1] + sh0);
+            uint32_t a2 = 0u, a3 = 0u;
+            if (s1 < NSL) {
+              const int tap1 = s1 / NQ, q1 = s1 % NQ;
+              const int sh1 = ((tap1 / 3 - 1) * wp2 + (tap1 % 3 - 1)) * (int)p.a_pitch + 16 * q1;
+              a2 = t_lds32(ctr[0] + sh1);
+              a3 = t_lds32(ctr[1] + sh1);
+            }
+#pragma unroll
+            for (int nt = 0; nt < NTD; ++nt) mma16816(accb[nt], a0, a1, a2, a3, wb_f[pr][nt].x, wb_f[pr][nt].y);
+          }
+          // BN + ReLU -> bf16: the accumulator fragment of b is the A fragment of c
+          uint32_t pb[NTD][2];
+#pragma unroll
+          for (int nt = 0; nt < NTD; ++nt) {
+            pb[nt][0] = pack_bf16x2(fmaxf(fmaf(accb[nt][0], sb_f[nt].x, sb_f[nt].y), 0.f),
+                                    fmaxf(fmaf(accb[nt][1], sb_f[nt].z, sb_f[nt].w), 0.f));
+            pb[nt][1] = pack_bf16x2(fmaxf(fmaf(accb[nt][2], sb_f[nt].x, sb_f[nt].y), 0.f),
+                                    fmaxf(fmaf(accb[nt][3], sb_f[nt].z, sb_f[nt].w), 0.f));
+          }
+          uint4 rg[NQ], rh[NQ];  // residual = x[t] at the tile's pixels, already in the c accumulator's layout
+          load_pieces<NQ>(res_s[0], t4, odd, rg);
+          load_pieces<NQ>(res_s[1], t4, odd, rh);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            uint32_t og[4], oh[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float accc[4] = {0.f, 0.f, 0.f, 0.f};
+              if (D >= 16) {
+#pragma unroll
+                for (int ks = 0; ks < KSC; ++ks)
+                  mma16816(accc, pb[(2 * ks) % NTD][0], pb[(2 * ks) % NTD][1], pb[(2 * ks + 1) % NTD][0],
+                           pb[(2 * ks + 1) % NTD][1], wc_f[q][i][ks].x, wc_f[q][i][ks].y);
+              } else {
+                mma1688(accc, pb[0][0], pb[0][1], wc_f[q][i][0].x);
+              }
+              const float4 s4 = t_lds128f(sbc_s + (uint32_t)((q * 4 + i) * 4 + t4) * 16);
+              const uint32_t r_g = piece_reg(rg[q], i), r_h = piece_reg(rh[q], i);
+              og[i] = pack_bf16x2(fmaxf(fmaf(accc[0], s4.x, s4.y) + bf16_lo(r_g), 0.f),
+                                  fmaxf(fmaf(accc[1], s4.z, s4.w) + bf16_hi(r_g), 0.f));
+              oh[i] = pack_bf16x2(fmaxf(fmaf(accc[2], s4.x, s4.y) + bf16_lo(r_h), 0.f),
+                                  fmaxf(fmaf(accc[3], s4.z, s4.w) + bf16_hi(r_h), 0.f));
+            }
+            if (valid[0]) t_stg128(out_frame + out_off[0] + 64 * q + 16 * t4, og[0], og[1], og[2], og[3]);
+            if (valid[1]) t_stg128(out_frame + out_off[1] + 64 * q + 16 * t4, oh[0], oh[1], oh[2], oh[3]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_empty[b]);
+          mbar_arrive(&empty[slot]);
+          // halo frames of the walk that no bc step visits
+          if (t == wk.t0)
+            for (int f = wk.f_lo; f < wk.t0; ++f) mbar_arrive(&empty[(wk.l0 + (uint32_t)(f - wk.f_lo)) % (uint32_t)p.S]);
+          if (t == wk.t1 - 1)
+            for (int f = wk.t1; f <= wk.f_hi; ++f) mbar_arrive(&empty[(wk.l0 + (uint32_t)(f - wk.f_lo)) % (uint32_t)p.S]);
+        }
+      }
+      wk.next();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct ThinPlan {
+  ThinParams params;
+  size_t smem_bytes;
+  unsigned grid;
+  int d, kt;
+};
+
+template <int D, int KT>
+static cudaError_t thin_set_attr() {
+  return cudaFuncSetAttribute(bottleneck_thin_kernel<D, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+bool thin_eligible(const vsb_bottleneck_desc* d) {
+  return (d->d == 8 || d->d == 16) && d->c == 4 * d->d && d->x_pitch == d->c;
+}
+
+int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
+  *out_plan = nullptr;
+  VSB_CHECK_ARG(d->d == 8 || d->d == 16, "warp-MMA bottleneck: bottleneck width (stored) must be 8 or 16");
+  VSB_CHECK_ARG(d->c == 4 * d->d, "warp-MMA bottleneck: block width must be 4 x the bottleneck width");
+  VSB_CHECK_ARG(d->x_pitch == d->c, "warp-MMA bottleneck: x must be dense (pitch == c): frames are fetched as one range");
+  VSB_CHECK_ARG(d->out_pitch >= d->c && d->out_pitch % 8 == 0, "out pitch must be >= c and a multiple of 8 elements");
+  VSB_CHECK_ARG(d->w <= 256 && d->h <= 4096, "frame too large");
+  ThinParams p{};
+  p.x = static_cast<const uint8_t*>(d->x);
+  p.out = static_cast<uint8_t*>(d->out);
+  p.wa = static_cast<const __nv_bfloat16*>(d->wa);
+  p.wb = static_cast<const __nv_bfloat16*>(d->wb);
+  p.wc = static_cast<const __nv_bfloat16*>(d->wc);
+  p.sa = d->sa; p.ba = d->ba; p.sb = d->sb; p.bb = d->bb; p.sc = d->sc; p.bc = d->bc;
+  p.n = d->n; p.T = d->t; p.H = d->h; p.W = d->w;
+  p.out_pitch_bytes = (uint32_t)d->out_pitch * 2;
+  p.row_bytes = (uint32_t)d->w * d->c * 2;
+  p.a_pitch = d->d == 8 ? 16u : (uint32_t)d->d * 2 + 16;  // 48 B for d = 16: conflict-free 32-bit reads of 8 pixel rows
+  p.magic_w = (1u << 24) / (uint32_t)d->w + 1;
+  const int ht = d->kt / 2;
+  const int min_slots = d->kt + 1;
+  // rows per strip: the strip (+ 2 halo rows) is one ring slot; fewest fetched rows per frame among the strips that
+  // leave room for min_slots + 1 slots (caller's override: walk_len)
+  const long long budget = 227ll * 1024 - 4096;
+  int best_r = 0, best_s = 0;
+  long long best_cost = 0;
+  for (int r = d->h; r >= 1; --r) {
+    if (d->walk_len > 0 && r != d->walk_len) continue;
+    const long long slot = (long long)(r + 2) * p.row_bytes;
+    const long long abuf = (long long)(r + 2) * (d->w + 2) * p.a_pitch;
+    const long long abuf_al = (abuf + 127) / 128 * 128;
+    long long s = (budget - 2 * abuf_al - 1024) / slot;
+    if (s > 6) s = 6;
+    if (d->stages > 0 && s > d->stages) s = d->stages;
+    if (s < min_slots) continue;
+    if ((long long)(r + 2) * d->w * 2 > (1 << 16)) continue;
+    // cost: rows fetched per frame (halo included), a small penalty for a short ring
+    const long long cost = (long long)ceil_div(d->h, r) * (r + 2) * 16 + (s < min_slots + 1 ? 8 : 0);
+    if (!best_r || cost < best_cost) {
+      best_r = r;
+      best_s = (int)s;
+      best_cost = cost;
+    }
+  }
+  if (!best_r) {
+    set_error("warp-MMA bottleneck: no row strip of a %d x %d x %d frame fits %d ring slots in shared memory", d->h, d->w,
+              d->c, min_slots);
+    return VSB_ERR_INVALID;
+  }
+  (void)ht;
+  p.R = best_r;
+  p.S = best_s;
+  p.row_tiles = ceil_div(d->h, p.R);
+  p.slot_bytes = (uint32_t)(p.R + 2) * p.row_bytes;
+  p.a_px = (p.R + 2) * d->w;
+  p.a_tiles = ceil_div(p.a_px, 16);
+  p.bc_px = p.R * d->w;
+  p.bc_tiles = ceil_div(p.bc_px, 16);
+  p.a_buf_bytes = (uint32_t)(((long long)(p.R + 2) * (d->w + 2) * p.a_pitch + 127) / 128 * 128);
+  // a tile's tail rows may read up to 16 pixels past the last slot: keep the a-tile buffers behind the ring
+  p.off_abuf = (uint32_t)p.S * p.slot_bytes;
+  p.off_abuf = (p.off_abuf + 127u) & ~127u;
+  p.off_sbc = p.off_abuf + 2 * p.a_buf_bytes;
+  p.off_bar = p.off_sbc + (uint32_t)(d->d / 8) * 16 * 16;
+  const size_t smem_bytes = (size_t)p.off_bar + (2 * kMaxSlots + 4) * 8 + 128;
+  VSB_CHECK_ARG(smem_bytes <= 227 * 1024, "warp-MMA bottleneck: shared memory plan exceeds 227 KiB");
+  p.total_steps = (long long)d->n * p.row_tiles * d->t;
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    (void)cudaGetLastError();
+  }
+  if (d->grid > 0 && d->grid < sms) sms = d->grid;
+  const long long grid = p.total_steps < sms ? p.total_steps : sms;
+  p.steps_per_cta = (int)ceil_div_ll(p.total_steps, grid);
+
+  cudaError_t e = cudaSuccess;
+  if (d->d == 8 && d->kt == 3) e = thin_set_attr<8, 3>();
+  else if (d->d == 8) e = thin_set_attr<8, 1>();
+  else if (d->kt == 3) e = thin_set_attr<16, 3>();
+  else e = thin_set_attr<16, 1>();
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(bottleneck_thin_kernel) failed: %s", cudaGetErrorString(e));
+    return VSB_ERR_CUDA;
+  }
+  ThinPlan* plan = new (std::nothrow) ThinPlan();
+  VSB_CHECK_ARG(plan, "out of host memory");
+  plan->params = p;
+  plan->smem_bytes = smem_bytes;
+  plan->grid = (unsigned)ceil_div_ll(p.total_steps, p.steps_per_cta);
+  plan->d = d->d;
+  plan->kt = d->kt;
+  *out_plan = plan;
+  return VSB_OK;
+}
+
+int thin_run(const ThinPlan* plan, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (plan->d == 8 && plan->kt == 3)
+    bottleneck_thin_kernel<8, 3><<<plan->grid, kThinThreads, plan->smem_bytes, s>>>(plan->params);
+  else if (plan->d == 8)
+    bottleneck_thin_kernel<8, 1><<<plan->grid, kThinThreads, plan->smem_bytes, s>>>(plan->params);
+  else if (plan->kt == 3)
+    bottleneck_thin_kernel<16, 3><<<plan->grid, kThinThreads, plan->smem_bytes, s>>>(plan->params);
+  else
+    bottleneck_thin_kernel<16, 1><<<plan->grid, kThinThreads, plan->smem_bytes, s>>>(plan->params);
+  VSB_CHECK_LAUNCH("bottleneck_thin_kernel");
+  return VSB_OK;
+}
+
+void thin_plan_destroy(ThinPlan* plan) { delete plan; }
+
+void thin_plan_info(const ThinPlan* plan, long long* out8) {
+  const ThinParams& p = plan->params;
+  out8[0] = p.R;
+  out8[1] = p.row_tiles;
+  out8[2] = p.S;
+  out8[3] = p.steps_per_cta;
+  out8[4] = plan->grid;
+  out8[5] = (long long)plan->smem_bytes;
+  out8[6] = p.a_tiles * 1000 + p.bc_tiles;
+  out8[7] = 0;
+}
+
+}  // namespace vsb

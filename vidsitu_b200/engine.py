@@ -622,6 +622,9 @@ class ClipEngine:
         tn = self._tune(blk.prefix)
         if self.dtype != VSB_BF16 or blk.branch1 is not None or blk.nonlocal_ is not None:
             return None
+        thin = self._thin_block(x, blk, out_pitch, tn)
+        if thin is not None:
+            return thin
         # opt-in (tune fuse_block / VSB_FUSE_BLOCK=1): measured on B200 the fused launch is at parity with the three
         # launches on the thin Fast pathway (it is bound by the TMA unit and the single MMA-issuing thread, not by HBM)
         # and, owning the whole SM, it no longer overlaps the Slow pathway's kernels: 11.53 vs 11.39 ms per step
@@ -670,6 +673,48 @@ class ClipEngine:
             return None
         self._keep.append(plan)
         name = blk.prefix + ".fused_abc"
+        self.op_bytes[name] = 2.0 * (x.pixels * x.c + y.pixels * y.c)
+        self.trunk_ops.append((name, plan.run, float(x.pixels) * (a.flops_per_out_pixel + b.flops_per_out_pixel
+                                                                  + c.flops_per_out_pixel)))
+        self.fused_blocks.append(blk.prefix)
+        self._free(x)
+        return y
+
+    def _thin_block(self, x: Act, blk: BlockSpec, out_pitch: Optional[int], tn: dict) -> Optional[Act]:
+        """Identity ResBlock of a THIN stage (stored bottleneck width 8 or 16, block width 4x that: the Fast
+        pathway's res2 / res3) as ONE launch of the warp-MMA walk kernel (vsb_bottleneck_* algo 1,
+        bottleneck_thin_sm100.cu): ungrouped weights, every frame of a row strip fetched once, a's and b's outputs
+        never reach HBM.  On by default (VSB_THIN_BLOCK=0 / tune {"thin_block": False} keeps the three launches)."""
+        if str(tn.get("thin_block", os.environ.get("VSB_THIN_BLOCK", "1"))) not in ("1", "True"):
+            return None
+        a, b, c = blk.a, blk.b, blk.c
+        d_store = self._store(a.cout)
+        if (d_store not in (8, 16) or x.c != 4 * d_store or self._store(c.cout) != x.c or x.c_real != a.cin
+                or x.c_off or x.pitch != x.c or c.cout != a.cin
+                or tuple(a.kernel[1:]) != (1, 1) or a.kernel[0] not in (1, 3) or tuple(b.kernel) != (1, 3, 3)
+                or tuple(c.kernel) != (1, 1, 1) or any(s != 1 for cs in (a, b, c) for s in cs.stride)
+                or tuple(a.pad) != (a.kernel[0] // 2, 0, 0) or tuple(b.pad) != (0, 1, 1) or tuple(c.pad) != (0, 0, 0)):
+            return None
+        if out_pitch is not None and out_pitch != x.c:
+            return None
+        w = self._memo((blk.prefix, "thin", x.c, d_store), lambda: (
+            self._up(pack_conv_weight(self._tensor(a.key + ".weight"), x.c, d_store, self.tdt)),
+            self._up(pack_conv_weight(self._tensor(b.key + ".weight"), d_store, d_store, self.tdt)),
+            self._up(pack_conv_weight(self._tensor(c.key + ".weight"), d_store, x.c, self.tdt))))
+        sa, ba = self._sb(a, d_store)
+        sb_, bb = self._sb(b, d_store)
+        sc, bc = self._sb(c, x.c)
+        y = self._alloc(x.n, x.t, x.h, x.w, c.cout)
+        try:
+            plan = BottleneckPlan(x, y, d_store, a.kernel[0], w[0], w[1], w[2], sa, ba, sb_, bb, sc, bc, algo=1,
+                                  stages=int(tn.get("thin_slots", 0)), walk_len=int(tn.get("thin_rows", 0)))
+        except VsbError:
+            if tn.get("thin_block") is True:
+                raise
+            self._free(y)
+            return None
+        self._keep.append(plan)
+        name = blk.prefix + ".thin_abc"
         self.op_bytes[name] = 2.0 * (x.pixels * x.c + y.pixels * y.c)
         self.trunk_ops.append((name, plan.run, float(x.pixels) * (a.flops_per_out_pixel + b.flops_per_out_pixel
                                                                   + c.flops_per_out_pixel)))

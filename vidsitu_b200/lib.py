@@ -68,6 +68,7 @@ class BottleneckDesc(C.Structure):
         ("sb", C.c_void_p), ("bb", C.c_void_p),
         ("sc", C.c_void_p), ("bc", C.c_void_p),
         ("stages", C.c_int), ("walk_len", C.c_int), ("grid", C.c_int),
+        ("algo", C.c_int),
     ]
 
 
@@ -193,8 +194,8 @@ def load() -> C.CDLL:
                  "vsb_program_add_transpose_pad", "vsb_program_add_sync", "vsb_program_run", "vsb_program_capture",
                  "vsb_program_save", "vsb_program_file_device_bytes", "vsb_program_load"):
         getattr(lib, name).restype = i
-    if lib.vsb_abi_version() != 7:
-        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 7")
+    if lib.vsb_abi_version() != 8:
+        raise VsbError(f"ABI mismatch: library reports {lib.vsb_abi_version()}, binding expects 8")
     _lib = lib
     return lib
 

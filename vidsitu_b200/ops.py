@@ -266,7 +266,7 @@ class BottleneckPlan:
 
     def __init__(self, x: Act, out: Act, d: int, kt: int, wa: torch.Tensor, wb: torch.Tensor, wc: torch.Tensor,
                  sa: torch.Tensor, ba: torch.Tensor, sb: torch.Tensor, bb: torch.Tensor, sc: torch.Tensor,
-                 bc: torch.Tensor, stages: int = 0, walk_len: int = 0, grid: int = 0):
+                 bc: torch.Tensor, stages: int = 0, walk_len: int = 0, grid: int = 0, algo: int = 0):
         _require_cuda(x.buf, out.buf, wa, wb, wc, sa, ba, sb, bb, sc, bc)
         c = x.c
         if (out.n, out.t, out.h, out.w, out.c) != (x.n, x.t, x.h, x.w, c):
@@ -288,6 +288,8 @@ class BottleneckPlan:
         dsc.wa, dsc.wb, dsc.wc = wa.data_ptr(), wb.data_ptr(), wc.data_ptr()
         dsc.sa, dsc.ba, dsc.sb, dsc.bb, dsc.sc, dsc.bc = (t.data_ptr() for t in (sa, ba, sb, bb, sc, bc))
         dsc.stages, dsc.walk_len, dsc.grid = stages, walk_len, grid
+        dsc.algo = algo   # 0 = tcgen05 flat-raster kernel, 1 = warp-MMA walk kernel (thin blocks: d = 8 / 16, c = 4 d)
+        self.algo = algo
         self._keep = (x.buf, out.buf, wa, wb, wc, sa, ba, sb, bb, sc, bc)
         self._desc = dsc
         self._h = C.c_void_p()
@@ -305,7 +307,10 @@ class BottleneckPlan:
     def info(self) -> dict:
         out = (C.c_longlong * 8)()
         check(self._lib.vsb_bottleneck_plan_info(self._h, out), "vsb_bottleneck_plan_info")
-        keys = ("rp", "fp", "stages_x100_cps", "tiles_per_cta", "grid", "smem_bytes", "tiles_per_clip", "tmem_cols")
+        if self.algo == 1:
+            keys = ("rows_per_strip", "strips", "ring_slots", "steps_per_cta", "grid", "smem_bytes", "a_x1000_bc_tiles", "_")
+        else:
+            keys = ("rp", "fp", "stages_x100_cps", "tiles_per_cta", "grid", "smem_bytes", "tiles_per_clip", "tmem_cols")
         return dict(zip(keys, [int(v) for v in out]))
 
     def stats(self) -> list:
