@@ -35,6 +35,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <new>
 
 #include "bottleneck_thin.h"
@@ -44,9 +46,11 @@
 namespace vsb {
 
 namespace {
-constexpr int kAWarps = 8, kBCWarps = 8;
-constexpr int kProducerWarp = kAWarps + kBCWarps;
-constexpr int kThinThreads = (kAWarps + kBCWarps + 1) * 32;
+constexpr int kComputeWarps = 15;            // a-warps + bc-warps (split chosen by the plan), + one fetch warp
+constexpr int kThinThreads = (kComputeWarps + 1) * 32;
+// 16-pixel tiles per warp and frame step (unrolled)
+__host__ __device__ constexpr int max_a_tiles(int d) { return d == 8 ? 6 : 3; }
+__host__ __device__ constexpr int max_bc_tiles(int d) { return d == 8 ? 4 : 2; }
 constexpr int kMaxSlots = 8;
 }  // namespace
 
@@ -57,11 +61,12 @@ struct ThinParams {
   const float *sa, *ba, *sb, *bb, *sc, *bc;
   int n, T, H, W;
   int R, row_tiles;
+  int a_warps;  // warps 0 .. a_warps-1 run conv a, a_warps .. 14 conv b + c, warp 15 fetches
   uint32_t out_pitch_bytes;
   int S;
   uint32_t slot_bytes, row_bytes;
   int a_px, a_tiles, bc_px, bc_tiles;
-  uint32_t a_pitch, a_buf_bytes;
+  uint32_t a_buf_bytes;
   uint32_t off_abuf, off_sbc, off_bar;
   uint32_t magic_w;  // floor(2^24 / W) + 1: px / W == (px * magic_w) >> 24 for px < 2^24 / W
   long long total_steps;
@@ -91,6 +96,12 @@ __device__ __forceinline__ void t_sts32(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void t_stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// relu + one rounding to bf16 of two floats (lo -> bits 0-15): relu(round(v)) == round(relu(v))
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 // D (16 x 8, fp32) += A (16 x 16, bf16, row) . B (16 x 8, bf16, col)
 __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
@@ -98,11 +109,18 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// D (16 x 8, fp32) += A (16 x 8, bf16, row) . B (8 x 8, bf16, col)
-__device__ __forceinline__ void mma1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a0), "r"(a1), "r"(b0));
+// D = A . B (no accumulator input: no register initialisation)
+__device__ __forceinline__ void mma16816_z(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                           uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+// D (16 x 8, fp32) = A (16 x 8, bf16, row) . B (8 x 8, bf16, col)
+__device__ __forceinline__ void mma1688_z(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%7, %7, %7, %7};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0), "f"(0.f));
 }
 // contiguous global -> shared copy by the TMA unit (no tensor map), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -112,17 +130,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void* src, uint32
 }
 __device__ __forceinline__ uint32_t sel(bool c, uint32_t a, uint32_t b) { return c ? a : b; }
 
-// The 16-byte pieces (q = 0 .. NQ-1) of one pixel row for thread t: v[q] = bytes [64 q + 16 t, + 16) of the pixel.
+// The 16-byte pieces (q = 0 .. NQ-1) of one pixel row for thread t: v[q] = bytes [64 q + 16 t, + 16) of the pixel;
+// addr = pixel address + 16 t.
 template <int NQ>
-__device__ __forceinline__ void load_pieces(uint32_t px_addr, int t, bool odd, uint4 (&v)[NQ]) {
+__device__ __forceinline__ void load_pieces(uint32_t addr, bool odd, uint4 (&v)[NQ]) {
   if (NQ == 1) {
-    v[0] = t_lds128(px_addr + 16 * t);
+    v[0] = t_lds128(addr);
   } else {
+    const uint32_t swap = odd ? 64u : 0u;
 #pragma unroll
     for (int m = 0; m < NQ / 2; ++m) {
-      const uint32_t base = px_addr + 128 * m + 16 * t;
-      const uint4 first = t_lds128(base + (odd ? 64u : 0u));
-      const uint4 second = t_lds128(base + (odd ? 0u : 64u));
+      const uint4 first = t_lds128(addr + 128 * m + swap);
+      const uint4 second = t_lds128(addr + 128 * m + (64u - swap));
       v[2 * m].x = sel(odd, second.x, first.x); v[2 * m].y = sel(odd, second.y, first.y);
       v[2 * m].z = sel(odd, second.z, first.z); v[2 * m].w = sel(odd, second.w, first.w);
       v[2 * m + 1].x = sel(odd, first.x, second.x); v[2 * m + 1].y = sel(odd, first.y, second.y);
@@ -178,6 +197,8 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
   constexpr int NSL = 9 * NQ;     // 8-channel K slices of conv b (tap-major)
   constexpr int NP = (NSL + 1) / 2;
   constexpr int KSC = D >= 16 ? D / 16 : 1;  // K steps of conv c
+  constexpr int AP = D == 8 ? 16 : 2 * D + 16;  // bytes per a-tile pixel (48 for d = 16: conflict-free 32-bit reads)
+  constexpr int kMaxATiles = max_a_tiles(D), kMaxBCTiles = max_bc_tiles(D);
 
   extern __shared__ uint8_t thin_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(thin_smem_raw) + 127) & ~uintptr_t(127));
@@ -196,11 +217,11 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kAWarps + kBCWarps);
+      mbar_init(&empty[s], kComputeWarps);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&a_full[b], kAWarps);
-      mbar_init(&a_empty[b], kBCWarps);
+      mbar_init(&a_full[b], p.a_warps);
+      mbar_init(&a_empty[b], kComputeWarps - p.a_warps);
     }
     fence_mbar_init();
   }
@@ -214,13 +235,20 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
     const int ch = 8 * (4 * q + tt) + 2 * i;
     reinterpret_cast<float4*>(smem + p.off_sbc)[e] = make_float4(p.sc[ch], p.bc[ch], p.sc[ch + 1], p.bc[ch + 1]);
   }
+  // (scale, bias) of conv b, entry nt * 4 + t = channels 8 nt + 2 t, + 1 (d = 16 reads them per tile: registers)
+  for (int e = threadIdx.x; e < NTD * 4; e += kThinThreads) {
+    const int ch = 8 * (e >> 2) + 2 * (e & 3);
+    reinterpret_cast<float4*>(smem + p.off_sbc + 512)[e] = make_float4(p.sb[ch], p.bb[ch], p.sb[ch + 1], p.bb[ch + 1]);
+  }
   __syncthreads();
 
   ThinWalk wk;
   wk.init(p);
+  const int wp2 = p.W + 2;
 
-  if (warp == kProducerWarp) {
-    // ------------------------------------------------------------------ producer
+  const int kAWarps = p.a_warps, kBCWarps = kComputeWarps - p.a_warps;
+  if (warp == kComputeWarps) {
+    // ------------------------------------------------------------------ frame fetches
     if (lane == 0) {
       uint32_t slot = 0, round = 0;  // load index L = round * S + slot
       while (wk.load<HT>(p)) {
@@ -262,8 +290,23 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
       const int ch = 8 * nt + 2 * t4;
       sa_f[nt] = make_float4(p.sa[ch], p.ba[ch], p.sa[ch + 1], p.ba[ch + 1]);
     }
+    // tile geometry (the same tiles every frame step): per tile slot and pixel row, strip row << 16 | byte offset of
+    // the pixel in the a-tile buffer (+ 4 t); 0xFFFF.... = past the strip
+    uint32_t geo[kMaxATiles][2];
+#pragma unroll
+    for (int sl = 0; sl < kMaxATiles; ++sl)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int px = (warp + kAWarps * sl) * 16 + g + 8 * half;
+        const int rr = (int)(((uint32_t)px * p.magic_w) >> 24);
+        const int col = px - rr * p.W;
+        geo[sl][half] = px < p.a_px ? ((uint32_t)rr << 16) | (uint32_t)((rr * wp2 + col + 1) * AP + 4 * t4) : 0xFFFF0000u;
+      }
     uint32_t istep = 0;
     while (wk.load<HT>(p)) {
+      // strip rows [rr_lo, rr_hi) lie inside the image; the others are the zero padding of conv b
+      const uint32_t rr_lo = wk.r0 == 0 ? 1u : 0u;
+      const uint32_t rr_hi = (uint32_t)(p.H - wk.r0 + 1 < p.R + 2 ? p.H - wk.r0 + 1 : p.R + 2);
       for (int t = wk.t0; t < wk.t1; ++t, ++istep) {
         const uint32_t b = istep & 1;
         if (istep >= 2) mbar_wait(&a_empty[b], ((istep >> 1) - 1) & 1);
@@ -278,13 +321,17 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
             const uint32_t L = wk.l0 + (uint32_t)(f - wk.f_lo);
             const uint32_t slot = L % (uint32_t)p.S;
             mbar_wait(&full[slot], (L / (uint32_t)p.S) & 1);
-            slot_s[tap] = ring_s + slot * p.slot_bytes;
+            slot_s[tap] = ring_s + slot * p.slot_bytes + 16 * t4;
           }
         }
         const uint32_t dst_s = abuf_s + b * p.a_buf_bytes;
-        for (int tile = warp; tile < p.a_tiles; tile += kAWarps) {
+#pragma unroll
+        for (int sl = 0; sl < kMaxATiles; ++sl) {
+          const int tile = warp + kAWarps * sl;
+          if (tile >= p.a_tiles) break;
           const int px_g = tile * 16 + g, px_h = px_g + 8;
-          const int pc_g = px_g < p.a_px ? px_g : p.a_px - 1, pc_h = px_h < p.a_px ? px_h : p.a_px - 1;
+          const uint32_t off_g = (uint32_t)(px_g < p.a_px ? px_g : p.a_px - 1) * CB;
+          const uint32_t off_h = (uint32_t)(px_h < p.a_px ? px_h : p.a_px - 1) * CB;
           float acc[NTD][4];
 #pragma unroll
           for (int nt = 0; nt < NTD; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
@@ -292,8 +339,8 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
           for (int tap = 0; tap < KT; ++tap) {
             if (!have[tap]) continue;
             uint4 vg[NQ], vh[NQ];
-            load_pieces<NQ>(slot_s[tap] + (uint32_t)pc_g * CB, t4, odd, vg);
-            load_pieces<NQ>(slot_s[tap] + (uint32_t)pc_h * CB, t4, odd, vh);
+            load_pieces<NQ>(slot_s[tap] + off_g, odd, vg);
+            load_pieces<NQ>(slot_s[tap] + off_h, odd, vh);
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
 #pragma unroll
@@ -306,22 +353,19 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
           // BN + ReLU -> bf16 -> a-tile buffer; rows outside the image are the zero padding of conv b
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            const int px = half ? px_h : px_g;
-            if (px < p.a_px) {
-              const int rr = (int)(((uint32_t)px * p.magic_w) >> 24);
-              const int col = px - rr * p.W;
-              const int row = wk.r0 - 1 + rr;
-              const bool inside = row >= 0 && row < p.H;
-              const uint32_t dst = dst_s + (uint32_t)(rr * (p.W + 2) + col + 1) * p.a_pitch + 4 * t4;
+            const uint32_t ge = geo[sl][half], rr = ge >> 16;
+            if (rr != 0xFFFFu) {
+              const bool inside = rr >= rr_lo && rr < rr_hi;
+              const uint32_t dst = dst_s + (ge & 0xFFFFu);
 #pragma unroll
               for (int nt = 0; nt < NTD; ++nt) {
-                const float v0 = fmaxf(fmaf(acc[nt][2 * half], sa_f[nt].x, sa_f[nt].y), 0.f);
-                const float v1 = fmaxf(fmaf(acc[nt][2 * half + 1], sa_f[nt].z, sa_f[nt].w), 0.f);
-                t_sts32(dst + 16 * nt, inside ? pack_bf16x2(v0, v1) : 0u);
+                const uint32_t v = pack_relu_bf16x2(fmaf(acc[nt][2 * half], sa_f[nt].x, sa_f[nt].y),
+                                                    fmaf(acc[nt][2 * half + 1], sa_f[nt].z, sa_f[nt].w));
+                t_sts32(dst + 16 * nt, inside ? v : 0u);
               }
             }
           }
-        }
+          }
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&a_full[b]);
@@ -362,15 +406,33 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
           wc_f[q][i][ks].x = *reinterpret_cast<const uint32_t*>(row);
           wc_f[q][i][ks].y = D >= 16 ? *reinterpret_cast<const uint32_t*>(row + 8) : 0u;
         }
-    float4 sb_f[NTD];
+    float4 sb_f[NTD], sc_f[4];  // d = 8 only: the (scale, bias) pairs of conv b and conv c stay in registers
+    if (D == 8) {
 #pragma unroll
-    for (int nt = 0; nt < NTD; ++nt) {
-      const int ch = 8 * nt + 2 * t4;
-      sb_f[nt] = make_float4(p.sb[ch], p.bb[ch], p.sb[ch + 1], p.bb[ch + 1]);
+      for (int nt = 0; nt < NTD; ++nt) sb_f[nt] = t_lds128f(sbc_s + 512 + (uint32_t)(nt * 4 + t4) * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc_f[i] = t_lds128f(sbc_s + (uint32_t)(i * 4 + t4) * 16);
     }
-    const int wp2 = p.W + 2;
+    // tile geometry: per tile slot and pixel row, [0] = byte offset of the pixel's centre in the a-tile buffer
+    // (+ 4 t) | byte offset of the pixel in the frame slot (+ 16 t) << 16, [1] = strip row << 24 | pixel index
+    // (0xFF...... = past the strip)
+    uint32_t geo[kMaxBCTiles][2][2];
+#pragma unroll
+    for (int sl = 0; sl < kMaxBCTiles; ++sl)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int px = (bw + kBCWarps * sl) * 16 + g + 8 * half;
+        const int pc = px < p.bc_px ? px : p.bc_px - 1;
+        const int rr = (int)(((uint32_t)pc * p.magic_w) >> 24);
+        const int col = pc - rr * p.W;
+        geo[sl][half][0] = (uint32_t)(((rr + 1) * wp2 + col + 1) * AP + 4 * t4) |
+                           ((uint32_t)(((rr + 1) * p.W + col) * CB + 16 * t4) << 16);
+        geo[sl][half][1] = px < p.bc_px ? ((uint32_t)rr << 24) | (uint32_t)pc : 0xFF000000u;
+      }
+    const uint32_t rowb = (uint32_t)wp2 * AP;
     uint32_t istep = 0;
     while (wk.load<HT>(p)) {
+      const uint32_t rr_hi = (uint32_t)(p.H - wk.r0 < p.R ? p.H - wk.r0 : p.R);
       for (int t = wk.t0; t < wk.t1; ++t, ++istep) {
         const uint32_t b = istep & 1;
         mbar_wait(&a_full[b], (istep >> 1) & 1);
@@ -379,76 +441,73 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
         mbar_wait(&full[slot], (L / (uint32_t)p.S) & 1);
         const uint32_t xs = ring_s + slot * p.slot_bytes;
         const uint32_t src_s = abuf_s + b * p.a_buf_bytes;
-        uint8_t* out_frame = p.out + (((long long)wk.n * p.T + t) * p.H + wk.r0) * (long long)p.W * p.out_pitch_bytes;
-        for (int tile = bw; tile < p.bc_tiles; tile += kBCWarps) {
-          int px[2] = {tile * 16 + g, tile * 16 + g + 8};
-          bool valid[2];
-          uint32_t ctr[2], res_s[2], out_off[2];
+        uint8_t* out_frame = p.out + (((long long)wk.n * p.T + t) * p.H + wk.r0) * (long long)p.W * p.out_pitch_bytes + 16 * t4;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const bool in_tile = px[half] < p.bc_px;
-            const int pc = in_tile ? px[half] : p.bc_px - 1;
-            const int rr = (int)(((uint32_t)pc * p.magic_w) >> 24);
-            const int col = pc - rr * p.W;
-            valid[half] = in_tile && wk.r0 + rr < p.H;
-            ctr[half] = src_s + (uint32_t)((rr + 1) * wp2 + col + 1) * p.a_pitch + 4 * t4;
-            res_s[half] = xs + (uint32_t)((rr + 1) * p.W + col) * CB;
-            out_off[half] = (uint32_t)(rr * p.W + col) * p.out_pitch_bytes;
-          }
+        for (int sl = 0; sl < kMaxBCTiles; ++sl) {
+          if (bw + kBCWarps * sl >= p.bc_tiles) break;
+          const uint32_t ctr0 = src_s + (geo[sl][0][0] & 0xFFFFu), ctr1 = src_s + (geo[sl][1][0] & 0xFFFFu);
           float accb[NTD][4];
-#pragma unroll
-          for (int nt = 0; nt < NTD; ++nt) accb[nt][0] = accb[nt][1] = accb[nt][2] = accb[nt][3] = 0.f;
 #pragma unroll
           for (int pr = 0; pr < NP; ++pr) {
             const int s0 = 2 * pr, s1 = 2 * pr + 1;
             const int tap0 = s0 / NQ, q0 = s0 % NQ;
-            const int sh0 = ((tap0 / 3 - 1) * wp2 + (tap0 % 3 - 1)) * (int)p.a_pitch + 16 * q0;
-            const uint32_t a0 = t_lds32(ctr[0] + sh0), a1 = t_lds32(ctr[1] + sh0);
+            const uint32_t sh0 = (uint32_t)(tap0 / 3) * rowb - rowb + (uint32_t)((tap0 % 3 - 1) * AP + 16 * q0);
+            const uint32_t a0 = t_lds32(ctr0 + sh0), a1 = t_lds32(ctr1 + sh0);
             uint32_t a2 = 0u, a3 = 0u;
             if (s1 < NSL) {
               const int tap1 = s1 / NQ, q1 = s1 % NQ;
-              const int sh1 = ((tap1 / 3 - 1) * wp2 + (tap1 % 3 - 1)) * (int)p.a_pitch + 16 * q1;
-              a2 = t_lds32(ctr[0] + sh1);
-              a3 = t_lds32(ctr[1] + sh1);
+              const uint32_t sh1 = (uint32_t)(tap1 / 3) * rowb - rowb + (uint32_t)((tap1 % 3 - 1) * AP + 16 * q1);
+              a2 = t_lds32(ctr0 + sh1);
+              a3 = t_lds32(ctr1 + sh1);
             }
 #pragma unroll
-            for (int nt = 0; nt < NTD; ++nt) mma16816(accb[nt], a0, a1, a2, a3, wb_f[pr][nt].x, wb_f[pr][nt].y);
+            for (int nt = 0; nt < NTD; ++nt) {
+              if (pr == 0) mma16816_z(accb[nt], a0, a1, a2, a3, wb_f[pr][nt].x, wb_f[pr][nt].y);
+              else mma16816(accb[nt], a0, a1, a2, a3, wb_f[pr][nt].x, wb_f[pr][nt].y);
+            }
           }
           // BN + ReLU -> bf16: the accumulator fragment of b is the A fragment of c
           uint32_t pb[NTD][2];
 #pragma unroll
           for (int nt = 0; nt < NTD; ++nt) {
-            pb[nt][0] = pack_bf16x2(fmaxf(fmaf(accb[nt][0], sb_f[nt].x, sb_f[nt].y), 0.f),
-                                    fmaxf(fmaf(accb[nt][1], sb_f[nt].z, sb_f[nt].w), 0.f));
-            pb[nt][1] = pack_bf16x2(fmaxf(fmaf(accb[nt][2], sb_f[nt].x, sb_f[nt].y), 0.f),
-                                    fmaxf(fmaf(accb[nt][3], sb_f[nt].z, sb_f[nt].w), 0.f));
+            const float4 s4 = D == 8 ? sb_f[nt] : t_lds128f(sbc_s + 512 + (uint32_t)(nt * 4 + t4) * 16);
+            pb[nt][0] = pack_relu_bf16x2(fmaf(accb[nt][0], s4.x, s4.y), fmaf(accb[nt][1], s4.z, s4.w));
+            pb[nt][1] = pack_relu_bf16x2(fmaf(accb[nt][2], s4.x, s4.y), fmaf(accb[nt][3], s4.z, s4.w));
           }
-          uint4 rg[NQ], rh[NQ];  // residual = x[t] at the tile's pixels, already in the c accumulator's layout
-          load_pieces<NQ>(res_s[0], t4, odd, rg);
-          load_pieces<NQ>(res_s[1], t4, odd, rh);
+          // residual = x[t] at the tile's pixels, already in the c accumulator's layout (plain loads: two-way bank
+          // conflicts for d = 16, but half the registers of the swapped pair loads conv a uses)
+          const uint32_t res0 = xs + (geo[sl][0][0] >> 16), res1 = xs + (geo[sl][1][0] >> 16);
+          const uint32_t g0 = geo[sl][0][1], g1 = geo[sl][1][1];
+          const bool valid0 = (g0 >> 24) < rr_hi, valid1 = (g1 >> 24) < rr_hi;
+          uint8_t* out0 = out_frame + (size_t)(g0 & 0xFFFFFFu) * p.out_pitch_bytes;
+          uint8_t* out1 = out_frame + (size_t)(g1 & 0xFFFFFFu) * p.out_pitch_bytes;
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
             uint32_t og[4], oh[4];
+            const uint4 rgq = t_lds128(res0 + 64 * q), rhq = t_lds128(res1 + 64 * q);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float accc[4] = {0.f, 0.f, 0.f, 0.f};
+              float accc[4];
               if (D >= 16) {
 #pragma unroll
-                for (int ks = 0; ks < KSC; ++ks)
-                  mma16816(accc, pb[(2 * ks) % NTD][0], pb[(2 * ks) % NTD][1], pb[(2 * ks + 1) % NTD][0],
-                           pb[(2 * ks + 1) % NTD][1], wc_f[q][i][ks].x, wc_f[q][i][ks].y);
+                for (int ks = 0; ks < KSC; ++ks) {
+                  if (ks == 0)
+                    mma16816_z(accc, pb[(2 * ks) % NTD][0], pb[(2 * ks) % NTD][1], pb[(2 * ks + 1) % NTD][0],
+                               pb[(2 * ks + 1) % NTD][1], wc_f[q][i][ks].x, wc_f[q][i][ks].y);
+                  else
+                    mma16816(accc, pb[(2 * ks) % NTD][0], pb[(2 * ks) % NTD][1], pb[(2 * ks + 1) % NTD][0],
+                             pb[(2 * ks + 1) % NTD][1], wc_f[q][i][ks].x, wc_f[q][i][ks].y);
+                }
               } else {
-                mma1688(accc, pb[0][0], pb[0][1], wc_f[q][i][0].x);
+                mma1688_z(accc, pb[0][0], pb[0][1], wc_f[q][i][0].x);
               }
-              const float4 s4 = t_lds128f(sbc_s + (uint32_t)((q * 4 + i) * 4 + t4) * 16);
-              const uint32_t r_g = piece_reg(rg[q], i), r_h = piece_reg(rh[q], i);
-              og[i] = pack_bf16x2(fmaxf(fmaf(accc[0], s4.x, s4.y) + bf16_lo(r_g), 0.f),
-                                  fmaxf(fmaf(accc[1], s4.z, s4.w) + bf16_hi(r_g), 0.f));
-              oh[i] = pack_bf16x2(fmaxf(fmaf(accc[2], s4.x, s4.y) + bf16_lo(r_h), 0.f),
-                                  fmaxf(fmaf(accc[3], s4.z, s4.w) + bf16_hi(r_h), 0.f));
+              const float4 s4 = D == 8 ? sc_f[i] : t_lds128f(sbc_s + (uint32_t)((q * 4 + i) * 4 + t4) * 16);
+              const uint32_t r_g = piece_reg(rgq, i), r_h = piece_reg(rhq, i);
+              og[i] = pack_relu_bf16x2(fmaf(accc[0], s4.x, s4.y) + bf16_lo(r_g), fmaf(accc[1], s4.z, s4.w) + bf16_hi(r_g));
+              oh[i] = pack_relu_bf16x2(fmaf(accc[2], s4.x, s4.y) + bf16_lo(r_h), fmaf(accc[3], s4.z, s4.w) + bf16_hi(r_h));
             }
-            if (valid[0]) t_stg128(out_frame + out_off[0] + 64 * q + 16 * t4, og[0], og[1], og[2], og[3]);
-            if (valid[1]) t_stg128(out_frame + out_off[1] + 64 * q + 16 * t4, oh[0], oh[1], oh[2], oh[3]);
+            if (valid0) t_stg128(out0 + 64 * q, og[0], og[1], og[2], og[3]);
+            if (valid1) t_stg128(out1 + 64 * q, oh[0], oh[1], oh[2], oh[3]);
           }
         }
         __syncwarp();
@@ -501,8 +560,12 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   p.n = d->n; p.T = d->t; p.H = d->h; p.W = d->w;
   p.out_pitch_bytes = (uint32_t)d->out_pitch * 2;
   p.row_bytes = (uint32_t)d->w * d->c * 2;
-  p.a_pitch = d->d == 8 ? 16u : (uint32_t)d->d * 2 + 16;  // 48 B for d = 16: conflict-free 32-bit reads of 8 pixel rows
+  const uint32_t a_pitch = d->d == 8 ? 16u : (uint32_t)d->d * 2 + 16;  // as AP in the kernel
   p.magic_w = (1u << 24) / (uint32_t)d->w + 1;
+  int a_warps = 7;  // experiments: VSB_THIN_AWARPS
+  if (getenv("VSB_THIN_AWARPS")) a_warps = atoi(getenv("VSB_THIN_AWARPS"));
+  if (a_warps < 6 || a_warps > 8) a_warps = 7;
+  p.a_warps = a_warps;
   const int ht = d->kt / 2;
   const int min_slots = d->kt + 1;
   // rows per strip: the strip (+ 2 halo rows) is one ring slot; fewest fetched rows per frame among the strips that
@@ -513,13 +576,14 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   for (int r = d->h; r >= 1; --r) {
     if (d->walk_len > 0 && r != d->walk_len) continue;
     const long long slot = (long long)(r + 2) * p.row_bytes;
-    const long long abuf = (long long)(r + 2) * (d->w + 2) * p.a_pitch;
+    const long long abuf = (long long)(r + 2) * (d->w + 2) * a_pitch;
     const long long abuf_al = (abuf + 127) / 128 * 128;
-    long long s = (budget - 2 * abuf_al - 1024) / slot;
+    long long s = (budget - 2 * abuf_al - 2048) / slot;
     if (s > 6) s = 6;
     if (d->stages > 0 && s > d->stages) s = d->stages;
     if (s < min_slots) continue;
-    if ((long long)(r + 2) * d->w * 2 > (1 << 16)) continue;
+    if (abuf > 0xFFFF || slot > 0xFFFF) continue;  // tile geometry is packed in 16-bit offsets
+    if (ceil_div((r + 2) * d->w, 16) > a_warps * max_a_tiles(d->d) || ceil_div(r * d->w, 16) > (kComputeWarps - a_warps) * max_bc_tiles(d->d)) continue;
     // cost: rows fetched per frame (halo included), a small penalty for a short ring
     const long long cost = (long long)ceil_div(d->h, r) * (r + 2) * 16 + (s < min_slots + 1 ? 8 : 0);
     if (!best_r || cost < best_cost) {
@@ -542,12 +606,12 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   p.a_tiles = ceil_div(p.a_px, 16);
   p.bc_px = p.R * d->w;
   p.bc_tiles = ceil_div(p.bc_px, 16);
-  p.a_buf_bytes = (uint32_t)(((long long)(p.R + 2) * (d->w + 2) * p.a_pitch + 127) / 128 * 128);
+  p.a_buf_bytes = (uint32_t)(((long long)(p.R + 2) * (d->w + 2) * a_pitch + 127) / 128 * 128);
   // a tile's tail rows may read up to 16 pixels past the last slot: keep the a-tile buffers behind the ring
   p.off_abuf = (uint32_t)p.S * p.slot_bytes;
   p.off_abuf = (p.off_abuf + 127u) & ~127u;
   p.off_sbc = p.off_abuf + 2 * p.a_buf_bytes;
-  p.off_bar = p.off_sbc + (uint32_t)(d->d / 8) * 16 * 16;
+  p.off_bar = p.off_sbc + 1024;  // conv c table at +0 (<= 512 B), conv b table at +512
   const size_t smem_bytes = (size_t)p.off_bar + (2 * kMaxSlots + 4) * 8 + 128;
   VSB_CHECK_ARG(smem_bytes <= 227 * 1024, "warp-MMA bottleneck: shared memory plan exceeds 227 KiB");
   p.total_steps = (long long)d->n * p.row_tiles * d->t;

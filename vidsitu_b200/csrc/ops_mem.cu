@@ -3,6 +3,7 @@
 // channels-last with 128-bit accesses; none of them is reshaped into a GEMM.
 #include <cuda_bf16.h>
 #include <float.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.h"
@@ -105,6 +106,77 @@ pack_frames_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, i
         const float g = lut[1][c1];
         const float bb = reverse ? lut[0][c0] : lut[2][c2];
         store_px4<OutT>(dst_frame + ((long long)y * out_w + x_off + x) * 4, r, g, bb);
+      }
+    }
+  }
+}
+
+// bf16 form without the table: out = bf16(fma(x, A_c, B_c)) with A_c ~ 1 / (255 std_c), B_c ~ -mean_c / std_c chosen
+// by the host so that, for all 256 byte values, the ONE rounding to bf16 lands on the value the table path produces
+// (three fp32 IEEE operations, then bf16): the host checks every (channel, byte) pair (pack_fma_coeffs) and the
+// caller falls back to the table kernel when no such pair exists.  Same staging and store pattern as the table
+// kernel; what goes away are the three table reads per pixel (random shared-memory addresses: ~3.4-way bank
+// conflicts, the kernel's limiter) and the division by the row width.
+struct PackFma {
+  float a[3], b[3];
+  unsigned magic_w;  // floor(2^32 / w) + 1: px / w == umulhi(px, magic_w) for px * w < 2^32
+};
+
+__global__ void __launch_bounds__(256)
+pack_frames_fma_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16* __restrict__ out, int n, int t_in, int t_out,
+                       int frame_px, int w, int out_w, int x_off, PackIdx idx, PackFma k, int reverse) {
+  __shared__ __align__(16) uint8_t raw[2][3072];
+  const int chunks_per_frame = (frame_px + 1023) >> 10;
+  const long long total = (long long)n * t_out * chunks_per_frame;
+  const int h = frame_px / w;
+  int buf = 0;
+  auto chunk_src = [&](long long u, int& npx) -> const uint4* {
+    const int chunk = (int)(u % chunks_per_frame);
+    const long long f = u / chunks_per_frame;
+    const int to = (int)(f % t_out);
+    const long long clip = f / t_out;
+    const int px0 = chunk << 10;
+    npx = min(1024, frame_px - px0);  // multiple of 16
+    return reinterpret_cast<const uint4*>(frames + ((clip * t_in + idx.v[to]) * (long long)frame_px + px0) * 3);
+  };
+  uint4 stage = make_uint4(0, 0, 0, 0);
+  if ((long long)blockIdx.x < total) {
+    int npx0;
+    const uint4* src = chunk_src(blockIdx.x, npx0);
+    if ((int)threadIdx.x * 16 < npx0 * 3) stage = __ldg(src + threadIdx.x);
+  }
+  // REVERSE_INPUT_CHANNEL flips AFTER the per-channel normalisation (video_utils.py:54-55): output channel 0 is
+  // input channel 2 normalised with channel 2's statistics
+  const int i0 = reverse ? 2 : 0, i2 = reverse ? 0 : 2;
+  const float a0 = k.a[i0], b0 = k.b[i0], a1 = k.a[1], b1 = k.b[1], a2 = k.a[i2], b2 = k.b[i2];
+  for (long long u = blockIdx.x; u < total; u += gridDim.x, buf ^= 1) {
+    const int chunk = (int)(u % chunks_per_frame);
+    const long long f = u / chunks_per_frame;
+    const int to = (int)(f % t_out);
+    const long long clip = f / t_out;
+    const int px0 = chunk << 10;
+    const int npx = min(1024, frame_px - px0);
+    if ((int)threadIdx.x * 16 < npx * 3) *reinterpret_cast<uint4*>(raw[buf] + threadIdx.x * 16) = stage;
+    __syncthreads();  // the other buffer is free: its readers passed the previous barrier
+    if (u + gridDim.x < total) {
+      int npx1;
+      const uint4* src = chunk_src(u + gridDim.x, npx1);
+      if ((int)threadIdx.x * 16 < npx1 * 3) stage = __ldg(src + threadIdx.x);
+    }
+    __nv_bfloat16* dst_frame = out + ((clip * t_out + to) * (long long)h) * out_w * 4;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int i = threadIdx.x + kk * 256;
+      if (i < npx) {
+        const unsigned px = (unsigned)(px0 + i);
+        const unsigned y = __umulhi(px, k.magic_w), x = px - y * (unsigned)w;
+        const uint8_t* b = raw[buf] + i * 3;
+        // byte -> float without a conversion instruction: 0x4B000000 | v is the float 2^23 + v
+        const float c0 = __uint_as_float(0x4B000000u | b[i0]) - 8388608.f;
+        const float c1 = __uint_as_float(0x4B000000u | b[1]) - 8388608.f;
+        const float c2 = __uint_as_float(0x4B000000u | b[i2]) - 8388608.f;
+        store_px4<__nv_bfloat16>(dst_frame + ((long long)y * out_w + x_off + x) * 4, fmaf(c0, a0, b0), fmaf(c1, a1, b1),
+                                 fmaf(c2, a2, b2));
       }
     }
   }
@@ -353,23 +425,35 @@ maxpool_133_stream_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
 }
 
 // ------------------------------------------------------- global average pool
-// grid (n, ceil(c / (32*V))): each warp strides over the thw positions, each lane
-// owns one 16-byte channel vector; partial sums meet in shared memory.
+// grid (n, ceil(c / (8*V))): a block owns 8 channel vectors (8*V channels = one 128-byte line per position) of one
+// clip; its 256 threads are 32 position streams x 8 vectors, so a warp load covers 4 whole lines and the Fast
+// pathway's 256 channels still spread over 4 x n blocks (one block per clip left most of the SMs idle).  Partial
+// sums meet in shared memory and are added in a fixed order (deterministic, independent of the batch).
 template <typename T>
 __global__ void __launch_bounds__(256)
 global_avgpool_kernel(const T* __restrict__ in, float* __restrict__ feats, int thw, int c, int in_pitch,
                       int feat_pitch, int feat_off) {
   constexpr int V = Vec16<T>::N;
-  __shared__ float part[8][32 * 8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float part[32][8 * 8 + 1];
+  const int vec = threadIdx.x & 7, stream = threadIdx.x >> 3;  // stream = warp * 4 + lane / 8
   const int clip = blockIdx.x;
-  const int c0 = (blockIdx.y * 32 + lane) * V;
+  const int c0 = (blockIdx.y * 8 + vec) * V;
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (c0 < c) {
     const T* base = in + (long long)clip * thw * in_pitch + c0;
-    for (int pos = warp; pos < thw; pos += 8) {
+    int pos = stream;
+    for (; pos + 96 < thw; pos += 128) {  // four independent loads in flight
+      float v0[8], v1[8], v2[8], v3[8];
+      Vec16<T>::load(base + (long long)pos * in_pitch, v0);
+      Vec16<T>::load(base + (long long)(pos + 32) * in_pitch, v1);
+      Vec16<T>::load(base + (long long)(pos + 64) * in_pitch, v2);
+      Vec16<T>::load(base + (long long)(pos + 96) * in_pitch, v3);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += (v0[k] + v1[k]) + (v2[k] + v3[k]);
+    }
+    for (; pos < thw; pos += 32) {
       float v[8];
       Vec16<T>::load(base + (long long)pos * in_pitch, v);
 #pragma unroll
@@ -377,14 +461,14 @@ global_avgpool_kernel(const T* __restrict__ in, float* __restrict__ feats, int t
     }
   }
 #pragma unroll
-  for (int k = 0; k < V; ++k) part[warp][lane * V + k] = acc[k];
+  for (int k = 0; k < V; ++k) part[stream][vec * V + k] = acc[k];
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * V; i += blockDim.x) {
-    const int ch = blockIdx.y * 32 * V + i;
+  if (threadIdx.x < 8 * V) {
+    const int ch = blockIdx.y * 8 * V + threadIdx.x;
     if (ch < c) {
       float s = 0.f;
 #pragma unroll
-      for (int wq = 0; wq < 8; ++wq) s += part[wq][i];
+      for (int q = 0; q < 32; ++q) s += part[q][threadIdx.x];
       feats[(long long)clip * feat_pitch + feat_off + ch] = s / (float)thw;
     }
   }
@@ -500,6 +584,41 @@ static inline unsigned grid_for(long long total, int block) {
 
 using namespace vsb;
 
+// (A_c, B_c) such that bf16(fma(x, A_c, B_c)) == bf16(((x / 255) - mean_c) / std_c) for x = 0 .. 255, searched within a
+// few ulps of the exactly rounded coefficients; false when there is none (the caller then uses the table kernel).
+static bool pack_fma_coeffs(const float* mean3, const float* std3, PackFma* out) {
+  for (int c = 0; c < 3; ++c) {
+    unsigned short want[256];
+    for (int x = 0; x < 256; ++x) {
+      volatile float v = (float)x / 255.0f;
+      v = v - mean3[c];
+      v = v / std3[c];
+      want[x] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    }
+    const float a_mid = (float)(1.0 / (255.0 * (double)std3[c]));
+    const float b_mid = (float)(-(double)mean3[c] / (double)std3[c]);
+    bool found = false;
+    for (int r = 0; r <= 3 && !found; ++r)
+      for (int da = -r; da <= r && !found; ++da)
+        for (int db = -r; db <= r && !found; ++db) {
+          if (abs(da) != r && abs(db) != r) continue;
+          float a = a_mid, b = b_mid;
+          for (int i = 0; i < abs(da); ++i) a = nextafterf(a, da > 0 ? INFINITY : -INFINITY);
+          for (int i = 0; i < abs(db); ++i) b = nextafterf(b, db > 0 ? INFINITY : -INFINITY);
+          bool ok = true;
+          for (int x = 0; x < 256 && ok; ++x)
+            ok = __bfloat16_as_ushort(__float2bfloat16_rn(fmaf((float)x, a, b))) == want[x];
+          if (ok) {
+            out->a[c] = a;
+            out->b[c] = b;
+            found = true;
+          }
+        }
+    if (!found) return false;
+  }
+  return true;
+}
+
 extern "C" int vsb_pack_frames(const uint8_t* frames, int n, int t_in, int h, int w, const int* idx, int t_out,
                                const float* mean3, const float* std3, int reverse_channels, void* out, int c_pad,
                                int out_w, int x_off, int dtype, void* stream) {
@@ -522,7 +641,13 @@ extern "C" int vsb_pack_frames(const uint8_t* frames, int n, int t_in, int h, in
   const long long total = (long long)n * t_out * ((frame_px + 1023) / 1024);  // 1024-pixel chunks
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)(total < 148ll * 16 ? total : 148ll * 16);
-  if (dtype == VSB_BF16) {
+  PackFma fk;
+  static const bool use_table = getenv("VSB_PACK_TABLE") && atoi(getenv("VSB_PACK_TABLE")) != 0;  // A/B knob
+  if (dtype == VSB_BF16 && !use_table && frame_px * w < (1ll << 32) && pack_fma_coeffs(mean3, std3, &fk)) {
+    fk.magic_w = (unsigned)((1ull << 32) / (unsigned)w) + 1u;
+    pack_frames_fma_kernel<<<grid, 256, 0, s>>>(frames, static_cast<__nv_bfloat16*>(out), n, t_in, t_out, (int)frame_px,
+                                                 w, out_w, x_off, pi, fk, reverse_channels);
+  } else if (dtype == VSB_BF16) {
     pack_frames_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(frames, static_cast<__nv_bfloat16*>(out), n, t_in, t_out,
                                                           (int)frame_px, w, out_w, x_off, pi, mean3[0], mean3[1],
                                                           mean3[2], std3[0], std3[1], std3[2], reverse_channels);
@@ -613,7 +738,7 @@ extern "C" int vsb_global_avgpool(const void* in, int n, int thw, int c, int in_
   const int V = dtype == VSB_BF16 ? 8 : 4;
   VSB_CHECK_ARG(n > 0 && thw > 0 && c > 0 && c % V == 0 && in_pitch % V == 0 && in_pitch >= c, "bad extent");
   VSB_CHECK_ARG(feat_off >= 0 && feat_off + c <= feat_pitch, "feature slice outside the row");
-  dim3 grid(n, ceil_div(c, 32 * V));
+  dim3 grid(n, ceil_div(c, 8 * V));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == VSB_BF16)
     global_avgpool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in), feats, thw, c,

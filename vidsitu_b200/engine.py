@@ -689,6 +689,8 @@ class ClipEngine:
             return None
         a, b, c = blk.a, blk.b, blk.c
         d_store = self._store(a.cout)
+        if d_store == 16 and str(tn.get("thin_d16", os.environ.get("VSB_THIN_D16", "1"))) not in ("1", "True"):
+            return None
         if (d_store not in (8, 16) or x.c != 4 * d_store or self._store(c.cout) != x.c or x.c_real != a.cin
                 or x.c_off or x.pitch != x.c or c.cout != a.cin
                 or tuple(a.kernel[1:]) != (1, 1) or a.kernel[0] not in (1, 3) or tuple(b.kernel) != (1, 3, 3)
