@@ -46,8 +46,11 @@
 namespace vsb {
 
 namespace {
-constexpr int kComputeWarps = 15;            // a-warps + bc-warps (split chosen by the plan), + one fetch warp
-constexpr int kThinThreads = (kComputeWarps + 1) * 32;
+// a-warps + bc-warps (split chosen by the plan) + one fetch warp = 16 warps of 128 registers.  (24 warps of 80
+// registers were measured slower for d = 8, 0.28 - 0.31 vs 0.22 ms per res2 block at batch 64: the kernel is bound by
+// instruction issue and shared-memory wavefronts, not by exposed latency.)
+__host__ __device__ constexpr int compute_warps(int) { return 15; }
+__host__ __device__ constexpr int default_a_warps(int) { return 7; }
 // 16-pixel tiles per warp and frame step (unrolled)
 __host__ __device__ constexpr int max_a_tiles(int d) { return d == 8 ? 6 : 3; }
 __host__ __device__ constexpr int max_bc_tiles(int d) { return d == 8 ? 4 : 2; }
@@ -61,7 +64,7 @@ struct ThinParams {
   const float *sa, *ba, *sb, *bb, *sc, *bc;
   int n, T, H, W;
   int R, row_tiles;
-  int a_warps;  // warps 0 .. a_warps-1 run conv a, a_warps .. 14 conv b + c, warp 15 fetches
+  int a_warps;  // warps 0 .. a_warps-1 run conv a, the other compute warps conv b + c, the last warp fetches
   uint32_t out_pitch_bytes;
   int S;
   uint32_t slot_bytes, row_bytes;
@@ -130,6 +133,54 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void* src, uint32
 }
 __device__ __forceinline__ uint32_t sel(bool c, uint32_t a, uint32_t b) { return c ? a : b; }
 
+// mbarrier wait that lets the hardware park the thread (suspend-time hint) instead of polling: a spinning warp takes
+// issue slots from the working warps of its scheduler.  Bounded: a protocol bug traps.
+__device__ __forceinline__ void t_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(200000u)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 18)) __trap();
+  }
+}
+
+// Ring position of the frames around t: frame t sits in (slot, round) -- load index L = round * S + slot -- and
+// advances by one slot per frame step; the neighbours t - 1 / t + 1 are one slot back / ahead.  No division per step.
+struct RingPos {
+  uint32_t slot, round;
+  __device__ __forceinline__ void set(uint32_t L, uint32_t S) {
+    round = L / S;
+    slot = L - round * S;
+  }
+  __device__ __forceinline__ void step(uint32_t S) {
+    if (++slot == S) {
+      slot = 0;
+      ++round;
+    }
+  }
+  __device__ __forceinline__ RingPos at(int delta, uint32_t S) const {  // delta = -1, 0, +1
+    RingPos r = *this;
+    if (delta > 0) r.step(S);
+    if (delta < 0) {
+      if (r.slot == 0) {
+        r.slot = S - 1;
+        --r.round;
+      } else {
+        --r.slot;
+      }
+    }
+    return r;
+  }
+};
+
 // The 16-byte pieces (q = 0 .. NQ-1) of one pixel row for thread t: v[q] = bytes [64 q + 16 t, + 16) of the pixel;
 // addr = pixel address + 16 t.
 template <int NQ>
@@ -188,7 +239,8 @@ struct ThinWalk {
 }  // namespace
 
 template <int D, int KT>
-__global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const ThinParams p) {
+__global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thin_kernel(const ThinParams p) {
+  constexpr int kComputeWarps = compute_warps(D), kThinThreads = (kComputeWarps + 1) * 32;
   constexpr int C = 4 * D;        // block width
   constexpr int NQ = D / 8;       // 32-channel groups of the block width = 8-channel slices of the bottleneck width
   constexpr int NTD = D / 8;      // 8-column MMA tiles of the bottleneck width
@@ -257,7 +309,7 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
         const uint32_t bytes = (uint32_t)(row_hi - row_lo) * p.row_bytes;
         const uint32_t dst_off = (uint32_t)(row_lo - (wk.r0 - 1)) * p.row_bytes;
         for (int f = wk.f_lo; f <= wk.f_hi; ++f) {
-          if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+          if (round > 0) t_mbar_wait(&empty[slot], (round - 1) & 1);
           const uint8_t* src = p.x + (((long long)wk.n * p.T + f) * p.H + row_lo) * (long long)p.row_bytes;
           mbar_expect_tx(&full[slot], bytes);
           bulk_g2s(ring_s + slot * p.slot_bytes + dst_off, src, bytes, &full[slot]);
@@ -303,13 +355,16 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
         geo[sl][half] = px < p.a_px ? ((uint32_t)rr << 16) | (uint32_t)((rr * wp2 + col + 1) * AP + 4 * t4) : 0xFFFF0000u;
       }
     uint32_t istep = 0;
+    const uint32_t S = (uint32_t)p.S;
     while (wk.load<HT>(p)) {
       // strip rows [rr_lo, rr_hi) lie inside the image; the others are the zero padding of conv b
       const uint32_t rr_lo = wk.r0 == 0 ? 1u : 0u;
       const uint32_t rr_hi = (uint32_t)(p.H - wk.r0 + 1 < p.R + 2 ? p.H - wk.r0 + 1 : p.R + 2);
-      for (int t = wk.t0; t < wk.t1; ++t, ++istep) {
+      RingPos pos;  // of frame t
+      pos.set(wk.l0 + (uint32_t)(wk.t0 - wk.f_lo), S);
+      for (int t = wk.t0; t < wk.t1; ++t, ++istep, pos.step(S)) {
         const uint32_t b = istep & 1;
-        if (istep >= 2) mbar_wait(&a_empty[b], ((istep >> 1) - 1) & 1);
+        if (istep >= 2) t_mbar_wait(&a_empty[b], ((istep >> 1) - 1) & 1);
         uint32_t slot_s[KT];
         bool have[KT];
 #pragma unroll
@@ -318,10 +373,9 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
           have[tap] = f >= 0 && f < p.T;
           slot_s[tap] = ring_s;
           if (have[tap]) {
-            const uint32_t L = wk.l0 + (uint32_t)(f - wk.f_lo);
-            const uint32_t slot = L % (uint32_t)p.S;
-            mbar_wait(&full[slot], (L / (uint32_t)p.S) & 1);
-            slot_s[tap] = ring_s + slot * p.slot_bytes + 16 * t4;
+            const RingPos rp = pos.at(tap - HT, S);
+            t_mbar_wait(&full[rp.slot], rp.round & 1);
+            slot_s[tap] = ring_s + rp.slot * p.slot_bytes + 16 * t4;
           }
         }
         const uint32_t dst_s = abuf_s + b * p.a_buf_bytes;
@@ -371,10 +425,10 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
           mbar_arrive(&a_full[b]);
           // frames conv a no longer needs
           const int f_done = t - HT;
-          if (f_done >= wk.f_lo) mbar_arrive(&empty[(wk.l0 + (uint32_t)(f_done - wk.f_lo)) % (uint32_t)p.S]);
+          if (f_done >= wk.f_lo) mbar_arrive(&empty[pos.at(-HT, S).slot]);
           if (t == wk.t1 - 1)
             for (int f = (f_done + 1 > wk.f_lo ? f_done + 1 : wk.f_lo); f <= wk.f_hi; ++f)
-              mbar_arrive(&empty[(wk.l0 + (uint32_t)(f - wk.f_lo)) % (uint32_t)p.S]);
+              mbar_arrive(&empty[pos.at(f - t, S).slot]);
         }
       }
       wk.next();
@@ -406,17 +460,14 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
           wc_f[q][i][ks].x = *reinterpret_cast<const uint32_t*>(row);
           wc_f[q][i][ks].y = D >= 16 ? *reinterpret_cast<const uint32_t*>(row + 8) : 0u;
         }
-    float4 sb_f[NTD], sc_f[4];  // d = 8 only: the (scale, bias) pairs of conv b and conv c stay in registers
+    float4 sb_f[NTD];  // d = 8 only: the (scale, bias) pairs of conv b stay in registers
     if (D == 8) {
 #pragma unroll
       for (int nt = 0; nt < NTD; ++nt) sb_f[nt] = t_lds128f(sbc_s + 512 + (uint32_t)(nt * 4 + t4) * 16);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) sc_f[i] = t_lds128f(sbc_s + (uint32_t)(i * 4 + t4) * 16);
     }
-    // tile geometry: per tile slot and pixel row, [0] = byte offset of the pixel's centre in the a-tile buffer
-    // (+ 4 t) | byte offset of the pixel in the frame slot (+ 16 t) << 16, [1] = strip row << 24 | pixel index
-    // (0xFF...... = past the strip)
-    uint32_t geo[kMaxBCTiles][2][2];
+    // tile geometry: per tile slot and pixel row, byte offset of the pixel's centre in the a-tile buffer (+ 4 t) |
+    // pixel index in the strip << 16 | strip row << 26 (row 63 = past the strip)
+    uint32_t geo[kMaxBCTiles][2];
 #pragma unroll
     for (int sl = 0; sl < kMaxBCTiles; ++sl)
 #pragma unroll
@@ -425,27 +476,30 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
         const int pc = px < p.bc_px ? px : p.bc_px - 1;
         const int rr = (int)(((uint32_t)pc * p.magic_w) >> 24);
         const int col = pc - rr * p.W;
-        geo[sl][half][0] = (uint32_t)(((rr + 1) * wp2 + col + 1) * AP + 4 * t4) |
-                           ((uint32_t)(((rr + 1) * p.W + col) * CB + 16 * t4) << 16);
-        geo[sl][half][1] = px < p.bc_px ? ((uint32_t)rr << 24) | (uint32_t)pc : 0xFF000000u;
+        geo[sl][half] = (uint32_t)(((rr + 1) * wp2 + col + 1) * AP + 4 * t4) | ((uint32_t)pc << 16) |
+                        ((uint32_t)(px < p.bc_px ? rr : 63) << 26);
       }
+    const uint32_t res_base = (uint32_t)p.W * CB + 16 * t4;  // the slot starts one row above the strip
     const uint32_t rowb = (uint32_t)wp2 * AP;
     uint32_t istep = 0;
+    const uint32_t S = (uint32_t)p.S;
     while (wk.load<HT>(p)) {
       const uint32_t rr_hi = (uint32_t)(p.H - wk.r0 < p.R ? p.H - wk.r0 : p.R);
-      for (int t = wk.t0; t < wk.t1; ++t, ++istep) {
+      RingPos pos;  // of frame t
+      pos.set(wk.l0 + (uint32_t)(wk.t0 - wk.f_lo), S);
+      for (int t = wk.t0; t < wk.t1; ++t, ++istep, pos.step(S)) {
         const uint32_t b = istep & 1;
-        mbar_wait(&a_full[b], (istep >> 1) & 1);
-        const uint32_t L = wk.l0 + (uint32_t)(t - wk.f_lo);
-        const uint32_t slot = L % (uint32_t)p.S;
-        mbar_wait(&full[slot], (L / (uint32_t)p.S) & 1);
+        t_mbar_wait(&a_full[b], (istep >> 1) & 1);
+        const uint32_t slot = pos.slot;
+        t_mbar_wait(&full[slot], pos.round & 1);
         const uint32_t xs = ring_s + slot * p.slot_bytes;
         const uint32_t src_s = abuf_s + b * p.a_buf_bytes;
         uint8_t* out_frame = p.out + (((long long)wk.n * p.T + t) * p.H + wk.r0) * (long long)p.W * p.out_pitch_bytes + 16 * t4;
 #pragma unroll
         for (int sl = 0; sl < kMaxBCTiles; ++sl) {
           if (bw + kBCWarps * sl >= p.bc_tiles) break;
-          const uint32_t ctr0 = src_s + (geo[sl][0][0] & 0xFFFFu), ctr1 = src_s + (geo[sl][1][0] & 0xFFFFu);
+          const uint32_t g0 = geo[sl][0], g1 = geo[sl][1];
+          const uint32_t ctr0 = src_s + (g0 & 0xFFFFu), ctr1 = src_s + (g1 & 0xFFFFu);
           float accb[NTD][4];
 #pragma unroll
           for (int pr = 0; pr < NP; ++pr) {
@@ -476,11 +530,11 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
           }
           // residual = x[t] at the tile's pixels, already in the c accumulator's layout (plain loads: two-way bank
           // conflicts for d = 16, but half the registers of the swapped pair loads conv a uses)
-          const uint32_t res0 = xs + (geo[sl][0][0] >> 16), res1 = xs + (geo[sl][1][0] >> 16);
-          const uint32_t g0 = geo[sl][0][1], g1 = geo[sl][1][1];
-          const bool valid0 = (g0 >> 24) < rr_hi, valid1 = (g1 >> 24) < rr_hi;
-          uint8_t* out0 = out_frame + (size_t)(g0 & 0xFFFFFFu) * p.out_pitch_bytes;
-          uint8_t* out1 = out_frame + (size_t)(g1 & 0xFFFFFFu) * p.out_pitch_bytes;
+          const uint32_t pc0 = (g0 >> 16) & 0x3FFu, pc1 = (g1 >> 16) & 0x3FFu;
+          const uint32_t res0 = xs + res_base + pc0 * CB, res1 = xs + res_base + pc1 * CB;
+          const bool valid0 = (g0 >> 26) < rr_hi, valid1 = (g1 >> 26) < rr_hi;
+          uint8_t* out0 = out_frame + (size_t)pc0 * p.out_pitch_bytes;
+          uint8_t* out1 = out_frame + (size_t)pc1 * p.out_pitch_bytes;
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
             uint32_t og[4], oh[4];
@@ -501,7 +555,7 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
               } else {
                 mma1688_z(accc, pb[0][0], pb[0][1], wc_f[q][i][0].x);
               }
-              const float4 s4 = D == 8 ? sc_f[i] : t_lds128f(sbc_s + (uint32_t)((q * 4 + i) * 4 + t4) * 16);
+              const float4 s4 = t_lds128f(sbc_s + (uint32_t)((q * 4 + i) * 4 + t4) * 16);
               const uint32_t r_g = piece_reg(rgq, i), r_h = piece_reg(rhq, i);
               og[i] = pack_relu_bf16x2(fmaf(accc[0], s4.x, s4.y) + bf16_lo(r_g), fmaf(accc[1], s4.z, s4.w) + bf16_hi(r_g));
               oh[i] = pack_relu_bf16x2(fmaf(accc[2], s4.x, s4.y) + bf16_lo(r_h), fmaf(accc[3], s4.z, s4.w) + bf16_hi(r_h));
@@ -516,9 +570,9 @@ __global__ void __launch_bounds__(kThinThreads, 1) bottleneck_thin_kernel(const 
           mbar_arrive(&empty[slot]);
           // halo frames of the walk that no bc step visits
           if (t == wk.t0)
-            for (int f = wk.f_lo; f < wk.t0; ++f) mbar_arrive(&empty[(wk.l0 + (uint32_t)(f - wk.f_lo)) % (uint32_t)p.S]);
+            for (int f = wk.f_lo; f < wk.t0; ++f) mbar_arrive(&empty[pos.at(f - t, S).slot]);
           if (t == wk.t1 - 1)
-            for (int f = wk.t1; f <= wk.f_hi; ++f) mbar_arrive(&empty[(wk.l0 + (uint32_t)(f - wk.f_lo)) % (uint32_t)p.S]);
+            for (int f = wk.t1; f <= wk.f_hi; ++f) mbar_arrive(&empty[pos.at(f - t, S).slot]);
         }
       }
       wk.next();
@@ -562,9 +616,9 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   p.row_bytes = (uint32_t)d->w * d->c * 2;
   const uint32_t a_pitch = d->d == 8 ? 16u : (uint32_t)d->d * 2 + 16;  // as AP in the kernel
   p.magic_w = (1u << 24) / (uint32_t)d->w + 1;
-  int a_warps = 7;  // experiments: VSB_THIN_AWARPS
-  if (getenv("VSB_THIN_AWARPS")) a_warps = atoi(getenv("VSB_THIN_AWARPS"));
-  if (a_warps < 6 || a_warps > 8) a_warps = 7;
+  int a_warps = d->d == 8 ? default_a_warps(8) : default_a_warps(16);  // experiments: VSB_THIN_AWARPS
+  if (getenv("VSB_THIN_AWARPS") && d->d == 8) a_warps = atoi(getenv("VSB_THIN_AWARPS"));
+  if (a_warps < 4 || a_warps > compute_warps(d->d) - 4) a_warps = default_a_warps(d->d);
   p.a_warps = a_warps;
   const int ht = d->kt / 2;
   const int min_slots = d->kt + 1;
@@ -582,8 +636,8 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
     if (s > 6) s = 6;
     if (d->stages > 0 && s > d->stages) s = d->stages;
     if (s < min_slots) continue;
-    if (abuf > 0xFFFF || slot > 0xFFFF) continue;  // tile geometry is packed in 16-bit offsets
-    if (ceil_div((r + 2) * d->w, 16) > a_warps * max_a_tiles(d->d) || ceil_div(r * d->w, 16) > (kComputeWarps - a_warps) * max_bc_tiles(d->d)) continue;
+    if (abuf > 0xFFFF || slot > 0xFFFF || r * d->w > 1023 || r > 60) continue;  // tile geometry is bit-packed
+    if (ceil_div((r + 2) * d->w, 16) > a_warps * max_a_tiles(d->d) || ceil_div(r * d->w, 16) > (compute_warps(d->d) - a_warps) * max_bc_tiles(d->d)) continue;
     // cost: rows fetched per frame (halo included), a small penalty for a short ring
     const long long cost = (long long)ceil_div(d->h, r) * (r + 2) * 16 + (s < min_slots + 1 ? 8 : 0);
     if (!best_r || cost < best_cost) {
@@ -648,13 +702,13 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
 int thin_run(const ThinPlan* plan, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (plan->d == 8 && plan->kt == 3)
-    bottleneck_thin_kernel<8, 3><<<plan->grid, kThinThreads, plan->smem_bytes, s>>>(plan->params);
+    bottleneck_thin_kernel<8, 3><<<plan->grid, (compute_warps(8) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
   else if (plan->d == 8)
-    bottleneck_thin_kernel<8, 1><<<plan->grid, kThinThreads, plan->smem_bytes, s>>>(plan->params);
+    bottleneck_thin_kernel<8, 1><<<plan->grid, (compute_warps(8) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
   else if (plan->kt == 3)
-    bottleneck_thin_kernel<16, 3><<<plan->grid, kThinThreads, plan->smem_bytes, s>>>(plan->params);
+    bottleneck_thin_kernel<16, 3><<<plan->grid, (compute_warps(16) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
   else
-    bottleneck_thin_kernel<16, 1><<<plan->grid, kThinThreads, plan->smem_bytes, s>>>(plan->params);
+    bottleneck_thin_kernel<16, 1><<<plan->grid, (compute_warps(16) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
   VSB_CHECK_LAUNCH("bottleneck_thin_kernel");
   return VSB_OK;
 }
