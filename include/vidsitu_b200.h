@@ -215,6 +215,11 @@ typedef struct vsb_bottleneck_desc {
    * run on mma.sync fragments (the Fast pathway's res2 / res3, where a tcgen05.mma would be N <= 64 wide and
    * issue-bound).  Same tensors, weight layouts and rounding points as algo 0. */
   int algo;
+  /* algo 1 only.  0 = identity block (x has c channels).  8 = block 0 of a stage WITH a 1x1x1 projection shortcut
+   * (resnet_helper.py:296-310, 352-358: relu(BN_1(W1 x) + BN_c(c(..)))) and unit strides: x has cin = d = 8 channels,
+   * wa is [d][kt][cin], wc is [c][d + cin] = [Wc * r_c | W1 * r_1] with the two BatchNorm scales folded as ratios to
+   * the common per-channel scale sc, bc = the sum of the two biases; out = relu(sc * ([b | x] . wc) + bc). */
+  int cin;
 } vsb_bottleneck_desc;
 
 typedef struct vsb_bottleneck_plan vsb_bottleneck_plan;

@@ -64,6 +64,14 @@ CASES = [
     ("thin_crop64_s2", 2, 32, 16, 16, 32, 8, 3, dict(algo=1), 0, 0),
     ("thin_crop64_s3", 2, 32, 8, 8, 64, 16, 3, dict(algo=1), 0, 0),
     ("thin_many_steps", 8, 32, 28, 28, 64, 16, 3, dict(algo=1), 0, 0),
+    # algo 1, block 0 of a stage with a projection shortcut (cin = d = 8, out 32 channels)
+    ("thin_proj_s2_like", 2, 8, 56, 56, 32, 8, 3, dict(algo=1, cin=8), 0, 0),
+    ("thin_proj_odd_13x11", 2, 5, 13, 11, 32, 8, 3, dict(algo=1, cin=8), 0, 0),
+    ("thin_proj_kt1", 2, 4, 28, 28, 32, 8, 1, dict(algo=1, cin=8), 0, 0),
+    ("thin_proj_rows5_grid3", 3, 6, 28, 28, 32, 8, 3, dict(algo=1, cin=8, walk_len=5, grid=3), 0, 0),
+    ("thin_proj_pitched_out", 2, 4, 16, 16, 32, 8, 3, dict(algo=1, cin=8), 0, 48),
+    ("thin_proj_x16", 2, 8, 56, 56, 32, 8, 3, dict(algo=1, cin=8), 16, 0),
+    ("thin_proj_x16_odd", 2, 5, 13, 11, 32, 8, 3, dict(algo=1, cin=8), 16, 0),
 ]
 
 # full-size blocks of SlowFast-R50 8x8, batch 64 (Fast pathway res2 on 2-pixel groups, res3, res4)
@@ -76,6 +84,8 @@ BENCH_CASES = [
     ("bench_thin_s3", 64, 32, 28, 28, 64, 16, 3, dict(algo=1), 0, 0),
     ("bench_thin_s2_slots4", 64, 32, 56, 56, 32, 8, 3, dict(algo=1, stages=4), 0, 0),
     ("bench_thin_s2_rows7", 64, 32, 56, 56, 32, 8, 3, dict(algo=1, walk_len=7), 0, 0),
+    ("bench_thin_proj_s2", 64, 32, 56, 56, 32, 8, 3, dict(algo=1, cin=8), 0, 0),
+    ("bench_thin_proj_s2_x16", 64, 32, 56, 56, 32, 8, 3, dict(algo=1, cin=8), 16, 0),
 ]
 
 
@@ -83,10 +93,11 @@ def make_case(case):
     name, n, t, h, w, c, d, kt, tune, xp, op = case
     dev = "cuda"
     g = torch.Generator(device="cpu").manual_seed(zlib.crc32(name.encode()) % (2 ** 31))
-    xp = xp or c
+    cin = tune.get("cin", 0) or c
+    xp = xp or cin
     op = op or c
     xbuf = torch.randn((n, t, h, w, xp), generator=g).to(torch.bfloat16).to(dev)
-    wa = (torch.randn((d, c, kt, 1, 1), generator=g) / (c * kt) ** 0.5).to(torch.bfloat16).to(dev)
+    wa = (torch.randn((d, cin, kt, 1, 1), generator=g) / (cin * kt) ** 0.5).to(torch.bfloat16).to(dev)
     wb = (torch.randn((d, d, 1, 3, 3), generator=g) / (9 * d) ** 0.5).to(torch.bfloat16).to(dev)
     wc = (torch.randn((c, d, 1, 1, 1), generator=g) / d ** 0.5).to(torch.bfloat16).to(dev)
     aff = []
@@ -107,14 +118,44 @@ def reference(x, wa, wb, wc, aff, kt):
     return y.permute(0, 2, 3, 4, 1)
 
 
+def reference_proj(x, wa, wb, wcat, aff, kt, d):
+    """Projection block as the kernel (and the engine's fused-shortcut conv) computes it: one accumulation over
+    [b | x] with the folded bf16 weights, then the common scale and the summed bias."""
+    sa, ba, sb, bb, s, bsum = aff
+    v = lambda q: q.view(1, -1, 1, 1, 1)
+    xc = x.float().permute(0, 4, 1, 2, 3)
+    a = torch.relu(F.conv3d(xc, wa.float(), padding=(kt // 2, 0, 0)) * v(sa) + v(ba)).to(torch.bfloat16).float()
+    b = torch.relu(F.conv3d(a, wb.float(), padding=(0, 1, 1)) * v(sb) + v(bb)).to(torch.bfloat16).float()
+    wf = wcat.float()
+    acc = F.conv3d(b, wf[:, :d, None, None, None]) + F.conv3d(xc, wf[:, d:, None, None, None])
+    return torch.relu(acc * v(s) + v(bsum)).permute(0, 2, 3, 4, 1)
+
+
 def run_case(case, bench=False):
     name, n, t, h, w, c, d, kt, tune, _, _ = case
     xbuf, wa, wb, wc, aff, outbuf, xp, op = make_case(case)
-    wa_p = wa.permute(0, 2, 3, 4, 1).reshape(d, kt, c).contiguous()
+    cin = tune.get("cin", 0)
+    wa_p = wa.permute(0, 2, 3, 4, 1).reshape(d, kt, cin or c).contiguous()
     wb_p = wb.permute(0, 2, 3, 4, 1).reshape(d, 9, d).contiguous()
     wc_p = wc.reshape(c, d).contiguous()
-    plan = BottleneckPlan(Act(xbuf, n, t, h, w, c, xp), Act(outbuf, n, t, h, w, c, op), d, kt, wa_p, wb_p, wc_p, *aff,
+    if cin:
+        # fold the two BatchNorm scales as ratios to the larger one (engine._conv_with_shortcut)
+        g = torch.Generator(device="cpu").manual_seed(zlib.crc32((name + "proj").encode()) % (2 ** 31))
+        w1 = (torch.randn((c, cin), generator=g) / cin ** 0.5).cuda()
+        s_1 = (torch.rand(c, generator=g) + 0.5).cuda() * torch.where(torch.rand(c, generator=g) < 0.3, -1.0, 1.0).cuda()
+        b_1 = (torch.randn(c, generator=g) * 0.1).cuda()
+        s_c, b_c = aff[4], aff[5]
+        use_c = s_c.abs() >= s_1.abs()
+        s = torch.where(use_c, s_c, s_1)
+        wc_p = torch.cat([wc_p.float() * (s_c / s)[:, None], w1 * (s_1 / s)[:, None]], dim=1).to(torch.bfloat16).contiguous()
+        aff = aff[:4] + [s.contiguous(), (b_c + b_1).contiguous()]
+    plan = BottleneckPlan(Act(xbuf, n, t, h, w, cin or c, xp), Act(outbuf, n, t, h, w, c, op), d, kt, wa_p, wb_p, wc_p, *aff,
                           **tune)
+    if cin:
+        reference_fn = lambda xx, *_: reference_proj(xx, wa, wb, wc_p, aff, kt, d)
+    else:
+        reference_fn = lambda xx, *_: reference(xx, wa, wb, wc, aff, kt)
+    cx = cin or c
     info = {"plan": plan.info()}
     plan.run()
     torch.cuda.synchronize()
@@ -131,14 +172,14 @@ def run_case(case, bench=False):
         ms = e0.elapsed_time(e1) / iters
         px = n * t * h * w
         info["ms"] = ms
-        info["hbm_gbs"] = px * c * 2 * 2 / ms / 1e6
+        info["hbm_gbs"] = px * (c + cx) * 2 / ms / 1e6
         info["tflops"] = 2.0 * px * (kt * c * d + 9 * d * d + d * c) / ms / 1e9
         # reference on a slice of the batch (memory)
         ns = 2
-        ref = reference(xbuf[:ns, ..., :c], wa, wb, wc, aff, kt)
+        ref = reference_fn(xbuf[:ns, ..., :cx])
         got = outbuf[:ns, ..., :c].float()
     else:
-        ref = reference(xbuf[..., :c], wa, wb, wc, aff, kt)
+        ref = reference_fn(xbuf[..., :cx])
         got = outbuf[..., :c].float()
     err = (got - ref).abs()
     tol = 2e-2 + 1.6e-2 * ref.abs()

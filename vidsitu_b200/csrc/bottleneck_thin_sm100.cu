@@ -68,6 +68,7 @@ struct ThinParams {
   uint32_t out_pitch_bytes;
   int S;
   uint32_t slot_bytes, row_bytes;
+  uint32_t x_px_bytes;  // bytes per x pixel (projection blocks: the pitch may exceed the 8 channels read)
   int a_px, a_tiles, bc_px, bc_tiles;
   uint32_t a_buf_bytes;
   uint32_t off_abuf, off_sbc, off_bar;
@@ -124,6 +125,12 @@ __device__ __forceinline__ void mma1688_z(float (&d)[4], uint32_t a0, uint32_t a
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%7, %7, %7, %7};"
                : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
                : "r"(a0), "r"(a1), "r"(b0), "f"(0.f));
+}
+// D (16 x 8, fp32) += A (16 x 8, bf16, row) . B (8 x 8, bf16, col)
+__device__ __forceinline__ void mma1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0));
 }
 // contiguous global -> shared copy by the TMA unit (no tensor map), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -238,14 +245,20 @@ struct ThinWalk {
 
 }  // namespace
 
-template <int D, int KT>
+// PROJ: block 0 of a stage with a 1x1x1 projection shortcut and unit strides (d = 8 only: the Fast pathway's res2):
+// x has d channels, conv c and the shortcut are ONE K = 16 MMA per column tile -- [b | x[t]] . [Wc' ; W1'] with the two
+// BatchNorm scales folded into the weights as ratios to a common per-channel scale, exactly as the three-launch
+// engine's fused-shortcut conv does (engine._conv_with_shortcut) -- and there is no residual.
+template <int D, int KT, bool PROJ>
 __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thin_kernel(const ThinParams p) {
+  static_assert(!PROJ || D == 8, "projection blocks: d = 8 only");
   constexpr int kComputeWarps = compute_warps(D), kThinThreads = (kComputeWarps + 1) * 32;
-  constexpr int C = 4 * D;        // block width
-  constexpr int NQ = D / 8;       // 32-channel groups of the block width = 8-channel slices of the bottleneck width
+  constexpr int C = PROJ ? D : 4 * D;  // channels of x
+  constexpr int NQ = D / 8;       // 32-channel groups of the output = 8-channel slices of the bottleneck width
   constexpr int NTD = D / 8;      // 8-column MMA tiles of the bottleneck width
   constexpr int HT = KT / 2;
-  constexpr int CB = C * 2;       // bytes per x pixel
+  constexpr int CBc = C * 2;      // bytes per x pixel (identity blocks: dense)
+  const uint32_t CB = PROJ ? p.x_px_bytes : (uint32_t)CBc;
   constexpr int NSL = 9 * NQ;     // 8-channel K slices of conv b (tap-major)
   constexpr int NP = (NSL + 1) / 2;
   constexpr int KSC = D >= 16 ? D / 16 : 1;  // K steps of conv c
@@ -326,16 +339,23 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
     // weight fragments: step (tap, q, h) of K, column tile nt: b0 = Wa[8 nt + g][tap][8 (4 q + t) + 4 h + {0, 1}],
     // b1 = the next two channels
     uint2 wa_f[KT][NQ][2][NTD];
+    uint32_t wa_p[KT];  // PROJ: x has 8 channels, tap's fragment = Wa[g][tap][2 t, + 1]
+    if constexpr (PROJ) {
 #pragma unroll
-    for (int tap = 0; tap < KT; ++tap)
+      for (int tap = 0; tap < KT; ++tap)
+        wa_p[tap] = *reinterpret_cast<const uint32_t*>(p.wa + ((size_t)g * KT + tap) * C + 2 * t4);
+    } else {
 #pragma unroll
-      for (int q = 0; q < NQ; ++q)
+      for (int tap = 0; tap < KT; ++tap)
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int q = 0; q < NQ; ++q)
 #pragma unroll
-          for (int nt = 0; nt < NTD; ++nt)
-            wa_f[tap][q][h][nt] = *reinterpret_cast<const uint2*>(
-                p.wa + ((size_t)(8 * nt + g) * KT + tap) * C + 8 * (4 * q + t4) + 4 * h);
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int nt = 0; nt < NTD; ++nt)
+              wa_f[tap][q][h][nt] = *reinterpret_cast<const uint2*>(
+                  p.wa + ((size_t)(8 * nt + g) * KT + tap) * C + 8 * (4 * q + t4) + 4 * h);
+    }
     float4 sa_f[NTD];  // (scale, bias) of channels 8 nt + 2 t, + 1
 #pragma unroll
     for (int nt = 0; nt < NTD; ++nt) {
@@ -375,7 +395,7 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
           if (have[tap]) {
             const RingPos rp = pos.at(tap - HT, S);
             t_mbar_wait(&full[rp.slot], rp.round & 1);
-            slot_s[tap] = ring_s + rp.slot * p.slot_bytes + 16 * t4;
+            slot_s[tap] = ring_s + rp.slot * p.slot_bytes + (PROJ ? 4 : 16) * t4;
           }
         }
         const uint32_t dst_s = abuf_s + b * p.a_buf_bytes;
@@ -387,6 +407,22 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
           const uint32_t off_g = (uint32_t)(px_g < p.a_px ? px_g : p.a_px - 1) * CB;
           const uint32_t off_h = (uint32_t)(px_h < p.a_px ? px_h : p.a_px - 1) * CB;
           float acc[NTD][4];
+          if constexpr (PROJ) {
+            // 8 channels per tap: taps 0 and 1 are the two halves of one K = 16 MMA, tap 2 a K = 8 MMA; a missing
+            // frame (temporal padding) is a zero fragment
+            uint32_t xg[KT], xh[KT];
+#pragma unroll
+            for (int tap = 0; tap < KT; ++tap) {
+              xg[tap] = have[tap] ? t_lds32(slot_s[tap] + off_g) : 0u;
+              xh[tap] = have[tap] ? t_lds32(slot_s[tap] + off_h) : 0u;
+            }
+            if (KT == 3) {
+              mma16816_z(acc[0], xg[0], xh[0], xg[1], xh[1], wa_p[0], wa_p[1]);
+              mma1688(acc[0], xg[KT - 1], xh[KT - 1], wa_p[KT - 1]);
+            } else {
+              mma1688_z(acc[0], xg[0], xh[0], wa_p[0]);
+            }
+          } else {
 #pragma unroll
           for (int nt = 0; nt < NTD; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
@@ -403,6 +439,7 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
                 for (int nt = 0; nt < NTD; ++nt)
                   mma16816(acc[nt], piece_reg(vg[q], 2 * h), piece_reg(vh[q], 2 * h), piece_reg(vg[q], 2 * h + 1),
                            piece_reg(vh[q], 2 * h + 1), wa_f[tap][q][h][nt].x, wa_f[tap][q][h][nt].y);
+          }
           }
           // BN + ReLU -> bf16 -> a-tile buffer; rows outside the image are the zero padding of conv b
 #pragma unroll
@@ -456,9 +493,10 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
 #pragma unroll
         for (int ks = 0; ks < KSC; ++ks) {
           const int co = 8 * (4 * q + (g >> 1)) + 2 * i + (g & 1);
-          const __nv_bfloat16* row = p.wc + (size_t)co * D + 16 * ks + 2 * t4;
+          // PROJ: rows of [Wc' | W1'], K = 8 + 8
+          const __nv_bfloat16* row = p.wc + (size_t)co * (PROJ ? 2 * D : D) + 16 * ks + 2 * t4;
           wc_f[q][i][ks].x = *reinterpret_cast<const uint32_t*>(row);
-          wc_f[q][i][ks].y = D >= 16 ? *reinterpret_cast<const uint32_t*>(row + 8) : 0u;
+          wc_f[q][i][ks].y = (D >= 16 || PROJ) ? *reinterpret_cast<const uint32_t*>(row + 8) : 0u;
         }
     float4 sb_f[NTD];  // d = 8 only: the (scale, bias) pairs of conv b stay in registers
     if (D == 8) {
@@ -479,7 +517,7 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
         geo[sl][half] = (uint32_t)(((rr + 1) * wp2 + col + 1) * AP + 4 * t4) | ((uint32_t)pc << 16) |
                         ((uint32_t)(px < p.bc_px ? rr : 63) << 26);
       }
-    const uint32_t res_base = (uint32_t)p.W * CB + 16 * t4;  // the slot starts one row above the strip
+    const uint32_t res_base = (uint32_t)p.W * CB + (PROJ ? 4 : 16) * t4;  // the slot starts one row above the strip
     const uint32_t rowb = (uint32_t)wp2 * AP;
     uint32_t istep = 0;
     const uint32_t S = (uint32_t)p.S;
@@ -538,11 +576,21 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
             uint32_t og[4], oh[4];
-            const uint4 rgq = t_lds128(res0 + 64 * q), rhq = t_lds128(res1 + 64 * q);
+            uint4 rgq = make_uint4(0, 0, 0, 0), rhq = rgq;
+            uint32_t xg = 0, xh = 0;  // PROJ: x[t] at the tile's pixels, channels 2 t, + 1 = the second K half of conv c
+            if constexpr (PROJ) {
+              xg = t_lds32(res0);
+              xh = t_lds32(res1);
+            } else {
+              rgq = t_lds128(res0 + 64 * q);
+              rhq = t_lds128(res1 + 64 * q);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float accc[4];
-              if (D >= 16) {
+              if constexpr (PROJ) {
+                mma16816_z(accc, pb[0][0], pb[0][1], xg, xh, wc_f[q][i][0].x, wc_f[q][i][0].y);
+              } else if (D >= 16) {
 #pragma unroll
                 for (int ks = 0; ks < KSC; ++ks) {
                   if (ks == 0)
@@ -556,9 +604,14 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
                 mma1688_z(accc, pb[0][0], pb[0][1], wc_f[q][i][0].x);
               }
               const float4 s4 = t_lds128f(sbc_s + (uint32_t)((q * 4 + i) * 4 + t4) * 16);
-              const uint32_t r_g = piece_reg(rgq, i), r_h = piece_reg(rhq, i);
-              og[i] = pack_relu_bf16x2(fmaf(accc[0], s4.x, s4.y) + bf16_lo(r_g), fmaf(accc[1], s4.z, s4.w) + bf16_hi(r_g));
-              oh[i] = pack_relu_bf16x2(fmaf(accc[2], s4.x, s4.y) + bf16_lo(r_h), fmaf(accc[3], s4.z, s4.w) + bf16_hi(r_h));
+              if constexpr (PROJ) {
+                og[i] = pack_relu_bf16x2(fmaf(accc[0], s4.x, s4.y), fmaf(accc[1], s4.z, s4.w));
+                oh[i] = pack_relu_bf16x2(fmaf(accc[2], s4.x, s4.y), fmaf(accc[3], s4.z, s4.w));
+              } else {
+                const uint32_t r_g = piece_reg(rgq, i), r_h = piece_reg(rhq, i);
+                og[i] = pack_relu_bf16x2(fmaf(accc[0], s4.x, s4.y) + bf16_lo(r_g), fmaf(accc[1], s4.z, s4.w) + bf16_hi(r_g));
+                oh[i] = pack_relu_bf16x2(fmaf(accc[2], s4.x, s4.y) + bf16_lo(r_h), fmaf(accc[3], s4.z, s4.w) + bf16_hi(r_h));
+              }
             }
             if (valid0) t_stg128(out0 + 64 * q, og[0], og[1], og[2], og[3]);
             if (valid1) t_stg128(out1 + 64 * q, oh[0], oh[1], oh[2], oh[3]);
@@ -585,23 +638,29 @@ struct ThinPlan {
   ThinParams params;
   size_t smem_bytes;
   unsigned grid;
-  int d, kt;
+  int d, kt, proj;
 };
 
-template <int D, int KT>
+template <int D, int KT, bool PROJ>
 static cudaError_t thin_set_attr() {
-  return cudaFuncSetAttribute(bottleneck_thin_kernel<D, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return cudaFuncSetAttribute(bottleneck_thin_kernel<D, KT, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 bool thin_eligible(const vsb_bottleneck_desc* d) {
-  return (d->d == 8 || d->d == 16) && d->c == 4 * d->d && d->x_pitch == d->c;
+  const int cin = d->cin > 0 ? d->cin : d->c;
+  return (d->d == 8 || d->d == 16) && d->c == 4 * d->d && (d->x_pitch == cin || (cin == 8 && d->x_pitch == 16)) &&
+         (cin == d->c || (cin == d->d && d->d == 8));
 }
 
 int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   *out_plan = nullptr;
   VSB_CHECK_ARG(d->d == 8 || d->d == 16, "warp-MMA bottleneck: bottleneck width (stored) must be 8 or 16");
   VSB_CHECK_ARG(d->c == 4 * d->d, "warp-MMA bottleneck: block width must be 4 x the bottleneck width");
-  VSB_CHECK_ARG(d->x_pitch == d->c, "warp-MMA bottleneck: x must be dense (pitch == c): frames are fetched as one range");
+  const int cin = d->cin > 0 ? d->cin : d->c;  // cin != c: block with a projection shortcut (wc = [Wc' | W1'])
+  const bool proj = cin != d->c;
+  VSB_CHECK_ARG(!proj || (d->d == 8 && cin == 8), "warp-MMA bottleneck: projection blocks need d = cin = 8");
+  VSB_CHECK_ARG(d->x_pitch == cin || (proj && d->x_pitch == 16),
+                "warp-MMA bottleneck: x must be dense (pitch == channels; projection blocks: 8 or 16): frames are fetched as one range");
   VSB_CHECK_ARG(d->out_pitch >= d->c && d->out_pitch % 8 == 0, "out pitch must be >= c and a multiple of 8 elements");
   VSB_CHECK_ARG(d->w <= 256 && d->h <= 4096, "frame too large");
   ThinParams p{};
@@ -613,7 +672,8 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   p.sa = d->sa; p.ba = d->ba; p.sb = d->sb; p.bb = d->bb; p.sc = d->sc; p.bc = d->bc;
   p.n = d->n; p.T = d->t; p.H = d->h; p.W = d->w;
   p.out_pitch_bytes = (uint32_t)d->out_pitch * 2;
-  p.row_bytes = (uint32_t)d->w * d->c * 2;
+  p.row_bytes = (uint32_t)d->w * d->x_pitch * 2;
+  p.x_px_bytes = (uint32_t)d->x_pitch * 2;
   const uint32_t a_pitch = d->d == 8 ? 16u : (uint32_t)d->d * 2 + 16;  // as AP in the kernel
   p.magic_w = (1u << 24) / (uint32_t)d->w + 1;
   int a_warps = d->d == 8 ? default_a_warps(8) : default_a_warps(16);  // experiments: VSB_THIN_AWARPS
@@ -680,10 +740,11 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   p.steps_per_cta = (int)ceil_div_ll(p.total_steps, grid);
 
   cudaError_t e = cudaSuccess;
-  if (d->d == 8 && d->kt == 3) e = thin_set_attr<8, 3>();
-  else if (d->d == 8) e = thin_set_attr<8, 1>();
-  else if (d->kt == 3) e = thin_set_attr<16, 3>();
-  else e = thin_set_attr<16, 1>();
+  if (proj) e = d->kt == 3 ? thin_set_attr<8, 3, true>() : thin_set_attr<8, 1, true>();
+  else if (d->d == 8 && d->kt == 3) e = thin_set_attr<8, 3, false>();
+  else if (d->d == 8) e = thin_set_attr<8, 1, false>();
+  else if (d->kt == 3) e = thin_set_attr<16, 3, false>();
+  else e = thin_set_attr<16, 1, false>();
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(bottleneck_thin_kernel) failed: %s", cudaGetErrorString(e));
     return VSB_ERR_CUDA;
@@ -695,20 +756,25 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   plan->grid = (unsigned)ceil_div_ll(p.total_steps, p.steps_per_cta);
   plan->d = d->d;
   plan->kt = d->kt;
+  plan->proj = proj ? 1 : 0;
   *out_plan = plan;
   return VSB_OK;
 }
 
 int thin_run(const ThinPlan* plan, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (plan->d == 8 && plan->kt == 3)
-    bottleneck_thin_kernel<8, 3><<<plan->grid, (compute_warps(8) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
+  if (plan->proj && plan->kt == 3)
+    bottleneck_thin_kernel<8, 3, true><<<plan->grid, (compute_warps(8) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
+  else if (plan->proj)
+    bottleneck_thin_kernel<8, 1, true><<<plan->grid, (compute_warps(8) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
+  else if (plan->d == 8 && plan->kt == 3)
+    bottleneck_thin_kernel<8, 3, false><<<plan->grid, (compute_warps(8) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
   else if (plan->d == 8)
-    bottleneck_thin_kernel<8, 1><<<plan->grid, (compute_warps(8) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
+    bottleneck_thin_kernel<8, 1, false><<<plan->grid, (compute_warps(8) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
   else if (plan->kt == 3)
-    bottleneck_thin_kernel<16, 3><<<plan->grid, (compute_warps(16) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
+    bottleneck_thin_kernel<16, 3, false><<<plan->grid, (compute_warps(16) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
   else
-    bottleneck_thin_kernel<16, 1><<<plan->grid, (compute_warps(16) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
+    bottleneck_thin_kernel<16, 1, false><<<plan->grid, (compute_warps(16) + 1) * 32, plan->smem_bytes, s>>>(plan->params);
   VSB_CHECK_LAUNCH("bottleneck_thin_kernel");
   return VSB_OK;
 }

@@ -620,11 +620,13 @@ class ClipEngine:
         restated on J-pixel groups (J * d = 16 channels at least) exactly like the single convs.  Returns None
         when the block is outside the kernel's domain (then the three-launch path runs)."""
         tn = self._tune(blk.prefix)
-        if self.dtype != VSB_BF16 or blk.branch1 is not None or blk.nonlocal_ is not None:
+        if self.dtype != VSB_BF16 or blk.nonlocal_ is not None:
             return None
         thin = self._thin_block(x, blk, out_pitch, tn)
         if thin is not None:
             return thin
+        if blk.branch1 is not None:
+            return None
         # opt-in (tune fuse_block / VSB_FUSE_BLOCK=1): measured on B200 the fused launch is at parity with the three
         # launches on the thin Fast pathway (it is bound by the TMA unit and the single MMA-issuing thread, not by HBM)
         # and, owning the whole SM, it no longer overlaps the Slow pathway's kernels: 11.53 vs 11.39 ms per step
@@ -681,34 +683,63 @@ class ClipEngine:
         return y
 
     def _thin_block(self, x: Act, blk: BlockSpec, out_pitch: Optional[int], tn: dict) -> Optional[Act]:
-        """Identity ResBlock of a THIN stage (stored bottleneck width 8 or 16, block width 4x that: the Fast
-        pathway's res2 / res3) as ONE launch of the warp-MMA walk kernel (vsb_bottleneck_* algo 1,
+        """ResBlock of a THIN stage (stored bottleneck width 8 or 16, block width 4x that: the Fast pathway's
+        res2 / res3) with unit strides as ONE launch of the warp-MMA walk kernel (vsb_bottleneck_* algo 1,
         bottleneck_thin_sm100.cu): ungrouped weights, every frame of a row strip fetched once, a's and b's outputs
-        never reach HBM.  On by default (VSB_THIN_BLOCK=0 / tune {"thin_block": False} keeps the three launches)."""
+        never reach HBM.  Identity blocks, and - for width 8 - block 0 with its 1x1x1 projection shortcut folded
+        into conv c as a second K half (same folding as _conv_with_shortcut).  On by default (VSB_THIN_BLOCK=0 /
+        tune {"thin_block": False} keeps the three launches)."""
         if str(tn.get("thin_block", os.environ.get("VSB_THIN_BLOCK", "1"))) not in ("1", "True"):
             return None
-        a, b, c = blk.a, blk.b, blk.c
+        a, b, c, br = blk.a, blk.b, blk.c, blk.branch1
         d_store = self._store(a.cout)
+        c_out = self._store(c.cout)
         if d_store == 16 and str(tn.get("thin_d16", os.environ.get("VSB_THIN_D16", "1"))) not in ("1", "True"):
             return None
-        if (d_store not in (8, 16) or x.c != 4 * d_store or self._store(c.cout) != x.c or x.c_real != a.cin
-                or x.c_off or x.pitch != x.c or c.cout != a.cin
+        if (d_store not in (8, 16) or c_out != 4 * d_store or x.c_real != a.cin or x.c_off or x.pitch != x.c
                 or tuple(a.kernel[1:]) != (1, 1) or a.kernel[0] not in (1, 3) or tuple(b.kernel) != (1, 3, 3)
                 or tuple(c.kernel) != (1, 1, 1) or any(s != 1 for cs in (a, b, c) for s in cs.stride)
                 or tuple(a.pad) != (a.kernel[0] // 2, 0, 0) or tuple(b.pad) != (0, 1, 1) or tuple(c.pad) != (0, 0, 0)):
             return None
-        if out_pitch is not None and out_pitch != x.c:
+        if br is None:
+            if x.c != c_out or c.cout != a.cin:
+                return None
+        else:
+            if (str(tn.get("thin_proj", os.environ.get("VSB_THIN_PROJ", "1"))) not in ("1", "True")
+                    or d_store != 8 or x.c not in (8, 16) or x.c_real != 8 or br.cin != a.cin or br.cout != c.cout
+                    or tuple(br.kernel) != (1, 1, 1) or any(s != 1 for s in br.stride) or any(br.pad)):
+                return None
+        if out_pitch is not None and out_pitch != c_out:
             return None
-        w = self._memo((blk.prefix, "thin", x.c, d_store), lambda: (
-            self._up(pack_conv_weight(self._tensor(a.key + ".weight"), x.c, d_store, self.tdt)),
-            self._up(pack_conv_weight(self._tensor(b.key + ".weight"), d_store, d_store, self.tdt)),
-            self._up(pack_conv_weight(self._tensor(c.key + ".weight"), d_store, x.c, self.tdt))))
+
+        def make():
+            cin = x.c if br is None else 8   # projection blocks read the 8 real channels of a (possibly 16-wide) pixel
+            wa = pack_conv_weight(self._tensor(a.key + ".weight"), cin, d_store, self.tdt)
+            wb = pack_conv_weight(self._tensor(b.key + ".weight"), d_store, d_store, self.tdt)
+            if br is None:
+                wc = pack_conv_weight(self._tensor(c.key + ".weight"), d_store, c_out, self.tdt)
+                s_, b_ = self._affine(c, c_out)
+            else:
+                # one accumulator for conv c and the shortcut: the two BatchNorm scales become ratios to the
+                # larger one (the common epilogue scale), the biases add
+                s_c, b_c = self._affine(c, c_out)
+                s_1, b_1 = self._affine(br, c_out)
+                s_ = torch.where(s_c.abs() >= s_1.abs(), s_c, s_1)
+                safe = torch.where(s_ == 0, torch.ones_like(s_), s_)
+                r_c = torch.where(s_ == 0, torch.zeros_like(s_), s_c / safe)
+                r_1 = torch.where(s_ == 0, torch.zeros_like(s_), s_1 / safe)
+                w_c = pack_conv_weight(self._tensor(c.key + ".weight"), d_store, c_out, torch.float32).reshape(c_out, d_store)
+                w_1 = pack_conv_weight(self._tensor(br.key + ".weight"), cin, c_out, torch.float32).reshape(c_out, cin)
+                wc = torch.cat([w_c * r_c[:, None], w_1 * r_1[:, None]], dim=1).to(self.tdt)
+                b_ = b_c + b_1
+            return self._up(wa), self._up(wb), self._up(wc), self._up(s_), self._up(b_)
+        w = self._memo((blk.prefix, "thin", x.c, d_store, br is not None), make)
         sa, ba = self._sb(a, d_store)
         sb_, bb = self._sb(b, d_store)
-        sc, bc = self._sb(c, x.c)
         y = self._alloc(x.n, x.t, x.h, x.w, c.cout)
         try:
-            plan = BottleneckPlan(x, y, d_store, a.kernel[0], w[0], w[1], w[2], sa, ba, sb_, bb, sc, bc, algo=1,
+            plan = BottleneckPlan(x, y, d_store, a.kernel[0], w[0], w[1], w[2], sa, ba, sb_, bb, w[3], w[4], algo=1,
+                                  cin=(8 if br is not None else 0),
                                   stages=int(tn.get("thin_slots", 0)), walk_len=int(tn.get("thin_rows", 0)))
         except VsbError:
             if tn.get("thin_block") is True:
@@ -718,8 +749,11 @@ class ClipEngine:
         self._keep.append(plan)
         name = blk.prefix + ".thin_abc"
         self.op_bytes[name] = 2.0 * (x.pixels * x.c + y.pixels * y.c)
-        self.trunk_ops.append((name, plan.run, float(x.pixels) * (a.flops_per_out_pixel + b.flops_per_out_pixel
-                                                                  + c.flops_per_out_pixel)))
+        flops = a.flops_per_out_pixel + b.flops_per_out_pixel + c.flops_per_out_pixel
+        if br is not None:
+            flops += br.flops_per_out_pixel
+            self.fused_shortcuts.append(br.key)
+        self.trunk_ops.append((name, plan.run, float(x.pixels) * flops))
         self.fused_blocks.append(blk.prefix)
         self._free(x)
         return y

@@ -68,7 +68,7 @@ class BottleneckDesc(C.Structure):
         ("sb", C.c_void_p), ("bb", C.c_void_p),
         ("sc", C.c_void_p), ("bc", C.c_void_p),
         ("stages", C.c_int), ("walk_len", C.c_int), ("grid", C.c_int),
-        ("algo", C.c_int),
+        ("algo", C.c_int), ("cin", C.c_int),
     ]
 
 

@@ -266,16 +266,17 @@ class BottleneckPlan:
 
     def __init__(self, x: Act, out: Act, d: int, kt: int, wa: torch.Tensor, wb: torch.Tensor, wc: torch.Tensor,
                  sa: torch.Tensor, ba: torch.Tensor, sb: torch.Tensor, bb: torch.Tensor, sc: torch.Tensor,
-                 bc: torch.Tensor, stages: int = 0, walk_len: int = 0, grid: int = 0, algo: int = 0):
+                 bc: torch.Tensor, stages: int = 0, walk_len: int = 0, grid: int = 0, algo: int = 0, cin: int = 0):
         _require_cuda(x.buf, out.buf, wa, wb, wc, sa, ba, sb, bb, sc, bc)
-        c = x.c
-        if (out.n, out.t, out.h, out.w, out.c) != (x.n, x.t, x.h, x.w, c):
+        c = out.c if cin else x.c   # cin: projection block (algo 1), x has cin channels, wc = [Wc' | W1']
+        if (out.n, out.t, out.h, out.w) != (x.n, x.t, x.h, x.w) or out.c != c or (cin and x.c < cin):
             raise VsbError("fused bottleneck: output extent / width must equal the input's")
         for t in (x.buf, out.buf, wa, wb, wc):
             if t.dtype != torch.bfloat16:
                 raise VsbError("fused bottleneck tensors must be bfloat16")
-        if wa.numel() != d * kt * c or wb.numel() != d * 9 * d or wc.numel() != c * d:
-            raise VsbError(f"fused bottleneck weights must be [{d},{kt},{c}], [{d},9,{d}], [{c},{d}]")
+        ca, kc = (cin, d + cin) if cin else (c, d)
+        if wa.numel() != d * kt * ca or wb.numel() != d * 9 * d or wc.numel() != c * kc:
+            raise VsbError(f"fused bottleneck weights must be [{d},{kt},{ca}], [{d},9,{d}], [{c},{kc}]")
         for t, nn in ((sa, d), (ba, d), (sb, d), (bb, d), (sc, c), (bc, c)):
             if t.dtype != torch.float32 or t.numel() != nn or not t.is_contiguous():
                 raise VsbError("fused bottleneck scale / bias must be contiguous float32 of the stored widths")
@@ -288,6 +289,7 @@ class BottleneckPlan:
         dsc.wa, dsc.wb, dsc.wc = wa.data_ptr(), wb.data_ptr(), wc.data_ptr()
         dsc.sa, dsc.ba, dsc.sb, dsc.bb, dsc.sc, dsc.bc = (t.data_ptr() for t in (sa, ba, sb, bb, sc, bc))
         dsc.stages, dsc.walk_len, dsc.grid = stages, walk_len, grid
+        dsc.cin = cin
         dsc.algo = algo   # 0 = tcgen05 flat-raster kernel, 1 = warp-MMA walk kernel (thin blocks: d = 8 / 16, c = 4 d)
         self.algo = algo
         self._keep = (x.buf, out.buf, wa, wb, wc, sa, ba, sb, bb, sc, bc)
