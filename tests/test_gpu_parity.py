@@ -208,6 +208,19 @@ def test_fused_bottleneck_rejects_what_it_cannot_run():
             GF.run_case(case)
 
 
+def test_thin_bottleneck_rejects_what_it_cannot_run():
+    """vsb_bottleneck_* algo 1 (warp-MMA walk kernel): widths outside d = 8 / 16, c = 4 d and non-dense inputs are
+    refused with a message."""
+    import gpu_check_fused as GF
+    from vidsitu_b200.lib import VsbError
+    for case in (("thin_d32", 1, 4, 14, 14, 128, 32, 3, dict(algo=1), 0, 0),
+                 ("thin_c_not_4d", 1, 4, 14, 14, 64, 8, 3, dict(algo=1), 0, 0),
+                 ("thin_x_pitched", 1, 4, 14, 14, 32, 8, 3, dict(algo=1), 48, 0),
+                 ("thin_proj_d16", 1, 4, 14, 14, 64, 16, 3, dict(algo=1, cin=16), 0, 0)):
+        with pytest.raises(VsbError):
+            GF.run_case(case)
+
+
 def test_memory_bound_ops():
     import gpu_check_ops as G
     res = G.run_mem_checks()

@@ -38,6 +38,11 @@ for name in ("w_sp3_64_64_7_wrap", "w_g_sp3_32_32_J2", "w_stem_fast_J4_tsc_T2", 
 fused = {c[0]: c for c in GF.CASES}
 for name in ("tiny_7x7", "crop64_s4", "walk3_grid3", "pitched"):
     report("fused/" + name, GF.run_case(fused[name]))
+# the warp-MMA walk kernel (algo 1): identity blocks d = 8 / 16, several strips and walks per CTA, one-frame clips, a
+# projection block on 16-wide pixels
+for name in ("thin_tiny_7x7", "thin_odd_13x11_d8", "thin_rows5_grid3_d8", "thin_rows3_grid5", "thin_t1", "thin_pitched_out",
+             "thin_proj_odd_13x11", "thin_proj_x16_odd"):
+    report("thin/" + name, GF.run_case(fused[name]))
 # fused stems (kt = 1 and the temporal-scatter kt = 5 kernel) and a whole forward through a clip program
 from vidsitu_b200 import ops as _ops
 from vidsitu_b200.lib import VSB_BF16 as _BF16

@@ -305,6 +305,31 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
     const int ch = 8 * (e >> 2) + 2 * (e & 3);
     reinterpret_cast<float4*>(smem + p.off_sbc + 512)[e] = make_float4(p.sb[ch], p.bb[ch], p.sb[ch + 1], p.bb[ch + 1]);
   }
+  // d = 16: the conv b weight fragments live in shared memory (36 registers per thread otherwise: spills), entry
+  // ((pr * NTD + nt) * 32 + lane) = the (b0, b1) pair of K-slice pair pr, column tile nt for that lane
+  if constexpr (D == 16) {
+    for (int e = threadIdx.x; e < NP * NTD * 32; e += kThinThreads) {
+      const int ln = e & 31, nt = (e >> 5) % NTD, pr = (e >> 5) / NTD;
+      const int gg = ln >> 2, tt = ln & 3;
+      const int s0 = 2 * pr, s1 = 2 * pr + 1;
+      const __nv_bfloat16* row = p.wb + (size_t)(8 * nt + gg) * 9 * D;
+      uint2 v;
+      v.x = *reinterpret_cast<const uint32_t*>(row + (s0 / NQ) * D + 8 * (s0 % NQ) + 2 * tt);
+      v.y = s1 < NSL ? *reinterpret_cast<const uint32_t*>(row + (s1 / NQ) * D + 8 * (s1 % NQ) + 2 * tt) : 0u;
+      reinterpret_cast<uint2*>(smem + p.off_sbc + 1024)[e] = v;
+    }
+    // ... and so do conv c's: entry ((q * 4 + i) * 32 + lane), K = 16 in one step
+    for (int e = threadIdx.x; e < NQ * 4 * 32; e += kThinThreads) {
+      const int ln = e & 31, i = (e >> 5) & 3, q = e >> 7;
+      const int gg = ln >> 2, tt = ln & 3;
+      const int co = 8 * (4 * q + (gg >> 1)) + 2 * i + (gg & 1);
+      const __nv_bfloat16* row = p.wc + (size_t)co * D + 2 * tt;
+      uint2 v;
+      v.x = *reinterpret_cast<const uint32_t*>(row);
+      v.y = *reinterpret_cast<const uint32_t*>(row + 8);
+      reinterpret_cast<uint2*>(smem + p.off_sbc + 1024 + 4608)[e] = v;
+    }
+  }
   __syncthreads();
 
   ThinWalk wk;
@@ -475,6 +500,8 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
     const int bw = warp - kAWarps;
     // conv b: K slices s = tap * NQ + q of 8 channels, two per MMA: b0 = Wb[8 nt + g][tap][8 q + 2 t, + 1]
     uint2 wb_f[NP][NTD];
+    const uint32_t wb_s = sbc_s + 1024 + (uint32_t)lane * 8;
+    if constexpr (D == 8)
 #pragma unroll
     for (int pr = 0; pr < NP; ++pr)
 #pragma unroll
@@ -486,6 +513,7 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
       }
     // conv c: column tile (q, i) holds the output channels 8 (4 q + n / 2) + 2 i + n % 2 in its column n
     uint2 wc_f[NQ][4][KSC];
+    if constexpr (D == 8)
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
 #pragma unroll
@@ -554,8 +582,14 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
             }
 #pragma unroll
             for (int nt = 0; nt < NTD; ++nt) {
-              if (pr == 0) mma16816_z(accb[nt], a0, a1, a2, a3, wb_f[pr][nt].x, wb_f[pr][nt].y);
-              else mma16816(accb[nt], a0, a1, a2, a3, wb_f[pr][nt].x, wb_f[pr][nt].y);
+              uint2 wv;
+              if constexpr (D == 8) {
+                wv = wb_f[pr][nt];
+              } else {
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(wv.x), "=r"(wv.y) : "r"(wb_s + (uint32_t)(pr * NTD + nt) * 256));
+              }
+              if (pr == 0) mma16816_z(accb[nt], a0, a1, a2, a3, wv.x, wv.y);
+              else mma16816(accb[nt], a0, a1, a2, a3, wv.x, wv.y);
             }
           }
           // BN + ReLU -> bf16: the accumulator fragment of b is the A fragment of c
@@ -591,15 +625,10 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
               if constexpr (PROJ) {
                 mma16816_z(accc, pb[0][0], pb[0][1], xg, xh, wc_f[q][i][0].x, wc_f[q][i][0].y);
               } else if (D >= 16) {
-#pragma unroll
-                for (int ks = 0; ks < KSC; ++ks) {
-                  if (ks == 0)
-                    mma16816_z(accc, pb[(2 * ks) % NTD][0], pb[(2 * ks) % NTD][1], pb[(2 * ks + 1) % NTD][0],
-                               pb[(2 * ks + 1) % NTD][1], wc_f[q][i][ks].x, wc_f[q][i][ks].y);
-                  else
-                    mma16816(accc, pb[(2 * ks) % NTD][0], pb[(2 * ks) % NTD][1], pb[(2 * ks + 1) % NTD][0],
-                             pb[(2 * ks + 1) % NTD][1], wc_f[q][i][ks].x, wc_f[q][i][ks].y);
-                }
+                static_assert(D <= 16, "conv c fragments in shared memory: one K step");
+                uint2 wv;
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(wv.x), "=r"(wv.y) : "r"(wb_s + 4608 + (uint32_t)(q * 4 + i) * 256));
+                mma16816_z(accc, pb[0][0], pb[0][1], pb[1 % NTD][0], pb[1 % NTD][1], wv.x, wv.y);
               } else {
                 mma1688_z(accc, pb[0][0], pb[0][1], wc_f[q][i][0].x);
               }
@@ -692,7 +721,7 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
     const long long slot = (long long)(r + 2) * p.row_bytes;
     const long long abuf = (long long)(r + 2) * (d->w + 2) * a_pitch;
     const long long abuf_al = (abuf + 127) / 128 * 128;
-    long long s = (budget - 2 * abuf_al - 2048) / slot;
+    long long s = (budget - 2 * abuf_al - 10240) / slot;
     if (s > 6) s = 6;
     if (d->stages > 0 && s > d->stages) s = d->stages;
     if (s < min_slots) continue;
@@ -725,7 +754,7 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   p.off_abuf = (uint32_t)p.S * p.slot_bytes;
   p.off_abuf = (p.off_abuf + 127u) & ~127u;
   p.off_sbc = p.off_abuf + 2 * p.a_buf_bytes;
-  p.off_bar = p.off_sbc + 1024;  // conv c table at +0 (<= 512 B), conv b table at +512
+  p.off_bar = p.off_sbc + 1024 + 4608 + 2048;  // conv c table at +0 (<= 512 B), conv b table at +512, d = 16: conv b / conv c weight fragments at +1024 (4608 B) / +5632 (2048 B)
   const size_t smem_bytes = (size_t)p.off_bar + (2 * kMaxSlots + 4) * 8 + 128;
   VSB_CHECK_ARG(smem_bytes <= 227 * 1024, "warp-MMA bottleneck: shared memory plan exceeds 227 KiB");
   p.total_steps = (long long)d->n * p.row_tiles * d->t;
