@@ -364,7 +364,7 @@ def main():
                 tsrc = cand
                 break
         roofline = {"bound": "tensor", "kernel": "all conv launches of a step (conv_igemm_kernel, conv_igemm2_kernel, "
-                    "conv_win_kernel, bottleneck_fused_kernel)",
+                    "conv_win_kernel, stem_pool_kernel, bottleneck_thin_kernel)",
                     "achieved": round(achieved, 2), "peak": peak_sus, "unit": "TFLOP/s",
                     "frac": round(achieved / peak_sus, 4), "frac_sustained": round(achieved / peak_sus, 4),
                     "frac_burst": round(achieved / peak_burst, 4), "peak_burst": peak_burst,
@@ -410,7 +410,7 @@ def main():
                        f"synthetic event clips ({t_frames}x224x224) per GPU", "clips_per_gpu_per_step": B, "model": args.model,
                        "weights": "random-init (seed 0) + seeded BatchNorm statistics",
                        "l2": "inputs larger than L2: 2 alternating 308 MB uint8 frame batches per GPU, "
-                             "activations >> 126 MB", "cuda_graph": True, "replay": ("clip program: one vsb_program_run per step (C ABI v7, graph captured inside the library)" if eng._use_program() else "torch CUDA graph of the Python launch loop"), "pack_overlap": nslots > 1,
+                             "activations >> 126 MB", "cuda_graph": True, "replay": ("clip program: one vsb_program_run per step (C ABI v8, graph captured inside the library)" if eng._use_program() else "torch CUDA graph of the Python launch loop"), "pack_overlap": nslots > 1,
                        "parallelism": f"clip-sharded x{world}, features all-gathered each step" if world > 1 else "single GPU",
                        "host_placement": {"rank0_cpus": (f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else None),
                                           "numa_nodes": nodes}},

@@ -30,6 +30,10 @@ FULL_METRICS = [
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("sm__cycles_active.avg", "SM active cycles"),
     ("smsp__cycles_active.avg", "SMSP active cycles"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("smsp__inst_executed.sum", "warp instructions"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+    ("sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "HMMA (mma.sync) pipe %"),
 ]
 
 
