@@ -24,6 +24,14 @@ def report(name, info):
     print(("ok   " if good else "FAIL ") + name, {k: v for k, v in info.items() if k in ("max_abs_err", "n_bad", "algo")}, flush=True)
 
 
+if "--thin-only" in sys.argv:   # quick pass over the warp-MMA bottleneck kernel alone
+    fused = {c[0]: c for c in GF.CASES}
+    for name in ("thin_tiny_7x7", "thin_odd_13x11_d8", "thin_rows5_grid3_d8", "thin_rows3_grid5", "thin_t1",
+                 "thin_pitched_out", "thin_proj_odd_13x11", "thin_proj_x16_odd"):
+        report("thin/" + name, GF.run_case(fused[name]))
+    torch.cuda.synchronize()
+    print("ALL OK" if ok else "FAILURES")
+    sys.exit(0 if ok else 1)
 conv = {c[0]: c for c in G.CONV_CASES}
 for name in ("pw_64_64_relu_res", "sp3_64_64", "tm3_16_16", "lat5_s4_16_16", "concat_slice"):
     report("conv/" + name, G.run_conv_case(conv[name], 0))

@@ -15,16 +15,20 @@
 // Schedule.  A CTA owns a strip of R output rows of one clip (full width) and WALKS it through time.  Per frame the
 // strip plus one halo row above and below is ONE contiguous range of the NTHWC tensor, fetched by a single
 // cp.async.bulk (no tensor map) into a ring of S frame slots; every frame is fetched once and used by the three
-// temporal taps of `a` and by the residual.  Warp roles (17 warps):
-//   a-warps  0-7  : a[t] = relu(BN(sum_taps x[t + tap - 1] . Wa[tap])) for the strip + halo rows, 16-pixel MMA tiles,
+// temporal taps of `a` and by the residual.  Warp roles (16 warps of 128 registers; the a : bc split is a plan parameter):
+//   a-warps  (7)  : a[t] = relu(BN(sum_taps x[t + tap - 1] . Wa[tap])) for the strip + halo rows, 16-pixel MMA tiles,
 //                   Wa fragments resident in registers; result -> bf16 -> one of two a-tile buffers in shared memory
 //                   laid out (R + 2) x (W + 2) pixels with a zero border (= the padding of the 3x3 conv)
-//   bc-warps 8-15 : b = relu(BN(sum_taps a[.. + dy, .. + dx] . Wb[tap])) from the a-tile buffer (every tap is a shifted
+//   bc-warps (8)  : b = relu(BN(sum_taps a[.. + dy, .. + dx] . Wb[tap])) from the a-tile buffer (every tap is a shifted
 //                   shared-memory read), the b accumulator fragment IS the A fragment of c (no exchange), c 32 channels
 //                   at a time, + BN + residual (x[t] from the ring) + ReLU -> 16-byte global stores
-//   warp 16       : producer (one lane): waits for a free slot, arms the slot's mbarrier, issues the bulk copy
-// The two a-tile buffers let the a-warps run one frame ahead of the bc-warps.  All handshakes are mbarriers with
-// bounded waits (a protocol bug traps, it never hangs the GPU).
+//   fetch warp    : one lane waits for a free slot, arms the slot's mbarrier and issues the bulk copy (merged into a
+//                   compute warp it stalled that warp's tiles: 0.31 vs 0.22 ms per res2 block)
+// The two a-tile buffers let the a-warps run one frame ahead of the bc-warps.  All handshakes are mbarriers on which
+// every lane arrives for its own accesses, with bounded back-off waits (a protocol bug traps, it never hangs the GPU).
+// Measured on B200 (batch 64): res2 identity block 0.198 ms (three launches: 0.385), res2 block 0 with its projection
+// 0.152 ms (0.30), res3 identity block 0.182 ms (0.208); bound by instruction issue and shared-memory wavefronts (ncu:
+// profiles/r02_ncu_full_thin_bottleneck.txt), HBM time of the res2 block incl. the 1.25x halo re-reads: 0.142 ms.
 //
 // Channel permutation.  The K order of `a` and the N order of `c` are free as long as weights and activations agree,
 // so thread (g, t) of a warp owns, for pixel rows g and g + 8, the 16-byte pieces [8 (4 q + t), + 8) of the pixel's
@@ -140,22 +144,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void* src, uint32
 }
 __device__ __forceinline__ uint32_t sel(bool c, uint32_t a, uint32_t b) { return c ? a : b; }
 
-// mbarrier wait that lets the hardware park the thread (suspend-time hint) instead of polling: a spinning warp takes
-// issue slots from the working warps of its scheduler.  Bounded: a protocol bug traps.
+// mbarrier wait with back-off: a warp that spins on try_wait takes issue slots from the working warps of its
+// scheduler, so a failed attempt sleeps before the next one.  Bounded: a protocol bug traps, it never hangs the GPU.
 __device__ __forceinline__ void t_mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(200000u)
-        : "memory");
-    if (ok) return;
-    if (++spins > (1u << 18)) __trap();
+    __nanosleep(40);
+    if (mbar_try_wait(bar, parity)) return;
+    if (++spins > (1u << 24)) __trap();
   }
 }
 
@@ -277,16 +274,22 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const bool odd = (g & 1) != 0;
+#ifndef VSB_THIN_SWAP_PIECES
+#define VSB_THIN_SWAP_PIECES 0
+#endif
+  // conflict-free pair loads of conv a's x pieces (see the file comment) cost 8 selects per pair and pixel row; with
+  // plain loads the two pixel rows of a quarter-warp collide (2 wavefronts more per load) but the kernel is bound by
+  // instruction issue, not by shared-memory wavefronts: measured faster without the swap (VSB_THIN_SWAP_PIECES)
+  const bool odd = VSB_THIN_SWAP_PIECES ? (g & 1) != 0 : false;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kComputeWarps);
+      mbar_init(&empty[s], kComputeWarps * 32);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&a_full[b], p.a_warps);
-      mbar_init(&a_empty[b], kComputeWarps - p.a_warps);
+      mbar_init(&a_full[b], p.a_warps * 32);
+      mbar_init(&a_empty[b], (kComputeWarps - p.a_warps) * 32);
     }
     fence_mbar_init();
   }
@@ -482,8 +485,9 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
             }
           }
           }
-        __syncwarp();
-        if (lane == 0) {
+        // every lane arrives for its own shared-memory accesses (release / acquire per thread: nothing rests on
+        // cumulativity through a warp barrier, and the race checker can follow it)
+        {
           mbar_arrive(&a_full[b]);
           // frames conv a no longer needs
           const int f_done = t - HT;
@@ -646,8 +650,7 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
             if (valid1) t_stg128(out1 + 64 * q, oh[0], oh[1], oh[2], oh[3]);
           }
         }
-        __syncwarp();
-        if (lane == 0) {
+        {
           mbar_arrive(&a_empty[b]);
           mbar_arrive(&empty[slot]);
           // halo frames of the walk that no bc step visits

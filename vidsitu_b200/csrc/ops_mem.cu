@@ -379,21 +379,21 @@ template <int RY>
 __global__ void __launch_bounds__(256)
 maxpool_133_stream_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolParams p, int strips,
                           long long total) {
+  // threads cover the REAL channel vectors only; the thread of the last real vector also writes the zero vectors of
+  // the channel padding (the Fast stem: 8 real + 8 padding channels - a thread per padding vector left every second
+  // lane of a warp without loads)
   const int cv_in = p.in_pitch / 8, cv_out = p.c_out / 8, cv_real = (p.c + 7) / 8, op = p.out_pitch / 8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % cv_out);
-    long long r = idx / cv_out;
+    const int cv = (int)(idx % cv_real);
+    long long r = idx / cv_real;
     const int xo = (int)(r % p.wo); r /= p.wo;
     const int strip = (int)(r % strips);
     const long long frame = r / strips;
     const int y0 = strip * RY, y1 = min(y0 + RY, p.ho);
     uint4* dst = out + ((frame * p.ho + y0) * p.wo + xo) * op + cv;
     const size_t dstep = (size_t)p.wo * op;
-    if (cv >= cv_real) {  // channel padding
-      for (int y = y0; y < y1; ++y, dst += dstep) *dst = make_uint4(0, 0, 0, 0);
-      continue;
-    }
+    const int npad = cv == cv_real - 1 ? cv_out - cv_real : 0;
     const int xc = 2 * xo, xl = xc > 0 ? xc - 1 : xc, xr = xc + 1 < p.w ? xc + 1 : xc;
     const uint4* src = in + frame * p.h * p.w * cv_in + cv;
     const size_t rstep = (size_t)p.w * cv_in;
@@ -420,6 +420,7 @@ maxpool_133_stream_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
       carry = hb;
       best.x &= keep.x; best.y &= keep.y; best.z &= keep.z; best.w &= keep.w;
       *dst = best;
+      for (int k = 1; k <= npad; ++k) dst[k] = make_uint4(0, 0, 0, 0);
     }
   }
 }
@@ -688,7 +689,7 @@ extern "C" int vsb_maxpool3d(const void* in, int n, int t, int h, int w, int c, 
     if (!staged) {
       constexpr int RY = 8;
       const int strips = (p.ho + RY - 1) / RY;
-      const long long threads = (long long)n * p.to * strips * p.wo * (c_out / 8);
+      const long long threads = (long long)n * p.to * strips * p.wo * ((c + 7) / 8);
       const long long blocks = (threads + 255) / 256;
       VSB_CHECK_ARG(blocks < (1ll << 31), "too many pool blocks");
       maxpool_133_stream_kernel<RY><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const uint4*>(in),
