@@ -59,6 +59,7 @@ CASES = [
     ("thin_t2", 2, 2, 14, 14, 64, 16, 3, dict(algo=1), 0, 0),
     ("thin_rows3_grid5", 2, 8, 28, 28, 64, 16, 3, dict(algo=1, walk_len=3, grid=5), 0, 0),
     ("thin_rows5_grid3_d8", 3, 6, 28, 28, 32, 8, 3, dict(algo=1, walk_len=5, grid=3), 0, 0),
+    ("thin_grid7_d8", 3, 6, 28, 28, 32, 8, 3, dict(algo=1, walk_len=7, grid=7), 0, 0),
     ("thin_slots4", 2, 8, 28, 28, 64, 16, 3, dict(algo=1, stages=4), 0, 0),
     ("thin_pitched_out", 2, 4, 14, 14, 64, 16, 3, dict(algo=1), 0, 80),
     ("thin_crop64_s2", 2, 32, 16, 16, 32, 8, 3, dict(algo=1), 0, 0),

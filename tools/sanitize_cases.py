@@ -24,10 +24,13 @@ def report(name, info):
     print(("ok   " if good else "FAIL ") + name, {k: v for k, v in info.items() if k in ("max_abs_err", "n_bad", "algo")}, flush=True)
 
 
-if "--thin-only" in sys.argv:   # quick pass over the warp-MMA bottleneck kernel alone
+if "--thin-only" in sys.argv:   # quick pass over the warp-MMA bottleneck kernel alone (--case NAME: one case)
     fused = {c[0]: c for c in GF.CASES}
-    for name in ("thin_tiny_7x7", "thin_odd_13x11_d8", "thin_rows5_grid3_d8", "thin_rows3_grid5", "thin_t1",
-                 "thin_pitched_out", "thin_proj_odd_13x11", "thin_proj_x16_odd"):
+    names = ("thin_tiny_7x7", "thin_odd_13x11_d8", "thin_rows5_grid3_d8", "thin_rows3_grid5", "thin_t1",
+             "thin_pitched_out", "thin_proj_odd_13x11", "thin_proj_x16_odd")
+    if "--case" in sys.argv:
+        names = (sys.argv[sys.argv.index("--case") + 1],)
+    for name in names:
         report("thin/" + name, GF.run_case(fused[name]))
     torch.cuda.synchronize()
     print("ALL OK" if ok else "FAILURES")

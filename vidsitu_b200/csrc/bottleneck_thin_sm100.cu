@@ -293,6 +293,7 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
     }
     fence_mbar_init();
   }
+  __syncthreads();
   // zero both a-tile buffers once: the border columns are never written again
   for (uint32_t i = threadIdx.x * 16; i < 2 * p.a_buf_bytes; i += kThinThreads * 16)
     *reinterpret_cast<uint4*>(smem + p.off_abuf + i) = make_uint4(0, 0, 0, 0);
@@ -710,6 +711,7 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   p.magic_w = (1u << 24) / (uint32_t)d->w + 1;
   int a_warps = d->d == 8 ? default_a_warps(8) : default_a_warps(16);  // experiments: VSB_THIN_AWARPS
   if (getenv("VSB_THIN_AWARPS") && d->d == 8) a_warps = atoi(getenv("VSB_THIN_AWARPS"));
+  if (getenv("VSB_THIN_AWARPS16") && d->d == 16) a_warps = atoi(getenv("VSB_THIN_AWARPS16"));
   if (a_warps < 4 || a_warps > compute_warps(d->d) - 4) a_warps = default_a_warps(d->d);
   p.a_warps = a_warps;
   const int ht = d->kt / 2;
