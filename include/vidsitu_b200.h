@@ -227,7 +227,8 @@ int vsb_bottleneck_plan_create(const vsb_bottleneck_desc* desc, vsb_bottleneck_p
 int vsb_bottleneck_run(const vsb_bottleneck_plan* plan, void* stream);
 void vsb_bottleneck_plan_destroy(vsb_bottleneck_plan* plan);
 /* out8 = {slots per flat row, flat rows per frame, x ring slots * 100 + chunks per slot, tiles per CTA, grid, dynamic shared memory
- * bytes, tiles per clip, TMEM columns} */
+ * bytes, tiles per clip, TMEM columns}; algo 1: {rows per strip, strips per frame, ring slots, frame steps per CTA, grid, dynamic
+ * shared memory bytes, conv-a tiles * 1000 + conv-b/c tiles per frame step, 0} */
 int vsb_bottleneck_plan_info(const vsb_bottleneck_plan* plan, long long* out8);
 
 /* ------------------------------------------------- fused [kt,7,7] stem: conv + BN + ReLU + max-pool (ABI v7)

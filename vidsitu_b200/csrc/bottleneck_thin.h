@@ -4,7 +4,6 @@
 
 namespace vsb {
 struct ThinPlan;
-bool thin_eligible(const vsb_bottleneck_desc* d);
 int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan);
 int thin_run(const ThinPlan* plan, void* stream);
 void thin_plan_destroy(ThinPlan* plan);

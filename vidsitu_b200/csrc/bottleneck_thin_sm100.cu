@@ -34,8 +34,10 @@
 // so thread (g, t) of a warp owns, for pixel rows g and g + 8, the 16-byte pieces [8 (4 q + t), + 8) of the pixel's
 // channels (q = 0 .. c / 32 - 1): its x fragments are 128-bit shared loads, its residual is already in the layout of
 // the c accumulator, and its output is one 16-byte store per 32 channels; the weight fragments are gathered with the
-// same permutation once per CTA.  Pixel rows of 128 bytes and more would make two pixel rows of a quarter-warp hit
-// the same banks: lanes with odd g fetch the pieces of q and q ^ 1 in swapped order and swap them back in registers.
+// same permutation once per CTA.  Pixel rows of 128 bytes and more make two pixel rows of a quarter-warp hit the
+// same banks; the conflict-free variant (lanes with odd g fetch the pieces of q and q ^ 1 in swapped order and swap them
+// back in registers, VSB_THIN_SWAP_PIECES) costs 8 selects per pair and was measured slower: issue slots, not
+// shared-memory wavefronts, are what this kernel runs out of.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -679,12 +681,6 @@ static cudaError_t thin_set_attr() {
   return cudaFuncSetAttribute(bottleneck_thin_kernel<D, KT, PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-bool thin_eligible(const vsb_bottleneck_desc* d) {
-  const int cin = d->cin > 0 ? d->cin : d->c;
-  return (d->d == 8 || d->d == 16) && d->c == 4 * d->d && (d->x_pitch == cin || (cin == 8 && d->x_pitch == 16)) &&
-         (cin == d->c || (cin == d->d && d->d == 8));
-}
-
 int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   *out_plan = nullptr;
   VSB_CHECK_ARG(d->d == 8 || d->d == 16, "warp-MMA bottleneck: bottleneck width (stored) must be 8 or 16");
@@ -714,7 +710,6 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   if (getenv("VSB_THIN_AWARPS16") && d->d == 16) a_warps = atoi(getenv("VSB_THIN_AWARPS16"));
   if (a_warps < 4 || a_warps > compute_warps(d->d) - 4) a_warps = default_a_warps(d->d);
   p.a_warps = a_warps;
-  const int ht = d->kt / 2;
   const int min_slots = d->kt + 1;
   // rows per strip: the strip (+ 2 halo rows) is one ring slot; fewest fetched rows per frame among the strips that
   // leave room for min_slots + 1 slots (caller's override: walk_len)
@@ -745,7 +740,6 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
               d->c, min_slots);
     return VSB_ERR_INVALID;
   }
-  (void)ht;
   p.R = best_r;
   p.S = best_s;
   p.row_tiles = ceil_div(d->h, p.R);
