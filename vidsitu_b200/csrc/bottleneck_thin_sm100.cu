@@ -26,9 +26,9 @@
 //                   compute warp it stalled that warp's tiles: 0.31 vs 0.22 ms per res2 block)
 // The two a-tile buffers let the a-warps run one frame ahead of the bc-warps.  All handshakes are mbarriers on which
 // every lane arrives for its own accesses, with bounded back-off waits (a protocol bug traps, it never hangs the GPU).
-// Measured on B200 (batch 64): res2 identity block 0.198 ms (three launches: 0.385), res2 block 0 with its projection
-// 0.152 ms (0.30), res3 identity block 0.182 ms (0.208); bound by instruction issue and shared-memory wavefronts (ncu:
-// profiles/r02_ncu_full_thin_bottleneck.txt), HBM time of the res2 block incl. the 1.25x halo re-reads: 0.142 ms.
+// Measured on B200 (batch 64): res2 identity block 0.189 ms (three launches: 0.385), res2 block 0 with its projection
+// 0.144 ms (0.30), res3 identity block 0.181 ms (0.208); bound by instruction issue and shared-memory wavefronts (ncu:
+// profiles/r02c_ncu_full_thin_bottleneck.txt), HBM time of the res2 block incl. the 1.25x halo re-reads: 0.142 ms.
 //
 // Channel permutation.  The K order of `a` and the N order of `c` are free as long as weights and activations agree,
 // so thread (g, t) of a warp owns, for pixel rows g and g + 8, the 16-byte pieces [8 (4 q + t), + 8) of the pixel's
@@ -36,8 +36,7 @@
 // the c accumulator, and its output is one 16-byte store per 32 channels; the weight fragments are gathered with the
 // same permutation once per CTA.  Pixel rows of 128 bytes and more make two pixel rows of a quarter-warp hit the
 // same banks; the conflict-free variant (lanes with odd g fetch the pieces of q and q ^ 1 in swapped order and swap them
-// back in registers, VSB_THIN_SWAP_PIECES) costs 8 selects per pair and was measured slower: issue slots, not
-// shared-memory wavefronts, are what this kernel runs out of.
+// back in registers, VSB_THIN_SWAP_PIECES) costs 8 selects per pair and pixel row and was measured no faster (res3 block 0.182 vs 0.181 ms).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -280,8 +279,8 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
 #define VSB_THIN_SWAP_PIECES 0
 #endif
   // conflict-free pair loads of conv a's x pieces (see the file comment) cost 8 selects per pair and pixel row; with
-  // plain loads the two pixel rows of a quarter-warp collide (2 wavefronts more per load) but the kernel is bound by
-  // instruction issue, not by shared-memory wavefronts: measured faster without the swap (VSB_THIN_SWAP_PIECES)
+  // plain loads the two pixel rows of a quarter-warp collide (2 wavefronts more per load): measured no faster with the
+  // swap (VSB_THIN_SWAP_PIECES=1), so the simpler loads are the default
   const bool odd = VSB_THIN_SWAP_PIECES ? (g & 1) != 0 : false;
 
   if (threadIdx.x == 0) {
