@@ -56,6 +56,12 @@ int vsb_debug_tma_rate(const void* x, int n, int t, int h, int w, int c, int mod
 struct vsb_bottleneck_plan;
 int vsb_debug_bottleneck_stats(const struct vsb_bottleneck_plan* plan, long long* out32);
 
+/* Host only (no GPU needed): the (A_c, B_c) pairs vsb_pack_frames uses in bf16 mode, i.e. coefficients with
+ * bf16(fma(x, A_c, B_c)) == bf16(((x / 255) - mean_c) / std_c) for every byte value x (utils/video_utils.py:147-164
+ * evaluated in fp32, then rounded once).  Returns 1 and fills a3 / b3, or 0 when no such pair exists within 3 ulps of the
+ * rounded exact coefficients (vsb_pack_frames then runs the table kernel). */
+int vsb_debug_pack_fma_coeffs(const float* mean3, const float* std3, float* a3, float* b3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -371,3 +371,24 @@ def test_jpeg_header_parser_needs_no_gpu():
         jpeg_info(buf.getvalue())
     with pytest.raises(VsbError, match="not a JPEG"):
         jpeg_info(b"GIF89a" + bytes(32))
+
+
+@pytest.mark.parametrize("mean,std", [([0.45, 0.45, 0.45], [0.225, 0.225, 0.225]),
+                                      ([0.485, 0.456, 0.406], [0.229, 0.224, 0.225]),
+                                      ([0.5, 0.43216, 0.1], [0.5, 0.22803, 1.0])])
+def test_pack_fma_coefficients_reproduce_the_three_fp32_operations(mean, std):
+    """The bf16 pack kernel computes bf16(fma(x, A, B)) instead of the reference's x / 255, - mean, / std
+    (utils/video_utils.py:147-164) followed by the rounding to bf16: the host search (vsb_debug_pack_fma_coeffs, no GPU)
+    must return coefficients that give the SAME bf16 value for every byte value and channel."""
+    lib = L.load()
+    f3 = ctypes.c_float * 3
+    lib.vsb_debug_pack_fma_coeffs.restype = ctypes.c_int
+    lib.vsb_debug_pack_fma_coeffs.argtypes = [ctypes.POINTER(ctypes.c_float)] * 4
+    a, b = f3(), f3()
+    assert lib.vsb_debug_pack_fma_coeffs(f3(*mean), f3(*std), a, b) == 1
+    x = torch.arange(256, dtype=torch.float32)
+    for c in range(3):
+        want = (((x / 255.0) - torch.tensor(mean[c], dtype=torch.float32)) / torch.tensor(std[c], dtype=torch.float32))
+        # fma in float64 is exact for an 8-bit x times a 24-bit coefficient; one rounding to fp32, one to bf16
+        got = (x.double() * float(a[c]) + float(b[c])).float()
+        assert torch.equal(got.to(torch.bfloat16), want.to(torch.bfloat16)), c

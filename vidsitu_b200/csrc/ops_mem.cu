@@ -9,6 +9,7 @@
 
 #include <mutex>
 
+#include "../../include/vidsitu_b200_debug.h"
 #include "common.h"
 
 namespace vsb {
@@ -647,6 +648,17 @@ static bool pack_fma_coeffs(const float* mean3, const float* std3, PackFma* out)
   val = *out;
   have = all ? 1 : 2;
   return all;
+}
+
+extern "C" int vsb_debug_pack_fma_coeffs(const float* mean3, const float* std3, float* a3, float* b3) {
+  if (!mean3 || !std3 || !a3 || !b3) return 0;
+  PackFma k;
+  if (!pack_fma_coeffs(mean3, std3, &k)) return 0;
+  for (int c = 0; c < 3; ++c) {
+    a3[c] = k.a[c];
+    b3[c] = k.b[c];
+  }
+  return 1;
 }
 
 extern "C" int vsb_pack_frames(const uint8_t* frames, int n, int t_in, int h, int w, const int* idx, int t_out,
