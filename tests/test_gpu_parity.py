@@ -208,6 +208,42 @@ def test_fused_bottleneck_rejects_what_it_cannot_run():
             GF.run_case(case)
 
 
+def test_thin_bottleneck_random_shapes():
+    """vsb_bottleneck_* algo 1 on 40 seeded random problems (frame sizes 3 .. 40, 1 .. 9 frames, d = 8 / 16, kt = 1 / 3,
+    projection blocks on 8- and 16-wide pixels, pitched outputs, forced strip heights and grids so that CTAs cross
+    strips, clips and walks) against torch conv3d x 3: no shape-dependent indexing slip survives this."""
+    import random
+    import gpu_check_fused as GF
+    from vidsitu_b200.lib import VsbError
+    rnd = random.Random(20260)
+    ran = 0
+    for i in range(40):
+        d = rnd.choice((8, 16))
+        proj = d == 8 and rnd.random() < 0.35
+        h, w = rnd.randint(3, 40), rnd.randint(3, 40)
+        tune = dict(algo=1)
+        if proj:
+            tune["cin"] = 8
+        if rnd.random() < 0.5:
+            tune["walk_len"] = rnd.randint(1, h)
+        if rnd.random() < 0.5:
+            tune["grid"] = rnd.randint(1, 9)
+        if rnd.random() < 0.3:
+            tune["stages"] = rnd.choice((4, 5))
+        c = 4 * d
+        xp = 16 if (proj and rnd.random() < 0.5) else 0
+        op = c + 8 * rnd.randint(1, 3) if rnd.random() < 0.3 else 0
+        case = (f"thin_rand_{i}", rnd.randint(1, 3), rnd.randint(1, 9), h, w, c, d, rnd.choice((1, 3)), tune, xp, op)
+        try:
+            info = GF.run_case(case)
+        except VsbError as e:   # a forced strip height that does not fit the tile slots / shared memory
+            assert "walk_len" in tune and ("strip" in str(e) or "fits" in str(e)), (case, str(e))
+            continue
+        assert info["ok"], (case, info)
+        ran += 1
+    assert ran >= 30, ran
+
+
 def test_thin_bottleneck_rejects_what_it_cannot_run():
     """vsb_bottleneck_* algo 1 (warp-MMA walk kernel): widths outside d = 8 / 16, c = 4 d and non-dense inputs are
     refused with a message."""
