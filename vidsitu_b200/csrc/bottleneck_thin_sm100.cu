@@ -60,6 +60,7 @@ __host__ __device__ constexpr int default_a_warps(int) { return 7; }
 __host__ __device__ constexpr int max_a_tiles(int d) { return d == 8 ? 6 : 3; }
 __host__ __device__ constexpr int max_bc_tiles(int d) { return d == 8 ? 4 : 2; }
 constexpr int kMaxSlots = 8;
+constexpr uint32_t kRingOffset = 256;  // the mbarriers (2 * kMaxSlots + 4) sit in front of the ring
 }  // namespace
 
 struct ThinParams {
@@ -265,9 +266,11 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
 
   extern __shared__ uint8_t thin_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(thin_smem_raw) + 127) & ~uintptr_t(127));
-  const uint32_t ring_s = smem_u32(smem);
-  const uint32_t abuf_s = ring_s + p.off_abuf;
-  const uint32_t sbc_s = ring_s + p.off_sbc;
+  // shared-memory layout: [mbarriers | frame ring | two a-tile buffers | tables]
+  const uint32_t base_s = smem_u32(smem);
+  const uint32_t ring_s = base_s + kRingOffset;
+  const uint32_t abuf_s = base_s + p.off_abuf;
+  const uint32_t sbc_s = base_s + p.off_sbc;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* empty = full + kMaxSlots;
   uint64_t* a_full = empty + kMaxSlots;
@@ -749,11 +752,12 @@ int thin_plan_create(const vsb_bottleneck_desc* d, ThinPlan** out_plan) {
   p.bc_tiles = ceil_div(p.bc_px, 16);
   p.a_buf_bytes = (uint32_t)(((long long)(p.R + 2) * (d->w + 2) * a_pitch + 127) / 128 * 128);
   // a tile's tail rows may read up to 16 pixels past the last slot: keep the a-tile buffers behind the ring
-  p.off_abuf = (uint32_t)p.S * p.slot_bytes;
+  p.off_bar = 0;
+  p.off_abuf = kRingOffset + (uint32_t)p.S * p.slot_bytes;
   p.off_abuf = (p.off_abuf + 127u) & ~127u;
   p.off_sbc = p.off_abuf + 2 * p.a_buf_bytes;
-  p.off_bar = p.off_sbc + 1024 + 4608 + 2048;  // conv c table at +0 (<= 512 B), conv b table at +512, d = 16: conv b / conv c weight fragments at +1024 (4608 B) / +5632 (2048 B)
-  const size_t smem_bytes = (size_t)p.off_bar + (2 * kMaxSlots + 4) * 8 + 128;
+  const uint32_t off_end = p.off_sbc + 1024 + 4608 + 2048;  // conv c table at +0 (<= 512 B), conv b table at +512, d = 16: conv b / conv c weight fragments at +1024 (4608 B) / +5632 (2048 B)
+  const size_t smem_bytes = (size_t)off_end + 128;
   VSB_CHECK_ARG(smem_bytes <= 227 * 1024, "warp-MMA bottleneck: shared memory plan exceeds 227 KiB");
   p.total_steps = (long long)d->n * p.row_tiles * d->t;
   int sms = 148;
