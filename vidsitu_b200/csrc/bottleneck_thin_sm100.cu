@@ -60,7 +60,8 @@ __host__ __device__ constexpr int default_a_warps(int) { return 7; }
 __host__ __device__ constexpr int max_a_tiles(int d) { return d == 8 ? 6 : 3; }
 __host__ __device__ constexpr int max_bc_tiles(int d) { return d == 8 ? 4 : 2; }
 constexpr int kMaxSlots = 8;
-constexpr uint32_t kRingOffset = 256;  // the mbarriers (2 * kMaxSlots + 4) sit in front of the ring
+constexpr int kBarStride = 8;           // mbarriers are spaced 64 bytes apart (uint64 units)
+constexpr uint32_t kRingOffset = (2 * kMaxSlots + 4) * kBarStride * 8;  // the mbarriers sit in front of the ring
 }  // namespace
 
 struct ThinParams {
@@ -272,9 +273,10 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
   const uint32_t abuf_s = base_s + p.off_abuf;
   const uint32_t sbc_s = base_s + p.off_sbc;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-  uint64_t* empty = full + kMaxSlots;
-  uint64_t* a_full = empty + kMaxSlots;
-  uint64_t* a_empty = a_full + 2;
+  // one mbarrier per 64 bytes
+  uint64_t* empty = full + kMaxSlots * kBarStride;
+  uint64_t* a_full = empty + kMaxSlots * kBarStride;
+  uint64_t* a_empty = a_full + 2 * kBarStride;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -288,12 +290,12 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.S; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kComputeWarps * 32);
+      mbar_init(&full[kBarStride * (s)], 1);
+      mbar_init(&empty[kBarStride * (s)], kComputeWarps * 32);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&a_full[b], p.a_warps * 32);
-      mbar_init(&a_empty[b], (kComputeWarps - p.a_warps) * 32);
+      mbar_init(&a_full[kBarStride * (b)], p.a_warps * 32);
+      mbar_init(&a_empty[kBarStride * (b)], (kComputeWarps - p.a_warps) * 32);
     }
     fence_mbar_init();
   }
@@ -355,10 +357,10 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
         const uint32_t bytes = (uint32_t)(row_hi - row_lo) * p.row_bytes;
         const uint32_t dst_off = (uint32_t)(row_lo - (wk.r0 - 1)) * p.row_bytes;
         for (int f = wk.f_lo; f <= wk.f_hi; ++f) {
-          if (round > 0) t_mbar_wait(&empty[slot], (round - 1) & 1);
+          if (round > 0) t_mbar_wait(&empty[kBarStride * (slot)], (round - 1) & 1);
           const uint8_t* src = p.x + (((long long)wk.n * p.T + f) * p.H + row_lo) * (long long)p.row_bytes;
-          mbar_expect_tx(&full[slot], bytes);
-          bulk_g2s(ring_s + slot * p.slot_bytes + dst_off, src, bytes, &full[slot]);
+          mbar_expect_tx(&full[kBarStride * (slot)], bytes);
+          bulk_g2s(ring_s + slot * p.slot_bytes + dst_off, src, bytes, &full[kBarStride * (slot)]);
           if (++slot == (uint32_t)p.S) {
             slot = 0;
             ++round;
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
       pos.set(wk.l0 + (uint32_t)(wk.t0 - wk.f_lo), S);
       for (int t = wk.t0; t < wk.t1; ++t, ++istep, pos.step(S)) {
         const uint32_t b = istep & 1;
-        if (istep >= 2) t_mbar_wait(&a_empty[b], ((istep >> 1) - 1) & 1);
+        if (istep >= 2) t_mbar_wait(&a_empty[kBarStride * (b)], ((istep >> 1) - 1) & 1);
         uint32_t slot_s[KT];
         bool have[KT];
 #pragma unroll
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
           slot_s[tap] = ring_s;
           if (have[tap]) {
             const RingPos rp = pos.at(tap - HT, S);
-            t_mbar_wait(&full[rp.slot], rp.round & 1);
+            t_mbar_wait(&full[kBarStride * (rp.slot)], rp.round & 1);
             slot_s[tap] = ring_s + rp.slot * p.slot_bytes + (PROJ ? 4 : 16) * t4;
           }
         }
@@ -493,13 +495,13 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
         // every lane arrives for its own shared-memory accesses (release / acquire per thread: nothing rests on
         // cumulativity through a warp barrier, and the race checker can follow it)
         {
-          mbar_arrive(&a_full[b]);
+          mbar_arrive(&a_full[kBarStride * (b)]);
           // frames conv a no longer needs
           const int f_done = t - HT;
-          if (f_done >= wk.f_lo) mbar_arrive(&empty[pos.at(-HT, S).slot]);
+          if (f_done >= wk.f_lo) mbar_arrive(&empty[kBarStride * (pos.at(-HT, S).slot)]);
           if (t == wk.t1 - 1)
             for (int f = (f_done + 1 > wk.f_lo ? f_done + 1 : wk.f_lo); f <= wk.f_hi; ++f)
-              mbar_arrive(&empty[pos.at(f - t, S).slot]);
+              mbar_arrive(&empty[kBarStride * (pos.at(f - t, S).slot)]);
         }
       }
       wk.next();
@@ -564,9 +566,9 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
       pos.set(wk.l0 + (uint32_t)(wk.t0 - wk.f_lo), S);
       for (int t = wk.t0; t < wk.t1; ++t, ++istep, pos.step(S)) {
         const uint32_t b = istep & 1;
-        t_mbar_wait(&a_full[b], (istep >> 1) & 1);
+        t_mbar_wait(&a_full[kBarStride * (b)], (istep >> 1) & 1);
         const uint32_t slot = pos.slot;
-        t_mbar_wait(&full[slot], pos.round & 1);
+        t_mbar_wait(&full[kBarStride * (slot)], pos.round & 1);
         const uint32_t xs = ring_s + slot * p.slot_bytes;
         const uint32_t src_s = abuf_s + b * p.a_buf_bytes;
         uint8_t* out_frame = p.out + (((long long)wk.n * p.T + t) * p.H + wk.r0) * (long long)p.W * p.out_pitch_bytes + 16 * t4;
@@ -656,13 +658,13 @@ __global__ void __launch_bounds__((compute_warps(D) + 1) * 32, 1) bottleneck_thi
           }
         }
         {
-          mbar_arrive(&a_empty[b]);
-          mbar_arrive(&empty[slot]);
+          mbar_arrive(&a_empty[kBarStride * (b)]);
+          mbar_arrive(&empty[kBarStride * (slot)]);
           // halo frames of the walk that no bc step visits
           if (t == wk.t0)
-            for (int f = wk.f_lo; f < wk.t0; ++f) mbar_arrive(&empty[pos.at(f - t, S).slot]);
+            for (int f = wk.f_lo; f < wk.t0; ++f) mbar_arrive(&empty[kBarStride * (pos.at(f - t, S).slot)]);
           if (t == wk.t1 - 1)
-            for (int f = wk.t1; f <= wk.f_hi; ++f) mbar_arrive(&empty[pos.at(f - t, S).slot]);
+            for (int f = wk.t1; f <= wk.f_hi; ++f) mbar_arrive(&empty[kBarStride * (pos.at(f - t, S).slot)]);
         }
       }
       wk.next();
