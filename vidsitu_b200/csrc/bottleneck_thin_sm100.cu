@@ -60,7 +60,10 @@ __host__ __device__ constexpr int default_a_warps(int) { return 7; }
 __host__ __device__ constexpr int max_a_tiles(int d) { return d == 8 ? 6 : 3; }
 __host__ __device__ constexpr int max_bc_tiles(int d) { return d == 8 ? 4 : 2; }
 constexpr int kMaxSlots = 8;
-constexpr int kBarStride = 8;           // mbarriers are spaced 64 bytes apart (uint64 units)
+// mbarriers are spaced 64 bytes apart (uint64 units): packed as adjacent 8-byte words, three frame barriers armed back
+// to back made compute-sanitizer report the first one as uninitialised (synccheck) and the ring fills as racing with
+// the slot's readers (racecheck); spaced, both tools are clean
+constexpr int kBarStride = 8;
 constexpr uint32_t kRingOffset = (2 * kMaxSlots + 4) * kBarStride * 8;  // the mbarriers sit in front of the ring
 }  // namespace
 
