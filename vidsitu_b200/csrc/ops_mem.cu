@@ -799,11 +799,18 @@ extern "C" int vsb_global_avgpool(const void* in, int n, int thw, int c, int in_
 // 765 MB for proj_head.0 at 64 clips); a warp owns 4 neurons, lanes stride over K with 128-bit loads
 // and keep 4 x LT_ROWS accumulators; a shuffle tree reduces them.  Summation order is fixed
 // (deterministic, batch-invariant: a row's result does not depend on the other rows).
+// The kernel is one block per SM and latency-bound (9 K chunks for proj_head.0, each a global load of x, a
+// barrier, a global load of w, 512 FMAs per thread): the next chunk's x and w are fetched into registers
+// while the current chunk is multiplied, and x is double-buffered in shared memory (one barrier per chunk:
+// a buffer is rewritten two chunks later, after every warp has passed the barrier in between).  The
+// accumulation order per (row, neuron) is unchanged, so results are bit-identical to the unpipelined form.
 constexpr int LT_ROWS = 16, LT_KC = 256;
+constexpr int LT_XV = LT_ROWS * (LT_KC / 4) / 256;   // float4 of the x chunk per thread
+constexpr int LT_H = LT_KC / 128;                    // float4 of a weight row per lane and chunk
 __global__ void __launch_bounds__(256)
 linear_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                     float* __restrict__ y, int n, int din, int dout, int relu) {
-  __shared__ float4 xs[LT_ROWS][LT_KC / 4];
+  __shared__ float4 xs[2][LT_ROWS][LT_KC / 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o0 = blockIdx.x * 32 + warp * 4;
   const int r0 = blockIdx.y * LT_ROWS;
@@ -812,34 +819,53 @@ linear_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w, co
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int r = 0; r < LT_ROWS; ++r) acc[j][r] = 0.f;
-  for (int kc = 0; kc < din; kc += LT_KC) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < LT_ROWS * (LT_KC / 4); i += 256) {
-      const int r = i / (LT_KC / 4), k4 = i - r * (LT_KC / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r0 + r < n && kc + k4 * 4 < din) v = *reinterpret_cast<const float4*>(x + (long long)(r0 + r) * din + kc + k4 * 4);
-      xs[r][k4] = v;
-    }
-    __syncthreads();
+  float4 xv_n[LT_XV], wv_n[LT_H][4];
+  auto fetch = [&](int kc) {
 #pragma unroll
-    for (int h = 0; h < LT_KC / 128; ++h) {
-      const int k4 = h * 32 + lane;
-      const int k = kc + k4 * 4;
-      float4 wv[4];
+    for (int q = 0; q < LT_XV; ++q) {
+      const int i = threadIdx.x + q * 256;
+      const int r = i / (LT_KC / 4), k4 = i - r * (LT_KC / 4);
+      xv_n[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < n && kc + k4 * 4 < din)
+        xv_n[q] = *reinterpret_cast<const float4*>(x + (long long)(r0 + r) * din + kc + k4 * 4);
+    }
+#pragma unroll
+    for (int h = 0; h < LT_H; ++h) {
+      const int k = kc + (h * 32 + lane) * 4;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        wv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o0 + j < dout && k < din) wv[j] = __ldg(reinterpret_cast<const float4*>(w + (long long)(o0 + j) * din + k));
+        wv_n[h][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o0 + j < dout && k < din) wv_n[h][j] = __ldg(reinterpret_cast<const float4*>(w + (long long)(o0 + j) * din + k));
       }
+    }
+  };
+  fetch(0);
+  int buf = 0;
+  for (int kc = 0; kc < din; kc += LT_KC, buf ^= 1) {
+    float4 wv[LT_H][4];
+#pragma unroll
+    for (int q = 0; q < LT_XV; ++q) {
+      const int i = threadIdx.x + q * 256;
+      xs[buf][i / (LT_KC / 4)][i % (LT_KC / 4)] = xv_n[q];
+    }
+#pragma unroll
+    for (int h = 0; h < LT_H; ++h)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[h][j] = wv_n[h][j];
+    __syncthreads();
+    if (kc + LT_KC < din) fetch(kc + LT_KC);
+#pragma unroll
+    for (int h = 0; h < LT_H; ++h) {
+      const int k4 = h * 32 + lane;
 #pragma unroll
       for (int r = 0; r < LT_ROWS; ++r) {
-        const float4 xv = xs[r][k4];
+        const float4 xv = xs[buf][r][k4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          acc[j][r] = fmaf(wv[j].x, xv.x, acc[j][r]);
-          acc[j][r] = fmaf(wv[j].y, xv.y, acc[j][r]);
-          acc[j][r] = fmaf(wv[j].z, xv.z, acc[j][r]);
-          acc[j][r] = fmaf(wv[j].w, xv.w, acc[j][r]);
+          acc[j][r] = fmaf(wv[h][j].x, xv.x, acc[j][r]);
+          acc[j][r] = fmaf(wv[h][j].y, xv.y, acc[j][r]);
+          acc[j][r] = fmaf(wv[h][j].z, xv.z, acc[j][r]);
+          acc[j][r] = fmaf(wv[h][j].w, xv.w, acc[j][r]);
         }
       }
     }

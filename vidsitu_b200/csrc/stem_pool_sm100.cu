@@ -474,13 +474,18 @@ stem5_pool_kernel(const __grid_constant__ CUtensorMap map_odd, const __grid_cons
   }
 }
 
-// zero the first `chunks` 16-byte chunks of every pixel of a [pixels, pitch_chunks * 16 B] tensor
-__global__ void zero_channels_kernel(uint4* out, long long pixels, int chunks, int pitch_chunks) {
+// Zero the first `chunks` 16-byte chunks of every SEAM pixel of the pooled [frames, ph, pw, pitch_chunks * 16 B] tensor:
+// the pooled pixels that epilogue_tile combines from two or four conv tiles with red.max (pooled row a multiple of 4
+// and >= 4, or pooled column a multiple of 8 and >= 8 - the same predicate as `seam` there).  Every other pixel is
+// written exactly once by a plain store, so it needs no initial value (a third of the tensor is zeroed, not all of it).
+__global__ void zero_seams_kernel(uint4* out, long long pixels, int ph, int pw, int chunks, int pitch_chunks) {
   const long long total = pixels * chunks;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long px = i / chunks;
     const int k = (int)(i - px * chunks);
-    out[px * pitch_chunks + k] = make_uint4(0, 0, 0, 0);
+    const long long row = px / pw;
+    const int qg = (int)(px - row * pw), pg = (int)(row % ph);
+    if ((pg >= 4 && (pg & 3) == 0) || (qg >= 8 && (qg & 7) == 0)) out[px * pitch_chunks + k] = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -579,8 +584,8 @@ extern "C" int vsb_stem_pool_run(const vsb_stem_pool_plan* plan, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const StemParams& p = plan->params;
   const long long pixels = (long long)p.frames * p.ph * p.pw;
-  zero_channels_kernel<<<1184, 256, 0, s>>>(reinterpret_cast<uint4*>(p.out), pixels, kCout / 8, p.out_pitch / 8);
-  VSB_CHECK_LAUNCH("zero_channels_kernel");
+  zero_seams_kernel<<<1184, 256, 0, s>>>(reinterpret_cast<uint4*>(p.out), pixels, p.ph, p.pw, kCout / 8, p.out_pitch / 8);
+  VSB_CHECK_LAUNCH("zero_seams_kernel");
   if (plan->desc.kt == 5)
     stem5_pool_kernel<<<plan->grid, kThreads5, kSmemBytes5, s>>>(plan->map_odd, plan->map_even, plan->map_w, p);
   else
