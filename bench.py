@@ -355,7 +355,7 @@ def main():
         step_tf = flops / (ms_step / 1e3) / 1e12
         traffic = traffic_all = None   # DRAM bytes of one step, from the committed ncu capture of this round
         tsrc = None
-        for cand in ("r02c_step_dram_traffic.json", "r02_step_dram_traffic.json", "r01_step_dram_traffic.json"):
+        for cand in ("r02d_step_dram_traffic.json", "r02c_step_dram_traffic.json", "r02_step_dram_traffic.json", "r01_step_dram_traffic.json"):
             tp = os.path.join(ROOT, "profiles", cand)
             if os.path.exists(tp) and B == 64 and args.model == MODEL:
                 ks = json.load(open(tp))["kernels"]

@@ -478,14 +478,22 @@ stem5_pool_kernel(const __grid_constant__ CUtensorMap map_odd, const __grid_cons
 // the pooled pixels that epilogue_tile combines from two or four conv tiles with red.max (pooled row a multiple of 4
 // and >= 4, or pooled column a multiple of 8 and >= 8 - the same predicate as `seam` there).  Every other pixel is
 // written exactly once by a plain store, so it needs no initial value (a third of the tensor is zeroed, not all of it).
-__global__ void zero_seams_kernel(uint4* out, long long pixels, int ph, int pw, int chunks, int pitch_chunks) {
-  const long long total = pixels * chunks;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long px = i / chunks;
-    const int k = (int)(i - px * chunks);
-    const long long row = px / pw;
-    const int qg = (int)(px - row * pw), pg = (int)(row % ph);
-    if ((pg >= 4 && (pg & 3) == 0) || (qg >= 8 && (qg & 7) == 0)) out[px * pitch_chunks + k] = make_uint4(0, 0, 0, 0);
+// One warp per pooled row (32-bit index arithmetic, one division per row): a seam row is zeroed whole, any other row
+// only at its seam columns.
+__global__ void zero_seams_kernel(uint4* out, long long rows, int ph, int pw, int pitch_chunks) {
+  constexpr int kChunks = kCout / 8;
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+    const int pg = (int)(row % ph);
+    uint4* base = out + row * pw * pitch_chunks;
+    if (pg >= 4 && (pg & 3) == 0) {
+      for (int i = lane; i < pw * kChunks; i += 32) base[(i / kChunks) * pitch_chunks + (i % kChunks)] = make_uint4(0, 0, 0, 0);
+    } else {
+      const int nseam = (pw - 1) >> 3;   // columns 8, 16, ... below pw
+      for (int i = lane; i < nseam * kChunks; i += 32)
+        base[((i / kChunks) + 1) * 8 * pitch_chunks + (i % kChunks)] = make_uint4(0, 0, 0, 0);
+    }
   }
 }
 
@@ -583,8 +591,7 @@ extern "C" int vsb_stem_pool_run(const vsb_stem_pool_plan* plan, void* stream) {
   VSB_CHECK_ARG(plan, "null plan");
   cudaStream_t s = (cudaStream_t)stream;
   const StemParams& p = plan->params;
-  const long long pixels = (long long)p.frames * p.ph * p.pw;
-  zero_seams_kernel<<<1184, 256, 0, s>>>(reinterpret_cast<uint4*>(p.out), pixels, p.ph, p.pw, kCout / 8, p.out_pitch / 8);
+  zero_seams_kernel<<<1184, 256, 0, s>>>(reinterpret_cast<uint4*>(p.out), (long long)p.frames * p.ph, p.ph, p.pw, p.out_pitch / 8);
   VSB_CHECK_LAUNCH("zero_seams_kernel");
   if (plan->desc.kt == 5)
     stem5_pool_kernel<<<plan->grid, kThreads5, kSmemBytes5, s>>>(plan->map_odd, plan->map_even, plan->map_w, p);
