@@ -481,6 +481,22 @@ def run_mem_checks():
     ref = torch.relu(x.double() @ wl.double().t() + bl.double()).float()
     err = float((y - ref).abs().max())
     res["linear_relu"] = {"ok": err < 1e-4, "max_abs_err": err}
+    # ragged shapes of the tiled kernel (din not a multiple of its 256-wide K chunk, one chunk only, rows / neurons that do
+    # not fill a block) and the warp-per-neuron kernel (din % 4 != 0); rows must not depend on their batch (bit-equal)
+    for n, din, dout, relu in ((33, 300, 37, False), (16, 256, 32, True), (1, 2048, 5, False), (5, 1028, 70, True),
+                               (7, 301, 9, False)):
+        x = torch.randn((n, din), generator=g).to(dev)
+        wl = (torch.randn((dout, din), generator=g) * 0.05).to(dev)
+        bl = torch.randn(dout, generator=g).to(dev)
+        y = torch.full((n, dout), 7.0, device=dev)
+        ops.linear(x, wl, bl, y, relu)
+        y1 = torch.full((1, dout), 7.0, device=dev)
+        ops.linear(x[n - 1:].clone(), wl, bl, y1, relu)
+        torch.cuda.synchronize()
+        ref = x.double() @ wl.double().t() + bl.double()
+        ref = (torch.relu(ref) if relu else ref).float()
+        err = float((y - ref).abs().max())
+        res[f"linear_n{n}_k{din}_o{dout}"] = {"ok": err < 1e-4 and bool(torch.equal(y[n - 1:], y1)), "max_abs_err": err}
     # ---- nthwc -> ncthw
     x = torch.randn((2, 2, 7, 7, 48), generator=g).to(torch.bfloat16).to(dev)
     got = ops.act_to_ncthw(Act(x, 2, 2, 7, 7, 48, 48), L.VSB_BF16)
