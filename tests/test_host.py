@@ -392,3 +392,37 @@ def test_pack_fma_coefficients_reproduce_the_three_fp32_operations(mean, std):
         # fma in float64 is exact for an 8-bit x times a 24-bit coefficient; one rounding to fp32, one to bf16
         got = (x.double() * float(a[c]) + float(b[c])).float()
         assert torch.equal(got.to(torch.bfloat16), want.to(torch.bfloat16)), c
+
+
+@pytest.mark.parametrize("ph,pw", [(56, 56), (24, 40), (8, 8), (16, 24), (64, 8)])   # crop / 4: multiples of 8
+def test_fused_stem_seam_zeroing_covers_exactly_the_red_max_pixels(ph, pw):
+    """stem_pool_sm100.cu: epilogue_tile writes a pooled pixel with a plain store when one 8 x 16 conv tile holds its whole
+    3x3/s2 window and with red.max when two or four tiles contribute (`seam`); zero_seams_kernel gives only the latter their
+    initial value.  Replay both index computations: every pooled pixel is either stored exactly once and never touched by
+    red.max, or zeroed and only ever combined by red.max (max-pool after ReLU, stem_helper.py:157-178: values >= 0)."""
+    tiles_h, tiles_w = ph // 4, pw // 8            # 8 x 16 conv tiles = 4 x 8 pooled pixels (+ the seam row / column)
+    stores = [[0] * pw for _ in range(ph)]
+    reds = [[0] * pw for _ in range(ph)]
+    for th in range(tiles_h):
+        for tw in range(tiles_w):
+            for pl in range(5):
+                for ql in range(9):
+                    pg, qg = th * 4 + pl, tw * 8 + ql
+                    if pg >= ph or qg >= pw:
+                        continue
+                    seam = (pl == 0 and th > 0) or pl == 4 or (ql == 0 and tw > 0) or ql == 8
+                    (reds if seam else stores)[pg][qg] += 1
+    nseam = (pw - 1) >> 3
+    zeroed = [[False] * pw for _ in range(ph)]
+    for pg in range(ph):                            # one warp per pooled row
+        if pg >= 4 and pg % 4 == 0:
+            zeroed[pg] = [True] * pw
+        else:
+            for s in range(nseam):
+                zeroed[pg][(s + 1) * 8] = True
+    for pg in range(ph):
+        for qg in range(pw):
+            if zeroed[pg][qg]:
+                assert stores[pg][qg] == 0 and reds[pg][qg] in (2, 4), (pg, qg)
+            else:
+                assert stores[pg][qg] == 1 and reds[pg][qg] == 0, (pg, qg)
